@@ -1,0 +1,301 @@
+"""Generate the golden vectors under tests/golden/ by running the REFERENCE's own code on CPU.
+
+Run in the authoring container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+Every fixture is a small .npz holding seeded inputs, the reference module's ``state_dict``
+(keys prefixed ``sd::``) and the reference outputs. The oracle (``oracle/``) is pinned against
+these files by ``tests/test_oracle_golden.py``; the CUDA path is checked against the same files
+by the ``-m gpu`` tests. The reference publishes no stored vectors of its own:
+the only known-answer recipe it has is ops/test.py (seed 3, shapes [(6,4),(3,2)]), replayed
+below as ``msdeform_core_testpy``.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_shim  # noqa: E402
+
+torch.set_num_threads(4)
+torch.backends.mkldnn.enabled = True
+
+
+def sd_arrays(module):
+    return {"sd::" + k: v.detach().cpu().numpy() for k, v in module.state_dict().items()}
+
+
+def save(name, **arrays):
+    out = {}
+    for k, v in arrays.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().cpu().numpy()
+        out[k] = v
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB, {len(out)} arrays")
+
+
+def gen_hypersphere_attention():
+    au = ref_shim.ref("modeling.transformer_decoder.attention_util")
+    torch.manual_seed(0)
+    BH, Q, S, E = 4, 10, 50, 8
+    q, k, v = torch.randn(BH, Q, E), torch.randn(BH, S, E), torch.randn(BH, S, E)
+    blocked = torch.rand(BH, Q, S) < 0.5
+    blocked[:, :, 0] = False  # no fully blocked row (the decoder guarantees this, decoder.py:618)
+    fmask = torch.zeros(BH, Q, S).masked_fill_(blocked, float("-inf"))
+    out_m, attn_m = au.hypersphere_attention(q, k, v, fmask)
+    out_n, attn_n = au.hypersphere_attention(q, k, v, None)
+    out_k, attn_k = au.hypersphere_attention(q, k, v, None, 0.0, 10.0)
+    save("hypersphere_attention", q=q, k=k, v=v, blocked=blocked, out_masked=out_m, attn_masked=attn_m,
+         out_nomask=out_n, attn_nomask=attn_n, out_kappa10=out_k, attn_kappa10=attn_k,
+         kappa_default=np.float32(au.KAPPA))
+
+
+def gen_meanshift_attention():
+    au = ref_shim.ref("modeling.transformer_decoder.attention_util")
+    torch.manual_seed(1)
+    E, H, L, S, N = 32, 2, 10, 50, 2
+    m = au.MeanShiftAttention(E, H).eval()
+    with torch.no_grad():
+        m.in_proj_bias.normal_(0, 0.1)
+        m.out_proj.bias.normal_(0, 0.1)
+    query, key, value = torch.randn(L, N, E), torch.randn(S, N, E), torch.randn(S, N, E)
+    blocked = torch.rand(N, 1, L, S) < 0.5
+    blocked[..., 3] = False
+    blocked = blocked.repeat(1, H, 1, 1).flatten(0, 1)
+    with torch.no_grad():
+        out, w = m(query, key, value, attn_mask=blocked)
+        out_self, w_self = m(query, query, query)
+    save("meanshift_attention", query=query, key=key, value=value, blocked=blocked, out=out, weights=w,
+         out_self=out_self, weights_self=w_self, num_heads=np.int64(H), **sd_arrays(m))
+
+
+def _decoder_kwargs():
+    return dict(num_classes=2, hidden_dim=32, num_queries=10, nheads=2, dim_feedforward=64, dec_layers=4,
+                pre_norm=False, mask_dim=32, enforce_input_project=False, use_meanshift_cross_attention=True,
+                disable_attention_mask=False, use_meanshift_self_attention=True, decoder_block_norm=True)
+
+
+def _randomise_biases(module, std=0.05):
+    # reference initialisers leave every bias at 0 / LayerNorm at (1, 0); perturb so that the
+    # fixtures exercise those terms too
+    with torch.no_grad():
+        for n, p in module.named_parameters():
+            if p.dim() == 1:
+                p.add_(torch.randn_like(p) * std)
+
+
+def _dump_decoder_out(o):
+    d = {"pred_logits": o["pred_logits"], "pred_masks": o["pred_masks"]}
+    for i, a in enumerate(o["aux_outputs"]):
+        d[f"aux{i}_pred_logits"] = a["pred_logits"]
+        d[f"aux{i}_pred_masks"] = a["pred_masks"]
+    return d
+
+
+def gen_decoder_multiscale():
+    dec = ref_shim.ref("modeling.transformer_decoder.meanshiftformer_transformer_decoder")
+    torch.manual_seed(2)
+    m = dec.MeanShiftTransformerDecoder(16, True, **_decoder_kwargs()).eval()
+    _randomise_biases(m)
+    x = [torch.randn(2, 16, 3, 4), torch.randn(2, 16, 6, 8), torch.randn(2, 16, 12, 16)]
+    mf = torch.randn(2, 32, 24, 32)
+    with torch.no_grad():
+        o = m(x, mf)
+    save("decoder_multiscale", x0=x[0], x1=x[1], x2=x[2], mask_features=mf, in_channels=np.int64(16),
+         **_dump_decoder_out(o), **sd_arrays(m))
+
+
+def gen_decoder_pretrained():
+    dec = ref_shim.ref("modeling.transformer_decoder.meanshiftformer_transformer_decoder")
+    torch.manual_seed(3)
+    kw = _decoder_kwargs()
+    kw["dec_layers"] = 3
+    m = dec.PretrainedMeanShiftTransformerDecoder(16, True, **kw).eval()
+    _randomise_biases(m)
+    x = [F.normalize(torch.randn(2, 16, 12, 20), dim=1)]
+    mf = torch.randn(2, 32, 12, 20)
+    with torch.no_grad():
+        o = m(x, mf)
+    save("decoder_pretrained", x0=x[0], mask_features=mf, in_channels=np.int64(16),
+         **_dump_decoder_out(o), **sd_arrays(m))
+
+
+def gen_posenc():
+    pe = ref_shim.ref("modeling.transformer_decoder.position_encoding")
+    x = torch.zeros(2, 3, 5, 7)
+    save("position_encoding", pos16=pe.PositionEmbeddingSine(16, normalize=True)(x),
+         pos128_15x20=pe.PositionEmbeddingSine(128, normalize=True)(torch.zeros(1, 1, 15, 20)),
+         shape=np.array([2, 3, 5, 7]))
+
+
+def gen_msdeform_core():
+    fn = ref_shim.ref("modeling.pixel_decoder.ops.functions.ms_deform_attn_func")
+    # --- ops/test.py:24-47 recipe (seed 3; generated on the CPU generator, the script uses .cuda()) ---
+    N, M, D = 1, 2, 2
+    Lq, L, P = 2, 2, 2
+    shapes = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.long)
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    S = int(shapes.prod(1).sum())
+    torch.manual_seed(3)
+    value = torch.rand(N, S, M, D) * 0.01
+    loc = torch.rand(N, Lq, M, L, P, 2)
+    w = torch.rand(N, Lq, M, L, P) + 1e-5
+    w /= w.sum(-1, keepdim=True).sum(-2, keepdim=True)
+    out64 = fn.ms_deform_attn_core_pytorch(value.double(), shapes, loc.double(), w.double())
+    out32 = fn.ms_deform_attn_core_pytorch(value, shapes, loc, w)
+    save("msdeform_core_testpy", value=value, spatial_shapes=shapes, level_start_index=lsi, sampling_locations=loc,
+         attention_weights=w, out_fp64=out64, out_fp32=out32)
+
+    # --- UOIS-like geometry: 8 heads x 8 channels, 3 levels x 4 points, locations spilling outside [0,1] ---
+    torch.manual_seed(4)
+    N, M, D, L, P = 2, 8, 8, 3, 4
+    shapes = torch.as_tensor([(3, 4), (6, 8), (12, 16)], dtype=torch.long)
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    S = int(shapes.prod(1).sum())
+    Lq = S
+    value = torch.randn(N, S, M, D)
+    loc = torch.rand(N, Lq, M, L, P, 2) * 1.4 - 0.2
+    w = torch.softmax(torch.randn(N, Lq, M, L * P), -1).view(N, Lq, M, L, P)
+    out32 = fn.ms_deform_attn_core_pytorch(value, shapes, loc, w)
+    out64 = fn.ms_deform_attn_core_pytorch(value.double(), shapes, loc.double(), w.double())
+    save("msdeform_core_uois", value=value, spatial_shapes=shapes, level_start_index=lsi, sampling_locations=loc,
+         attention_weights=w, out_fp32=out32, out_fp64=out64)
+
+
+def gen_msdeform_module():
+    mod = ref_shim.ref("modeling.pixel_decoder.ops.modules.ms_deform_attn")
+    torch.manual_seed(5)
+    m = mod.MSDeformAttn(d_model=32, n_levels=3, n_heads=4, n_points=4).eval()
+    with torch.no_grad():  # reference init zeroes these weights; make them matter
+        m.sampling_offsets.weight.normal_(0, 0.3)
+        m.attention_weights.weight.normal_(0, 0.5)
+        m.attention_weights.bias.normal_(0, 0.5)
+        m.value_proj.bias.normal_(0, 0.1)
+        m.output_proj.bias.normal_(0, 0.1)
+    shapes = torch.as_tensor([(2, 3), (4, 6), (8, 12)], dtype=torch.long)
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    S = int(shapes.prod(1).sum())
+    N = 2
+    query, src = torch.randn(N, S, 32), torch.randn(N, S, 32)
+    refp = torch.rand(N, S, 3, 2)
+    with torch.no_grad():
+        out = m(query, refp, src, shapes, lsi, None)
+    save("msdeform_module", query=query, input_flatten=src, reference_points=refp, spatial_shapes=shapes,
+         level_start_index=lsi, out=out, **sd_arrays(m))
+
+
+def _pixel_decoder(pd, ShapeSpec):
+    input_shape = {"res2": ShapeSpec(channels=8, stride=4), "res3": ShapeSpec(channels=16, stride=8),
+                   "res4": ShapeSpec(channels=32, stride=16), "res5": ShapeSpec(channels=64, stride=32)}
+    return pd.MSDeformAttnPixelDecoder(
+        input_shape, transformer_dropout=0.0, transformer_nheads=4, transformer_dim_feedforward=64,
+        transformer_enc_layers=2, conv_dim=32, mask_dim=32, norm="GN",
+        transformer_in_features=["res3", "res4", "res5"], common_stride=4)
+
+
+def _features(seed):
+    g = torch.Generator().manual_seed(seed)
+    return {"res2": torch.randn(2, 8, 16, 24, generator=g), "res3": torch.randn(2, 16, 8, 12, generator=g),
+            "res4": torch.randn(2, 32, 4, 6, generator=g), "res5": torch.randn(2, 64, 2, 3, generator=g)}
+
+
+def _perturb_msdeform(module):
+    mod = ref_shim.ref("modeling.pixel_decoder.ops.modules.ms_deform_attn")
+    with torch.no_grad():
+        for m in module.modules():
+            if isinstance(m, mod.MSDeformAttn):
+                m.sampling_offsets.weight.normal_(0, 0.2)
+                m.attention_weights.weight.normal_(0, 0.5)
+
+
+def gen_pixel_decoder_msdeform():
+    pd = ref_shim.ref("modeling.pixel_decoder.msdeformattn")
+    from detectron2.layers import ShapeSpec
+    torch.manual_seed(6)
+    m = _pixel_decoder(pd, ShapeSpec).eval()
+    _perturb_msdeform(m)
+    _randomise_biases(m)
+    feats = _features(60)
+    with torch.no_grad():
+        mask_features, enc0, ms = m.forward_features(feats)
+    save("pixel_decoder_msdeform", **{"in_" + k: v for k, v in feats.items()}, mask_features=mask_features,
+         encoder_first=enc0, ms0=ms[0], ms1=ms[1], ms2=ms[2], **sd_arrays(m))
+
+
+def gen_pixel_decoder_simple():
+    fpn = ref_shim.ref("modeling.pixel_decoder.fpn")
+    from detectron2.layers import ShapeSpec
+    torch.manual_seed(7)
+    m = fpn.SimpleBasePixelDecoder({"res5": ShapeSpec(channels=16, stride=1)}, conv_dim=16, mask_dim=32, norm="GN").eval()
+    _randomise_biases(m)
+    x = F.normalize(torch.randn(2, 16, 12, 16), dim=1)
+    with torch.no_grad():
+        mf, none, ms = m.forward_features({"res5": x})
+    assert none is None and len(ms) == 1 and ms[0] is x
+    save("pixel_decoder_simple", x=x, mask_features=mf, **sd_arrays(m))
+
+
+def gen_head_r50style():
+    """pixel decoder -> multi-scale decoder through the reference head class (meanshift_former_head.py:246-275)."""
+    pd = ref_shim.ref("modeling.pixel_decoder.msdeformattn")
+    dec = ref_shim.ref("modeling.transformer_decoder.meanshiftformer_transformer_decoder")
+    head = ref_shim.ref("modeling.meta_arch.meanshift_former_head")
+    from detectron2.layers import ShapeSpec
+    torch.manual_seed(8)
+    pixel = _pixel_decoder(pd, ShapeSpec)
+    _perturb_msdeform(pixel)
+    predictor = dec.MeanShiftTransformerDecoder(32, True, **_decoder_kwargs())
+    input_shape = {"res2": ShapeSpec(channels=8, stride=4), "res3": ShapeSpec(channels=16, stride=8),
+                   "res4": ShapeSpec(channels=32, stride=16), "res5": ShapeSpec(channels=64, stride=32)}
+    m = head.PretrainedMeanShiftMaskFormerHead(input_shape, num_classes=2, pixel_decoder=pixel, loss_weight=1.0,
+                                               ignore_value=255, transformer_predictor=predictor,
+                                               transformer_in_feature="multi_scale_pixel_decoder").eval()
+    _randomise_biases(m)
+    feats = _features(80)
+    with torch.no_grad():
+        o, last = m(feats, 64, 96)
+    save("head_r50style", **{"in_" + k: v for k, v in feats.items()}, last_feature_map=last,
+         **_dump_decoder_out(o), **sd_arrays(m))
+
+
+def gen_mean_shift():
+    ms = ref_shim.ref("modeling.transformer_decoder.mean_shift")
+    torch.manual_seed(9)
+    n, d, c = 600, 16, 5
+    centers = F.normalize(torch.randn(c, d), dim=1)
+    X = F.normalize(centers[torch.randint(0, c, (n,))] + 0.15 * torch.randn(n, d), dim=1)
+    idx = torch.randperm(n)[:12]
+    Z0 = X[idx].clone()
+    Z10 = ms.seed_hill_climbing_ball(X, Z0, kappa=10, max_iters=10)
+    Z20 = ms.seed_hill_climbing_ball(X, Z0, kappa=20, max_iters=4)
+    cc = ms.connected_components(Z10, 0.04)
+    labels_ws, Z_ws = ms.mean_shift_with_seeds(X, Z0, 10, max_iters=10)
+    np.random.seed(3)  # lib/fcn/config.py:380 RNG_SEED
+    seeds, sel = ms.select_smart_seeds(X, 12, return_selected_indices=True)
+    np.random.seed(3)
+    labels, sel2 = ms.mean_shift_smart_init(X, kappa=20, num_seeds=12, max_iters=10)
+    assert torch.equal(sel, sel2)
+    save("mean_shift", X=X, seed_indices=idx, Z0=Z0, Z_kappa10_it10=Z10, Z_kappa20_it4=Z20, cc_labels=cc,
+         ws_labels=labels_ws, ws_Z=Z_ws, smart_seeds=seeds, smart_indices=sel, smart_init_labels=labels,
+         first_seed_index=np.int64(sel[0].item()))
+
+
+if __name__ == "__main__":
+    gen_hypersphere_attention()
+    gen_meanshift_attention()
+    gen_decoder_multiscale()
+    gen_decoder_pretrained()
+    gen_posenc()
+    gen_msdeform_core()
+    gen_msdeform_module()
+    gen_pixel_decoder_msdeform()
+    gen_pixel_decoder_simple()
+    gen_head_r50style()
+    gen_mean_shift()
