@@ -1,0 +1,135 @@
+/*
+ * msmformer_b200.h - C ABI of libmsmformer_b200.so, the sm_100a implementation of the MSMFormer
+ * segmentation hot path (reference: YoungSean/UnseenObjectsWithMeanShift @ d1c8487).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 data unless its name ends in _host; tensors are
+ *     dense row-major with the innermost (channel) axis contiguous; sizes/strides are in ELEMENTS;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); all work is
+ *     enqueued on it, nothing synchronises, so the calls can be captured in a CUDA graph;
+ *   - return value 0 = success; <0 = bad argument (MSM_E_*); >0 = cudaError_t of a failed launch.
+ *     msm_last_error() returns a static, thread-local description of the last non-zero return;
+ *   - `workspace` buffers are caller-owned scratch; query the size with the matching *_workspace_bytes.
+ *
+ * Reference paths below are relative to MSMFormer/meanshiftformer/modeling/ in the reference.
+ */
+#ifndef MSMFORMER_B200_H_
+#define MSMFORMER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSM_E_BADARG (-1)
+#define MSM_E_UNSUPPORTED (-2)
+#define MSM_E_WORKSPACE (-3)
+
+#define MSM_ABI_VERSION 1
+
+int msm_abi_version(void);
+const char* msm_last_error(void);
+/* compute capability major*10+minor of the current device (100 on B200), <0 on error */
+int msm_device_arch(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * vMF ("hypersphere") attention core.
+ * Replaces hypersphere_attention(q, k, v, attn_mask, dropout_p, kappa),
+ *   transformer_decoder/attention_util.py:30-82:
+ *     out = unit( softmax_s( kappa * unit(q).unit(k_s) + mask ) . v )
+ * for G = batch*heads independent problems of Nq queries x Ns keys x hd channels.
+ *
+ * Element (b, h, i, d) of q lives at  q[b*q_sb + h*q_sh + i*q_sl + d]  (same scheme for k, v, out),
+ * so both the reference's seq-first [L, N, E] projections and batch-first [N, L, E] buffers are
+ * addressed without a transpose.
+ *
+ * Mask, exactly one of (all may be NULL = no mask):
+ *   blocked_bits  packed bits [batch][Nq][words_per_row], bit (s & 31) of word (s >> 5) set = key s
+ *                 may NOT be attended (the bool attn_mask of meanshiftformer_transformer_decoder.py:675-680,
+ *                 stored once for all heads). row_open [batch][Nq] (int32, may be NULL): 0 = this row
+ *                 blocks every key and is therefore treated as un-masked (decoder.py:618).
+ *   add_mask      fp32 additive mask [G][Nq][Ns] (0 / -inf) as hypersphere_attention receives it.
+ * flags: bit0 = L2-normalise q rows (eps 1e-12), bit1 = L2-normalise k rows. The reference attention
+ *        uses both; the mean-shift update (mean_shift.py:90-109) uses neither.
+ * den (may be NULL): [G][Nq] softmax denominators sum_s exp(kappa*(cos-1))*open, for msm_vmf_attention_weights.
+ * ---------------------------------------------------------------------------------------------- */
+#define MSM_VMF_NORMALIZE_Q 1
+#define MSM_VMF_NORMALIZE_K 2
+
+size_t msm_vmf_attention_workspace_bytes(int batch, int heads, int Nq, int Ns, int hd);
+
+int msm_vmf_attention_fwd(const float* q, int64_t q_sb, int64_t q_sh, int64_t q_sl,
+                          const float* k, int64_t k_sb, int64_t k_sh, int64_t k_sl,
+                          const float* v, int64_t v_sb, int64_t v_sh, int64_t v_sl,
+                          float* out, int64_t o_sb, int64_t o_sh, int64_t o_sl,
+                          float* den,
+                          const uint32_t* blocked_bits, int words_per_row, const int32_t* row_open,
+                          const float* add_mask,
+                          int batch, int heads, int Nq, int Ns, int hd, float kappa, int flags,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* attention weights [G][Nq][Ns] (second return value of hypersphere_attention, attention_util.py:75).
+ * Needs `den` from msm_vmf_attention_fwd. Not on the hot path: the decoder layers discard it. */
+int msm_vmf_attention_weights(const float* q, int64_t q_sb, int64_t q_sh, int64_t q_sl,
+                              const float* k, int64_t k_sb, int64_t k_sh, int64_t k_sl,
+                              const float* den,
+                              const uint32_t* blocked_bits, int words_per_row, const int32_t* row_open,
+                              const float* add_mask, float* attn,
+                              int batch, int heads, int Nq, int Ns, int hd, float kappa, int flags, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Mask head.
+ * msm_mask_logits replaces  torch.einsum("bqc,bchw->bqhw", mask_embed, mask_features)
+ *   (meanshiftformer_transformer_decoder.py:668 / :1020):
+ *   masks[b][q][p] = sum_c embed[b][q][c] * feat[b][c][p],   p in [0, HW).
+ * msm_mask_to_attn_bits replaces  F.interpolate(masks, size, "bilinear", align_corners=False)
+ *   .sigmoid() ... < 0.5  (decoder.py:675-680) and the un-mask rule of decoder.py:618:
+ *   writes bits [B][Q][ceil(Ht*Wt/32)] (1 = blocked) and row_open [B][Q] (1 = some key open).
+ * ---------------------------------------------------------------------------------------------- */
+int msm_mask_logits(const float* embed, const float* feat, float* masks,
+                    int B, int Q, int C, int64_t HW, void* stream);
+
+int msm_mask_to_attn_bits(const float* masks, uint32_t* bits, int32_t* row_open,
+                          int B, int Q, int H, int W, int Ht, int Wt, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-scale deformable attention, forward.
+ * Replaces MultiScaleDeformableAttention.ms_deform_attn_forward(value, spatial_shapes,
+ *   level_start_index, sampling_loc, attn_weight, im2col_step)
+ *   (pixel_decoder/ops/src/vision.cpp:18-21, ms_deform_attn.h:25-45, cuda/ms_deform_attn_cuda.cu:25-85,
+ *    kernel cuda/ms_deform_im2col_cuda.cuh:242-304).
+ * value [N][S][M][D]; spatial_shapes int64 [L][2] (H,W) and level_start_index int64 [L] on the DEVICE,
+ * as the reference passes them; sampling_loc [N][Lq][M][L][P][2] (x,y in [0,1]); attn_weight
+ * [N][Lq][M][L][P]; out [N][Lq][M*D]. im2col_step only chunks the batch in the reference and has no
+ * numerical effect; it is accepted and ignored.
+ * ---------------------------------------------------------------------------------------------- */
+int msm_ms_deform_attn_fwd(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                           const float* sampling_loc, const float* attn_weight, float* out,
+                           int N, int S, int M, int D, int L, int Lq, int P, int im2col_step, void* stream);
+
+/* backward of the above (ms_deform_attn.h:47-67, cuda/ms_deform_attn_cuda.cu:88-158): grads are
+ * ACCUMULATED into grad_value (caller zero-fills), grad_sampling_loc and grad_attn_weight are written. */
+int msm_ms_deform_attn_bwd(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                           const float* sampling_loc, const float* attn_weight, const float* grad_out,
+                           float* grad_value, float* grad_sampling_loc, float* grad_attn_weight,
+                           int N, int S, int M, int D, int L, int Lq, int P, int im2col_step, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * vMF mean-shift hill climbing.
+ * Replaces seed_hill_climbing_ball(X, Z, kappa, max_iters, metric='cosine'),
+ *   transformer_decoder/mean_shift.py:79-109 (= lib/utils/mean_shift.py:79-109), batched over images:
+ *   repeat max_iters times:  Z <- unit( exp(kappa * Z X^T) X ).
+ * X [B][n][d] unit rows, Z0 [B][m][d], Z_out [B][m][d] (may alias Z0).
+ * ---------------------------------------------------------------------------------------------- */
+size_t msm_mean_shift_workspace_bytes(int B, int n, int m, int d);
+
+int msm_mean_shift_hill_climb(const float* X, const float* Z0, float* Z_out,
+                              int B, int n, int m, int d, float kappa, int max_iters,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSMFORMER_B200_H_ */

@@ -1,0 +1,408 @@
+"""Parity of the CUDA path (called through the C ABI, libmsmformer_b200.so) against the CPU
+oracle and against the golden vectors produced by the reference's own code.
+
+Tolerances (BASELINE.json north_star: 1e-3 relative fp32 on mask logits, bit-exact labels where
+the domain allows): stated per test. Errors relative to the tensor's peak magnitude are used for
+logits (an element-wise relative error is meaningless at zero crossings).
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import decoder as odec
+from oracle import mean_shift as oms
+from oracle import pixel_decoder as opd
+from oracle import vmf_attention as ovmf
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def msm():
+    import unseenobjectswithmeanshift_b200 as pkg
+    from unseenobjectswithmeanshift_b200 import _lib, ops
+    from unseenobjectswithmeanshift_b200.meanshiftformer import modeling
+    assert _lib.lib().msm_device_arch() >= 100, "these kernels are built for sm_100a only"
+
+    class NS:
+        pass
+    ns = NS()
+    ns.ops, ns.modeling, ns.pkg = ops, modeling, pkg
+    return ns
+
+
+def peak_rel(a, b):
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+def _additive(blocked):
+    return torch.zeros(blocked.shape).masked_fill_(blocked, float("-inf"))
+
+
+# ----------------------------------------------------------------------------- vMF attention
+def test_hypersphere_attention_golden(msm, golden):
+    from unseenobjectswithmeanshift_b200.meanshiftformer.modeling.transformer_decoder.attention_util import (
+        KAPPA, hypersphere_attention)
+    g, _ = golden("hypersphere_attention")
+    assert KAPPA == 30
+    q, k, v = g["q"].cuda(), g["k"].cuda(), g["v"].cuda()
+    with torch.no_grad():
+        out, attn = hypersphere_attention(q, k, v, _additive(g["blocked"]).cuda())
+        torch.testing.assert_close(out.cpu(), g["out_masked"], rtol=1e-4, atol=2e-6)
+        torch.testing.assert_close(attn.cpu(), g["attn_masked"], rtol=1e-4, atol=1e-7)
+        out, attn = hypersphere_attention(q, k, v)
+        torch.testing.assert_close(out.cpu(), g["out_nomask"], rtol=1e-4, atol=2e-6)
+        torch.testing.assert_close(attn.cpu(), g["attn_nomask"], rtol=1e-4, atol=1e-7)
+        out, attn = hypersphere_attention(q, k, v, None, 0.0, 10.0)
+        torch.testing.assert_close(out.cpu(), g["out_kappa10"], rtol=1e-4, atol=2e-6)
+        torch.testing.assert_close(attn.cpu(), g["attn_kappa10"], rtol=1e-4, atol=1e-7)
+        # bool mask is accepted like the float one
+        out_b, _ = hypersphere_attention(q, k, v, g["blocked"].cuda(), need_weights=False)
+        torch.testing.assert_close(out_b.cpu(), g["out_masked"], rtol=1e-4, atol=2e-6)
+
+
+def _pack_bits(blocked_bqs):
+    B, Q, S = blocked_bqs.shape
+    words = (S + 31) // 32
+    pad = torch.zeros(B, Q, words * 32, dtype=torch.int64)
+    pad[..., :S] = blocked_bqs.long()
+    w = (pad.view(B, Q, words, 32) << torch.arange(32)).sum(-1)
+    w = torch.where(w >= 2 ** 31, w - 2 ** 32, w)
+    return w.to(torch.int32)
+
+
+@pytest.mark.parametrize("B,H,Q,S,hd", [(2, 8, 100, 1200, 32), (1, 2, 10, 77, 16), (1, 1, 150, 300, 64),
+                                        (2, 3, 5, 1, 8), (1, 2, 33, 130, 12), (1, 1, 7, 500, 128)])
+def test_vmf_attention_bits_vs_oracle(msm, B, H, Q, S, hd):
+    """packed-bit mask path incl. fully-blocked rows, key tails, >128 queries, odd head sizes."""
+    g = torch.Generator().manual_seed(B * 1000 + S)
+    C = H * hd
+    q, k, v = (torch.randn(B, n, C, generator=g) for n in (Q, S, S))
+    blocked = torch.rand(B, Q, S, generator=g) < 0.6
+    blocked[:, 0, :] = True  # a row that blocks everything -> reference un-masks it (decoder.py:618)
+    row_open = (~blocked).any(-1).to(torch.int32)
+    eff = blocked & (row_open != 0).unsqueeze(-1)
+    # oracle on [B*H, L, hd]
+    def split(t, n):
+        return t.view(B, n, H, hd).permute(0, 2, 1, 3).reshape(B * H, n, hd)
+    ref, _ = ovmf.hypersphere_attention(split(q, Q), split(k, S), split(v, S),
+                                        _additive(eff.unsqueeze(1).repeat(1, H, 1, 1).flatten(0, 1)))
+    ref = ref.view(B, H, Q, hd).permute(0, 2, 1, 3).reshape(B, Q, C)
+
+    def hv(t):
+        return t.cuda().unflatten(-1, (H, hd)).permute(0, 2, 1, 3)
+    with torch.no_grad():
+        out = msm.ops.vmf_attention(hv(q), hv(k), hv(v), blocked_bits=_pack_bits(blocked).cuda(),
+                                    row_open=row_open.cuda())
+    got = out.permute(0, 2, 1, 3).reshape(B, Q, C).cpu()
+    assert (got - ref).abs().max().item() < 2e-5  # unit vectors: absolute == relative-to-peak
+    torch.testing.assert_close(got.view(B, Q, H, hd).norm(dim=-1), torch.ones(B, Q, H), rtol=0, atol=1e-5)
+    # unpack helper reproduces the reference's bool mask after the un-mask rule
+    un = msm.ops.unpack_attn_bits(_pack_bits(blocked).cuda(), row_open.cuda(), S, H).cpu()
+    assert torch.equal(un, eff.unsqueeze(1).repeat(1, H, 1, 1).flatten(0, 1))
+
+
+def test_vmf_attention_config2_full_size(msm):
+    """BASELINE config #2 cross-attention shape: B=8, 8 heads, 100 queries, 4800 keys, hd 32."""
+    g = torch.Generator().manual_seed(7)
+    B, H, Q, S, hd = 8, 8, 100, 4800, 32
+    q, k, v = (torch.randn(B, n, H * hd, generator=g) for n in (Q, S, S))
+    def split(t, n):
+        return t.view(B, n, H, hd).permute(0, 2, 1, 3).reshape(B * H, n, hd)
+    ref, _ = ovmf.hypersphere_attention(split(q, Q), split(k, S), split(v, S))
+    def hv(t):
+        return t.cuda().unflatten(-1, (H, hd)).permute(0, 2, 1, 3)
+    with torch.no_grad():
+        out = msm.ops.vmf_attention(hv(q), hv(k), hv(v))
+    got = out.reshape(B * H, Q, hd).cpu()
+    assert (got - ref).abs().max().item() < 2e-5
+
+
+def test_meanshift_attention_module_golden(msm, golden):
+    from unseenobjectswithmeanshift_b200.meanshiftformer.modeling.transformer_decoder.attention_util import (
+        MeanShiftAttention)
+    g, sd = golden("meanshift_attention")
+    m = MeanShiftAttention(32, int(g["num_heads"]))
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        out, w = m(g["query"].cuda(), g["key"].cuda(), g["value"].cuda(), attn_mask=g["blocked"].cuda())
+        torch.testing.assert_close(out.cpu(), g["out"], rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(w.cpu(), g["weights"], rtol=1e-4, atol=1e-7)
+        q = g["query"].cuda()
+        out, w = m(q, q, q)
+        torch.testing.assert_close(out.cpu(), g["out_self"], rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(w.cpu(), g["weights_self"], rtol=1e-4, atol=1e-7)
+
+
+# ----------------------------------------------------------------------------- mask head
+@pytest.mark.parametrize("B,Q,C,H,W", [(2, 100, 256, 120, 160), (1, 10, 32, 24, 32), (1, 130, 20, 5, 7),
+                                       (1, 100, 256, 224, 224)])
+def test_mask_logits_vs_einsum(msm, B, Q, C, H, W):
+    g = torch.Generator().manual_seed(Q + C)
+    e, f = torch.randn(B, Q, C, generator=g), torch.randn(B, C, H, W, generator=g)
+    ref = torch.einsum("bqc,bchw->bqhw", e, f)
+    with torch.no_grad():
+        got = msm.ops.mask_logits(e.cuda(), f.cuda()).cpu()
+    assert peak_rel(got, ref) < 1e-5  # fp32 products, only the summation order differs
+
+
+@pytest.mark.parametrize("src,dst", [((120, 160), (15, 20)), ((120, 160), (30, 40)), ((120, 160), (60, 80)),
+                                     ((48, 64), (48, 64)), ((24, 32), (5, 7)), ((9, 11), (20, 30))])
+def test_mask_to_attn_bits_vs_oracle(msm, src, dst):
+    """Same logits in, reference expression out (interpolate -> sigmoid -> < 0.5): bit-exact
+    for integer-ratio and identity resampling; general ratios may differ on exact ties only."""
+    g = torch.Generator().manual_seed(src[0] * dst[1])
+    B, Q, heads = 2, 17, 2
+    masks = torch.randn(B, Q, *src, generator=g)
+    masks[0, 3] = -5.0  # a row that blocks every key
+    masks[1, 2, :4, :4] = -3e-8  # sigmoid rounds to 0.5 -> NOT blocked, although the logit is negative
+    up = F.interpolate(masks, size=dst, mode="bilinear", align_corners=False)
+    ref = (up.sigmoid().flatten(2) < 0.5)
+    with torch.no_grad():
+        bits, row_open = msm.ops.mask_to_attn_bits(masks.cuda(), dst)
+        got = msm.ops.unpack_attn_bits(bits, torch.ones_like(row_open), dst[0] * dst[1], 1).cpu()
+    mism = (got != ref).float().mean().item()
+    assert mism <= 1e-5, mism
+    assert torch.equal(row_open.cpu() != 0, (~ref).any(-1))
+    assert row_open[0, 3].item() == 0
+
+
+# ----------------------------------------------------------------------------- decoders
+def _decoder_kwargs(layers):
+    return dict(num_classes=2, hidden_dim=32, num_queries=10, nheads=2, dim_feedforward=64, dec_layers=layers,
+                pre_norm=False, mask_dim=32, enforce_input_project=False, use_meanshift_cross_attention=True,
+                disable_attention_mask=False, use_meanshift_self_attention=True, decoder_block_norm=True)
+
+
+def _check_decoder(out, g, n_aux, tol=1e-3):
+    assert peak_rel(out["pred_logits"].cpu(), g["pred_logits"]) < tol
+    assert peak_rel(out["pred_masks"].cpu(), g["pred_masks"]) < tol
+    assert len(out["aux_outputs"]) == n_aux
+    for i, a in enumerate(out["aux_outputs"]):
+        assert peak_rel(a["pred_logits"].cpu(), g[f"aux{i}_pred_logits"]) < tol
+        assert peak_rel(a["pred_masks"].cpu(), g[f"aux{i}_pred_masks"]) < tol
+    # instance labels: per-pixel argmax over queries, bit-exact
+    assert torch.equal(out["pred_masks"].cpu().argmax(1), g["pred_masks"].argmax(1))
+
+
+def test_decoder_multiscale_golden(msm, golden):
+    g, sd = golden("decoder_multiscale")
+    m = msm.modeling.MeanShiftTransformerDecoder(16, True, **_decoder_kwargs(4))
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        out = m([g["x0"].cuda(), g["x1"].cuda(), g["x2"].cuda()], g["mask_features"].cuda())
+    _check_decoder(out, g, 4)
+
+
+def test_decoder_pretrained_golden(msm, golden):
+    g, sd = golden("decoder_pretrained")
+    m = msm.modeling.PretrainedMeanShiftTransformerDecoder(16, True, **_decoder_kwargs(3))
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        out = m([g["x0"].cuda()], g["mask_features"].cuda())
+    _check_decoder(out, g, 3)
+        
+
+def test_decoder_reference_style_heads(msm, golden):
+    """forward_prediction_heads keeps the reference's seq-first signature and bool mask."""
+    g, sd = golden("decoder_pretrained")
+    m = msm.modeling.PretrainedMeanShiftTransformerDecoder(16, True, **_decoder_kwargs(3))
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    out0 = sd["query_feat.weight"].unsqueeze(1).repeat(1, 2, 1)
+    with torch.no_grad():
+        cls, masks, attn = m.forward_prediction_heads(out0.cuda(), g["mask_features"].cuda(), (12, 20))
+    rc, rm, rb = odec.prediction_heads(sd, out0, g["mask_features"], (12, 20), 2)
+    assert peak_rel(masks.cpu(), rm) < 1e-5 and peak_rel(cls.cpu(), rc) < 1e-5
+    assert attn.shape == rb.shape and attn.dtype == torch.bool
+    assert (attn.cpu() != rb).float().mean().item() < 1e-3
+
+
+# ----------------------------------------------------------------------------- deformable attention
+def test_msdeform_known_answer_testpy(msm, golden):
+    """The reference's own recipe (pixel_decoder/ops/test.py:24-63), fp32 leg and its tolerance."""
+    g, _ = golden("msdeform_core_testpy")
+    with torch.no_grad():
+        out = msm.ops.ms_deform_attn_forward(g["value"].cuda(), g["spatial_shapes"].cuda(),
+                                             g["level_start_index"].cuda(), g["sampling_locations"].cuda(),
+                                             g["attention_weights"].cuda(), 2).cpu()
+    assert torch.allclose(out, g["out_fp32"], rtol=1e-2, atol=1e-3)  # test.py:59
+    assert torch.allclose(out, g["out_fp64"].float(), rtol=1e-4, atol=1e-7)
+
+
+def test_msdeform_uois_geometry(msm, golden):
+    g, _ = golden("msdeform_core_uois")
+    with torch.no_grad():
+        out = msm.ops.ms_deform_attn_forward(g["value"].cuda(), g["spatial_shapes"].cuda(),
+                                             g["level_start_index"].cuda(), g["sampling_locations"].cuda(),
+                                             g["attention_weights"].cuda()).cpu()
+    assert peak_rel(out, g["out_fp64"].float()) < 1e-5
+
+
+@pytest.mark.parametrize("M,D", [(2, 2), (8, 8), (3, 5), (4, 16), (1, 71)])
+def test_msdeform_forward_backward_vs_oracle(msm, M, D):
+    from unseenobjectswithmeanshift_b200.meanshiftformer.modeling.pixel_decoder.ops.functions import (
+        MSDeformAttnFunction)
+    g = torch.Generator().manual_seed(M * 100 + D)
+    N, Lq, L, P = 2, 9, 2, 3
+    shapes = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.long)
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    S = int(shapes.prod(1).sum())
+    value = torch.randn(N, S, M, D, generator=g)
+    loc = torch.rand(N, Lq, M, L, P, 2, generator=g) * 1.3 - 0.15
+    w = torch.softmax(torch.randn(N, Lq, M, L * P, generator=g), -1).view(N, Lq, M, L, P)
+    gout = torch.randn(N, Lq, M * D, generator=g)
+    # oracle in fp64 with autograd
+    v64, l64, w64 = (t.double().requires_grad_(True) for t in (value, loc, w))
+    ref = opd.ms_deform_attn_core(v64, shapes, lsi, l64, w64)
+    ref.backward(gout.double())
+    vc, lc, wc = (t.cuda().requires_grad_(True) for t in (value, loc, w))
+    out = MSDeformAttnFunction.apply(vc, shapes.cuda(), lsi.cuda(), lc, wc, 128)
+    out.backward(gout.cuda())
+    assert peak_rel(out.detach().cpu(), ref.detach().float()) < 1e-5
+    assert peak_rel(vc.grad.cpu(), v64.grad.float()) < 1e-5
+    assert peak_rel(wc.grad.cpu(), w64.grad.float()) < 1e-5
+    assert peak_rel(lc.grad.cpu(), l64.grad.float()) < 1e-4
+
+
+def test_msdeform_module_golden(msm, golden):
+    from unseenobjectswithmeanshift_b200.meanshiftformer.modeling.pixel_decoder.ops.modules import MSDeformAttn
+    g, sd = golden("msdeform_module")
+    m = MSDeformAttn(d_model=32, n_levels=3, n_heads=4, n_points=4)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        out = m(g["query"].cuda(), g["reference_points"].cuda(), g["input_flatten"].cuda(),
+                g["spatial_shapes"].cuda(), g["level_start_index"].cuda(), None).cpu()
+    assert peak_rel(out, g["out"]) < 1e-5
+
+
+def _shapes():
+    from unseenobjectswithmeanshift_b200.d2compat import ShapeSpec
+    return {"res2": ShapeSpec(channels=8, stride=4), "res3": ShapeSpec(channels=16, stride=8),
+            "res4": ShapeSpec(channels=32, stride=16), "res5": ShapeSpec(channels=64, stride=32)}
+
+
+def _pixel_decoder(msm):
+    return msm.modeling.MSDeformAttnPixelDecoder(
+        _shapes(), transformer_dropout=0.0, transformer_nheads=4, transformer_dim_feedforward=64,
+        transformer_enc_layers=2, conv_dim=32, mask_dim=32, norm="GN",
+        transformer_in_features=["res3", "res4", "res5"], common_stride=4)
+
+
+def test_pixel_decoder_msdeform_golden(msm, golden):
+    g, sd = golden("pixel_decoder_msdeform")
+    m = _pixel_decoder(msm)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    feats = {k[3:]: v.cuda() for k, v in g.items() if k.startswith("in_")}
+    with torch.no_grad():
+        mf, first, ms = m.forward_features(feats)
+    assert peak_rel(mf.cpu(), g["mask_features"]) < 1e-4
+    assert peak_rel(first.cpu(), g["encoder_first"]) < 1e-4
+    for i in range(3):
+        assert peak_rel(ms[i].cpu(), g[f"ms{i}"]) < 1e-4
+
+
+def test_pixel_decoder_simple_golden(msm, golden):
+    from unseenobjectswithmeanshift_b200.d2compat import ShapeSpec
+    g, sd = golden("pixel_decoder_simple")
+    m = msm.modeling.SimpleBasePixelDecoder({"res5": ShapeSpec(channels=16, stride=1)}, conv_dim=16, mask_dim=32,
+                                            norm="GN")
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        mf, none, ms = m.forward_features({"res5": g["x"].cuda()})
+    assert none is None and len(ms) == 1
+    assert peak_rel(mf.cpu(), g["mask_features"]) < 1e-4
+
+
+def test_head_r50style_golden(msm, golden):
+    g, sd = golden("head_r50style")
+    head = msm.modeling.PretrainedMeanShiftMaskFormerHead(
+        _shapes(), num_classes=2, pixel_decoder=_pixel_decoder(msm), loss_weight=1.0, ignore_value=255,
+        transformer_predictor=msm.modeling.MeanShiftTransformerDecoder(32, True, **_decoder_kwargs(4)),
+        transformer_in_feature="multi_scale_pixel_decoder")
+    head.load_state_dict(sd, strict=True)
+    head = head.cuda().eval()
+    feats = {k[3:]: v.cuda() for k, v in g.items() if k.startswith("in_")}
+    with torch.no_grad():
+        out, last = head(feats, 64, 96)
+    assert peak_rel(last.cpu(), g["last_feature_map"]) < 1e-4
+    _check_decoder(out, g, 4)
+
+
+# ----------------------------------------------------------------------------- mean shift
+def test_mean_shift_golden(msm, golden):
+    from unseenobjectswithmeanshift_b200.meanshiftformer.modeling.transformer_decoder import mean_shift as ms
+    g, _ = golden("mean_shift")
+    X, Z0 = g["X"].cuda(), g["Z0"].cuda()
+    with torch.no_grad():
+        Z = ms.seed_hill_climbing_ball(X, Z0, 10, 10)
+        assert (Z.cpu() - g["Z_kappa10_it10"]).abs().max().item() < 1e-5
+        Z = ms.seed_hill_climbing_ball(X, Z0, 20, 4)
+        assert (Z.cpu() - g["Z_kappa20_it4"]).abs().max().item() < 1e-5
+        labels, Zw = ms.mean_shift_with_seeds(X, Z0, 10, 10)
+        assert torch.equal(labels, g["ws_labels"])
+        first = int(g["first_seed_index"])
+        seeds, idx = ms.select_smart_seeds(X, 12, return_selected_indices=True, first_index=first)
+        assert torch.equal(idx, g["smart_indices"])
+        labels, idx = ms.mean_shift_smart_init(X, 20, 12, 10, first_index=first)
+        assert torch.equal(idx, g["smart_indices"])
+        assert torch.equal(labels.cpu(), g["smart_init_labels"])  # instance labels: bit-exact
+        # batched form == per-image form
+        Xb = torch.stack([X, X.flip(0)])
+        Zb = torch.stack([Z0, Z0])
+        out = ms.seed_hill_climbing_ball(Xb, Zb, 10, 3)
+        torch.testing.assert_close(out[0], ms.seed_hill_climbing_ball(X, Z0, 10, 3), rtol=0, atol=0)
+
+
+def test_mean_shift_config4_size_properties(msm):
+    """BASELINE config #4 geometry for one image (n=307200, d=64, m=100, kappa=10, 10 iterations):
+    size-independent properties + the oracle on the same data (finishes in seconds on CPU)."""
+    g = torch.Generator().manual_seed(4)
+    n, d, m = 307200, 64, 100
+    X = F.normalize(torch.randn(n, d, generator=g), dim=1)
+    idx = torch.randperm(n, generator=g)[:m]
+    Z0 = X[idx].clone()
+    with torch.no_grad():
+        Z = msm.ops.mean_shift_hill_climb(X.cuda(), Z0.cuda(), 10.0, 10)
+        torch.testing.assert_close(Z.norm(dim=1).cpu(), torch.ones(m), rtol=0, atol=1e-5)  # unit rows
+        # duplicating the data set does not move the modes
+        Z2 = msm.ops.mean_shift_hill_climb(torch.cat([X, X]).cuda(), Z0.cuda(), 10.0, 10)
+        assert (Z2 - Z).abs().max().item() < 1e-5
+        # max_iters composes: 10 = 4 + 6
+        Za = msm.ops.mean_shift_hill_climb(X.cuda(), Z0.cuda(), 10.0, 4)
+        Zb = msm.ops.mean_shift_hill_climb(X.cuda(), Za, 10.0, 6)
+        torch.testing.assert_close(Zb, Z, rtol=0, atol=0)
+        # a data set made of one direction is a fixed point
+        u = F.normalize(torch.randn(1, d, generator=g), dim=1)
+        Zu = msm.ops.mean_shift_hill_climb(u.repeat(5000, 1).cuda(), Z0[:7].cuda(), 10.0, 2)
+        assert (Zu.cpu() - u).abs().max().item() < 1e-6
+    ref = oms.seed_hill_climbing_ball(X, Z0, 10.0, 10)
+    assert (Z.cpu() - ref).abs().max().item() < 1e-4
+
+
+# ----------------------------------------------------------------------------- error behaviour
+def test_errors_are_loud(msm):
+    ops = msm.ops
+    q = torch.randn(1, 1, 4, 8)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.vmf_attention(q, q, q)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        v = torch.randn(1, 6, 2, 4, device="cuda").transpose(1, 2)
+        ops.ms_deform_attn_forward(v, torch.tensor([[2, 3]], device="cuda"), torch.tensor([0], device="cuda"),
+                                   torch.rand(1, 2, 2, 1, 1, 2, device="cuda"), torch.rand(1, 2, 2, 1, 1, device="cuda"))
+    from unseenobjectswithmeanshift_b200._lib import MsmError, lib
+    with pytest.raises(MsmError, match="bad argument"):
+        big = torch.randn(1, 1, 4, 200, device="cuda")
+        ops.vmf_attention(big, big, big)
+    assert lib().msm_vmf_attention_fwd(None, 0, 0, 0, None, 0, 0, 0, None, 0, 0, 0, None, 0, 0, 0, None, None, 0,
+                                       None, None, 1, 1, 1, 1, 8, 30.0, 3, None, 0, None) == -1
+    qg = torch.randn(1, 1, 4, 8, device="cuda", requires_grad=True)
+    with pytest.raises(RuntimeError, match="forward-only"):
+        ops.vmf_attention(qg, qg, qg)

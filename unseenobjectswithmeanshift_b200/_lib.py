@@ -1,0 +1,60 @@
+"""ctypes binding of libmsmformer_b200.so (the C ABI in include/msmformer_b200.h).
+
+The library is loaded lazily and loudly: a missing .so is an ImportError telling the user to run
+``python __graft_entry__.py build`` - the package never falls back to PyTorch or CPU code.
+"""
+import ctypes
+import os
+from ctypes import c_float, c_int, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmsmformer_b200.so")
+
+_lib = None
+
+# name -> (restype, argtypes); kept in the order of include/msmformer_b200.h
+_P, _I, _L, _F, _Z = c_void_p, c_int, c_int64, c_float, c_size_t
+SIGNATURES = {
+    "msm_abi_version": (_I, []),
+    "msm_last_error": (ctypes.c_char_p, []),
+    "msm_device_arch": (_I, []),
+    "msm_vmf_attention_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
+    "msm_vmf_attention_fwd": (_I, [_P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _L, _L, _P,
+                                   _P, _I, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P, _Z, _P]),
+    "msm_vmf_attention_weights": (_I, [_P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _I, _P, _P, _P,
+                                       _I, _I, _I, _I, _I, _F, _I, _P]),
+    "msm_mask_logits": (_I, [_P, _P, _P, _I, _I, _I, _L, _P]),
+    "msm_mask_to_attn_bits": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "msm_ms_deform_attn_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "msm_ms_deform_attn_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "msm_mean_shift_workspace_bytes": (_Z, [_I, _I, _I, _I]),
+    "msm_mean_shift_hill_climb": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _I, _P, _Z, _P]),
+}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build the CUDA library first (python __graft_entry__.py build). "
+                "unseenobjectswithmeanshift_b200 has no PyTorch/CPU fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the ABI and the binding disagree
+            fn.restype = res
+            fn.argtypes = args
+        if handle.msm_abi_version() != 1:
+            raise ImportError(f"{LIB_PATH}: ABI version {handle.msm_abi_version()} != 1, rebuild")
+        _lib = handle
+    return _lib
+
+
+class MsmError(RuntimeError):
+    pass
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().msm_last_error().decode("utf-8", "replace")
+        raise MsmError(f"{what} failed (code {rc}): {msg}")

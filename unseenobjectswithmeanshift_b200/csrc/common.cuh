@@ -1,0 +1,52 @@
+// Shared helpers for libmsmformer_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/msmformer_b200.h"
+
+namespace msm {
+
+void set_error(const char* fmt, ...);
+
+inline int fail_arg(const char* what) {
+  set_error("bad argument: %s", what);
+  return MSM_E_BADARG;
+}
+
+#define MSM_REQUIRE(cond, what) \
+  do {                          \
+    if (!(cond)) return ::msm::fail_arg(what); \
+  } while (0)
+
+inline int check_launch(const char* kernel) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", kernel, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+#define MSM_CUDA(call)                                                      \
+  do {                                                                      \
+    cudaError_t e_ = (call);                                                \
+    if (e_ != cudaSuccess) {                                                \
+      ::msm::set_error("%s: %s", #call, cudaGetErrorString(e_));            \
+      return (int)e_;                                                       \
+    }                                                                       \
+  } while (0)
+
+int num_sms();
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+}  // namespace msm

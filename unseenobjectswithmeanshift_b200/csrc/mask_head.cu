@@ -1,0 +1,209 @@
+// Mask head: query x pixel-feature contraction and the next layer's attention mask.
+//
+//   msm_mask_logits        einsum("bqc,bchw->bqhw")            meanshiftformer_transformer_decoder.py:668 / :1020
+//   msm_mask_to_attn_bits  interpolate(bilinear) -> sigmoid -> < 0.5, packed to 1 bit per (query, key),
+//                          shared by all heads, plus the "row blocks everything" flag of decoder.py:618
+//                          (decoder.py:675-680)
+//
+// This file holds the fp32 CUDA-core GEMM (exact fp32 products); mask_head_tc.cu holds the
+// tcgen05 tile version used for the shapes it supports.
+#include "common.cuh"
+
+namespace msm {
+
+constexpr int BM = 128, BN = 64, BK = 16;
+constexpr int GEMM_THREADS = 256;
+
+// C[b] (M x N) = A[b] (M x K, row-major) * B[b] (K x N, row-major), fp32.
+__global__ void __launch_bounds__(GEMM_THREADS) mask_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
+                                                                float* __restrict__ C, int M, int K, int64_t N,
+                                                                bool n_vec) {
+  __shared__ __align__(16) float sA[2][BK][BM + 4];
+  __shared__ __align__(16) float sB[2][BK][BN];
+  const int tid = threadIdx.x;
+  const int ty = tid / 16, tx = tid % 16;
+  const int64_t n0 = (int64_t)blockIdx.x * BN;
+  const int m0 = blockIdx.y * BM;
+  const int b = blockIdx.z;
+  const float* Ab = A + (int64_t)b * M * K;
+  const float* Bb = Bm + (int64_t)b * K * N;
+  float* Cb = C + (int64_t)b * M * N;
+
+  // global -> register staging
+  float4 ra[2];
+  float4 rb;
+  const int a_row[2] = {tid / 4, tid / 4 + 64};
+  const int a_c4 = tid % 4;
+  const int b_row = tid / 16, b_c4 = tid % 16;
+  const bool k_vec = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(Ab) & 15) == 0);
+
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int m = m0 + a_row[h];
+      const int kk = k0 + a_c4 * 4;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < M) {
+        const float* p = Ab + (int64_t)m * K + kk;
+        if (k_vec && kk + 3 < K) {
+          x = __ldg(reinterpret_cast<const float4*>(p));
+        } else {
+          if (kk + 0 < K) x.x = __ldg(p + 0);
+          if (kk + 1 < K) x.y = __ldg(p + 1);
+          if (kk + 2 < K) x.z = __ldg(p + 2);
+          if (kk + 3 < K) x.w = __ldg(p + 3);
+        }
+      }
+      ra[h] = x;
+    }
+    {
+      const int kk = k0 + b_row;
+      const int64_t n = n0 + b_c4 * 4;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kk < K) {
+        const float* p = Bb + (int64_t)kk * N + n;
+        if (n_vec && n + 3 < N) {
+          x = __ldg(reinterpret_cast<const float4*>(p));
+        } else {
+          if (n + 0 < N) x.x = __ldg(p + 0);
+          if (n + 1 < N) x.y = __ldg(p + 1);
+          if (n + 2 < N) x.z = __ldg(p + 2);
+          if (n + 3 < N) x.w = __ldg(p + 3);
+        }
+      }
+      rb = x;
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      sA[buf][a_c4 * 4 + 0][a_row[h]] = ra[h].x;
+      sA[buf][a_c4 * 4 + 1][a_row[h]] = ra[h].y;
+      sA[buf][a_c4 * 4 + 2][a_row[h]] = ra[h].z;
+      sA[buf][a_c4 * 4 + 3][a_row[h]] = ra[h].w;
+    }
+    *reinterpret_cast<float4*>(&sB[buf][b_row][b_c4 * 4]) = rb;
+  };
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+
+  const int nk = (K + BK - 1) / BK;
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  for (int t = 0; t < nk; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < nk) load_tiles((t + 1) * BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&sA[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&sA[buf][kk][64 + ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&sB[buf][kk][tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i][0] = fmaf(av[i], bv.x, acc[i][0]);
+        acc[i][1] = fmaf(av[i], bv.y, acc[i][1]);
+        acc[i][2] = fmaf(av[i], bv.z, acc[i][2]);
+        acc[i][3] = fmaf(av[i], bv.w, acc[i][3]);
+      }
+    }
+    if (t + 1 < nk) {
+      store_tiles(buf ^ 1);
+      __syncthreads();
+    }
+  }
+  const int64_t n = n0 + tx * 4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= M) continue;
+    float* p = Cb + (int64_t)m * N + n;
+    if (n_vec && n + 3 < N) {
+      *reinterpret_cast<float4*>(p) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    } else {
+      if (n + 0 < N) p[0] = acc[i][0];
+      if (n + 1 < N) p[1] = acc[i][1];
+      if (n + 2 < N) p[2] = acc[i][2];
+      if (n + 3 < N) p[3] = acc[i][3];
+    }
+  }
+}
+
+// Bilinear resample (align_corners=False, PyTorch's source-index rule) -> sigmoid < 0.5 -> bit.
+// One warp emits one 32-bit word (32 consecutive target pixels of one (b, q) row).
+__global__ void mask_bits_kernel(const float* __restrict__ masks, uint32_t* __restrict__ bits,
+                                 int32_t* __restrict__ row_open, int rows, int H, int W, int Ht, int Wt, int words) {
+  const int lane = threadIdx.x & 31;
+  const int warp_in_block = threadIdx.x >> 5;
+  const int warps_per_block = blockDim.x >> 5;
+  const int row = blockIdx.y;
+  const float* mp = masks + (int64_t)row * H * W;
+  const int St = Ht * Wt;
+  const bool identity = (H == Ht) && (W == Wt);
+  const float sh = (float)H / (float)Ht, sw = (float)W / (float)Wt;
+  bool any_open = false;
+  for (int w = blockIdx.x * warps_per_block + warp_in_block; w < words; w += gridDim.x * warps_per_block) {
+    const int s = w * 32 + lane;
+    bool blocked = false;
+    if (s < St) {
+      float val;
+      if (identity) {
+        val = mp[s];
+      } else {
+        const int y = s / Wt, x = s - y * Wt;
+        float sy = sh * ((float)y + 0.5f) - 0.5f;
+        float sx = sw * ((float)x + 0.5f) - 0.5f;
+        sy = sy < 0.f ? 0.f : sy;
+        sx = sx < 0.f ? 0.f : sx;
+        const int y0 = (int)sy, x0 = (int)sx;
+        const int yp = (y0 < H - 1) ? 1 : 0, xp = (x0 < W - 1) ? 1 : 0;
+        const float ly = sy - (float)y0, lx = sx - (float)x0;
+        const float hy = 1.f - ly, hx = 1.f - lx;
+        const float* p = mp + (int64_t)y0 * W + x0;
+        const float v00 = __ldg(p), v01 = __ldg(p + xp), v10 = __ldg(p + yp * W), v11 = __ldg(p + yp * W + xp);
+        val = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+      }
+      const float sig = 1.f / (1.f + expf(-val));  // the reference thresholds the sigmoid, not the logit
+      blocked = sig < 0.5f;
+      any_open |= !blocked;
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, blocked);
+    if (lane == 0) bits[(int64_t)row * words + w] = word;
+  }
+  if (__any_sync(0xffffffffu, any_open) && lane == 0) atomicOr(row_open + row, 1);
+}
+
+}  // namespace msm
+
+extern "C" int msm_mask_logits(const float* embed, const float* feat, float* masks, int B, int Q, int C, int64_t HW,
+                               void* stream) {
+  MSM_REQUIRE(embed && feat && masks, "embed, feat, masks must be non-null");
+  MSM_REQUIRE(B > 0 && Q > 0 && C > 0 && HW > 0, "sizes must be positive");
+  MSM_REQUIRE(B <= 65535, "batch too large");
+  const bool n_vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(feat) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(masks) & 15) == 0);
+  dim3 grid((unsigned)((HW + msm::BN - 1) / msm::BN), (Q + msm::BM - 1) / msm::BM, B);
+  msm::mask_gemm_kernel<<<grid, msm::GEMM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(embed, feat, masks, Q, C, HW,
+                                                                                          n_vec);
+  return msm::check_launch("mask_gemm_kernel");
+}
+
+extern "C" int msm_mask_to_attn_bits(const float* masks, uint32_t* bits, int32_t* row_open, int B, int Q, int H, int W,
+                                     int Ht, int Wt, void* stream) {
+  MSM_REQUIRE(masks && bits && row_open, "masks, bits, row_open must be non-null");
+  MSM_REQUIRE(B > 0 && Q > 0 && H > 0 && W > 0 && Ht > 0 && Wt > 0, "sizes must be positive");
+  const int rows = B * Q;
+  MSM_REQUIRE(rows <= 65535, "B*Q too large");
+  const int words = (Ht * Wt + 31) / 32;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MSM_CUDA(cudaMemsetAsync(row_open, 0, sizeof(int32_t) * rows, st));
+  const int wpb = 8;
+  int bx = (words + wpb - 1) / wpb;
+  if (bx > 64) bx = 64;
+  dim3 grid(bx, rows);
+  msm::mask_bits_kernel<<<grid, wpb * 32, 0, st>>>(masks, bits, row_open, rows, H, W, Ht, Wt, words);
+  return msm::check_launch("mask_bits_kernel");
+}

@@ -1,0 +1,426 @@
+"""Mean-shift transformer decoders - mirror of the reference's
+modeling/transformer_decoder/meanshiftformer_transformer_decoder.py (layers :27-315, MLP :329-341,
+MeanShiftTransformerDecoder :343-695, PretrainedMeanShiftTransformerDecoder :697-1048).
+
+Same class names, constructor keywords, ``from_config`` keys, registry and ``state_dict`` layout
+(``transformer_cross_attention_layers.{i}.meanshift_attn.*`` ... ``mask_embed.layers.{j}.*``), so
+reference checkpoints load with ``strict=True``. What differs is how ``forward`` runs:
+
+* batch-first [B, len, C] buffers throughout; heads are addressed by strides (no transposes);
+* the sine position embedding is a cached [S, C] table added to the keys' input, not a
+  [B, C, H, W] tensor rebuilt per call;
+* keys/values of all layers that share a feature level are projected in one GEMM before the
+  sequential loop (they do not depend on the queries);
+* cross/self attention run in the streaming vMF kernel (csrc/vmf_attention.cu): no [B*h, Q, S]
+  score, weight or additive-mask tensors;
+* the attention mask is 1 bit per (query, key) shared by all heads (csrc/mask_head.cu), with the
+  reference's "row blocks everything -> attend everywhere" rule (:618) carried as a per-row flag.
+"""
+import logging
+from typing import Optional
+
+import torch
+from torch import Tensor, nn
+from torch.nn import functional as F
+
+from .... import ops
+from ....d2compat import Conv2d, c2_xavier_fill, configurable
+from .attention_util import MeanShiftAttention
+from .maskformer_transformer_decoder import TRANSFORMER_DECODER_REGISTRY
+from .position_encoding import PositionEmbeddingSine
+from .transformer import _get_activation_fn
+
+# keys+values of one feature level are pre-projected for all its layers when they fit this budget
+_KV_PRECOMPUTE_BYTES = 4 << 30
+
+
+def _xavier(module):
+    for p in module.parameters():
+        if p.dim() > 1:
+            nn.init.xavier_uniform_(p)
+
+
+class _AttentionLayerBase(nn.Module):
+    def with_pos_embed(self, tensor, pos: Optional[Tensor]):
+        return tensor if pos is None else tensor + pos
+
+
+class SelfAttentionLayer(_AttentionLayerBase):
+    """Vanilla softmax self-attention layer (reference :27-87); selected only when
+    USE_MEANSHIFT_SELF_ATTENTION is False, which no UOIS config does. Plain torch."""
+
+    def __init__(self, d_model, nhead, dropout=0.0, activation="relu", normalize_before=False):
+        super().__init__()
+        self.self_attn = nn.MultiheadAttention(d_model, nhead, dropout=dropout)
+        self.norm = nn.LayerNorm(d_model)
+        self.dropout = nn.Dropout(dropout)
+        self.activation = _get_activation_fn(activation)
+        self.normalize_before = normalize_before
+        _xavier(self)
+
+    def forward(self, tgt, tgt_mask=None, tgt_key_padding_mask=None, query_pos=None):
+        if self.normalize_before:
+            t2 = self.norm(tgt)
+            q = k = self.with_pos_embed(t2, query_pos)
+            return tgt + self.dropout(self.self_attn(q, k, value=t2, attn_mask=tgt_mask,
+                                                     key_padding_mask=tgt_key_padding_mask)[0])
+        q = k = self.with_pos_embed(tgt, query_pos)
+        t2 = self.self_attn(q, k, value=tgt, attn_mask=tgt_mask, key_padding_mask=tgt_key_padding_mask)[0]
+        return self.norm(tgt + self.dropout(t2))
+
+
+class CrossAttentionLayer(_AttentionLayerBase):
+    """Vanilla softmax cross-attention layer (reference :90-145); unused by UOIS configs. Plain torch."""
+
+    def __init__(self, d_model, nhead, dropout=0.0, activation="relu", normalize_before=False):
+        super().__init__()
+        self.multihead_attn = nn.MultiheadAttention(d_model, nhead, dropout=dropout)
+        self.norm = nn.LayerNorm(d_model)
+        self.dropout = nn.Dropout(dropout)
+        self.activation = _get_activation_fn(activation)
+        self.normalize_before = normalize_before
+        _xavier(self)
+
+    def forward(self, tgt, memory, memory_mask=None, memory_key_padding_mask=None, pos=None, query_pos=None):
+        if self.normalize_before:
+            t2 = self.norm(tgt)
+            t2 = self.multihead_attn(query=self.with_pos_embed(t2, query_pos), key=self.with_pos_embed(memory, pos),
+                                     value=memory, attn_mask=memory_mask,
+                                     key_padding_mask=memory_key_padding_mask)[0]
+            return tgt + self.dropout(t2)
+        t2 = self.multihead_attn(query=self.with_pos_embed(tgt, query_pos), key=self.with_pos_embed(memory, pos),
+                                 value=memory, attn_mask=memory_mask, key_padding_mask=memory_key_padding_mask)[0]
+        return self.norm(tgt + self.dropout(t2))
+
+
+class MeanShiftSelfAttentionLayer(_AttentionLayerBase):
+    """Reference :148-203. Stand-alone ``forward`` keeps the reference's seq-first signature."""
+
+    def __init__(self, d_model, nhead, dropout=0.0, activation="relu", normalize_before=False):
+        super().__init__()
+        self.self_attn = MeanShiftAttention(d_model, nhead, dropout=dropout)
+        self.norm = nn.LayerNorm(d_model)
+        self.dropout = nn.Dropout(dropout)
+        self.activation = _get_activation_fn(activation)
+        self.normalize_before = normalize_before
+        _xavier(self)
+
+    def forward_post(self, tgt, tgt_mask=None, tgt_key_padding_mask=None, query_pos=None):
+        q = k = self.with_pos_embed(tgt, query_pos)
+        t2 = self.self_attn(q, k, value=tgt, attn_mask=tgt_mask, key_padding_mask=tgt_key_padding_mask,
+                            need_weights=False)[0]
+        return self.norm(tgt + self.dropout(t2))
+
+    def forward_pre(self, tgt, tgt_mask=None, tgt_key_padding_mask=None, query_pos=None):
+        t2 = self.norm(tgt)
+        q = k = self.with_pos_embed(t2, query_pos)
+        t2 = self.self_attn(q, k, value=t2, attn_mask=tgt_mask, key_padding_mask=tgt_key_padding_mask,
+                            need_weights=False)[0]
+        return tgt + self.dropout(t2)
+
+    def forward(self, tgt, tgt_mask=None, tgt_key_padding_mask=None, query_pos=None):
+        if self.normalize_before:
+            return self.forward_pre(tgt, tgt_mask, tgt_key_padding_mask, query_pos)
+        return self.forward_post(tgt, tgt_mask, tgt_key_padding_mask, query_pos)
+
+
+class MeanShiftCrossAttentionLayer(_AttentionLayerBase):
+    """Reference :206-272."""
+
+    def __init__(self, d_model, nhead=1, dropout=0.0, activation="relu", layer_normalize_before=False):
+        super().__init__()
+        self.meanshift_attn = MeanShiftAttention(d_model, nhead, dropout=dropout)
+        self.norm = nn.LayerNorm(d_model)
+        self.dropout = nn.Dropout(dropout)
+        self.activation = _get_activation_fn(activation)
+        self.normalize_before = layer_normalize_before
+        _xavier(self)
+
+    def forward_pre(self, tgt, memory, memory_mask=None, memory_key_padding_mask=None, pos=None, query_pos=None):
+        t2 = self.norm(tgt)
+        t2 = self.meanshift_attn(query=self.with_pos_embed(t2, query_pos), key=self.with_pos_embed(memory, pos),
+                                 value=memory, attn_mask=memory_mask, key_padding_mask=memory_key_padding_mask,
+                                 need_weights=False)[0]
+        return tgt + self.dropout(t2)
+
+    def forward_post(self, tgt, memory, memory_mask=None, memory_key_padding_mask=None, pos=None, query_pos=None):
+        t2 = self.meanshift_attn(query=self.with_pos_embed(tgt, query_pos), key=self.with_pos_embed(memory, pos),
+                                 value=memory, attn_mask=memory_mask, key_padding_mask=memory_key_padding_mask,
+                                 need_weights=False)[0]
+        return self.norm(tgt + self.dropout(t2))
+
+    def forward(self, tgt, memory, memory_mask=None, memory_key_padding_mask=None, pos=None, query_pos=None):
+        if self.normalize_before:
+            return self.forward_pre(tgt, memory, memory_mask, memory_key_padding_mask, pos, query_pos)
+        return self.forward_post(tgt, memory, memory_mask, memory_key_padding_mask, pos, query_pos)
+
+
+class FFNLayer(nn.Module):
+    """Reference :275-315."""
+
+    def __init__(self, d_model, dim_feedforward=2048, dropout=0.0, activation="relu", normalize_before=False):
+        super().__init__()
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.dropout = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm = nn.LayerNorm(d_model)
+        self.activation = _get_activation_fn(activation)
+        self.normalize_before = normalize_before
+        _xavier(self)
+
+    def forward(self, tgt):
+        if self.normalize_before:
+            t2 = self.norm(tgt)
+            return tgt + self.dropout(self.linear2(self.dropout(self.activation(self.linear1(t2)))))
+        t2 = self.linear2(self.dropout(self.activation(self.linear1(tgt))))
+        return self.norm(tgt + self.dropout(t2))
+
+
+class MLP(nn.Module):
+    """Reference :329-341."""
+
+    def __init__(self, input_dim, hidden_dim, output_dim, num_layers):
+        super().__init__()
+        self.num_layers = num_layers
+        h = [hidden_dim] * (num_layers - 1)
+        self.layers = nn.ModuleList(nn.Linear(n, k) for n, k in zip([input_dim] + h, h + [output_dim]))
+
+    def forward(self, x):
+        for i, layer in enumerate(self.layers):
+            x = F.relu(layer(x)) if i < self.num_layers - 1 else layer(x)
+        return x
+
+
+class _MeanShiftDecoderBase(nn.Module):
+    """Shared body of the two registered decoders; they differ only in ``_NUM_LEVELS`` (3 vs 1,
+    reference :494 vs :848)."""
+
+    _version = 2
+    _NUM_LEVELS = 3
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                              error_msgs):
+        version = local_metadata.get("version", None)
+        if version is None or version < 2:  # reference :348-369: static_query -> query_feat
+            renamed = False
+            for k in list(state_dict.keys()):
+                if k.startswith(prefix) and "static_query" in k:
+                    state_dict[k.replace("static_query", "query_feat")] = state_dict.pop(k)
+                    renamed = True
+            if renamed:
+                logging.getLogger(__name__).warning(
+                    f"Weight format of {self.__class__.__name__} have changed! "
+                    "Please upgrade your models. Applying automatic conversion now ...")
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                                      error_msgs)
+
+    @configurable
+    def __init__(self, in_channels, mask_classification=True, *, num_classes: int, hidden_dim: int, num_queries: int,
+                 nheads: int, dim_feedforward: int, dec_layers: int, pre_norm: bool, mask_dim: int,
+                 enforce_input_project: bool, use_meanshift_cross_attention: bool, disable_attention_mask: bool,
+                 use_meanshift_self_attention: bool, decoder_block_norm: bool):
+        super().__init__()
+        assert mask_classification, "Only support mask classification model"
+        self.mask_classification = mask_classification
+        self.pe_layer = PositionEmbeddingSine(hidden_dim // 2, normalize=True)
+        self.num_heads = nheads
+        self.num_layers = dec_layers
+        self.pre_norm = pre_norm
+        self.use_meanshift_seeds = False  # hard-coded in the reference (:424, :778)
+        self.use_meanshift_cross_attention = use_meanshift_cross_attention
+        self.disable_attention_mask = disable_attention_mask
+        self.use_meanshift_self_attention = use_meanshift_self_attention
+        self.decoder_block_norm = decoder_block_norm
+        self.transformer_self_attention_layers = nn.ModuleList()
+        self.transformer_cross_attention_layers = nn.ModuleList()
+        self.transformer_ffn_layers = nn.ModuleList()
+        for _ in range(self.num_layers):
+            sa = MeanShiftSelfAttentionLayer if use_meanshift_self_attention else SelfAttentionLayer
+            self.transformer_self_attention_layers.append(
+                sa(d_model=hidden_dim, nhead=nheads, dropout=0.0, normalize_before=pre_norm))
+            if use_meanshift_cross_attention:
+                self.transformer_cross_attention_layers.append(MeanShiftCrossAttentionLayer(
+                    d_model=hidden_dim, nhead=nheads, dropout=0.0, layer_normalize_before=pre_norm))
+            else:
+                self.transformer_cross_attention_layers.append(CrossAttentionLayer(
+                    d_model=hidden_dim, nhead=nheads, dropout=0.0, normalize_before=pre_norm))
+            self.transformer_ffn_layers.append(FFNLayer(d_model=hidden_dim, dim_feedforward=dim_feedforward,
+                                                        dropout=0.0, normalize_before=pre_norm))
+        self.decoder_norm = nn.LayerNorm(hidden_dim)
+        self.num_queries = num_queries
+        self.query_feat = nn.Embedding(num_queries, hidden_dim)
+        self.query_embed = nn.Embedding(num_queries, hidden_dim)
+        self.num_feature_levels = self._NUM_LEVELS
+        self.level_embed = nn.Embedding(self.num_feature_levels, hidden_dim)
+        self.input_proj = nn.ModuleList()
+        for _ in range(self.num_feature_levels):
+            if in_channels != hidden_dim or enforce_input_project:
+                self.input_proj.append(Conv2d(in_channels, hidden_dim, kernel_size=1))
+                c2_xavier_fill(self.input_proj[-1])
+            else:
+                self.input_proj.append(nn.Sequential())
+        if self.mask_classification:
+            self.class_embed = nn.Linear(hidden_dim, num_classes + 1)
+        self.mask_embed = MLP(hidden_dim, hidden_dim, mask_dim, 3)
+
+    @classmethod
+    def from_config(cls, cfg, in_channels, mask_classification):
+        mf = cfg.MODEL.MASK_FORMER
+        assert mf.DEC_LAYERS >= 1
+        return {
+            "in_channels": in_channels,
+            "mask_classification": mask_classification,
+            "num_classes": cfg.MODEL.SEM_SEG_HEAD.NUM_CLASSES,
+            "hidden_dim": mf.HIDDEN_DIM,
+            "num_queries": mf.NUM_OBJECT_QUERIES,
+            "nheads": mf.NHEADS,
+            "dim_feedforward": mf.DIM_FEEDFORWARD,
+            "dec_layers": mf.DEC_LAYERS - 1,  # reference :529: one "layer" is the learnable-query prediction
+            "pre_norm": mf.PRE_NORM,
+            "enforce_input_project": mf.ENFORCE_INPUT_PROJ,
+            "mask_dim": cfg.MODEL.SEM_SEG_HEAD.MASK_DIM,
+            "use_meanshift_cross_attention": mf.USE_MEANSHIFT_CROSS_ATTENTION,
+            "disable_attention_mask": mf.DISABLE_MEANSHIFT_ATTENTION_MASK,
+            "use_meanshift_self_attention": mf.USE_MEANSHIFT_SELF_ATTENTION,
+            "decoder_block_norm": mf.DECODER_BLOCK_NORM,
+        }
+
+    # ------------------------------------------------------------------ prediction heads
+    def _heads(self, out, mask_features, target_size, need_mask):
+        """out [B,Q,C] -> (class logits [B,Q,K+1], mask logits [B,Q,h,w], bits, row_open)."""
+        dec = self.decoder_norm(out)
+        logits = self.class_embed(dec)
+        embed = self.mask_embed(dec)
+        masks = ops.mask_logits(embed, mask_features)
+        bits = row_open = None
+        if need_mask:
+            bits, row_open = ops.mask_to_attn_bits(masks, target_size)
+        return logits, masks, bits, row_open
+
+    def forward_prediction_heads(self, output, mask_features, attn_mask_target_size):
+        """Reference :660-682 / :1012-1035 (seq-first ``output`` [Q,B,C]); returns the reference's
+        (outputs_class, outputs_mask, bool attn_mask [B*heads, Q, S] or None)."""
+        logits, masks, bits, _ = self._heads(output.transpose(0, 1).contiguous(), mask_features,
+                                             attn_mask_target_size, not self.disable_attention_mask)
+        attn_mask = None
+        if bits is not None:
+            S = int(attn_mask_target_size[0]) * int(attn_mask_target_size[1])
+            attn_mask = ops.unpack_attn_bits(bits, torch.ones_like(bits[..., 0]), S, self.num_heads)
+        return logits, masks, attn_mask
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x, mask_features, mask=None):
+        assert len(x) == self.num_feature_levels
+        del mask  # reference :548 / :900
+        if not (self.use_meanshift_cross_attention and self.use_meanshift_self_attention) or self.pre_norm:
+            raise NotImplementedError(
+                "the CUDA path implements the configuration every UOIS YAML selects: post-norm with "
+                "mean-shift cross- and self-attention")
+        B = x[0].shape[0]
+        C = self.query_feat.weight.shape[1]
+        H, L = self.num_heads, self.num_feature_levels
+        hd = C // H
+        dev = x[0].device
+        mask_features = mask_features.float().contiguous()
+
+        # ---- per-level memory (keys' input = src + pos, values' input = src), batch-first [B,S,C]
+        sizes, src, key_in = [], [], []
+        for l in range(L):
+            h, w = x[l].shape[-2:]
+            sizes.append((h, w))
+            xl = x[l].float().flatten(2).transpose(1, 2)  # [B,S,Cin]
+            proj = self.input_proj[l]
+            if isinstance(proj, nn.Conv2d):
+                s = F.linear(xl, proj.weight.flatten(1), proj.bias + self.level_embed.weight[l])
+            else:
+                s = xl + self.level_embed.weight[l]
+            src.append(s)
+            key_in.append(s + self.pe_layer.table(h, w, dev))
+
+        # ---- keys / values: independent of the queries, so project them up front per level
+        layers_of = [[i for i in range(self.num_layers) if i % L == l] for l in range(L)]
+        kv = {}
+
+        def project_kv(level, layer_ids):
+            attn = [self.transformer_cross_attention_layers[i].meanshift_attn for i in layer_ids]
+            wk = torch.cat([a.in_proj_weight[C:2 * C] for a in attn], 0)
+            bk = torch.cat([a.in_proj_bias[C:2 * C] for a in attn], 0)
+            wv = torch.cat([a.in_proj_weight[2 * C:] for a in attn], 0)
+            bv = torch.cat([a.in_proj_bias[2 * C:] for a in attn], 0)
+            K = F.linear(key_in[level], wk, bk)  # [B,S,n*C]
+            V = F.linear(src[level], wv, bv)
+            for j, i in enumerate(layer_ids):
+                kv[i] = (K[..., j * C:(j + 1) * C], V[..., j * C:(j + 1) * C])
+
+        for l in range(L):
+            S = sizes[l][0] * sizes[l][1]
+            if layers_of[l] and 8 * B * S * C * len(layers_of[l]) <= _KV_PRECOMPUTE_BYTES:
+                project_kv(l, layers_of[l])
+
+        def heads_view(t):  # [B,len,C] (row stride may exceed C) -> [B,H,len,hd] view
+            return t.unflatten(-1, (H, hd)).permute(0, 2, 1, 3)
+
+        query_pos = self.query_embed.weight.unsqueeze(0)  # [1,Q,C]
+        out = self.query_feat.weight.unsqueeze(0).expand(B, -1, -1).contiguous()
+        need_mask = not self.disable_attention_mask
+
+        predictions_class, predictions_mask = [], []
+        logits, masks, bits, row_open = self._heads(out, mask_features, sizes[0], need_mask)
+        predictions_class.append(logits)
+        predictions_mask.append(masks)
+
+        for i in range(self.num_layers):
+            lvl = i % L
+            if i not in kv:
+                project_kv(lvl, [i])
+            K, V = kv.pop(i)
+            # cross-attention (reference :245-260), post-norm
+            ca = self.transformer_cross_attention_layers[i]
+            a = ca.meanshift_attn
+            q = F.linear(out + query_pos, a.in_proj_weight[:C], a.in_proj_bias[:C])
+            o = torch.empty(B, self.num_queries, C, device=dev, dtype=torch.float32)
+            ops.vmf_attention(heads_view(q), heads_view(K), heads_view(V), blocked_bits=bits, row_open=row_open,
+                              out=heads_view(o))
+            out = ca.norm(out + a.out_proj(o))
+            del K, V
+            # self-attention (reference :171-181): q = k = out + query_pos, v = out
+            sl = self.transformer_self_attention_layers[i]
+            a = sl.self_attn
+            qk = F.linear(out + query_pos, a.in_proj_weight[:2 * C], a.in_proj_bias[:2 * C])
+            v = F.linear(out, a.in_proj_weight[2 * C:], a.in_proj_bias[2 * C:])
+            o = torch.empty(B, self.num_queries, C, device=dev, dtype=torch.float32)
+            ops.vmf_attention(heads_view(qk[..., :C]), heads_view(qk[..., C:]), heads_view(v), out=heads_view(o))
+            out = sl.norm(out + a.out_proj(o))
+            # FFN (reference :300-304) and block norm (:637-638)
+            out = self.transformer_ffn_layers[i](out)
+            if self.decoder_block_norm:
+                out = F.normalize(out, dim=-1)
+            logits, masks, bits, row_open = self._heads(out, mask_features, sizes[(i + 1) % L], need_mask)
+            predictions_class.append(logits)
+            predictions_mask.append(masks)
+
+        assert len(predictions_class) == self.num_layers + 1
+        return {
+            "pred_logits": predictions_class[-1],
+            "pred_masks": predictions_mask[-1],
+            "aux_outputs": self._set_aux_loss(predictions_class if self.mask_classification else None,
+                                              predictions_mask),
+        }
+
+    @torch.jit.unused
+    def _set_aux_loss(self, outputs_class, outputs_seg_masks):
+        if self.mask_classification:
+            return [{"pred_logits": a, "pred_masks": b} for a, b in zip(outputs_class[:-1], outputs_seg_masks[:-1])]
+        return [{"pred_masks": b} for b in outputs_seg_masks[:-1]]
+
+
+@TRANSFORMER_DECODER_REGISTRY.register()
+class MeanShiftTransformerDecoder(_MeanShiftDecoderBase):
+    """Reference :343-695: three feature levels, cycled ``i % 3`` (ResNet-50 configs)."""
+    _NUM_LEVELS = 3
+
+
+@TRANSFORMER_DECODER_REGISTRY.register()
+class PretrainedMeanShiftTransformerDecoder(_MeanShiftDecoderBase):
+    """Reference :697-1048: one full-resolution level (UCN RGB-D configs)."""
+    _NUM_LEVELS = 1

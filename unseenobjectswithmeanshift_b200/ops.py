@@ -1,0 +1,257 @@
+"""torch.Tensor front-ends of the C ABI (include/msmformer_b200.h).
+
+PyTorch here is plumbing: it owns device memory and the CUDA stream; every function below hands
+raw device pointers + sizes to libmsmformer_b200.so and enqueues on torch's current stream.
+All functions require CUDA fp32 tensors and raise otherwise - there is no CPU path.
+"""
+import torch
+
+from . import _lib
+from ._lib import check
+
+KAPPA = 30.0  # reference: transformer_decoder/attention_util.py:26
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require(t, name, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: unseenobjectswithmeanshift_b200 has no CPU path")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if t.requires_grad and torch.is_grad_enabled():
+        raise RuntimeError(f"{name} requires grad: this op is forward-only, call it under torch.no_grad() "
+                           "(only MSDeformAttnFunction has a backward)")
+    return t
+
+
+def _bhld(t, name):
+    """4-D view [B, H, L, hd] with unit stride on the last axis -> (tensor, sb, sh, sl)."""
+    _require(t, name)
+    if t.dim() != 4:
+        raise ValueError(f"{name} must be a [B, H, L, hd] view")
+    if t.shape[3] > 1 and t.stride(3) != 1:
+        raise ValueError(f"{name}: channel axis must be contiguous")
+    return t, t.stride(0), t.stride(1), t.stride(2)
+
+
+def vmf_attention(q, k, v, *, blocked_bits=None, row_open=None, add_mask=None, kappa=KAPPA,
+                  normalize_q=True, normalize_k=True, out=None, return_den=False):
+    """vMF attention core on [B, H, L, hd] *views* (any batch/head/row strides, see msm_vmf_attention_fwd).
+
+    blocked_bits int32 [B, Nq, ceil(Ns/32)] (bit set = blocked), row_open int32 [B, Nq];
+    or add_mask float [B*H, Nq, Ns]. Returns out [B, H, Nq, hd] view of a [B, Nq, H*hd] buffer
+    (and den [B*H, Nq] if asked)."""
+    q, q_sb, q_sh, q_sl = _bhld(q, "q")
+    k, k_sb, k_sh, k_sl = _bhld(k, "k")
+    v, v_sb, v_sh, v_sl = _bhld(v, "v")
+    B, H, Nq, hd = q.shape
+    Ns = k.shape[2]
+    if k.shape != (B, H, Ns, hd) or v.shape != (B, H, Ns, hd):
+        raise ValueError(f"shape mismatch: q {tuple(q.shape)} k {tuple(k.shape)} v {tuple(v.shape)}")
+    if out is None:
+        out = torch.empty(B, Nq, H, hd, device=q.device, dtype=torch.float32).permute(0, 2, 1, 3)
+    out, o_sb, o_sh, o_sl = _bhld(out, "out")
+    den = torch.empty(B * H, Nq, device=q.device, dtype=torch.float32) if return_den else None
+    wpr = 0
+    if blocked_bits is not None:
+        _require(blocked_bits, "blocked_bits", torch.int32)
+        if not blocked_bits.is_contiguous() or blocked_bits.shape[:2] != (B, Nq):
+            raise ValueError("blocked_bits must be contiguous [B, Nq, words]")
+        wpr = blocked_bits.shape[2]
+        if row_open is not None:
+            _require(row_open, "row_open", torch.int32)
+    if add_mask is not None:
+        _require(add_mask, "add_mask")
+        if not add_mask.is_contiguous() or tuple(add_mask.shape) != (B * H, Nq, Ns):
+            raise ValueError("add_mask must be contiguous [B*H, Nq, Ns]")
+    L = _lib.lib()
+    ws_bytes = L.msm_vmf_attention_workspace_bytes(B, H, Nq, Ns, hd)
+    ws = torch.empty(ws_bytes, device=q.device, dtype=torch.uint8)
+    flags = (1 if normalize_q else 0) | (2 if normalize_k else 0)
+    rc = L.msm_vmf_attention_fwd(
+        q.data_ptr(), q_sb, q_sh, q_sl, k.data_ptr(), k_sb, k_sh, k_sl, v.data_ptr(), v_sb, v_sh, v_sl,
+        out.data_ptr(), o_sb, o_sh, o_sl, den.data_ptr() if den is not None else None,
+        blocked_bits.data_ptr() if blocked_bits is not None else None, wpr,
+        row_open.data_ptr() if row_open is not None else None,
+        add_mask.data_ptr() if add_mask is not None else None,
+        B, H, Nq, Ns, hd, float(kappa), flags, ws.data_ptr(), ws_bytes, _stream())
+    check(rc, "msm_vmf_attention_fwd")
+    return (out, den) if return_den else out
+
+
+def vmf_attention_weights(q, k, den, *, blocked_bits=None, row_open=None, add_mask=None, kappa=KAPPA,
+                          normalize_q=True, normalize_k=True):
+    """Attention weights [B*H, Nq, Ns] (the second value hypersphere_attention returns)."""
+    q, q_sb, q_sh, q_sl = _bhld(q, "q")
+    k, k_sb, k_sh, k_sl = _bhld(k, "k")
+    B, H, Nq, hd = q.shape
+    Ns = k.shape[2]
+    attn = torch.empty(B * H, Nq, Ns, device=q.device, dtype=torch.float32)
+    flags = (1 if normalize_q else 0) | (2 if normalize_k else 0)
+    rc = _lib.lib().msm_vmf_attention_weights(
+        q.data_ptr(), q_sb, q_sh, q_sl, k.data_ptr(), k_sb, k_sh, k_sl, _require(den, "den").data_ptr(),
+        blocked_bits.data_ptr() if blocked_bits is not None else None,
+        blocked_bits.shape[2] if blocked_bits is not None else 0,
+        row_open.data_ptr() if row_open is not None else None,
+        add_mask.data_ptr() if add_mask is not None else None,
+        attn.data_ptr(), B, H, Nq, Ns, hd, float(kappa), flags, _stream())
+    check(rc, "msm_vmf_attention_weights")
+    return attn
+
+
+def mask_logits(mask_embed, mask_features, out=None):
+    """einsum('bqc,bchw->bqhw'): mask_embed [B,Q,C], mask_features [B,C,H,W] -> [B,Q,H,W]."""
+    e = _require(mask_embed, "mask_embed").contiguous()
+    f = _require(mask_features, "mask_features").contiguous()
+    B, Q, C = e.shape
+    if f.dim() != 4 or f.shape[0] != B or f.shape[1] != C:
+        raise ValueError(f"mask_features {tuple(f.shape)} does not match mask_embed {tuple(e.shape)}")
+    H, W = f.shape[2], f.shape[3]
+    if out is None:
+        out = torch.empty(B, Q, H, W, device=e.device, dtype=torch.float32)
+    rc = _lib.lib().msm_mask_logits(e.data_ptr(), f.data_ptr(), out.data_ptr(), B, Q, C, H * W, _stream())
+    check(rc, "msm_mask_logits")
+    return out
+
+
+def mask_to_attn_bits(masks, target_size):
+    """masks [B,Q,H,W] -> (blocked bits int32 [B,Q,ceil(Ht*Wt/32)], row_open int32 [B,Q])."""
+    m = _require(masks, "masks").contiguous()
+    B, Q, H, W = m.shape
+    Ht, Wt = int(target_size[0]), int(target_size[1])
+    words = (Ht * Wt + 31) // 32
+    bits = torch.empty(B, Q, words, device=m.device, dtype=torch.int32)
+    row_open = torch.empty(B, Q, device=m.device, dtype=torch.int32)
+    rc = _lib.lib().msm_mask_to_attn_bits(m.data_ptr(), bits.data_ptr(), row_open.data_ptr(), B, Q, H, W, Ht, Wt,
+                                          _stream())
+    check(rc, "msm_mask_to_attn_bits")
+    return bits, row_open
+
+
+def unpack_attn_bits(bits, row_open, num_keys, num_heads):
+    """bits/row_open -> the reference's bool attn_mask [B*heads, Q, S] AFTER its un-mask rule
+    (decoder.py:618). For tests and for callers that want the reference representation."""
+    B, Q, words = bits.shape
+    shifts = torch.arange(32, device=bits.device, dtype=torch.int32)
+    blocked = ((bits.unsqueeze(-1) >> shifts) & 1).bool().reshape(B, Q, words * 32)[..., :num_keys]
+    blocked = blocked & (row_open != 0).unsqueeze(-1)
+    return blocked.unsqueeze(1).repeat(1, num_heads, 1, 1).flatten(0, 1)
+
+
+def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step=128):
+    """Same signature and result as MultiScaleDeformableAttention.ms_deform_attn_forward
+    (pixel_decoder/ops/src/ms_deform_attn.h:25-45): returns [N, Lq, M*D]."""
+    for t, n in ((value, "value"), (sampling_loc, "sampling_loc"), (attn_weight, "attn_weight")):
+        _require(t, n)
+        if not t.is_contiguous():  # the reference asserts this too (ms_deform_attn_cuda.cu:33-37)
+            raise RuntimeError(f"{n} tensor has to be contiguous")
+    _require(spatial_shapes, "spatial_shapes", torch.int64)
+    _require(level_start_index, "level_start_index", torch.int64)
+    if not spatial_shapes.is_contiguous() or not level_start_index.is_contiguous():
+        raise RuntimeError("spatial_shapes / level_start_index tensor has to be contiguous")
+    N, S, M, D = value.shape
+    _, Lq, _, L, P, _ = sampling_loc.shape
+    out = torch.empty(N, Lq, M * D, device=value.device, dtype=torch.float32)
+    rc = _lib.lib().msm_ms_deform_attn_fwd(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                                           sampling_loc.data_ptr(), attn_weight.data_ptr(), out.data_ptr(),
+                                           N, S, M, D, L, Lq, P, int(im2col_step), _stream())
+    check(rc, "msm_ms_deform_attn_fwd")
+    return out
+
+
+def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+                            im2col_step=128):
+    """MultiScaleDeformableAttention.ms_deform_attn_backward (ms_deform_attn.h:47-67):
+    returns [grad_value, grad_sampling_loc, grad_attn_weight]."""
+    go = _require(grad_output, "grad_output").contiguous()
+    N, S, M, D = value.shape
+    _, Lq, _, L, P, _ = sampling_loc.shape
+    gv = torch.zeros_like(value)
+    gl = torch.empty_like(sampling_loc)
+    ga = torch.empty_like(attn_weight)
+    rc = _lib.lib().msm_ms_deform_attn_bwd(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                                           sampling_loc.data_ptr(), attn_weight.data_ptr(), go.data_ptr(),
+                                           gv.data_ptr(), gl.data_ptr(), ga.data_ptr(),
+                                           N, S, M, D, L, Lq, P, int(im2col_step), _stream())
+    check(rc, "msm_ms_deform_attn_bwd")
+    return [gv, gl, ga]
+
+
+def mean_shift_hill_climb(X, Z, kappa, max_iters=10):
+    """Batched seed_hill_climbing_ball: X [B,n,d] (or [n,d]), Z [B,m,d] (or [m,d]) -> Z' same shape."""
+    squeeze = X.dim() == 2
+    Xb = _require(X, "X").contiguous()
+    Zb = _require(Z, "Z").contiguous()
+    if squeeze:
+        Xb, Zb = Xb.unsqueeze(0), Zb.unsqueeze(0)
+    B, n, d = Xb.shape
+    m = Zb.shape[1]
+    if Zb.shape[0] != B or Zb.shape[2] != d:
+        raise ValueError(f"X {tuple(X.shape)} / Z {tuple(Z.shape)} mismatch")
+    out = torch.empty_like(Zb)
+    L = _lib.lib()
+    ws_bytes = L.msm_mean_shift_workspace_bytes(B, n, m, d)
+    ws = torch.empty(ws_bytes, device=Xb.device, dtype=torch.uint8)
+    rc = L.msm_mean_shift_hill_climb(Xb.data_ptr(), Zb.data_ptr(), out.data_ptr(), B, n, m, d, float(kappa),
+                                     int(max_iters), ws.data_ptr(), ws_bytes, _stream())
+    check(rc, "msm_mean_shift_hill_climb")
+    return out[0] if squeeze else out
+
+
+# ----------------------------------------------------------------------------------------------
+# launch accounting / per-op device timing (used by bench.py; off by default)
+# ----------------------------------------------------------------------------------------------
+class _Stats:
+    launches = 0          # kernels of THIS library enqueued since reset
+    timing = False        # when True every op is bracketed by CUDA events on the launching stream
+    events = []           # (tag, start_event, end_event)
+
+
+def reset_stats(timing=False):
+    _Stats.launches = 0
+    _Stats.timing = timing
+    _Stats.events = []
+
+
+def launches():
+    return _Stats.launches
+
+
+def op_times_ms():
+    """tag -> (count, total ms); call after torch.cuda.synchronize()."""
+    agg = {}
+    for tag, a, b in _Stats.events:
+        c, t = agg.get(tag, (0, 0.0))
+        agg[tag] = (c + 1, t + a.elapsed_time(b))
+    return agg
+
+
+def _instrument(tag, kernels):
+    def deco(fn):
+        def wrapped(*args, **kwargs):
+            n = kernels(*args, **kwargs) if callable(kernels) else kernels
+            _Stats.launches += n
+            if not _Stats.timing:
+                return fn(*args, **kwargs)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = fn(*args, **kwargs)
+            b.record()
+            _Stats.events.append((tag, a, b))
+            return r
+        wrapped.__name__, wrapped.__doc__ = fn.__name__, fn.__doc__
+        return wrapped
+    return deco
+
+
+vmf_attention = _instrument("vmf_attention", 2)(vmf_attention)
+vmf_attention_weights = _instrument("vmf_attention_weights", 1)(vmf_attention_weights)
+mask_logits = _instrument("mask_logits", 1)(mask_logits)
+mask_to_attn_bits = _instrument("mask_to_attn_bits", 1)(mask_to_attn_bits)
+ms_deform_attn_forward = _instrument("ms_deform_attn_forward", 1)(ms_deform_attn_forward)
+ms_deform_attn_backward = _instrument("ms_deform_attn_backward", 1)(ms_deform_attn_backward)
+mean_shift_hill_climb = _instrument("mean_shift_hill_climb", lambda X, Z, kappa, max_iters=10: 2 * int(max_iters))(
+    mean_shift_hill_climb)

@@ -1,0 +1,103 @@
+"""The BASELINE.json configurations as constructors + synthetic inputs.
+
+``r50``   config #2: MSDeformAttnPixelDecoder (res2..res5 of a ResNet-50 at 640x480) +
+          MeanShiftTransformerDecoder, 100 queries, 9 layers  (configs/mixture_ResNet50.yaml).
+``ucn``   config #1/#3 stage 1: SimpleBasePixelDecoder on a unit-norm 64-d embedding map at full
+          resolution + PretrainedMeanShiftTransformerDecoder, 6 layers (configs/mixture_UCN.yaml).
+``crop``  config #3 stage 2: same at 224x224, 8 layers (configs/crop_mixture_UCN.yaml).
+Weights are random-init by the modules' own (reference-identical) initialisers under a fixed seed.
+"""
+import torch
+import torch.nn.functional as F
+
+from .d2compat import ShapeSpec
+
+R50_SHAPES = {"res2": ShapeSpec(channels=256, stride=4), "res3": ShapeSpec(channels=512, stride=8),
+              "res4": ShapeSpec(channels=1024, stride=16), "res5": ShapeSpec(channels=2048, stride=32)}
+
+HEAD_CFG = {
+    "r50": dict(pixel_decoder="MSDeformAttnPixelDecoder", decoder="MeanShiftTransformerDecoder", dec_layers=9,
+                height=480, width=640),
+    "ucn": dict(pixel_decoder="SimpleBasePixelDecoder", decoder="PretrainedMeanShiftTransformerDecoder",
+                dec_layers=6, height=480, width=640),
+    "crop": dict(pixel_decoder="SimpleBasePixelDecoder", decoder="PretrainedMeanShiftTransformerDecoder",
+                 dec_layers=8, height=224, width=224),
+}
+
+
+def decoder_kwargs(dec_layers, num_queries=100):
+    return dict(num_classes=2, hidden_dim=256, num_queries=num_queries, nheads=8, dim_feedforward=2048,
+                dec_layers=dec_layers, pre_norm=False, mask_dim=256, enforce_input_project=False,
+                use_meanshift_cross_attention=True, disable_attention_mask=False,
+                use_meanshift_self_attention=True, decoder_block_norm=True)
+
+
+def build_head(kind, seed=0):
+    """-> PretrainedMeanShiftMaskFormerHead (CPU, eval) for workload ``kind``."""
+    from .meanshiftformer import modeling as M
+    cfg = HEAD_CFG[kind]
+    torch.manual_seed(seed)
+    if cfg["pixel_decoder"] == "MSDeformAttnPixelDecoder":
+        shapes = R50_SHAPES
+        pixel = M.MSDeformAttnPixelDecoder(shapes, transformer_dropout=0.0, transformer_nheads=8,
+                                           transformer_dim_feedforward=1024, transformer_enc_layers=6, conv_dim=64,
+                                           mask_dim=256, norm="GN", transformer_in_features=["res3", "res4", "res5"],
+                                           common_stride=4)
+    else:
+        shapes = {"res5": ShapeSpec(channels=64, stride=1)}
+        pixel = M.SimpleBasePixelDecoder(shapes, conv_dim=64, mask_dim=256, norm="GN")
+    decoder = getattr(M, cfg["decoder"])(64, True, **decoder_kwargs(cfg["dec_layers"]))
+    head = M.PretrainedMeanShiftMaskFormerHead(shapes, num_classes=2, pixel_decoder=pixel, loss_weight=1.0,
+                                               ignore_value=255, transformer_predictor=decoder,
+                                               transformer_in_feature="multi_scale_pixel_decoder")
+    return head.eval()
+
+
+def synthetic_features(kind, batch, seed=0, pin=False):
+    """Backbone outputs for ``batch`` images as CPU tensors (optionally pinned)."""
+    cfg = HEAD_CFG[kind]
+    g = torch.Generator().manual_seed(1000 + seed)
+    H, W = cfg["height"], cfg["width"]
+    if kind == "r50":
+        feats = {k: torch.randn(batch, s.channels, H // s.stride, W // s.stride, generator=g)
+                 for k, s in R50_SHAPES.items()}
+    else:  # unit-norm 64-d pixel embeddings (pretrained_meanshiftformer_model.py:298)
+        feats = {"res5": F.normalize(torch.randn(batch, 64, H, W, generator=g), p=2, dim=1)}
+    if pin:
+        feats = {k: v.pin_memory() for k, v in feats.items()}
+    return feats
+
+
+def oracle_kwargs(kind):
+    cfg = HEAD_CFG[kind]
+    kw = dict(pixel_decoder=cfg["pixel_decoder"], num_heads=8, dec_layers=cfg["dec_layers"])
+    if cfg["pixel_decoder"] == "MSDeformAttnPixelDecoder":
+        kw.update(pd_heads=8, pd_enc_layers=6)
+    return kw
+
+
+def head_flops_per_image(kind):
+    """Algorithmic FLOP of one head forward (SURVEY.md §8d, 2*MAC), for reporting only."""
+    cfg = HEAD_CFG[kind]
+    Q, C, h, ffn = 100, 256, 8, 2048
+    n = cfg["dec_layers"]
+    if kind == "r50":
+        keys = [300, 1200, 4800]
+        mh = mw_ = None
+        hw = 120 * 160
+        S = [keys[i % 3] for i in range(n)]
+        pix = 12.15e9 + 3.22e9
+    else:
+        hw = cfg["height"] * cfg["width"]
+        S = [hw] * n
+        pix = 2.0 * 9 * 64 * 256 * hw
+    f = pix
+    for s in S:
+        f += 4.0 * Q * s * C              # QK^T + AV
+        f += 2.0 * 2 * s * C * C          # K, V projections
+        f += 2.0 * Q * C * C * 2          # Q, out projections
+        f += 4.0 * Q * Q * C + 2.0 * Q * C * C * 4  # self attention
+        f += 2.0 * 2 * Q * C * ffn        # FFN
+    f += (n + 1) * (2.0 * Q * C * hw + 2.0 * Q * C * C * 3)  # mask head
+    f += sum(2.0 * s * 64 * C for s in set(S))  # input_proj
+    return f
