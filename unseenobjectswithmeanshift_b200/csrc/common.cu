@@ -1,4 +1,8 @@
 #include "common.cuh"
+#include "tc.cuh"
+
+#include <cudaTypedefs.h>
+#include <stdlib.h>
 
 namespace msm {
 
@@ -22,6 +26,53 @@ int num_sms() {
   }
   return cached[dev];
 }
+
+bool tc_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("MSM_DISABLE_TC");
+    cached = (e != nullptr && e[0] != '\0' && e[0] != '0') ? 0 : 1;
+  }
+  return cached == 1;
+}
+
+namespace tc {
+
+// cuTensorMapEncodeTiled is a driver entry point; fetching it through the runtime keeps
+// libmsmformer_b200.so free of a link-time libcuda dependency.
+int encode_tensor_map_f32(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box) {
+  static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  if (encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+      set_error("cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e));
+      return MSM_E_UNSUPPORTED;
+    }
+    encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  }
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i + 1 < rank) gstr[i] = strides_bytes[i];
+  }
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim,
+                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, inner dim %llu, box %u)", (int)r, rank,
+              (unsigned long long)dims[0], box[0]);
+    return MSM_E_BADARG;
+  }
+  return 0;
+}
+
+}  // namespace tc
 
 }  // namespace msm
 

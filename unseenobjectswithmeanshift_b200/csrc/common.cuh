@@ -40,6 +40,8 @@ inline int check_launch(const char* kernel) {
   } while (0)
 
 int num_sms();
+// false when MSM_DISABLE_TC is set: forces the fp32 CUDA-core kernels (cross-check of the tcgen05 paths)
+bool tc_enabled();
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

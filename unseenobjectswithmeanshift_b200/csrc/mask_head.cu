@@ -11,6 +11,9 @@
 
 namespace msm {
 
+int mask_logits_tc(const float* embed, const float* feat, float* masks, int B, int Q, int C, int64_t HW,
+                   cudaStream_t st);
+
 constexpr int BM = 128, BN = 64, BK = 16;
 constexpr int GEMM_THREADS = 256;
 
@@ -183,6 +186,10 @@ extern "C" int msm_mask_logits(const float* embed, const float* feat, float* mas
   MSM_REQUIRE(embed && feat && masks, "embed, feat, masks must be non-null");
   MSM_REQUIRE(B > 0 && Q > 0 && C > 0 && HW > 0, "sizes must be positive");
   MSM_REQUIRE(B <= 65535, "batch too large");
+  if (msm::tc_enabled()) {
+    const int rc = msm::mask_logits_tc(embed, feat, masks, B, Q, C, HW, static_cast<cudaStream_t>(stream));
+    if (rc != MSM_E_UNSUPPORTED) return rc;  // shapes outside the tensor-core kernel fall through to the CUDA-core GEMM
+  }
   const bool n_vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(feat) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(masks) & 15) == 0);
   dim3 grid((unsigned)((HW + msm::BN - 1) / msm::BN), (Q + msm::BM - 1) / msm::BM, B);

@@ -1,0 +1,279 @@
+// Mask head on the tcgen05 tensor cores: masks[b][q][p] = sum_c embed[b][q][c] * feat[b][c][p]
+// (einsum "bqc,bchw->bqhw", meanshiftformer_transformer_decoder.py:668 / :1020).
+//
+// The contraction is HBM-bound (per pixel: read C floats of mask_features, write Q logits), so the
+// kernel is organised around streaming `feat` exactly once at full TMA rate:
+//
+//   D^T[128 pixels x N queries] (TMEM, fp32) += F^T tile [128 px x 32 ch] (A, MN-major) * E[N x 32 ch] (B, K-major)
+//
+//   warp 0      TMA producer: 3-D tensor map over feat [B][C][HW], box 128 px x 32 ch, ring of fp32 stages
+//   warps 8-11  converters: fp32 stage -> bf16 hi/lo operand tiles in the UMMA canonical (no-swizzle) layout
+//   warp 1      MMA issuer: 3 tcgen05.mma per 16-channel step (hi*hi + lo*hi + hi*lo = fp32-grade product)
+//   warps 4-7   epilogue: tcgen05.ld of the accumulator (lane = pixel, column = query), coalesced
+//               128-byte stores into masks[b][q][p0..p0+31]; accumulators are double-buffered in TMEM
+//   warp 2      TMEM allocation
+//
+// `embed` of the CTA's image (<= 128 x 256) is split to bf16 hi/lo once and stays resident in
+// shared memory; every CTA works on the pixel tiles of ONE image (grid = B x CTAs-per-image).
+#include "common.cuh"
+#include "tc.cuh"
+
+#include <stdlib.h>
+
+namespace msm {
+
+namespace mtc {
+constexpr int kTeamWarps = 4;                   // converter warps per team; two teams work on alternate stages
+constexpr int kThreads = 256 + 2 * kTeamWarps * 32;
+constexpr int kPx = 128;                       // pixels per tile = UMMA M
+constexpr int kKc = 32;                        // channels per pipeline stage
+constexpr int kF32Stage = kKc * kPx * 4;       // 16 KB
+constexpr int kSboA = 144;                     // 128 B core matrix + 16 B pad: conflict-free converter stores
+constexpr int kLboA = (kPx / 8) * kSboA;       // 2304
+constexpr int kOpTile = (kKc / 8) * kLboA;     // 9216 bytes per hi (or lo) operand tile
+constexpr int kOpStages = 2;
+constexpr int kMaxSmem = 232448;
+
+struct Params {
+  const float* embed;  // [B][Q][C]
+  float* masks;        // [B][Q][HW]
+  int B, Q, C, N;      // N = Q rounded up to 16
+  int64_t HW;
+  int tiles_per_image, ctas_per_image, nstages;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+mask_gemm_tc_kernel(const __grid_constant__ CUtensorMap fmap, const Params P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkc = P.C / kKc;
+  const uint32_t lboB = (uint32_t)(P.N / 8) * 128u;       // K-group stride of the resident embed operand
+  const uint32_t eBytes = (uint32_t)(P.C / 8) * lboB;     // one of hi / lo
+
+  uint8_t* sF32 = smem;                                   // [nstages][32 ch][128 px] fp32 (TMA landing)
+  uint8_t* sOp = sF32 + P.nstages * kF32Stage;            // [2 stages][hi|lo][kOpTile]
+  uint8_t* sEhi = sOp + kOpStages * 2 * kOpTile;
+  uint8_t* sElo = sEhi + eBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sElo + eBytes);
+  uint64_t* full_f32 = bars;                              // [nstages] TMA -> converters
+  uint64_t* empty_f32 = full_f32 + 12;                     // [nstages] converters -> TMA
+  uint64_t* full_op = empty_f32 + 12;                      // [2] converters -> MMA
+  uint64_t* empty_op = full_op + 2;                       // [2] MMA -> converters
+  uint64_t* acc_full = empty_op + 2;                      // [2] MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;                     // [2] epilogue -> MMA
+  uint64_t* e_ready = acc_empty + 2;                      // embed operand resident (warps 2-7 -> MMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(e_ready + 1);
+
+  const int b = blockIdx.x / P.ctas_per_image;
+  const int slot = blockIdx.x % P.ctas_per_image;
+
+  if (threadIdx.x == 0) {
+    tc::tma_prefetch_desc(&fmap);
+    for (int i = 0; i < P.nstages; ++i) {
+      tc::mbar_init(&full_f32[i], 1);
+      tc::mbar_init(&empty_f32[i], kTeamWarps);
+    }
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&full_op[i], kTeamWarps);
+      tc::mbar_init(&empty_op[i], 1);
+      tc::mbar_init(&acc_full[i], 1);
+      tc::mbar_init(&acc_empty[i], 4);
+    }
+    tc::mbar_init(e_ready, 6);
+    tc::fence_mbar_init();
+  }
+  if (warp == 2) tc::tmem_alloc(tmem_slot, 256);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 2 && warp < 8) {
+    // ---- resident B operand: embed[b] -> bf16 hi/lo, K-major canonical layout (rows >= Q are zero).
+    // Done by the six warps that are idle until the first accumulator is ready, while the TMA /
+    // converter pipeline is already streaming mask_features.
+    const float* E = P.embed + (int64_t)b * P.Q * P.C;
+    const int items = P.N * (P.C / 8);
+    for (int it = threadIdx.x - 64; it < items; it += 192) {
+      const int n = it % P.N, kg = it / P.N;
+      float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+      if (n < P.Q) {
+        const float4* src = reinterpret_cast<const float4*>(E + (int64_t)n * P.C + kg * 8);
+        x0 = __ldg(src);
+        x1 = __ldg(src + 1);
+      }
+      uint4 hi, lo;
+      tc::split2(x0.x, x0.y, hi.x, lo.x);
+      tc::split2(x0.z, x0.w, hi.y, lo.y);
+      tc::split2(x1.x, x1.y, hi.z, lo.z);
+      tc::split2(x1.z, x1.w, hi.w, lo.w);
+      const uint32_t off = (uint32_t)(n & 7) * 16u + (uint32_t)(n >> 3) * 128u + (uint32_t)kg * lboB;
+      *reinterpret_cast<uint4*>(sEhi + off) = hi;
+      *reinterpret_cast<uint4*>(sElo + off) = lo;
+    }
+    tc::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(e_ready);
+  }
+
+  if (warp == 0) {
+    // =================================================================== TMA producer
+    if (lane == 0) {
+      tc::Ring fs;
+      for (int pt = slot; pt < P.tiles_per_image; pt += P.ctas_per_image) {
+        for (int kc = 0; kc < nkc; ++kc) {
+          tc::mbar_wait(&empty_f32[fs.stage], fs.phase ^ 1);
+          tc::mbar_arrive_expect_tx(&full_f32[fs.stage], kF32Stage);
+          tc::tma_load_3d(sF32 + fs.stage * kF32Stage, &fmap, &full_f32[fs.stage], pt * kPx, kc * kKc, b);
+          fs.advance(P.nstages);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = tc::idesc_bf16(kPx, P.N, /*A MN-major*/ true, /*B K-major*/ false);
+      const uint32_t ehi = tc::smem_u32(sEhi), elo = tc::smem_u32(sElo);
+      tc::Ring os;
+      int t = 0;
+      tc::mbar_wait(e_ready, 0);
+      for (int pt = slot; pt < P.tiles_per_image; pt += P.ctas_per_image, ++t) {
+        const int acc = t & 1;
+        tc::mbar_wait(&acc_empty[acc], ((t >> 1) & 1) ^ 1);
+        tc::tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)acc * 128u;
+        for (int kc = 0; kc < nkc; ++kc) {
+          tc::mbar_wait(&full_op[os.stage], os.phase);
+          tc::tc_fence_after();
+          const uint32_t ahi = tc::smem_u32(sOp + (os.stage * 2 + 0) * kOpTile);
+          const uint32_t alo = tc::smem_u32(sOp + (os.stage * 2 + 1) * kOpTile);
+#pragma unroll
+          for (int ks = 0; ks < kKc / 16; ++ks) {
+            const uint32_t aoff = (uint32_t)ks * 2u * kLboA;
+            const uint32_t boff = (uint32_t)(kc * (kKc / 8) + ks * 2) * lboB;
+            const uint64_t da_hi = tc::smem_desc(ahi + aoff, kLboA, kSboA);
+            const uint64_t da_lo = tc::smem_desc(alo + aoff, kLboA, kSboA);
+            const uint64_t db_hi = tc::smem_desc(ehi + boff, lboB, 128);
+            const uint64_t db_lo = tc::smem_desc(elo + boff, lboB, 128);
+            tc::mma_bf16_ss(d, da_lo, db_hi, idesc, (kc | ks) != 0);
+            tc::mma_bf16_ss(d, da_hi, db_lo, idesc, 1);
+            tc::mma_bf16_ss(d, da_hi, db_hi, idesc, 1);
+          }
+          tc::mma_commit(&empty_op[os.stage]);  // operand stage reusable once these MMAs retire
+          os.advance(kOpStages);
+        }
+        tc::mma_commit(&acc_full[acc]);
+      }
+    }
+  } else if (warp >= 8) {
+    // =================================================================== converters
+    // Two teams of kTeamWarps warps; team t converts the steps with (step & 1) == t into operand
+    // buffer t, so the per-stage latency chain (barrier wait -> LDS -> split -> STS -> proxy fence
+    // -> arrive) of one team overlaps with the other team's.
+    const int team = (warp - 8) / kTeamWarps, cw = (warp - 8) % kTeamWarps;
+    const int g = lane & 15;            // 8-pixel group within the tile
+    const int sw = (g >> 2) & 1;        // load-order swap: keeps the two 16-byte loads bank-conflict free
+    uint8_t* dhi = sOp + (team * 2 + 0) * kOpTile;
+    uint8_t* dlo = sOp + (team * 2 + 1) * kOpTile;
+    uint32_t step = 0;
+    for (int pt = slot; pt < P.tiles_per_image; pt += P.ctas_per_image) {
+      for (int kc = 0; kc < nkc; ++kc, ++step) {
+        if ((int)(step & 1u) != team) continue;
+        const uint32_t fstage = step % (uint32_t)P.nstages, fphase = (step / (uint32_t)P.nstages) & 1u;
+        tc::mbar_wait(&full_f32[fstage], fphase);
+        tc::mbar_wait(&empty_op[team], ((step >> 1) & 1u) ^ 1u);
+        const uint8_t* src = sF32 + fstage * kF32Stage;
+#pragma unroll
+        for (int it = 0; it < 16 / kTeamWarps; ++it) {
+          const int k = it * (2 * kTeamWarps) + cw * 2 + (lane >> 4);
+          const uint8_t* s = src + k * (kPx * 4) + g * 32;
+          const float4 c0 = *reinterpret_cast<const float4*>(s + (sw ? 16 : 0));
+          const float4 c1 = *reinterpret_cast<const float4*>(s + (sw ? 0 : 16));
+          const float4 x0 = sw ? c1 : c0, x1 = sw ? c0 : c1;
+          uint4 hi, lo;
+          tc::split2(x0.x, x0.y, hi.x, lo.x);
+          tc::split2(x0.z, x0.w, hi.y, lo.y);
+          tc::split2(x1.x, x1.y, hi.z, lo.z);
+          tc::split2(x1.z, x1.w, hi.w, lo.w);
+          const uint32_t off = (uint32_t)(k & 7) * 16u + (uint32_t)g * kSboA + (uint32_t)(k >> 3) * kLboA;
+          *reinterpret_cast<uint4*>(dhi + off) = hi;
+          *reinterpret_cast<uint4*>(dlo + off) = lo;
+        }
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tc::mbar_arrive(&full_op[team]);
+          tc::mbar_arrive(&empty_f32[fstage]);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // =================================================================== epilogue (lane quadrant = warp % 4)
+    const int q = warp - 4;
+    int t = 0;
+    for (int pt = slot; pt < P.tiles_per_image; pt += P.ctas_per_image, ++t) {
+      const int acc = t & 1;
+      tc::mbar_wait(&acc_full[acc], (t >> 1) & 1);
+      tc::tc_fence_after();
+      const int64_t pixel = (int64_t)pt * kPx + q * 32 + lane;
+      const bool in = pixel < P.HW;
+      float* orow = P.masks + (int64_t)b * P.Q * P.HW + pixel;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 128u;
+      for (int c = 0; c < P.N / 16; ++c) {
+        uint32_t r[16];
+        tc::tmem_ld16(taddr + c * 16, r);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int n = c * 16 + j;
+          if (in && n < P.Q) orow[(int64_t)n * P.HW] = __uint_as_float(r[j]);
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  if (warp == 2) tc::tmem_dealloc(tmem_base, 256);
+}
+
+}  // namespace mtc
+
+// returns 0 on success, MSM_E_UNSUPPORTED when the shape is outside what this kernel covers
+int mask_logits_tc(const float* embed, const float* feat, float* masks, int B, int Q, int C, int64_t HW,
+                   cudaStream_t st) {
+  using namespace mtc;
+  if (Q > 128 || C > 256 || C % kKc != 0 || HW % 4 != 0 || HW > 0x7fffffff ||
+      (reinterpret_cast<uintptr_t>(feat) & 15) || (reinterpret_cast<uintptr_t>(embed) & 15))
+    return MSM_E_UNSUPPORTED;
+  Params P;
+  P.embed = embed; P.masks = masks; P.B = B; P.Q = Q; P.C = C; P.HW = HW;
+  P.N = (Q + 15) / 16 * 16;
+  P.tiles_per_image = (int)((HW + kPx - 1) / kPx);
+  int cpi = num_sms() / B;
+  if (cpi < 1) cpi = 1;
+  if (cpi > P.tiles_per_image) cpi = P.tiles_per_image;
+  P.ctas_per_image = cpi;
+  const size_t fixed = (size_t)kOpStages * 2 * kOpTile + 2 * (size_t)(C / 8) * (P.N / 8) * 128 + 512;
+  P.nstages = 12;
+  if (const char* e = getenv("MSM_TC_STAGES")) P.nstages = atoi(e);
+  while (P.nstages > 2 && fixed + (size_t)P.nstages * kF32Stage > (size_t)kMaxSmem) --P.nstages;
+  const size_t smem = fixed + (size_t)P.nstages * kF32Stage;
+  if (smem > (size_t)kMaxSmem) return MSM_E_UNSUPPORTED;
+
+  CUtensorMap fmap;
+  const uint64_t dims[3] = {(uint64_t)HW, (uint64_t)C, (uint64_t)B};
+  const uint64_t strides[2] = {(uint64_t)HW * 4, (uint64_t)HW * C * 4};
+  const uint32_t box[3] = {(uint32_t)kPx, (uint32_t)kKc, 1};
+  int rc = tc::encode_tensor_map_f32(&fmap, feat, 3, dims, strides, box);
+  if (rc) return rc;
+  MSM_CUDA(cudaFuncSetAttribute(mask_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+  mask_gemm_tc_kernel<<<B * cpi, kThreads, smem, st>>>(fmap, P);
+  return check_launch("mask_gemm_tc_kernel");
+}
+
+}  // namespace msm
