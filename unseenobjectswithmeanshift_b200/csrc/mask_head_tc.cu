@@ -2,36 +2,39 @@
 // (einsum "bqc,bchw->bqhw", meanshiftformer_transformer_decoder.py:668 / :1020).
 //
 // The contraction is HBM-bound (per pixel: read C floats of mask_features, write Q logits), so the
-// kernel is organised around streaming `feat` exactly once at full TMA rate:
+// kernel is organised around streaming `feat` exactly once at TMA rate while keeping shared-memory
+// traffic (the next limiter: 128 B/clk/SM) low:
 //
-//   D^T[128 pixels x N queries] (TMEM, fp32) += F^T tile [128 px x 32 ch] (A, MN-major) * E[N x 32 ch] (B, K-major)
+//   D^T[128 pixels x N queries] (TMEM, fp32) += F^T tile [128 px x 32 ch] (A, in TMEM) * E[N x 32 ch] (B, smem, K-major)
 //
 //   warp 0      TMA producer: 3-D tensor map over feat [B][C][HW], box 128 px x 32 ch, ring of fp32 stages
-//   warps 8-11  converters: fp32 stage -> bf16 hi/lo operand tiles in the UMMA canonical (no-swizzle) layout
-//   warp 1      MMA issuer: 3 tcgen05.mma per 16-channel step (hi*hi + lo*hi + hi*lo = fp32-grade product)
+//   warps 8-15  converters, two teams of four warps on alternate stages: thread = pixel (TMEM lane),
+//               reads its 32 channel values (conflict-free LDS), splits them to bf16 hi/lo and writes
+//               them with tcgen05.st straight into the A-operand columns of TMEM - the streamed
+//               operand never goes back to shared memory
+//   warp 1      MMA issuer: 3 tcgen05.mma per 16-channel step (lo*hi + hi*lo + hi*hi = fp32-grade product)
 //   warps 4-7   epilogue: tcgen05.ld of the accumulator (lane = pixel, column = query), coalesced
 //               128-byte stores into masks[b][q][p0..p0+31]; accumulators are double-buffered in TMEM
-//   warp 2      TMEM allocation
+//   warps 2-7   prologue: `embed` of the CTA's image (<= 128 x 256) split to bf16 hi/lo once, resident
+//               in shared memory in the UMMA canonical K-major layout (overlaps the first TMA loads)
 //
-// `embed` of the CTA's image (<= 128 x 256) is split to bf16 hi/lo once and stays resident in
-// shared memory; every CTA works on the pixel tiles of ONE image (grid = B x CTAs-per-image).
+// Every CTA works on the pixel tiles of ONE image (grid = B x CTAs-per-image).
+// TMEM map (512 columns): [0,256) two accumulators; [256,384) four A stages of 16 hi + 16 lo columns.
 #include "common.cuh"
 #include "tc.cuh"
-
-#include <stdlib.h>
 
 namespace msm {
 
 namespace mtc {
-constexpr int kTeamWarps = 4;                   // converter warps per team; two teams work on alternate stages
-constexpr int kThreads = 256 + 2 * kTeamWarps * 32;
+constexpr int kTeams = 2;
+constexpr int kThreads = 256 + kTeams * 128;
 constexpr int kPx = 128;                       // pixels per tile = UMMA M
 constexpr int kKc = 32;                        // channels per pipeline stage
 constexpr int kF32Stage = kKc * kPx * 4;       // 16 KB
-constexpr int kSboA = 144;                     // 128 B core matrix + 16 B pad: conflict-free converter stores
-constexpr int kLboA = (kPx / 8) * kSboA;       // 2304
-constexpr int kOpTile = (kKc / 8) * kLboA;     // 9216 bytes per hi (or lo) operand tile
-constexpr int kOpStages = 2;
+constexpr int kAStages = 4;                    // A-operand stages in TMEM
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kTmemA = 256;               // first A column
+constexpr int kMaxStages = 8;
 constexpr int kMaxSmem = 232448;
 
 struct Params {
@@ -51,15 +54,14 @@ mask_gemm_tc_kernel(const __grid_constant__ CUtensorMap fmap, const Params P) {
   const uint32_t eBytes = (uint32_t)(P.C / 8) * lboB;     // one of hi / lo
 
   uint8_t* sF32 = smem;                                   // [nstages][32 ch][128 px] fp32 (TMA landing)
-  uint8_t* sOp = sF32 + P.nstages * kF32Stage;            // [2 stages][hi|lo][kOpTile]
-  uint8_t* sEhi = sOp + kOpStages * 2 * kOpTile;
+  uint8_t* sEhi = sF32 + P.nstages * kF32Stage;
   uint8_t* sElo = sEhi + eBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sElo + eBytes);
   uint64_t* full_f32 = bars;                              // [nstages] TMA -> converters
-  uint64_t* empty_f32 = full_f32 + 12;                     // [nstages] converters -> TMA
-  uint64_t* full_op = empty_f32 + 12;                      // [2] converters -> MMA
-  uint64_t* empty_op = full_op + 2;                       // [2] MMA -> converters
-  uint64_t* acc_full = empty_op + 2;                      // [2] MMA -> epilogue
+  uint64_t* empty_f32 = full_f32 + kMaxStages;            // [nstages] converters -> TMA
+  uint64_t* full_a = empty_f32 + kMaxStages;              // [kAStages] converters -> MMA
+  uint64_t* empty_a = full_a + kAStages;                  // [kAStages] MMA -> converters
+  uint64_t* acc_full = empty_a + kAStages;                // [2] MMA -> epilogue
   uint64_t* acc_empty = acc_full + 2;                     // [2] epilogue -> MMA
   uint64_t* e_ready = acc_empty + 2;                      // embed operand resident (warps 2-7 -> MMA)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(e_ready + 1);
@@ -71,45 +73,59 @@ mask_gemm_tc_kernel(const __grid_constant__ CUtensorMap fmap, const Params P) {
     tc::tma_prefetch_desc(&fmap);
     for (int i = 0; i < P.nstages; ++i) {
       tc::mbar_init(&full_f32[i], 1);
-      tc::mbar_init(&empty_f32[i], kTeamWarps);
+      tc::mbar_init(&empty_f32[i], 4);
+    }
+    for (int i = 0; i < kAStages; ++i) {
+      tc::mbar_init(&full_a[i], 4);
+      tc::mbar_init(&empty_a[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
-      tc::mbar_init(&full_op[i], kTeamWarps);
-      tc::mbar_init(&empty_op[i], 1);
       tc::mbar_init(&acc_full[i], 1);
       tc::mbar_init(&acc_empty[i], 4);
     }
     tc::mbar_init(e_ready, 6);
     tc::fence_mbar_init();
   }
-  if (warp == 2) tc::tmem_alloc(tmem_slot, 256);
+  if (warp == 2) tc::tmem_alloc(tmem_slot, kTmemCols);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= 2 && warp < 8) {
-    // ---- resident B operand: embed[b] -> bf16 hi/lo, K-major canonical layout (rows >= Q are zero).
-    // Done by the six warps that are idle until the first accumulator is ready, while the TMA /
-    // converter pipeline is already streaming mask_features.
+    // ---- resident B operand: embed[b] -> bf16 hi/lo, K-major canonical layout (rows >= Q are zero):
+    // element (n, k) at (k%8)*2 + (n%8)*16 + (n/8)*128 + (k/8)*lboB.
     const float* E = P.embed + (int64_t)b * P.Q * P.C;
     const int items = P.N * (P.C / 8);
-    for (int it = threadIdx.x - 64; it < items; it += 192) {
-      const int n = it % P.N, kg = it / P.N;
-      float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
-      if (n < P.Q) {
-        const float4* src = reinterpret_cast<const float4*>(E + (int64_t)n * P.C + kg * 8);
-        x0 = __ldg(src);
-        x1 = __ldg(src + 1);
+    constexpr int kBatch = 5;  // independent 32-byte loads in flight per thread (L2 latency ~1 us)
+    for (int it0 = threadIdx.x - 64; it0 < items; it0 += 192 * kBatch) {
+      float4 x0[kBatch], x1[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int it = it0 + u * 192;
+        const int n = it % P.N, kg = it / P.N;
+        x0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        x1[u] = x0[u];
+        if (it < items && n < P.Q) {
+          const float4* src = reinterpret_cast<const float4*>(E + (int64_t)n * P.C + kg * 8);
+          x0[u] = __ldg(src);
+          x1[u] = __ldg(src + 1);
+        }
       }
-      uint4 hi, lo;
-      tc::split2(x0.x, x0.y, hi.x, lo.x);
-      tc::split2(x0.z, x0.w, hi.y, lo.y);
-      tc::split2(x1.x, x1.y, hi.z, lo.z);
-      tc::split2(x1.z, x1.w, hi.w, lo.w);
-      const uint32_t off = (uint32_t)(n & 7) * 16u + (uint32_t)(n >> 3) * 128u + (uint32_t)kg * lboB;
-      *reinterpret_cast<uint4*>(sEhi + off) = hi;
-      *reinterpret_cast<uint4*>(sElo + off) = lo;
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int it = it0 + u * 192;
+        if (it >= items) break;
+        const int n = it % P.N, kg = it / P.N;
+        uint4 hi, lo;
+        tc::split2(x0[u].x, x0[u].y, hi.x, lo.x);
+        tc::split2(x0[u].z, x0[u].w, hi.y, lo.y);
+        tc::split2(x1[u].x, x1[u].y, hi.z, lo.z);
+        tc::split2(x1[u].z, x1[u].w, hi.w, lo.w);
+        const uint32_t off = (uint32_t)(n & 7) * 16u + (uint32_t)(n >> 3) * 128u + (uint32_t)kg * lboB;
+        *reinterpret_cast<uint4*>(sEhi + off) = hi;
+        *reinterpret_cast<uint4*>(sElo + off) = lo;
+      }
     }
     tc::fence_proxy_async();
     __syncwarp();
@@ -132,9 +148,9 @@ mask_gemm_tc_kernel(const __grid_constant__ CUtensorMap fmap, const Params P) {
   } else if (warp == 1) {
     // =================================================================== MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = tc::idesc_bf16(kPx, P.N, /*A MN-major*/ true, /*B K-major*/ false);
+      const uint32_t idesc = tc::idesc_bf16(kPx, P.N, /*A (TMEM) K-major*/ false, /*B K-major*/ false);
       const uint32_t ehi = tc::smem_u32(sEhi), elo = tc::smem_u32(sElo);
-      tc::Ring os;
+      tc::Ring as;
       int t = 0;
       tc::mbar_wait(e_ready, 0);
       for (int pt = slot; pt < P.tiles_per_image; pt += P.ctas_per_image, ++t) {
@@ -143,68 +159,53 @@ mask_gemm_tc_kernel(const __grid_constant__ CUtensorMap fmap, const Params P) {
         tc::tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)acc * 128u;
         for (int kc = 0; kc < nkc; ++kc) {
-          tc::mbar_wait(&full_op[os.stage], os.phase);
+          tc::mbar_wait(&full_a[as.stage], as.phase);
           tc::tc_fence_after();
-          const uint32_t ahi = tc::smem_u32(sOp + (os.stage * 2 + 0) * kOpTile);
-          const uint32_t alo = tc::smem_u32(sOp + (os.stage * 2 + 1) * kOpTile);
+          const uint32_t a_hi = tmem_base + kTmemA + as.stage * 32u, a_lo = a_hi + 16u;
 #pragma unroll
           for (int ks = 0; ks < kKc / 16; ++ks) {
-            const uint32_t aoff = (uint32_t)ks * 2u * kLboA;
             const uint32_t boff = (uint32_t)(kc * (kKc / 8) + ks * 2) * lboB;
-            const uint64_t da_hi = tc::smem_desc(ahi + aoff, kLboA, kSboA);
-            const uint64_t da_lo = tc::smem_desc(alo + aoff, kLboA, kSboA);
             const uint64_t db_hi = tc::smem_desc(ehi + boff, lboB, 128);
             const uint64_t db_lo = tc::smem_desc(elo + boff, lboB, 128);
-            tc::mma_bf16_ss(d, da_lo, db_hi, idesc, (kc | ks) != 0);
-            tc::mma_bf16_ss(d, da_hi, db_lo, idesc, 1);
-            tc::mma_bf16_ss(d, da_hi, db_hi, idesc, 1);
+            tc::mma_bf16_ts(d, a_lo + ks * 8u, db_hi, idesc, (kc | ks) != 0);
+            tc::mma_bf16_ts(d, a_hi + ks * 8u, db_lo, idesc, 1);
+            tc::mma_bf16_ts(d, a_hi + ks * 8u, db_hi, idesc, 1);
           }
-          tc::mma_commit(&empty_op[os.stage]);  // operand stage reusable once these MMAs retire
-          os.advance(kOpStages);
+          tc::mma_commit(&empty_a[as.stage]);  // A stage reusable once these MMAs retire
+          as.advance(kAStages);
         }
         tc::mma_commit(&acc_full[acc]);
       }
     }
   } else if (warp >= 8) {
     // =================================================================== converters
-    // Two teams of kTeamWarps warps; team t converts the steps with (step & 1) == t into operand
-    // buffer t, so the per-stage latency chain (barrier wait -> LDS -> split -> STS -> proxy fence
-    // -> arrive) of one team overlaps with the other team's.
-    const int team = (warp - 8) / kTeamWarps, cw = (warp - 8) % kTeamWarps;
-    const int g = lane & 15;            // 8-pixel group within the tile
-    const int sw = (g >> 2) & 1;        // load-order swap: keeps the two 16-byte loads bank-conflict free
-    uint8_t* dhi = sOp + (team * 2 + 0) * kOpTile;
-    uint8_t* dlo = sOp + (team * 2 + 1) * kOpTile;
+    // Team t takes the steps with step % kTeams == t. Thread = pixel row of the tile = TMEM lane
+    // (a warp may only touch the lane quadrant warp % 4). For kind::f16 the A operand in TMEM holds
+    // two consecutive K elements per 32-bit column (even k in the low half).
+    const int team = (warp - 8) >> 2, q = warp & 3;
+    const int px = q * 32 + lane;
     uint32_t step = 0;
     for (int pt = slot; pt < P.tiles_per_image; pt += P.ctas_per_image) {
       for (int kc = 0; kc < nkc; ++kc, ++step) {
-        if ((int)(step & 1u) != team) continue;
+        if ((int)(step % kTeams) != team) continue;
         const uint32_t fstage = step % (uint32_t)P.nstages, fphase = (step / (uint32_t)P.nstages) & 1u;
+        const uint32_t astage = step % kAStages, aphase = (step / kAStages) & 1u;
         tc::mbar_wait(&full_f32[fstage], fphase);
-        tc::mbar_wait(&empty_op[team], ((step >> 1) & 1u) ^ 1u);
-        const uint8_t* src = sF32 + fstage * kF32Stage;
+        const float* src = reinterpret_cast<const float*>(sF32 + fstage * kF32Stage) + px;
+        uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int it = 0; it < 16 / kTeamWarps; ++it) {
-          const int k = it * (2 * kTeamWarps) + cw * 2 + (lane >> 4);
-          const uint8_t* s = src + k * (kPx * 4) + g * 32;
-          const float4 c0 = *reinterpret_cast<const float4*>(s + (sw ? 16 : 0));
-          const float4 c1 = *reinterpret_cast<const float4*>(s + (sw ? 0 : 16));
-          const float4 x0 = sw ? c1 : c0, x1 = sw ? c0 : c1;
-          uint4 hi, lo;
-          tc::split2(x0.x, x0.y, hi.x, lo.x);
-          tc::split2(x0.z, x0.w, hi.y, lo.y);
-          tc::split2(x1.x, x1.y, hi.z, lo.z);
-          tc::split2(x1.z, x1.w, hi.w, lo.w);
-          const uint32_t off = (uint32_t)(k & 7) * 16u + (uint32_t)g * kSboA + (uint32_t)(k >> 3) * kLboA;
-          *reinterpret_cast<uint4*>(dhi + off) = hi;
-          *reinterpret_cast<uint4*>(dlo + off) = lo;
-        }
-        tc::fence_proxy_async();
+        for (int j = 0; j < 16; ++j) tc::split2(src[(2 * j) * kPx], src[(2 * j + 1) * kPx], hi[j], lo[j]);
         __syncwarp();
-        if (lane == 0) {
-          tc::mbar_arrive(&full_op[team]);
-          tc::mbar_arrive(&empty_f32[fstage]);
-        }
+        if (lane == 0) tc::mbar_arrive(&empty_f32[fstage]);  // fp32 stage consumed (values are in registers)
+        tc::mbar_wait(&empty_a[astage], aphase ^ 1u);
+        tc::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kTmemA + astage * 32u;
+        tc::tmem_st16(taddr, hi);
+        tc::tmem_st16(taddr + 16u, lo);
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&full_a[astage]);
       }
     }
   } else if (warp >= 4) {
@@ -238,7 +239,7 @@ mask_gemm_tc_kernel(const __grid_constant__ CUtensorMap fmap, const Params P) {
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  if (warp == 2) tc::tmem_dealloc(tmem_base, 256);
+  if (warp == 2) tc::tmem_dealloc(tmem_base, kTmemCols);
 }
 
 }  // namespace mtc
@@ -258,9 +259,8 @@ int mask_logits_tc(const float* embed, const float* feat, float* masks, int B, i
   if (cpi < 1) cpi = 1;
   if (cpi > P.tiles_per_image) cpi = P.tiles_per_image;
   P.ctas_per_image = cpi;
-  const size_t fixed = (size_t)kOpStages * 2 * kOpTile + 2 * (size_t)(C / 8) * (P.N / 8) * 128 + 512;
-  P.nstages = 12;
-  if (const char* e = getenv("MSM_TC_STAGES")) P.nstages = atoi(e);
+  const size_t fixed = 2 * (size_t)(C / 8) * (P.N / 8) * 128 + 512;
+  P.nstages = kMaxStages;
   while (P.nstages > 2 && fixed + (size_t)P.nstages * kF32Stage > (size_t)kMaxSmem) --P.nstages;
   const size_t smem = fixed + (size_t)P.nstages * kF32Stage;
   if (smem > (size_t)kMaxSmem) return MSM_E_UNSUPPORTED;
