@@ -19,7 +19,7 @@
 //               in shared memory in the UMMA canonical K-major layout (overlaps the first TMA loads)
 //
 // Every CTA works on the pixel tiles of ONE image (grid = B x CTAs-per-image).
-// TMEM map (512 columns): [0,256) two accumulators; [256,384) four A stages of 16 hi + 16 lo columns.
+// TMEM map (512 columns): [0,384) three accumulators; [384,512) four A stages of 16 hi + 16 lo columns.
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -33,7 +33,8 @@ constexpr int kKc = 32;                        // channels per pipeline stage
 constexpr int kF32Stage = kKc * kPx * 4;       // 16 KB
 constexpr int kAStages = 4;                    // A-operand stages in TMEM
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kTmemA = 256;               // first A column
+constexpr uint32_t kTmemA = 384;               // first A column
+constexpr int kAcc = 3;                        // accumulator buffers (128 columns each)
 constexpr int kMaxStages = 8;
 constexpr int kMaxSmem = 232448;
 
@@ -61,9 +62,9 @@ mask_gemm_tc_kernel(const __grid_constant__ CUtensorMap fmap, const Params P) {
   uint64_t* empty_f32 = full_f32 + kMaxStages;            // [nstages] converters -> TMA
   uint64_t* full_a = empty_f32 + kMaxStages;              // [kAStages] converters -> MMA
   uint64_t* empty_a = full_a + kAStages;                  // [kAStages] MMA -> converters
-  uint64_t* acc_full = empty_a + kAStages;                // [2] MMA -> epilogue
-  uint64_t* acc_empty = acc_full + 2;                     // [2] epilogue -> MMA
-  uint64_t* e_ready = acc_empty + 2;                      // embed operand resident (warps 2-7 -> MMA)
+  uint64_t* acc_full = empty_a + kAStages;                // [kAcc] MMA -> epilogue
+  uint64_t* acc_empty = acc_full + kAcc;                  // [kAcc] epilogue -> MMA
+  uint64_t* e_ready = acc_empty + kAcc;                      // embed operand resident (warps 2-7 -> MMA)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(e_ready + 1);
 
   const int b = blockIdx.x / P.ctas_per_image;
@@ -79,7 +80,7 @@ mask_gemm_tc_kernel(const __grid_constant__ CUtensorMap fmap, const Params P) {
       tc::mbar_init(&full_a[i], 4);
       tc::mbar_init(&empty_a[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kAcc; ++i) {
       tc::mbar_init(&acc_full[i], 1);
       tc::mbar_init(&acc_empty[i], 4);
     }
@@ -154,8 +155,8 @@ mask_gemm_tc_kernel(const __grid_constant__ CUtensorMap fmap, const Params P) {
       int t = 0;
       tc::mbar_wait(e_ready, 0);
       for (int pt = slot; pt < P.tiles_per_image; pt += P.ctas_per_image, ++t) {
-        const int acc = t & 1;
-        tc::mbar_wait(&acc_empty[acc], ((t >> 1) & 1) ^ 1);
+        const int acc = t % kAcc;
+        tc::mbar_wait(&acc_empty[acc], ((t / kAcc) & 1) ^ 1);
         tc::tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)acc * 128u;
         for (int kc = 0; kc < nkc; ++kc) {
@@ -210,29 +211,53 @@ mask_gemm_tc_kernel(const __grid_constant__ CUtensorMap fmap, const Params P) {
     }
   } else if (warp >= 4) {
     // =================================================================== epilogue (lane quadrant = warp % 4)
+    // The accumulator is pulled into registers in two halves and handed back to the MMA warp
+    // BEFORE the global stores are issued, so the store latency never holds a TMEM buffer.
     const int q = warp - 4;
     int t = 0;
     for (int pt = slot; pt < P.tiles_per_image; pt += P.ctas_per_image, ++t) {
-      const int acc = t & 1;
-      tc::mbar_wait(&acc_full[acc], (t >> 1) & 1);
+      const int acc = t % kAcc;
+      tc::mbar_wait(&acc_full[acc], (t / kAcc) & 1);
       tc::tc_fence_after();
       const int64_t pixel = (int64_t)pt * kPx + q * 32 + lane;
       const bool in = pixel < P.HW;
       float* orow = P.masks + (int64_t)b * P.Q * P.HW + pixel;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 128u;
-      for (int c = 0; c < P.N / 16; ++c) {
-        uint32_t r[16];
-        tc::tmem_ld16(taddr + c * 16, r);
-        tc::tmem_ld_wait();
+      const int nchunk = (P.N + 31) / 32;  // 32-column chunks holding queries
+      uint32_t r0[32], r1[32];
+      // first half (queries 0..63): load, then store while the second half is being fetched
+      tc::tmem_ld32(taddr, r0);
+      if (nchunk > 1) tc::tmem_ld32(taddr + 32, r1);
+      tc::tmem_ld_wait();
+      if (nchunk <= 2) {
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
+      }
+      if (in) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int n = c * 16 + j;
-          if (in && n < P.Q) orow[(int64_t)n * P.HW] = __uint_as_float(r[j]);
+        for (int j = 0; j < 32; ++j)
+          if (j < P.Q) orow[(int64_t)j * P.HW] = __uint_as_float(r0[j]);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (32 + j < P.Q) orow[(int64_t)(32 + j) * P.HW] = __uint_as_float(r1[j]);
+      }
+      if (nchunk > 2) {
+        tc::tmem_ld32(taddr + 64, r0);
+        if (nchunk > 3) tc::tmem_ld32(taddr + 96, r1);
+        tc::tmem_ld_wait();
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
+        if (in) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (64 + j < P.Q) orow[(int64_t)(64 + j) * P.HW] = __uint_as_float(r0[j]);
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (96 + j < P.Q) orow[(int64_t)(96 + j) * P.HW] = __uint_as_float(r1[j]);
         }
       }
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
     }
   }
 
