@@ -9,7 +9,7 @@
 #include "common.cuh"
 
 namespace msm {
-int vmf_attention_simt(const float* q, int64_t q_sb, int64_t q_sh, int64_t q_sl, const float* k, int64_t k_sb,
+int vmf_attention(const float* q, int64_t q_sb, int64_t q_sh, int64_t q_sl, const float* k, int64_t k_sb,
                        int64_t k_sh, int64_t k_sl, const float* v, int64_t v_sb, int64_t v_sh, int64_t v_sl,
                        float* out, int64_t o_sb, int64_t o_sh, int64_t o_sl, float* den, const uint32_t* bits,
                        int wpr, const int32_t* row_open, const float* add_mask, int batch, int heads, int Nq, int Ns,
@@ -35,7 +35,7 @@ extern "C" int msm_mean_shift_hill_climb(const float* X, const float* Z0, float*
   }
   const float* zin = Z0;
   for (int it = 0; it < max_iters; ++it) {
-    const int rc = msm::vmf_attention_simt(zin, (int64_t)m * d, 0, d, X, (int64_t)n * d, 0, d, X, (int64_t)n * d, 0, d,
+    const int rc = msm::vmf_attention(zin, (int64_t)m * d, 0, d, X, (int64_t)n * d, 0, d, X, (int64_t)n * d, 0, d,
                                            Z_out, (int64_t)m * d, 0, d, nullptr, nullptr, 0, nullptr, nullptr, B, 1, m,
                                            n, d, kappa, 0, workspace, workspace_bytes, st);
     if (rc) return rc;

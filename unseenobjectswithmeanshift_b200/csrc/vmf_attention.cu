@@ -7,8 +7,9 @@
 // denominator [Nq]; key ranges are split across CTAs and summed in a fixed order by the finalize
 // kernel (deterministic - no atomics). The [G,Nq,Ns] score matrix is never materialised.
 //
-// This file is the fp32 CUDA-core path: exact fp32 products, used for every head size and as the
-// cross-check for the tcgen05 path (vmf_attention_tc.cu).
+// This file holds the fp32 CUDA-core path (exact fp32 products, any head size <= 128, any strides,
+// additive masks) - the cross-check of the tcgen05 path in vmf_attention_tc.cu and the kernel for the
+// shapes that one does not take - plus the finalize kernel and the dispatcher both share.
 #include "common.cuh"
 
 namespace msm {
@@ -287,6 +288,17 @@ __global__ void vmf_weights_kernel(const float* __restrict__ q, int64_t q_sb, in
   }
 }
 
+static int launch_finalize(const float* part_acc, const float* part_den, float* out, int64_t o_sb, int64_t o_sh,
+                           int64_t o_sl, float* den, int G, int heads, int Nq, int hd, int HD, int nsplit,
+                           cudaStream_t st) {
+  const int warps = G * Nq;
+  const int threads = 256;
+  const int blocks = (warps * 32 + threads - 1) / threads;
+  vmf_finalize_kernel<<<blocks, threads, 0, st>>>(part_acc, part_den, out, o_sb, o_sh, o_sl, den, G, heads, Nq, hd, HD,
+                                                  nsplit);
+  return check_launch("vmf_finalize_kernel");
+}
+
 static int pad_hd(int hd) {
   for (int p = 8; p <= 128; p <<= 1)
     if (hd <= p) return p;
@@ -351,20 +363,58 @@ int vmf_attention_simt(const float* q, int64_t q_sb, int64_t q_sh, int64_t q_sl,
     default: set_error("head dim %d not supported (max 128)", hd); return MSM_E_UNSUPPORTED;
   }
   if (rc) return rc;
-  const int warps = G * Nq;
-  const int threads = 256;
-  const int blocks = (warps * 32 + threads - 1) / threads;
-  vmf_finalize_kernel<<<blocks, threads, 0, st>>>(P.part_acc, P.part_den, out, o_sb, o_sh, o_sl, den, G, heads, Nq, hd,
-                                                  HD, P.nsplit);
-  return check_launch("vmf_finalize_kernel");
+  return launch_finalize(P.part_acc, P.part_den, out, o_sb, o_sh, o_sl, den, G, heads, Nq, hd, HD, P.nsplit, st);
 }
+
+// tensor-core path (vmf_attention_tc.cu)
+bool vmf_tc_supported(const float* q, int64_t q_sb, int64_t q_sh, int64_t q_sl, const float* k, int64_t k_sb,
+                      int64_t k_sh, int64_t k_sl, const float* v, int64_t v_sb, int64_t v_sh, int64_t v_sl,
+                      const float* add_mask, int Nq, int hd);
+size_t vmf_tc_workspace_bytes(int G, int Nq, int Ns, int hd);
+int vmf_attention_tc_partial(const float* q, int64_t q_sb, int64_t q_sh, int64_t q_sl, const float* k, int64_t k_sb,
+                             int64_t k_sh, int64_t k_sl, const float* v, int64_t v_sb, int64_t v_sh, int64_t v_sl,
+                             const uint32_t* bits, int wpr, const int32_t* row_open, int batch, int heads, int Nq,
+                             int Ns, int hd, float kappa, int flags, float* part_acc, float* part_den, int* nsplit_out,
+                             cudaStream_t st);
 
 size_t vmf_workspace_bytes(int batch, int heads, int Nq, int Ns, int hd) {
   const int HD = pad_hd(hd);
   if (HD < 0 || batch <= 0 || heads <= 0 || Nq <= 0 || Ns <= 0) return 0;
   int nqt, nsplit, tps;
   plan_splits(batch * heads, Nq, Ns, &nqt, &nsplit, &tps);
-  return (size_t)batch * heads * nsplit * Nq * (HD + 1) * sizeof(float);
+  size_t need = (size_t)batch * heads * nsplit * Nq * (HD + 1) * sizeof(float);
+  if (Nq <= 128 && (hd == 32 || hd == 64)) {
+    const size_t tc_need = vmf_tc_workspace_bytes(batch * heads, Nq, Ns, hd);
+    if (tc_need > need) need = tc_need;
+  }
+  return need;
+}
+
+// tcgen05 kernel when the shape/strides allow it, fp32 CUDA-core kernel otherwise (same library, same algorithm)
+int vmf_attention(const float* q, int64_t q_sb, int64_t q_sh, int64_t q_sl, const float* k, int64_t k_sb, int64_t k_sh,
+                  int64_t k_sl, const float* v, int64_t v_sb, int64_t v_sh, int64_t v_sl, float* out, int64_t o_sb,
+                  int64_t o_sh, int64_t o_sl, float* den, const uint32_t* bits, int wpr, const int32_t* row_open,
+                  const float* add_mask, int batch, int heads, int Nq, int Ns, int hd, float kappa, int flags,
+                  void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (tc_enabled() && vmf_tc_supported(q, q_sb, q_sh, q_sl, k, k_sb, k_sh, k_sl, v, v_sb, v_sh, v_sl, add_mask, Nq, hd)) {
+    const int G = batch * heads;
+    const size_t need = vmf_tc_workspace_bytes(G, Nq, Ns, hd);
+    if (workspace == nullptr || workspace_bytes < need) {
+      set_error("vmf attention workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+      return MSM_E_WORKSPACE;
+    }
+    float* part_acc = static_cast<float*>(workspace);
+    float* part_den = part_acc + need / sizeof(float) / (hd + 1) * hd;
+    int nsplit = 0;
+    const int rc = vmf_attention_tc_partial(q, q_sb, q_sh, q_sl, k, k_sb, k_sh, k_sl, v, v_sb, v_sh, v_sl, bits, wpr,
+                                            row_open, batch, heads, Nq, Ns, hd, kappa, flags, part_acc, part_den,
+                                            &nsplit, st);
+    if (rc) return rc;
+    return launch_finalize(part_acc, part_den, out, o_sb, o_sh, o_sl, den, G, heads, Nq, hd, hd, nsplit, st);
+  }
+  return vmf_attention_simt(q, q_sb, q_sh, q_sl, k, k_sb, k_sh, k_sl, v, v_sb, v_sh, v_sl, out, o_sb, o_sh, o_sl, den,
+                            bits, wpr, row_open, add_mask, batch, heads, Nq, Ns, hd, kappa, flags, workspace,
+                            workspace_bytes, st);
 }
 
 }  // namespace msm
@@ -385,9 +435,9 @@ extern "C" int msm_vmf_attention_fwd(const float* q, int64_t q_sb, int64_t q_sh,
   MSM_REQUIRE(hd <= 128, "hd must be <= 128");
   MSM_REQUIRE(!(blocked_bits && add_mask), "pass blocked_bits or add_mask, not both");
   MSM_REQUIRE(!blocked_bits || words_per_row * 32 >= Ns, "words_per_row too small for Ns");
-  return msm::vmf_attention_simt(q, q_sb, q_sh, q_sl, k, k_sb, k_sh, k_sl, v, v_sb, v_sh, v_sl, out, o_sb, o_sh, o_sl,
-                                 den, blocked_bits, words_per_row, row_open, add_mask, batch, heads, Nq, Ns, hd, kappa,
-                                 flags, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+  return msm::vmf_attention(q, q_sb, q_sh, q_sl, k, k_sb, k_sh, k_sl, v, v_sb, v_sh, v_sl, out, o_sb, o_sh, o_sl, den,
+                            blocked_bits, words_per_row, row_open, add_mask, batch, heads, Nq, Ns, hd, kappa, flags,
+                            workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int msm_vmf_attention_weights(const float* q, int64_t q_sb, int64_t q_sh, int64_t q_sl, const float* k,
