@@ -95,6 +95,24 @@ int msm_mask_to_attn_bits(const float* masks, uint32_t* bits, int32_t* row_open,
                           int B, int Q, int H, int W, int Ht, int Wt, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Dense layer  Y[M][N] = act( X[M][K] . W[N][K]^T + bias[N] ),  act: 0 = identity, 1 = ReLU.
+ * Replaces the torch.nn.functional.linear calls of the hot path: the packed q/k/v in-projection
+ *   ms_in_projection_packed (transformer_decoder/attention_util.py:84-140), FFNLayer / MLP
+ *   (meanshiftformer_transformer_decoder.py:300-304, :329-341) and the projections + FFN of the deformable
+ *   encoder (pixel_decoder/ops/modules/ms_deform_attn.py:96-124, pixel_decoder/msdeformattn.py:76-84).
+ * The weight is converted ONCE (msm_linear_prepare_weight) into the layout the tensor-core kernel streams:
+ *   bf16 [hi|lo][K/8][N][8]; `prepared` must hold msm_linear_weight_bytes(N, K) bytes, 128-byte aligned.
+ * X rows start every ldx floats, Y rows every ldy floats (both multiples of 4, 16-byte aligned bases), so
+ * column slices of wider buffers are addressed in place. N and K must be multiples of 32.
+ * ---------------------------------------------------------------------------------------------- */
+size_t msm_linear_weight_bytes(int N, int K);
+
+int msm_linear_prepare_weight(const float* W, int64_t ldw, void* prepared, int N, int K, void* stream);
+
+int msm_linear_fwd(const float* X, int64_t ldx, const void* prepared, const float* bias, float* Y, int64_t ldy,
+                   int M, int N, int K, int act, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Multi-scale deformable attention, forward.
  * Replaces MultiScaleDeformableAttention.ms_deform_attn_forward(value, spatial_shapes,
  *   level_start_index, sampling_loc, attn_weight, im2col_step)

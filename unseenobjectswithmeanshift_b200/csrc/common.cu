@@ -40,8 +40,7 @@ namespace tc {
 
 // cuTensorMapEncodeTiled is a driver entry point; fetching it through the runtime keeps
 // libmsmformer_b200.so free of a link-time libcuda dependency.
-int encode_tensor_map_f32(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                          const uint64_t* strides_bytes, const uint32_t* box) {
+static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
   static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
   if (encode == nullptr) {
     void* fn = nullptr;
@@ -49,10 +48,17 @@ int encode_tensor_map_f32(CUtensorMap* map, const void* base, int rank, const ui
     cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
     if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr) {
       set_error("cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e));
-      return MSM_E_UNSUPPORTED;
+      return nullptr;
     }
     encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
   }
+  return encode;
+}
+
+int encode_tensor_map(CUtensorMap* map, TmapType type, TmapSwizzle swizzle, const void* base, int rank,
+                      const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+  PFN_cuTensorMapEncodeTiled_v12000 encode = tensor_map_encoder();
+  if (encode == nullptr) return MSM_E_UNSUPPORTED;
   cuuint64_t gdim[5], gstr[4];
   cuuint32_t bdim[5], estr[5];
   for (int i = 0; i < rank; ++i) {
@@ -61,15 +67,21 @@ int encode_tensor_map_f32(CUtensorMap* map, const void* base, int rank, const ui
     estr[i] = 1;
     if (i + 1 < rank) gstr[i] = strides_bytes[i];
   }
-  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim,
-                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = encode(map, type == TmapType::F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                      (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      swizzle == TmapSwizzle::B128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, inner dim %llu, box %u)", (int)r, rank,
               (unsigned long long)dims[0], box[0]);
     return MSM_E_BADARG;
   }
   return 0;
+}
+
+int encode_tensor_map_f32(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box) {
+  return encode_tensor_map(map, TmapType::F32, TmapSwizzle::None, base, rank, dims, strides_bytes, box);
 }
 
 }  // namespace tc

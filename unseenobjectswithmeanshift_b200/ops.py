@@ -141,6 +141,64 @@ def unpack_attn_bits(bits, row_open, num_keys, num_heads):
     return blocked.unsqueeze(1).repeat(1, num_heads, 1, 1).flatten(0, 1)
 
 
+# prepared (bf16 hi/lo) copies of weights, keyed by the fp32 tensor's storage + version
+_PREPARED = {}
+
+
+def prepare_linear_weight(weight):
+    """fp32 weight [N, K] (rows 16-byte aligned) -> cached uint8 buffer in the kernel's streaming layout."""
+    w = _require(weight, "weight")
+    if w.dim() != 2 or w.stride(1) != 1:
+        raise ValueError("weight must be a [N, K] matrix with contiguous rows")
+    key = (w.data_ptr(), tuple(w.shape), w.stride(0), w._version, w.device.index)
+    buf = _PREPARED.get(key)
+    if buf is None:
+        if len(_PREPARED) > 4096:
+            _PREPARED.clear()
+        N, K = w.shape
+        L = _lib.lib()
+        buf = torch.empty(L.msm_linear_weight_bytes(N, K), device=w.device, dtype=torch.uint8)
+        check(L.msm_linear_prepare_weight(w.data_ptr(), w.stride(0), buf.data_ptr(), N, K, _stream()),
+              "msm_linear_prepare_weight")
+        _PREPARED[key] = buf
+    return buf
+
+
+def linear_supported(x, weight):
+    """True when msm_linear_fwd takes this layer (N, K multiples of 32, aligned fp32 CUDA rows)."""
+    return (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and weight.dim() == 2
+            and weight.shape[0] % 32 == 0 and weight.shape[1] % 32 == 0 and weight.stride(1) == 1
+            and weight.stride(0) % 4 == 0 and weight.data_ptr() % 16 == 0 and x.shape[-1] == weight.shape[1])
+
+
+def linear(x, weight, bias=None, relu=False, out=None):
+    """act(x @ weight.T + bias) on the tensor cores (bf16x3 split precision, fp32 accumulate).
+    x [..., K] whose leading axes collapse to uniformly strided rows; weight [N, K]; returns [..., N]."""
+    _require(x, "x")
+    N, K = weight.shape
+    if x.shape[-1] != K:
+        raise ValueError(f"x {tuple(x.shape)} does not match weight {tuple(weight.shape)}")
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, K)  # a view whenever the rows are uniformly strided
+    if x2.stride(1) != 1 or x2.stride(0) % 4 != 0 or x2.data_ptr() % 16 != 0:
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    if out is None:
+        out = torch.empty(*lead, N, device=x.device, dtype=torch.float32)
+    y2 = out.view(-1, N) if out.is_contiguous() else out
+    if y2.dim() != 2 or y2.shape != (M, N) or y2.stride(1) != 1:
+        raise ValueError("out must be a [M, N] matrix with contiguous rows")
+    wp = prepare_linear_weight(weight)
+    b = None
+    if bias is not None:
+        b = _require(bias, "bias").contiguous()
+    if M > 0:
+        rc = _lib.lib().msm_linear_fwd(x2.data_ptr(), x2.stride(0), wp.data_ptr(), b.data_ptr() if b is not None else None,
+                                       y2.data_ptr(), y2.stride(0), M, N, K, 1 if relu else 0, _stream())
+        check(rc, "msm_linear_fwd")
+    return out
+
+
 def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step=128):
     """Same signature and result as MultiScaleDeformableAttention.ms_deform_attn_forward
     (pixel_decoder/ops/src/ms_deform_attn.h:25-45): returns [N, Lq, M*D]."""
@@ -251,6 +309,7 @@ vmf_attention = _instrument("vmf_attention", 2)(vmf_attention)
 vmf_attention_weights = _instrument("vmf_attention_weights", 1)(vmf_attention_weights)
 mask_logits = _instrument("mask_logits", 1)(mask_logits)
 mask_to_attn_bits = _instrument("mask_to_attn_bits", 1)(mask_to_attn_bits)
+linear = _instrument("linear", 1)(linear)
 ms_deform_attn_forward = _instrument("ms_deform_attn_forward", 1)(ms_deform_attn_forward)
 ms_deform_attn_backward = _instrument("ms_deform_attn_backward", 1)(ms_deform_attn_backward)
 mean_shift_hill_climb = _instrument("mean_shift_hill_climb", lambda X, Z, kappa, max_iters=10: 2 * int(max_iters))(
