@@ -32,6 +32,14 @@ def msm():
     return ns
 
 
+# Shapes the tcgen05 attention kernel takes (hd 32/64, <= 128 queries) are computed in bf16x3 split
+# precision: each product carries ~2^-17 relative error (fp32: 2^-24) and kappa = 30 multiplies the
+# score error inside the exponential, so unit-norm outputs agree to a few 1e-5 instead of a few 1e-6
+# (the fp32 CUDA-core kernel, MSM_DISABLE_TC=1, meets 2e-5 on the same inputs: tools/dev_vmf_tc.py).
+TC_ATTN_TOL = 1e-4
+SIMT_ATTN_TOL = 2e-5
+
+
 def peak_rel(a, b):
     return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
 
@@ -96,7 +104,8 @@ def test_vmf_attention_bits_vs_oracle(msm, B, H, Q, S, hd):
         out = msm.ops.vmf_attention(hv(q), hv(k), hv(v), blocked_bits=_pack_bits(blocked).cuda(),
                                     row_open=row_open.cuda())
     got = out.permute(0, 2, 1, 3).reshape(B, Q, C).cpu()
-    assert (got - ref).abs().max().item() < 2e-5  # unit vectors: absolute == relative-to-peak
+    tol = TC_ATTN_TOL if (hd in (32, 64) and Q <= 128) else SIMT_ATTN_TOL
+    assert (got - ref).abs().max().item() < tol  # unit vectors: absolute == relative-to-peak
     torch.testing.assert_close(got.view(B, Q, H, hd).norm(dim=-1), torch.ones(B, Q, H), rtol=0, atol=1e-5)
     # unpack helper reproduces the reference's bool mask after the un-mask rule
     un = msm.ops.unpack_attn_bits(_pack_bits(blocked).cuda(), row_open.cuda(), S, H).cpu()
@@ -116,7 +125,7 @@ def test_vmf_attention_config2_full_size(msm):
     with torch.no_grad():
         out = msm.ops.vmf_attention(hv(q), hv(k), hv(v))
     got = out.reshape(B * H, Q, hd).cpu()
-    assert (got - ref).abs().max().item() < 2e-5
+    assert (got - ref).abs().max().item() < TC_ATTN_TOL
 
 
 def test_meanshift_attention_module_golden(msm, golden):

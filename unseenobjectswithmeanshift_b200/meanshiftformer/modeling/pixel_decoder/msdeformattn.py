@@ -11,6 +11,7 @@ from torch import nn
 from torch.nn import functional as F
 from torch.nn.init import normal_
 
+from .... import ops
 from ....d2compat import SEM_SEG_HEADS_REGISTRY, Conv2d, ShapeSpec, c2_xavier_fill, configurable, get_norm
 from ....precision import conv_precision
 from ..transformer_decoder.position_encoding import PositionEmbeddingSine
@@ -36,6 +37,9 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
         return tensor if pos is None else tensor + pos
 
     def forward_ffn(self, src):
+        if self.activation is F.relu and not self.training:
+            h = ops.dense(src, self.linear1.weight, self.linear1.bias, relu=True)
+            return self.norm2(src + ops.dense(h, self.linear2.weight, self.linear2.bias))
         return self.norm2(src + self.dropout3(self.linear2(self.dropout2(self.activation(self.linear1(src))))))
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):

@@ -13,6 +13,7 @@ from torch import nn
 from torch.nn import functional as F
 from torch.nn.init import constant_, xavier_uniform_
 
+from ...... import ops
 from ..functions import MSDeformAttnFunction
 
 
@@ -63,12 +64,20 @@ class MSDeformAttn(nn.Module):
         S = input_flatten.shape[1]
         assert int((input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum()) == S
         M, L, P = self.n_heads, self.n_levels, self.n_points
-        value = self.value_proj(input_flatten)
+        value = ops.dense(input_flatten, self.value_proj.weight, self.value_proj.bias)
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], float(0))
         value = value.view(N, S, M, self.d_model // M)
-        offsets = self.sampling_offsets(query).view(N, Lq, M, L, P, 2)
-        weights = F.softmax(self.attention_weights(query).view(N, Lq, M, L * P), -1).view(N, Lq, M, L, P)
+        # offsets and attention logits share their input: one GEMM over the concatenated weights
+        n_off = M * L * P * 2
+        w_ow = ops.cached_cat(self, "w_ow", [self.sampling_offsets.weight, self.attention_weights.weight])
+        b_ow = ops.cached_cat(self, "b_ow", [self.sampling_offsets.bias, self.attention_weights.bias])
+        if torch.is_grad_enabled() and self.sampling_offsets.weight.requires_grad:
+            ow = torch.cat([self.sampling_offsets(query), self.attention_weights(query)], -1)
+        else:
+            ow = ops.dense(query, w_ow, b_ow)
+        offsets = ow[..., :n_off].reshape(N, Lq, M, L, P, 2)
+        weights = F.softmax(ow[..., n_off:].reshape(N, Lq, M, L * P), -1).view(N, Lq, M, L, P)
         if reference_points.shape[-1] == 2:
             wh = torch.stack([input_spatial_shapes[..., 1], input_spatial_shapes[..., 0]], -1)
             locations = reference_points[:, :, None, :, None, :] + offsets / wh[None, None, None, :, None, :]
@@ -80,4 +89,4 @@ class MSDeformAttn(nn.Module):
                 "Last dim of reference_points must be 2 or 4, but get {} instead.".format(reference_points.shape[-1]))
         output = MSDeformAttnFunction.apply(value.contiguous(), input_spatial_shapes, input_level_start_index,
                                             locations.contiguous(), weights.contiguous(), self.im2col_step)
-        return self.output_proj(output)
+        return ops.dense(output, self.output_proj.weight, self.output_proj.bias)

@@ -172,7 +172,11 @@ class FFNLayer(nn.Module):
         if self.normalize_before:
             t2 = self.norm(tgt)
             return tgt + self.dropout(self.linear2(self.dropout(self.activation(self.linear1(t2)))))
-        t2 = self.linear2(self.dropout(self.activation(self.linear1(tgt))))
+        if self.activation is F.relu and not self.training:
+            t2 = ops.dense(ops.dense(tgt, self.linear1.weight, self.linear1.bias, relu=True),
+                           self.linear2.weight, self.linear2.bias)
+        else:
+            t2 = self.linear2(self.dropout(self.activation(self.linear1(tgt))))
         return self.norm(tgt + self.dropout(t2))
 
 
@@ -187,7 +191,7 @@ class MLP(nn.Module):
 
     def forward(self, x):
         for i, layer in enumerate(self.layers):
-            x = F.relu(layer(x)) if i < self.num_layers - 1 else layer(x)
+            x = ops.dense(x, layer.weight, layer.bias, relu=i < self.num_layers - 1)
         return x
 
 
@@ -331,7 +335,7 @@ class _MeanShiftDecoderBase(nn.Module):
             xl = x[l].float().flatten(2).transpose(1, 2)  # [B,S,Cin]
             proj = self.input_proj[l]
             if isinstance(proj, nn.Conv2d):
-                s = F.linear(xl, proj.weight.flatten(1), proj.bias + self.level_embed.weight[l])
+                s = F.linear(xl, proj.weight.flatten(1), proj.bias + self.level_embed.weight[l])  # xl is a transposed view
             else:
                 s = xl + self.level_embed.weight[l]
             src.append(s)
@@ -343,12 +347,13 @@ class _MeanShiftDecoderBase(nn.Module):
 
         def project_kv(level, layer_ids):
             attn = [self.transformer_cross_attention_layers[i].meanshift_attn for i in layer_ids]
-            wk = torch.cat([a.in_proj_weight[C:2 * C] for a in attn], 0)
-            bk = torch.cat([a.in_proj_bias[C:2 * C] for a in attn], 0)
-            wv = torch.cat([a.in_proj_weight[2 * C:] for a in attn], 0)
-            bv = torch.cat([a.in_proj_bias[2 * C:] for a in attn], 0)
-            K = F.linear(key_in[level], wk, bk)  # [B,S,n*C]
-            V = F.linear(src[level], wv, bv)
+            tag = "kv%d_%s" % (level, "_".join(map(str, layer_ids)))
+            wk = ops.cached_cat(self, tag + "wk", [a.in_proj_weight[C:2 * C] for a in attn])
+            bk = ops.cached_cat(self, tag + "bk", [a.in_proj_bias[C:2 * C] for a in attn])
+            wv = ops.cached_cat(self, tag + "wv", [a.in_proj_weight[2 * C:] for a in attn])
+            bv = ops.cached_cat(self, tag + "bv", [a.in_proj_bias[2 * C:] for a in attn])
+            K = ops.dense(key_in[level], wk, bk)  # [B,S,n*C]
+            V = ops.dense(src[level], wv, bv)
             for j, i in enumerate(layer_ids):
                 kv[i] = (K[..., j * C:(j + 1) * C], V[..., j * C:(j + 1) * C])
 
@@ -377,20 +382,20 @@ class _MeanShiftDecoderBase(nn.Module):
             # cross-attention (reference :245-260), post-norm
             ca = self.transformer_cross_attention_layers[i]
             a = ca.meanshift_attn
-            q = F.linear(out + query_pos, a.in_proj_weight[:C], a.in_proj_bias[:C])
+            q = ops.dense(out + query_pos, a.in_proj_weight[:C], a.in_proj_bias[:C])
             o = torch.empty(B, self.num_queries, C, device=dev, dtype=torch.float32)
             ops.vmf_attention(heads_view(q), heads_view(K), heads_view(V), blocked_bits=bits, row_open=row_open,
                               out=heads_view(o))
-            out = ca.norm(out + a.out_proj(o))
+            out = ca.norm(out + ops.dense(o, a.out_proj.weight, a.out_proj.bias))
             del K, V
             # self-attention (reference :171-181): q = k = out + query_pos, v = out
             sl = self.transformer_self_attention_layers[i]
             a = sl.self_attn
-            qk = F.linear(out + query_pos, a.in_proj_weight[:2 * C], a.in_proj_bias[:2 * C])
-            v = F.linear(out, a.in_proj_weight[2 * C:], a.in_proj_bias[2 * C:])
+            qk = ops.dense(out + query_pos, a.in_proj_weight[:2 * C], a.in_proj_bias[:2 * C])
+            v = ops.dense(out, a.in_proj_weight[2 * C:], a.in_proj_bias[2 * C:])
             o = torch.empty(B, self.num_queries, C, device=dev, dtype=torch.float32)
             ops.vmf_attention(heads_view(qk[..., :C]), heads_view(qk[..., C:]), heads_view(v), out=heads_view(o))
-            out = sl.norm(out + a.out_proj(o))
+            out = sl.norm(out + ops.dense(o, a.out_proj.weight, a.out_proj.bias))
             # FFN (reference :300-304) and block norm (:637-638)
             out = self.transformer_ffn_layers[i](out)
             if self.decoder_block_norm:

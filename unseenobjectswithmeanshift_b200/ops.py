@@ -199,6 +199,32 @@ def linear(x, weight, bias=None, relu=False, out=None):
     return out
 
 
+def dense(x, weight, bias=None, relu=False):
+    """The layer call the modules use: tensor-core ``linear`` for inference on shapes it takes,
+    torch's F.linear (cuBLAS fp32, autograd-capable) when gradients are needed or N/K are not
+    multiples of 32 (e.g. the 3-way class head)."""
+    if not x.is_cuda:
+        raise RuntimeError("x must be a CUDA tensor: unseenobjectswithmeanshift_b200 has no CPU path")
+    needs_grad = torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad
+                                              or (bias is not None and bias.requires_grad))
+    if needs_grad or not linear_supported(x, weight):
+        y = torch.nn.functional.linear(x, weight, bias)
+        return torch.relu_(y) if relu else y
+    return linear(x, weight.detach(), None if bias is None else bias.detach(), relu=relu)
+
+
+def cached_cat(owner, name, tensors, dim=0):
+    """torch.cat(tensors, dim) cached on ``owner`` until any source tensor is modified in place or
+    replaced (keeps concatenated projection weights - and their prepared copies - stable across calls)."""
+    key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
+    cache = owner.__dict__.setdefault("_msm_cat_cache", {})
+    hit = cache.get(name)
+    if hit is None or hit[0] != key:
+        hit = (key, torch.cat([t.detach() for t in tensors], dim).contiguous())
+        cache[name] = hit
+    return hit[1]
+
+
 def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step=128):
     """Same signature and result as MultiScaleDeformableAttention.ms_deform_attn_forward
     (pixel_decoder/ops/src/ms_deform_attn.h:25-45): returns [N, Lq, M*D]."""
