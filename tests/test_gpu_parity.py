@@ -391,7 +391,8 @@ def test_mean_shift_config4_size_properties(msm):
         # a data set made of one direction is a fixed point
         u = F.normalize(torch.randn(1, d, generator=g), dim=1)
         Zu = msm.ops.mean_shift_hill_climb(u.repeat(5000, 1).cuda(), Z0[:7].cuda(), 10.0, 2)
-        assert (Zu.cpu() - u).abs().max().item() < 1e-6
+        # (bf16x3 operands represent u to ~2^-17 relative per component, hence not 1e-7)
+        assert (Zu.cpu() - u).abs().max().item() < 5e-6
     ref = oms.seed_hill_climbing_ball(X, Z0, 10.0, 10)
     assert (Z.cpu() - ref).abs().max().item() < 1e-4
 

@@ -68,9 +68,12 @@ class MSDeformAttnTransformerEncoder(nn.Module):
         ref = torch.cat(pts, 1)
         return ref[:, :, None] * valid_ratios[:, None]
 
-    def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None):
+    def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None,
+                reference_points=None):
         out = src
-        ref = self.get_reference_points(spatial_shapes, valid_ratios, device=src.device)
+        ref = reference_points
+        if ref is None:
+            ref = self.get_reference_points(spatial_shapes, valid_ratios, device=src.device)
         for layer in self.layers:
             out = layer(out, pos, ref, spatial_shapes, level_start_index, padding_mask)
         return out
@@ -97,19 +100,34 @@ class MSDeformAttnTransformerEncoderOnly(nn.Module):
                 m._reset_parameters()
         normal_(self.level_embed)
 
+    def _geometry(self, shapes, batch, device):
+        """Device-side constants of a feature pyramid (level shapes, level starts, pixel-centre reference
+        points), built once per (shapes, batch, device): no host<->device traffic on later calls, which also
+        keeps the forward capturable in a CUDA graph."""
+        key = (shapes, batch, str(device))
+        cache = self.__dict__.setdefault("_geom_cache", {})
+        if key not in cache:
+            spatial_shapes = torch.as_tensor(shapes, dtype=torch.long, device=device)
+            starts = [0]
+            for h, w in shapes[:-1]:
+                starts.append(starts[-1] + h * w)
+            level_start_index = torch.as_tensor(starts, dtype=torch.long, device=device)
+            valid_ratios = torch.ones(batch, len(shapes), 2, dtype=torch.float32, device=device)
+            ref = self.encoder.get_reference_points(spatial_shapes, valid_ratios, device)
+            cache[key] = (spatial_shapes, level_start_index, valid_ratios, ref)
+        return cache[key]
+
     def forward(self, srcs, pos_embeds):
         """srcs / pos_embeds: per-level [B,C,H,W], coarse to fine. No padding: valid ratios are 1."""
         B = srcs[0].shape[0]
         dev = srcs[0].device
-        shapes = [tuple(s.shape[-2:]) for s in srcs]
+        shapes = tuple((int(s.shape[-2]), int(s.shape[-1])) for s in srcs)
         src = torch.cat([s.flatten(2).transpose(1, 2) for s in srcs], 1)
         pos = torch.cat([p.flatten(2).transpose(1, 2) + self.level_embed[l].view(1, 1, -1)
                          for l, p in enumerate(pos_embeds)], 1)
-        spatial_shapes = torch.as_tensor(shapes, dtype=torch.long, device=dev)
-        level_start_index = torch.cat((spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
-        valid_ratios = torch.ones(B, len(srcs), 2, dtype=torch.float32, device=dev)
-        memory = self.encoder(src, spatial_shapes, level_start_index, valid_ratios, pos, None)
-        return memory, spatial_shapes, level_start_index
+        spatial_shapes, level_start_index, valid_ratios, ref = self._geometry(shapes, B, dev)
+        memory = self.encoder(src, spatial_shapes, level_start_index, valid_ratios, pos, None, reference_points=ref)
+        return memory, shapes, level_start_index
 
 
 @SEM_SEG_HEADS_REGISTRY.register()
@@ -188,11 +206,10 @@ class MSDeformAttnPixelDecoder(nn.Module):
                 x = features[f].float()
                 srcs.append(self.input_proj[idx](x))
                 pos.append(self.pe_layer(x))
-            y, spatial_shapes, level_start_index = self.transformer(srcs, pos)
+            y, shapes, level_start_index = self.transformer(srcs, pos)
             B = y.shape[0]
-            sizes = [int(h * w) for h, w in spatial_shapes.tolist()]
-            out = [z.transpose(1, 2).reshape(B, -1, *spatial_shapes[i].tolist())
-                   for i, z in enumerate(torch.split(y, sizes, dim=1))]
+            sizes = [h * w for h, w in shapes]
+            out = [z.transpose(1, 2).reshape(B, -1, *shapes[i]) for i, z in enumerate(torch.split(y, sizes, dim=1))]
             for idx, f in enumerate(self.in_features[:self.num_fpn_levels][::-1]):
                 cur = self.lateral_convs[idx](features[f].float())
                 up = F.interpolate(out[-1], size=cur.shape[-2:], mode="bilinear", align_corners=False)

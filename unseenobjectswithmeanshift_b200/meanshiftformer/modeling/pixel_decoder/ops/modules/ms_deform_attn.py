@@ -62,7 +62,8 @@ class MSDeformAttn(nn.Module):
         input_spatial_shapes int64 [L,2]; input_level_start_index int64 [L] -> [N,Lq,C]."""
         N, Lq, _ = query.shape
         S = input_flatten.shape[1]
-        assert int((input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum()) == S
+        if not torch.cuda.is_current_stream_capturing():  # the check reads the device (not capturable)
+            assert int((input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum()) == S
         M, L, P = self.n_heads, self.n_levels, self.n_points
         value = ops.dense(input_flatten, self.value_proj.weight, self.value_proj.bias)
         if input_padding_mask is not None:

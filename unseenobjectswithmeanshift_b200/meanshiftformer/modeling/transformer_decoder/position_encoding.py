@@ -43,10 +43,16 @@ class PositionEmbeddingSine(nn.Module):
 
     def table(self, height, width, device):
         """[H*W, 2*npf] rows in raster order: the same values as forward(...).flatten(2).T for one image."""
+        key = ("full", height, width, str(device))
+        if key in self._cache:
+            return self._cache[key]
         ty, tx = self.tables(height, width, device)
         npf = self.num_pos_feats
-        return torch.cat((ty[:, None, :].expand(height, width, npf), tx[None, :, :].expand(height, width, npf)),
-                         dim=2).reshape(height * width, 2 * npf)
+        t = torch.cat((ty[:, None, :].expand(height, width, npf), tx[None, :, :].expand(height, width, npf)),
+                      dim=2).reshape(height * width, 2 * npf)
+        if t.numel() * 4 <= (64 << 20):  # keep small tables; the full-resolution one (315 MB) is rebuilt per call
+            self._cache[key] = t
+        return t
 
     def forward(self, x, mask=None):
         if mask is not None:  # padded batches: the reference's cumsum formulation

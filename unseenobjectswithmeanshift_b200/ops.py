@@ -4,6 +4,8 @@ PyTorch here is plumbing: it owns device memory and the CUDA stream; every funct
 raw device pointers + sizes to libmsmformer_b200.so and enqueues on torch's current stream.
 All functions require CUDA fp32 tensors and raise otherwise - there is no CPU path.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -141,8 +143,16 @@ def unpack_attn_bits(bits, row_open, num_keys, num_heads):
     return blocked.unsqueeze(1).repeat(1, num_heads, 1, 1).flatten(0, 1)
 
 
-# prepared (bf16 hi/lo) copies of weights, keyed by the fp32 tensor's storage + version
+# prepared (bf16 hi/lo) copies of weights, keyed by the fp32 tensor's address + shape + version. Each entry
+# keeps a reference to its source tensor, so the address cannot be recycled by the allocator while the
+# entry lives (a freed-and-reused address with the same version would otherwise be a stale hit).
 _PREPARED = {}
+
+
+def clear_prepared_weights():
+    """Drop all prepared weight copies (call after editing weights through ``.data`` - in-place ops on the
+    parameter itself, load_state_dict and optimizer steps are tracked by the tensor version)."""
+    _PREPARED.clear()
 
 
 def prepare_linear_weight(weight):
@@ -151,21 +161,25 @@ def prepare_linear_weight(weight):
     if w.dim() != 2 or w.stride(1) != 1:
         raise ValueError("weight must be a [N, K] matrix with contiguous rows")
     key = (w.data_ptr(), tuple(w.shape), w.stride(0), w._version, w.device.index)
-    buf = _PREPARED.get(key)
-    if buf is None:
-        if len(_PREPARED) > 4096:
+    hit = _PREPARED.get(key)
+    if hit is not None:
+        return hit[0]
+    if True:
+        if len(_PREPARED) > 1024:
             _PREPARED.clear()
         N, K = w.shape
         L = _lib.lib()
         buf = torch.empty(L.msm_linear_weight_bytes(N, K), device=w.device, dtype=torch.uint8)
         check(L.msm_linear_prepare_weight(w.data_ptr(), w.stride(0), buf.data_ptr(), N, K, _stream()),
               "msm_linear_prepare_weight")
-        _PREPARED[key] = buf
+        _PREPARED[key] = (buf, w)
     return buf
 
 
 def linear_supported(x, weight):
     """True when msm_linear_fwd takes this layer (N, K multiples of 32, aligned fp32 CUDA rows)."""
+    if os.environ.get("MSM_DISABLE_TC_LINEAR", "") not in ("", "0"):
+        return False
     return (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and weight.dim() == 2
             and weight.shape[0] % 32 == 0 and weight.shape[1] % 32 == 0 and weight.stride(1) == 1
             and weight.stride(0) % 4 == 0 and weight.data_ptr() % 16 == 0 and x.shape[-1] == weight.shape[1])
@@ -220,7 +234,8 @@ def cached_cat(owner, name, tensors, dim=0):
     cache = owner.__dict__.setdefault("_msm_cat_cache", {})
     hit = cache.get(name)
     if hit is None or hit[0] != key:
-        hit = (key, torch.cat([t.detach() for t in tensors], dim).contiguous())
+        # the sources are kept referenced so their addresses stay unique while the entry lives
+        hit = (key, torch.cat([t.detach() for t in tensors], dim).contiguous(), list(tensors))
         cache[name] = hit
     return hit[1]
 
