@@ -177,6 +177,7 @@ def main():
         torch.cuda.synchronize()
         launches_per_step = ops.launches() // n_eager
         op_ms = {k: (c / n_eager, t / n_eager) for k, (c, t) in ops.op_times_ms().items()}
+        op_groups = ops.op_groups()
         ops.reset_stats(timing=False)
 
         # ---------------- the step as ONE CUDA graph (static input / output buffers)
@@ -232,29 +233,37 @@ def main():
     if rank != 0:
         return
 
-    # ---------------- roofline of the dominant kernel of this library
+    # ---------------- roofline of the dominant kernel of this library: the (kernel, shape) group with the
+    # largest device time per step; achieved = algorithmic bytes (or flops) of its launches / their duration
     peaks = load_peaks()
-    dom = max(op_ms.items(), key=lambda kv: kv[1][1]) if op_ms else None
     roofline = None
-    if dom is not None:
-        tag, (cnt, tot) = dom
-        avg_ms = tot / cnt
-        roofline = {"kernel": tag, "avg_launch_ms": avg_ms, "launches_per_step": cnt,
-                    "share_of_step": tot / (ms_dev / args.steps), "traffic": None,
-                    "timing": "CUDA events around each library call in an eager pass of the same step"}
-        if tag == "mask_logits":
-            hw = (H // 4) * (W // 4) if kind == "r50" else H * W
-            by = 4.0 * B * (256 * hw + 100 * hw + 100 * 256)  # read mask_features + embed, write logits
-            ach = by / (avg_ms * 1e-3) / 1e9
-            roofline.update({"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                             "frac": ach / peaks["hbm_gbs"], "peak_source": peaks["source"],
-                             "algorithmic_bytes_per_launch": by})
-        elif tag == "vmf_attention":
-            roofline.update({"bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None,
-                             "peak_source": peaks["source"], "note": "mixed key lengths; see op_ms"})
+    if op_groups:
+        (tag, sig), g = max(op_groups.items(), key=lambda kv: kv[1]["ms"])
+        per = g["count"] / n_eager
+        avg_ms = g["ms"] / g["count"]
+        gbs = g["bytes"] / g["ms"] / 1e6
+        tfs = g["flops"] / g["ms"] / 1e9
+        # HBM-bound unless the arithmetic intensity (x3 tensor passes of the bf16 split) exceeds the ridge
+        ridge = peaks["bf16_tflops"] * 1e3 / peaks["hbm_gbs"]
+        tensor_bound = g["bytes"] > 0 and 3.0 * g["flops"] / g["bytes"] > ridge
+        roofline = {"kernel": tag, "shape": sig, "launches_per_step": per, "avg_launch_ms": avg_ms,
+                    "share_of_step": (g["ms"] / n_eager) / (ms_dev / args.steps),
+                    "algorithmic_bytes_per_launch": g["bytes"] / g["count"],
+                    "algorithmic_flops_per_launch": g["flops"] / g["count"], "traffic": None,
+                    "timing": "CUDA events around each library call, eager pass of the same step (same stream)",
+                    "peak_source": peaks["source"]}
+        if tensor_bound:
+            roofline.update({"bound": "tensor", "achieved": 3.0 * tfs, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                             "frac": 3.0 * tfs / peaks["bf16_tflops"],
+                             "note": "bf16 tensor passes issued (3 per fp32-grade product)"})
         else:
-            roofline.update({"bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None,
-                             "peak_source": peaks["source"]})
+            roofline.update({"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": gbs / peaks["hbm_gbs"]})
+        top = sorted(op_groups.items(), key=lambda kv: -kv[1]["ms"])[:8]
+        roofline["top_groups"] = [{"kernel": t, "shape": sg, "launches_per_step": v["count"] / n_eager,
+                                   "ms_per_step": v["ms"] / n_eager,
+                                   "GBps": v["bytes"] / v["ms"] / 1e6 if v["ms"] else None,
+                                   "TFLOPps": v["flops"] / v["ms"] / 1e9 if v["ms"] else None} for (t, sg), v in top]
     op_summary = {k: {"calls_per_step": c, "ms_per_step": t} for k, (c, t) in op_ms.items()}
 
     # ---------------- CPU baseline (oracle port) on a bounded sample, rank 0, N == 1 only

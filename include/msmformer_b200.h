@@ -127,6 +127,16 @@ int msm_ms_deform_attn_fwd(const float* value, const int64_t* spatial_shapes, co
                            const float* sampling_loc, const float* attn_weight, float* out,
                            int N, int S, int M, int D, int L, int Lq, int P, int im2col_step, void* stream);
 
+/* Fused sampling stage of MSDeformAttn.forward (pixel_decoder/ops/modules/ms_deform_attn.py:96-121): the
+ * softmax over the L*P attention logits of each head, sampling_locations = reference_points[l] +
+ * offsets / (W_l, H_l)  (reference_points with last dim 2, :103-106) and the op above, in one kernel.
+ * offsets_logits: one row of ld_ol floats per (n, query): [M*L*P*2 raw sampling offsets (m,l,p,xy) |
+ * M*L*P raw attention logits (m,l,p)], i.e. the outputs of the two projections side by side;
+ * reference_points [N][Lq][L][2] (x, y in [0,1]). */
+int msm_ms_deform_attn_fused_fwd(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                 const float* offsets_logits, int64_t ld_ol, const float* reference_points,
+                                 float* out, int N, int S, int M, int D, int L, int Lq, int P, void* stream);
+
 /* backward of the above (ms_deform_attn.h:47-67, cuda/ms_deform_attn_cuda.cu:88-158): grads are
  * ACCUMULATED into grad_value (caller zero-fills), grad_sampling_loc and grad_attn_weight are written. */
 int msm_ms_deform_attn_bwd(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,

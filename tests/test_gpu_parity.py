@@ -192,8 +192,14 @@ def _check_decoder(out, g, n_aux, tol=1e-3):
     for i, a in enumerate(out["aux_outputs"]):
         assert peak_rel(a["pred_logits"].cpu(), g[f"aux{i}_pred_logits"]) < tol
         assert peak_rel(a["pred_masks"].cpu(), g[f"aux{i}_pred_masks"]) < tol
-    # instance labels: per-pixel argmax over queries, bit-exact
-    assert torch.equal(out["pred_masks"].cpu().argmax(1), g["pred_masks"].argmax(1))
+    # instance labels: per-pixel argmax over queries, bit-exact wherever the reference's own decision is not
+    # a tie at the logit tolerance (top-2 margin above tol x peak); ties may go either way within tol
+    ref = g["pred_masks"]
+    top2 = ref.topk(2, dim=1).values
+    decided = (top2[:, 0] - top2[:, 1]) > tol * ref.abs().max()
+    same = out["pred_masks"].cpu().argmax(1) == ref.argmax(1)
+    assert bool(same[decided].all())
+    assert same.float().mean().item() > 0.995
 
 
 def test_decoder_multiscale_golden(msm, golden):

@@ -1,6 +1,6 @@
 """Run one hot-path op at a BASELINE.json size a few times - the command ncu wraps.
 
-    python tools/prof_ops.py mask_r50|mask_ucn|vmf_r50|vmf_ucn|meanshift|msda [--iters N]
+    python tools/prof_ops.py mask_r50|mask_ucn|vmf_r50|vmf_ucn|meanshift|msda|linear_kv|linear_ffn1|linear_ffn2|linear_ucn [--iters N]
 """
 import argparse
 import os
@@ -48,6 +48,12 @@ def main():
             loc = torch.rand(N, S, M, L, P, 2, device=dev, generator=g)
             aw = torch.softmax(rn(N, S, M, L * P), -1).view(N, S, M, L, P)
             fn = lambda: ops.ms_deform_attn_forward(value, shapes, lsi, loc, aw)  # noqa: E731
+        elif a.what in ("linear_kv", "linear_ffn1", "linear_ffn2", "linear_ucn"):
+            M, N, K = {"linear_kv": (38400, 768, 256), "linear_ffn1": (50400, 1024, 64),
+                       "linear_ffn2": (50400, 64, 1024), "linear_ucn": (307200, 256, 256)}[a.what]
+            x, w, b = rn(M, K), rn(N, K) / K ** 0.5, rn(N)
+            out = torch.empty(M, N, device=dev)
+            fn = lambda: ops.linear(x, w, b, out=out)  # noqa: E731
         else:
             raise SystemExit(f"unknown op {a.what}")
         for _ in range(a.iters):

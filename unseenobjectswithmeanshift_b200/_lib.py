@@ -29,6 +29,7 @@ SIGNATURES = {
     "msm_linear_prepare_weight": (_I, [_P, _L, _P, _I, _I, _P]),
     "msm_linear_fwd": (_I, [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _P]),
     "msm_ms_deform_attn_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "msm_ms_deform_attn_fused_fwd": (_I, [_P, _P, _P, _P, _L, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "msm_ms_deform_attn_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "msm_mean_shift_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "msm_mean_shift_hill_climb": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _I, _P, _Z, _P]),

@@ -112,6 +112,88 @@ __global__ void __launch_bounds__(256) msda_fwd_kernel(const float* __restrict__
   }
 }
 
+// Fused form of MSDeformAttn.forward's sampling stage (pixel_decoder/ops/modules/ms_deform_attn.py:96-121):
+// takes the RAW outputs of the sampling_offsets / attention_weights projections (one row per query:
+// [M*L*P*2 offsets | M*L*P logits]) and the reference points, and does in registers what the reference does
+// in five elementwise passes over [N,Lq,M,L,P,2] tensors:  weights = softmax_{l,p}(logits),
+// loc = ref[l] + offset / (W_l, H_l)  (same operation order as the reference, so the sampled pixel
+// coordinates are the same floats), then the bilinear gather of the op itself.
+template <int VEC>
+__global__ void __launch_bounds__(256) msda_fused_fwd_kernel(const float* __restrict__ value,
+                                                             const int64_t* __restrict__ shapes,
+                                                             const int64_t* __restrict__ lsi,
+                                                             const float* __restrict__ ol, int64_t ld_ol,
+                                                             const float* __restrict__ ref, float* __restrict__ out,
+                                                             int64_t total, int S, int M, int D, int L, int Lq, int P) {
+  __shared__ int sH[kMaxLevels], sW[kMaxLevels], sStart[kMaxLevels];
+  if (threadIdx.x < L) {
+    sH[threadIdx.x] = (int)shapes[2 * threadIdx.x];
+    sW[threadIdx.x] = (int)shapes[2 * threadIdx.x + 1];
+    sStart[threadIdx.x] = (int)lsi[threadIdx.x];
+  }
+  __syncthreads();
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int DV = D / VEC;
+  const int dv = (int)(idx % DV);
+  int64_t t = idx / DV;
+  const int m = (int)(t % M);
+  t /= M;  // t = b*Lq + q
+  const int b = (int)(t / Lq);
+  const int LP = L * P;
+  const float* offp = ol + t * ld_ol + (int64_t)m * LP * 2;
+  const float* logp = ol + t * ld_ol + (int64_t)M * LP * 2 + (int64_t)m * LP;
+  const float* refp = ref + t * L * 2;
+  // softmax over the L*P logits of this head (max-shifted, like torch.softmax)
+  float mx = -INFINITY;
+  for (int i = 0; i < LP; ++i) mx = fmaxf(mx, __ldg(logp + i));
+  float den = 0.f;
+  for (int i = 0; i < LP; ++i) den += expf(__ldg(logp + i) - mx);
+  const int64_t row = (int64_t)M * D;
+  const float* vb = value + (int64_t)b * S * row + m * D + dv * VEC;
+  float acc[VEC];
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
+  for (int l = 0; l < L; ++l) {
+    const int H = sH[l], W = sW[l];
+    const float* vl = vb + (int64_t)sStart[l] * row;
+    const float2 rp = __ldg(reinterpret_cast<const float2*>(refp) + l);
+    for (int p = 0; p < P; ++p) {
+      const float2 off = __ldg(reinterpret_cast<const float2*>(offp) + l * P + p);
+      const float wgt = expf(__ldg(logp + l * P + p) - mx) / den;
+      const float lx = rp.x + __fdiv_rn(off.x, (float)W);
+      const float ly = rp.y + __fdiv_rn(off.y, (float)H);
+      const float h_im = ly * H - 0.5f;
+      const float w_im = lx * W - 0.5f;
+      if (h_im > -1.f && w_im > -1.f && h_im < H && w_im < W) {
+        const int h0 = (int)floorf(h_im), w0 = (int)floorf(w_im);
+        const float lh = h_im - h0, lw = w_im - w0;
+        const float hh = 1.f - lh, hw = 1.f - lw;
+        float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) v1[c] = v2[c] = v3[c] = v4[c] = 0.f;
+        const bool top = h0 >= 0, bot = h0 + 1 <= H - 1, lef = w0 >= 0, rig = w0 + 1 <= W - 1;
+        const float* p00 = vl + ((int64_t)h0 * W + w0) * row;
+        if (top && lef) vload<VEC>(v1, p00);
+        if (top && rig) vload<VEC>(v2, p00 + row);
+        if (bot && lef) vload<VEC>(v3, p00 + (int64_t)W * row);
+        if (bot && rig) vload<VEC>(v4, p00 + (int64_t)W * row + row);
+        const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) acc[c] += (w1 * v1[c] + w2 * v2[c] + w3 * v3[c] + w4 * v4[c]) * wgt;
+      }
+    }
+  }
+  float* op = out + (t * M + m) * D + dv * VEC;
+  if constexpr (VEC == 4) {
+    *reinterpret_cast<float4*>(op) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  } else if constexpr (VEC == 2) {
+    *reinterpret_cast<float2*>(op) = make_float2(acc[0], acc[1]);
+  } else {
+    op[0] = acc[0];
+  }
+}
+
 template <int VEC>
 __device__ __forceinline__ void vatomic_add(float* p, const float (&g)[VEC]) {
   if constexpr (VEC == 4) {
@@ -222,6 +304,36 @@ extern "C" int msm_ms_deform_attn_fwd(const float* value, const int64_t* spatial
     msm::msda_fwd_kernel<1><<<blocks, threads, 0, st>>>(value, spatial_shapes, level_start_index, sampling_loc,
                                                         attn_weight, out, total, S, M, D, L, Lq, P);
   return msm::check_launch("msda_fwd_kernel");
+}
+
+extern "C" int msm_ms_deform_attn_fused_fwd(const float* value, const int64_t* spatial_shapes,
+                                            const int64_t* level_start_index, const float* offsets_logits,
+                                            int64_t ld_ol, const float* reference_points, float* out, int N, int S,
+                                            int M, int D, int L, int Lq, int P, void* stream) {
+  MSM_REQUIRE(value && spatial_shapes && level_start_index && offsets_logits && reference_points && out,
+              "all tensor pointers must be non-null");
+  MSM_REQUIRE(N > 0 && S > 0 && M > 0 && D > 0 && L > 0 && Lq > 0 && P > 0, "sizes must be positive");
+  MSM_REQUIRE(L <= msm::kMaxLevels, "at most 32 feature levels");
+  MSM_REQUIRE(ld_ol >= (int64_t)M * L * P * 3 && ld_ol % 2 == 0, "ld_ol must be even and >= M*L*P*3");
+  MSM_REQUIRE((reinterpret_cast<uintptr_t>(offsets_logits) & 7) == 0 &&
+                  (reinterpret_cast<uintptr_t>(reference_points) & 7) == 0,
+              "offsets_logits and reference_points must be 8-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int vec = msm::pick_vec(D, value, out, out);
+  if (vec == 4 && D == 8) vec = 2;
+  const int64_t total = (int64_t)N * Lq * M * (D / vec);
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+  if (vec == 4)
+    msm::msda_fused_fwd_kernel<4><<<blocks, threads, 0, st>>>(value, spatial_shapes, level_start_index, offsets_logits,
+                                                              ld_ol, reference_points, out, total, S, M, D, L, Lq, P);
+  else if (vec == 2)
+    msm::msda_fused_fwd_kernel<2><<<blocks, threads, 0, st>>>(value, spatial_shapes, level_start_index, offsets_logits,
+                                                              ld_ol, reference_points, out, total, S, M, D, L, Lq, P);
+  else
+    msm::msda_fused_fwd_kernel<1><<<blocks, threads, 0, st>>>(value, spatial_shapes, level_start_index, offsets_logits,
+                                                              ld_ol, reference_points, out, total, S, M, D, L, Lq, P);
+  return msm::check_launch("msda_fused_fwd_kernel");
 }
 
 extern "C" int msm_ms_deform_attn_bwd(const float* value, const int64_t* spatial_shapes,

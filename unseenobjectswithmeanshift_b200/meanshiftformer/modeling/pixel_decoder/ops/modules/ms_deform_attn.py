@@ -77,6 +77,11 @@ class MSDeformAttn(nn.Module):
             ow = torch.cat([self.sampling_offsets(query), self.attention_weights(query)], -1)
         else:
             ow = ops.dense(query, w_ow, b_ow)
+            if reference_points.shape[-1] == 2 and input_padding_mask is None:
+                # inference: softmax + sampling locations + gather in one kernel
+                output = ops.ms_deform_attn_fused_forward(value.contiguous(), input_spatial_shapes,
+                                                          input_level_start_index, ow, reference_points, L, P)
+                return ops.dense(output, self.output_proj.weight, self.output_proj.bias)
         offsets = ow[..., :n_off].reshape(N, Lq, M, L, P, 2)
         weights = F.softmax(ow[..., n_off:].reshape(N, Lq, M, L * P), -1).view(N, Lq, M, L, P)
         if reference_points.shape[-1] == 2:

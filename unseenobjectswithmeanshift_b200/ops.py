@@ -261,6 +261,33 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     return out
 
 
+def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, offsets_logits, reference_points,
+                                 n_levels, n_points):
+    """value [N,S,M,D]; offsets_logits [N,Lq,M*L*P*3] (raw sampling offsets | raw attention logits);
+    reference_points [N,Lq,L,2] -> [N,Lq,M*D]. Softmax, sampling-location arithmetic and the gather in one kernel."""
+    for t, n in ((value, "value"), (offsets_logits, "offsets_logits"), (reference_points, "reference_points")):
+        _require(t, n)
+    _require(spatial_shapes, "spatial_shapes", torch.int64)
+    _require(level_start_index, "level_start_index", torch.int64)
+    if not value.is_contiguous():
+        raise RuntimeError("value tensor has to be contiguous")
+    N, S, M, D = value.shape
+    Lq = offsets_logits.shape[1]
+    L, P = int(n_levels), int(n_points)
+    ol = offsets_logits if offsets_logits.stride(-1) == 1 and offsets_logits.stride(0) == Lq * offsets_logits.stride(1) \
+        else offsets_logits.contiguous()
+    if ol.shape != (N, Lq, M * L * P * 3) or reference_points.shape != (N, Lq, L, 2):
+        raise ValueError(f"offsets_logits {tuple(ol.shape)} / reference_points {tuple(reference_points.shape)} "
+                         f"do not match value {tuple(value.shape)} with L={L}, P={P}")
+    ref = reference_points.contiguous()
+    out = torch.empty(N, Lq, M * D, device=value.device, dtype=torch.float32)
+    rc = _lib.lib().msm_ms_deform_attn_fused_fwd(value.data_ptr(), spatial_shapes.data_ptr(),
+                                                 level_start_index.data_ptr(), ol.data_ptr(), ol.stride(1),
+                                                 ref.data_ptr(), out.data_ptr(), N, S, M, D, L, Lq, P, _stream())
+    check(rc, "msm_ms_deform_attn_fused_fwd")
+    return out
+
+
 def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
                             im2col_step=128):
     """MultiScaleDeformableAttention.ms_deform_attn_backward (ms_deform_attn.h:47-67):
@@ -306,7 +333,7 @@ def mean_shift_hill_climb(X, Z, kappa, max_iters=10):
 class _Stats:
     launches = 0          # kernels of THIS library enqueued since reset
     timing = False        # when True every op is bracketed by CUDA events on the launching stream
-    events = []           # (tag, start_event, end_event)
+    events = []           # (tag, shape signature, algorithmic bytes, flops, start_event, end_event)
 
 
 def reset_stats(timing=False):
@@ -322,36 +349,98 @@ def launches():
 def op_times_ms():
     """tag -> (count, total ms); call after torch.cuda.synchronize()."""
     agg = {}
-    for tag, a, b in _Stats.events:
+    for tag, _, _, _, a, b in _Stats.events:
         c, t = agg.get(tag, (0, 0.0))
         agg[tag] = (c + 1, t + a.elapsed_time(b))
     return agg
 
 
-def _instrument(tag, kernels):
+def op_groups():
+    """(tag, shape signature) -> dict(count, ms, bytes, flops): launches of one kernel at one shape, with the
+    ALGORITHMIC bytes / flops of each launch. Call after torch.cuda.synchronize()."""
+    agg = {}
+    for tag, sig, by, fl, a, b in _Stats.events:
+        g = agg.setdefault((tag, sig), {"count": 0, "ms": 0.0, "bytes": 0.0, "flops": 0.0})
+        g["count"] += 1
+        g["ms"] += a.elapsed_time(b)
+        g["bytes"] += by
+        g["flops"] += fl
+    return agg
+
+
+def _instrument(tag, kernels, work=None):
+    """work(*args, **kwargs) -> (shape signature, algorithmic bytes, flops) of one call."""
     def deco(fn):
         def wrapped(*args, **kwargs):
             n = kernels(*args, **kwargs) if callable(kernels) else kernels
             _Stats.launches += n
             if not _Stats.timing:
                 return fn(*args, **kwargs)
+            sig, by, fl = work(*args, **kwargs) if work is not None else ("", 0.0, 0.0)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             r = fn(*args, **kwargs)
             b.record()
-            _Stats.events.append((tag, a, b))
+            _Stats.events.append((tag, sig, by, fl, a, b))
             return r
         wrapped.__name__, wrapped.__doc__ = fn.__name__, fn.__doc__
         return wrapped
     return deco
 
 
-vmf_attention = _instrument("vmf_attention", 2)(vmf_attention)
+def _work_vmf(q, k, v, **kw):
+    B, H, Nq, hd = q.shape
+    Ns = k.shape[2]
+    shared = k.data_ptr() == v.data_ptr()
+    by = 4.0 * B * H * hd * (Ns * (1 if shared else 2) + 2 * Nq) + (B * Nq * Ns / 8.0 if kw.get("blocked_bits") is not None else 0)
+    return f"B{B} H{H} Q{Nq} S{Ns} hd{hd}", by, 4.0 * B * H * Nq * Ns * hd
+
+
+def _work_mask(e, f, out=None):
+    B, Q, C = e.shape
+    hw = f.shape[2] * f.shape[3]
+    return f"B{B} Q{Q} C{C} HW{hw}", 4.0 * B * (C * hw + Q * hw + Q * C), 2.0 * B * Q * C * hw
+
+
+def _work_bits(m, target):
+    B, Q, H, W = m.shape
+    return f"B{B} Q{Q} {H}x{W}->{int(target[0])}x{int(target[1])}", 4.0 * B * Q * H * W + B * Q * target[0] * target[1] / 8.0, 0.0
+
+
+def _work_linear(x, w, bias=None, relu=False, out=None):
+    N, K = w.shape
+    M = x.numel() // K
+    return f"M{M} N{N} K{K}", 4.0 * (M * K + M * N) + 4.0 * N * K, 2.0 * M * N * K
+
+
+def _work_msda(value, shapes, lsi, loc, aw, *a, **k):
+    N, S, M, D = value.shape
+    Lq = loc.shape[1]
+    by = 4.0 * (value.numel() + loc.numel() + aw.numel() + N * Lq * M * D)
+    return f"N{N} S{S} M{M} D{D} Lq{Lq}", by, 0.0
+
+
+def _work_msda_fused(value, shapes, lsi, ol, ref, L, P):
+    N, S, M, D = value.shape
+    Lq = ol.shape[1]
+    by = 4.0 * (value.numel() + ol.numel() + ref.numel() + N * Lq * M * D)
+    return f"fused N{N} S{S} M{M} D{D} Lq{Lq}", by, 0.0
+
+
+def _work_ms(X, Z, kappa, max_iters=10):
+    n, d = X.shape[-2], X.shape[-1]
+    B = X.shape[0] if X.dim() == 3 else 1
+    m = Z.shape[-2]
+    return f"B{B} n{n} m{m} d{d} it{max_iters}", 4.0 * B * n * d * max_iters, 4.0 * B * m * n * d * max_iters
+
+
+vmf_attention = _instrument("vmf_attention", 2, _work_vmf)(vmf_attention)
 vmf_attention_weights = _instrument("vmf_attention_weights", 1)(vmf_attention_weights)
-mask_logits = _instrument("mask_logits", 1)(mask_logits)
-mask_to_attn_bits = _instrument("mask_to_attn_bits", 1)(mask_to_attn_bits)
-linear = _instrument("linear", 1)(linear)
-ms_deform_attn_forward = _instrument("ms_deform_attn_forward", 1)(ms_deform_attn_forward)
+mask_logits = _instrument("mask_logits", 1, _work_mask)(mask_logits)
+mask_to_attn_bits = _instrument("mask_to_attn_bits", 1, _work_bits)(mask_to_attn_bits)
+linear = _instrument("linear", 1, _work_linear)(linear)
+ms_deform_attn_forward = _instrument("ms_deform_attn_forward", 1, _work_msda)(ms_deform_attn_forward)
+ms_deform_attn_fused_forward = _instrument("ms_deform_attn_forward", 1, _work_msda_fused)(ms_deform_attn_fused_forward)
 ms_deform_attn_backward = _instrument("ms_deform_attn_backward", 1)(ms_deform_attn_backward)
-mean_shift_hill_climb = _instrument("mean_shift_hill_climb", lambda X, Z, kappa, max_iters=10: 2 * int(max_iters))(
-    mean_shift_hill_climb)
+mean_shift_hill_climb = _instrument("mean_shift_hill_climb", lambda X, Z, kappa, max_iters=10: 2 * int(max_iters),
+                                    _work_ms)(mean_shift_hill_climb)
