@@ -112,6 +112,23 @@ int msm_linear_prepare_weight(const float* W, int64_t ldw, void* prepared, int N
 int msm_linear_fwd(const float* X, int64_t ldx, const void* prepared, const float* bias, float* Y, int64_t ldy,
                    int M, int N, int K, int act, void* stream);
 
+/* Y = LayerNorm_N( residual + X . W^T + bias ) * gamma + beta  (biased variance, eps inside the square root, as
+ * torch.nn.LayerNorm): the post-norm residual blocks of the deformable encoder, norm1(src + output_proj(...)) and
+ * norm2(src + linear2(...)) (pixel_decoder/msdeformattn.py:64-84), with the add and the normalisation done in the
+ * GEMM epilogue on the accumulator row. N must be 32 or 64 (one thread holds a whole output row). */
+int msm_linear_ln_fwd(const float* X, int64_t ldx, const void* prepared, const float* bias, const float* residual,
+                      int64_t ldr, const float* gamma, const float* beta, float eps, float* Y, int64_t ldy, int M,
+                      int N, int K, void* stream);
+
+/* 1x1 convolution on NCHW input with the same kernel: X [B][K][HW] (pixels contiguous), weight prepared as above
+ * from the conv weight viewed as [N][K]. y_nchw != 0: Y [B][N][HW] (what nn.Conv2d returns); y_nchw == 0:
+ * Y [B][HW][N] (token-major, what the decoders consume after flatten(2).transpose(1,2)).
+ * Replaces the kernel_size=1 Conv2d layers of the head: pixel-decoder input_proj / lateral / mask_features
+ *   (pixel_decoder/msdeformattn.py:206-216, :258-262, :242) and the decoder's input_proj
+ *   (meanshiftformer_transformer_decoder.py:498-499, :575). HW must be a multiple of 4. */
+int msm_conv1x1_fwd(const float* X, const void* prepared, const float* bias, float* Y, int y_nchw, int B, int HW,
+                    int N, int K, int act, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Multi-scale deformable attention, forward.
  * Replaces MultiScaleDeformableAttention.ms_deform_attn_forward(value, spatial_shapes,

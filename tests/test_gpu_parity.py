@@ -403,6 +403,122 @@ def test_mean_shift_config4_size_properties(msm):
     assert (Z.cpu() - ref).abs().max().item() < 1e-4
 
 
+# ----------------------------------------------------------------------------- dense layers (tcgen05 linear kernel)
+# bf16x3 split-precision products: ~2^-17 relative per product, fp32 accumulation -> 2e-5 of the output's peak.
+LINEAR_TOL = 2e-5
+
+
+@pytest.mark.parametrize("M,N,K,relu", [(100, 256, 256, False), (130, 96, 64, True), (800, 2048, 256, True),
+                                        (800, 256, 2048, False), (12600, 288, 64, False), (12600, 64, 1024, False),
+                                        (1, 32, 32, False), (4800, 768, 256, False)])
+def test_linear_vs_fp64(msm, M, N, K, relu):
+    """F.linear replacement (attention_util.py:84-140 in-projections, decoder FFN/MLP, encoder projections):
+    every output element against an fp64 reference, incl. ragged row tails and multi-tile-per-CTA schedules."""
+    g = torch.Generator().manual_seed(M + N + K)
+    x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    ref = x.double() @ w.double().t() + b.double()
+    if relu:
+        ref = ref.clamp_min(0)
+    with torch.no_grad():
+        y = msm.ops.linear(x.cuda(), w.cuda(), b.cuda(), relu=relu)
+        assert peak_rel(y.cpu().double(), ref) < LINEAR_TOL
+        # no bias; strided input rows and a column slice of a wider output buffer, addressed in place
+        xw = torch.randn(M, K + 64, generator=g)
+        big = torch.full((M, N + 32), 7.0).cuda()
+        msm.ops.linear(xw.cuda()[:, 32:32 + K], w.cuda(), None, out=big[:, 32:])
+        ref2 = xw[:, 32:32 + K].double() @ w.double().t()
+        assert peak_rel(big[:, 32:].cpu().double(), ref2) < LINEAR_TOL
+        assert bool((big[:, :32] == 7.0).all())
+
+
+def test_linear_prepared_weight_cache_tracks_updates(msm):
+    """the prepared (bf16 hi/lo) copy of a weight follows in-place updates and never aliases a recycled address."""
+    x = torch.randn(64, 64).cuda()
+    w = torch.randn(32, 64).cuda()
+    with torch.no_grad():
+        y0 = msm.ops.linear(x, w)
+        w.mul_(2.0)
+        y1 = msm.ops.linear(x, w)
+        assert peak_rel(y1, 2 * y0) < 1e-6
+        for _ in range(4):  # fresh tensors that may land on the freed address of the previous one
+            w2 = torch.randn(32, 64).cuda()
+            y2 = msm.ops.linear(x, w2)
+            assert peak_rel(y2.cpu().double(), x.cpu().double() @ w2.cpu().double().t()) < LINEAR_TOL
+            del w2
+
+
+@pytest.mark.parametrize("M,N,K", [(12600, 64, 64), (12600, 64, 1024), (252, 32, 32), (300, 32, 64)])
+def test_linear_residual_layernorm_vs_fp64(msm, M, N, K):
+    """norm(src + linear(x)) of the deformable encoder layer (pixel_decoder/msdeformattn.py:64-84) with the add
+    and the LayerNorm in the GEMM epilogue."""
+    g = torch.Generator().manual_seed(M + K)
+    x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    res = torch.randn(M, N, generator=g)
+    norm = torch.nn.LayerNorm(N)
+    with torch.no_grad():
+        norm.weight.copy_(torch.rand(N, generator=g) + 0.5)
+        norm.bias.copy_(torch.randn(N, generator=g))
+        ref = F.layer_norm(res.double() + x.double() @ w.double().t() + b.double(), (N,), norm.weight.double(),
+                           norm.bias.double(), norm.eps)
+        norm = norm.cuda()
+        assert msm.ops.linear_ln_supported(x.cuda(), w.cuda(), res.cuda(), norm)
+        y = msm.ops.linear_ln(x.cuda(), w.cuda(), b.cuda(), res.cuda(), norm)
+    assert peak_rel(y.cpu().double(), ref) < LINEAR_TOL
+
+
+@pytest.mark.parametrize("B,K,N,H,W", [(2, 2048, 64, 15, 20), (2, 512, 64, 60, 80), (1, 64, 256, 120, 160),
+                                       (3, 64, 256, 15, 20), (2, 32, 32, 6, 2)])
+def test_conv1x1_vs_fp64(msm, B, K, N, H, W):
+    """kernel_size=1 Conv2d on NCHW input (pixel-decoder input_proj / lateral / mask_features, decoder input_proj):
+    NCHW output and the token-major [B, HW, N] output, ragged per-image pixel tails included."""
+    g = torch.Generator().manual_seed(K + N + H)
+    x, w, b = torch.randn(B, K, H, W, generator=g), torch.randn(N, K, 1, 1, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    ref = F.conv2d(x.double(), w.double(), b.double())
+    with torch.no_grad():
+        assert msm.ops.conv1x1_supported(x.cuda(), w.cuda())
+        y = msm.ops.conv1x1(x.cuda(), w.cuda(), b.cuda())
+        yt = msm.ops.conv1x1(x.cuda(), w.cuda(), b.cuda(), tokens_out=True)
+    assert y.shape == ref.shape and peak_rel(y.cpu().double(), ref) < LINEAR_TOL
+    assert peak_rel(yt.cpu().double(), ref.flatten(2).transpose(1, 2)) < LINEAR_TOL
+
+
+def test_msdeform_fused_sampling_vs_module_math(msm):
+    """the fused softmax + sampling-location + gather kernel against the reference's unfused arithmetic
+    (ops/modules/ms_deform_attn.py:96-121) feeding the plain op, at the UOIS geometry (3 levels, 4 points)."""
+    g = torch.Generator().manual_seed(11)
+    N, M, D, L, P = 2, 8, 8, 3, 4
+    shapes = [(15, 20), (30, 40), (60, 80)]
+    S = sum(h * w for h, w in shapes)
+    value = torch.randn(N, S, M, D, generator=g)
+    ow = torch.randn(N, S, M * L * P * 3, generator=g)
+    ref_pts = torch.rand(N, S, L, 2, generator=g)
+    ss = torch.tensor(shapes)
+    lsi = torch.tensor([0, 300, 1500])
+    n_off = M * L * P * 2
+    offsets = ow[..., :n_off].reshape(N, S, M, L, P, 2)
+    weights = F.softmax(ow[..., n_off:].reshape(N, S, M, L * P), -1).view(N, S, M, L, P)
+    wh = torch.stack([ss[..., 1], ss[..., 0]], -1)
+    loc = ref_pts[:, :, None, :, None, :] + offsets / wh[None, None, None, :, None, :]
+    want = opd.ms_deform_attn_core(value.double(), ss, lsi, loc.double(), weights.double()).float()
+    with torch.no_grad():
+        got = msm.ops.ms_deform_attn_fused_forward(value.cuda(), ss.cuda(), lsi.cuda(), ow.cuda(), ref_pts.cuda(), L, P)
+        # generic (run-time L, P) instantiation: 2 levels x 2 points
+        shapes2 = [(6, 4), (3, 2)]
+        S2 = 30
+        v2 = torch.randn(1, S2, 2, 4, generator=g)
+        ow2 = torch.randn(1, 5, 2 * 2 * 2 * 3, generator=g)
+        rp2 = torch.rand(1, 5, 2, 2, generator=g)
+        got2 = msm.ops.ms_deform_attn_fused_forward(v2.cuda(), torch.tensor(shapes2).cuda(), torch.tensor([0, 24]).cuda(),
+                                                    ow2.cuda(), rp2.cuda(), 2, 2)
+    assert peak_rel(got.cpu(), want) < 1e-5
+    off2 = ow2[..., :16].reshape(1, 5, 2, 2, 2, 2)
+    w2 = F.softmax(ow2[..., 16:].reshape(1, 5, 2, 4), -1).view(1, 5, 2, 2, 2)
+    wh2 = torch.tensor([[4, 6], [2, 3]])
+    loc2 = rp2[:, :, None, :, None, :] + off2 / wh2[None, None, None, :, None, :]
+    want2 = opd.ms_deform_attn_core(v2.double(), torch.tensor(shapes2), torch.tensor([0, 24]), loc2.double(), w2.double()).float()
+    assert peak_rel(got2.cpu(), want2) < 1e-5
+
+
 # ----------------------------------------------------------------------------- error behaviour
 def test_errors_are_loud(msm):
     ops = msm.ops

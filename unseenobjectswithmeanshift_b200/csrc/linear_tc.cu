@@ -17,8 +17,9 @@
 //               (swizzle makes the 16-byte reads conflict-free), splits to bf16 hi/lo, tcgen05.st into
 //               the A columns of TMEM
 //   warp 1      MMA issuer: 3 tcgen05.mma (M=128, N=BN, K=16) per 16 input channels
-//   warps 4-7   epilogue: tcgen05.ld (lane = row), + bias, activation, 128B-swizzled staging tile in shared
-//               memory, TMA store of 32-column x 128-row boxes (coalesced, clips the M tail)
+//   warps 4-7   epilogue: tcgen05.ld (lane = row), + bias, activation - or residual + LayerNorm over the row when
+//               N <= 64 - into a warp-private 128B-swizzled 32x32 staging tile, TMA store (coalesced, clips the
+//               M tail); no block-level barrier: every warp owns its 32 rows end to end
 //
 // Persistent: grid = min(tiles, SMs); tile = (row tile, N chunk) with the N chunk fastest so that
 // CTAs running side by side share the X tile in L2.
@@ -36,17 +37,27 @@ constexpr int kThreads = 512;
 constexpr int kRows = 128;                // rows per tile = UMMA M
 constexpr int kKc = 32;                   // input channels per pipeline stage
 constexpr int kAStageBytes = kRows * kKc * 4;  // 16 KB
-constexpr int kStages = 4;                // shared-memory stages (X fp32 and W bf16 rings)
+constexpr int kStages = 4;                // shared-memory stages of the W (bf16) ring
+constexpr int kXStages = 6;               // shared-memory stages of the X (fp32) ring: 96 KB in flight per SM
 constexpr int kAStagesT = 4;              // A-operand stages in TMEM
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTmemA = 256;
 constexpr int kAcc = 2;
-constexpr int kYStageBytes = kRows * 32 * 4;   // 16 KB staging tile (32 output columns)
+constexpr int kYWarpBytes = 32 * 32 * 4;  // 4 KB staging tile of one epilogue warp (32 rows x 32 columns)
 constexpr int kMaxSmem = 232448;
 
 struct Params {
   const float* bias;  // [N] or null
   int M, N, K, BN, n_chunks, m_tiles, act;
+  // 1x1-convolution form: X is [Bt][K][Mb] (NCHW, rows = pixels are the contiguous axis), tiles never straddle
+  // images. y_nchw: Y is written as [Bt][N][Mb] by direct stores (lane = pixel, coalesced) instead of TMA.
+  int x_nchw, y_nchw, Mb, tiles_per_b;
+  float* y;  // used when y_nchw
+  // fused epilogue Y = LayerNorm(residual + X W^T + bias) over the N = BN <= 64 outputs of a row
+  const float* residual;
+  int64_t ldr;
+  const float *ln_gamma, *ln_beta;
+  float ln_eps;
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -64,14 +75,14 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
   const uint32_t bStage = 128u * (uint32_t)P.BN;     // [hi|lo][4 k-groups][BN][8] bf16
   const uint32_t lboB = 16u * (uint32_t)P.BN;        // byte stride between 8-channel groups
 
-  uint8_t* sX = smem;                                // [kStages][128 rows][32] fp32, swizzled
-  uint8_t* sY = sX + kStages * kAStageBytes;         // [2][128 rows][32] fp32, swizzled
-  uint8_t* sW = sY + 2 * kYStageBytes;               // [kStages][bStage]
-  float* sBias = reinterpret_cast<float*>(sW + kStages * bStage);  // [128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 128);
+  uint8_t* sX = smem;                                // [kXStages][128 rows][32] fp32, swizzled
+  uint8_t* sY = sX + kXStages * kAStageBytes;        // [4 warps][2][32 rows][32] fp32, swizzled
+  uint8_t* sW = sY + 8 * kYWarpBytes;                // [kStages][bStage]
+  float* sBias = reinterpret_cast<float*>(sW + kStages * bStage);  // [4 warps][bias | gamma | beta][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 4 * 384);
   uint64_t* full_x = bars;                           // TMA -> converters
-  uint64_t* empty_x = full_x + kStages;              // converters -> TMA
-  uint64_t* full_w = empty_x + kStages;              // TMA -> MMA
+  uint64_t* empty_x = full_x + kXStages;             // converters -> TMA
+  uint64_t* full_w = empty_x + kXStages;             // TMA -> MMA
   uint64_t* empty_w = full_w + kStages;              // MMA -> TMA
   uint64_t* full_a = empty_w + kStages;              // converters -> MMA
   uint64_t* empty_a = full_a + kAStagesT;            // MMA -> converters
@@ -85,9 +96,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     tc::tma_prefetch_desc(&xmap);
     tc::tma_prefetch_desc(&wmap);
     tc::tma_prefetch_desc(&ymap);
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kXStages; ++i) {
       tc::mbar_init(&full_x[i], 1);
       tc::mbar_init(&empty_x[i], 4);
+    }
+    for (int i = 0; i < kStages; ++i) {
       tc::mbar_init(&full_w[i], 1);
       tc::mbar_init(&empty_w[i], 1);
     }
@@ -110,13 +123,18 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
   if (warp == 0) {
     // =================================================================== TMA producer
     if (lane == 0) {
-      tc::Ring rs;
+      tc::Ring xs, rs;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int mt = tile / P.n_chunks, nc = tile % P.n_chunks;
         for (int kc = 0; kc < nkc; ++kc) {
-          tc::mbar_wait(&empty_x[rs.stage], rs.phase ^ 1);
-          tc::mbar_arrive_expect_tx(&full_x[rs.stage], kAStageBytes);
-          tc::tma_load_2d(sX + rs.stage * kAStageBytes, &xmap, &full_x[rs.stage], kc * kKc, mt * kRows);
+          tc::mbar_wait(&empty_x[xs.stage], xs.phase ^ 1);
+          tc::mbar_arrive_expect_tx(&full_x[xs.stage], kAStageBytes);
+          if (P.x_nchw)
+            tc::tma_load_3d(sX + xs.stage * kAStageBytes, &xmap, &full_x[xs.stage], (mt % P.tiles_per_b) * kRows,
+                            kc * kKc, mt / P.tiles_per_b);
+          else
+            tc::tma_load_2d(sX + xs.stage * kAStageBytes, &xmap, &full_x[xs.stage], kc * kKc, mt * kRows);
+          xs.advance(kXStages);
           tc::mbar_wait(&empty_w[rs.stage], rs.phase ^ 1);
           tc::mbar_arrive_expect_tx(&full_w[rs.stage], bStage);
           tc::tma_load_4d(sW + rs.stage * bStage, &wmap, &full_w[rs.stage], 0, nc * P.BN, kc * (kKc / 8), 0);
@@ -167,16 +185,22 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       for (int kc = 0; kc < nkc; ++kc, ++step) {
         if ((int)(step & 1u) != team) continue;
-        const uint32_t xstage = step % kStages, xphase = (step / kStages) & 1u;
+        const uint32_t xstage = step % kXStages, xphase = (step / kXStages) & 1u;
         const uint32_t astage = step % kAStagesT, aphase = (step / kAStagesT) & 1u;
         tc::mbar_wait(&full_x[xstage], xphase);
-        const uint8_t* src = sX + xstage * kAStageBytes + rowoff;
         uint32_t hi[16], lo[16];
+        if (P.x_nchw) {  // stage = [32 channels][128 pixels]: thread = pixel, conflict-free column reads
+          const float* src = reinterpret_cast<const float*>(sX + xstage * kAStageBytes) + row;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 x = *reinterpret_cast<const float4*>(src + (((uint32_t)c ^ sx) << 4));
-          tc::split2(x.x, x.y, hi[2 * c], lo[2 * c]);
-          tc::split2(x.z, x.w, hi[2 * c + 1], lo[2 * c + 1]);
+          for (int j = 0; j < 16; ++j) tc::split2(src[(2 * j) * kRows], src[(2 * j + 1) * kRows], hi[j], lo[j]);
+        } else {         // stage = [128 rows][32 channels], 128B-swizzled
+          const uint8_t* src = sX + xstage * kAStageBytes + rowoff;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 x = *reinterpret_cast<const float4*>(src + (((uint32_t)c ^ sx) << 4));
+            tc::split2(x.x, x.y, hi[2 * c], lo[2 * c]);
+            tc::split2(x.z, x.w, hi[2 * c + 1], lo[2 * c + 1]);
+          }
         }
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&empty_x[xstage]);
@@ -193,21 +217,129 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     }
   } else if (warp >= 4) {
     // =================================================================== epilogue
+    // Each warp owns the 32 rows of its TMEM lane quadrant end to end: its own bias / LayerNorm parameter
+    // copies, its own two 32x32 staging tiles and its own TMA stores - no block-level barrier in the loop.
     const int q = warp - 4;
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - 128;  // 0..127
-    const uint32_t rowoff = (uint32_t)row * 128u, sx = (uint32_t)(row & 7);
+    const uint32_t rowoff = (uint32_t)lane * 128u, sx = (uint32_t)(lane & 7);
     const int nchunk = P.BN / 32;
+    float* wBias = sBias + q * 384;  // [bias 128 | gamma 128 | beta 128] of this warp
+    uint8_t* wY = sY + q * (2 * kYWarpBytes);
     uint32_t ychunk = 0;  // staging-buffer cursor
     int t = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
       const int mt = tile / P.n_chunks, nc = tile % P.n_chunks;
       const int acc = t % kAcc;
-      sBias[et] = (P.bias != nullptr && et < P.BN) ? __ldg(P.bias + nc * P.BN + et) : 0.f;
+      __syncwarp();  // the previous tile's reads of wBias are done
+      for (int j = lane; j < P.BN; j += 32) {
+        wBias[j] = P.bias != nullptr ? __ldg(P.bias + nc * P.BN + j) : 0.f;
+        if (P.ln_gamma != nullptr) {
+          wBias[128 + j] = __ldg(P.ln_gamma + j);
+          wBias[256 + j] = __ldg(P.ln_beta + j);
+        }
+      }
+      __syncwarp();
       tc::mbar_wait(&acc_full[acc], (t / kAcc) & 1);
       tc::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 128u;
-      for (int ch = 0; ch < nchunk; ++ch, ++ychunk) {
+      if (P.y_nchw) {
+        // Y[b][n][pixel]: lane = pixel, so each store instruction writes one 128-byte row segment
+        const int bi = mt / P.tiles_per_b;
+        const int pixel = (mt % P.tiles_per_b) * kRows + row;
+        const bool in = pixel < P.Mb;
+        float* orow = P.y + ((int64_t)bi * P.N + (int64_t)nc * P.BN) * P.Mb + pixel;
+        for (int ch = 0; ch < nchunk; ++ch) {
+          uint32_t r[32];
+          tc::tmem_ld32(taddr + ch * 32, r);
+          tc::tmem_ld_wait();
+          if (ch == nchunk - 1) {
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
+          }
+          if (in) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float v = __uint_as_float(r[j]) + wBias[ch * 32 + j];
+              if (P.act == 1) v = fmaxf(v, 0.f);
+              orow[(int64_t)(ch * 32 + j) * P.Mb] = v;
+            }
+          }
+        }
+        continue;
+      }
+      auto store_chunk = [&](const float* v, int ch) {
+        uint8_t* ybuf = wY + (ychunk & 1u) * kYWarpBytes;
+        ++ychunk;
+        // the TMA store that read this staging tile two chunks ago must be done with it
+        if (lane == 0) tc::tma_store_wait_read<1>();
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<float4*>(ybuf + rowoff + (((uint32_t)c ^ sx) << 4)) =
+              make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (P.x_nchw)  // token-major output of a per-image tile: the 3-D map clips at the image's last pixel
+            tc::tma_store_3d(&ymap, ybuf, nc * P.BN + ch * 32, (mt % P.tiles_per_b) * kRows + q * 32,
+                             mt / P.tiles_per_b);
+          else
+            tc::tma_store_2d(&ymap, ybuf, nc * P.BN + ch * 32, mt * kRows + q * 32);
+          tc::tma_store_commit();
+        }
+      };
+      if (P.ln_gamma != nullptr) {
+        // Y = LayerNorm(residual + X W^T + bias): the whole row (N = BN <= 64) sits in this thread's registers
+        float v[64];
+        const int grow = mt * kRows + row;
+        const float* rp = P.residual + (int64_t)(grow < P.M ? grow : 0) * P.ldr;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          if (ch < nchunk) {
+            uint32_t r[32];
+            tc::tmem_ld32(taddr + ch * 32, r);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 res = __ldg(reinterpret_cast<const float4*>(rp) + ch * 8 + c);
+              v[ch * 32 + 4 * c + 0] = __uint_as_float(r[4 * c + 0]) + wBias[ch * 32 + 4 * c + 0] + res.x;
+              v[ch * 32 + 4 * c + 1] = __uint_as_float(r[4 * c + 1]) + wBias[ch * 32 + 4 * c + 1] + res.y;
+              v[ch * 32 + 4 * c + 2] = __uint_as_float(r[4 * c + 2]) + wBias[ch * 32 + 4 * c + 2] + res.z;
+              v[ch * 32 + 4 * c + 3] = __uint_as_float(r[4 * c + 3]) + wBias[ch * 32 + 4 * c + 3] + res.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[ch * 32 + j] = 0.f;
+          }
+        }
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
+        const float inv_n = 1.f / (float)P.BN;
+        float mean = 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) mean += v[j];
+        mean *= inv_n;
+        float var = 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          const float d = (j < P.BN) ? v[j] - mean : 0.f;
+          var = fmaf(d, d, var);
+        }
+        const float rstd = rsqrtf(var * inv_n + P.ln_eps);
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          if (ch < nchunk) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              v[ch * 32 + j] = (v[ch * 32 + j] - mean) * rstd * wBias[128 + ch * 32 + j] + wBias[256 + ch * 32 + j];
+            store_chunk(v + ch * 32, ch);
+          }
+        }
+        continue;
+      }
+      for (int ch = 0; ch < nchunk; ++ch) {
         uint32_t r[32];
         tc::tmem_ld32(taddr + ch * 32, r);
         tc::tmem_ld_wait();
@@ -216,31 +348,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
         }
-        uint8_t* ybuf = sY + (ychunk & 1u) * kYStageBytes;
-        // the TMA store that read this staging buffer two chunks ago must be done with it
-        if (et == 0) tc::tma_store_wait_read<1>();
-        named_bar_sync(2, 128);  // also orders the sBias writes of this tile
+        float v[32];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float4 v;
-          v.x = __uint_as_float(r[4 * c + 0]) + sBias[ch * 32 + 4 * c + 0];
-          v.y = __uint_as_float(r[4 * c + 1]) + sBias[ch * 32 + 4 * c + 1];
-          v.z = __uint_as_float(r[4 * c + 2]) + sBias[ch * 32 + 4 * c + 2];
-          v.w = __uint_as_float(r[4 * c + 3]) + sBias[ch * 32 + 4 * c + 3];
-          if (P.act == 1) {
-            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-          }
-          *reinterpret_cast<float4*>(ybuf + rowoff + (((uint32_t)c ^ sx) << 4)) = v;
+        for (int j = 0; j < 32; ++j) {
+          v[j] = __uint_as_float(r[j]) + wBias[ch * 32 + j];
+          if (P.act == 1) v[j] = fmaxf(v[j], 0.f);
         }
-        tc::fence_proxy_async();
-        named_bar_sync(3, 128);
-        if (et == 0) {
-          tc::tma_store_2d(&ymap, ybuf, nc * P.BN + ch * 32, mt * kRows);
-          tc::tma_store_commit();
-        }
+        store_chunk(v, ch);
       }
     }
-    if (et == 0) tc::tma_store_wait_all();
+    if (lane == 0) tc::tma_store_wait_all();
   }
 
   tc::tc_fence_before();
@@ -293,23 +410,37 @@ extern "C" int msm_linear_prepare_weight(const float* W, int64_t ldw, void* prep
   return msm::check_launch("linear_prepare_weight_kernel");
 }
 
-extern "C" int msm_linear_fwd(const float* X, int64_t ldx, const void* prepared, const float* bias, float* Y,
-                              int64_t ldy, int M, int N, int K, int act, void* stream) {
-  using namespace msm;
-  using namespace msm::ltc;
-  MSM_REQUIRE(X && prepared && Y, "X, prepared, Y must be non-null");
-  MSM_REQUIRE(M > 0 && N > 0 && K > 0, "sizes must be positive");
-  MSM_REQUIRE(K % 32 == 0 && N % 32 == 0, "N and K must be multiples of 32");
-  MSM_REQUIRE(act == 0 || act == 1, "act must be 0 (none) or 1 (relu)");
-  MSM_REQUIRE(ldx >= K && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0, "X rows must be 16-byte aligned");
-  MSM_REQUIRE(ldy >= N && ldy % 4 == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0, "Y rows must be 16-byte aligned");
+namespace msm {
+namespace ltc {
+
+// x_nchw: X is [Bt][K][Mb]; otherwise X is [M][K] with row stride ldx. y_nchw: Y is [Bt][N][Mb]; otherwise
+// token-major rows of ldy floats ([M][N], or [Bt][Mb][N] when x_nchw).
+struct LnArgs {
+  const float* residual = nullptr;
+  int64_t ldr = 0;
+  const float *gamma = nullptr, *beta = nullptr;
+  float eps = 0.f;
+};
+
+static int launch(const float* X, int64_t ldx, const void* prepared, const float* bias, float* Y, int64_t ldy, int M,
+                  int N, int K, int act, int x_nchw, int y_nchw, int Bt, int Mb, cudaStream_t st,
+                  const LnArgs& ln = LnArgs()) {
   Params P;
   P.bias = bias; P.M = M; P.N = N; P.K = K; P.act = act;
+  P.residual = ln.residual; P.ldr = ln.ldr; P.ln_gamma = ln.gamma; P.ln_beta = ln.beta; P.ln_eps = ln.eps;
   P.BN = pick_bn(N);
   P.n_chunks = N / P.BN;
-  P.m_tiles = (M + kRows - 1) / kRows;
+  P.x_nchw = x_nchw; P.y_nchw = y_nchw; P.Mb = Mb; P.y = Y;
+  P.tiles_per_b = x_nchw ? (Mb + kRows - 1) / kRows : 1;
+  P.m_tiles = x_nchw ? Bt * P.tiles_per_b : (M + kRows - 1) / kRows;
   CUtensorMap xmap, wmap, ymap;
-  {
+  if (x_nchw) {
+    const uint64_t dims[3] = {(uint64_t)Mb, (uint64_t)K, (uint64_t)Bt};
+    const uint64_t strides[2] = {(uint64_t)Mb * 4, (uint64_t)Mb * K * 4};
+    const uint32_t box[3] = {(uint32_t)kRows, (uint32_t)kKc, 1};
+    int rc = tc::encode_tensor_map(&xmap, tc::TmapType::F32, tc::TmapSwizzle::None, X, 3, dims, strides, box);
+    if (rc) return rc;
+  } else {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
     const uint64_t strides[1] = {(uint64_t)ldx * 4};
     const uint32_t box[2] = {(uint32_t)kKc, (uint32_t)kRows};
@@ -323,14 +454,23 @@ extern "C" int msm_linear_fwd(const float* X, int64_t ldx, const void* prepared,
     int rc = tc::encode_tensor_map(&wmap, tc::TmapType::BF16, tc::TmapSwizzle::None, prepared, 4, dims, strides, box);
     if (rc) return rc;
   }
-  {
+  if (y_nchw) {
+    ymap = wmap;  // unused by the kernel in this mode
+  } else if (x_nchw) {
+    const uint64_t dims[3] = {(uint64_t)N, (uint64_t)Mb, (uint64_t)Bt};
+    const uint64_t strides[2] = {(uint64_t)ldy * 4, (uint64_t)ldy * 4 * (uint64_t)Mb};
+    const uint32_t box[3] = {32, 32, 1};
+    int rc = tc::encode_tensor_map(&ymap, tc::TmapType::F32, tc::TmapSwizzle::B128, Y, 3, dims, strides, box);
+    if (rc) return rc;
+  } else {
     const uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
     const uint64_t strides[1] = {(uint64_t)ldy * 4};
-    const uint32_t box[2] = {32, (uint32_t)kRows};
+    const uint32_t box[2] = {32, 32};
     int rc = tc::encode_tensor_map(&ymap, tc::TmapType::F32, tc::TmapSwizzle::B128, Y, 2, dims, strides, box);
     if (rc) return rc;
   }
-  const size_t smem = 1024 + (size_t)kStages * kAStageBytes + 2 * kYStageBytes + (size_t)kStages * 128 * P.BN + 512 + 512;
+  const size_t smem = 1024 + (size_t)kXStages * kAStageBytes + 8 * kYWarpBytes + (size_t)kStages * 128 * P.BN +
+                      4 * 384 * sizeof(float) + 512;
   static bool configured = false;
   if (!configured) {
     MSM_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
@@ -340,6 +480,47 @@ extern "C" int msm_linear_fwd(const float* X, int64_t ldx, const void* prepared,
   const int grid = tiles < num_sms() ? tiles : num_sms();
   // >= 116 KB of dynamic shared memory keeps it at one CTA per SM (each CTA allocates all of TMEM)
   const size_t req = smem < (size_t)(120 << 10) ? (size_t)(120 << 10) : smem;
-  linear_tc_kernel<<<grid, kThreads, req, static_cast<cudaStream_t>(stream)>>>(xmap, wmap, ymap, P);
+  linear_tc_kernel<<<grid, kThreads, req, st>>>(xmap, wmap, ymap, P);
   return check_launch("linear_tc_kernel");
+}
+
+}  // namespace ltc
+}  // namespace msm
+
+extern "C" int msm_linear_fwd(const float* X, int64_t ldx, const void* prepared, const float* bias, float* Y,
+                              int64_t ldy, int M, int N, int K, int act, void* stream) {
+  MSM_REQUIRE(X && prepared && Y, "X, prepared, Y must be non-null");
+  MSM_REQUIRE(M > 0 && N > 0 && K > 0, "sizes must be positive");
+  MSM_REQUIRE(K % 32 == 0 && N % 32 == 0, "N and K must be multiples of 32");
+  MSM_REQUIRE(act == 0 || act == 1, "act must be 0 (none) or 1 (relu)");
+  MSM_REQUIRE(ldx >= K && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0, "X rows must be 16-byte aligned");
+  MSM_REQUIRE(ldy >= N && ldy % 4 == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0, "Y rows must be 16-byte aligned");
+  return msm::ltc::launch(X, ldx, prepared, bias, Y, ldy, M, N, K, act, 0, 0, 1, M, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int msm_linear_ln_fwd(const float* X, int64_t ldx, const void* prepared, const float* bias,
+                                 const float* residual, int64_t ldr, const float* gamma, const float* beta, float eps,
+                                 float* Y, int64_t ldy, int M, int N, int K, void* stream) {
+  MSM_REQUIRE(X && prepared && Y && residual && gamma && beta, "X, prepared, residual, gamma, beta, Y must be non-null");
+  MSM_REQUIRE(M > 0 && K > 0 && K % 32 == 0, "M must be positive and K a positive multiple of 32");
+  MSM_REQUIRE(N == 32 || N == 64, "the fused LayerNorm epilogue takes N = 32 or 64");
+  MSM_REQUIRE(ldx >= K && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0, "X rows must be 16-byte aligned");
+  MSM_REQUIRE(ldy >= N && ldy % 4 == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0, "Y rows must be 16-byte aligned");
+  MSM_REQUIRE(ldr >= N && ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
+              "residual rows must be 16-byte aligned");
+  msm::ltc::LnArgs ln;
+  ln.residual = residual; ln.ldr = ldr; ln.gamma = gamma; ln.beta = beta; ln.eps = eps;
+  return msm::ltc::launch(X, ldx, prepared, bias, Y, ldy, M, N, K, 0, 0, 0, 1, M, static_cast<cudaStream_t>(stream), ln);
+}
+
+extern "C" int msm_conv1x1_fwd(const float* X, const void* prepared, const float* bias, float* Y, int y_nchw, int B,
+                               int HW, int N, int K, int act, void* stream) {
+  MSM_REQUIRE(X && prepared && Y, "X, prepared, Y must be non-null");
+  MSM_REQUIRE(B > 0 && HW > 0 && N > 0 && K > 0, "sizes must be positive");
+  MSM_REQUIRE(K % 32 == 0 && N % 32 == 0, "N and K must be multiples of 32");
+  MSM_REQUIRE(act == 0 || act == 1, "act must be 0 (none) or 1 (relu)");
+  MSM_REQUIRE(HW % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0, "H*W must be a multiple of 4 and X 16-byte aligned");
+  MSM_REQUIRE((reinterpret_cast<uintptr_t>(Y) & 15) == 0, "Y must be 16-byte aligned");
+  return msm::ltc::launch(X, 0, prepared, bias, Y, N, B * HW, N, K, act, 1, y_nchw ? 1 : 0, B, HW,
+                          static_cast<cudaStream_t>(stream));
 }

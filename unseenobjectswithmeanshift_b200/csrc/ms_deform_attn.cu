@@ -118,13 +118,15 @@ __global__ void __launch_bounds__(256) msda_fwd_kernel(const float* __restrict__
 // in five elementwise passes over [N,Lq,M,L,P,2] tensors:  weights = softmax_{l,p}(logits),
 // loc = ref[l] + offset / (W_l, H_l)  (same operation order as the reference, so the sampled pixel
 // coordinates are the same floats), then the bilinear gather of the op itself.
-template <int VEC>
+template <int VEC, int CL, int CP>  // CL, CP: compile-time levels / points (0 = take the run-time values)
 __global__ void __launch_bounds__(256) msda_fused_fwd_kernel(const float* __restrict__ value,
                                                              const int64_t* __restrict__ shapes,
                                                              const int64_t* __restrict__ lsi,
                                                              const float* __restrict__ ol, int64_t ld_ol,
                                                              const float* __restrict__ ref, float* __restrict__ out,
-                                                             int64_t total, int S, int M, int D, int L, int Lq, int P) {
+                                                             int64_t total, int S, int M, int D, int L_rt, int Lq,
+                                                             int P_rt) {
+  const int L = CL > 0 ? CL : L_rt, P = CP > 0 ? CP : P_rt;
   __shared__ int sH[kMaxLevels], sW[kMaxLevels], sStart[kMaxLevels];
   if (threadIdx.x < L) {
     sH[threadIdx.x] = (int)shapes[2 * threadIdx.x];
@@ -144,23 +146,44 @@ __global__ void __launch_bounds__(256) msda_fused_fwd_kernel(const float* __rest
   const float* offp = ol + t * ld_ol + (int64_t)m * LP * 2;
   const float* logp = ol + t * ld_ol + (int64_t)M * LP * 2 + (int64_t)m * LP;
   const float* refp = ref + t * L * 2;
-  // softmax over the L*P logits of this head (max-shifted, like torch.softmax)
-  float mx = -INFINITY;
-  for (int i = 0; i < LP; ++i) mx = fmaxf(mx, __ldg(logp + i));
-  float den = 0.f;
-  for (int i = 0; i < LP; ++i) den += expf(__ldg(logp + i) - mx);
+  // softmax over the L*P logits of this head (max-shifted, like torch.softmax); with compile-time L, P the
+  // exponentials are computed once and live in registers
+  constexpr int NE = CL * CP > 0 ? CL * CP : 1;
+  float e[NE];
+  float mx = -INFINITY, den = 0.f;
+  if constexpr (CL * CP > 0) {
+#pragma unroll
+    for (int i = 0; i < NE; ++i) {
+      e[i] = __ldg(logp + i);
+      mx = fmaxf(mx, e[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < NE; ++i) {
+      e[i] = expf(e[i] - mx);
+      den += e[i];
+    }
+  } else {
+    for (int i = 0; i < LP; ++i) mx = fmaxf(mx, __ldg(logp + i));
+    for (int i = 0; i < LP; ++i) den += expf(__ldg(logp + i) - mx);
+  }
   const int64_t row = (int64_t)M * D;
   const float* vb = value + (int64_t)b * S * row + m * D + dv * VEC;
   float acc[VEC];
 #pragma unroll
   for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
+#pragma unroll
   for (int l = 0; l < L; ++l) {
     const int H = sH[l], W = sW[l];
     const float* vl = vb + (int64_t)sStart[l] * row;
     const float2 rp = __ldg(reinterpret_cast<const float2*>(refp) + l);
+#pragma unroll
     for (int p = 0; p < P; ++p) {
       const float2 off = __ldg(reinterpret_cast<const float2*>(offp) + l * P + p);
-      const float wgt = expf(__ldg(logp + l * P + p) - mx) / den;
+      float wgt;
+      if constexpr (CL * CP > 0)
+        wgt = e[l * P + p] / den;
+      else
+        wgt = expf(__ldg(logp + l * P + p) - mx) / den;
       const float lx = rp.x + __fdiv_rn(off.x, (float)W);
       const float ly = rp.y + __fdiv_rn(off.y, (float)H);
       const float h_im = ly * H - 0.5f;
@@ -324,15 +347,19 @@ extern "C" int msm_ms_deform_attn_fused_fwd(const float* value, const int64_t* s
   const int64_t total = (int64_t)N * Lq * M * (D / vec);
   const int threads = 256;
   const unsigned blocks = (unsigned)((total + threads - 1) / threads);
-  if (vec == 4)
-    msm::msda_fused_fwd_kernel<4><<<blocks, threads, 0, st>>>(value, spatial_shapes, level_start_index, offsets_logits,
-                                                              ld_ol, reference_points, out, total, S, M, D, L, Lq, P);
-  else if (vec == 2)
-    msm::msda_fused_fwd_kernel<2><<<blocks, threads, 0, st>>>(value, spatial_shapes, level_start_index, offsets_logits,
-                                                              ld_ol, reference_points, out, total, S, M, D, L, Lq, P);
-  else
-    msm::msda_fused_fwd_kernel<1><<<blocks, threads, 0, st>>>(value, spatial_shapes, level_start_index, offsets_logits,
-                                                              ld_ol, reference_points, out, total, S, M, D, L, Lq, P);
+#define MSM_FUSED_LAUNCH(V, CL, CP)                                                                                  \
+  msm::msda_fused_fwd_kernel<V, CL, CP><<<blocks, threads, 0, st>>>(value, spatial_shapes, level_start_index,        \
+                                                                    offsets_logits, ld_ol, reference_points, out,    \
+                                                                    total, S, M, D, L, Lq, P)
+  const bool l3p4 = (L == 3 && P == 4);  // every UOIS config
+  if (vec == 4) {
+    if (l3p4) MSM_FUSED_LAUNCH(4, 3, 4); else MSM_FUSED_LAUNCH(4, 0, 0);
+  } else if (vec == 2) {
+    if (l3p4) MSM_FUSED_LAUNCH(2, 3, 4); else MSM_FUSED_LAUNCH(2, 0, 0);
+  } else {
+    if (l3p4) MSM_FUSED_LAUNCH(1, 3, 4); else MSM_FUSED_LAUNCH(1, 0, 0);
+  }
+#undef MSM_FUSED_LAUNCH
   return msm::check_launch("msda_fused_fwd_kernel");
 }
 

@@ -43,8 +43,19 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
         return self.norm2(src + self.dropout3(self.linear2(self.dropout2(self.activation(self.linear1(src))))))
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
-        a = self.self_attn(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes, level_start_index,
-                           padding_mask)
+        attn = self.self_attn
+        if not self.training and self.activation is F.relu and src.is_contiguous() \
+                and self.linear1.weight.shape[0] % 32 == 0 and padding_mask is None \
+                and reference_points.shape[-1] == 2 \
+                and ops.linear_ln_supported(src, attn.output_proj.weight, src, self.norm1) \
+                and ops.linear_ln_supported(src, attn.output_proj.weight, src, self.norm2):
+            # inference: both post-norm residual blocks end in a GEMM whose epilogue does the add + LayerNorm
+            sampled = attn(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes, level_start_index,
+                           padding_mask, project=False)
+            src = ops.linear_ln(sampled, attn.output_proj.weight, attn.output_proj.bias, src, self.norm1)
+            h = ops.dense(src, self.linear1.weight, self.linear1.bias, relu=True)
+            return ops.linear_ln(h, self.linear2.weight, self.linear2.bias, src, self.norm2)
+        a = attn(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes, level_start_index, padding_mask)
         return self.forward_ffn(self.norm1(src + self.dropout1(a)))
 
 
@@ -204,15 +215,16 @@ class MSDeformAttnPixelDecoder(nn.Module):
             srcs, pos = [], []
             for idx, f in enumerate(self.transformer_in_features[::-1]):
                 x = features[f].float()
-                srcs.append(self.input_proj[idx](x))
+                proj = self.input_proj[idx]
+                srcs.append(proj[1](ops.conv1x1_layer(proj[0], x)))
                 pos.append(self.pe_layer(x))
             y, shapes, level_start_index = self.transformer(srcs, pos)
             B = y.shape[0]
             sizes = [h * w for h, w in shapes]
             out = [z.transpose(1, 2).reshape(B, -1, *shapes[i]) for i, z in enumerate(torch.split(y, sizes, dim=1))]
             for idx, f in enumerate(self.in_features[:self.num_fpn_levels][::-1]):
-                cur = self.lateral_convs[idx](features[f].float())
+                cur = ops.conv1x1_layer(self.lateral_convs[idx], features[f].float())
                 up = F.interpolate(out[-1], size=cur.shape[-2:], mode="bilinear", align_corners=False)
                 out.append(self.output_convs[idx](cur + up))
             multi_scale = out[:self.maskformer_num_feature_levels]
-            return self.mask_features(out[-1]), out[0], multi_scale
+            return ops.conv1x1_layer(self.mask_features, out[-1]), out[0], multi_scale

@@ -57,7 +57,7 @@ class MSDeformAttn(nn.Module):
         constant_(self.output_proj.bias.data, 0.)
 
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
-                input_padding_mask=None):
+                input_padding_mask=None, project=True):
         """query [N,Lq,C]; reference_points [N,Lq,L,2] (or 4); input_flatten [N,S,C];
         input_spatial_shapes int64 [L,2]; input_level_start_index int64 [L] -> [N,Lq,C]."""
         N, Lq, _ = query.shape
@@ -81,6 +81,8 @@ class MSDeformAttn(nn.Module):
                 # inference: softmax + sampling locations + gather in one kernel
                 output = ops.ms_deform_attn_fused_forward(value.contiguous(), input_spatial_shapes,
                                                           input_level_start_index, ow, reference_points, L, P)
+                if not project:  # extension: the caller fuses output_proj with its residual + LayerNorm
+                    return output
                 return ops.dense(output, self.output_proj.weight, self.output_proj.bias)
         offsets = ow[..., :n_off].reshape(N, Lq, M, L, P, 2)
         weights = F.softmax(ow[..., n_off:].reshape(N, Lq, M, L * P), -1).view(N, Lq, M, L, P)
@@ -95,4 +97,6 @@ class MSDeformAttn(nn.Module):
                 "Last dim of reference_points must be 2 or 4, but get {} instead.".format(reference_points.shape[-1]))
         output = MSDeformAttnFunction.apply(value.contiguous(), input_spatial_shapes, input_level_start_index,
                                             locations.contiguous(), weights.contiguous(), self.im2col_step)
+        if not project:
+            return output
         return ops.dense(output, self.output_proj.weight, self.output_proj.bias)

@@ -332,12 +332,16 @@ class _MeanShiftDecoderBase(nn.Module):
         for l in range(L):
             h, w = x[l].shape[-2:]
             sizes.append((h, w))
-            xl = x[l].float().flatten(2).transpose(1, 2)  # [B,S,Cin]
+            xf = x[l].float()
             proj = self.input_proj[l]
             if isinstance(proj, nn.Conv2d):
-                s = F.linear(xl, proj.weight.flatten(1), proj.bias + self.level_embed.weight[l])  # xl is a transposed view
+                bias = proj.bias + self.level_embed.weight[l]
+                if not torch.is_grad_enabled() and ops.conv1x1_supported(xf, proj.weight):
+                    s = ops.conv1x1(xf, proj.weight, bias, tokens_out=True)      # NCHW in, [B,S,C] out
+                else:  # e.g. the pixel decoder's token-major maps seen through a transposed view
+                    s = ops.dense(xf.flatten(2).transpose(1, 2), proj.weight.flatten(1), bias)
             else:
-                s = xl + self.level_embed.weight[l]
+                s = xf.flatten(2).transpose(1, 2) + self.level_embed.weight[l]
             src.append(s)
             key_in.append(s + self.pe_layer.table(h, w, dev))
 

@@ -213,6 +213,72 @@ def linear(x, weight, bias=None, relu=False, out=None):
     return out
 
 
+def linear_ln_supported(x, weight, residual, norm):
+    """Shapes msm_linear_ln_fwd takes: N in (32, 64), contiguous fp32 residual rows, an affine LayerNorm over N."""
+    N = weight.shape[0]
+    return (not torch.is_grad_enabled() and linear_supported(x, weight) and N in (32, 64)
+            and isinstance(norm, torch.nn.LayerNorm) and norm.elementwise_affine and norm.bias is not None
+            and tuple(norm.normalized_shape) == (N,) and residual.is_cuda and residual.dtype == torch.float32
+            and residual.is_contiguous() and residual.shape[-1] == N and residual.numel() // N == x.numel() // x.shape[-1])
+
+
+def linear_ln(x, weight, bias, residual, norm):
+    """norm(residual + x @ weight.T + bias) with the add and the LayerNorm fused into the GEMM epilogue."""
+    _require(x, "x")
+    N, K = weight.shape
+    x2 = x.reshape(-1, K)
+    if x2.stride(1) != 1 or x2.stride(0) % 4 != 0 or x2.data_ptr() % 16 != 0:
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    out = torch.empty_like(residual)
+    wp = prepare_linear_weight(weight.detach())
+    b = None if bias is None else bias.detach().contiguous()
+    rc = _lib.lib().msm_linear_ln_fwd(x2.data_ptr(), x2.stride(0), wp.data_ptr(), b.data_ptr() if b is not None else None,
+                                      residual.data_ptr(), N, norm.weight.data_ptr(), norm.bias.data_ptr(),
+                                      float(norm.eps), out.data_ptr(), N, M, N, K, _stream())
+    check(rc, "msm_linear_ln_fwd")
+    return out
+
+
+def conv1x1_supported(x, weight):
+    if os.environ.get("MSM_DISABLE_TC_LINEAR", "") not in ("", "0"):
+        return False
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous() and weight.dim() == 4
+            and weight.shape[2] == 1 and weight.shape[3] == 1 and weight.is_contiguous()
+            and weight.shape[0] % 32 == 0 and weight.shape[1] % 32 == 0 and x.shape[1] == weight.shape[1]
+            and (x.shape[2] * x.shape[3]) % 4 == 0 and x.data_ptr() % 16 == 0)
+
+
+def conv1x1(x, weight, bias=None, relu=False, tokens_out=False):
+    """kernel_size=1 convolution on the tensor cores. x [B,K,H,W] contiguous, weight [N,K,1,1];
+    returns [B,N,H,W] (default) or the token-major [B,H*W,N] the decoders consume."""
+    _require(x, "x")
+    B, K, H, W = x.shape
+    N = weight.shape[0]
+    wp = prepare_linear_weight(weight.detach().view(N, K))
+    b = None if bias is None else _require(bias.detach(), "bias").contiguous()
+    out = torch.empty((B, H * W, N) if tokens_out else (B, N, H, W), device=x.device, dtype=torch.float32)
+    rc = _lib.lib().msm_conv1x1_fwd(x.data_ptr(), wp.data_ptr(), b.data_ptr() if b is not None else None, out.data_ptr(),
+                                    0 if tokens_out else 1, B, H * W, N, K, 1 if relu else 0, _stream())
+    check(rc, "msm_conv1x1_fwd")
+    return out
+
+
+def conv1x1_layer(conv, x):
+    """Forward of a kernel_size=1 Conv2d module (detectron2-style wrapper with optional .norm / .activation,
+    or a plain nn.Conv2d): tensor-core path for inference on shapes it takes, the module itself otherwise."""
+    needs_grad = torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad)
+    if needs_grad or conv.kernel_size != (1, 1) or conv.stride != (1, 1) or conv.groups != 1 \
+            or not conv1x1_supported(x, conv.weight):
+        return conv(x)
+    y = conv1x1(x, conv.weight, conv.bias)
+    if getattr(conv, "norm", None) is not None:
+        y = conv.norm(y)
+    if getattr(conv, "activation", None) is not None:
+        y = conv.activation(y)
+    return y
+
+
 def dense(x, weight, bias=None, relu=False):
     """The layer call the modules use: tensor-core ``linear`` for inference on shapes it takes,
     torch's F.linear (cuBLAS fp32, autograd-capable) when gradients are needed or N/K are not
@@ -413,6 +479,19 @@ def _work_linear(x, w, bias=None, relu=False, out=None):
     return f"M{M} N{N} K{K}", 4.0 * (M * K + M * N) + 4.0 * N * K, 2.0 * M * N * K
 
 
+def _work_linear_ln(x, w, bias, residual, norm):
+    N, K = w.shape
+    M = x.numel() // K
+    return f"+res+LN M{M} N{N} K{K}", 4.0 * (M * K + 2 * M * N) + 4.0 * N * K, 2.0 * M * N * K
+
+
+def _work_conv(x, weight, bias=None, relu=False, tokens_out=False):
+    B, K, H, W = x.shape
+    N = weight.shape[0]
+    M = B * H * W
+    return f"conv1x1 M{M} N{N} K{K}", 4.0 * (M * K + M * N) + 4.0 * N * K, 2.0 * M * N * K
+
+
 def _work_msda(value, shapes, lsi, loc, aw, *a, **k):
     N, S, M, D = value.shape
     Lq = loc.shape[1]
@@ -439,6 +518,8 @@ vmf_attention_weights = _instrument("vmf_attention_weights", 1)(vmf_attention_we
 mask_logits = _instrument("mask_logits", 1, _work_mask)(mask_logits)
 mask_to_attn_bits = _instrument("mask_to_attn_bits", 1, _work_bits)(mask_to_attn_bits)
 linear = _instrument("linear", 1, _work_linear)(linear)
+conv1x1 = _instrument("linear", 1, _work_conv)(conv1x1)
+linear_ln = _instrument("linear", 1, _work_linear_ln)(linear_ln)
 ms_deform_attn_forward = _instrument("ms_deform_attn_forward", 1, _work_msda)(ms_deform_attn_forward)
 ms_deform_attn_fused_forward = _instrument("ms_deform_attn_forward", 1, _work_msda_fused)(ms_deform_attn_fused_forward)
 ms_deform_attn_backward = _instrument("ms_deform_attn_backward", 1)(ms_deform_attn_backward)
