@@ -10,6 +10,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -207,6 +208,23 @@ __device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t&
   hi = pack_bf16(x, y);
   const float xh = __uint_as_float(hi << 16), yh = __uint_as_float(hi & 0xFFFF0000u);
   lo = pack_bf16(x - xh, y - yh);
+}
+
+// ------------------------------------------------------------------------------------------ fp16 hi/lo split
+// Same three-pass scheme with IEEE half operands: 11 + 11 significant bits, i.e. ~2^-22 relative instead of
+// ~2^-17, for operands known to stay inside the fp16 range - unit vectors, probabilities, projected values
+// (|x| < 65504; components below 2^-14 are kept to an absolute 2^-25, which is what matters for unit vectors).
+__device__ __forceinline__ void split2h(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x, y);  // x in the low half
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x - f.x, y - f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// Instruction descriptor for kind::f16 with fp16 A/B (format code 0) and fp32 D.
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
 }
 
 // host side: encode a tiled tensor map without linking libcuda (entry point fetched from the runtime)

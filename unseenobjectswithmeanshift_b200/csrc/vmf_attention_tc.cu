@@ -7,12 +7,14 @@
 //
 // Same algorithm as the CUDA-core kernel in vmf_attention.cu (fixed shift -kappa instead of a
 // running max, key axis split across CTAs, partial numerators / denominators summed in a fixed
-// order by vmf_finalize_kernel), with both contractions on the tensor cores in bf16x3 split
-// precision (tc.cuh). One CTA = one (batch, head) problem x one range of 128-key tiles:
+// order by vmf_finalize_kernel), with both contractions on the tensor cores in fp16x3 split
+// precision (tc.cuh: hi/lo halves, three passes, ~2^-22 per product - every operand here is a unit
+// vector, a probability or a projected value, well inside the fp16 range; |k|, |v| < 65504 is required when
+// the caller does not ask for normalisation). One CTA = one (batch, head) problem x one range of 128-key tiles:
 //
 //   warps 8-15  loaders, two teams on alternate tiles: K and V rows are read from global memory
 //               (coalesced 128-byte row segments), K rows L2-normalised in fp32, both split to
-//               bf16 hi/lo and stored in the UMMA canonical no-swizzle layout
+//               fp16 hi/lo and stored in the UMMA canonical no-swizzle layout
 //               [d/8][key/8][key%8][d%8] - which is at once the K-major view of K (B operand of
 //               S = Q K^T) and the MN-major view of V (B operand of O = P V), so when k == v
 //               (mean-shift) one copy serves both products
@@ -20,7 +22,7 @@
 //               pipe works on the next score tile while the softmax warps turn S(t) into P(t)
 //   warps 0-7   softmax: tcgen05.ld of S (lane = query, column = key), p = 2^(c*s - c),
 //               blocked keys (1 bit per query x key, shared by all heads) and keys beyond Ns -> 0,
-//               row sums, bf16 hi/lo split, tcgen05.st of P back into TMEM as the A operand of
+//               row sums, fp16 hi/lo split, tcgen05.st of P back into TMEM as the A operand of
 //               the second product. Two warps per TMEM lane quadrant, 64 key columns each.
 //               Prologue: q rows normalised, split and stored into TMEM (A operand of S).
 //               Epilogue: O and the row sums go to the partial buffers.
@@ -91,10 +93,10 @@ __device__ __forceinline__ void scale8(float4& a, float4& b, float s) {
 }
 __device__ __forceinline__ void split_store8(const float4& a, const float4& b, uint8_t* hi_dst, uint8_t* lo_dst) {
   uint4 hi, lo;
-  tc::split2(a.x, a.y, hi.x, lo.x);
-  tc::split2(a.z, a.w, hi.y, lo.y);
-  tc::split2(b.x, b.y, hi.z, lo.z);
-  tc::split2(b.z, b.w, hi.w, lo.w);
+  tc::split2h(a.x, a.y, hi.x, lo.x);
+  tc::split2h(a.z, a.w, hi.y, lo.y);
+  tc::split2h(b.x, b.y, hi.z, lo.z);
+  tc::split2h(b.z, b.w, hi.w, lo.w);
   *reinterpret_cast<uint4*>(hi_dst) = hi;
   *reinterpret_cast<uint4*>(lo_dst) = lo;
 }
@@ -102,7 +104,7 @@ __device__ __forceinline__ void split_store8(const float4& a, const float4& b, u
 template <int HD, bool SHARED>
 __global__ void __launch_bounds__(kThreads, 1) vmf_attn_tc_kernel(const Params P) {
   constexpr int CH = HD / 32;                      // 8-channel chunks per loader thread and row
-  constexpr uint32_t kOpBytes = kTile * HD * 2;    // one bf16 operand (hi or lo) of one tile
+  constexpr uint32_t kOpBytes = kTile * HD * 2;    // one fp16 operand (hi or lo) of one tile
   constexpr uint32_t kStageBytes = (SHARED ? 2 : 4) * kOpBytes;
   constexpr uint32_t kLboK = (kTile / 8) * 128;    // byte stride between 8-channel groups = 2048
   extern __shared__ __align__(128) uint8_t smem[];
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_tc_kernel(const Params P
     const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
 
     if (half == 0) {
-      // ---- prologue: q row -> (normalise) -> bf16 hi/lo -> TMEM A operand of the score product
+      // ---- prologue: q row -> (normalise) -> fp16 hi/lo -> TMEM A operand of the score product
       const float* qp = P.q + b * P.q_sb + h * P.q_sh + (int64_t)qi * P.q_sl;
       float x[HD];
       float ss = 0.f;
@@ -173,7 +175,7 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_tc_kernel(const Params P
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          tc::split2(x[c16 * 32 + 2 * j] * inv, x[c16 * 32 + 2 * j + 1] * inv, hi[j], lo[j]);
+          tc::split2h(x[c16 * 32 + 2 * j] * inv, x[c16 * 32 + 2 * j + 1] * inv, hi[j], lo[j]);
         tc::tmem_st16(lane_addr + kColQ + c16 * 16, hi);
         tc::tmem_st16(lane_addr + kColQ + HD / 2 + c16 * 16, lo);
       }
@@ -189,17 +191,23 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_tc_kernel(const Params P
     float den = 0.f;
     const float c = P.c;
 
-    for (int j = 0; j < nt; ++j) {
-      const int buf = j & 1;
-      const int key0 = (tile_begin + j) * kTile + half * 64;  // first key of this warp's 64 columns
-      // blocked-key words of this row (+ keys beyond Ns are treated as blocked)
-      uint32_t w[2] = {0u, 0u};
-      if (row_masked) {
-        const int wi = key0 >> 5;
+    // blocked-key words of this row for one tile; fetched one tile ahead so the load latency is off the path
+    auto load_words = [&](int j, uint32_t (&w)[2]) {
+      w[0] = w[1] = 0u;
+      if (row_masked && j < nt) {
+        const int wi = ((tile_begin + j) * kTile + half * 64) >> 5;
         if (wi < P.words_per_row) w[0] = __ldg(brow + wi);
         if (wi + 1 < P.words_per_row) w[1] = __ldg(brow + wi + 1);
       }
-      const int nv = P.Ns - key0;  // valid keys in [key0, key0 + 64)
+    };
+    uint32_t wnext[2];
+    load_words(0, wnext);
+    for (int j = 0; j < nt; ++j) {
+      const int buf = j & 1;
+      const int key0 = (tile_begin + j) * kTile + half * 64;  // first key of this warp's 64 columns
+      uint32_t w[2] = {wnext[0], wnext[1]};
+      load_words(j + 1, wnext);
+      const int nv = P.Ns - key0;  // valid keys in [key0, key0 + 64); keys beyond Ns are treated as blocked
       if (nv < 32) w[0] |= (nv <= 0) ? 0xffffffffu : ~((1u << nv) - 1u);
       if (nv < 64) w[1] |= (nv <= 32) ? 0xffffffffu : ~((1u << (nv - 32)) - 1u);
 
@@ -224,7 +232,7 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_tc_kernel(const Params P
           if ((wm >> (2 * i)) & 1u) p0 = 0.f;
           if ((wm >> (2 * i + 1)) & 1u) p1 = 0.f;
           den += p0 + p1;
-          tc::split2(p0, p1, hi[i], lo[i]);
+          tc::split2h(p0, p1, hi[i], lo[i]);
         }
         if (ch == 0) {  // P is single-buffered: the previous tile's second product must have retired
           tc::mbar_wait(p_empty, (j & 1) ^ 1);
@@ -295,12 +303,15 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_tc_kernel(const Params P
 #pragma unroll
         for (int u = 0; u < BATCH; ++u) {
           const int kg = (it0 + u) * 4 + wq;  // 8-key group of the tile
-          float ss = 0.f;
+          float inv = 1.f;
+          if (norm_k) {
+            float ss = 0.f;
 #pragma unroll
-          for (int cc = 0; cc < CH; ++cc) ss += sumsq8(ka[u][cc], kb[u][cc]);
-          ss += __shfl_xor_sync(0xffffffffu, ss, 8);
-          ss += __shfl_xor_sync(0xffffffffu, ss, 16);
-          const float inv = norm_k ? 1.f / fmaxf(sqrtf(ss), 1e-12f) : 1.f;
+            for (int cc = 0; cc < CH; ++cc) ss += sumsq8(ka[u][cc], kb[u][cc]);
+            ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+            ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+            inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+          }
 #pragma unroll
           for (int cc = 0; cc < CH; ++cc) {
             const int dg = dgl + 4 * cc;
@@ -318,8 +329,8 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_tc_kernel(const Params P
   } else {
     // =================================================================== MMA issuer
     if (lane == 0) {
-      const uint32_t idesc_s = tc::idesc_bf16(128, kTile, false, false);  // A (TMEM) K-major, B K-major
-      const uint32_t idesc_o = tc::idesc_bf16(128, HD, false, true);      // B = V, MN-major
+      const uint32_t idesc_s = tc::idesc_f16(128, kTile, false, false);  // A (TMEM) K-major, B K-major
+      const uint32_t idesc_o = tc::idesc_f16(128, HD, false, true);      // B = V, MN-major
       const uint32_t q_hi = tmem_base + kColQ, q_lo = q_hi + HD / 2;
       const uint32_t p_hi = tmem_base + kColP, p_lo = p_hi + 64;
       const uint32_t d_o = tmem_base + kColO;
