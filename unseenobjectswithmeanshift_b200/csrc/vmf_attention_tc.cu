@@ -7,14 +7,13 @@
 //
 // Same algorithm as the CUDA-core kernel in vmf_attention.cu (fixed shift -kappa instead of a
 // running max, key axis split across CTAs, partial numerators / denominators summed in a fixed
-// order by vmf_finalize_kernel), with both contractions on the tensor cores in fp16x3 split
-// precision (tc.cuh: hi/lo halves, three passes, ~2^-22 per product - every operand here is a unit
-// vector, a probability or a projected value, well inside the fp16 range; |k|, |v| < 65504 is required when
-// the caller does not ask for normalisation). One CTA = one (batch, head) problem x one range of 128-key tiles:
+// order by vmf_finalize_kernel), with both contractions on the tensor cores in split precision
+// (tc.cuh: hi/lo halves, three passes): fp16 halves (~2^-22 per product) for the score product of
+// unit-normalised q and k, bf16 halves (~2^-17, full exponent range) for the weights and values. One CTA = one (batch, head) problem x one range of 128-key tiles:
 //
 //   warps 8-15  loaders, two teams on alternate tiles: K and V rows are read from global memory
 //               (coalesced 128-byte row segments), K rows L2-normalised in fp32, both split to
-//               fp16 hi/lo and stored in the UMMA canonical no-swizzle layout
+//               16-bit hi/lo halves and stored in the UMMA canonical no-swizzle layout
 //               [d/8][key/8][key%8][d%8] - which is at once the K-major view of K (B operand of
 //               S = Q K^T) and the MN-major view of V (B operand of O = P V), so when k == v
 //               (mean-shift) one copy serves both products
@@ -22,7 +21,7 @@
 //               pipe works on the next score tile while the softmax warps turn S(t) into P(t)
 //   warps 0-7   softmax: tcgen05.ld of S (lane = query, column = key), p = 2^(c*s - c),
 //               blocked keys (1 bit per query x key, shared by all heads) and keys beyond Ns -> 0,
-//               row sums, fp16 hi/lo split, tcgen05.st of P back into TMEM as the A operand of
+//               row sums, bf16 hi/lo split, tcgen05.st of P back into TMEM as the A operand of
 //               the second product. Two warps per TMEM lane quadrant, 64 key columns each.
 //               Prologue: q rows normalised, split and stored into TMEM (A operand of S).
 //               Epilogue: O and the row sums go to the partial buffers.
@@ -91,20 +90,33 @@ __device__ __forceinline__ void scale8(float4& a, float4& b, float s) {
   a.x *= s; a.y *= s; a.z *= s; a.w *= s;
   b.x *= s; b.y *= s; b.z *= s; b.w *= s;
 }
+template <bool F16>
+__device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint32_t& lo) {
+  if constexpr (F16)
+    tc::split2h(x, y, hi, lo);
+  else
+    tc::split2(x, y, hi, lo);
+}
+template <bool F16>
 __device__ __forceinline__ void split_store8(const float4& a, const float4& b, uint8_t* hi_dst, uint8_t* lo_dst) {
   uint4 hi, lo;
-  tc::split2h(a.x, a.y, hi.x, lo.x);
-  tc::split2h(a.z, a.w, hi.y, lo.y);
-  tc::split2h(b.x, b.y, hi.z, lo.z);
-  tc::split2h(b.z, b.w, hi.w, lo.w);
+  split_pair<F16>(a.x, a.y, hi.x, lo.x);
+  split_pair<F16>(a.z, a.w, hi.y, lo.y);
+  split_pair<F16>(b.x, b.y, hi.z, lo.z);
+  split_pair<F16>(b.z, b.w, hi.w, lo.w);
   *reinterpret_cast<uint4*>(hi_dst) = hi;
   *reinterpret_cast<uint4*>(lo_dst) = lo;
 }
 
-template <int HD, bool SHARED>
+// QK16: the score product runs on fp16 hi/lo operands (both q and k are unit-normalised by the kernel, so they
+// are inside the fp16 range and keep 22 bits: kappa multiplies the score error inside the exponential).
+// P and V always use bf16 hi/lo: a row's weights exp(kappa (cos - 1)) may ALL be tiny (no key near the query),
+// which needs bf16's exponent range; their error enters the output unamplified.
+template <int HD, bool SHARED, bool QK16>
 __global__ void __launch_bounds__(kThreads, 1) vmf_attn_tc_kernel(const Params P) {
+  static_assert(!(SHARED && QK16), "a shared k == v copy serves both products and must be bf16");
   constexpr int CH = HD / 32;                      // 8-channel chunks per loader thread and row
-  constexpr uint32_t kOpBytes = kTile * HD * 2;    // one fp16 operand (hi or lo) of one tile
+  constexpr uint32_t kOpBytes = kTile * HD * 2;    // one 16-bit operand (hi or lo) of one tile
   constexpr uint32_t kStageBytes = (SHARED ? 2 : 4) * kOpBytes;
   constexpr uint32_t kLboK = (kTile / 8) * 128;    // byte stride between 8-channel groups = 2048
   extern __shared__ __align__(128) uint8_t smem[];
@@ -158,7 +170,7 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_tc_kernel(const Params P
     const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
 
     if (half == 0) {
-      // ---- prologue: q row -> (normalise) -> fp16 hi/lo -> TMEM A operand of the score product
+      // ---- prologue: q row -> (normalise) -> 16-bit hi/lo -> TMEM A operand of the score product
       const float* qp = P.q + b * P.q_sb + h * P.q_sh + (int64_t)qi * P.q_sl;
       float x[HD];
       float ss = 0.f;
@@ -175,7 +187,7 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_tc_kernel(const Params P
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          tc::split2h(x[c16 * 32 + 2 * j] * inv, x[c16 * 32 + 2 * j + 1] * inv, hi[j], lo[j]);
+          split_pair<QK16>(x[c16 * 32 + 2 * j] * inv, x[c16 * 32 + 2 * j + 1] * inv, hi[j], lo[j]);
         tc::tmem_st16(lane_addr + kColQ + c16 * 16, hi);
         tc::tmem_st16(lane_addr + kColQ + HD / 2 + c16 * 16, lo);
       }
@@ -232,7 +244,7 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_tc_kernel(const Params P
           if ((wm >> (2 * i)) & 1u) p0 = 0.f;
           if ((wm >> (2 * i + 1)) & 1u) p1 = 0.f;
           den += p0 + p1;
-          tc::split2h(p0, p1, hi[i], lo[i]);
+          tc::split2(p0, p1, hi[i], lo[i]);
         }
         if (ch == 0) {  // P is single-buffered: the previous tile's second product must have retired
           tc::mbar_wait(p_empty, (j & 1) ^ 1);
@@ -317,8 +329,8 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_tc_kernel(const Params P
             const int dg = dgl + 4 * cc;
             const uint32_t off = (uint32_t)dg * kLboK + (uint32_t)kg * 128u + (uint32_t)key_lo * 16u;
             if (norm_k) scale8(ka[u][cc], kb[u][cc], inv);
-            split_store8(ka[u][cc], kb[u][cc], st + off, st + kOpBytes + off);
-            if (!SHARED) split_store8(va[u][cc], vb[u][cc], st + 2 * kOpBytes + off, st + 3 * kOpBytes + off);
+            split_store8<QK16>(ka[u][cc], kb[u][cc], st + off, st + kOpBytes + off);
+            if (!SHARED) split_store8<false>(va[u][cc], vb[u][cc], st + 2 * kOpBytes + off, st + 3 * kOpBytes + off);
           }
         }
       }
@@ -329,8 +341,9 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_tc_kernel(const Params P
   } else {
     // =================================================================== MMA issuer
     if (lane == 0) {
-      const uint32_t idesc_s = tc::idesc_f16(128, kTile, false, false);  // A (TMEM) K-major, B K-major
-      const uint32_t idesc_o = tc::idesc_f16(128, HD, false, true);      // B = V, MN-major
+      // A (TMEM) K-major, B K-major; B = V is MN-major
+      const uint32_t idesc_s = QK16 ? tc::idesc_f16(128, kTile, false, false) : tc::idesc_bf16(128, kTile, false, false);
+      const uint32_t idesc_o = tc::idesc_bf16(128, HD, false, true);
       const uint32_t q_hi = tmem_base + kColQ, q_lo = q_hi + HD / 2;
       const uint32_t p_hi = tmem_base + kColP, p_lo = p_hi + 64;
       const uint32_t d_o = tmem_base + kColO;
@@ -424,20 +437,20 @@ size_t vmf_tc_workspace_bytes(int G, int Nq, int Ns, int hd) {
   return (size_t)G * ns * Nq * (hd + 1) * sizeof(float);
 }
 
-template <int HD, bool SHARED>
+template <int HD, bool SHARED, bool QK16>
 static int launch_tc(const vtc::Params& P, int G, cudaStream_t st) {
   using namespace vtc;
   const size_t stage = (size_t)(SHARED ? 2 : 4) * kTile * HD * 2;
   const size_t smem = (size_t)P.nstages * stage + 256 + 128 * sizeof(float);
   static bool configured = false;
   if (!configured) {
-    MSM_CUDA(cudaFuncSetAttribute(vmf_attn_tc_kernel<HD, SHARED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MSM_CUDA(cudaFuncSetAttribute(vmf_attn_tc_kernel<HD, SHARED, QK16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kMaxSmem));
     configured = true;
   }
   // >= 116 KB of dynamic shared memory keeps it at one CTA per SM (each CTA allocates all of TMEM)
   const size_t req = smem < (size_t)(120 << 10) ? (size_t)(120 << 10) : smem;
-  vmf_attn_tc_kernel<HD, SHARED><<<G * P.nsplit, kThreads, req, st>>>(P);
+  vmf_attn_tc_kernel<HD, SHARED, QK16><<<G * P.nsplit, kThreads, req, st>>>(P);
   return check_launch("vmf_attn_tc_kernel");
 }
 
@@ -470,12 +483,15 @@ int vmf_attention_tc_partial(const float* q, int64_t q_sb, int64_t q_sh, int64_t
   P.part_acc = part_acc;
   P.part_den = part_den;
   const bool shared = (k == v) && k_sb == v_sb && k_sh == v_sh && k_sl == v_sl && !(flags & MSM_VMF_NORMALIZE_K);
+  const bool qk16 = !shared && (flags & MSM_VMF_NORMALIZE_Q) && (flags & MSM_VMF_NORMALIZE_K);
   if (hd == 32) {
     P.nstages = 4;
-    return shared ? launch_tc<32, true>(P, G, st) : launch_tc<32, false>(P, G, st);
+    if (shared) return launch_tc<32, true, false>(P, G, st);
+    return qk16 ? launch_tc<32, false, true>(P, G, st) : launch_tc<32, false, false>(P, G, st);
   }
   P.nstages = shared ? 4 : 3;
-  return shared ? launch_tc<64, true>(P, G, st) : launch_tc<64, false>(P, G, st);
+  if (shared) return launch_tc<64, true, false>(P, G, st);
+  return qk16 ? launch_tc<64, false, true>(P, G, st) : launch_tc<64, false, false>(P, G, st);
 }
 
 }  // namespace msm
