@@ -122,13 +122,104 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_meanshift(args, rank, local_rank, world, dev, sharding, ops):
+    """BASELINE.json configs[3]: standalone vMF mean-shift hill climb, 640x480x64-d unit embeddings, 100 seeds,
+    kappa=10, 10 iterations, `--batch` images per GPU (default 32). One step = the whole 10-iteration climb of
+    the batch (20 kernel launches: partial + finalize per iteration); X stays resident in HBM across iterations."""
+    import torch.nn.functional as F
+    B = args.batch if args.batch != PER_GPU_BATCH else 32
+    n, d, m, kappa, iters = 480 * 640, 64, 100, 10.0, 10
+    g = torch.Generator().manual_seed(4 + rank)
+    hostX = torch.empty(B, n, d).pin_memory()
+    for b in range(B):
+        hostX[b] = F.normalize(torch.randn(n, d, generator=g), dim=1)
+    idx = torch.stack([torch.randperm(n, generator=g)[:m] for _ in range(B)])
+    hostZ = torch.stack([hostX[b, idx[b]] for b in range(B)]).pin_memory()
+    X, Z0 = hostX.to(dev), hostZ.to(dev)
+    hostOut = torch.empty(B, m, d).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            ops.mean_shift_hill_climb(X, Z0, kappa, iters)
+        torch.cuda.synchronize()
+        sharding.barrier()
+        if rank == 0:
+            sampler.start()
+        ops.reset_stats()
+        e0.record()
+        for _ in range(args.steps):
+            Z = ops.mean_shift_hill_climb(X, Z0, kappa, iters)
+        e1.record()
+        torch.cuda.synchronize()
+        sharding.barrier()
+        ms_dev = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
+        launches = ops.launches()
+        # end to end: embeddings from pinned host memory in, modes out, every step
+        stage = torch.empty_like(X)
+        for _ in range(1):
+            stage.copy_(hostX, non_blocking=True)
+            hostOut.copy_(ops.mean_shift_hill_climb(stage, Z0, kappa, iters), non_blocking=True)
+        torch.cuda.synchronize()
+        sharding.barrier()
+        n_e2e = max(1, min(args.steps, 5))
+        e0.record()
+        for _ in range(n_e2e):
+            stage.copy_(hostX, non_blocking=True)
+            hostOut.copy_(ops.mean_shift_hill_climb(stage, Z0, kappa, iters), non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        sharding.barrier()
+        ms_e2e = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        return
+    peaks = load_peaks()
+    value = B * world * args.steps / (ms_dev / 1e3)
+    by = 4.0 * B * n * d * iters           # X read once per iteration (SURVEY.md 8d)
+    fl = 4.0 * B * m * n * d * iters
+    t = ms_dev / args.steps / 1e3
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import mean_shift as oms
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        t0 = time.perf_counter()
+        ref = oms.seed_hill_climbing_ball(hostX[0], hostZ[0], kappa, iters)
+        dt = time.perf_counter() - t0
+        err = (Z[0].cpu() - ref).abs().max().item()
+        cpu_baseline = {"value": 1.0 / dt, "unit": "images/s", "cores": cores, "kind": "port",
+                        "sample": f"1 image, {iters} iterations (oracle, fp32, {cores} threads)",
+                        "parity_on_sample": {"modes_max_abs_err": err}}
+    line = {"metric": "images/sec standalone vMF mean-shift hill climb (640x480x64-d embeddings, 100 seeds, kappa=10, "
+                      "10 iterations)", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"meanshift n=307200 d=64 m=100 kappa=10 iters=10 batch {B}/GPU",
+                       "global_batch": B * world, "parallelism": f"replicas x{world} (batch-sharded, no collective)",
+                       "l2_policy": f"inputs_exceed_l2 ({4.0 * B * n * d / 1e6:.0f} MB of embeddings per pass)"},
+            "clocks": clocks,
+            "e2e": {"value": B * world * n_e2e / (ms_e2e / 1e3), "unit": "images/s",
+                    "h2d_bytes_per_step": hostX.numel() * 4, "d2h_bytes_per_step": hostOut.numel() * 4,
+                    "ms_per_step": ms_e2e / n_e2e},
+            "gpu_launches": launches,
+            "roofline": {"kernel": "vmf_attn_tc_kernel<64, shared>", "bound": "hbm", "achieved": by / t / 1e9,
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": by / t / 1e9 / peaks["hbm_gbs"],
+                         "traffic": None, "algorithmic_bytes_per_step": by, "peak_source": peaks["source"],
+                         "tensor_TFLOPps_issued": 3.0 * fl / t / 1e12,
+                         "tensor_frac_of_bf16_peak": 3.0 * fl / t / 1e12 / peaks["bf16_tflops"]},
+            "cpu_baseline": cpu_baseline}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="r50", choices=["r50", "ucn", "crop"])
+    ap.add_argument("--workload", default="r50", choices=["r50", "ucn", "crop", "meanshift"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
@@ -152,6 +243,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     kind, B = args.workload, args.batch
+    if kind == "meanshift":
+        run_meanshift(args, rank, local_rank, world, dev, sharding, ops)
+        return
 
     head = workloads.build_head(kind).to(dev)
     host_feats = workloads.synthetic_features(kind, B, seed=rank, pin=True)

@@ -145,7 +145,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
   } else if (warp == 1) {
     // =================================================================== MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = tc::idesc_bf16(kRows, P.BN, false, false);
+      const uint32_t idesc = tc::idesc_g(kRows, P.BN, false, false);
       const uint32_t sw = tc::smem_u32(sW);
       tc::Ring as, ws;
       int t = 0;
@@ -192,14 +192,14 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         if (P.x_nchw) {  // stage = [32 channels][128 pixels]: thread = pixel, conflict-free column reads
           const float* src = reinterpret_cast<const float*>(sX + xstage * kAStageBytes) + row;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) tc::split2(src[(2 * j) * kRows], src[(2 * j + 1) * kRows], hi[j], lo[j]);
+          for (int j = 0; j < 16; ++j) tc::split2g(src[(2 * j) * kRows], src[(2 * j + 1) * kRows], hi[j], lo[j]);
         } else {         // stage = [128 rows][32 channels], 128B-swizzled
           const uint8_t* src = sX + xstage * kAStageBytes + rowoff;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const float4 x = *reinterpret_cast<const float4*>(src + (((uint32_t)c ^ sx) << 4));
-            tc::split2(x.x, x.y, hi[2 * c], lo[2 * c]);
-            tc::split2(x.z, x.w, hi[2 * c + 1], lo[2 * c + 1]);
+            tc::split2g(x.x, x.y, hi[2 * c], lo[2 * c]);
+            tc::split2g(x.z, x.w, hi[2 * c + 1], lo[2 * c + 1]);
           }
         }
         __syncwarp();
@@ -375,10 +375,10 @@ __global__ void linear_prepare_weight_kernel(const float* __restrict__ W, int64_
     const float4 a = __ldg(reinterpret_cast<const float4*>(W + (int64_t)n * ldw + kg * 8));
     const float4 b = __ldg(reinterpret_cast<const float4*>(W + (int64_t)n * ldw + kg * 8) + 1);
     uint4 hi, lo;
-    tc::split2(a.x, a.y, hi.x, lo.x);
-    tc::split2(a.z, a.w, hi.y, lo.y);
-    tc::split2(b.x, b.y, hi.z, lo.z);
-    tc::split2(b.z, b.w, hi.w, lo.w);
+    tc::split2g(a.x, a.y, hi.x, lo.x);
+    tc::split2g(a.z, a.w, hi.y, lo.y);
+    tc::split2g(b.x, b.y, hi.z, lo.z);
+    tc::split2g(b.z, b.w, hi.w, lo.w);
     out[i] = hi;
     out[total + i] = lo;
   }

@@ -119,10 +119,10 @@ mask_gemm_tc_kernel(const __grid_constant__ CUtensorMap fmap, const Params P) {
         if (it >= items) break;
         const int n = it % P.N, kg = it / P.N;
         uint4 hi, lo;
-        tc::split2(x0[u].x, x0[u].y, hi.x, lo.x);
-        tc::split2(x0[u].z, x0[u].w, hi.y, lo.y);
-        tc::split2(x1[u].x, x1[u].y, hi.z, lo.z);
-        tc::split2(x1[u].z, x1[u].w, hi.w, lo.w);
+        tc::split2g(x0[u].x, x0[u].y, hi.x, lo.x);
+        tc::split2g(x0[u].z, x0[u].w, hi.y, lo.y);
+        tc::split2g(x1[u].x, x1[u].y, hi.z, lo.z);
+        tc::split2g(x1[u].z, x1[u].w, hi.w, lo.w);
         const uint32_t off = (uint32_t)(n & 7) * 16u + (uint32_t)(n >> 3) * 128u + (uint32_t)kg * lboB;
         *reinterpret_cast<uint4*>(sEhi + off) = hi;
         *reinterpret_cast<uint4*>(sElo + off) = lo;
@@ -149,7 +149,7 @@ mask_gemm_tc_kernel(const __grid_constant__ CUtensorMap fmap, const Params P) {
   } else if (warp == 1) {
     // =================================================================== MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = tc::idesc_bf16(kPx, P.N, /*A (TMEM) K-major*/ false, /*B K-major*/ false);
+      const uint32_t idesc = tc::idesc_g(kPx, P.N, /*A (TMEM) K-major*/ false, /*B K-major*/ false);
       const uint32_t ehi = tc::smem_u32(sEhi), elo = tc::smem_u32(sElo);
       tc::Ring as;
       int t = 0;
@@ -195,7 +195,7 @@ mask_gemm_tc_kernel(const __grid_constant__ CUtensorMap fmap, const Params P) {
         const float* src = reinterpret_cast<const float*>(sF32 + fstage * kF32Stage) + px;
         uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) tc::split2(src[(2 * j) * kPx], src[(2 * j + 1) * kPx], hi[j], lo[j]);
+        for (int j = 0; j < 16; ++j) tc::split2g(src[(2 * j) * kPx], src[(2 * j + 1) * kPx], hi[j], lo[j]);
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&empty_f32[fstage]);  // fp32 stage consumed (values are in registers)
         tc::mbar_wait(&empty_a[astage], aphase ^ 1u);

@@ -227,6 +227,21 @@ __host__ __device__ constexpr uint32_t idesc_f16(int M, int N, bool a_mn_major, 
          ((uint32_t)(M >> 4) << 24);
 }
 
+// Operand format of the general GEMMs (mask head, dense layers, 1x1 convolutions): fp16 halves. The reference
+// trains this network under fp16 autocast, so its activations and weights live inside the fp16 range by
+// construction; a value beyond 65504 turns into inf/NaN in the output (loud), it is never silently clipped.
+// Set to false to fall back to bf16 halves (8 + 8 bits, full fp32 exponent range).
+constexpr bool kGemmF16 = true;
+__device__ __forceinline__ void split2g(float x, float y, uint32_t& hi, uint32_t& lo) {
+  if constexpr (kGemmF16)
+    split2h(x, y, hi, lo);
+  else
+    split2(x, y, hi, lo);
+}
+__host__ __device__ constexpr uint32_t idesc_g(int M, int N, bool a_mn_major, bool b_mn_major) {
+  return kGemmF16 ? idesc_f16(M, N, a_mn_major, b_mn_major) : idesc_bf16(M, N, a_mn_major, b_mn_major);
+}
+
 // host side: encode a tiled tensor map without linking libcuda (entry point fetched from the runtime)
 enum class TmapType { F32, BF16 };
 enum class TmapSwizzle { None, B128 };

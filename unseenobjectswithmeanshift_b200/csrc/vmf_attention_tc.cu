@@ -73,6 +73,12 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+__device__ __forceinline__ uint32_t ld_nc_volatile(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
 // 8 consecutive channels of one row: two 16-byte loads (zeros when the row is out of range)
 __device__ __forceinline__ void load8(const float* p, bool in, float4& a, float4& b) {
   if (in) {
@@ -208,8 +214,9 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_tc_kernel(const Params P
       w[0] = w[1] = 0u;
       if (row_masked && j < nt) {
         const int wi = ((tile_begin + j) * kTile + half * 64) >> 5;
-        if (wi < P.words_per_row) w[0] = __ldg(brow + wi);
-        if (wi + 1 < P.words_per_row) w[1] = __ldg(brow + wi + 1);
+        // volatile asm keeps the loads HERE, a whole tile ahead of their use (a plain __ldg is sunk to its use)
+        if (wi < P.words_per_row) w[0] = ld_nc_volatile(brow + wi);
+        if (wi + 1 < P.words_per_row) w[1] = ld_nc_volatile(brow + wi + 1);
       }
     };
     uint32_t wnext[2];
