@@ -409,15 +409,22 @@ def main():
                         "sample": f"1 run x {sb} images of the same head workload (oracle, fp32, {cores} threads)",
                         "parity_on_sample": {"pred_masks_max_err_rel_to_peak": err, "argmax_label_agreement": agree}}
 
-    line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+    metric = METRIC if kind == "r50" else {
+        "ucn": "images/sec MSMFormer head forward 640x480 (UCN RGB-D config: SimpleBasePixelDecoder + 6-layer "
+               "pretrained mean-shift decoder on the full-resolution 64-d embedding, 100 queries)",
+        "crop": "crops/sec MSMFormer head forward 224x224 (crop config: SimpleBasePixelDecoder + 8-layer "
+                "pretrained mean-shift decoder, 100 queries)"}[kind]
+    line = {"metric": metric, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{kind}-head 640x480 batch {B}/GPU, 100 queries, "
                                    f"{workloads.HEAD_CFG[kind]['dec_layers']} decoder layers",
                        "launch": "eager" if args.no_graph else "one CUDA graph per step",
                        "global_batch": B * world, "parallelism": f"replicas x{world} (batch-sharded, no collective)",
-                       "l2_policy": "inputs_exceed_l2 (295 MB features + 157 MB mask features per step)",
-                       "backbone": "excluded: cuDNN ResNet-50 is outside the hot path (SURVEY.md §8)",
+                       "l2_policy": f"inputs_exceed_l2 ({h2d / 1e6:.0f} MB of backbone features per step; every layer "
+                                    "streams the mask features and writes a fresh logits tensor)",
+                       "backbone": "excluded: the cuDNN backbone (ResNet-50 / UCN) is outside the hot path "
+                                   "(SURVEY.md §8)",
                        "gflop_per_image": workloads.head_flops_per_image(kind) / 1e9},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
