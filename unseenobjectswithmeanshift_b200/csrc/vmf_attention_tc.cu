@@ -17,17 +17,20 @@
 //               [d/8][key/8][key%8][d%8] - which is at once the K-major view of K (B operand of
 //               S = Q K^T) and the MN-major view of V (B operand of O = P V), so when k == v
 //               (mean-shift) one copy serves both products
-//   warp 16     MMA issuer: S(t+1) = Q K(t+1)^T is issued before O += P(t) V(t), so the tensor
-//               pipe works on the next score tile while the softmax warps turn S(t) into P(t)
-//   warps 0-7   softmax: tcgen05.ld of S (lane = query, column = key), p = 2^(c*s - c),
-//               blocked keys (1 bit per query x key, shared by all heads) and keys beyond Ns -> 0,
-//               row sums, bf16 hi/lo split, tcgen05.st of P back into TMEM as the A operand of
-//               the second product. Two warps per TMEM lane quadrant, 64 key columns each.
-//               Prologue: q rows normalised, split and stored into TMEM (A operand of S).
+//   warp 16     MMA issuer: S(t+2) = Q K(t+2)^T is issued right after O += P(t) V(t), into the TMEM
+//               columns P(t) just vacated (the tensor pipe executes in issue order), so there are always
+//               two score tiles in flight
+//   warps 0-7   softmax, two groups of four warps (one per TMEM lane quadrant) on ALTERNATE key tiles, so one
+//               group's barrier / TMEM-load latencies are covered by the other group's arithmetic:
+//               tcgen05.ld of S (lane = query, column = key), p = 2^(c*s - c), blocked keys (1 bit per
+//               query x key, shared by all heads, fetched one tile ahead) and keys beyond Ns -> 0, row
+//               sums, bf16 hi/lo split, tcgen05.st of P IN PLACE over the score columns just read (each
+//               32-key chunk becomes 16 hi + 16 lo columns, two keys per column) - the A operand of the
+//               second product. Prologue: q rows normalised, split and stored into TMEM (A operand of S).
 //               Epilogue: O and the row sums go to the partial buffers.
 //
-// TMEM map (512 columns): [0,256) two score tiles, [256,384) P (64 hi + 64 lo, two keys per
-// column), [384,384+HD) O, [448,448+HD) Q (HD/2 hi + HD/2 lo).
+// TMEM map (512 columns allocated): [0,128) and [128,256) score / weight tiles of the two softmax groups,
+// [256,256+HD) O, [320,320+HD) Q (HD/2 hi + HD/2 lo).
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -44,7 +47,7 @@ constexpr int kThreads = (kMmaWarp + 1) * 32;           // 544
 constexpr int kTile = 128;                              // keys per tile = UMMA N of the score product
 constexpr int kMaxStages = 4;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColS = 0, kColP = 256, kColO = 384, kColQ = 448;
+constexpr uint32_t kColS = 0, kColO = 256, kColQ = 320;
 constexpr int kMaxSmem = 232448;
 
 struct Params {
@@ -132,11 +135,9 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_tc_kernel(const Params P
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)P.nstages * kStageBytes);
   uint64_t* kv_full = bars;                    // [kMaxStages] loaders -> MMA
   uint64_t* kv_empty = kv_full + kMaxStages;   // [kMaxStages] MMA -> loaders
-  uint64_t* s_full = kv_empty + kMaxStages;    // [2] MMA -> softmax
-  uint64_t* s_empty = s_full + 2;              // [2] softmax -> MMA
-  uint64_t* p_full = s_empty + 2;              // softmax -> MMA
-  uint64_t* p_empty = p_full + 1;              // MMA -> softmax
-  uint64_t* o_full = p_empty + 1;              // MMA -> epilogue
+  uint64_t* s_full = kv_empty + kMaxStages;    // [2] MMA -> softmax group g: scores of its next tile are in TMEM
+  uint64_t* p_full = s_full + 2;               // [2] softmax group g -> MMA: weights stored over the scores
+  uint64_t* o_full = p_full + 2;               // MMA -> epilogue
   uint64_t* q_ready = o_full + 1;              // prologue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_ready + 1);
   float* s_den = reinterpret_cast<float*>(tmem_slot + 2);  // [128] row sums of the upper key half
@@ -155,10 +156,8 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_tc_kernel(const Params P
     }
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&s_full[i], 1);
-      tc::mbar_init(&s_empty[i], kSoftmaxWarps);
+      tc::mbar_init(&p_full[i], 4);
     }
-    tc::mbar_init(p_full, kSoftmaxWarps);
-    tc::mbar_init(p_empty, 1);
     tc::mbar_init(o_full, 1);
     tc::mbar_init(q_ready, 4);
     tc::fence_mbar_init();
@@ -171,11 +170,11 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_tc_kernel(const Params P
 
   if (warp < kSoftmaxWarps) {
     // =================================================================== softmax warps
-    const int qd = warp & 3, half = warp >> 2;
-    const int qi = qd * 32 + lane;  // query row = TMEM lane
+    const int qd = warp & 3, grp = warp >> 2;  // grp: softmax group = parity of the key tiles it handles
+    const int qi = qd * 32 + lane;             // query row = TMEM lane
     const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
 
-    if (half == 0) {
+    if (grp == 0) {
       // ---- prologue: q row -> (normalise) -> 16-bit hi/lo -> TMEM A operand of the score product
       const float* qp = P.q + b * P.q_sb + h * P.q_sh + (int64_t)qi * P.q_sl;
       float x[HD];
@@ -208,68 +207,63 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_tc_kernel(const Params P
     const uint32_t* brow = P.bits + (int64_t)(b * P.Nq + (qi < P.Nq ? qi : 0)) * P.words_per_row;
     float den = 0.f;
     const float c = P.c;
+    const uint32_t sp = lane_addr + kColS + (uint32_t)grp * 128u;  // this group's score / weight tile
 
-    // blocked-key words of this row for one tile; fetched one tile ahead so the load latency is off the path
-    auto load_words = [&](int j, uint32_t (&w)[2]) {
-      w[0] = w[1] = 0u;
+    // blocked-key words of this row for one 128-key tile, fetched one of this group's tiles ahead
+    auto load_words = [&](int j, uint32_t (&w)[4]) {
+      w[0] = w[1] = w[2] = w[3] = 0u;
       if (row_masked && j < nt) {
-        const int wi = ((tile_begin + j) * kTile + half * 64) >> 5;
-        // volatile asm keeps the loads HERE, a whole tile ahead of their use (a plain __ldg is sunk to its use)
-        if (wi < P.words_per_row) w[0] = ld_nc_volatile(brow + wi);
-        if (wi + 1 < P.words_per_row) w[1] = ld_nc_volatile(brow + wi + 1);
+        const int wi = ((tile_begin + j) * kTile) >> 5;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (wi + i < P.words_per_row) w[i] = ld_nc_volatile(brow + wi + i);
       }
     };
-    uint32_t wnext[2];
-    load_words(0, wnext);
-    for (int j = 0; j < nt; ++j) {
-      const int buf = j & 1;
-      const int key0 = (tile_begin + j) * kTile + half * 64;  // first key of this warp's 64 columns
-      uint32_t w[2] = {wnext[0], wnext[1]};
-      load_words(j + 1, wnext);
-      const int nv = P.Ns - key0;  // valid keys in [key0, key0 + 64); keys beyond Ns are treated as blocked
-      if (nv < 32) w[0] |= (nv <= 0) ? 0xffffffffu : ~((1u << nv) - 1u);
-      if (nv < 64) w[1] |= (nv <= 32) ? 0xffffffffu : ~((1u << (nv - 32)) - 1u);
-
-      tc::mbar_wait(&s_full[buf], (j >> 1) & 1);
-      tc::tc_fence_after();
+    uint32_t wnext[4];
+    load_words(grp, wnext);
+    int use = 0;
+    for (int j = grp; j < nt; j += 2, ++use) {
+      const int key0 = (tile_begin + j) * kTile;
+      uint32_t w[4] = {wnext[0], wnext[1], wnext[2], wnext[3]};
+      load_words(j + 2, wnext);
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        uint32_t r[32];
-        tc::tmem_ld32(lane_addr + kColS + buf * 128 + half * 64 + ch * 32, r);
+      for (int i = 0; i < 4; ++i) {  // keys beyond Ns are treated as blocked
+        const int nv = P.Ns - (key0 + 32 * i);
+        if (nv < 32) w[i] |= (nv <= 0) ? 0xffffffffu : ~((1u << nv) - 1u);
+      }
+      tc::mbar_wait(&s_full[grp], use & 1);
+      tc::tc_fence_after();
+      uint32_t r[2][32];
+      tc::tmem_ld32(sp, r[0]);
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
         tc::tmem_ld_wait();
-        if (ch == 1) {  // both halves of this warp's columns are in registers: hand the score tile back
-          tc::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&s_empty[buf]);
-        }
+        if (ch < 3) tc::tmem_ld32(sp + (ch + 1) * 32, r[(ch + 1) & 1]);  // in flight while this chunk is processed
         const uint32_t wm = w[ch];
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float p0 = ex2(fmaf(__uint_as_float(r[2 * i]), c, -c));
-          float p1 = ex2(fmaf(__uint_as_float(r[2 * i + 1]), c, -c));
+          float p0 = ex2(fmaf(__uint_as_float(r[ch & 1][2 * i]), c, -c));
+          float p1 = ex2(fmaf(__uint_as_float(r[ch & 1][2 * i + 1]), c, -c));
           if ((wm >> (2 * i)) & 1u) p0 = 0.f;
           if ((wm >> (2 * i + 1)) & 1u) p1 = 0.f;
           den += p0 + p1;
           tc::split2(p0, p1, hi[i], lo[i]);
         }
-        if (ch == 0) {  // P is single-buffered: the previous tile's second product must have retired
-          tc::mbar_wait(p_empty, (j & 1) ^ 1);
-          tc::tc_fence_after();
-        }
-        tc::tmem_st16(lane_addr + kColP + half * 32 + ch * 16, hi);
-        tc::tmem_st16(lane_addr + kColP + 64 + half * 32 + ch * 16, lo);
+        // in place: the 32 score columns of this chunk become 16 hi + 16 lo weight columns
+        tc::tmem_st16(sp + ch * 32, hi);
+        tc::tmem_st16(sp + ch * 32 + 16, lo);
       }
       tc::tmem_st_wait();
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(p_full);
+      if (lane == 0) tc::mbar_arrive(&p_full[grp]);
     }
 
     // ---- epilogue: numerator rows and row sums of this key range
-    if (half == 1) s_den[qi] = den;
+    if (grp == 1) s_den[qi] = den;
     named_bar_sync(1, kSoftmaxWarps * 32);
-    if (half == 0) {
+    if (grp == 0) {
       den += s_den[qi];
       tc::mbar_wait(o_full, 0);
       tc::tc_fence_after();
@@ -352,7 +346,6 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_tc_kernel(const Params P
       const uint32_t idesc_s = QK16 ? tc::idesc_f16(128, kTile, false, false) : tc::idesc_bf16(128, kTile, false, false);
       const uint32_t idesc_o = tc::idesc_bf16(128, HD, false, true);
       const uint32_t q_hi = tmem_base + kColQ, q_lo = q_hi + HD / 2;
-      const uint32_t p_hi = tmem_base + kColP, p_lo = p_hi + 64;
       const uint32_t d_o = tmem_base + kColO;
       const uint32_t v_lbo = P.v_desc_swap ? kLboK : 128u, v_sbo = P.v_desc_swap ? 128u : kLboK;
       const uint32_t skv = tc::smem_u32(sKV);
@@ -360,7 +353,6 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_tc_kernel(const Params P
       auto issue_scores = [&](int j) {
         const int stage = j % P.nstages;
         tc::mbar_wait(&kv_full[stage], (j / P.nstages) & 1);
-        tc::mbar_wait(&s_empty[j & 1], ((j >> 1) & 1) ^ 1);
         tc::tc_fence_after();
         const uint32_t d_s = tmem_base + kColS + (uint32_t)(j & 1) * 128u;
         const uint32_t k_hi = skv + (uint32_t)stage * kStageBytes, k_lo = k_hi + kOpBytes;
@@ -378,23 +370,27 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_tc_kernel(const Params P
       tc::mbar_wait(q_ready, 0);
       tc::tc_fence_after();
       issue_scores(0);
+      if (nt > 1) issue_scores(1);
       for (int j = 0; j < nt; ++j) {
-        if (j + 1 < nt) issue_scores(j + 1);
         const int stage = j % P.nstages;
-        tc::mbar_wait(p_full, j & 1);
+        tc::mbar_wait(&p_full[j & 1], (j >> 1) & 1);
         tc::tc_fence_after();
+        const uint32_t pw = tmem_base + kColS + (uint32_t)(j & 1) * 128u;  // weights, stored over the scores
         const uint32_t v_hi = skv + (uint32_t)stage * kStageBytes + (SHARED ? 0u : 2u * kOpBytes);
         const uint32_t v_lo = v_hi + kOpBytes;
 #pragma unroll
         for (int ks = 0; ks < kTile / 16; ++ks) {  // 16 keys = two 8-key groups of 128 bytes
           const uint64_t db_hi = tc::smem_desc(v_hi + ks * 256, v_lbo, v_sbo);
           const uint64_t db_lo = tc::smem_desc(v_lo + ks * 256, v_lbo, v_sbo);
-          tc::mma_bf16_ts(d_o, p_lo + ks * 8, db_hi, idesc_o, (j | ks) != 0);
-          tc::mma_bf16_ts(d_o, p_hi + ks * 8, db_lo, idesc_o, 1);
-          tc::mma_bf16_ts(d_o, p_hi + ks * 8, db_hi, idesc_o, 1);
+          const uint32_t p_hi = pw + (uint32_t)(ks >> 1) * 32u + (uint32_t)(ks & 1) * 8u, p_lo = p_hi + 16u;
+          tc::mma_bf16_ts(d_o, p_lo, db_hi, idesc_o, (j | ks) != 0);
+          tc::mma_bf16_ts(d_o, p_hi, db_lo, idesc_o, 1);
+          tc::mma_bf16_ts(d_o, p_hi, db_hi, idesc_o, 1);
         }
-        tc::mma_commit(p_empty);
         tc::mma_commit(&kv_empty[stage]);
+        // the next scores of this group go into the columns the weights just read occupy: the tensor pipe
+        // executes MMAs in issue order, so they cannot overtake the product above
+        if (j + 2 < nt) issue_scores(j + 2);
       }
       tc::mma_commit(o_full);
     }
