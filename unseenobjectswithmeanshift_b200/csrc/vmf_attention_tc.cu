@@ -121,7 +121,7 @@ __device__ __forceinline__ void split_store8(const float4& a, const float4& b, u
 // are inside the fp16 range and keep 22 bits: kappa multiplies the score error inside the exponential).
 // P and V always use bf16 hi/lo: a row's weights exp(kappa (cos - 1)) may ALL be tiny (no key near the query),
 // which needs bf16's exponent range; their error enters the output unamplified.
-template <int HD, bool SHARED, bool QK16>
+template <int HD, bool SHARED, bool QK16, bool MASKED>
 __global__ void __launch_bounds__(kThreads, 1) vmf_attn_tc_kernel(const Params P) {
   static_assert(!(SHARED && QK16), "a shared k == v copy serves both products and must be bf16");
   constexpr int CH = HD / 32;                      // 8-channel chunks per loader thread and row
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_tc_kernel(const Params P
       if (lane == 0) tc::mbar_arrive(q_ready);
     }
 
-    const bool row_masked = (P.bits != nullptr) && qi < P.Nq &&
+    const bool row_masked = MASKED && (P.bits != nullptr) && qi < P.Nq &&
                             (P.row_open == nullptr || __ldg(P.row_open + b * P.Nq + qi) != 0);
     const uint32_t* brow = P.bits + (int64_t)(b * P.Nq + (qi < P.Nq ? qi : 0)) * P.words_per_row;
     float den = 0.f;
@@ -233,22 +233,33 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_tc_kernel(const Params P
       }
       tc::mbar_wait(&s_full[grp], use & 1);
       tc::tc_fence_after();
-      uint32_t r[2][32];
-      tc::tmem_ld32(sp, r[0]);
+      // whole 32-key chunks can only be cut by the tail of the key range when there is no mask
+      const bool plain = !MASKED && (P.Ns - key0 >= kTile);
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
+        uint32_t r[32];
+        tc::tmem_ld32(sp + ch * 32, r);
         tc::tmem_ld_wait();
-        if (ch < 3) tc::tmem_ld32(sp + (ch + 1) * 32, r[(ch + 1) & 1]);  // in flight while this chunk is processed
         const uint32_t wm = w[ch];
         uint32_t hi[16], lo[16];
+        if (plain) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = ex2(fmaf(__uint_as_float(r[ch & 1][2 * i]), c, -c));
-          float p1 = ex2(fmaf(__uint_as_float(r[ch & 1][2 * i + 1]), c, -c));
-          if ((wm >> (2 * i)) & 1u) p0 = 0.f;
-          if ((wm >> (2 * i + 1)) & 1u) p1 = 0.f;
-          den += p0 + p1;
-          tc::split2(p0, p1, hi[i], lo[i]);
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = ex2(fmaf(__uint_as_float(r[2 * i]), c, -c));
+            const float p1 = ex2(fmaf(__uint_as_float(r[2 * i + 1]), c, -c));
+            den += p0 + p1;
+            tc::split2(p0, p1, hi[i], lo[i]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float p0 = ex2(fmaf(__uint_as_float(r[2 * i]), c, -c));
+            float p1 = ex2(fmaf(__uint_as_float(r[2 * i + 1]), c, -c));
+            if ((wm >> (2 * i)) & 1u) p0 = 0.f;
+            if ((wm >> (2 * i + 1)) & 1u) p1 = 0.f;
+            den += p0 + p1;
+            tc::split2(p0, p1, hi[i], lo[i]);
+          }
         }
         // in place: the 32 score columns of this chunk become 16 hi + 16 lo weight columns
         tc::tmem_st16(sp + ch * 32, hi);
@@ -440,21 +451,26 @@ size_t vmf_tc_workspace_bytes(int G, int Nq, int Ns, int hd) {
   return (size_t)G * ns * Nq * (hd + 1) * sizeof(float);
 }
 
-template <int HD, bool SHARED, bool QK16>
-static int launch_tc(const vtc::Params& P, int G, cudaStream_t st) {
+template <int HD, bool SHARED, bool QK16, bool MASKED>
+static int launch_tc_m(const vtc::Params& P, int G, cudaStream_t st) {
   using namespace vtc;
   const size_t stage = (size_t)(SHARED ? 2 : 4) * kTile * HD * 2;
   const size_t smem = (size_t)P.nstages * stage + 256 + 128 * sizeof(float);
   static bool configured = false;
   if (!configured) {
-    MSM_CUDA(cudaFuncSetAttribute(vmf_attn_tc_kernel<HD, SHARED, QK16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MSM_CUDA(cudaFuncSetAttribute(vmf_attn_tc_kernel<HD, SHARED, QK16, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kMaxSmem));
     configured = true;
   }
   // >= 116 KB of dynamic shared memory keeps it at one CTA per SM (each CTA allocates all of TMEM)
   const size_t req = smem < (size_t)(120 << 10) ? (size_t)(120 << 10) : smem;
-  vmf_attn_tc_kernel<HD, SHARED, QK16><<<G * P.nsplit, kThreads, req, st>>>(P);
+  vmf_attn_tc_kernel<HD, SHARED, QK16, MASKED><<<G * P.nsplit, kThreads, req, st>>>(P);
   return check_launch("vmf_attn_tc_kernel");
+}
+
+template <int HD, bool SHARED, bool QK16>
+static int launch_tc(const vtc::Params& P, int G, cudaStream_t st) {
+  return P.bits != nullptr ? launch_tc_m<HD, SHARED, QK16, true>(P, G, st) : launch_tc_m<HD, SHARED, QK16, false>(P, G, st);
 }
 
 // partial pass on the tensor cores; the caller runs vmf_finalize_kernel on (part_acc, part_den)
