@@ -120,6 +120,22 @@ int msm_linear_ln_fwd(const float* X, int64_t ldx, const void* prepared, const f
                       int64_t ldr, const float* gamma, const float* beta, float eps, float* Y, int64_t ldy, int M,
                       int N, int K, void* stream);
 
+/* General fused form (every stage optional, applied in this order on each output row):
+ *   v  = act( X . W^T + bias[n] + rowbias[row % rowbias_period][n] ) + residual[row][n]
+ *   y  = LayerNorm(v; ln_gamma, ln_beta, ln_eps)
+ *   z  = y / max(|y|_2, 1e-12)                     (l2_normalize; F.normalize)
+ *   Y  = z ;   Y2 = LayerNorm(z; ln2_gamma, ln2_beta, ln2_eps)     (second output, optional)
+ * One launch for the post-norm residual blocks of the decoder layers,  norm(tgt + out_proj(attn)),
+ * norm(tgt + linear2(relu(linear1(tgt)))) followed by the block's F.normalize and the prediction heads'
+ * decoder_norm (meanshiftformer_transformer_decoder.py:171-181, :245-260, :300-304, :637-638, :663), and - through
+ * rowbias - for  in_proj(tgt + query_pos) = in_proj(tgt) + in_proj_nobias(query_pos)  with the second term a per-layer
+ * [num_queries][N] table. Row stages (residual / LayerNorm / normalise / Y2) need N <= 256. */
+int msm_linear_fused_fwd(const float* X, int64_t ldx, const void* prepared, const float* bias, const float* rowbias,
+                         int rowbias_period, int act, const float* residual, int64_t ldr, const float* ln_gamma,
+                         const float* ln_beta, float ln_eps, int l2_normalize, const float* ln2_gamma,
+                         const float* ln2_beta, float ln2_eps, float* Y2, int64_t ldy2, float* Y, int64_t ldy, int M,
+                         int N, int K, void* stream);
+
 /* 1x1 convolution on NCHW input with the same kernel: X [B][K][HW] (pixels contiguous), weight prepared as above
  * from the conv weight viewed as [N][K]. y_nchw != 0: Y [B][N][HW] (what nn.Conv2d returns); y_nchw == 0:
  * Y [B][HW][N] (token-major, what the decoders consume after flatten(2).transpose(1,2)).

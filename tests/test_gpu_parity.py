@@ -466,6 +466,42 @@ def test_linear_residual_layernorm_vs_fp64(msm, M, N, K):
     assert peak_rel(y.cpu().double(), ref) < LINEAR_TOL
 
 
+@pytest.mark.parametrize("M,N,K,period", [(800, 256, 256, 100), (800, 256, 2048, 100), (200, 32, 64, 10),
+                                          (800, 768, 256, 100), (130, 96, 32, 13)])
+def test_linear_fused_row_epilogue_vs_fp64(msm, M, N, K, period):
+    """decoder residual blocks in one launch (meanshiftformer_transformer_decoder.py:171-181, 245-260, 300-304,
+    637-638, 663): act(x W^T + b + rowbias[row % period]) + residual -> LayerNorm -> F.normalize -> second LayerNorm."""
+    g = torch.Generator().manual_seed(M + N + K)
+    x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    rb, res = torch.randn(period, N, generator=g), torch.randn(M, N, generator=g)
+    n1, n2 = torch.nn.LayerNorm(N), torch.nn.LayerNorm(N)
+    with torch.no_grad():
+        for n in (n1, n2):
+            n.weight.copy_(torch.rand(N, generator=g) + 0.5)
+            n.bias.copy_(torch.randn(N, generator=g))
+        lin = x.double() @ w.double().t() + b.double() + rb.double().repeat(M // period + 1, 1)[:M]
+        # row bias only (any N)
+        y = msm.ops.linear_fused(x.cuda(), w.cuda(), b.cuda(), rowbias=rb.cuda())
+        assert peak_rel(y.cpu().double(), lin) < LINEAR_TOL
+        if N > 256:
+            with pytest.raises(Exception, match="N <= 256"):
+                msm.ops.linear_fused(x.cuda(), w.cuda(), b.cuda(), residual=res.cuda())
+            return
+        n1c, n2c = n1.cuda(), n2.cuda()
+        v = lin.clamp_min(0) + res.double()
+        yln = F.layer_norm(v, (N,), n1.weight.double(), n1.bias.double(), n1.eps)
+        z = F.normalize(yln, dim=-1)
+        z2 = F.layer_norm(z, (N,), n2.weight.double(), n2.bias.double(), n2.eps)
+        got, got2 = msm.ops.linear_fused(x.cuda(), w.cuda(), b.cuda(), rowbias=rb.cuda(), relu=True, residual=res.cuda(),
+                                         norm=n1c, l2_normalize=True, norm2=n2c)
+        assert peak_rel(got.cpu().double(), z) < LINEAR_TOL and peak_rel(got2.cpu().double(), z2) < LINEAR_TOL
+        # residual + LayerNorm only (the attention blocks)
+        got = msm.ops.linear_fused(x.cuda(), w.cuda(), b.cuda(), residual=res.cuda(), norm=n1c)
+        want = F.layer_norm(x.double() @ w.double().t() + b.double() + res.double(), (N,), n1.weight.double(),
+                            n1.bias.double(), n1.eps)
+        assert peak_rel(got.cpu().double(), want) < LINEAR_TOL
+
+
 @pytest.mark.parametrize("B,K,N,H,W", [(2, 2048, 64, 15, 20), (2, 512, 64, 60, 80), (1, 64, 256, 120, 160),
                                        (3, 64, 256, 15, 20), (2, 32, 32, 6, 2)])
 def test_conv1x1_vs_fp64(msm, B, K, N, H, W):

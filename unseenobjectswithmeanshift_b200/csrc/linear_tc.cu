@@ -37,8 +37,8 @@ constexpr int kThreads = 512;
 constexpr int kRows = 128;                // rows per tile = UMMA M
 constexpr int kKc = 32;                   // input channels per pipeline stage
 constexpr int kAStageBytes = kRows * kKc * 4;  // 16 KB
-constexpr int kStages = 4;                // shared-memory stages of the W (bf16) ring
-constexpr int kXStages = 6;               // shared-memory stages of the X (fp32) ring: 96 KB in flight per SM
+constexpr int kStages = 4;                // max shared-memory stages of the W (16-bit) ring
+constexpr int kXStages = 6;               // max shared-memory stages of the X (fp32) ring: 96 KB in flight per SM
 constexpr int kAStagesT = 4;              // A-operand stages in TMEM
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTmemA = 256;
@@ -58,6 +58,16 @@ struct Params {
   int64_t ldr;
   const float *ln_gamma, *ln_beta;
   float ln_eps;
+  // ring depths and accumulator count (BN = 256 uses one 256-column accumulator and shallower rings)
+  int xstages, wstages, nacc;
+  // row-periodic bias: + rowbias[(row % rowbias_period)][n]  (a projected positional embedding folded into the layer)
+  const float* rowbias;
+  int rowbias_period;
+  // wide fused epilogue (one N chunk, BN = N <= 256): act -> + residual -> LayerNorm -> L2 normalise -> Y,
+  // and optionally Y2 = LayerNorm2(Y) through a second tensor map
+  int wide, l2norm, has_y2;
+  const float *ln2_gamma, *ln2_beta;
+  float ln2_eps;
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -66,7 +76,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 __global__ void __launch_bounds__(kThreads, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap,
-                 const __grid_constant__ CUtensorMap ymap, const Params P) {
+                 const __grid_constant__ CUtensorMap ymap, const __grid_constant__ CUtensorMap y2map, const Params P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 128B-swizzled TMA tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -75,10 +85,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
   const uint32_t bStage = 128u * (uint32_t)P.BN;     // [hi|lo][4 k-groups][BN][8] bf16
   const uint32_t lboB = 16u * (uint32_t)P.BN;        // byte stride between 8-channel groups
 
-  uint8_t* sX = smem;                                // [kXStages][128 rows][32] fp32, swizzled
-  uint8_t* sY = sX + kXStages * kAStageBytes;        // [4 warps][2][32 rows][32] fp32, swizzled
-  uint8_t* sW = sY + 8 * kYWarpBytes;                // [kStages][bStage]
-  float* sBias = reinterpret_cast<float*>(sW + kStages * bStage);  // [4 warps][bias | gamma | beta][128]
+  uint8_t* sX = smem;                                // [xstages][128 rows][32] fp32, swizzled
+  uint8_t* sY = sX + P.xstages * kAStageBytes;       // [4 warps][2][32 rows][32] fp32, swizzled
+  uint8_t* sW = sY + 8 * kYWarpBytes;                // [wstages][bStage]
+  // [4 warps][bias | gamma | beta][128]; wide mode: [bias | gamma | beta | gamma2 | beta2][256] shared by the CTA
+  float* sBias = reinterpret_cast<float*>(sW + P.wstages * bStage);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 4 * 384);
   uint64_t* full_x = bars;                           // TMA -> converters
   uint64_t* empty_x = full_x + kXStages;             // converters -> TMA
@@ -96,6 +107,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     tc::tma_prefetch_desc(&xmap);
     tc::tma_prefetch_desc(&wmap);
     tc::tma_prefetch_desc(&ymap);
+    tc::tma_prefetch_desc(&y2map);
     for (int i = 0; i < kXStages; ++i) {
       tc::mbar_init(&full_x[i], 1);
       tc::mbar_init(&empty_x[i], 4);
@@ -134,11 +146,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                             kc * kKc, mt / P.tiles_per_b);
           else
             tc::tma_load_2d(sX + xs.stage * kAStageBytes, &xmap, &full_x[xs.stage], kc * kKc, mt * kRows);
-          xs.advance(kXStages);
+          xs.advance(P.xstages);
           tc::mbar_wait(&empty_w[rs.stage], rs.phase ^ 1);
           tc::mbar_arrive_expect_tx(&full_w[rs.stage], bStage);
           tc::tma_load_4d(sW + rs.stage * bStage, &wmap, &full_w[rs.stage], 0, nc * P.BN, kc * (kKc / 8), 0);
-          rs.advance(kStages);
+          rs.advance(P.wstages);
         }
       }
     }
@@ -150,8 +162,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
       tc::Ring as, ws;
       int t = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
-        const int acc = t % kAcc;
-        tc::mbar_wait(&acc_empty[acc], ((t / kAcc) & 1) ^ 1);
+        const int acc = t % P.nacc;
+        tc::mbar_wait(&acc_empty[acc], ((t / P.nacc) & 1) ^ 1);
         tc::tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)acc * 128u;
         for (int kc = 0; kc < nkc; ++kc) {
@@ -171,7 +183,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           tc::mma_commit(&empty_a[as.stage]);
           tc::mma_commit(&empty_w[ws.stage]);
           as.advance(kAStagesT);
-          ws.advance(kStages);
+          ws.advance(P.wstages);
         }
         tc::mma_commit(&acc_full[acc]);
       }
@@ -185,7 +197,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       for (int kc = 0; kc < nkc; ++kc, ++step) {
         if ((int)(step & 1u) != team) continue;
-        const uint32_t xstage = step % kXStages, xphase = (step / kXStages) & 1u;
+        const uint32_t xstage = step % (uint32_t)P.xstages, xphase = (step / (uint32_t)P.xstages) & 1u;
         const uint32_t astage = step % kAStagesT, aphase = (step / kAStagesT) & 1u;
         tc::mbar_wait(&full_x[xstage], xphase);
         uint32_t hi[16], lo[16];
@@ -227,11 +239,21 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     uint8_t* wY = sY + q * (2 * kYWarpBytes);
     uint32_t ychunk = 0;  // staging-buffer cursor
     int t = 0;
+    if (P.wide) {  // parameters of the fused epilogue: one copy for the CTA (single N chunk)
+      for (int j = threadIdx.x - 128; j < P.BN; j += 128) {
+        sBias[j] = P.bias != nullptr ? __ldg(P.bias + j) : 0.f;
+        sBias[256 + j] = P.ln_gamma != nullptr ? __ldg(P.ln_gamma + j) : 1.f;
+        sBias[512 + j] = P.ln_beta != nullptr ? __ldg(P.ln_beta + j) : 0.f;
+        sBias[768 + j] = P.has_y2 ? __ldg(P.ln2_gamma + j) : 1.f;
+        sBias[1024 + j] = P.has_y2 ? __ldg(P.ln2_beta + j) : 0.f;
+      }
+      named_bar_sync(2, 128);
+    }
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
       const int mt = tile / P.n_chunks, nc = tile % P.n_chunks;
-      const int acc = t % kAcc;
+      const int acc = t % P.nacc;
       __syncwarp();  // the previous tile's reads of wBias are done
-      for (int j = lane; j < P.BN; j += 32) {
+      for (int j = lane; j < P.BN && !P.wide; j += 32) {
         wBias[j] = P.bias != nullptr ? __ldg(P.bias + nc * P.BN + j) : 0.f;
         if (P.ln_gamma != nullptr) {
           wBias[128 + j] = __ldg(P.ln_gamma + j);
@@ -239,7 +261,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         }
       }
       __syncwarp();
-      tc::mbar_wait(&acc_full[acc], (t / kAcc) & 1);
+      tc::mbar_wait(&acc_full[acc], (t / P.nacc) & 1);
       tc::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 128u;
       if (P.y_nchw) {
@@ -268,7 +290,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         }
         continue;
       }
-      auto store_chunk = [&](const float* v, int ch) {
+      auto store_chunk = [&](const float* v, int ch, const CUtensorMap* omap) {
         uint8_t* ybuf = wY + (ychunk & 1u) * kYWarpBytes;
         ++ychunk;
         // the TMA store that read this staging tile two chunks ago must be done with it
@@ -282,13 +304,100 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         __syncwarp();
         if (lane == 0) {
           if (P.x_nchw)  // token-major output of a per-image tile: the 3-D map clips at the image's last pixel
-            tc::tma_store_3d(&ymap, ybuf, nc * P.BN + ch * 32, (mt % P.tiles_per_b) * kRows + q * 32,
+            tc::tma_store_3d(omap, ybuf, nc * P.BN + ch * 32, (mt % P.tiles_per_b) * kRows + q * 32,
                              mt / P.tiles_per_b);
           else
-            tc::tma_store_2d(&ymap, ybuf, nc * P.BN + ch * 32, mt * kRows + q * 32);
+            tc::tma_store_2d(omap, ybuf, nc * P.BN + ch * 32, mt * kRows + q * 32);
           tc::tma_store_commit();
         }
       };
+      if (P.wide) {
+        // Fused row epilogue over N = BN <= 256 columns (thread = row; the accumulator row is re-read from TMEM
+        // in each pass instead of being held in registers):
+        //   v = act(acc + bias + rowbias) + residual;  y = LayerNorm(v);  z = y / max(|y|, 1e-12);  Y = z;
+        //   Y2 = LayerNorm2(z)   - every stage optional.
+        const int grow = mt * kRows + row;
+        const int srow = grow < P.M ? grow : 0;
+        const float* rp = P.residual != nullptr ? P.residual + (int64_t)srow * P.ldr : nullptr;
+        const float* rb = P.rowbias != nullptr ? P.rowbias + (int64_t)(srow % P.rowbias_period) * P.N : nullptr;
+        auto load_v = [&](int ch, float (&v)[32]) {
+          uint32_t r[32];
+          tc::tmem_ld32(taddr + ch * 32, r);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            float4 x = make_float4(__uint_as_float(r[4 * c4]), __uint_as_float(r[4 * c4 + 1]),
+                                   __uint_as_float(r[4 * c4 + 2]), __uint_as_float(r[4 * c4 + 3]));
+            const float4 bb = *reinterpret_cast<const float4*>(sBias + ch * 32 + 4 * c4);
+            x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
+            if (rb != nullptr) {
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(rb) + ch * 8 + c4);
+              x.x += t4.x; x.y += t4.y; x.z += t4.z; x.w += t4.w;
+            }
+            if (P.act == 1) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+            if (rp != nullptr) {
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(rp) + ch * 8 + c4);
+              x.x += t4.x; x.y += t4.y; x.z += t4.z; x.w += t4.w;
+            }
+            v[4 * c4] = x.x; v[4 * c4 + 1] = x.y; v[4 * c4 + 2] = x.z; v[4 * c4 + 3] = x.w;
+          }
+        };
+        const bool has_ln = P.ln_gamma != nullptr;
+        const float inv_n = 1.f / (float)P.BN;
+        float mean = 0.f, rstd = 1.f;
+        if (has_ln) {
+          float s1 = 0.f, s2 = 0.f;
+          for (int ch = 0; ch < nchunk; ++ch) {
+            float v[32];
+            load_v(ch, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
+          }
+          mean = s1 * inv_n;
+          rstd = rsqrtf(fmaxf(s2 * inv_n - mean * mean, 0.f) + P.ln_eps);
+        }
+        auto to_y = [&](int ch, float (&v)[32]) {
+          if (has_ln) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              v[j] = (v[j] - mean) * rstd * sBias[256 + ch * 32 + j] + sBias[512 + ch * 32 + j];
+          }
+        };
+        float scale = 1.f, mean2 = 0.f, rstd2 = 1.f;
+        if (P.l2norm || P.has_y2) {
+          float s1 = 0.f, s2 = 0.f;
+          for (int ch = 0; ch < nchunk; ++ch) {
+            float v[32];
+            load_v(ch, v);
+            to_y(ch, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
+          }
+          if (P.l2norm) scale = 1.f / fmaxf(sqrtf(s2), 1e-12f);
+          mean2 = scale * s1 * inv_n;
+          rstd2 = rsqrtf(fmaxf(scale * scale * s2 * inv_n - mean2 * mean2, 0.f) + P.ln2_eps);
+        }
+        for (int ch = 0; ch < nchunk; ++ch) {
+          float v[32];
+          load_v(ch, v);
+          if (ch == nchunk - 1) {  // last read of the accumulator: hand it back to the MMA warp
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
+          }
+          to_y(ch, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= scale;
+          store_chunk(v, ch, &ymap);
+          if (P.has_y2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              v[j] = (v[j] - mean2) * rstd2 * sBias[768 + ch * 32 + j] + sBias[1024 + ch * 32 + j];
+            store_chunk(v, ch, &y2map);
+          }
+        }
+        continue;
+      }
       if (P.ln_gamma != nullptr) {
         // Y = LayerNorm(residual + X W^T + bias): the whole row (N = BN <= 64) sits in this thread's registers
         float v[64];
@@ -334,7 +443,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               v[ch * 32 + j] = (v[ch * 32 + j] - mean) * rstd * wBias[128 + ch * 32 + j] + wBias[256 + ch * 32 + j];
-            store_chunk(v + ch * 32, ch);
+            store_chunk(v + ch * 32, ch, &ymap);
           }
         }
         continue;
@@ -350,11 +459,22 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         }
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          v[j] = __uint_as_float(r[j]) + wBias[ch * 32 + j];
-          if (P.act == 1) v[j] = fmaxf(v[j], 0.f);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + wBias[ch * 32 + j];
+        if (P.rowbias != nullptr) {
+          const int grow = mt * kRows + row;
+          const float4* rb = reinterpret_cast<const float4*>(
+              P.rowbias + (int64_t)((grow < P.M ? grow : 0) % P.rowbias_period) * P.N + nc * P.BN + ch * 32);
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 t4 = __ldg(rb + c4);
+            v[4 * c4] += t4.x; v[4 * c4 + 1] += t4.y; v[4 * c4 + 2] += t4.z; v[4 * c4 + 3] += t4.w;
+          }
         }
-        store_chunk(v, ch);
+        if (P.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        store_chunk(v, ch, &ymap);
       }
     }
     if (lane == 0) tc::tma_store_wait_all();
@@ -420,6 +540,14 @@ struct LnArgs {
   int64_t ldr = 0;
   const float *gamma = nullptr, *beta = nullptr;
   float eps = 0.f;
+  // wide fused epilogue / row bias
+  int wide = 0, l2norm = 0;
+  const float* rowbias = nullptr;
+  int rowbias_period = 1;
+  const float *gamma2 = nullptr, *beta2 = nullptr;
+  float eps2 = 0.f;
+  float* y2 = nullptr;
+  int64_t ldy2 = 0;
 };
 
 static int launch(const float* X, int64_t ldx, const void* prepared, const float* bias, float* Y, int64_t ldy, int M,
@@ -428,12 +556,17 @@ static int launch(const float* X, int64_t ldx, const void* prepared, const float
   Params P;
   P.bias = bias; P.M = M; P.N = N; P.K = K; P.act = act;
   P.residual = ln.residual; P.ldr = ln.ldr; P.ln_gamma = ln.gamma; P.ln_beta = ln.beta; P.ln_eps = ln.eps;
-  P.BN = pick_bn(N);
+  P.wide = ln.wide; P.l2norm = ln.l2norm; P.rowbias = ln.rowbias; P.rowbias_period = ln.rowbias_period;
+  P.has_y2 = ln.y2 != nullptr; P.ln2_gamma = ln.gamma2; P.ln2_beta = ln.beta2; P.ln2_eps = ln.eps2;
+  P.BN = ln.wide ? N : pick_bn(N);
+  P.nacc = P.BN > 128 ? 1 : kAcc;
+  P.xstages = P.BN > 128 ? 3 : kXStages;
+  P.wstages = P.BN > 128 ? 3 : kStages;
   P.n_chunks = N / P.BN;
   P.x_nchw = x_nchw; P.y_nchw = y_nchw; P.Mb = Mb; P.y = Y;
   P.tiles_per_b = x_nchw ? (Mb + kRows - 1) / kRows : 1;
   P.m_tiles = x_nchw ? Bt * P.tiles_per_b : (M + kRows - 1) / kRows;
-  CUtensorMap xmap, wmap, ymap;
+  CUtensorMap xmap, wmap, ymap, y2map;
   if (x_nchw) {
     const uint64_t dims[3] = {(uint64_t)Mb, (uint64_t)K, (uint64_t)Bt};
     const uint64_t strides[2] = {(uint64_t)Mb * 4, (uint64_t)Mb * K * 4};
@@ -469,7 +602,15 @@ static int launch(const float* X, int64_t ldx, const void* prepared, const float
     int rc = tc::encode_tensor_map(&ymap, tc::TmapType::F32, tc::TmapSwizzle::B128, Y, 2, dims, strides, box);
     if (rc) return rc;
   }
-  const size_t smem = 1024 + (size_t)kXStages * kAStageBytes + 8 * kYWarpBytes + (size_t)kStages * 128 * P.BN +
+  y2map = ymap;
+  if (ln.y2 != nullptr) {
+    const uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+    const uint64_t strides[1] = {(uint64_t)ln.ldy2 * 4};
+    const uint32_t box[2] = {32, 32};
+    int rc = tc::encode_tensor_map(&y2map, tc::TmapType::F32, tc::TmapSwizzle::B128, ln.y2, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  const size_t smem = 1024 + (size_t)P.xstages * kAStageBytes + 8 * kYWarpBytes + (size_t)P.wstages * 128 * P.BN +
                       4 * 384 * sizeof(float) + 512;
   static bool configured = false;
   if (!configured) {
@@ -480,7 +621,7 @@ static int launch(const float* X, int64_t ldx, const void* prepared, const float
   const int grid = tiles < num_sms() ? tiles : num_sms();
   // >= 116 KB of dynamic shared memory keeps it at one CTA per SM (each CTA allocates all of TMEM)
   const size_t req = smem < (size_t)(120 << 10) ? (size_t)(120 << 10) : smem;
-  linear_tc_kernel<<<grid, kThreads, req, st>>>(xmap, wmap, ymap, P);
+  linear_tc_kernel<<<grid, kThreads, req, st>>>(xmap, wmap, ymap, y2map, P);
   return check_launch("linear_tc_kernel");
 }
 
@@ -511,6 +652,36 @@ extern "C" int msm_linear_ln_fwd(const float* X, int64_t ldx, const void* prepar
   msm::ltc::LnArgs ln;
   ln.residual = residual; ln.ldr = ldr; ln.gamma = gamma; ln.beta = beta; ln.eps = eps;
   return msm::ltc::launch(X, ldx, prepared, bias, Y, ldy, M, N, K, 0, 0, 0, 1, M, static_cast<cudaStream_t>(stream), ln);
+}
+
+extern "C" int msm_linear_fused_fwd(const float* X, int64_t ldx, const void* prepared, const float* bias,
+                                    const float* rowbias, int rowbias_period, int act, const float* residual,
+                                    int64_t ldr, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                                    int l2_normalize, const float* ln2_gamma, const float* ln2_beta, float ln2_eps,
+                                    float* Y2, int64_t ldy2, float* Y, int64_t ldy, int M, int N, int K,
+                                    void* stream) {
+  MSM_REQUIRE(X && prepared && Y, "X, prepared, Y must be non-null");
+  MSM_REQUIRE(M > 0 && K > 0 && K % 32 == 0, "M must be positive and K a positive multiple of 32");
+  MSM_REQUIRE(N > 0 && N % 32 == 0, "N must be a positive multiple of 32");
+  MSM_REQUIRE(act == 0 || act == 1, "act must be 0 (none) or 1 (relu)");
+  MSM_REQUIRE(ldx >= K && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0, "X rows must be 16-byte aligned");
+  MSM_REQUIRE(ldy >= N && ldy % 4 == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0, "Y rows must be 16-byte aligned");
+  MSM_REQUIRE(!rowbias || (rowbias_period > 0 && (reinterpret_cast<uintptr_t>(rowbias) & 15) == 0),
+              "rowbias needs a positive period and 16-byte alignment");
+  const bool row_ops = residual || ln_gamma || l2_normalize || Y2;
+  MSM_REQUIRE(!row_ops || N <= 256, "residual / LayerNorm / normalise / second output need N <= 256");
+  MSM_REQUIRE(!residual || (ldr >= N && ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0),
+              "residual rows must be 16-byte aligned");
+  MSM_REQUIRE((ln_gamma == nullptr) == (ln_beta == nullptr), "LayerNorm needs both gamma and beta");
+  MSM_REQUIRE(!Y2 || (ln2_gamma && ln2_beta && ldy2 >= N && ldy2 % 4 == 0 && (reinterpret_cast<uintptr_t>(Y2) & 15) == 0),
+              "the second output needs gamma2, beta2 and 16-byte aligned rows");
+  msm::ltc::LnArgs a;
+  a.rowbias = rowbias; a.rowbias_period = rowbias ? rowbias_period : 1;
+  if (row_ops) {
+    a.wide = 1; a.residual = residual; a.ldr = ldr; a.gamma = ln_gamma; a.beta = ln_beta; a.eps = ln_eps;
+    a.l2norm = l2_normalize ? 1 : 0; a.gamma2 = ln2_gamma; a.beta2 = ln2_beta; a.eps2 = ln2_eps; a.y2 = Y2; a.ldy2 = ldy2;
+  }
+  return msm::ltc::launch(X, ldx, prepared, bias, Y, ldy, M, N, K, act, 0, 0, 1, M, static_cast<cudaStream_t>(stream), a);
 }
 
 extern "C" int msm_conv1x1_fwd(const float* X, const void* prepared, const float* bias, float* Y, int y_nchw, int B,

@@ -290,9 +290,11 @@ class _MeanShiftDecoderBase(nn.Module):
         }
 
     # ------------------------------------------------------------------ prediction heads
-    def _heads(self, out, mask_features, target_size, need_mask):
-        """out [B,Q,C] -> (class logits [B,Q,K+1], mask logits [B,Q,h,w], bits, row_open)."""
-        dec = self.decoder_norm(out)
+    def _heads(self, out, mask_features, target_size, need_mask, dec=None):
+        """out [B,Q,C] -> (class logits [B,Q,K+1], mask logits [B,Q,h,w], bits, row_open).
+        ``dec`` = decoder_norm(out) when the caller already has it (fused into the previous GEMM's epilogue)."""
+        if dec is None:
+            dec = self.decoder_norm(out)
         logits = self.class_embed(dec)
         embed = self.mask_embed(dec)
         masks = ops.mask_logits(embed, mask_features)
@@ -378,14 +380,52 @@ class _MeanShiftDecoderBase(nn.Module):
         predictions_class.append(logits)
         predictions_mask.append(masks)
 
+        # Inference fast path: every post-norm residual block ends in ONE GEMM launch whose epilogue does
+        # + residual, LayerNorm (and for the FFN block F.normalize + the heads' decoder_norm), and
+        # in_proj(tgt + query_pos) becomes in_proj(tgt) + a cached [Q, N] row-bias table.
+        fused = (not torch.is_grad_enabled() and C % 32 == 0 and C <= 256 and self.mask_classification
+                 and isinstance(self.decoder_norm, nn.LayerNorm) and ops.tc_linear_enabled()
+                 and self.transformer_ffn_layers[0].linear1.weight.shape[0] % 32 == 0)
+        qpos = self.query_embed.weight
+
         for i in range(self.num_layers):
             lvl = i % L
             if i not in kv:
                 project_kv(lvl, [i])
             K, V = kv.pop(i)
-            # cross-attention (reference :245-260), post-norm
             ca = self.transformer_cross_attention_layers[i]
+            sl = self.transformer_self_attention_layers[i]
+            ffn = self.transformer_ffn_layers[i]
             a = ca.meanshift_attn
+            sa = sl.self_attn
+            if fused and ffn.activation is F.relu:
+                # cross-attention (reference :245-260), post-norm
+                tq = ops.cached_value(self, f"tq{i}", [qpos, a.in_proj_weight],
+                                      lambda: F.linear(qpos, a.in_proj_weight[:C]).contiguous())
+                q = ops.linear_fused(out, a.in_proj_weight[:C], a.in_proj_bias[:C], rowbias=tq)
+                o = torch.empty(B, self.num_queries, C, device=dev, dtype=torch.float32)
+                ops.vmf_attention(heads_view(q), heads_view(K), heads_view(V), blocked_bits=bits, row_open=row_open,
+                                  out=heads_view(o))
+                out = ops.linear_fused(o, a.out_proj.weight, a.out_proj.bias, residual=out, norm=ca.norm)
+                del K, V
+                # self-attention (reference :171-181): q = k = out + query_pos, v = out -> one GEMM, N = 3C
+                tqk = ops.cached_value(self, f"tqk{i}", [qpos, sa.in_proj_weight],
+                                       lambda: torch.cat([F.linear(qpos, sa.in_proj_weight[:2 * C]),
+                                                          qpos.new_zeros(qpos.shape[0], C)], 1).contiguous())
+                qkv = ops.linear_fused(out, sa.in_proj_weight, sa.in_proj_bias, rowbias=tqk)
+                o = torch.empty(B, self.num_queries, C, device=dev, dtype=torch.float32)
+                ops.vmf_attention(heads_view(qkv[..., :C]), heads_view(qkv[..., C:2 * C]), heads_view(qkv[..., 2 * C:]),
+                                  out=heads_view(o))
+                out = ops.linear_fused(o, sa.out_proj.weight, sa.out_proj.bias, residual=out, norm=sl.norm)
+                # FFN (reference :300-304), block norm (:637-638) and the heads' decoder_norm (:663)
+                hdn = ops.dense(out, ffn.linear1.weight, ffn.linear1.bias, relu=True)
+                out, dec = ops.linear_fused(hdn, ffn.linear2.weight, ffn.linear2.bias, residual=out, norm=ffn.norm,
+                                            l2_normalize=self.decoder_block_norm, norm2=self.decoder_norm)
+                logits, masks, bits, row_open = self._heads(out, mask_features, sizes[(i + 1) % L], need_mask, dec=dec)
+                predictions_class.append(logits)
+                predictions_mask.append(masks)
+                continue
+            # cross-attention (reference :245-260), post-norm
             q = ops.dense(out + query_pos, a.in_proj_weight[:C], a.in_proj_bias[:C])
             o = torch.empty(B, self.num_queries, C, device=dev, dtype=torch.float32)
             ops.vmf_attention(heads_view(q), heads_view(K), heads_view(V), blocked_bits=bits, row_open=row_open,
@@ -393,15 +433,14 @@ class _MeanShiftDecoderBase(nn.Module):
             out = ca.norm(out + ops.dense(o, a.out_proj.weight, a.out_proj.bias))
             del K, V
             # self-attention (reference :171-181): q = k = out + query_pos, v = out
-            sl = self.transformer_self_attention_layers[i]
-            a = sl.self_attn
+            a = sa
             qk = ops.dense(out + query_pos, a.in_proj_weight[:2 * C], a.in_proj_bias[:2 * C])
             v = ops.dense(out, a.in_proj_weight[2 * C:], a.in_proj_bias[2 * C:])
             o = torch.empty(B, self.num_queries, C, device=dev, dtype=torch.float32)
             ops.vmf_attention(heads_view(qk[..., :C]), heads_view(qk[..., C:]), heads_view(v), out=heads_view(o))
             out = sl.norm(out + ops.dense(o, a.out_proj.weight, a.out_proj.bias))
             # FFN (reference :300-304) and block norm (:637-638)
-            out = self.transformer_ffn_layers[i](out)
+            out = ffn(out)
             if self.decoder_block_norm:
                 out = F.normalize(out, dim=-1)
             logits, masks, bits, row_open = self._heads(out, mask_features, sizes[(i + 1) % L], need_mask)

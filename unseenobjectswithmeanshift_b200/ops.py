@@ -176,9 +176,14 @@ def prepare_linear_weight(weight):
     return buf
 
 
+def tc_linear_enabled():
+    """False when MSM_DISABLE_TC_LINEAR is set (dense layers then run in cuBLAS fp32 - a cross-check switch)."""
+    return os.environ.get("MSM_DISABLE_TC_LINEAR", "") in ("", "0")
+
+
 def linear_supported(x, weight):
     """True when msm_linear_fwd takes this layer (N, K multiples of 32, aligned fp32 CUDA rows)."""
-    if os.environ.get("MSM_DISABLE_TC_LINEAR", "") not in ("", "0"):
+    if not tc_linear_enabled():
         return False
     return (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and weight.dim() == 2
             and weight.shape[0] % 32 == 0 and weight.shape[1] % 32 == 0 and weight.stride(1) == 1
@@ -238,6 +243,60 @@ def linear_ln(x, weight, bias, residual, norm):
                                       float(norm.eps), out.data_ptr(), N, M, N, K, _stream())
     check(rc, "msm_linear_ln_fwd")
     return out
+
+
+def linear_fused(x, weight, bias=None, *, rowbias=None, relu=False, residual=None, norm=None, l2_normalize=False,
+                 norm2=None):
+    """One launch for  v = act(x @ W.T + bias + rowbias[row % len(rowbias)]) + residual;  y = norm(v);
+    z = F.normalize(y) if l2_normalize;  returns z, or (z, norm2(z)) when norm2 is given.
+    norm / norm2 are affine torch.nn.LayerNorm modules over N; row stages need N <= 256."""
+    _require(x, "x")
+    N, K = weight.shape
+    x2 = x.reshape(-1, K)
+    if x2.stride(1) != 1 or x2.stride(0) % 4 != 0 or x2.data_ptr() % 16 != 0:
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    lead = x.shape[:-1]
+    out = torch.empty(*lead, N, device=x.device, dtype=torch.float32)
+    out2 = torch.empty_like(out) if norm2 is not None else None
+    wp = prepare_linear_weight(weight.detach())
+    b = None if bias is None else bias.detach().contiguous()
+    rb = None
+    if rowbias is not None:
+        rb = _require(rowbias.detach(), "rowbias").contiguous()
+        if rb.dim() != 2 or rb.shape[1] != N:
+            raise ValueError(f"rowbias must be [period, {N}]")
+    res = None
+    if residual is not None:
+        res = _require(residual.detach(), "residual")
+        if not res.is_contiguous() or res.numel() != M * N:
+            raise ValueError("residual must be a contiguous tensor with the output's shape")
+    for nm in (norm, norm2):
+        if nm is not None and not (isinstance(nm, torch.nn.LayerNorm) and nm.elementwise_affine and nm.bias is not None
+                                   and tuple(nm.normalized_shape) == (N,)):
+            raise ValueError("norm / norm2 must be affine LayerNorm modules over the output features")
+    p = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+    rc = _lib.lib().msm_linear_fused_fwd(
+        x2.data_ptr(), x2.stride(0), wp.data_ptr(), p(b), p(rb), rb.shape[0] if rb is not None else 1,
+        1 if relu else 0, p(res), N, p(norm.weight) if norm is not None else None,
+        p(norm.bias) if norm is not None else None, float(norm.eps) if norm is not None else 0.0,
+        1 if l2_normalize else 0, p(norm2.weight) if norm2 is not None else None,
+        p(norm2.bias) if norm2 is not None else None, float(norm2.eps) if norm2 is not None else 0.0,
+        p(out2), N, out.data_ptr(), N, M, N, K, _stream())
+    check(rc, "msm_linear_fused_fwd")
+    return out if norm2 is None else (out, out2)
+
+
+def cached_value(owner, name, deps, fn):
+    """fn() cached on ``owner`` until one of the ``deps`` tensors is modified in place or replaced."""
+    key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in deps)
+    cache = owner.__dict__.setdefault("_msm_cat_cache", {})
+    hit = cache.get(name)
+    if hit is None or hit[0] != key:
+        with torch.no_grad():
+            hit = (key, fn(), list(deps))
+        cache[name] = hit
+    return hit[1]
 
 
 def conv1x1_supported(x, weight):
@@ -485,6 +544,13 @@ def _work_linear_ln(x, w, bias, residual, norm):
     return f"+res+LN M{M} N{N} K{K}", 4.0 * (M * K + 2 * M * N) + 4.0 * N * K, 2.0 * M * N * K
 
 
+def _work_linear_fused(x, w, bias=None, **kw):
+    N, K = w.shape
+    M = x.numel() // K
+    extra = (1 if kw.get("residual") is not None else 0) + (1 if kw.get("norm2") is not None else 0)
+    return f"fused M{M} N{N} K{K}", 4.0 * (M * K + (1 + extra) * M * N) + 4.0 * N * K, 2.0 * M * N * K
+
+
 def _work_conv(x, weight, bias=None, relu=False, tokens_out=False):
     B, K, H, W = x.shape
     N = weight.shape[0]
@@ -520,6 +586,7 @@ mask_to_attn_bits = _instrument("mask_to_attn_bits", 1, _work_bits)(mask_to_attn
 linear = _instrument("linear", 1, _work_linear)(linear)
 conv1x1 = _instrument("linear", 1, _work_conv)(conv1x1)
 linear_ln = _instrument("linear", 1, _work_linear_ln)(linear_ln)
+linear_fused = _instrument("linear", 1, _work_linear_fused)(linear_fused)
 ms_deform_attn_forward = _instrument("ms_deform_attn_forward", 1, _work_msda)(ms_deform_attn_forward)
 ms_deform_attn_fused_forward = _instrument("ms_deform_attn_forward", 1, _work_msda_fused)(ms_deform_attn_fused_forward)
 ms_deform_attn_backward = _instrument("ms_deform_attn_backward", 1)(ms_deform_attn_backward)
