@@ -487,7 +487,8 @@ def test_linear_fused_row_epilogue_vs_fp64(msm, M, N, K, period):
             with pytest.raises(Exception, match="N <= 256"):
                 msm.ops.linear_fused(x.cuda(), w.cuda(), b.cuda(), residual=res.cuda())
             return
-        n1c, n2c = n1.cuda(), n2.cuda()
+        import copy
+        n1c, n2c = copy.deepcopy(n1).cuda(), copy.deepcopy(n2).cuda()
         v = lin.clamp_min(0) + res.double()
         yln = F.layer_norm(v, (N,), n1.weight.double(), n1.bias.double(), n1.eps)
         z = F.normalize(yln, dim=-1)
@@ -516,6 +517,21 @@ def test_conv1x1_vs_fp64(msm, B, K, N, H, W):
         yt = msm.ops.conv1x1(x.cuda(), w.cuda(), b.cuda(), tokens_out=True)
     assert y.shape == ref.shape and peak_rel(y.cpu().double(), ref) < LINEAR_TOL
     assert peak_rel(yt.cpu().double(), ref.flatten(2).transpose(1, 2)) < LINEAR_TOL
+
+
+@pytest.mark.parametrize("B,C,N,H,W", [(2, 64, 64, 120, 160), (1, 64, 256, 30, 44), (1, 32, 32, 5, 8), (2, 64, 256, 33, 36)])
+def test_conv3x3_vs_fp64(msm, B, C, N, H, W):
+    """3x3 / pad 1 convolution as an implicit GEMM (SimpleBasePixelDecoder.mask_features fpn.py:238-246, FPN
+    layer_1 msdeformattn.py:258-262): borders (zero padding), ragged tile edges, every output element."""
+    g = torch.Generator().manual_seed(C + N + H)
+    x, w, b = torch.randn(B, C, H, W, generator=g), torch.randn(N, C, 3, 3, generator=g) / (9 * C) ** 0.5, torch.randn(N, generator=g)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    with torch.no_grad():
+        assert msm.ops.conv3x3_supported(x.cuda(), w.cuda())
+        y = msm.ops.conv3x3(x.cuda(), w.cuda(), b.cuda())
+        yr = msm.ops.conv3x3(x.cuda(), w.cuda(), None, relu=True)
+    assert y.shape == ref.shape and peak_rel(y.cpu().double(), ref) < LINEAR_TOL
+    assert peak_rel(yr.cpu().double(), F.conv2d(x.double(), w.double(), None, padding=1).clamp_min(0)) < LINEAR_TOL
 
 
 def test_msdeform_fused_sampling_vs_module_math(msm):

@@ -53,6 +53,9 @@ struct Params {
   // images. y_nchw: Y is written as [Bt][N][Mb] by direct stores (lane = pixel, coalesced) instead of TMA.
   int x_nchw, y_nchw, Mb, tiles_per_b;
   float* y;  // used when y_nchw
+  // 3x3 convolution (pad 1, stride 1) as an implicit GEMM over K' = 9*C: a tile is 4 image rows x 32 columns,
+  // tap (dy, dx) of channel chunk c is the same TMA box shifted by (dx, dy) - out-of-image reads are zero-filled
+  int conv3, H, W, C, tiles_x;
   // fused epilogue Y = LayerNorm(residual + X W^T + bias) over the N = BN <= 64 outputs of a row
   const float* residual;
   int64_t ldr;
@@ -141,7 +144,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         for (int kc = 0; kc < nkc; ++kc) {
           tc::mbar_wait(&empty_x[xs.stage], xs.phase ^ 1);
           tc::mbar_arrive_expect_tx(&full_x[xs.stage], kAStageBytes);
-          if (P.x_nchw)
+          if (P.conv3) {
+            const int cchunks = P.C / kKc;
+            const int tap = kc / cchunks, cc = kc - tap * cchunks;
+            const int tt = mt % P.tiles_per_b;
+            tc::tma_load_4d(sX + xs.stage * kAStageBytes, &xmap, &full_x[xs.stage], (tt % P.tiles_x) * 32 + tap % 3 - 1,
+                            (tt / P.tiles_x) * 4 + tap / 3 - 1, cc * kKc, mt / P.tiles_per_b);
+          } else if (P.x_nchw)
             tc::tma_load_3d(sX + xs.stage * kAStageBytes, &xmap, &full_x[xs.stage], (mt % P.tiles_per_b) * kRows,
                             kc * kKc, mt / P.tiles_per_b);
           else
@@ -267,8 +276,14 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
       if (P.y_nchw) {
         // Y[b][n][pixel]: lane = pixel, so each store instruction writes one 128-byte row segment
         const int bi = mt / P.tiles_per_b;
-        const int pixel = (mt % P.tiles_per_b) * kRows + row;
-        const bool in = pixel < P.Mb;
+        int pixel = (mt % P.tiles_per_b) * kRows + row;
+        bool in = pixel < P.Mb;
+        if (P.conv3) {  // warp q = image row q of the 4 x 32 tile, lane = column
+          const int tt = mt % P.tiles_per_b;
+          const int yy = (tt / P.tiles_x) * 4 + q, xx = (tt % P.tiles_x) * 32 + lane;
+          in = yy < P.H && xx < P.W;
+          pixel = yy * P.W + xx;
+        }
         float* orow = P.y + ((int64_t)bi * P.N + (int64_t)nc * P.BN) * P.Mb + pixel;
         for (int ch = 0; ch < nchunk; ++ch) {
           uint32_t r[32];
@@ -548,6 +563,8 @@ struct LnArgs {
   float eps2 = 0.f;
   float* y2 = nullptr;
   int64_t ldy2 = 0;
+  // 3x3 convolution geometry
+  int conv3 = 0, H = 0, W = 0, C = 0;
 };
 
 static int launch(const float* X, int64_t ldx, const void* prepared, const float* bias, float* Y, int64_t ldy, int M,
@@ -564,10 +581,17 @@ static int launch(const float* X, int64_t ldx, const void* prepared, const float
   P.wstages = P.BN > 128 ? 3 : kStages;
   P.n_chunks = N / P.BN;
   P.x_nchw = x_nchw; P.y_nchw = y_nchw; P.Mb = Mb; P.y = Y;
-  P.tiles_per_b = x_nchw ? (Mb + kRows - 1) / kRows : 1;
+  P.conv3 = ln.conv3; P.H = ln.H; P.W = ln.W; P.C = ln.C; P.tiles_x = ln.conv3 ? (ln.W + 31) / 32 : 1;
+  P.tiles_per_b = ln.conv3 ? P.tiles_x * ((ln.H + 3) / 4) : x_nchw ? (Mb + kRows - 1) / kRows : 1;
   P.m_tiles = x_nchw ? Bt * P.tiles_per_b : (M + kRows - 1) / kRows;
   CUtensorMap xmap, wmap, ymap, y2map;
-  if (x_nchw) {
+  if (ln.conv3) {
+    const uint64_t dims[4] = {(uint64_t)ln.W, (uint64_t)ln.H, (uint64_t)ln.C, (uint64_t)Bt};
+    const uint64_t strides[3] = {(uint64_t)ln.W * 4, (uint64_t)ln.W * ln.H * 4, (uint64_t)ln.W * ln.H * ln.C * 4};
+    const uint32_t box[4] = {32, 4, (uint32_t)kKc, 1};
+    int rc = tc::encode_tensor_map(&xmap, tc::TmapType::F32, tc::TmapSwizzle::None, X, 4, dims, strides, box);
+    if (rc) return rc;
+  } else if (x_nchw) {
     const uint64_t dims[3] = {(uint64_t)Mb, (uint64_t)K, (uint64_t)Bt};
     const uint64_t strides[2] = {(uint64_t)Mb * 4, (uint64_t)Mb * K * 4};
     const uint32_t box[3] = {(uint32_t)kRows, (uint32_t)kKc, 1};
@@ -652,6 +676,19 @@ extern "C" int msm_linear_ln_fwd(const float* X, int64_t ldx, const void* prepar
   msm::ltc::LnArgs ln;
   ln.residual = residual; ln.ldr = ldr; ln.gamma = gamma; ln.beta = beta; ln.eps = eps;
   return msm::ltc::launch(X, ldx, prepared, bias, Y, ldy, M, N, K, 0, 0, 0, 1, M, static_cast<cudaStream_t>(stream), ln);
+}
+
+extern "C" int msm_conv3x3_fwd(const float* X, const void* prepared, const float* bias, float* Y, int B, int C, int H,
+                               int W, int N, int act, void* stream) {
+  MSM_REQUIRE(X && prepared && Y, "X, prepared, Y must be non-null");
+  MSM_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && N > 0, "sizes must be positive");
+  MSM_REQUIRE(C % 32 == 0 && N % 32 == 0, "C and N must be multiples of 32");
+  MSM_REQUIRE(act == 0 || act == 1, "act must be 0 (none) or 1 (relu)");
+  MSM_REQUIRE(W % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0, "W must be a multiple of 4 and X 16-byte aligned");
+  msm::ltc::LnArgs a;
+  a.conv3 = 1; a.H = H; a.W = W; a.C = C;
+  return msm::ltc::launch(X, 0, prepared, bias, Y, N, B * H * W, N, 9 * C, act, 1, 1, B, H * W,
+                          static_cast<cudaStream_t>(stream), a);
 }
 
 extern "C" int msm_linear_fused_fwd(const float* X, int64_t ldx, const void* prepared, const float* bias,

@@ -118,102 +118,110 @@ __global__ void __launch_bounds__(256) msda_fwd_kernel(const float* __restrict__
 // in five elementwise passes over [N,Lq,M,L,P,2] tensors:  weights = softmax_{l,p}(logits),
 // loc = ref[l] + offset / (W_l, H_l)  (same operation order as the reference, so the sampled pixel
 // coordinates are the same floats), then the bilinear gather of the op itself.
-template <int VEC, int CL, int CP>  // CL, CP: compile-time levels / points (0 = take the run-time values)
+// One block = QB consecutive (batch, query) rows. Phase 1 stages their offset/logit rows in shared memory with
+// coalesced 16-byte loads; phase 2 turns the logits into softmax weights in place, one thread per (row, head);
+// phase 3 is the gather, one thread per (row, head, channel vector), reading offsets / weights from shared memory.
+template <int VEC>
 __global__ void __launch_bounds__(256) msda_fused_fwd_kernel(const float* __restrict__ value,
                                                              const int64_t* __restrict__ shapes,
                                                              const int64_t* __restrict__ lsi,
                                                              const float* __restrict__ ol, int64_t ld_ol,
                                                              const float* __restrict__ ref, float* __restrict__ out,
-                                                             int64_t total, int S, int M, int D, int L_rt, int Lq,
-                                                             int P_rt) {
-  const int L = CL > 0 ? CL : L_rt, P = CP > 0 ? CP : P_rt;
+                                                             int64_t rows, int QB, int S, int M, int D, int L, int Lq,
+                                                             int P) {
+  extern __shared__ __align__(16) float s_ol[];  // [QB][M*L*P*3]
   __shared__ int sH[kMaxLevels], sW[kMaxLevels], sStart[kMaxLevels];
   if (threadIdx.x < L) {
     sH[threadIdx.x] = (int)shapes[2 * threadIdx.x];
     sW[threadIdx.x] = (int)shapes[2 * threadIdx.x + 1];
     sStart[threadIdx.x] = (int)lsi[threadIdx.x];
   }
-  __syncthreads();
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int DV = D / VEC;
-  const int dv = (int)(idx % DV);
-  int64_t t = idx / DV;
-  const int m = (int)(t % M);
-  t /= M;  // t = b*Lq + q
-  const int b = (int)(t / Lq);
   const int LP = L * P;
-  const float* offp = ol + t * ld_ol + (int64_t)m * LP * 2;
-  const float* logp = ol + t * ld_ol + (int64_t)M * LP * 2 + (int64_t)m * LP;
-  const float* refp = ref + t * L * 2;
-  // softmax over the L*P logits of this head (max-shifted, like torch.softmax); with compile-time L, P the
-  // exponentials are computed once and live in registers
-  constexpr int NE = CL * CP > 0 ? CL * CP : 1;
-  float e[NE];
-  float mx = -INFINITY, den = 0.f;
-  if constexpr (CL * CP > 0) {
-#pragma unroll
-    for (int i = 0; i < NE; ++i) {
-      e[i] = __ldg(logp + i);
-      mx = fmaxf(mx, e[i]);
-    }
-#pragma unroll
-    for (int i = 0; i < NE; ++i) {
-      e[i] = expf(e[i] - mx);
-      den += e[i];
+  const int rowlen = M * LP * 3;
+  const int64_t row0 = (int64_t)blockIdx.x * QB;
+  const int nrows = (int)min((int64_t)QB, rows - row0);
+  // ---- phase 1: stage (coalesced; rows are rowlen floats, 16-byte aligned when ld_ol % 4 == 0)
+  if ((ld_ol & 3) == 0 && (rowlen & 3) == 0) {
+    const int v4 = rowlen / 4;
+    for (int i = threadIdx.x; i < nrows * v4; i += blockDim.x) {
+      const int r = i / v4, c = i - r * v4;
+      reinterpret_cast<float4*>(s_ol)[r * v4 + c] = __ldg(reinterpret_cast<const float4*>(ol + (row0 + r) * ld_ol) + c);
     }
   } else {
-    for (int i = 0; i < LP; ++i) mx = fmaxf(mx, __ldg(logp + i));
-    for (int i = 0; i < LP; ++i) den += expf(__ldg(logp + i) - mx);
+    for (int i = threadIdx.x; i < nrows * rowlen; i += blockDim.x) {
+      const int r = i / rowlen, c = i - r * rowlen;
+      s_ol[r * rowlen + c] = __ldg(ol + (row0 + r) * ld_ol + c);
+    }
   }
-  const int64_t row = (int64_t)M * D;
-  const float* vb = value + (int64_t)b * S * row + m * D + dv * VEC;
-  float acc[VEC];
+  __syncthreads();
+  // ---- phase 2: softmax over the L*P logits of each (row, head), max-shifted like torch.softmax
+  for (int i = threadIdx.x; i < nrows * M; i += blockDim.x) {
+    float* lg = s_ol + (i / M) * rowlen + M * LP * 2 + (i % M) * LP;
+    float mx = -INFINITY;
+    for (int k = 0; k < LP; ++k) mx = fmaxf(mx, lg[k]);
+    float den = 0.f;
+    for (int k = 0; k < LP; ++k) {
+      const float e = expf(lg[k] - mx);
+      lg[k] = e;
+      den += e;
+    }
+    for (int k = 0; k < LP; ++k) lg[k] = lg[k] / den;
+  }
+  __syncthreads();
+  // ---- phase 3: gather
+  const int DV = D / VEC;
+  const int per_row = M * DV;
+  for (int i = threadIdx.x; i < nrows * per_row; i += blockDim.x) {
+    const int r = i / per_row;
+    const int m = (i - r * per_row) / DV, dv = i % DV;
+    const int64_t t = row0 + r;  // b*Lq + q
+    const int b = (int)(t / Lq);
+    const float* offp = s_ol + r * rowlen + m * LP * 2;
+    const float* wp = s_ol + r * rowlen + M * LP * 2 + m * LP;
+    const float* refp = ref + t * L * 2;
+    const int64_t row = (int64_t)M * D;
+    const float* vb = value + (int64_t)b * S * row + m * D + dv * VEC;
+    float acc[VEC];
 #pragma unroll
-  for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
+    for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
+    for (int l = 0; l < L; ++l) {
+      const int H = sH[l], W = sW[l];
+      const float* vl = vb + (int64_t)sStart[l] * row;
+      const float2 rp = __ldg(reinterpret_cast<const float2*>(refp) + l);
+      for (int p = 0; p < P; ++p) {
+        const float2 off = *reinterpret_cast<const float2*>(offp + (l * P + p) * 2);
+        const float wgt = wp[l * P + p];
+        const float lx = rp.x + __fdiv_rn(off.x, (float)W);
+        const float ly = rp.y + __fdiv_rn(off.y, (float)H);
+        const float h_im = ly * H - 0.5f;
+        const float w_im = lx * W - 0.5f;
+        if (h_im > -1.f && w_im > -1.f && h_im < H && w_im < W) {
+          const int h0 = (int)floorf(h_im), w0 = (int)floorf(w_im);
+          const float lh = h_im - h0, lw = w_im - w0;
+          const float hh = 1.f - lh, hw = 1.f - lw;
+          float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
 #pragma unroll
-  for (int l = 0; l < L; ++l) {
-    const int H = sH[l], W = sW[l];
-    const float* vl = vb + (int64_t)sStart[l] * row;
-    const float2 rp = __ldg(reinterpret_cast<const float2*>(refp) + l);
+          for (int c = 0; c < VEC; ++c) v1[c] = v2[c] = v3[c] = v4[c] = 0.f;
+          const bool top = h0 >= 0, bot = h0 + 1 <= H - 1, lef = w0 >= 0, rig = w0 + 1 <= W - 1;
+          const float* p00 = vl + ((int64_t)h0 * W + w0) * row;
+          if (top && lef) vload<VEC>(v1, p00);
+          if (top && rig) vload<VEC>(v2, p00 + row);
+          if (bot && lef) vload<VEC>(v3, p00 + (int64_t)W * row);
+          if (bot && rig) vload<VEC>(v4, p00 + (int64_t)W * row + row);
+          const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
 #pragma unroll
-    for (int p = 0; p < P; ++p) {
-      const float2 off = __ldg(reinterpret_cast<const float2*>(offp) + l * P + p);
-      float wgt;
-      if constexpr (CL * CP > 0)
-        wgt = e[l * P + p] / den;
-      else
-        wgt = expf(__ldg(logp + l * P + p) - mx) / den;
-      const float lx = rp.x + __fdiv_rn(off.x, (float)W);
-      const float ly = rp.y + __fdiv_rn(off.y, (float)H);
-      const float h_im = ly * H - 0.5f;
-      const float w_im = lx * W - 0.5f;
-      if (h_im > -1.f && w_im > -1.f && h_im < H && w_im < W) {
-        const int h0 = (int)floorf(h_im), w0 = (int)floorf(w_im);
-        const float lh = h_im - h0, lw = w_im - w0;
-        const float hh = 1.f - lh, hw = 1.f - lw;
-        float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
-#pragma unroll
-        for (int c = 0; c < VEC; ++c) v1[c] = v2[c] = v3[c] = v4[c] = 0.f;
-        const bool top = h0 >= 0, bot = h0 + 1 <= H - 1, lef = w0 >= 0, rig = w0 + 1 <= W - 1;
-        const float* p00 = vl + ((int64_t)h0 * W + w0) * row;
-        if (top && lef) vload<VEC>(v1, p00);
-        if (top && rig) vload<VEC>(v2, p00 + row);
-        if (bot && lef) vload<VEC>(v3, p00 + (int64_t)W * row);
-        if (bot && rig) vload<VEC>(v4, p00 + (int64_t)W * row + row);
-        const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
-#pragma unroll
-        for (int c = 0; c < VEC; ++c) acc[c] += (w1 * v1[c] + w2 * v2[c] + w3 * v3[c] + w4 * v4[c]) * wgt;
+          for (int c = 0; c < VEC; ++c) acc[c] += (w1 * v1[c] + w2 * v2[c] + w3 * v3[c] + w4 * v4[c]) * wgt;
+        }
       }
     }
-  }
-  float* op = out + (t * M + m) * D + dv * VEC;
-  if constexpr (VEC == 4) {
-    *reinterpret_cast<float4*>(op) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-  } else if constexpr (VEC == 2) {
-    *reinterpret_cast<float2*>(op) = make_float2(acc[0], acc[1]);
-  } else {
-    op[0] = acc[0];
+    float* op = out + (t * M + m) * D + dv * VEC;
+    if constexpr (VEC == 4) {
+      *reinterpret_cast<float4*>(op) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    } else if constexpr (VEC == 2) {
+      *reinterpret_cast<float2*>(op) = make_float2(acc[0], acc[1]);
+    } else {
+      op[0] = acc[0];
+    }
   }
 }
 
@@ -344,20 +352,26 @@ extern "C" int msm_ms_deform_attn_fused_fwd(const float* value, const int64_t* s
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int vec = msm::pick_vec(D, value, out, out);
   if (vec == 4 && D == 8) vec = 2;
-  const int64_t total = (int64_t)N * Lq * M * (D / vec);
   const int threads = 256;
-  const unsigned blocks = (unsigned)((total + threads - 1) / threads);
-#define MSM_FUSED_LAUNCH(V, CL, CP)                                                                                  \
-  msm::msda_fused_fwd_kernel<V, CL, CP><<<blocks, threads, 0, st>>>(value, spatial_shapes, level_start_index,        \
-                                                                    offsets_logits, ld_ol, reference_points, out,    \
-                                                                    total, S, M, D, L, Lq, P)
-  const bool l3p4 = (L == 3 && P == 4);  // every UOIS config
+  const int rowlen = M * L * P * 3;
+  // rows per block: one thread per (row, head, channel vector), capped by 48 KB of staged offsets / logits
+  int QB = threads / (M * (D / vec));
+  if (QB < 1) QB = 1;
+  while (QB > 1 && (size_t)QB * rowlen * sizeof(float) > 48 * 1024) --QB;
+  MSM_REQUIRE((size_t)QB * rowlen * sizeof(float) <= 48 * 1024, "M*L*P too large for the fused kernel");
+  const int64_t rows = (int64_t)N * Lq;
+  const unsigned blocks = (unsigned)((rows + QB - 1) / QB);
+  const size_t smem = (size_t)QB * rowlen * sizeof(float);
+#define MSM_FUSED_LAUNCH(V)                                                                                         \
+  msm::msda_fused_fwd_kernel<V><<<blocks, threads, smem, st>>>(value, spatial_shapes, level_start_index,            \
+                                                               offsets_logits, ld_ol, reference_points, out, rows,  \
+                                                               QB, S, M, D, L, Lq, P)
   if (vec == 4) {
-    if (l3p4) MSM_FUSED_LAUNCH(4, 3, 4); else MSM_FUSED_LAUNCH(4, 0, 0);
+    MSM_FUSED_LAUNCH(4);
   } else if (vec == 2) {
-    if (l3p4) MSM_FUSED_LAUNCH(2, 3, 4); else MSM_FUSED_LAUNCH(2, 0, 0);
+    MSM_FUSED_LAUNCH(2);
   } else {
-    if (l3p4) MSM_FUSED_LAUNCH(1, 3, 4); else MSM_FUSED_LAUNCH(1, 0, 0);
+    MSM_FUSED_LAUNCH(1);
   }
 #undef MSM_FUSED_LAUNCH
   return msm::check_launch("msda_fused_fwd_kernel");

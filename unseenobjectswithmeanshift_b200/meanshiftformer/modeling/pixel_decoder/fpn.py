@@ -7,6 +7,7 @@ from typing import Callable, Dict, Optional, Union
 
 from torch import nn
 
+from .... import ops
 from ....d2compat import SEM_SEG_HEADS_REGISTRY, Conv2d, ShapeSpec, c2_xavier_fill, configurable
 from ....precision import conv_precision
 
@@ -53,7 +54,7 @@ class SimpleBasePixelDecoder(nn.Module):
         if self.mask_dim == 64:
             return y, None, multi_scale
         with conv_precision():
-            return self.mask_features(y), None, multi_scale
+            return ops.conv_layer(self.mask_features, y.float()), None, multi_scale
 
     def forward(self, features, targets=None):
         logging.getLogger(__name__).warning("Calling forward() may cause unpredicted behavior of PixelDecoder module.")

@@ -225,6 +225,6 @@ class MSDeformAttnPixelDecoder(nn.Module):
             for idx, f in enumerate(self.in_features[:self.num_fpn_levels][::-1]):
                 cur = ops.conv1x1_layer(self.lateral_convs[idx], features[f].float())
                 up = F.interpolate(out[-1], size=cur.shape[-2:], mode="bilinear", align_corners=False)
-                out.append(self.output_convs[idx](cur + up))
+                out.append(ops.conv_layer(self.output_convs[idx], cur + up))
             multi_scale = out[:self.maskformer_num_feature_levels]
             return ops.conv1x1_layer(self.mask_features, out[-1]), out[0], multi_scale

@@ -17,6 +17,7 @@ reference checkpoints load with ``strict=True``. What differs is how ``forward``
   reference's "row blocks everything -> attend everywhere" rule (:618) carried as a per-row flag.
 """
 import logging
+import os
 from typing import Optional
 
 import torch
@@ -387,6 +388,10 @@ class _MeanShiftDecoderBase(nn.Module):
                  and isinstance(self.decoder_norm, nn.LayerNorm) and ops.tc_linear_enabled()
                  and self.transformer_ffn_layers[0].linear1.weight.shape[0] % 32 == 0)
         qpos = self.query_embed.weight
+        # MSM_DECODER_FUSION: 0 = separate add / LayerNorm kernels, 1 = only the query_pos row bias is folded into
+        # the in-projections, 2 (default) = residual + LayerNorm (+ normalise + decoder_norm) epilogues as well
+        level = int(os.environ.get("MSM_DECODER_FUSION", "2"))
+        fused = fused and level > 0
 
         for i in range(self.num_layers):
             lvl = i % L
@@ -406,7 +411,10 @@ class _MeanShiftDecoderBase(nn.Module):
                 o = torch.empty(B, self.num_queries, C, device=dev, dtype=torch.float32)
                 ops.vmf_attention(heads_view(q), heads_view(K), heads_view(V), blocked_bits=bits, row_open=row_open,
                                   out=heads_view(o))
-                out = ops.linear_fused(o, a.out_proj.weight, a.out_proj.bias, residual=out, norm=ca.norm)
+                if level >= 2:
+                    out = ops.linear_fused(o, a.out_proj.weight, a.out_proj.bias, residual=out, norm=ca.norm)
+                else:
+                    out = ca.norm(out + ops.dense(o, a.out_proj.weight, a.out_proj.bias))
                 del K, V
                 # self-attention (reference :171-181): q = k = out + query_pos, v = out -> one GEMM, N = 3C
                 tqk = ops.cached_value(self, f"tqk{i}", [qpos, sa.in_proj_weight],
@@ -416,11 +424,18 @@ class _MeanShiftDecoderBase(nn.Module):
                 o = torch.empty(B, self.num_queries, C, device=dev, dtype=torch.float32)
                 ops.vmf_attention(heads_view(qkv[..., :C]), heads_view(qkv[..., C:2 * C]), heads_view(qkv[..., 2 * C:]),
                                   out=heads_view(o))
-                out = ops.linear_fused(o, sa.out_proj.weight, sa.out_proj.bias, residual=out, norm=sl.norm)
-                # FFN (reference :300-304), block norm (:637-638) and the heads' decoder_norm (:663)
-                hdn = ops.dense(out, ffn.linear1.weight, ffn.linear1.bias, relu=True)
-                out, dec = ops.linear_fused(hdn, ffn.linear2.weight, ffn.linear2.bias, residual=out, norm=ffn.norm,
-                                            l2_normalize=self.decoder_block_norm, norm2=self.decoder_norm)
+                if level >= 2:
+                    out = ops.linear_fused(o, sa.out_proj.weight, sa.out_proj.bias, residual=out, norm=sl.norm)
+                    # FFN (reference :300-304), block norm (:637-638) and the heads' decoder_norm (:663)
+                    hdn = ops.dense(out, ffn.linear1.weight, ffn.linear1.bias, relu=True)
+                    out, dec = ops.linear_fused(hdn, ffn.linear2.weight, ffn.linear2.bias, residual=out, norm=ffn.norm,
+                                                l2_normalize=self.decoder_block_norm, norm2=self.decoder_norm)
+                else:
+                    out = sl.norm(out + ops.dense(o, sa.out_proj.weight, sa.out_proj.bias))
+                    out = ffn(out)
+                    if self.decoder_block_norm:
+                        out = F.normalize(out, dim=-1)
+                    dec = None
                 logits, masks, bits, row_open = self._heads(out, mask_features, sizes[(i + 1) % L], need_mask, dec=dec)
                 predictions_class.append(logits)
                 predictions_mask.append(masks)

@@ -323,6 +323,59 @@ def conv1x1(x, weight, bias=None, relu=False, tokens_out=False):
     return out
 
 
+def conv3x3_supported(x, weight):
+    return (tc_linear_enabled() and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous()
+            and weight.dim() == 4 and weight.shape[2] == 3 and weight.shape[3] == 3 and weight.shape[0] % 32 == 0
+            and weight.shape[1] % 32 == 0 and x.shape[1] == weight.shape[1] and x.shape[3] % 4 == 0
+            and x.data_ptr() % 16 == 0)
+
+
+def conv3x3(x, weight, bias=None, relu=False):
+    """3x3 convolution (padding 1, stride 1) on the tensor cores as an implicit GEMM over 9*C. x [B,C,H,W]
+    contiguous, weight [N,C,3,3] -> [B,N,H,W]."""
+    _require(x, "x")
+    B, C, H, W = x.shape
+    N = weight.shape[0]
+    w = weight.detach()
+    w2 = cached_value(_CONV3_CACHE_OWNER, f"w{w.data_ptr()}_{tuple(w.shape)}", [w],
+                      lambda: w.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous())
+    wp = prepare_linear_weight(w2)
+    b = None if bias is None else _require(bias.detach(), "bias").contiguous()
+    out = torch.empty(B, N, H, W, device=x.device, dtype=torch.float32)
+    rc = _lib.lib().msm_conv3x3_fwd(x.data_ptr(), wp.data_ptr(), b.data_ptr() if b is not None else None, out.data_ptr(),
+                                    B, C, H, W, N, 1 if relu else 0, _stream())
+    check(rc, "msm_conv3x3_fwd")
+    return out
+
+
+class _Owner:
+    pass
+
+
+_CONV3_CACHE_OWNER = _Owner()
+
+
+def conv_layer(conv, x):
+    """Forward of a Conv2d module (detectron2-style wrapper with optional .norm / .activation, or plain
+    nn.Conv2d): tensor-core path for 1x1 and 3x3/pad-1 convolutions at inference, the module itself otherwise."""
+    needs_grad = torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad)
+    is3 = (conv.kernel_size == (3, 3) and conv.padding == (1, 1) and conv.dilation == (1, 1)
+           and getattr(conv, "padding_mode", "zeros") == "zeros")
+    if needs_grad or conv.stride != (1, 1) or conv.groups != 1:
+        return conv(x)
+    if conv.kernel_size == (1, 1) and conv1x1_supported(x, conv.weight):
+        y = conv1x1(x, conv.weight, conv.bias)
+    elif is3 and conv3x3_supported(x, conv.weight):
+        y = conv3x3(x, conv.weight, conv.bias)
+    else:
+        return conv(x)
+    if getattr(conv, "norm", None) is not None:
+        y = conv.norm(y)
+    if getattr(conv, "activation", None) is not None:
+        y = conv.activation(y)
+    return y
+
+
 def conv1x1_layer(conv, x):
     """Forward of a kernel_size=1 Conv2d module (detectron2-style wrapper with optional .norm / .activation,
     or a plain nn.Conv2d): tensor-core path for inference on shapes it takes, the module itself otherwise."""
@@ -558,6 +611,13 @@ def _work_conv(x, weight, bias=None, relu=False, tokens_out=False):
     return f"conv1x1 M{M} N{N} K{K}", 4.0 * (M * K + M * N) + 4.0 * N * K, 2.0 * M * N * K
 
 
+def _work_conv3(x, weight, bias=None, relu=False):
+    B, C, H, W = x.shape
+    N = weight.shape[0]
+    M = B * H * W
+    return f"conv3x3 M{M} N{N} C{C}", 4.0 * (M * C + M * N) + 36.0 * N * C, 18.0 * M * N * C
+
+
 def _work_msda(value, shapes, lsi, loc, aw, *a, **k):
     N, S, M, D = value.shape
     Lq = loc.shape[1]
@@ -585,6 +645,7 @@ mask_logits = _instrument("mask_logits", 1, _work_mask)(mask_logits)
 mask_to_attn_bits = _instrument("mask_to_attn_bits", 1, _work_bits)(mask_to_attn_bits)
 linear = _instrument("linear", 1, _work_linear)(linear)
 conv1x1 = _instrument("linear", 1, _work_conv)(conv1x1)
+conv3x3 = _instrument("linear", 1, _work_conv3)(conv3x3)
 linear_ln = _instrument("linear", 1, _work_linear_ln)(linear_ln)
 linear_fused = _instrument("linear", 1, _work_linear_fused)(linear_fused)
 ms_deform_attn_forward = _instrument("ms_deform_attn_forward", 1, _work_msda)(ms_deform_attn_forward)
