@@ -145,13 +145,14 @@ int msm_linear_fused_fwd(const float* X, int64_t ldx, const void* prepared, cons
 int msm_conv1x1_fwd(const float* X, const void* prepared, const float* bias, float* Y, int y_nchw, int B, int HW,
                     int N, int K, int act, void* stream);
 
-/* 3x3 convolution, padding 1, stride 1, NCHW in / NCHW out, as an implicit GEMM over K' = 9*C on the same kernel
- * (each tap is the input tile's TMA box shifted by (dx, dy); reads outside the image are zero-filled by TMA).
- * `prepared` comes from msm_linear_prepare_weight on the conv weight permuted to [N][ky][kx][C] and viewed as
- * [N][9*C]. Replaces SimpleBasePixelDecoder.mask_features (pixel_decoder/fpn.py:238-246, 90.6 GFLOP per 640x480
- * image) and the FPN output conv layer_1 (pixel_decoder/msdeformattn.py:258-262). W must be a multiple of 4. */
+/* 3x3 convolution, padding 1, stride 1, as an implicit GEMM over K' = 9*C on the same kernel (each tap is the
+ * input tile's TMA box shifted by (kx, ky)). X is the input ALREADY zero-padded: [B][C][H+2][Wp], one zero row
+ * above and below, one zero column on the left and Wp - W - 1 >= 1 on the right, Wp a multiple of 4;
+ * Y is [B][N][H][W]. `prepared` comes from msm_linear_prepare_weight on the conv weight permuted to
+ * [N][ky][kx][C] and viewed as [N][9*C]. Replaces SimpleBasePixelDecoder.mask_features (pixel_decoder/fpn.py:238-246,
+ * 90.6 GFLOP per 640x480 image) and the FPN output conv layer_1 (pixel_decoder/msdeformattn.py:258-262). */
 int msm_conv3x3_fwd(const float* X, const void* prepared, const float* bias, float* Y, int B, int C, int H, int W,
-                    int N, int act, void* stream);
+                    int Wp, int N, int act, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Multi-scale deformable attention, forward.

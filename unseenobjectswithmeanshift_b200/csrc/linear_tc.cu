@@ -28,6 +28,7 @@
 #include "tc.cuh"
 
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace msm {
 
@@ -44,6 +45,10 @@ constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTmemA = 256;
 constexpr int kAcc = 2;
 constexpr int kYWarpBytes = 32 * 32 * 4;  // 4 KB staging tile of one epilogue warp (32 rows x 32 columns)
+// 3x3 mode: one X stage = halo tile [32 channels][6 rows][36 columns] of the zero-padded input; it serves all 9 taps
+constexpr int kHaloW = 36, kHaloH = 6;
+constexpr int kHaloBytes = kKc * kHaloH * kHaloW * 4;      // 27648
+constexpr int kHaloStage = (kHaloBytes + 1023) / 1024 * 1024;  // 28672
 constexpr int kMaxSmem = 232448;
 
 struct Params {
@@ -53,9 +58,10 @@ struct Params {
   // images. y_nchw: Y is written as [Bt][N][Mb] by direct stores (lane = pixel, coalesced) instead of TMA.
   int x_nchw, y_nchw, Mb, tiles_per_b;
   float* y;  // used when y_nchw
-  // 3x3 convolution (pad 1, stride 1) as an implicit GEMM over K' = 9*C: a tile is 4 image rows x 32 columns,
-  // tap (dy, dx) of channel chunk c is the same TMA box shifted by (dx, dy) - out-of-image reads are zero-filled
-  int conv3, H, W, C, tiles_x;
+  // 3x3 convolution (pad 1, stride 1) as an implicit GEMM over K' = 9*C: a tile is 4 image rows x 32 columns; per
+  // 32-channel chunk ONE halo tile (6 x 36, 16-byte aligned start: TMA cannot shift the innermost coordinate by
+  // single fp32 elements) of the zero-padded input [H+2][Wp] is loaded and the converters read the 9 shifted views
+  int conv3, H, W, C, tiles_x, xstage_bytes;
   // fused epilogue Y = LayerNorm(residual + X W^T + bias) over the N = BN <= 64 outputs of a row
   const float* residual;
   int64_t ldr;
@@ -89,7 +95,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
   const uint32_t lboB = 16u * (uint32_t)P.BN;        // byte stride between 8-channel groups
 
   uint8_t* sX = smem;                                // [xstages][128 rows][32] fp32, swizzled
-  uint8_t* sY = sX + P.xstages * kAStageBytes;       // [4 warps][2][32 rows][32] fp32, swizzled
+  uint8_t* sY = sX + P.xstages * P.xstage_bytes;     // [4 warps][2][32 rows][32] fp32, swizzled
   uint8_t* sW = sY + 8 * kYWarpBytes;                // [wstages][bStage]
   // [4 warps][bias | gamma | beta][128]; wide mode: [bias | gamma | beta | gamma2 | beta2][256] shared by the CTA
   float* sBias = reinterpret_cast<float*>(sW + P.wstages * bStage);
@@ -113,7 +119,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     tc::tma_prefetch_desc(&y2map);
     for (int i = 0; i < kXStages; ++i) {
       tc::mbar_init(&full_x[i], 1);
-      tc::mbar_init(&empty_x[i], 4);
+      tc::mbar_init(&empty_x[i], P.conv3 ? 36 : 4);  // 3x3: nine taps x four converter warps read each halo tile
     }
     for (int i = 0; i < kStages; ++i) {
       tc::mbar_init(&full_w[i], 1);
@@ -141,16 +147,30 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
       tc::Ring xs, rs;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int mt = tile / P.n_chunks, nc = tile % P.n_chunks;
+        if (P.conv3) {
+          const int cchunks = P.C / kKc;
+          const int tt = mt % P.tiles_per_b;
+          for (int cc = 0; cc < cchunks; ++cc) {
+            tc::mbar_wait(&empty_x[xs.stage], xs.phase ^ 1);
+            tc::mbar_arrive_expect_tx(&full_x[xs.stage], kHaloBytes);
+            // (batch and channel are one axis of the map: the padded input is dense, so b*C + c is uniform)
+            tc::tma_load_3d(sX + xs.stage * kHaloStage, &xmap, &full_x[xs.stage], (tt % P.tiles_x) * 32,
+                            (tt / P.tiles_x) * 4, (mt / P.tiles_per_b) * P.C + cc * kKc);
+            xs.advance(P.xstages);
+            for (int tap = 0; tap < 9; ++tap) {  // weight chunk of k' = tap*C + cc*32 ..
+              tc::mbar_wait(&empty_w[rs.stage], rs.phase ^ 1);
+              tc::mbar_arrive_expect_tx(&full_w[rs.stage], bStage);
+              tc::tma_load_4d(sW + rs.stage * bStage, &wmap, &full_w[rs.stage], 0, nc * P.BN,
+                              (tap * P.C + cc * kKc) / 8, 0);
+              rs.advance(P.wstages);
+            }
+          }
+          continue;
+        }
         for (int kc = 0; kc < nkc; ++kc) {
           tc::mbar_wait(&empty_x[xs.stage], xs.phase ^ 1);
           tc::mbar_arrive_expect_tx(&full_x[xs.stage], kAStageBytes);
-          if (P.conv3) {
-            const int cchunks = P.C / kKc;
-            const int tap = kc / cchunks, cc = kc - tap * cchunks;
-            const int tt = mt % P.tiles_per_b;
-            tc::tma_load_4d(sX + xs.stage * kAStageBytes, &xmap, &full_x[xs.stage], (tt % P.tiles_x) * 32 + tap % 3 - 1,
-                            (tt / P.tiles_x) * 4 + tap / 3 - 1, cc * kKc, mt / P.tiles_per_b);
-          } else if (P.x_nchw)
+          if (P.x_nchw)
             tc::tma_load_3d(sX + xs.stage * kAStageBytes, &xmap, &full_x[xs.stage], (mt % P.tiles_per_b) * kRows,
                             kc * kKc, mt / P.tiles_per_b);
           else
@@ -206,11 +226,20 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       for (int kc = 0; kc < nkc; ++kc, ++step) {
         if ((int)(step & 1u) != team) continue;
-        const uint32_t xstage = step % (uint32_t)P.xstages, xphase = (step / (uint32_t)P.xstages) & 1u;
+        // 3x3: nine consecutive steps (taps) read the same halo stage
+        const uint32_t xuse = P.conv3 ? step / 9u : step;
+        const uint32_t xstage = xuse % (uint32_t)P.xstages, xphase = (xuse / (uint32_t)P.xstages) & 1u;
         const uint32_t astage = step % kAStagesT, aphase = (step / kAStagesT) & 1u;
         tc::mbar_wait(&full_x[xstage], xphase);
         uint32_t hi[16], lo[16];
-        if (P.x_nchw) {  // stage = [32 channels][128 pixels]: thread = pixel, conflict-free column reads
+        if (P.conv3) {   // stage = [32 channels][6 rows][36 cols]; pixel (q, lane) of tap (ky, kx) is (q+ky, lane+kx)
+          const uint32_t tap = step % 9u;
+          const float* src = reinterpret_cast<const float*>(sX + xstage * kHaloStage) + (q + tap / 3u) * kHaloW +
+                             lane + tap % 3u;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            tc::split2g(src[(2 * j) * (kHaloH * kHaloW)], src[(2 * j + 1) * (kHaloH * kHaloW)], hi[j], lo[j]);
+        } else if (P.x_nchw) {  // stage = [32 channels][128 pixels]: thread = pixel, conflict-free column reads
           const float* src = reinterpret_cast<const float*>(sX + xstage * kAStageBytes) + row;
 #pragma unroll
           for (int j = 0; j < 16; ++j) tc::split2g(src[(2 * j) * kRows], src[(2 * j + 1) * kRows], hi[j], lo[j]);
@@ -519,10 +548,19 @@ __global__ void linear_prepare_weight_kernel(const float* __restrict__ W, int64_
   }
 }
 
-static int pick_bn(int N) {
+// Column-chunk width. Large problems: the widest chunk that divides N (fewest re-reads of X). Problems that cannot
+// fill the GPU anyway (few row tiles): the narrowest chunk that still fits one wave of CTAs - more SMs share the
+// work and the per-CTA MMA / epilogue chain (the latency of these launch-bound layers) gets shorter.
+static int pick_bn(int N, int m_tiles) {
+  int widest = 0;
   for (int bn = 128; bn >= 32; bn -= 32)
-    if (N % bn == 0) return bn;
-  return 0;
+    if (N % bn == 0) { widest = bn; break; }
+  if (widest == 0) return 0;
+  const int sms = num_sms();
+  if (m_tiles * (N / widest) >= sms) return widest;
+  for (int bn = 32; bn <= widest; bn += 32)
+    if (N % bn == 0 && m_tiles * (N / bn) <= sms) return bn;
+  return widest;
 }
 
 }  // namespace ltc
@@ -550,6 +588,8 @@ namespace ltc {
 
 // x_nchw: X is [Bt][K][Mb]; otherwise X is [M][K] with row stride ldx. y_nchw: Y is [Bt][N][Mb]; otherwise
 // token-major rows of ldy floats ([M][N], or [Bt][Mb][N] when x_nchw).
+static int sms_many() { return 1 << 20; }
+
 struct LnArgs {
   const float* residual = nullptr;
   int64_t ldr = 0;
@@ -564,7 +604,7 @@ struct LnArgs {
   float* y2 = nullptr;
   int64_t ldy2 = 0;
   // 3x3 convolution geometry
-  int conv3 = 0, H = 0, W = 0, C = 0;
+  int conv3 = 0, H = 0, W = 0, C = 0, Wp = 0;
 };
 
 static int launch(const float* X, int64_t ldx, const void* prepared, const float* bias, float* Y, int64_t ldy, int M,
@@ -575,9 +615,11 @@ static int launch(const float* X, int64_t ldx, const void* prepared, const float
   P.residual = ln.residual; P.ldr = ln.ldr; P.ln_gamma = ln.gamma; P.ln_beta = ln.beta; P.ln_eps = ln.eps;
   P.wide = ln.wide; P.l2norm = ln.l2norm; P.rowbias = ln.rowbias; P.rowbias_period = ln.rowbias_period;
   P.has_y2 = ln.y2 != nullptr; P.ln2_gamma = ln.gamma2; P.ln2_beta = ln.beta2; P.ln2_eps = ln.eps2;
-  P.BN = ln.wide ? N : pick_bn(N);
+  const int m_tiles_est = x_nchw ? Bt * ((Mb + kRows - 1) / kRows) : (M + kRows - 1) / kRows;
+  P.BN = ln.wide ? N : pick_bn(N, ln.conv3 ? sms_many() : m_tiles_est);
   P.nacc = P.BN > 128 ? 1 : kAcc;
-  P.xstages = P.BN > 128 ? 3 : kXStages;
+  P.xstages = (P.BN > 128 || ln.conv3) ? 3 : kXStages;
+  P.xstage_bytes = ln.conv3 ? kHaloStage : kAStageBytes;
   P.wstages = P.BN > 128 ? 3 : kStages;
   P.n_chunks = N / P.BN;
   P.x_nchw = x_nchw; P.y_nchw = y_nchw; P.Mb = Mb; P.y = Y;
@@ -586,10 +628,11 @@ static int launch(const float* X, int64_t ldx, const void* prepared, const float
   P.m_tiles = x_nchw ? Bt * P.tiles_per_b : (M + kRows - 1) / kRows;
   CUtensorMap xmap, wmap, ymap, y2map;
   if (ln.conv3) {
-    const uint64_t dims[4] = {(uint64_t)ln.W, (uint64_t)ln.H, (uint64_t)ln.C, (uint64_t)Bt};
-    const uint64_t strides[3] = {(uint64_t)ln.W * 4, (uint64_t)ln.W * ln.H * 4, (uint64_t)ln.W * ln.H * ln.C * 4};
-    const uint32_t box[4] = {32, 4, (uint32_t)kKc, 1};
-    int rc = tc::encode_tensor_map(&xmap, tc::TmapType::F32, tc::TmapSwizzle::None, X, 4, dims, strides, box);
+    const uint64_t Hp = (uint64_t)ln.H + 2, Wp = (uint64_t)ln.Wp;
+    const uint64_t dims[3] = {Wp, Hp, (uint64_t)ln.C * (uint64_t)Bt};
+    const uint64_t strides[2] = {Wp * 4, Wp * Hp * 4};
+    const uint32_t box[3] = {(uint32_t)kHaloW, (uint32_t)kHaloH, (uint32_t)kKc};
+    int rc = tc::encode_tensor_map(&xmap, tc::TmapType::F32, tc::TmapSwizzle::None, X, 3, dims, strides, box);
     if (rc) return rc;
   } else if (x_nchw) {
     const uint64_t dims[3] = {(uint64_t)Mb, (uint64_t)K, (uint64_t)Bt};
@@ -634,7 +677,7 @@ static int launch(const float* X, int64_t ldx, const void* prepared, const float
     int rc = tc::encode_tensor_map(&y2map, tc::TmapType::F32, tc::TmapSwizzle::B128, ln.y2, 2, dims, strides, box);
     if (rc) return rc;
   }
-  const size_t smem = 1024 + (size_t)P.xstages * kAStageBytes + 8 * kYWarpBytes + (size_t)P.wstages * 128 * P.BN +
+  const size_t smem = 1024 + (size_t)P.xstages * P.xstage_bytes + 8 * kYWarpBytes + (size_t)P.wstages * 128 * P.BN +
                       4 * 384 * sizeof(float) + 512;
   static bool configured = false;
   if (!configured) {
@@ -679,14 +722,15 @@ extern "C" int msm_linear_ln_fwd(const float* X, int64_t ldx, const void* prepar
 }
 
 extern "C" int msm_conv3x3_fwd(const float* X, const void* prepared, const float* bias, float* Y, int B, int C, int H,
-                               int W, int N, int act, void* stream) {
+                               int W, int Wp, int N, int act, void* stream) {
   MSM_REQUIRE(X && prepared && Y, "X, prepared, Y must be non-null");
   MSM_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && N > 0, "sizes must be positive");
   MSM_REQUIRE(C % 32 == 0 && N % 32 == 0, "C and N must be multiples of 32");
   MSM_REQUIRE(act == 0 || act == 1, "act must be 0 (none) or 1 (relu)");
-  MSM_REQUIRE(W % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0, "W must be a multiple of 4 and X 16-byte aligned");
+  MSM_REQUIRE(Wp >= W + 2 && Wp % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0,
+              "the padded row length Wp must be >= W + 2 and a multiple of 4, X 16-byte aligned");
   msm::ltc::LnArgs a;
-  a.conv3 = 1; a.H = H; a.W = W; a.C = C;
+  a.conv3 = 1; a.H = H; a.W = W; a.C = C; a.Wp = Wp;
   return msm::ltc::launch(X, 0, prepared, bias, Y, N, B * H * W, N, 9 * C, act, 1, 1, B, H * W,
                           static_cast<cudaStream_t>(stream), a);
 }

@@ -326,8 +326,7 @@ def conv1x1(x, weight, bias=None, relu=False, tokens_out=False):
 def conv3x3_supported(x, weight):
     return (tc_linear_enabled() and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous()
             and weight.dim() == 4 and weight.shape[2] == 3 and weight.shape[3] == 3 and weight.shape[0] % 32 == 0
-            and weight.shape[1] % 32 == 0 and x.shape[1] == weight.shape[1] and x.shape[3] % 4 == 0
-            and x.data_ptr() % 16 == 0)
+            and weight.shape[1] % 32 == 0 and x.shape[1] == weight.shape[1])
 
 
 def conv3x3(x, weight, bias=None, relu=False):
@@ -342,8 +341,10 @@ def conv3x3(x, weight, bias=None, relu=False):
     wp = prepare_linear_weight(w2)
     b = None if bias is None else _require(bias.detach(), "bias").contiguous()
     out = torch.empty(B, N, H, W, device=x.device, dtype=torch.float32)
-    rc = _lib.lib().msm_conv3x3_fwd(x.data_ptr(), wp.data_ptr(), b.data_ptr() if b is not None else None, out.data_ptr(),
-                                    B, C, H, W, N, 1 if relu else 0, _stream())
+    Wp = (W + 2 + 3) // 4 * 4  # zero border of one pixel, rows padded to a 16-byte multiple for TMA
+    xp = torch.nn.functional.pad(x, (1, Wp - W - 1, 1, 1))
+    rc = _lib.lib().msm_conv3x3_fwd(xp.data_ptr(), wp.data_ptr(), b.data_ptr() if b is not None else None,
+                                    out.data_ptr(), B, C, H, W, Wp, N, 1 if relu else 0, _stream())
     check(rc, "msm_conv3x3_fwd")
     return out
 
