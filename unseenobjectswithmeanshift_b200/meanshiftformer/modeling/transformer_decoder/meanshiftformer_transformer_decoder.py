@@ -388,9 +388,10 @@ class _MeanShiftDecoderBase(nn.Module):
                  and isinstance(self.decoder_norm, nn.LayerNorm) and ops.tc_linear_enabled()
                  and self.transformer_ffn_layers[0].linear1.weight.shape[0] % 32 == 0)
         qpos = self.query_embed.weight
-        # MSM_DECODER_FUSION: 0 = separate add / LayerNorm kernels, 1 = only the query_pos row bias is folded into
-        # the in-projections, 2 (default) = residual + LayerNorm (+ normalise + decoder_norm) epilogues as well
-        level = int(os.environ.get("MSM_DECODER_FUSION", "2"))
+        # MSM_DECODER_FUSION: 0 = separate add / LayerNorm kernels; 1 (default) = the query_pos row bias is folded
+        # into the in-projections; 2 = residual + LayerNorm (+ normalise + decoder_norm) GEMM epilogues as well -
+        # measured slower at B*Q = 800 rows (one 256-column CTA per 128 rows = 7 CTAs; 5.5 vs 6.3 ms per step)
+        level = int(os.environ.get("MSM_DECODER_FUSION", "1"))
         fused = fused and level > 0
 
         for i in range(self.num_layers):
