@@ -188,52 +188,30 @@ __global__ void __launch_bounds__(256) msda_fused_fwd_kernel(const float* __rest
       const int H = sH[l], W = sW[l];
       const float* vl = vb + (int64_t)sStart[l] * row;
       const float2 rp = __ldg(reinterpret_cast<const float2*>(refp) + l);
-      // Branch-free taps, PU points at a time: indices are clamped into the map and the weight of a tap that lies
-      // outside it (or of a point the reference skips) is zeroed, so all 4*PU loads are issued before any is used.
-      constexpr int PU = 4;
-      for (int p0 = 0; p0 < P; p0 += PU) {
-        float tw[PU][4], awv[PU];
-        const float* tp[PU][4];
-#pragma unroll
-        for (int u = 0; u < PU; ++u) {
-          const int p = p0 + u < P ? p0 + u : P - 1;
-          const float2 off = *reinterpret_cast<const float2*>(offp + (l * P + p) * 2);
-          const float wgt = p0 + u < P ? wp[l * P + p] : 0.f;
-          const float lx = rp.x + __fdiv_rn(off.x, (float)W);
-          const float ly = rp.y + __fdiv_rn(off.y, (float)H);
-          const float h_im = ly * H - 0.5f;
-          const float w_im = lx * W - 0.5f;
-          const bool inside = h_im > -1.f && w_im > -1.f && h_im < H && w_im < W;
-          const float hf = floorf(h_im), wf = floorf(w_im);
-          const int h0 = (int)hf, w0 = (int)wf;
-          const float lh = h_im - hf, lw = w_im - wf;
+      for (int p = 0; p < P; ++p) {
+        const float2 off = *reinterpret_cast<const float2*>(offp + (l * P + p) * 2);
+        const float wgt = wp[l * P + p];
+        const float lx = rp.x + __fdiv_rn(off.x, (float)W);
+        const float ly = rp.y + __fdiv_rn(off.y, (float)H);
+        const float h_im = ly * H - 0.5f;
+        const float w_im = lx * W - 0.5f;
+        if (h_im > -1.f && w_im > -1.f && h_im < H && w_im < W) {
+          const int h0 = (int)floorf(h_im), w0 = (int)floorf(w_im);
+          const float lh = h_im - h0, lw = w_im - w0;
           const float hh = 1.f - lh, hw = 1.f - lw;
-          const bool top = inside && h0 >= 0, bot = inside && h0 + 1 <= H - 1, lef = w0 >= 0, rig = w0 + 1 <= W - 1;
-          const int hc0 = min(max(h0, 0), H - 1), hc1 = min(max(h0 + 1, 0), H - 1);
-          const int wc0 = min(max(w0, 0), W - 1), wc1 = min(max(w0 + 1, 0), W - 1);
-          tp[u][0] = vl + ((int64_t)hc0 * W + wc0) * row;
-          tp[u][1] = vl + ((int64_t)hc0 * W + wc1) * row;
-          tp[u][2] = vl + ((int64_t)hc1 * W + wc0) * row;
-          tp[u][3] = vl + ((int64_t)hc1 * W + wc1) * row;
-          tw[u][0] = (top && lef) ? hh * hw : 0.f;
-          tw[u][1] = (top && rig) ? hh * lw : 0.f;
-          tw[u][2] = (bot && lef) ? lh * hw : 0.f;
-          tw[u][3] = (bot && rig) ? lh * lw : 0.f;
+          float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tw[u][k] = inside ? tw[u][k] : 0.f;
-          awv[u] = wgt;  // applied after the tap sum, like the reference: (w1 v1 + w2 v2 + w3 v3 + w4 v4) * A
+          for (int c = 0; c < VEC; ++c) v1[c] = v2[c] = v3[c] = v4[c] = 0.f;
+          const bool top = h0 >= 0, bot = h0 + 1 <= H - 1, lef = w0 >= 0, rig = w0 + 1 <= W - 1;
+          const float* p00 = vl + ((int64_t)h0 * W + w0) * row;
+          if (top && lef) vload<VEC>(v1, p00);
+          if (top && rig) vload<VEC>(v2, p00 + row);
+          if (bot && lef) vload<VEC>(v3, p00 + (int64_t)W * row);
+          if (bot && rig) vload<VEC>(v4, p00 + (int64_t)W * row + row);
+          const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+#pragma unroll
+          for (int c = 0; c < VEC; ++c) acc[c] += (w1 * v1[c] + w2 * v2[c] + w3 * v3[c] + w4 * v4[c]) * wgt;
         }
-        float tv[PU][4][VEC];
-#pragma unroll
-        for (int u = 0; u < PU; ++u)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) vload<VEC>(tv[u][k], tp[u][k]);
-#pragma unroll
-        for (int u = 0; u < PU; ++u)
-#pragma unroll
-          for (int c = 0; c < VEC; ++c)
-            acc[c] += (tw[u][0] * tv[u][0][c] + tw[u][1] * tv[u][1][c] + tw[u][2] * tv[u][2][c] + tw[u][3] * tv[u][3][c]) *
-                      awv[u];
       }
     }
     float* op = out + (t * M + m) * D + dv * VEC;
