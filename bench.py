@@ -101,7 +101,7 @@ def run_reference(args, rank, world):
     torch.set_num_threads(cores)
     head = workloads.build_head(args.workload)
     sd = {k: v.detach() for k, v in head.state_dict().items()}
-    sample_b = 1
+    sample_b = 2
     feats = workloads.synthetic_features(args.workload, sample_b)
     for _ in range(args.warmup):
         cpu_oracle_step(sd, feats, args.workload)
