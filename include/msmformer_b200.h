@@ -136,6 +136,15 @@ int msm_linear_fused_fwd(const float* X, int64_t ldx, const void* prepared, cons
                          const float* ln2_beta, float ln2_eps, float* Y2, int64_t ldy2, float* Y, int64_t ldy, int M,
                          int N, int K, void* stream);
 
+/* Post-norm feed-forward block in one kernel:  Y = LayerNorm_D( X + relu(X . W1^T + b1) . W2^T + b2 ),
+ * X, Y [M][D] (rows of ldx / ldy floats), W1 [F][D], W2 [D][F] both given in the prepared layout of
+ * msm_linear_prepare_weight. Replaces MSDeformAttnTransformerEncoderLayer.forward_ffn
+ * (pixel_decoder/msdeformattn.py:76-84); the [M][F] hidden activation stays in tensor memory.
+ * D must be 32 or 64, F a multiple of 128 (F <= 1792 at D = 64: the bias vector lives in shared memory). */
+int msm_ffn_ln_fwd(const float* X, int64_t ldx, const void* w1_prepared, const float* b1, const void* w2_prepared,
+                   const float* b2, const float* gamma, const float* beta, float eps, float* Y, int64_t ldy, int M,
+                   int D, int F, void* stream);
+
 /* 1x1 convolution on NCHW input with the same kernel: X [B][K][HW] (pixels contiguous), weight prepared as above
  * from the conv weight viewed as [N][K]. y_nchw != 0: Y [B][N][HW] (what nn.Conv2d returns); y_nchw == 0:
  * Y [B][HW][N] (token-major, what the decoders consume after flatten(2).transpose(1,2)).

@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
+import torch.nn.functional as F_
 
 from oracle import decoder as odec
 from oracle import mean_shift as oms
@@ -463,6 +464,28 @@ def test_linear_residual_layernorm_vs_fp64(msm, M, N, K):
         norm = norm.cuda()
         assert msm.ops.linear_ln_supported(x.cuda(), w.cuda(), res.cuda(), norm)
         y = msm.ops.linear_ln(x.cuda(), w.cuda(), b.cuda(), res.cuda(), norm)
+    assert peak_rel(y.cpu().double(), ref) < LINEAR_TOL
+
+
+@pytest.mark.parametrize("M,D,F", [(12600, 64, 1024), (50400, 64, 1024), (252, 32, 128), (1000, 32, 384), (129, 64, 256)])
+def test_ffn_layernorm_block_vs_fp64(msm, M, D, F):
+    """norm2(src + linear2(relu(linear1(src)))) of the deformable encoder layer (pixel_decoder/msdeformattn.py:76-84)
+    as one chained-GEMM kernel; several row tiles per CTA, ragged last tile, one and many hidden chunks."""
+    g = torch.Generator().manual_seed(M + F)
+    x = torch.randn(M, D, generator=g)
+    w1, b1 = torch.randn(F, D, generator=g) / D ** 0.5, torch.randn(F, generator=g)
+    w2, b2 = torch.randn(D, F, generator=g) / F ** 0.5, torch.randn(D, generator=g)
+    norm = torch.nn.LayerNorm(D)
+    with torch.no_grad():
+        norm.weight.copy_(torch.rand(D, generator=g) + 0.5)
+        norm.bias.copy_(torch.randn(D, generator=g))
+        h = (x.double() @ w1.double().t() + b1.double()).clamp_min(0)
+        ref = F_.layer_norm(x.double() + h @ w2.double().t() + b2.double(), (D,), norm.weight.double(),
+                            norm.bias.double(), norm.eps)
+        import copy
+        nc = copy.deepcopy(norm).cuda()
+        assert msm.ops.ffn_ln_supported(x.cuda(), w1.cuda(), w2.cuda(), nc)
+        y = msm.ops.ffn_ln(x.cuda(), w1.cuda(), b1.cuda(), w2.cuda(), b2.cuda(), nc)
     assert peak_rel(y.cpu().double(), ref) < LINEAR_TOL
 
 

@@ -53,6 +53,9 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
             sampled = attn(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes, level_start_index,
                            padding_mask, project=False)
             src = ops.linear_ln(sampled, attn.output_proj.weight, attn.output_proj.bias, src, self.norm1)
+            if ops.ffn_ln_supported(src, self.linear1.weight, self.linear2.weight, self.norm2):
+                return ops.ffn_ln(src, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias,
+                                  self.norm2)
             h = ops.dense(src, self.linear1.weight, self.linear1.bias, relu=True)
             return ops.linear_ln(h, self.linear2.weight, self.linear2.bias, src, self.norm2)
         a = attn(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes, level_start_index, padding_mask)

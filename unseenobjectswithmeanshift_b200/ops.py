@@ -299,6 +299,31 @@ def cached_value(owner, name, deps, fn):
     return hit[1]
 
 
+def ffn_ln_supported(x, w1, w2, norm):
+    D = x.shape[-1]
+    return (tc_linear_enabled() and not torch.is_grad_enabled() and x.is_cuda and x.dtype == torch.float32
+            and x.is_contiguous() and D in (32, 64) and tuple(w1.shape[1:]) == (D,) and tuple(w2.shape) == (D, w1.shape[0])
+            and w1.shape[0] % 128 == 0 and w1.shape[0] <= 1792 and isinstance(norm, torch.nn.LayerNorm)
+            and norm.elementwise_affine and norm.bias is not None and tuple(norm.normalized_shape) == (D,)
+            and os.environ.get("MSM_DISABLE_FFN_FUSION", "") in ("", "0"))
+
+
+def ffn_ln(x, w1, b1, w2, b2, norm):
+    """norm(x + relu(x @ w1.T + b1) @ w2.T + b2) in one kernel; the hidden activation never reaches HBM."""
+    _require(x, "x")
+    D = x.shape[-1]
+    F = w1.shape[0]
+    x2 = x.reshape(-1, D)
+    M = x2.shape[0]
+    out = torch.empty_like(x)
+    w1p, w2p = prepare_linear_weight(w1.detach()), prepare_linear_weight(w2.detach())
+    rc = _lib.lib().msm_ffn_ln_fwd(x2.data_ptr(), x2.stride(0), w1p.data_ptr(), b1.detach().contiguous().data_ptr(),
+                                   w2p.data_ptr(), b2.detach().contiguous().data_ptr(), norm.weight.data_ptr(),
+                                   norm.bias.data_ptr(), float(norm.eps), out.data_ptr(), D, M, D, F, _stream())
+    check(rc, "msm_ffn_ln_fwd")
+    return out
+
+
 def conv1x1_supported(x, weight):
     if os.environ.get("MSM_DISABLE_TC_LINEAR", "") not in ("", "0"):
         return False
@@ -605,6 +630,13 @@ def _work_linear_fused(x, w, bias=None, **kw):
     return f"fused M{M} N{N} K{K}", 4.0 * (M * K + (1 + extra) * M * N) + 4.0 * N * K, 2.0 * M * N * K
 
 
+def _work_ffn(x, w1, b1, w2, b2, norm):
+    D = x.shape[-1]
+    F = w1.shape[0]
+    M = x.numel() // D
+    return f"ffn+LN M{M} D{D} F{F}", 4.0 * (3 * M * D) + 8.0 * D * F, 4.0 * M * D * F
+
+
 def _work_conv(x, weight, bias=None, relu=False, tokens_out=False):
     B, K, H, W = x.shape
     N = weight.shape[0]
@@ -648,6 +680,7 @@ linear = _instrument("linear", 1, _work_linear)(linear)
 conv1x1 = _instrument("linear", 1, _work_conv)(conv1x1)
 conv3x3 = _instrument("linear", 1, _work_conv3)(conv3x3)
 linear_ln = _instrument("linear", 1, _work_linear_ln)(linear_ln)
+ffn_ln = _instrument("ffn", 1, _work_ffn)(ffn_ln)
 linear_fused = _instrument("linear", 1, _work_linear_fused)(linear_fused)
 ms_deform_attn_forward = _instrument("ms_deform_attn_forward", 1, _work_msda)(ms_deform_attn_forward)
 ms_deform_attn_fused_forward = _instrument("ms_deform_attn_forward", 1, _work_msda_fused)(ms_deform_attn_fused_forward)
