@@ -54,6 +54,21 @@ def main():
             x, w, b = rn(M, K), rn(N, K) / K ** 0.5, rn(N)
             out = torch.empty(M, N, device=dev)
             fn = lambda: ops.linear(x, w, b, out=out)  # noqa: E731
+        elif a.what == "ffn":
+            M, D, F = 50400, 64, 1024
+            x = rn(M, D)
+            w1, b1, w2, b2 = rn(F, D) / 8, rn(F), rn(D, F) / 32, rn(D)
+            norm = torch.nn.LayerNorm(D).cuda()
+            fn = lambda: ops.ffn_ln(x, w1, b1, w2, b2, norm)  # noqa: E731
+        elif a.what == "msda_fused":
+            N, M, D, L, P = 8, 8, 8, 3, 4
+            shapes = torch.tensor([[15, 20], [30, 40], [60, 80]], device=dev)
+            lsi = torch.tensor([0, 300, 1500], device=dev)
+            S = 6300
+            value = rn(N, S, M, D)
+            ow = rn(N, S, M * L * P * 3)
+            ref = torch.rand(N, S, L, 2, device=dev, generator=g)
+            fn = lambda: ops.ms_deform_attn_fused_forward(value, shapes, lsi, ow, ref, L, P)  # noqa: E731
         else:
             raise SystemExit(f"unknown op {a.what}")
         for _ in range(a.iters):

@@ -12,14 +12,19 @@
 // for the F/128 hidden chunks c of a 128-row tile, then bias, residual, LayerNorm on the accumulator row (thread =
 // row, D <= 64) and a TMA store. Products are three-pass fp16 split precision (tc.cuh).
 //
+// A CTA works on PAIRS of 128-row tiles: both tiles of a pair consume the same W1 / W2 chunk (half the weight
+// traffic from L2 per FLOP - with one tile per weight pass the kernel was bound by the latency of re-streaming
+// 512 KB of weights per tile), and the pair gives the tensor pipe two independent chains: while the activation
+// warps of one tile rewrite its hidden chunk, the MMAs of the other tile run.
+//
 //   warp 0      producer of X tiles (fp32, 128B-swizzled) and W1 chunks (prepared layout, msm_linear_prepare_weight)
 //   warp 2      producer of W2 chunks; TMEM allocation
-//   warp 1      MMA issuer: the first product of chunk g+2 is issued right after the second product of chunk g
-//   warps 4-11  activation, two groups of four warps (one per TMEM lane quadrant) on alternate chunks
-//   warps 12-15 per tile: X rows -> fp16 hi/lo -> TMEM (A operand of the first product); epilogue of the previous tile
+//   warp 1      MMA issuer: per chunk c and tile slot s:  Y_s += A_s(c) W2_c^T ;  H_s = X_s W1_{c+1}^T
+//   warps 4-11  activation, one group of four warps (one per TMEM lane quadrant) per tile slot
+//   warps 12-15 per pair: X rows of both tiles -> fp16 hi/lo -> TMEM (A operand of the first product); epilogue
 //
-// TMEM map (512 columns): [0,128) [128,256) hidden chunk of the two activation groups, [256,320) [320,384) Y of
-// even / odd tiles, [384,448) [448,512) X operand of even / odd tiles.
+// TMEM map (512 columns): [0,128) [128,256) hidden chunk of tile slot 0 / 1, [256,320) [320,384) Y of slot 0 / 1,
+// [384,448) [448,512) X operand of slot 0 / 1.
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -80,9 +85,10 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_empty + 2);
 
   const int nch = P.F / kHc;
-  int my_tiles = 0;
-  for (int t = blockIdx.x; t < P.m_tiles; t += gridDim.x) ++my_tiles;
-  const int total = my_tiles * nch;  // hidden chunks this CTA processes
+  const int n_units = (P.m_tiles + 1) / 2;  // pairs of row tiles
+  int my_units = 0;
+  for (int u = blockIdx.x; u < n_units; u += gridDim.x) ++my_units;
+  const int total = my_units * nch;  // weight chunks this CTA streams
 
   if (threadIdx.x == 0) {
     tc::tma_prefetch_desc(&xmap);
@@ -125,12 +131,15 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
     // =================================================================== X and W1 producer
     if (lane == 0) {
       tc::Ring w1;
-      int ti = 0;
-      for (int tile = blockIdx.x; tile < P.m_tiles; tile += gridDim.x, ++ti) {
-        tc::mbar_wait(x_sfree, (ti & 1) ^ 1);
-        tc::mbar_arrive_expect_tx(x_full, kXBytes);
+      int xi = 0;  // X tiles loaded so far (one shared-memory staging tile, consumed by the converters in order)
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        for (int s2 = 0; s2 < 2; ++s2, ++xi) {
+          tc::mbar_wait(x_sfree, (xi & 1) ^ 1);
+          tc::mbar_arrive_expect_tx(x_full, kXBytes);
 #pragma unroll
-        for (int cb = 0; cb < D / 32; ++cb) tc::tma_load_2d(sX + cb * 16384, &xmap, x_full, cb * 32, tile * kRows);
+          for (int cb = 0; cb < D / 32; ++cb)
+            tc::tma_load_2d(sX + cb * 16384, &xmap, x_full, cb * 32, (2 * u + s2) * kRows);  // beyond M: zero fill
+        }
         for (int c = 0; c < nch; ++c) {
           tc::mbar_wait(&w1_empty[w1.stage], w1.phase ^ 1);
           tc::mbar_arrive_expect_tx(&w1_full[w1.stage], kW1Bytes);
@@ -156,16 +165,13 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
       const uint32_t idesc1 = tc::idesc_f16(kRows, kHc, false, false);
       const uint32_t idesc2 = tc::idesc_f16(kRows, D, false, false);
       const uint32_t sw1 = tc::smem_u32(sW1), sw2 = tc::smem_u32(sW2);
-      auto issue_first = [&](int g) {
-        const int ti = g / nch, c = g - ti * nch;
-        if (c == 0) {
-          tc::mbar_wait(&x_conv[ti & 1], (ti >> 1) & 1);
-        }
+      // first product of weight chunk g (global index) for tile slot s: H_s = X_s W1_c^T
+      auto issue_first = [&](int g, int s2) {
         const int st = g % kW1Stages;
-        tc::mbar_wait(&w1_full[st], (g / kW1Stages) & 1);
+        if (s2 == 0) tc::mbar_wait(&w1_full[st], (g / kW1Stages) & 1);
         tc::tc_fence_after();
-        const uint32_t d_h = tmem_base + kColH + (uint32_t)(g & 1) * 128u;
-        const uint32_t x_hi = tmem_base + kColX + (uint32_t)(ti & 1) * 64u, x_lo = x_hi + D / 2;
+        const uint32_t d_h = tmem_base + kColH + (uint32_t)s2 * 128u;
+        const uint32_t x_hi = tmem_base + kColX + (uint32_t)s2 * 64u, x_lo = x_hi + D / 2;
         const uint32_t w_hi = sw1 + st * kW1Bytes, w_lo = w_hi + kW1Bytes / 2;
 #pragma unroll
         for (int ks = 0; ks < D / 16; ++ks) {
@@ -175,47 +181,53 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
           tc::mma_bf16_ts(d_h, x_hi + ks * 8, db_lo, idesc1, 1);
           tc::mma_bf16_ts(d_h, x_hi + ks * 8, db_hi, idesc1, 1);
         }
-        tc::mma_commit(&w1_empty[st]);
-        tc::mma_commit(&h_full[g & 1]);
-        if (c == nch - 1) tc::mma_commit(&xt_free[ti & 1]);
+        tc::mma_commit(&h_full[s2]);
+        if (s2 == 1) tc::mma_commit(&w1_empty[st]);  // both tiles have read this W1 chunk
       };
-      if (total > 0) issue_first(0);
-      if (total > 1) issue_first(1);
-      for (int g = 0; g < total; ++g) {
-        const int ti = g / nch, c = g - ti * nch;
-        if (c == 0) {
-          tc::mbar_wait(&y_empty[ti & 1], ((ti >> 1) & 1) ^ 1);
+      int g = 0;
+      for (int ui = 0; ui < my_units; ++ui) {
+        for (int s2 = 0; s2 < 2; ++s2) {  // chunk 0 of both tiles
+          tc::mbar_wait(&x_conv[s2], ui & 1);
+          issue_first(g, s2);
         }
-        const int st = g % kW2Stages;
-        tc::mbar_wait(&w2_full[st], (g / kW2Stages) & 1);
-        tc::mbar_wait(&h_ready[g & 1], (g >> 1) & 1);
-        tc::tc_fence_after();
-        const uint32_t d_y = tmem_base + kColY + (uint32_t)(ti & 1) * 64u;
-        const uint32_t a = tmem_base + kColH + (uint32_t)(g & 1) * 128u;  // activations, stored over the chunk
-        const uint32_t w_hi = sw2 + st * kW2Bytes, w_lo = w_hi + kW2Bytes / 2;
+        for (int c = 0; c < nch; ++c, ++g) {
+          const int st = g % kW2Stages;
+          tc::mbar_wait(&w2_full[st], (g / kW2Stages) & 1);
+          const uint32_t w_hi = sw2 + st * kW2Bytes, w_lo = w_hi + kW2Bytes / 2;
+          for (int s2 = 0; s2 < 2; ++s2) {
+            if (c == 0) tc::mbar_wait(&y_empty[s2], (ui & 1) ^ 1);
+            tc::mbar_wait(&h_ready[s2], g & 1);
+            tc::tc_fence_after();
+            const uint32_t d_y = tmem_base + kColY + (uint32_t)s2 * 64u;
+            const uint32_t a = tmem_base + kColH + (uint32_t)s2 * 128u;  // activations, stored over the chunk
 #pragma unroll
-        for (int ks = 0; ks < kHc / 16; ++ks) {
-          const uint64_t db_hi = tc::smem_desc(w_hi + ks * 2 * kW2Lbo, kW2Lbo, 128);
-          const uint64_t db_lo = tc::smem_desc(w_lo + ks * 2 * kW2Lbo, kW2Lbo, 128);
-          const uint32_t a_hi = a + (uint32_t)(ks >> 1) * 32u + (uint32_t)(ks & 1) * 8u, a_lo = a_hi + 16u;
-          tc::mma_bf16_ts(d_y, a_lo, db_hi, idesc2, (c | ks) != 0);
-          tc::mma_bf16_ts(d_y, a_hi, db_lo, idesc2, 1);
-          tc::mma_bf16_ts(d_y, a_hi, db_hi, idesc2, 1);
+            for (int ks = 0; ks < kHc / 16; ++ks) {
+              const uint64_t db_hi = tc::smem_desc(w_hi + ks * 2 * kW2Lbo, kW2Lbo, 128);
+              const uint64_t db_lo = tc::smem_desc(w_lo + ks * 2 * kW2Lbo, kW2Lbo, 128);
+              const uint32_t a_hi = a + (uint32_t)(ks >> 1) * 32u + (uint32_t)(ks & 1) * 8u, a_lo = a_hi + 16u;
+              tc::mma_bf16_ts(d_y, a_lo, db_hi, idesc2, (c | ks) != 0);
+              tc::mma_bf16_ts(d_y, a_hi, db_lo, idesc2, 1);
+              tc::mma_bf16_ts(d_y, a_hi, db_hi, idesc2, 1);
+            }
+            if (s2 == 1) tc::mma_commit(&w2_empty[st]);
+            if (c + 1 < nch) {
+              // the tensor pipe executes in issue order: the next hidden chunk may overwrite the columns now
+              issue_first(g + 1, s2);
+            } else {
+              tc::mma_commit(&y_full[s2]);
+              tc::mma_commit(&xt_free[s2]);
+            }
+          }
         }
-        tc::mma_commit(&w2_empty[st]);
-        if (c == nch - 1) tc::mma_commit(&y_full[ti & 1]);
-        // the tensor pipe executes in issue order: the next chunk of this group may overwrite the columns now
-        if (g + 2 < total) issue_first(g + 2);
       }
     }
   } else if (warp >= 4 && warp < 12) {
-    // =================================================================== activation warps
+    // =================================================================== activation warps (group = tile slot)
     const int qd = warp & 3, grp = (warp - 4) >> 2;
     const uint32_t hp = tmem_base + ((uint32_t)(qd * 32) << 16) + kColH + (uint32_t)grp * 128u;
-    int use = 0;
-    for (int g = grp; g < total; g += 2, ++use) {
+    for (int g = 0; g < total; ++g) {
       const float* b1c = sB1 + (g % nch) * kHc;
-      tc::mbar_wait(&h_full[grp], use & 1);
+      tc::mbar_wait(&h_full[grp], g & 1);
       tc::tc_fence_after();
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
@@ -246,8 +258,8 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
     uint8_t* ybuf = sY + q * 4096;
     const uint32_t yrow = (uint32_t)lane * 128u, ysx = (uint32_t)(lane & 7);
 
-    auto epilogue = [&](int ti, int tile) {
-      tc::mbar_wait(&y_full[ti & 1], (ti >> 1) & 1);
+    auto epilogue = [&](int ui, int s2, int tile) {
+      tc::mbar_wait(&y_full[s2], ui & 1);
       tc::tc_fence_after();
       float v[D];
       const int grow = tile * kRows + row;
@@ -255,7 +267,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
 #pragma unroll
       for (int ch = 0; ch < D / 32; ++ch) {
         uint32_t r[32];
-        tc::tmem_ld32(lane_addr + kColY + (uint32_t)(ti & 1) * 64u + ch * 32, r);
+        tc::tmem_ld32(lane_addr + kColY + (uint32_t)s2 * 64u + ch * 32, r);
         tc::tmem_ld_wait();
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
@@ -268,7 +280,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
       }
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&y_empty[ti & 1]);
+      if (lane == 0) tc::mbar_arrive(&y_empty[s2]);
       float mean = 0.f;
 #pragma unroll
       for (int j = 0; j < D; ++j) mean += v[j];
@@ -299,37 +311,45 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
       }
     };
 
-    int ti = 0, prev_tile = -1;
-    for (int tile = blockIdx.x; tile < P.m_tiles; tile += gridDim.x, ++ti) {
-      // ---- X rows of this tile -> fp16 hi/lo -> TMEM (A operand of the first product)
-      tc::mbar_wait(x_full, ti & 1);
-      tc::mbar_wait(&xt_free[ti & 1], ((ti >> 1) & 1) ^ 1);
-      tc::tc_fence_after();
+    int ui = 0, xi = 0, prev_u = -1;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
+      // ---- X rows of both tiles of this pair -> fp16 hi/lo -> TMEM (A operands of the first product)
+      for (int s2 = 0; s2 < 2; ++s2, ++xi) {
+        tc::mbar_wait(x_full, xi & 1);
+        tc::mbar_wait(&xt_free[s2], (ui & 1) ^ 1);  // the previous pair's first products of this slot retired
+        tc::tc_fence_after();
 #pragma unroll
-      for (int cb = 0; cb < D / 32; ++cb) {
-        const uint8_t* src = sX + cb * 16384 + rowoff;
-        uint32_t hi[16], lo[16];
+        for (int cb = 0; cb < D / 32; ++cb) {
+          const uint8_t* src = sX + cb * 16384 + rowoff;
+          uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 x = *reinterpret_cast<const float4*>(src + (((uint32_t)c ^ sx) << 4));
-          tc::split2h(x.x, x.y, hi[2 * c], lo[2 * c]);
-          tc::split2h(x.z, x.w, hi[2 * c + 1], lo[2 * c + 1]);
+          for (int c = 0; c < 8; ++c) {
+            const float4 x = *reinterpret_cast<const float4*>(src + (((uint32_t)c ^ sx) << 4));
+            tc::split2h(x.x, x.y, hi[2 * c], lo[2 * c]);
+            tc::split2h(x.z, x.w, hi[2 * c + 1], lo[2 * c + 1]);
+          }
+          tc::tmem_st16(lane_addr + kColX + (uint32_t)s2 * 64u + cb * 16, hi);
+          tc::tmem_st16(lane_addr + kColX + (uint32_t)s2 * 64u + D / 2 + cb * 16, lo);
         }
-        tc::tmem_st16(lane_addr + kColX + (uint32_t)(ti & 1) * 64u + cb * 16, hi);
-        tc::tmem_st16(lane_addr + kColX + (uint32_t)(ti & 1) * 64u + D / 2 + cb * 16, lo);
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          tc::mbar_arrive(&x_conv[s2]);
+          tc::mbar_arrive(x_sfree);
+        }
       }
-      tc::tmem_st_wait();
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        tc::mbar_arrive(&x_conv[ti & 1]);
-        tc::mbar_arrive(x_sfree);
+      // ---- epilogue of the previous pair
+      if (prev_u >= 0) {
+        epilogue(ui - 1, 0, 2 * prev_u);
+        epilogue(ui - 1, 1, 2 * prev_u + 1);
       }
-      // ---- epilogue of the previous tile (its chunks are in flight while this tile's X was converted)
-      if (prev_tile >= 0) epilogue(ti - 1, prev_tile);
-      prev_tile = tile;
+      prev_u = u;
     }
-    if (prev_tile >= 0) epilogue(ti - 1, prev_tile);
+    if (prev_u >= 0) {
+      epilogue(ui - 1, 0, 2 * prev_u);
+      epilogue(ui - 1, 1, 2 * prev_u + 1);
+    }
     if (lane == 0) tc::tma_store_wait_all();
   }
 
@@ -387,7 +407,8 @@ static int launch(const float* X, int64_t ldx, const void* w1p, const float* b1,
     MSM_CUDA(cudaFuncSetAttribute(ffn_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     configured = true;
   }
-  const int grid = P.m_tiles < num_sms() ? P.m_tiles : num_sms();
+  const int n_units = (P.m_tiles + 1) / 2;
+  const int grid = n_units < num_sms() ? n_units : num_sms();
   const size_t req = smem < (size_t)(120 << 10) ? (size_t)(120 << 10) : smem;
   ffn_tc_kernel<D><<<grid, kThreads, req, st>>>(xmap, w1map, w2map, ymap, P);
   return check_launch("ffn_tc_kernel");
