@@ -225,6 +225,112 @@ __global__ void __launch_bounds__(256) msda_fused_fwd_kernel(const float* __rest
   }
 }
 
+// One block = QB consecutive (batch, query) rows. Phase 1 stages their offset/logit rows in shared memory with
+// coalesced 16-byte loads; phase 2 turns the logits into softmax weights in place, one thread per (row, head);
+// phase 3 is the gather, one thread per (row, head), reading offsets / weights from shared memory.
+template <int DH>  // channels per head, a multiple of 4; value / out 16-byte aligned
+__global__ void __launch_bounds__(256) msda_fused_head_kernel(const float* __restrict__ value,
+                                                             const int64_t* __restrict__ shapes,
+                                                             const int64_t* __restrict__ lsi,
+                                                             const float* __restrict__ ol, int64_t ld_ol,
+                                                             const float* __restrict__ ref, float* __restrict__ out,
+                                                             int64_t rows, int QB, int S, int M, int D, int L, int Lq,
+                                                             int P) {
+  extern __shared__ __align__(16) float s_ol[];  // [QB][M*L*P*3]
+  __shared__ int sH[kMaxLevels], sW[kMaxLevels], sStart[kMaxLevels];
+  if (threadIdx.x < L) {
+    sH[threadIdx.x] = (int)shapes[2 * threadIdx.x];
+    sW[threadIdx.x] = (int)shapes[2 * threadIdx.x + 1];
+    sStart[threadIdx.x] = (int)lsi[threadIdx.x];
+  }
+  const int LP = L * P;
+  const int rowlen = M * LP * 3;
+  const int64_t row0 = (int64_t)blockIdx.x * QB;
+  const int nrows = (int)min((int64_t)QB, rows - row0);
+  // ---- phase 1: stage (coalesced; rows are rowlen floats, 16-byte aligned when ld_ol % 4 == 0)
+  if ((ld_ol & 3) == 0 && (rowlen & 3) == 0) {
+    const int v4 = rowlen / 4;
+    for (int i = threadIdx.x; i < nrows * v4; i += blockDim.x) {
+      const int r = i / v4, c = i - r * v4;
+      reinterpret_cast<float4*>(s_ol)[r * v4 + c] = __ldg(reinterpret_cast<const float4*>(ol + (row0 + r) * ld_ol) + c);
+    }
+  } else {
+    for (int i = threadIdx.x; i < nrows * rowlen; i += blockDim.x) {
+      const int r = i / rowlen, c = i - r * rowlen;
+      s_ol[r * rowlen + c] = __ldg(ol + (row0 + r) * ld_ol + c);
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: softmax over the L*P logits of each (row, head), max-shifted like torch.softmax
+  for (int i = threadIdx.x; i < nrows * M; i += blockDim.x) {
+    float* lg = s_ol + (i / M) * rowlen + M * LP * 2 + (i % M) * LP;
+    float mx = -INFINITY;
+    for (int k = 0; k < LP; ++k) mx = fmaxf(mx, lg[k]);
+    float den = 0.f;
+    for (int k = 0; k < LP; ++k) {
+      const float e = expf(lg[k] - mx);
+      lg[k] = e;
+      den += e;
+    }
+    for (int k = 0; k < LP; ++k) lg[k] = lg[k] / den;
+  }
+  __syncthreads();
+  // ---- phase 3: gather, one thread per (row, head): the sampling arithmetic is done once per point instead of once
+  // per channel vector, and every bilinear tap is DH/4 16-byte loads of the head's contiguous channels
+  for (int i = threadIdx.x; i < nrows * M; i += blockDim.x) {
+    const int r = i / M, m = i - r * M;
+    const int64_t t = row0 + r;  // b*Lq + q
+    const int b = (int)(t / Lq);
+    const float* offp = s_ol + r * rowlen + m * LP * 2;
+    const float* wp = s_ol + r * rowlen + M * LP * 2 + m * LP;
+    const float* refp = ref + t * L * 2;
+    const int64_t row = (int64_t)M * DH;
+    const float* vb = value + (int64_t)b * S * row + m * DH;
+    float acc[DH];
+#pragma unroll
+    for (int c = 0; c < DH; ++c) acc[c] = 0.f;
+    for (int l = 0; l < L; ++l) {
+      const int H = sH[l], W = sW[l];
+      const float fH = (float)H, fW = (float)W;
+      const float* vl = vb + (int64_t)sStart[l] * row;
+      const float2 rp = __ldg(reinterpret_cast<const float2*>(refp) + l);
+      for (int p = 0; p < P; ++p) {
+        const float2 off = *reinterpret_cast<const float2*>(offp + (l * P + p) * 2);
+        const float wgt = wp[l * P + p];
+        const float lx = rp.x + __fdiv_rn(off.x, fW);
+        const float ly = rp.y + __fdiv_rn(off.y, fH);
+        const float h_im = ly * fH - 0.5f;
+        const float w_im = lx * fW - 0.5f;
+        if (h_im > -1.f && w_im > -1.f && h_im < fH && w_im < fW) {
+          const float hf = floorf(h_im), wf = floorf(w_im);
+          const int h0 = (int)hf, w0 = (int)wf;
+          const float lh = h_im - hf, lw = w_im - wf;
+          const float hh = 1.f - lh, hw = 1.f - lw;
+          const bool top = h0 >= 0, bot = h0 + 1 <= H - 1, lef = w0 >= 0, rig = w0 + 1 <= W - 1;
+          const float* p00 = vl + ((int64_t)h0 * W + w0) * row;
+          const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+#pragma unroll
+          for (int c4 = 0; c4 < DH / 4; ++c4) {
+            float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f), v2 = v1, v3 = v1, v4 = v1;
+            if (top && lef) v1 = __ldg(reinterpret_cast<const float4*>(p00) + c4);
+            if (top && rig) v2 = __ldg(reinterpret_cast<const float4*>(p00 + row) + c4);
+            if (bot && lef) v3 = __ldg(reinterpret_cast<const float4*>(p00 + (int64_t)W * row) + c4);
+            if (bot && rig) v4 = __ldg(reinterpret_cast<const float4*>(p00 + (int64_t)W * row + row) + c4);
+            acc[4 * c4 + 0] += (w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x) * wgt;
+            acc[4 * c4 + 1] += (w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y) * wgt;
+            acc[4 * c4 + 2] += (w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z) * wgt;
+            acc[4 * c4 + 3] += (w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w) * wgt;
+          }
+        }
+      }
+    }
+    float4* op = reinterpret_cast<float4*>(out + (t * M + m) * DH);
+#pragma unroll
+    for (int c4 = 0; c4 < DH / 4; ++c4)
+      op[c4] = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
+  }
+}
+
 template <int VEC>
 __device__ __forceinline__ void vatomic_add(float* p, const float (&g)[VEC]) {
   if constexpr (VEC == 4) {
@@ -350,10 +456,29 @@ extern "C" int msm_ms_deform_attn_fused_fwd(const float* value, const int64_t* s
                   (reinterpret_cast<uintptr_t>(reference_points) & 7) == 0,
               "offsets_logits and reference_points must be 8-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int vec = msm::pick_vec(D, value, out, out);
-  if (vec == 4 && D == 8) vec = 2;
   const int threads = 256;
   const int rowlen = M * L * P * 3;
+  const bool aligned16 = ((reinterpret_cast<uintptr_t>(value) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  if (aligned16 && (D == 4 || D == 8 || D == 16 || D == 32) && M <= threads) {
+    int QB = threads / M;  // one thread per (row, head)
+    while (QB > 1 && (size_t)QB * rowlen * sizeof(float) > 48 * 1024) --QB;
+    MSM_REQUIRE((size_t)QB * rowlen * sizeof(float) <= 48 * 1024, "M*L*P too large for the fused kernel");
+    const int64_t rows = (int64_t)N * Lq;
+    const unsigned blocks = (unsigned)((rows + QB - 1) / QB);
+    const size_t smem = (size_t)QB * rowlen * sizeof(float);
+#define MSM_HEAD_LAUNCH(DH)                                                                                       \
+  msm::msda_fused_head_kernel<DH><<<blocks, threads, smem, st>>>(value, spatial_shapes, level_start_index,         \
+                                                                 offsets_logits, ld_ol, reference_points, out,    \
+                                                                 rows, QB, S, M, D, L, Lq, P)
+    if (D == 4) MSM_HEAD_LAUNCH(4);
+    else if (D == 8) MSM_HEAD_LAUNCH(8);
+    else if (D == 16) MSM_HEAD_LAUNCH(16);
+    else MSM_HEAD_LAUNCH(32);
+#undef MSM_HEAD_LAUNCH
+    return msm::check_launch("msda_fused_head_kernel");
+  }
+  int vec = msm::pick_vec(D, value, out, out);
+  if (vec == 4 && D == 8) vec = 2;
   // rows per block: one thread per (row, head, channel vector), capped by 48 KB of staged offsets / logits
   int QB = threads / (M * (D / vec));
   if (QB < 1) QB = 1;
