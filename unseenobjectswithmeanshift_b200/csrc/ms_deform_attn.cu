@@ -15,6 +15,8 @@
 // serial shared-memory sum, .cuh:306-408); grad_value is scattered with vector atomics.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace msm {
 
 constexpr int kMaxLevels = 32;
@@ -459,7 +461,12 @@ extern "C" int msm_ms_deform_attn_fused_fwd(const float* value, const int64_t* s
   const int threads = 256;
   const int rowlen = M * L * P * 3;
   const bool aligned16 = ((reinterpret_cast<uintptr_t>(value) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
-  if (aligned16 && (D == 4 || D == 8 || D == 16 || D == 32) && M <= threads) {
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("MSM_MSDA_VARIANT");  // 1 = channel-vector threads (A/B switch for profiling)
+    variant = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  if (variant == 0 && aligned16 && (D == 4 || D == 8 || D == 16 || D == 32) && M <= threads) {
     int QB = threads / M;  // one thread per (row, head)
     while (QB > 1 && (size_t)QB * rowlen * sizeof(float) > 48 * 1024) --QB;
     MSM_REQUIRE((size_t)QB * rowlen * sizeof(float) <= 48 * 1024, "M*L*P too large for the fused kernel");
