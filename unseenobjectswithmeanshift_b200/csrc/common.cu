@@ -36,6 +36,15 @@ bool tc_enabled() {
   return cached == 1;
 }
 
+bool pdl_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("MSM_DISABLE_PDL");
+    cached = (e != nullptr && e[0] != '\0' && e[0] != '0') ? 0 : 1;
+  }
+  return cached == 1;
+}
+
 namespace tc {
 
 // cuTensorMapEncodeTiled is a driver entry point; fetching it through the runtime keeps

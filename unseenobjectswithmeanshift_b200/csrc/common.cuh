@@ -51,4 +51,30 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 constexpr float kLog2e = 1.4426950408889634f;
 
+// Programmatic dependent launch (PDL). A kernel launched with launch_pdl may start while its predecessor in the stream
+// is still running: everything before pdl_wait() (barrier init, TMEM allocation, descriptor prefetch) overlaps the
+// predecessor's tail; pdl_wait() returns once the predecessor has completed and its writes are visible, so all
+// global-memory traffic must come after it. pdl_trigger() lets the NEXT kernel begin its own prologue early.
+// Without the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();  // false when MSM_DISABLE_PDL is set
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace msm

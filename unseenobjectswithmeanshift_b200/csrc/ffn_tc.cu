@@ -115,17 +115,20 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
     }
     tc::fence_mbar_init();
   }
+  if (gridDim.x <= 148) pdl_trigger();
+  if (warp == 2) tc::tmem_alloc(tmem_slot, kTmemCols);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
   for (int i = threadIdx.x; i < P.F; i += kThreads) sB1[i] = __ldg(P.b1 + i);
   if (threadIdx.x < D) {
     sPar[threadIdx.x] = __ldg(P.b2 + threadIdx.x);
     sPar[64 + threadIdx.x] = __ldg(P.gamma + threadIdx.x);
     sPar[128 + threadIdx.x] = __ldg(P.beta + threadIdx.x);
   }
-  if (warp == 2) tc::tmem_alloc(tmem_slot, kTmemCols);
-  tc::tc_fence_before();
   __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // =================================================================== X and W1 producer
@@ -410,7 +413,7 @@ static int launch(const float* X, int64_t ldx, const void* w1p, const float* b1,
   const int n_units = (P.m_tiles + 1) / 2;
   const int grid = n_units < num_sms() ? n_units : num_sms();
   const size_t req = smem < (size_t)(120 << 10) ? (size_t)(120 << 10) : smem;
-  ffn_tc_kernel<D><<<grid, kThreads, req, st>>>(xmap, w1map, w2map, ymap, P);
+  MSM_CUDA(launch_pdl(ffn_tc_kernel<D>, dim3(grid), dim3(kThreads), req, st, xmap, w1map, w2map, ymap, P));
   return check_launch("ffn_tc_kernel");
 }
 

@@ -135,11 +135,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     }
     tc::fence_mbar_init();
   }
+  if (gridDim.x <= 148) pdl_trigger();  // every CTA of this launch is resident: dependents may start their prologue
   if (warp == 2) tc::tmem_alloc(tmem_slot, kTmemCols);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // inputs of this launch (and buffers it overwrites) are final from here on
 
   if (warp == 0) {
     // =================================================================== TMA producer
@@ -688,7 +690,7 @@ static int launch(const float* X, int64_t ldx, const void* prepared, const float
   const int grid = tiles < num_sms() ? tiles : num_sms();
   // >= 116 KB of dynamic shared memory keeps it at one CTA per SM (each CTA allocates all of TMEM)
   const size_t req = smem < (size_t)(120 << 10) ? (size_t)(120 << 10) : smem;
-  linear_tc_kernel<<<grid, kThreads, req, st>>>(xmap, wmap, ymap, y2map, P);
+  MSM_CUDA(launch_pdl(linear_tc_kernel, dim3(grid), dim3(kThreads), req, st, xmap, wmap, ymap, y2map, P));
   return check_launch("linear_tc_kernel");
 }
 

@@ -87,11 +87,13 @@ mask_gemm_tc_kernel(const __grid_constant__ CUtensorMap fmap, const Params P) {
     tc::mbar_init(e_ready, 6);
     tc::fence_mbar_init();
   }
+  if (gridDim.x <= 148) pdl_trigger();
   if (warp == 2) tc::tmem_alloc(tmem_slot, kTmemCols);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp >= 2 && warp < 8) {
     // ---- resident B operand: embed[b] -> bf16 hi/lo, K-major canonical layout (rows >= Q are zero):
@@ -297,7 +299,7 @@ int mask_logits_tc(const float* embed, const float* feat, float* masks, int B, i
   int rc = tc::encode_tensor_map_f32(&fmap, feat, 3, dims, strides, box);
   if (rc) return rc;
   MSM_CUDA(cudaFuncSetAttribute(mask_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-  mask_gemm_tc_kernel<<<B * cpi, kThreads, smem, st>>>(fmap, P);
+  MSM_CUDA(launch_pdl(mask_gemm_tc_kernel, dim3(B * cpi), dim3(kThreads), smem, st, fmap, P));
   return check_launch("mask_gemm_tc_kernel");
 }
 

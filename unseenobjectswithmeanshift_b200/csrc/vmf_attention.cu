@@ -224,6 +224,8 @@ __global__ void __launch_bounds__(kThreads) vmf_partial_kernel(const VmfParams P
 __global__ void vmf_finalize_kernel(const float* __restrict__ part_acc, const float* __restrict__ part_den,
                                     float* __restrict__ out, int64_t o_sb, int64_t o_sh, int64_t o_sl,
                                     float* __restrict__ den_out, int G, int heads, int Nq, int hd, int HD, int nsplit) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= G * Nq) return;
@@ -294,8 +296,8 @@ static int launch_finalize(const float* part_acc, const float* part_den, float* 
   const int warps = G * Nq;
   const int threads = 256;
   const int blocks = (warps * 32 + threads - 1) / threads;
-  vmf_finalize_kernel<<<blocks, threads, 0, st>>>(part_acc, part_den, out, o_sb, o_sh, o_sl, den, G, heads, Nq, hd, HD,
-                                                  nsplit);
+  MSM_CUDA(launch_pdl(vmf_finalize_kernel, dim3(blocks), dim3(threads), 0, st, part_acc, part_den, out, o_sb, o_sh, o_sl,
+                      den, G, heads, Nq, hd, HD, nsplit));
   return check_launch("vmf_finalize_kernel");
 }
 

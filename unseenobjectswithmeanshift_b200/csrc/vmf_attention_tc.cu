@@ -162,11 +162,13 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_tc_kernel(const Params P
     tc::mbar_init(q_ready, 4);
     tc::fence_mbar_init();
   }
+  if (gridDim.x <= 148) pdl_trigger();
   if (warp == kMmaWarp) tc::tmem_alloc(tmem_slot, kTmemCols);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp < kSoftmaxWarps) {
     // =================================================================== softmax warps
@@ -464,7 +466,7 @@ static int launch_tc_m(const vtc::Params& P, int G, cudaStream_t st) {
   }
   // >= 116 KB of dynamic shared memory keeps it at one CTA per SM (each CTA allocates all of TMEM)
   const size_t req = smem < (size_t)(120 << 10) ? (size_t)(120 << 10) : smem;
-  vmf_attn_tc_kernel<HD, SHARED, QK16, MASKED><<<G * P.nsplit, kThreads, req, st>>>(P);
+  MSM_CUDA(launch_pdl(vmf_attn_tc_kernel<HD, SHARED, QK16, MASKED>, dim3(G * P.nsplit), dim3(kThreads), req, st, P));
   return check_launch("vmf_attn_tc_kernel");
 }
 
