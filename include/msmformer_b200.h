@@ -145,6 +145,14 @@ int msm_ffn_ln_fwd(const float* X, int64_t ldx, const void* w1_prepared, const f
                    const float* b2, const float* gamma, const float* beta, float eps, float* Y, int64_t ldy, int M,
                    int D, int F, void* stream);
 
+/* Row-wise tail of the decoder's post-norm residual blocks (meanshiftformer_transformer_decoder.py:181, :260, :304,
+ * :637-638, :663) in one launch, rows of C contiguous floats (C <= 1024):
+ *   v = x + y (y may be NULL);  o = LayerNorm(v; gamma, beta, eps);  o = o / max(|o|_2, 1e-12) if l2_normalize;
+ *   out = o;  out2 = LayerNorm(o; gamma2, beta2, eps2) if out2 != NULL. */
+int msm_add_layernorm_fwd(const float* x, const float* y, const float* gamma, const float* beta, float eps,
+                          int l2_normalize, const float* gamma2, const float* beta2, float eps2, float* out,
+                          float* out2, int rows, int C, void* stream);
+
 /* 1x1 convolution on NCHW input with the same kernel: X [B][K][HW] (pixels contiguous), weight prepared as above
  * from the conv weight viewed as [N][K]. y_nchw != 0: Y [B][N][HW] (what nn.Conv2d returns); y_nchw == 0:
  * Y [B][HW][N] (token-major, what the decoders consume after flatten(2).transpose(1,2)).

@@ -467,6 +467,29 @@ def test_linear_residual_layernorm_vs_fp64(msm, M, N, K):
     assert peak_rel(y.cpu().double(), ref) < LINEAR_TOL
 
 
+@pytest.mark.parametrize("rows,C", [(800, 256), (7, 32), (100, 1000), (33, 48)])
+def test_add_layernorm_tail_vs_fp64(msm, rows, C):
+    """norm(tgt + tgt2) -> F.normalize -> decoder_norm of the decoder blocks (decoder.py:181, 260, 304, 637-638, 663)."""
+    g = torch.Generator().manual_seed(rows + C)
+    x, y = torch.randn(rows, C, generator=g), torch.randn(rows, C, generator=g)
+    n1, n2 = torch.nn.LayerNorm(C), torch.nn.LayerNorm(C)
+    with torch.no_grad():
+        for n in (n1, n2):
+            n.weight.copy_(torch.rand(C, generator=g) + 0.5)
+            n.bias.copy_(torch.randn(C, generator=g))
+        o = F.layer_norm(x.double() + y.double(), (C,), n1.weight.double(), n1.bias.double(), n1.eps)
+        z = F.normalize(o, dim=-1)
+        z2 = F.layer_norm(z, (C,), n2.weight.double(), n2.bias.double(), n2.eps)
+        import copy
+        c1, c2 = copy.deepcopy(n1).cuda(), copy.deepcopy(n2).cuda()
+        got = msm.ops.add_layernorm(x.cuda(), y.cuda(), c1)
+        assert peak_rel(got.cpu().double(), o) < 2e-6
+        got, got2 = msm.ops.add_layernorm(x.cuda(), y.cuda(), c1, l2_normalize=True, norm2=c2)
+        assert peak_rel(got.cpu().double(), z) < 2e-6 and peak_rel(got2.cpu().double(), z2) < 2e-6
+        got = msm.ops.add_layernorm(x.cuda(), None, c1)
+        assert peak_rel(got.cpu().double(), F.layer_norm(x.double(), (C,), n1.weight.double(), n1.bias.double(), n1.eps)) < 2e-6
+
+
 @pytest.mark.parametrize("M,D,F", [(12600, 64, 1024), (50400, 64, 1024), (252, 32, 128), (1000, 32, 384), (129, 64, 256)])
 def test_ffn_layernorm_block_vs_fp64(msm, M, D, F):
     """norm2(src + linear2(relu(linear1(src)))) of the deformable encoder layer (pixel_decoder/msdeformattn.py:76-84)

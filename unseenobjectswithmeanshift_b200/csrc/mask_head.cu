@@ -136,19 +136,23 @@ __global__ void __launch_bounds__(GEMM_THREADS) mask_gemm_kernel(const float* __
 }
 
 // Bilinear resample (align_corners=False, PyTorch's source-index rule) -> sigmoid < 0.5 -> bit.
-// One warp emits one 32-bit word (32 consecutive target pixels of one (b, q) row).
-__global__ void mask_bits_kernel(const float* __restrict__ masks, uint32_t* __restrict__ bits,
-                                 int32_t* __restrict__ row_open, int rows, int H, int W, int Ht, int Wt, int words) {
+// One block per (b, q) row; each warp emits 32-bit words (32 consecutive target pixels); the row's "some key is
+// open" flag is a block-wide OR, so no atomics and no zero-fill launch are needed.
+__global__ void __launch_bounds__(256) mask_bits_kernel(const float* __restrict__ masks, uint32_t* __restrict__ bits,
+                                                        int32_t* __restrict__ row_open, int rows, int H, int W, int Ht,
+                                                        int Wt, int words) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
-  const int row = blockIdx.y;
+  const int row = blockIdx.x;
   const float* mp = masks + (int64_t)row * H * W;
   const int St = Ht * Wt;
   const bool identity = (H == Ht) && (W == Wt);
   const float sh = (float)H / (float)Ht, sw = (float)W / (float)Wt;
   bool any_open = false;
-  for (int w = blockIdx.x * warps_per_block + warp_in_block; w < words; w += gridDim.x * warps_per_block) {
+  for (int w = warp_in_block; w < words; w += warps_per_block) {
     const int s = w * 32 + lane;
     bool blocked = false;
     if (s < St) {
@@ -176,7 +180,8 @@ __global__ void mask_bits_kernel(const float* __restrict__ masks, uint32_t* __re
     const uint32_t word = __ballot_sync(0xffffffffu, blocked);
     if (lane == 0) bits[(int64_t)row * words + w] = word;
   }
-  if (__any_sync(0xffffffffu, any_open) && lane == 0) atomicOr(row_open + row, 1);
+  const int open = __syncthreads_or(any_open ? 1 : 0);
+  if (threadIdx.x == 0) row_open[row] = open ? 1 : 0;
 }
 
 }  // namespace msm
@@ -203,14 +208,9 @@ extern "C" int msm_mask_to_attn_bits(const float* masks, uint32_t* bits, int32_t
   MSM_REQUIRE(masks && bits && row_open, "masks, bits, row_open must be non-null");
   MSM_REQUIRE(B > 0 && Q > 0 && H > 0 && W > 0 && Ht > 0 && Wt > 0, "sizes must be positive");
   const int rows = B * Q;
-  MSM_REQUIRE(rows <= 65535, "B*Q too large");
   const int words = (Ht * Wt + 31) / 32;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  MSM_CUDA(cudaMemsetAsync(row_open, 0, sizeof(int32_t) * rows, st));
-  const int wpb = 8;
-  int bx = (words + wpb - 1) / wpb;
-  if (bx > 64) bx = 64;
-  dim3 grid(bx, rows);
-  msm::mask_bits_kernel<<<grid, wpb * 32, 0, st>>>(masks, bits, row_open, rows, H, W, Ht, Wt, words);
+  MSM_CUDA(msm::launch_pdl(msm::mask_bits_kernel, dim3(rows), dim3(256), 0, st, masks, bits, row_open, rows, H, W, Ht, Wt,
+                           words));
   return msm::check_launch("mask_bits_kernel");
 }

@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(256) msda_fused_head_kernel(const float* __res
                                                              const float* __restrict__ ref, float* __restrict__ out,
                                                              int64_t rows, int QB, int S, int M, int D, int L, int Lq,
                                                              int P) {
+  pdl_wait();  // (no early trigger: this launch has far more blocks than fit the GPU at once)
   extern __shared__ __align__(16) float s_ol[];  // [QB][M*L*P*3]
   __shared__ int sH[kMaxLevels], sW[kMaxLevels], sStart[kMaxLevels];
   if (threadIdx.x < L) {
@@ -474,9 +475,9 @@ extern "C" int msm_ms_deform_attn_fused_fwd(const float* value, const int64_t* s
     const unsigned blocks = (unsigned)((rows + QB - 1) / QB);
     const size_t smem = (size_t)QB * rowlen * sizeof(float);
 #define MSM_HEAD_LAUNCH(DH)                                                                                       \
-  msm::msda_fused_head_kernel<DH><<<blocks, threads, smem, st>>>(value, spatial_shapes, level_start_index,         \
-                                                                 offsets_logits, ld_ol, reference_points, out,    \
-                                                                 rows, QB, S, M, D, L, Lq, P)
+  MSM_CUDA(msm::launch_pdl(msm::msda_fused_head_kernel<DH>, dim3(blocks), dim3(threads), smem, st, value,           \
+                           spatial_shapes, level_start_index, offsets_logits, ld_ol, reference_points, out, rows,  \
+                           QB, S, M, D, L, Lq, P))
     if (D == 4) MSM_HEAD_LAUNCH(4);
     else if (D == 8) MSM_HEAD_LAUNCH(8);
     else if (D == 16) MSM_HEAD_LAUNCH(16);

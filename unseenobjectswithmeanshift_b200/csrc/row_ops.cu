@@ -1,0 +1,94 @@
+// Row-wise tail of the decoder's post-norm residual blocks in one launch:
+//   v = x + y ;  o = LayerNorm(v) ;  o = o / max(|o|_2, 1e-12) (optional) ;  out = o ;  out2 = LayerNorm2(o) (optional)
+// Replaces  norm(tgt + dropout(tgt2))  (meanshiftformer_transformer_decoder.py:181, :260, :304), the block's
+// F.normalize (:637-638) and the prediction heads' decoder_norm (:663): 2 to 7 elementwise launches on [B*Q, C].
+// One warp per row, the row lives in registers (C <= 1024); two-pass mean / variance like torch's LayerNorm.
+#include "common.cuh"
+
+namespace msm {
+
+constexpr int kMaxPerLane = 32;  // C <= 1024
+
+__global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                            const float* __restrict__ g1, const float* __restrict__ b1,
+                                                            float eps1, int l2norm, const float* __restrict__ g2,
+                                                            const float* __restrict__ b2, float eps2,
+                                                            float* __restrict__ out, float* __restrict__ out2, int rows,
+                                                            int C) {
+  pdl_trigger();
+  pdl_wait();
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (int64_t)row * C;
+  const float* yr = y != nullptr ? y + (int64_t)row * C : nullptr;
+  float v[kMaxPerLane];
+  const int n = (C + 31) / 32;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    if (i < n) {
+      const int c = lane + 32 * i;
+      float t = 0.f;
+      if (c < C) t = __ldg(xr + c) + (yr != nullptr ? __ldg(yr + c) : 0.f);
+      v[i] = t;
+      s += t;
+    }
+  }
+  const float inv_c = 1.f / (float)C;
+  const float mean = warp_sum(s) * inv_c;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i)
+    if (i < n && lane + 32 * i < C) q = fmaf(v[i] - mean, v[i] - mean, q);
+  const float rstd = rsqrtf(warp_sum(q) * inv_c + eps1);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    if (i < n) {
+      const int c = lane + 32 * i;
+      float o = 0.f;
+      if (c < C) o = (v[i] - mean) * rstd * __ldg(g1 + c) + __ldg(b1 + c);
+      v[i] = o;
+      s1 += o;
+      s2 = fmaf(o, o, s2);
+    }
+  }
+  float scale = 1.f;
+  if (l2norm) scale = 1.f / fmaxf(sqrtf(warp_sum(s2)), 1e-12f);
+  float mean2 = 0.f, rstd2 = 1.f;
+  if (out2 != nullptr) {
+    mean2 = warp_sum(s1) * scale * inv_c;
+    float q2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i)
+      if (i < n && lane + 32 * i < C) q2 = fmaf(v[i] * scale - mean2, v[i] * scale - mean2, q2);
+    rstd2 = rsqrtf(warp_sum(q2) * inv_c + eps2);
+  }
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    if (i < n) {
+      const int c = lane + 32 * i;
+      if (c < C) {
+        const float o = v[i] * scale;
+        out[(int64_t)row * C + c] = o;
+        if (out2 != nullptr) out2[(int64_t)row * C + c] = (o - mean2) * rstd2 * __ldg(g2 + c) + __ldg(b2 + c);
+      }
+    }
+  }
+}
+
+}  // namespace msm
+
+extern "C" int msm_add_layernorm_fwd(const float* x, const float* y, const float* gamma, const float* beta, float eps,
+                                     int l2_normalize, const float* gamma2, const float* beta2, float eps2, float* out,
+                                     float* out2, int rows, int C, void* stream) {
+  MSM_REQUIRE(x && gamma && beta && out, "x, gamma, beta, out must be non-null");
+  MSM_REQUIRE(rows > 0 && C > 0 && C <= 32 * msm::kMaxPerLane, "rows must be positive and 0 < C <= 1024");
+  MSM_REQUIRE(!out2 || (gamma2 && beta2), "the second output needs gamma2 and beta2");
+  const int threads = 256;
+  const int blocks = (rows * 32 + threads - 1) / threads;
+  MSM_CUDA(msm::launch_pdl(msm::add_layernorm_kernel, dim3(blocks), dim3(threads), 0, static_cast<cudaStream_t>(stream), x, y,
+                           gamma, beta, eps, l2_normalize, gamma2, beta2, eps2, out, out2, rows, C));
+  return msm::check_launch("add_layernorm_kernel");
+}

@@ -386,6 +386,7 @@ class _MeanShiftDecoderBase(nn.Module):
         # in_proj(tgt + query_pos) becomes in_proj(tgt) + a cached [Q, N] row-bias table.
         fused = (not torch.is_grad_enabled() and C % 32 == 0 and C <= 256 and self.mask_classification
                  and isinstance(self.decoder_norm, nn.LayerNorm) and ops.tc_linear_enabled()
+                 and all(isinstance(l.norm, nn.LayerNorm) for l in self.transformer_ffn_layers)
                  and self.transformer_ffn_layers[0].linear1.weight.shape[0] % 32 == 0)
         qpos = self.query_embed.weight
         # MSM_DECODER_FUSION: 0 = separate add / LayerNorm kernels; 1 (default) = the query_pos row bias is folded
@@ -415,7 +416,7 @@ class _MeanShiftDecoderBase(nn.Module):
                 if level >= 2:
                     out = ops.linear_fused(o, a.out_proj.weight, a.out_proj.bias, residual=out, norm=ca.norm)
                 else:
-                    out = ca.norm(out + ops.dense(o, a.out_proj.weight, a.out_proj.bias))
+                    out = ops.add_layernorm(out, ops.dense(o, a.out_proj.weight, a.out_proj.bias), ca.norm)
                 del K, V
                 # self-attention (reference :171-181): q = k = out + query_pos, v = out -> one GEMM, N = 3C
                 tqk = ops.cached_value(self, f"tqk{i}", [qpos, sa.in_proj_weight],
@@ -432,11 +433,12 @@ class _MeanShiftDecoderBase(nn.Module):
                     out, dec = ops.linear_fused(hdn, ffn.linear2.weight, ffn.linear2.bias, residual=out, norm=ffn.norm,
                                                 l2_normalize=self.decoder_block_norm, norm2=self.decoder_norm)
                 else:
-                    out = sl.norm(out + ops.dense(o, sa.out_proj.weight, sa.out_proj.bias))
-                    out = ffn(out)
-                    if self.decoder_block_norm:
-                        out = F.normalize(out, dim=-1)
-                    dec = None
+                    out = ops.add_layernorm(out, ops.dense(o, sa.out_proj.weight, sa.out_proj.bias), sl.norm)
+                    # FFN (reference :300-304), block norm (:637-638) and the heads' decoder_norm (:663)
+                    t2 = ops.dense(ops.dense(out, ffn.linear1.weight, ffn.linear1.bias, relu=True),
+                                   ffn.linear2.weight, ffn.linear2.bias)
+                    out, dec = ops.add_layernorm(out, t2, ffn.norm, l2_normalize=self.decoder_block_norm,
+                                                 norm2=self.decoder_norm)
                 logits, masks, bits, row_open = self._heads(out, mask_features, sizes[(i + 1) % L], need_mask, dec=dec)
                 predictions_class.append(logits)
                 predictions_mask.append(masks)

@@ -324,6 +324,30 @@ def ffn_ln(x, w1, b1, w2, b2, norm):
     return out
 
 
+def add_layernorm(x, y, norm, l2_normalize=False, norm2=None):
+    """norm(x + y) [-> F.normalize] [-> also norm2 of the result] in one launch. x, y contiguous [..., C] (y may be
+    None); norm / norm2 affine LayerNorm modules over C <= 1024. Returns out, or (out, out2) when norm2 is given."""
+    _require(x, "x")
+    C = x.shape[-1]
+    xc = x.contiguous()
+    yc = None if y is None else _require(y, "y").contiguous()
+    if yc is not None and yc.shape != xc.shape:
+        raise ValueError("x and y must have the same shape")
+    for nm in (norm, norm2):
+        if nm is not None and not (isinstance(nm, torch.nn.LayerNorm) and nm.elementwise_affine and nm.bias is not None
+                                   and tuple(nm.normalized_shape) == (C,)):
+            raise ValueError("norm / norm2 must be affine LayerNorm modules over the last axis")
+    out = torch.empty_like(xc)
+    out2 = torch.empty_like(xc) if norm2 is not None else None
+    rc = _lib.lib().msm_add_layernorm_fwd(
+        xc.data_ptr(), yc.data_ptr() if yc is not None else None, norm.weight.data_ptr(), norm.bias.data_ptr(),
+        float(norm.eps), 1 if l2_normalize else 0, norm2.weight.data_ptr() if norm2 is not None else None,
+        norm2.bias.data_ptr() if norm2 is not None else None, float(norm2.eps) if norm2 is not None else 0.0,
+        out.data_ptr(), out2.data_ptr() if out2 is not None else None, xc.numel() // C, C, _stream())
+    check(rc, "msm_add_layernorm_fwd")
+    return out if norm2 is None else (out, out2)
+
+
 def conv1x1_supported(x, weight):
     if os.environ.get("MSM_DISABLE_TC_LINEAR", "") not in ("", "0"):
         return False
@@ -675,12 +699,15 @@ def _work_ms(X, Z, kappa, max_iters=10):
 vmf_attention = _instrument("vmf_attention", 2, _work_vmf)(vmf_attention)
 vmf_attention_weights = _instrument("vmf_attention_weights", 1)(vmf_attention_weights)
 mask_logits = _instrument("mask_logits", 1, _work_mask)(mask_logits)
-mask_to_attn_bits = _instrument("mask_to_attn_bits", 1, _work_bits)(mask_to_attn_bits)
+mask_to_attn_bits = _instrument("mask_to_attn_bits", 1, _work_bits)(mask_to_attn_bits)  # one kernel, no memset
 linear = _instrument("linear", 1, _work_linear)(linear)
 conv1x1 = _instrument("linear", 1, _work_conv)(conv1x1)
 conv3x3 = _instrument("linear", 1, _work_conv3)(conv3x3)
 linear_ln = _instrument("linear", 1, _work_linear_ln)(linear_ln)
 ffn_ln = _instrument("ffn", 1, _work_ffn)(ffn_ln)
+add_layernorm = _instrument("add_layernorm", 1, lambda x, y, norm, l2_normalize=False, norm2=None: (
+    f"rows{x.numel() // x.shape[-1]} C{x.shape[-1]}", 4.0 * x.numel() * (3 + (1 if norm2 is not None else 0)), 0.0))(
+    add_layernorm)
 linear_fused = _instrument("linear", 1, _work_linear_fused)(linear_fused)
 ms_deform_attn_forward = _instrument("ms_deform_attn_forward", 1, _work_msda)(ms_deform_attn_forward)
 ms_deform_attn_fused_forward = _instrument("ms_deform_attn_forward", 1, _work_msda_fused)(ms_deform_attn_fused_forward)
