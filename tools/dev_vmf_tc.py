@@ -75,7 +75,7 @@ if __name__ == "__main__":
         child(len(sys.argv) > 2 and sys.argv[2] == "quick")
     else:
         quick = "quick" if (len(sys.argv) > 1 and sys.argv[1] == "quick") else "full"
-        for env in ({"MSM_DISABLE_TC": "1"}, {}, {"MSM_VMF_TC_VSWAP": "1"}):
+        for env in ({"MSM_DISABLE_TC": "1"}, {}):
             print("env", env, flush=True)
             e = dict(os.environ); e.update(env)
             try:

@@ -60,7 +60,6 @@ struct Params {
   float c;  // kappa * log2(e)
   int flags;
   int nsplit, tiles_per_split, ntiles, nstages;
-  int v_desc_swap;  // debug: exchange LBO/SBO of the MN-major V descriptor
   float* part_acc;  // [G][nsplit][Nq][HD]
   float* part_den;  // [G][nsplit][Nq]
 };
@@ -360,7 +359,8 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_tc_kernel(const Params P
       const uint32_t idesc_o = tc::idesc_bf16(128, HD, false, true);
       const uint32_t q_hi = tmem_base + kColQ, q_lo = q_hi + HD / 2;
       const uint32_t d_o = tmem_base + kColO;
-      const uint32_t v_lbo = P.v_desc_swap ? kLboK : 128u, v_sbo = P.v_desc_swap ? 128u : kLboK;
+      // V as the MN-major B operand: 8-key groups are 128 bytes apart (LBO), 8-channel groups kLboK apart (SBO)
+      const uint32_t v_lbo = 128u, v_sbo = kLboK;
       const uint32_t skv = tc::smem_u32(sKV);
 
       auto issue_scores = [&](int j) {
@@ -495,12 +495,6 @@ int vmf_attention_tc_partial(const float* q, int64_t q_sb, int64_t q_sh, int64_t
   const int G = batch * heads;
   vmf_tc_plan(G, Ns, &P.nsplit, &P.tiles_per_split);
   *nsplit_out = P.nsplit;
-  static int swap = -1;
-  if (swap < 0) {
-    const char* e = getenv("MSM_VMF_TC_VSWAP");
-    swap = (e != nullptr && e[0] == '1') ? 1 : 0;
-  }
-  P.v_desc_swap = swap;
   P.part_acc = part_acc;
   P.part_den = part_den;
   const bool shared = (k == v) && k_sb == v_sb && k_sh == v_sh && k_sl == v_sl && !(flags & MSM_VMF_NORMALIZE_K);
