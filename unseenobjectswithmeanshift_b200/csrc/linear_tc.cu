@@ -635,11 +635,21 @@ static int launch(const float* X, int64_t ldx, const void* prepared, const float
   P.xstages = (P.BN > 128 || ln.conv3) ? 3 : kXStages;
   P.xstage_bytes = ln.conv3 ? kHaloStage : kAStageBytes;
   // resident weights when the chunk fits beside at least three X stages (K * BN * 4 bytes <= 128 KB)
-  P.w_resident = (!ln.wide && !ln.conv3 && (int64_t)K * P.BN * 4 <= 128 * 1024) ? 1 : 0;
+  // EXPERIMENTAL, off by default (MSM_LINEAR_RESIDENT=1 enables it): 1.4-1.6x on the K = 256 projections in
+  // isolation (M307200 N256 K256: 250 -> 156 us), but the R50 bench step hung with it under graph replay + PDL,
+  // and the NCHW 128 KB configuration gave wrong results in about half of the runs. Not understood yet.
+  static const bool no_resident = getenv("MSM_LINEAR_RESIDENT") == nullptr;
+  // (token-major inputs only: with NCHW input the 128 KB configuration was flaky on B200 - wrong results or a
+  //  launch failure in ~half of the runs, clean under compute-sanitizer - and is kept on the streaming path)
+  P.w_resident = (!no_resident && !ln.wide && !ln.conv3 && !x_nchw && (int64_t)K * P.BN * 4 <= 128 * 1024) ? 1 : 0;
   if (P.w_resident) {
     const size_t fixed = 1024 + 8 * kYWarpBytes + (size_t)K * P.BN * 4 + 4 * 384 * sizeof(float) + 512;
     int xs = (int)(((size_t)kMaxSmem - fixed) / kAStageBytes);
     P.xstages = xs > kXStages ? kXStages : xs;
+  }
+  if (const char* e = getenv("MSM_DEBUG_XSTAGES")) {
+    const int v = atoi(e);
+    if (v >= 1 && v < P.xstages) P.xstages = v;
   }
   P.wstages = P.BN > 128 ? 3 : kStages;
   P.n_chunks = N / P.BN;
