@@ -150,10 +150,19 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     // =================================================================== TMA producer
     if (lane == 0) {
       tc::Ring xs, rs;
-      if (P.w_resident) {  // weights of this CTA's column chunk: once
-        tc::mbar_arrive_expect_tx(&full_w[0], (uint32_t)nkc * bStage);
-        for (int kc = 0; kc < nkc; ++kc)
-          tc::tma_load_4d(sW + kc * bStage, &wmap, &full_w[0], 0, (int)(blockIdx.x % P.n_chunks) * P.BN, kc * (kKc / 8), 0);
+      if (P.w_resident) {  // weights of this CTA's column chunk: once, spread over the four W barriers so that no
+                           // barrier expects more than 32 KB (a single 128 KB expectation behaved erratically)
+        for (int part = 0; part < kStages; ++part) {
+          const int k0 = nkc * part / kStages, k1 = nkc * (part + 1) / kStages;
+          if (k1 > k0) {
+            tc::mbar_arrive_expect_tx(&full_w[part], (uint32_t)(k1 - k0) * bStage);
+            for (int kc = k0; kc < k1; ++kc)
+              tc::tma_load_4d(sW + kc * bStage, &wmap, &full_w[part], 0, (int)(blockIdx.x % P.n_chunks) * P.BN,
+                              kc * (kKc / 8), 0);
+          } else {
+            tc::mbar_arrive(&full_w[part]);
+          }
+        }
       }
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int mt = tile / P.n_chunks, nc = tile % P.n_chunks;
@@ -201,7 +210,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
       const uint32_t sw = tc::smem_u32(sW);
       tc::Ring as, ws;
       int t = 0;
-      if (P.w_resident) tc::mbar_wait(&full_w[0], 0);
+      if (P.w_resident)
+        for (int part = 0; part < kStages; ++part) tc::mbar_wait(&full_w[part], 0);
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
         const int acc = t % P.nacc;
         tc::mbar_wait(&acc_empty[acc], ((t / P.nacc) & 1) ^ 1);
@@ -636,8 +646,9 @@ static int launch(const float* X, int64_t ldx, const void* prepared, const float
   P.xstage_bytes = ln.conv3 ? kHaloStage : kAStageBytes;
   // resident weights when the chunk fits beside at least three X stages (K * BN * 4 bytes <= 128 KB)
   // EXPERIMENTAL, off by default (MSM_LINEAR_RESIDENT=1 enables it): 1.4-1.6x on the K = 256 projections in
-  // isolation (M307200 N256 K256: 250 -> 156 us), but the R50 bench step hung with it under graph replay + PDL,
-  // and the NCHW 128 KB configuration gave wrong results in about half of the runs. Not understood yet.
+  // isolation (M307200 N256 K256: 250 -> 156 us) and every parity test passes with it, but one in three runs of
+  // the R50 bench step (CUDA-graph replay + programmatic dependent launch) hung, and the NCHW 128 KB configuration
+  // gave wrong results in about half of the runs. Not understood yet - see DESIGN.md section 4.3.
   static const bool no_resident = getenv("MSM_LINEAR_RESIDENT") == nullptr;
   // (token-major inputs only: with NCHW input the 128 KB configuration was flaky on B200 - wrong results or a
   //  launch failure in ~half of the runs, clean under compute-sanitizer - and is kept on the streaming path)
