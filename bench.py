@@ -372,10 +372,16 @@ def main():
         # HBM-bound unless the arithmetic intensity (x3 tensor passes of the bf16 split) exceeds the ridge
         ridge = peaks["bf16_tflops"] * 1e3 / peaks["hbm_gbs"]
         tensor_bound = g["bytes"] > 0 and 3.0 * g["flops"] / g["bytes"] > ridge
+        # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full`
+        # captures of these kernels at these shapes (profiles/r01_ncu_kernels.md); None when no capture exists
+        ncu_traffic = {("mask_logits", "B8 Q100 C256 HW19200"): 186.5e6,
+                       ("ms_deform_attn_forward", "fused N8 S6300 M8 D8 Lq6300"): 76.7e6,
+                       ("ffn", "ffn+LN M50400 D64 F1024"): 13.5e6,
+                       ("linear", "M38400 N768 K256"): None}
         roofline = {"kernel": tag, "shape": sig, "launches_per_step": per, "avg_launch_ms": avg_ms,
                     "share_of_step": (g["ms"] / n_eager) / (ms_dev / args.steps),
                     "algorithmic_bytes_per_launch": g["bytes"] / g["count"],
-                    "algorithmic_flops_per_launch": g["flops"] / g["count"], "traffic": None,
+                    "algorithmic_flops_per_launch": g["flops"] / g["count"], "traffic": ncu_traffic.get((tag, sig)),
                     "timing": "CUDA events around each library call, eager pass of the same step (same stream)",
                     "peak_source": peaks["source"]}
         if tensor_bound:

@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(256) msda_fused_head_kernel(const float* __res
     const float* offp = s_ol + r * rowlen + m * LP * 2;
     const float* wp = s_ol + r * rowlen + M * LP * 2 + m * LP;
     const float* refp = ref + t * L * 2;
-    const int64_t row = (int64_t)M * DH;
+    const int row = M * DH;  // floats per pixel; S * row < 2^31 is checked on the host, so per-image offsets are 32-bit
     const float* vb = value + (int64_t)b * S * row + m * DH;
     float acc[DH];
 #pragma unroll
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(256) msda_fused_head_kernel(const float* __res
     for (int l = 0; l < L; ++l) {
       const int H = sH[l], W = sW[l];
       const float fH = (float)H, fW = (float)W;
-      const float* vl = vb + (int64_t)sStart[l] * row;
+      const float* vl = vb + sStart[l] * row;
       const float2 rp = __ldg(reinterpret_cast<const float2*>(refp) + l);
       for (int p = 0; p < P; ++p) {
         const float2 off = *reinterpret_cast<const float2*>(offp + (l * P + p) * 2);
@@ -310,15 +310,15 @@ __global__ void __launch_bounds__(256) msda_fused_head_kernel(const float* __res
           const float lh = h_im - hf, lw = w_im - wf;
           const float hh = 1.f - lh, hw = 1.f - lw;
           const bool top = h0 >= 0, bot = h0 + 1 <= H - 1, lef = w0 >= 0, rig = w0 + 1 <= W - 1;
-          const float* p00 = vl + ((int64_t)h0 * W + w0) * row;
+          const float* p00 = vl + (h0 * W + w0) * row;
           const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
 #pragma unroll
           for (int c4 = 0; c4 < DH / 4; ++c4) {
             float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f), v2 = v1, v3 = v1, v4 = v1;
             if (top && lef) v1 = __ldg(reinterpret_cast<const float4*>(p00) + c4);
             if (top && rig) v2 = __ldg(reinterpret_cast<const float4*>(p00 + row) + c4);
-            if (bot && lef) v3 = __ldg(reinterpret_cast<const float4*>(p00 + (int64_t)W * row) + c4);
-            if (bot && rig) v4 = __ldg(reinterpret_cast<const float4*>(p00 + (int64_t)W * row + row) + c4);
+            if (bot && lef) v3 = __ldg(reinterpret_cast<const float4*>(p00 + W * row) + c4);
+            if (bot && rig) v4 = __ldg(reinterpret_cast<const float4*>(p00 + W * row + row) + c4);
             acc[4 * c4 + 0] += (w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x) * wgt;
             acc[4 * c4 + 1] += (w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y) * wgt;
             acc[4 * c4 + 2] += (w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z) * wgt;
@@ -467,7 +467,8 @@ extern "C" int msm_ms_deform_attn_fused_fwd(const float* value, const int64_t* s
     const char* e = getenv("MSM_MSDA_VARIANT");  // 1 = channel-vector threads (A/B switch for profiling)
     variant = (e != nullptr && e[0] == '1') ? 1 : 0;
   }
-  if (variant == 0 && aligned16 && (D == 4 || D == 8 || D == 16 || D == 32) && M <= threads) {
+  if (variant == 0 && aligned16 && (D == 4 || D == 8 || D == 16 || D == 32) && M <= threads &&
+      (int64_t)S * M * D < (int64_t)1 << 31) {
     int QB = threads / M;  // one thread per (row, head)
     while (QB > 1 && (size_t)QB * rowlen * sizeof(float) > 48 * 1024) --QB;
     MSM_REQUIRE((size_t)QB * rowlen * sizeof(float) <= 48 * 1024, "M*L*P too large for the fused kernel");
