@@ -184,6 +184,50 @@ __global__ void __launch_bounds__(256) mask_bits_kernel(const float* __restrict_
   if (threadIdx.x == 0) row_open[row] = open ? 1 : 0;
 }
 
+// Many-keys form (full-resolution key grids, S = 307200): several blocks per row, the row flag by atomicOr into a
+// zero-filled array.
+__global__ void mask_bits_multi_kernel(const float* __restrict__ masks, uint32_t* __restrict__ bits,
+                                 int32_t* __restrict__ row_open, int rows, int H, int W, int Ht, int Wt, int words) {
+  const int lane = threadIdx.x & 31;
+  const int warp_in_block = threadIdx.x >> 5;
+  const int warps_per_block = blockDim.x >> 5;
+  const int row = blockIdx.y;
+  const float* mp = masks + (int64_t)row * H * W;
+  const int St = Ht * Wt;
+  const bool identity = (H == Ht) && (W == Wt);
+  const float sh = (float)H / (float)Ht, sw = (float)W / (float)Wt;
+  bool any_open = false;
+  for (int w = blockIdx.x * warps_per_block + warp_in_block; w < words; w += gridDim.x * warps_per_block) {
+    const int s = w * 32 + lane;
+    bool blocked = false;
+    if (s < St) {
+      float val;
+      if (identity) {
+        val = mp[s];
+      } else {
+        const int y = s / Wt, x = s - y * Wt;
+        float sy = sh * ((float)y + 0.5f) - 0.5f;
+        float sx = sw * ((float)x + 0.5f) - 0.5f;
+        sy = sy < 0.f ? 0.f : sy;
+        sx = sx < 0.f ? 0.f : sx;
+        const int y0 = (int)sy, x0 = (int)sx;
+        const int yp = (y0 < H - 1) ? 1 : 0, xp = (x0 < W - 1) ? 1 : 0;
+        const float ly = sy - (float)y0, lx = sx - (float)x0;
+        const float hy = 1.f - ly, hx = 1.f - lx;
+        const float* p = mp + (int64_t)y0 * W + x0;
+        const float v00 = __ldg(p), v01 = __ldg(p + xp), v10 = __ldg(p + yp * W), v11 = __ldg(p + yp * W + xp);
+        val = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+      }
+      const float sig = 1.f / (1.f + expf(-val));  // the reference thresholds the sigmoid, not the logit
+      blocked = sig < 0.5f;
+      any_open |= !blocked;
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, blocked);
+    if (lane == 0) bits[(int64_t)row * words + w] = word;
+  }
+  if (__any_sync(0xffffffffu, any_open) && lane == 0) atomicOr(row_open + row, 1);
+}
+
 }  // namespace msm
 
 extern "C" int msm_mask_logits(const float* embed, const float* feat, float* masks, int B, int Q, int C, int64_t HW,
@@ -210,6 +254,14 @@ extern "C" int msm_mask_to_attn_bits(const float* masks, uint32_t* bits, int32_t
   const int rows = B * Q;
   const int words = (Ht * Wt + 31) / 32;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (words > 1024 && rows <= 65535) {  // one block per row would leave most of the GPU idle
+    MSM_CUDA(cudaMemsetAsync(row_open, 0, sizeof(int32_t) * rows, st));
+    const int wpb = 8;
+    int bx = (words + wpb - 1) / wpb;
+    if (bx > 64) bx = 64;
+    msm::mask_bits_multi_kernel<<<dim3(bx, rows), wpb * 32, 0, st>>>(masks, bits, row_open, rows, H, W, Ht, Wt, words);
+    return msm::check_launch("mask_bits_multi_kernel");
+  }
   MSM_CUDA(msm::launch_pdl(msm::mask_bits_kernel, dim3(rows), dim3(256), 0, st, masks, bits, row_open, rows, H, W, Ht, Wt,
                            words));
   return msm::check_launch("mask_bits_kernel");
