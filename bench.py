@@ -223,6 +223,7 @@ def main():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--vmf-tflops", action="store_true", help="also time the attention core alone (default with the CPU baseline)")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: leave out the host-buffer leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
@@ -398,6 +399,40 @@ def main():
                                    "TFLOPps": v["flops"] / v["ms"] / 1e9 if v["ms"] else None} for (t, sg), v in top]
     op_summary = {k: {"calls_per_step": c, "ms_per_step": t} for k, (c, t) in op_ms.items()}
 
+    # ---------------- vMF attention TFLOP/s (second half of BASELINE.json's metric): the attention core alone at the
+    # full-resolution key grid of the UCN config (1 image, 8 heads, 100 queries, 307200 keys, hd 32, masked),
+    # L2 flushed between launches, CUDA events on the launching stream
+    vmf = None
+    if not args.no_cpu_baseline or args.vmf_tflops:
+        with torch.no_grad():
+            gq = torch.Generator(device=dev).manual_seed(5)
+            Sk, Hh, Qn, hd = 307200, 8, 100, 32
+            q = torch.randn(1, Qn, Hh * hd, device=dev, generator=gq)
+            k = torch.randn(1, Sk, Hh * hd, device=dev, generator=gq)
+            v = torch.randn(1, Sk, Hh * hd, device=dev, generator=gq)
+            bits = torch.randint(-2 ** 31, 2 ** 31 - 1, (1, Qn, Sk // 32), device=dev, dtype=torch.int32)
+            ro = torch.ones(1, Qn, device=dev, dtype=torch.int32)
+            hv = lambda t: t.unflatten(-1, (Hh, hd)).permute(0, 2, 1, 3)  # noqa: E731
+            flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+            for _ in range(3):
+                ops.vmf_attention(hv(q), hv(k), hv(v), blocked_bits=bits, row_open=ro)
+            ts = []
+            for _ in range(10):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                ops.vmf_attention(hv(q), hv(k), hv(v), blocked_bits=bits, row_open=ro)
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            t_ms = statistics.median(ts)
+            fl = 4.0 * Hh * Qn * Sk * hd
+            vmf = {"shape": f"B1 H{Hh} Q{Qn} S{Sk} hd{hd} masked", "ms": t_ms, "tflops_useful": fl / t_ms / 1e9,
+                   "tflops_tensor_passes": 3 * fl / t_ms / 1e9,
+                   "frac_of_bf16_peak": 3 * fl / t_ms / 1e9 / peaks["bf16_tflops"],
+                   "GBps": 4.0 * 2 * Sk * Hh * hd / t_ms / 1e6, "frac_of_hbm_peak": 4.0 * 2 * Sk * Hh * hd / t_ms / 1e6 / peaks["hbm_gbs"]}
+            del q, k, v, bits, flush
+
     # ---------------- CPU baseline (oracle port) on a bounded sample, rank 0, N == 1 only
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -441,7 +476,7 @@ def main():
                     "how": "pinned host features -> device every step, pred_logits + pred_masks -> pinned host every "
                            "step; transfers of neighbouring steps overlap the graph replay on separate streams"},
             "gpu_launches": launches,
-            "roofline": roofline, "op_ms": op_summary, "cpu_baseline": cpu_baseline}
+            "roofline": roofline, "vmf_attention": vmf, "op_ms": op_summary, "cpu_baseline": cpu_baseline}
     print(json.dumps(line), flush=True)
 
 
