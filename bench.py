@@ -28,6 +28,17 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
+# stdout carries exactly ONE JSON line. Libraries (NCCL's version banner, cuDNN notices) write to file descriptor 1
+# directly, so the process's fd 1 is pointed at stderr and the JSON line goes to a duplicate of the original stdout.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 METRIC = "images/sec MSMFormer head forward 640x480 (R50 config: MSDeformAttn pixel decoder + 9-layer mean-shift decoder, 100 queries)"
 PER_GPU_BATCH = 8
 
@@ -119,7 +130,7 @@ def run_reference(args, rank, world):
                              "sample": f"{args.steps} steps x {sample_b} image(s) of the same head workload"},
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_meanshift(args, rank, local_rank, world, dev, sharding, ops):
@@ -210,7 +221,7 @@ def run_meanshift(args, rank, local_rank, world, dev, sharding, ops):
                          "tensor_TFLOPps_issued": 3.0 * fl / t / 1e12,
                          "tensor_frac_of_bf16_peak": 3.0 * fl / t / 1e12 / peaks["bf16_tflops"]},
             "cpu_baseline": cpu_baseline}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -477,7 +488,7 @@ def main():
                            "step; transfers of neighbouring steps overlap the graph replay on separate streams"},
             "gpu_launches": launches,
             "roofline": roofline, "vmf_attention": vmf, "op_ms": op_summary, "cpu_baseline": cpu_baseline}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 if __name__ == "__main__":
