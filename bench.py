@@ -224,13 +224,128 @@ def run_meanshift(args, rank, local_rank, world, dev, sharding, ops):
     emit(line)
 
 
+def run_cluster(args, rank, local_rank, world, dev, sharding, ops):
+    """the whole classical clusterer (mean_shift_smart_init / clustering_features,
+    lib/fcn/test_dataset.py:43-59) on config #4's geometry: 640x480x64-d unit embeddings, 100 farthest-point seeds,
+    kappa=20, 10 hill-climb iterations, connected components, nearest-seed labels. `--batch` images per GPU
+    (default 16). One step = the batch through all four stages, no host synchronisation inside."""
+    import torch.nn.functional as F
+    from unseenobjectswithmeanshift_b200.meanshiftformer.modeling.transformer_decoder import mean_shift as ms
+    B = args.batch if args.batch != PER_GPU_BATCH else 16
+    n, d, m, kappa, iters, objects = 480 * 640, 64, 100, 20.0, 10, 12
+    g = torch.Generator().manual_seed(40 + rank)
+    hostX = torch.empty(B, n, d).pin_memory()
+    for b in range(B):
+        centers = F.normalize(torch.randn(objects, d, generator=g), dim=1)
+        which = torch.multinomial(torch.arange(objects, 0, -1).float(), n, replacement=True, generator=g)
+        hostX[b] = F.normalize(centers[which] + 0.04 * torch.randn(n, d, generator=g), dim=1)
+    first = torch.randint(0, n, (B,), generator=g)
+    X, first_dev = hostX.to(dev), first.to(dev)
+    hostOut = torch.empty(B, n, dtype=torch.int64).pin_memory()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    stage_ms = [0.0] * 4
+    sampler = ClockSampler(local_rank)
+
+    def step(Xd, record=False):
+        if record:
+            ev[0].record()
+        seeds, selected = ops.select_smart_seeds(Xd, m, first_dev)
+        if record:
+            ev[1].record()
+        Z = ops.mean_shift_hill_climb(Xd, seeds, kappa, iters)
+        if record:
+            ev[2].record()
+        seed_labels, num = ops.seed_connected_components(Z, 0.04)
+        if record:
+            ev[3].record()
+        labels = ops.assign_clusters(Xd, Z, seed_labels, num)
+        if record:
+            ev[4].record()
+        return labels, selected
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            step(X)
+        torch.cuda.synchronize()
+        for _ in range(3):   # stage split (events between the stages; not part of the timed region)
+            step(X, record=True)
+            torch.cuda.synchronize()
+            for i in range(4):
+                stage_ms[i] += ev[i].elapsed_time(ev[i + 1]) / 3
+        sharding.barrier()
+        if rank == 0:
+            sampler.start()
+        ops.reset_stats()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            labels, selected = step(X)
+        e1.record()
+        torch.cuda.synchronize()
+        sharding.barrier()
+        ms_dev = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
+        launches = ops.launches()
+        stage = torch.empty_like(X)
+        n_e2e = max(1, min(args.steps, 3))
+        for timed in (False, True):
+            if timed:
+                e0.record()
+            for _ in range(n_e2e if timed else 1):
+                stage.copy_(hostX, non_blocking=True)
+                hostOut.copy_(step(stage)[0], non_blocking=True)
+            if timed:
+                e1.record()
+            torch.cuda.synchronize()
+            sharding.barrier()
+        ms_e2e = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        return
+    peaks = load_peaks()
+    value = B * world * args.steps / (ms_dev / 1e3)
+    by = (4.0 * d + 8.0) * B * n * (m - 1)   # X + the running nearest-seed distance, once per seeding pass
+    t_seed = stage_ms[0] / 1e3
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import mean_shift as oms
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        t0 = time.perf_counter()
+        ref_labels, ref_sel = oms.mean_shift_smart_init(hostX[0], kappa, m, iters, int(first[0]))
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": 1.0 / dt, "unit": "images/s", "cores": cores, "kind": "port",
+                        "sample": f"1 image, whole clusterer (oracle, fp32, {cores} threads)",
+                        "parity_on_sample": {"seed_indices_equal": bool(torch.equal(selected[0].cpu(), ref_sel)),
+                                             "label_agreement": float((labels[0].cpu() == ref_labels).float().mean())}}
+    line = {"metric": "images/sec classical vMF mean-shift clustering (640x480x64-d embeddings: 100 farthest-point "
+                      "seeds, kappa=20, 10 iterations, connected components, nearest-seed labels)",
+            "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"cluster n=307200 d=64 m=100 kappa=20 iters=10 batch {B}/GPU",
+                       "global_batch": B * world, "parallelism": f"replicas x{world} (batch-sharded, no collective)",
+                       "l2_policy": f"inputs_exceed_l2 ({4.0 * B * n * d / 1e6:.0f} MB of embeddings per pass)"},
+            "clocks": clocks,
+            "e2e": {"value": B * world * n_e2e / (ms_e2e / 1e3), "unit": "images/s",
+                    "h2d_bytes_per_step": hostX.numel() * 4, "d2h_bytes_per_step": hostOut.numel() * 8,
+                    "ms_per_step": ms_e2e / n_e2e},
+            "gpu_launches": launches,
+            "stage_ms": {"select_smart_seeds": stage_ms[0], "hill_climb": stage_ms[1],
+                         "connected_components": stage_ms[2], "assign_clusters": stage_ms[3]},
+            "roofline": {"kernel": "smart_seeds_kernel<64>", "bound": "hbm", "achieved": by / t_seed / 1e9,
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": by / t_seed / 1e9 / peaks["hbm_gbs"],
+                         "traffic": None, "algorithmic_bytes_per_step": by, "peak_source": peaks["source"]},
+            "cpu_baseline": cpu_baseline}
+    emit(line)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="r50", choices=["r50", "ucn", "crop", "meanshift"])
+    ap.add_argument("--workload", default="r50", choices=["r50", "ucn", "crop", "meanshift", "cluster"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
@@ -257,6 +372,9 @@ def main():
     kind, B = args.workload, args.batch
     if kind == "meanshift":
         run_meanshift(args, rank, local_rank, world, dev, sharding, ops)
+        return
+    if kind == "cluster":
+        run_cluster(args, rank, local_rank, world, dev, sharding, ops)
         return
 
     head = workloads.build_head(kind).to(dev)

@@ -216,6 +216,36 @@ int msm_mean_shift_hill_climb(const float* X, const float* Z0, float* Z_out,
                               int B, int n, int m, int d, float kappa, int max_iters,
                               void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * The rest of the classical clusterer (cosine metric), batched over images, no host round-trips.
+ *
+ * msm_select_smart_seeds replaces select_smart_seeds(X, num_seeds, return_selected_indices=True),
+ *   transformer_decoder/mean_shift.py:128-189: seed 0 = X[first_index[b]] (the reference draws it with
+ *   np.random.randint, :155; the caller supplies the draw), seed i+1 = the point with the largest distance
+ *   0.5 (1 - x.s) to its nearest chosen seed, ties -> smallest index (torch.argmax).
+ *   X [B][n][d] unit rows, first_index [B] int64 (device), seeds [B][num_seeds][d], selected [B][num_seeds] int64.
+ *   d in {16, 32, 64, 128}. One cooperative launch per <= (co-resident CTAs) images.
+ * msm_seed_connected_components replaces connected_components(Z, epsilon), mean_shift.py:41-76:
+ *   seed_labels [B][m] int64, num_labels [B] int32 = number of distinct labels (len(torch.unique(.)), :218).
+ * msm_assign_clusters replaces mean_shift.py:207-227: every point takes the label of its closest seed
+ *   (first minimum, torch.argmin), then label 0 and the most populous label among 0..num_labels-1 swap.
+ *   labels [B][n] int64.
+ * ---------------------------------------------------------------------------------------------- */
+size_t msm_smart_seeds_workspace_bytes(int B, int n, int num_seeds);
+
+int msm_select_smart_seeds(const float* X, const int64_t* first_index, float* seeds, int64_t* selected,
+                           int B, int n, int d, int num_seeds,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+int msm_seed_connected_components(const float* Z, int64_t* seed_labels, int32_t* num_labels,
+                                  int B, int m, int d, float epsilon, void* stream);
+
+size_t msm_assign_clusters_workspace_bytes(int B, int m);
+
+int msm_assign_clusters(const float* X, const float* Z, const int64_t* seed_labels, const int32_t* num_labels,
+                        int64_t* labels, int B, int n, int m, int d,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -287,6 +287,25 @@ def gen_mean_shift():
          first_seed_index=np.int64(sel[0].item()))
 
 
+def gen_mean_shift_d64():
+    """The whole classical clusterer at the UOIS embedding width (d = 64, 100 seeds, kappa 20, 10 iterations,
+    lib/fcn/test_dataset.py:43-59) on a 40x60 synthetic embedding map with 7 objects of unequal size."""
+    ms = ref_shim.ref("modeling.transformer_decoder.mean_shift")
+    torch.manual_seed(11)
+    n, d, c = 2400, 64, 7
+    centers = F.normalize(torch.randn(c, d), dim=1)
+    which = torch.multinomial(torch.tensor([8.0, 5, 3, 2, 1, 1, 0.5]), n, replacement=True)
+    X = F.normalize(centers[which] + 0.04 * torch.randn(n, d), dim=1)
+    np.random.seed(3)
+    seeds, sel = ms.select_smart_seeds(X, 100, return_selected_indices=True)
+    seed_labels, Z = ms.mean_shift_with_seeds(X, seeds.clone(), 20, max_iters=10)
+    np.random.seed(3)
+    labels, sel2 = ms.mean_shift_smart_init(X, kappa=20, num_seeds=100, max_iters=10)
+    assert torch.equal(sel, sel2)
+    save("mean_shift_d64", X=X, first_seed_index=np.int64(sel[0].item()), smart_indices=sel, smart_seeds=seeds,
+         Z=Z, seed_labels=seed_labels, smart_init_labels=labels)
+
+
 if __name__ == "__main__":
     gen_hypersphere_attention()
     gen_meanshift_attention()
@@ -299,3 +318,4 @@ if __name__ == "__main__":
     gen_pixel_decoder_simple()
     gen_head_r50style()
     gen_mean_shift()
+    gen_mean_shift_d64()

@@ -405,6 +405,124 @@ def test_mean_shift_config4_size_properties(msm):
     assert (Z.cpu() - ref).abs().max().item() < 1e-4
 
 
+# ----------------------------------------------------------------------------- classical clusterer
+def _clustered_points(n, d, c, seed, noise=0.04):
+    g = torch.Generator().manual_seed(seed)
+    centers = F.normalize(torch.randn(c, d, generator=g), dim=1)
+    which = torch.multinomial(torch.arange(c, 0, -1).float(), n, replacement=True, generator=g)
+    return F.normalize(centers[which] + noise * torch.randn(n, d, generator=g), dim=1)
+
+
+def _assert_seed_sequence(X, got, want, tol=3e-7):
+    """farthest-point indices: identical, or first divergent at a step whose two candidates tie within fp32
+    summation-order noise (after such a step the two sequences are legitimately different)."""
+    got, want = got.cpu(), want.cpu()
+    if torch.equal(got, want):
+        return
+    step = int((got != want).nonzero()[0])
+    assert step > 0, "first seed is given"
+    nearest = (0.5 * (1 - X @ X[want[:step]].t())).min(dim=1)[0]
+    gap = (nearest[want[step]] - nearest[got[step]]).abs().item()
+    assert gap < tol, f"seed {step}: picked {int(got[step])} instead of {int(want[step])}, distance gap {gap:.3e}"
+
+
+def _assert_assignment(X, Z, seed_labels, got, tol=3e-7):
+    """nearest-seed labels (before the largest-to-zero swap is undone by the caller): mismatches only where the
+    two closest seeds of different clusters are equidistant within fp32 noise."""
+    dist = 0.5 * (1 - X @ Z.t())
+    want = seed_labels[dist.argmin(dim=1)]
+    bad = (got != want).nonzero()[:, 0]
+    for p in bad.tolist():
+        mine = dist[p][seed_labels == got[p]]
+        assert mine.numel() and (mine.min() - dist[p].min()).item() < tol, f"point {p}: label {int(got[p])} vs {int(want[p])}"
+    return want
+
+
+def test_clusterer_golden_d64(msm, golden):
+    """select_smart_seeds / connected_components / mean_shift_smart_init (mean_shift.py:41-76, 128-229) against the
+    reference's own outputs at the UOIS width: d = 64, 100 seeds, kappa 20, 10 iterations."""
+    from unseenobjectswithmeanshift_b200.meanshiftformer.modeling.transformer_decoder import mean_shift as ms
+    g, _ = golden("mean_shift_d64")
+    X, first = g["X"].cuda(), int(g["first_seed_index"])
+    with torch.no_grad():
+        seeds, idx = ms.select_smart_seeds(X, 100, return_selected_indices=True, first_index=first)
+        assert idx.device.type == "cpu" and idx.dtype == torch.int64
+        assert torch.equal(idx, g["smart_indices"])
+        assert torch.equal(seeds.cpu(), g["smart_seeds"])            # rows of X: bit-exact
+        cc = ms.connected_components(g["Z"].cuda(), 0.04)
+        assert cc.device.type == "cpu" and torch.equal(cc, g["seed_labels"])
+        labels, idx = ms.mean_shift_smart_init(X, 20, 100, 10, first_index=first)
+        assert torch.equal(idx, g["smart_indices"])
+        assert torch.equal(labels.cpu(), g["smart_init_labels"])      # instance labels: bit-exact
+        # clustering_features (lib/fcn/test_dataset.py:43-59) on the same points laid out as a [B,C,H,W] map,
+        # second image = the first one mirrored: one batched pass == two single-image calls
+        fmap = X.t().reshape(1, 64, 40, 60)
+        both = torch.cat([fmap, fmap.flip(3)])
+        out, sel = ms.clustering_features(both, num_seeds=100, kappa=20, first_index=[first, 5])
+        assert out.shape == (2, 40, 60) and out.dtype == torch.float32
+        assert torch.equal(out[0].cpu().long().flatten(), g["smart_init_labels"])
+        assert torch.equal(sel[0], g["smart_indices"])
+        X1 = both[1].reshape(64, -1).t().contiguous()
+        l1, s1 = ms.mean_shift_smart_init(X1, 20, 100, 10, first_index=5)
+        assert torch.equal(out[1].long().flatten(), l1) and torch.equal(sel[1], s1)
+
+
+@pytest.mark.parametrize("B,n,d,m", [(1, 20000, 64, 100), (3, 7777, 32, 40), (2, 5000, 128, 17), (5, 999, 16, 12),
+                                     (2, 3, 64, 3), (1, 50, 64, 1)])
+def test_clusterer_vs_oracle(msm, B, n, d, m):
+    """each stage against the CPU oracle on the same inputs; ragged sizes, every supported width, m = 1,
+    n < points per warp."""
+    X = torch.stack([_clustered_points(n, d, 6, 100 * b + n) for b in range(B)])
+    first = [(37 * b + 11) % n for b in range(B)]
+    with torch.no_grad():
+        seeds, sel = msm.ops.select_smart_seeds(X.cuda(), m, first)
+        Z = msm.ops.mean_shift_hill_climb(X.cuda(), seeds, 20.0, 10)
+        seed_labels, num = msm.ops.seed_connected_components(Z, 0.04)
+        labels = msm.ops.assign_clusters(X.cuda(), Z, seed_labels, num)
+    assert sel.dtype == torch.int64 and seed_labels.dtype == torch.int64 and labels.dtype == torch.int64
+    for b in range(B):
+        _, want = oms.select_smart_seeds(X[b], m, first[b])
+        _assert_seed_sequence(X[b], sel[b], want)
+        assert torch.equal(seeds[b].cpu(), X[b][sel[b].cpu()])
+        Zb = Z[b].cpu()
+        want_cc = oms.connected_components(Zb, 0.04)
+        assert torch.equal(seed_labels[b].cpu(), want_cc)
+        assert int(num[b]) == len(torch.unique(want_cc))
+        # undo nothing: recompute the reference relabelling from the (noise-checked) closest-seed labels
+        got = labels[b].cpu()
+        count = torch.bincount(got, minlength=int(num[b]))
+        assert int(count[:int(num[b])].argmax()) == 0                 # most populous cluster carries label 0
+        pre = oms.connected_components(Zb, 0.04)[(0.5 * (1 - X[b] @ Zb.t())).argmin(dim=1)]
+        cnt = torch.stack([(pre == i).sum() for i in range(int(num[b]))])
+        big = int(cnt.argmax())
+        unswapped = got.clone()
+        if big != 0:
+            unswapped[got == 0], unswapped[got == big] = big, 0
+        _assert_assignment(X[b], Zb, want_cc, unswapped)
+
+
+def test_clusterer_config4_size(msm):
+    """BASELINE config #4 geometry (n = 307200, d = 64, 100 seeds), two images in one pass: oracle seeding sequence,
+    and the properties the labels must have at any size."""
+    n, d, m = 307200, 64, 100
+    X = torch.stack([_clustered_points(n, d, 12, 4), _clustered_points(n, d, 5, 5, noise=0.1)])
+    first = [123456, 7]
+    from unseenobjectswithmeanshift_b200.meanshiftformer.modeling.transformer_decoder import mean_shift as ms
+    with torch.no_grad():
+        labels, sel, Z = ms.mean_shift_smart_init_batched(X.cuda(), 20, m, 10, first)
+        labels1, sel1, _ = ms.mean_shift_smart_init_batched(X[1:].cuda(), 20, m, 10, first[1:])
+    assert torch.equal(labels[1], labels1[0]) and torch.equal(sel[1], sel1[0])   # batching changes nothing
+    for b in range(2):
+        _, want = oms.select_smart_seeds(X[b], m, first[b])
+        _assert_seed_sequence(X[b], sel[b], want)
+        assert sel[b].unique().numel() == m                                       # farthest points never repeat
+        want_cc = oms.connected_components(Z[b].cpu(), 0.04)
+        got = labels[b].cpu()
+        assert int(got.min()) == 0 and int(got.max()) < len(torch.unique(want_cc))
+        count = torch.bincount(got)
+        assert int(count.argmax()) == 0
+
+
 # ----------------------------------------------------------------------------- dense layers (tcgen05 linear kernel)
 # bf16x3 split-precision products: ~2^-17 relative per product, fp32 accumulation -> 2e-5 of the output's peak.
 LINEAR_TOL = 2e-5

@@ -148,3 +148,19 @@ def test_mean_shift(golden):
     assert torch.equal(idx, g["smart_indices"])
     assert torch.equal(labels, g["smart_init_labels"])
     assert int(np.bincount(labels.numpy()).argmax()) == 0  # largest cluster carries label 0
+
+
+def test_mean_shift_clusterer_d64(golden):
+    """whole clusterer at the UOIS width (d = 64, 100 seeds, kappa 20): oracle == reference outputs."""
+    g, _ = golden("mean_shift_d64")
+    X, first = g["X"], int(g["first_seed_index"])
+    seeds, idx = oms.select_smart_seeds(X, 100, first)
+    assert torch.equal(idx, g["smart_indices"])
+    assert torch.equal(seeds, g["smart_seeds"])
+    seed_labels, Z = oms.mean_shift_with_seeds(X, seeds, 20, 10)
+    torch.testing.assert_close(Z, g["Z"], **TOL)
+    assert torch.equal(seed_labels, g["seed_labels"])
+    assert torch.equal(oms.connected_components(g["Z"], 0.04), g["seed_labels"])
+    labels, idx = oms.mean_shift_smart_init(X, 20, 100, 10, first)
+    assert torch.equal(labels, g["smart_init_labels"])
+    assert int(np.bincount(labels.numpy()).argmax()) == 0

@@ -40,6 +40,11 @@ SIGNATURES = {
     "msm_ms_deform_attn_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "msm_mean_shift_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "msm_mean_shift_hill_climb": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _I, _P, _Z, _P]),
+    "msm_smart_seeds_workspace_bytes": (_Z, [_I, _I, _I]),
+    "msm_select_smart_seeds": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),
+    "msm_seed_connected_components": (_I, [_P, _P, _P, _I, _I, _I, _F, _P]),
+    "msm_assign_clusters_workspace_bytes": (_Z, [_I, _I]),
+    "msm_assign_clusters": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),
 }
 
 

@@ -555,6 +555,72 @@ def mean_shift_hill_climb(X, Z, kappa, max_iters=10):
     return out[0] if squeeze else out
 
 
+def _points(X, name="X"):
+    Xb = _require(X, name).contiguous()
+    return (Xb.unsqueeze(0), True) if Xb.dim() == 2 else (Xb, False)
+
+
+def select_smart_seeds(X, num_seeds, first_index):
+    """Farthest-point seeding, batched: X [B,n,d] (or [n,d]) unit rows, first_index [B] (int / sequence / int64
+    tensor; the reference draws it with np.random.randint, mean_shift.py:155) ->
+    (seeds [B,num_seeds,d], selected int64 [B,num_seeds]). One cooperative launch, no host sync."""
+    Xb, squeeze = _points(X)
+    B, n, d = Xb.shape
+    if torch.is_tensor(first_index):
+        first = first_index.to(device=Xb.device, dtype=torch.int64).reshape(-1).contiguous()
+    else:
+        first = torch.as_tensor(first_index, dtype=torch.int64).reshape(-1).to(Xb.device)
+    if first.numel() != B:
+        raise ValueError(f"first_index has {first.numel()} entries for {B} images")
+    if d not in (16, 32, 64, 128):
+        raise ValueError(f"embedding dim {d} not supported (16, 32, 64, 128)")
+    seeds = torch.empty(B, num_seeds, d, device=Xb.device, dtype=torch.float32)
+    selected = torch.empty(B, num_seeds, device=Xb.device, dtype=torch.int64)
+    L = _lib.lib()
+    ws_bytes = L.msm_smart_seeds_workspace_bytes(B, n, int(num_seeds))
+    ws = torch.empty(ws_bytes, device=Xb.device, dtype=torch.uint8)
+    rc = L.msm_select_smart_seeds(Xb.data_ptr(), first.data_ptr(), seeds.data_ptr(), selected.data_ptr(), B, n, d,
+                                  int(num_seeds), ws.data_ptr(), ws_bytes, _stream())
+    check(rc, "msm_select_smart_seeds")
+    return (seeds[0], selected[0]) if squeeze else (seeds, selected)
+
+
+def seed_connected_components(Z, epsilon):
+    """connected_components over converged seeds, batched: Z [B,m,d] (or [m,d]) ->
+    (seed_labels int64 [B,m], num_labels int32 [B]) on the device."""
+    Zb, squeeze = _points(Z, "Z")
+    B, m, d = Zb.shape
+    labels = torch.empty(B, m, device=Zb.device, dtype=torch.int64)
+    num = torch.empty(B, device=Zb.device, dtype=torch.int32)
+    rc = _lib.lib().msm_seed_connected_components(Zb.data_ptr(), labels.data_ptr(), num.data_ptr(), B, m, d,
+                                                  float(epsilon), _stream())
+    check(rc, "msm_seed_connected_components")
+    return (labels[0], num[0]) if squeeze else (labels, num)
+
+
+def assign_clusters(X, Z, seed_labels, num_labels):
+    """Label every point by its closest seed and make the most populous cluster label 0
+    (mean_shift.py:207-227), batched: -> labels int64 [B,n]."""
+    Xb, squeeze = _points(X)
+    Zb, _ = _points(Z, "Z")
+    B, n, d = Xb.shape
+    m = Zb.shape[1]
+    if Zb.shape[0] != B or Zb.shape[2] != d:
+        raise ValueError(f"X {tuple(X.shape)} / Z {tuple(Z.shape)} mismatch")
+    if d not in (16, 32, 64, 128):
+        raise ValueError(f"embedding dim {d} not supported (16, 32, 64, 128)")
+    sl = seed_labels.to(device=Xb.device, dtype=torch.int64).reshape(B, m).contiguous()
+    nl = num_labels.to(device=Xb.device, dtype=torch.int32).reshape(B).contiguous()
+    labels = torch.empty(B, n, device=Xb.device, dtype=torch.int64)
+    L = _lib.lib()
+    ws_bytes = L.msm_assign_clusters_workspace_bytes(B, m)
+    ws = torch.empty(ws_bytes, device=Xb.device, dtype=torch.uint8)
+    rc = L.msm_assign_clusters(Xb.data_ptr(), Zb.data_ptr(), sl.data_ptr(), nl.data_ptr(), labels.data_ptr(), B, n, m,
+                               d, ws.data_ptr(), ws_bytes, _stream())
+    check(rc, "msm_assign_clusters")
+    return labels[0] if squeeze else labels
+
+
 # ----------------------------------------------------------------------------------------------
 # launch accounting / per-op device timing (used by bench.py; off by default)
 # ----------------------------------------------------------------------------------------------
@@ -712,5 +778,13 @@ linear_fused = _instrument("linear", 1, _work_linear_fused)(linear_fused)
 ms_deform_attn_forward = _instrument("ms_deform_attn_forward", 1, _work_msda)(ms_deform_attn_forward)
 ms_deform_attn_fused_forward = _instrument("ms_deform_attn_forward", 1, _work_msda_fused)(ms_deform_attn_fused_forward)
 ms_deform_attn_backward = _instrument("ms_deform_attn_backward", 1)(ms_deform_attn_backward)
+select_smart_seeds = _instrument("select_smart_seeds", 1, lambda X, num_seeds, first_index: (
+    f"B{X.shape[0] if X.dim() == 3 else 1} n{X.shape[-2]} m{num_seeds} d{X.shape[-1]}",
+    (4.0 * X.shape[-1] + 8.0) * (X.numel() // X.shape[-1]) * (num_seeds - 1), 2.0 * X.numel() * (num_seeds - 1)))(
+    select_smart_seeds)
+seed_connected_components = _instrument("seed_connected_components", 1)(seed_connected_components)
+assign_clusters = _instrument("assign_clusters", 2, lambda X, Z, seed_labels, num_labels: (
+    f"B{X.shape[0] if X.dim() == 3 else 1} n{X.shape[-2]} m{Z.shape[-2]} d{X.shape[-1]}",
+    (4.0 * X.shape[-1] + 8.0) * (X.numel() // X.shape[-1]), 2.0 * X.numel() * Z.shape[-2]))(assign_clusters)
 mean_shift_hill_climb = _instrument("mean_shift_hill_climb", lambda X, Z, kappa, max_iters=10: 2 * int(max_iters),
                                     _work_ms)(mean_shift_hill_climb)
