@@ -35,3 +35,25 @@ for b in range(B):
           "label hist:", torch.bincount(labels[b].cpu()).tolist())
     ref_labels, _ = oms.mean_shift_smart_init(X[b], 20.0, m, 10, first[b])
     print(b, "label agreement with the oracle pipeline:", float((labels[b].cpu() == ref_labels).float().mean()))
+
+if len(sys.argv) > 3 and sys.argv[3] == "time":
+    Bt, nt, mt = 16, 307200, 100
+    Xt = F.normalize(torch.randn(Bt, nt, d, device="cuda"), dim=2)
+    ft = torch.arange(Bt, device="cuda") * 1000
+    for variant in ("seeds", "assign"):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        Zt = Xt[:, :mt].contiguous()
+        lt = torch.arange(mt, device="cuda").repeat(Bt, 1)
+        nl = torch.full((Bt,), mt, device="cuda", dtype=torch.int32)
+        fn = (lambda: ops.select_smart_seeds(Xt, mt, ft)) if variant == "seeds" else (lambda: ops.assign_clusters(Xt, Zt, lt, nl))
+        fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        by = (4.0 * d + 8) * Bt * nt * ((mt - 1) if variant == "seeds" else 1)
+        print(f"{variant}: {ms:.2f} ms  {by / ms / 1e6:.0f} GB/s algorithmic (MSM_SEEDS_VARIANT={os.environ.get('MSM_SEEDS_VARIANT', '1')})",
+              flush=True)

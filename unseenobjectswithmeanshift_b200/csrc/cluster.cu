@@ -14,7 +14,10 @@
 // barrier. HBM bound for a batch (B n d 4 bytes per pass); for one image X (78.6 MB at 480x640x64) is L2 resident.
 #include <cooperative_groups.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -109,6 +112,146 @@ __global__ void __launch_bounds__(kSeedThreads, 2)
     grid.sync();
     const unsigned long long win = __ldcg(kb + i);
     j = (long long)(0xffffffffu - (uint32_t)(win & 0xffffffffull));
+  }
+}
+
+// Same passes with X streamed through a shared-memory ring by bulk async copies (TMA, 1-D): a producer thread keeps
+// kRingStages x 32 KB per CTA in flight regardless of what the consumer warps are doing, and - X being constant - runs
+// ahead into the next pass while the consumers are still reducing / waiting at the barrier of the current one. The
+// barrier is per image (the CTAs of other images never wait for this one) and spans the consumer warps only.
+constexpr int kRingWarps = 8;
+constexpr int kRingThreads = (kRingWarps + 1) * 32;
+constexpr int kRingStages = 3;
+constexpr int kChunkFloats = 8192;
+
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   tc::smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(tc::smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void consumer_bar() {
+  asm volatile("bar.sync 1, %0;" ::"n"(kRingWarps * 32) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kRingThreads, 2)
+    smart_seeds_ring_kernel(const float* __restrict__ X, const int64_t* __restrict__ first_index,
+                            float* __restrict__ seeds, int64_t* __restrict__ selected, float* __restrict__ nearest,
+                            unsigned long long* __restrict__ keys, uint32_t* __restrict__ arrivals, int n,
+                            int num_seeds, int rows_per_cta) {
+  constexpr int LPR = D / 4;                 // lanes per point
+  constexpr int RPW = 32 / LPR;              // lane groups per warp
+  constexpr int CR = kChunkFloats / D;       // points per chunk (stage)
+  constexpr int WR = CR / kRingWarps;        // points per warp per chunk
+  constexpr int STEPS = WR / RPW;            // points per lane group per chunk
+  static_assert(STEPS <= LPR, "every point of a chunk needs an owner lane in its group");
+  extern __shared__ __align__(128) unsigned char ring_smem[];
+  float* stages = reinterpret_cast<float*>(ring_smem);
+  __shared__ uint64_t full[kRingStages], empty[kRingStages];
+  __shared__ unsigned long long warp_best[kRingWarps];
+  __shared__ long long s_next;
+  const int b = blockIdx.y;
+  const float* Xb = X + (size_t)b * n * D;
+  float* nb = nearest + (size_t)b * n;
+  unsigned long long* kb = keys + (size_t)b * num_seeds;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row0 = min((long long)n, (long long)blockIdx.x * rows_per_cta);
+  const int row1 = min((long long)n, (long long)row0 + rows_per_cta);
+  const int chunks = (row1 - row0 + CR - 1) / CR;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kRingStages; ++s) {
+      tc::mbar_init(&full[s], 1);
+      tc::mbar_init(&empty[s], kRingWarps);
+    }
+    tc::fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == kRingWarps) {  // producer
+    if (lane == 0) {
+      tc::Ring r;
+      for (int pass = 0; pass + 1 < num_seeds; ++pass)
+        for (int c = 0; c < chunks; ++c) {
+          tc::mbar_wait(&empty[r.stage], r.phase ^ 1);
+          const int c0 = row0 + c * CR;
+          const uint32_t bytes = (uint32_t)min(CR, row1 - c0) * D * sizeof(float);
+          tc::mbar_arrive_expect_tx(&full[r.stage], bytes);
+          bulk_load(stages + (size_t)r.stage * kChunkFloats, Xb + (size_t)c0 * D, bytes, &full[r.stage]);
+          r.advance(kRingStages);
+        }
+    }
+    return;
+  }
+
+  const int sub = lane % LPR, grp = lane / LPR;
+  long long j = first_index[b];
+  j = j < 0 ? 0 : (j >= n ? n - 1 : j);
+  tc::Ring r;
+  for (int i = 0; i < num_seeds; ++i) {
+    const float4 s = __ldg(reinterpret_cast<const float4*>(Xb + (size_t)j * D) + sub);
+    if (blockIdx.x == 0 && threadIdx.x < LPR) {
+      reinterpret_cast<float4*>(seeds + ((size_t)b * num_seeds + i) * D)[sub] = s;
+      if (threadIdx.x == 0) selected[(size_t)b * num_seeds + i] = j;
+    }
+    if (i == num_seeds - 1) break;
+
+    unsigned long long best = 0;
+    for (int c = 0; c < chunks; ++c) {
+      // lane `sub` of group `grp` owns point grp*STEPS + sub of this warp's WR points: it loads / stores the running
+      // distance (coalesced, and issued before the wait) and carries the arg-max candidate
+      const int local = warp * WR + grp * STEPS;
+      const int mine = row0 + c * CR + local + sub;
+      const bool owner = sub < STEPS && mine < row1;
+      const float old = (owner && i > 0) ? nb[mine] : __int_as_float(0x7f800000);
+      tc::mbar_wait(&full[r.stage], r.phase);
+      const float* xs = stages + (size_t)r.stage * kChunkFloats + (size_t)local * D + sub * 4;
+      float mydot = 0.f;
+#pragma unroll
+      for (int st = 0; st < STEPS; ++st) {
+        const float4 x = *reinterpret_cast<const float4*>(xs + st * D);
+        float dot = x.x * s.x;
+        dot = fmaf(x.y, s.y, dot);
+        dot = fmaf(x.z, s.z, dot);
+        dot = fmaf(x.w, s.w, dot);
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        if (sub == st) mydot = dot;  // after the butterfly every lane of the group holds the sum
+      }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&empty[r.stage]);
+      r.advance(kRingStages);
+      if (owner) {
+        const float dist = fminf(0.5f * (1.0f - mydot), old);
+        nb[mine] = dist;
+        const unsigned long long key =
+            ((unsigned long long)ordered_bits(dist) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)mine);
+        best = key > best ? key : best;
+      }
+    }
+    best = warp_max_u64(best);
+    if (lane == 0) warp_best[warp] = best;
+    consumer_bar();
+    if (threadIdx.x == 0) {
+      unsigned long long v = 0;
+#pragma unroll
+      for (int w = 0; w < kRingWarps; ++w) v = warp_best[w] > v ? warp_best[w] : v;
+      if (v != 0ull) atomicMax(kb + i, v);
+      __threadfence();
+      atomicAdd(arrivals + b, 1u);
+      const uint32_t target = (uint32_t)(i + 1) * gridDim.x;
+      while (ld_acquire_u32(arrivals + b) < target) {
+      }
+      const unsigned long long win = __ldcg(kb + i);
+      s_next = (long long)(0xffffffffu - (uint32_t)(win & 0xffffffffull));
+    }
+    consumer_bar();
+    j = s_next;
   }
 }
 
@@ -257,31 +400,61 @@ __global__ void relabel_kernel(int64_t* __restrict__ labels, const int32_t* __re
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+int seeds_variant() {
+  static const int v = [] {
+    const char* e = getenv("MSM_SEEDS_VARIANT");  // 0: register-pipelined loads + grid.sync; 1 (default): TMA ring
+    return e ? atoi(e) : 1;
+  }();
+  return v;
+}
+
 template <int D>
 int launch_seeds(const float* X, const int64_t* first_index, float* seeds, int64_t* selected, float* nearest,
-                 unsigned long long* keys, int B, int n, int num_seeds, cudaStream_t st) {
+                 unsigned long long* keys, uint32_t* arrivals, int B, int n, int num_seeds, cudaStream_t st) {
+  constexpr bool kHasRing = D >= 32;
+  const bool ring = kHasRing && seeds_variant() != 0;
+  constexpr size_t ring_smem = (size_t)kRingStages * kChunkFloats * sizeof(float);
   int per_sm = 0;
-  MSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smart_seeds_kernel<D>, kSeedThreads, 0));
+  if constexpr (kHasRing) {
+    if (ring) {
+      MSM_CUDA(cudaFuncSetAttribute(smart_seeds_ring_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)ring_smem));
+      MSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smart_seeds_ring_kernel<D>, kRingThreads,
+                                                             ring_smem));
+    }
+  }
+  if (!ring) MSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smart_seeds_kernel<D>, kSeedThreads, 0));
   const int resident = per_sm * num_sms();
   if (resident < 1) {
     set_error("smart_seeds_kernel: no co-resident CTAs");
     return MSM_E_UNSUPPORTED;
   }
-  MSM_CUDA(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)B * num_seeds, st));
-  for (int b0 = 0; b0 < B; b0 += resident) {  // images of one launch must be co-resident (grid barrier)
+  // keys and arrival counters are adjacent in the workspace: one memset
+  MSM_CUDA(cudaMemsetAsync(keys, 0, reinterpret_cast<char*>(arrivals + B) - reinterpret_cast<char*>(keys), st));
+  const int chunk_rows = ring ? kChunkFloats / D : 32;
+  for (int b0 = 0; b0 < B; b0 += resident) {  // the CTAs of one launch must be co-resident (they wait for each other)
     const int nb = min(B - b0, resident);
-    int G = resident / nb;
-    G = max(1, min(G, (n + 31) / 32));
+    int G = max(1, min(resident / nb, (n + chunk_rows - 1) / chunk_rows));
     int rows_per_cta = (n + G - 1) / G;
+    rows_per_cta = (rows_per_cta + chunk_rows - 1) / chunk_rows * chunk_rows;
     const float* Xp = X + (size_t)b0 * n * D;
     const int64_t* fp = first_index + b0;
     float* sp = seeds + (size_t)b0 * num_seeds * D;
     int64_t* ip = selected + (size_t)b0 * num_seeds;
     float* np_ = nearest + (size_t)b0 * n;
     unsigned long long* kp = keys + (size_t)b0 * num_seeds;
-    void* args[] = {&Xp, &fp, &sp, &ip, &np_, &kp, &n, &num_seeds, &rows_per_cta};
-    MSM_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(smart_seeds_kernel<D>), dim3(G, nb), dim3(kSeedThreads),
-                                         args, 0, st));
+    uint32_t* ap = arrivals + b0;
+    if (ring) {
+      if constexpr (kHasRing) {
+        void* args[] = {&Xp, &fp, &sp, &ip, &np_, &kp, &ap, &n, &num_seeds, &rows_per_cta};
+        MSM_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(smart_seeds_ring_kernel<D>), dim3(G, nb),
+                                             dim3(kRingThreads), args, ring_smem, st));
+      }
+    } else {
+      void* args[] = {&Xp, &fp, &sp, &ip, &np_, &kp, &n, &num_seeds, &rows_per_cta};
+      MSM_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(smart_seeds_kernel<D>), dim3(G, nb),
+                                           dim3(kSeedThreads), args, 0, st));
+    }
   }
   return 0;
 }
@@ -310,7 +483,8 @@ using namespace msm;
 
 extern "C" size_t msm_smart_seeds_workspace_bytes(int B, int n, int num_seeds) {
   if (B <= 0 || n <= 0 || num_seeds <= 0) return 0;
-  return align256(sizeof(float) * (size_t)B * n) + align256(sizeof(unsigned long long) * (size_t)B * num_seeds);
+  return align256(sizeof(float) * (size_t)B * n) +
+         align256(sizeof(unsigned long long) * (size_t)B * num_seeds + sizeof(uint32_t) * (size_t)B);
 }
 
 extern "C" int msm_select_smart_seeds(const float* X, const int64_t* first_index, float* seeds, int64_t* selected, int B,
@@ -324,11 +498,12 @@ extern "C" int msm_select_smart_seeds(const float* X, const int64_t* first_index
   float* nearest = static_cast<float*>(workspace);
   unsigned long long* keys =
       reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + align256(sizeof(float) * (size_t)B * n));
+  uint32_t* arrivals = reinterpret_cast<uint32_t*>(keys + (size_t)B * num_seeds);  // per-image barrier counters
   switch (d) {
-    case 16: return launch_seeds<16>(X, first_index, seeds, selected, nearest, keys, B, n, num_seeds, st);
-    case 32: return launch_seeds<32>(X, first_index, seeds, selected, nearest, keys, B, n, num_seeds, st);
-    case 64: return launch_seeds<64>(X, first_index, seeds, selected, nearest, keys, B, n, num_seeds, st);
-    default: return launch_seeds<128>(X, first_index, seeds, selected, nearest, keys, B, n, num_seeds, st);
+    case 16: return launch_seeds<16>(X, first_index, seeds, selected, nearest, keys, arrivals, B, n, num_seeds, st);
+    case 32: return launch_seeds<32>(X, first_index, seeds, selected, nearest, keys, arrivals, B, n, num_seeds, st);
+    case 64: return launch_seeds<64>(X, first_index, seeds, selected, nearest, keys, arrivals, B, n, num_seeds, st);
+    default: return launch_seeds<128>(X, first_index, seeds, selected, nearest, keys, arrivals, B, n, num_seeds, st);
   }
 }
 
