@@ -246,6 +246,29 @@ int msm_assign_clusters(const float* X, const float* Z, const int64_t* seed_labe
                         int64_t* labels, int B, int n, int m, int d,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Eval-mode tail: mask upsample + instance_inference, for the kept queries only.
+ * Replaces F.interpolate(pred_masks, image size, "bilinear", align_corners=False) followed per image by
+ *   instance_inference(mask_cls, mask_pred): MSMFormer/meanshiftformer/pretrained_meanshiftformer_model.py:337-343,
+ *   461-497 (= meanshiftformer_model.py:289-295, 414-450), with panoptic_on = False.
+ * msm_instance_topk: scores = softmax(logits)[:, :-1]; the T best of the Q*(K1-1) scores per image.
+ *   logits [B][Q][K1]; topk_query / topk_class int64 [B][T], topk_score [B][T]; order: descending score
+ *   (the reference's topk(sorted=False) promises none).
+ * msm_instance_masks: for kept query t of image b, the low-resolution logits mask_logits [B][Q][h][w] resampled to
+ *   H x W:  pred_masks [B][T][H][W] = (m > 0) as 0/1 floats; boxes [B][T][4] = (x0, y0, x1+1, y1+1) of the
+ *   foreground, zeros when empty (detectron2 BitMasks.get_bounding_boxes); scores [B][T] =
+ *   topk_score * sum(sigmoid(m) * mask) / (sum(mask) + 1e-6).
+ * ---------------------------------------------------------------------------------------------- */
+int msm_instance_topk(const float* logits, int64_t* topk_query, int64_t* topk_class, float* topk_score,
+                      int B, int Q, int K1, int T, void* stream);
+
+size_t msm_instance_masks_workspace_bytes(int B, int T, int H);
+
+int msm_instance_masks(const float* mask_logits, const int64_t* topk_query, const float* topk_score,
+                       float* pred_masks, float* boxes, float* scores,
+                       int B, int Q, int h, int w, int T, int H, int W,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

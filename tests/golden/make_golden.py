@@ -306,6 +306,59 @@ def gen_mean_shift_d64():
          Z=Z, seed_labels=seed_labels, smart_init_labels=labels)
 
 
+def gen_instance_inference():
+    """Runs the reference's own instance_inference (pretrained_meanshiftformer_model.py:461-497): the method is cut
+    out of the file by ast (the module itself needs detectron2 + the UCN networks to import) and executed with the
+    three detectron2 structures it touches stubbed: Instances (attribute bag), Boxes (tensor holder), BitMasks
+    (get_bounding_boxes restated from detectron2 v0.6 in oracle/instance_inference.py)."""
+    import ast
+    import types
+    from oracle import instance_inference as oii
+    path = os.path.join(ref_shim.REF_PKG, "pretrained_meanshiftformer_model.py")
+    tree = ast.parse(open(path).read())
+    fn = next(n for c in tree.body if isinstance(c, ast.ClassDef) for n in c.body
+              if isinstance(n, ast.FunctionDef) and n.name == "instance_inference")
+
+    class Instances:
+        def __init__(self, image_size):
+            self.image_size = image_size
+
+    class Boxes:
+        def __init__(self, t):
+            self.tensor = t
+
+    class BitMasks:
+        def __init__(self, t):
+            self.tensor = t
+
+        def get_bounding_boxes(self):
+            return Boxes(oii.get_bounding_boxes(self.tensor))
+
+    ns = {"torch": torch, "F": F, "Instances": Instances, "Boxes": Boxes, "BitMasks": BitMasks}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    torch.manual_seed(21)
+    B, Q, K, h, w, H, W, T = 2, 24, 2, 30, 40, 120, 160, 7
+    logits = torch.randn(B, Q, K + 1) * 2
+    yy, xx = torch.meshgrid(torch.arange(h).float(), torch.arange(w).float(), indexing="ij")
+    masks = torch.empty(B, Q, h, w)
+    for b in range(B):
+        for q in range(Q):
+            cy, cx, r = torch.rand(1) * h, torch.rand(1) * w, 2 + torch.rand(1) * 8
+            masks[b, q] = 4 * (1 - ((yy - cy) ** 2 + (xx - cx) ** 2).sqrt() / r) + 0.5 * torch.randn(h, w)
+    masks[1, :3] = -3.0 - torch.rand(3, h, w)      # empty masks: zero box, zero score
+    logits[1, :3, 0] += 6                           # ... that are certainly kept
+    up = F.interpolate(masks, size=(H, W), mode="bilinear", align_corners=False)   # :337-343
+    out = {}
+    for b in range(B):
+        self_ = types.SimpleNamespace(sem_seg_head=types.SimpleNamespace(num_classes=K), num_queries=Q,
+                                      test_topk_per_image=T, panoptic_on=False, device=torch.device("cpu"))
+        r = ns["instance_inference"](self_, logits[b], up[b])
+        out.update({f"masks_{b}": r.pred_masks.to(torch.uint8), f"boxes_{b}": r.pred_boxes.tensor,
+                    f"scores_{b}": r.scores, f"classes_{b}": r.pred_classes})
+    save("instance_inference", pred_logits=logits, pred_masks=masks, topk=np.int64(T), height=np.int64(H),
+         width=np.int64(W), **out)
+
+
 if __name__ == "__main__":
     gen_hypersphere_attention()
     gen_meanshift_attention()
@@ -319,3 +372,4 @@ if __name__ == "__main__":
     gen_head_r50style()
     gen_mean_shift()
     gen_mean_shift_d64()
+    gen_instance_inference()

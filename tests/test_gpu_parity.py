@@ -12,6 +12,7 @@ import torch.nn.functional as F
 import torch.nn.functional as F_
 
 from oracle import decoder as odec
+from oracle import instance_inference as oii
 from oracle import mean_shift as oms
 from oracle import pixel_decoder as opd
 from oracle import vmf_attention as ovmf
@@ -521,6 +522,78 @@ def test_clusterer_config4_size(msm):
         assert int(got.min()) == 0 and int(got.max()) < len(torch.unique(want_cc))
         count = torch.bincount(got)
         assert int(count.argmax()) == 0
+
+
+# ----------------------------------------------------------------------------- eval tail
+def _match_rows(got, b, want, K, logit_flip_tol=2e-6, up=None):
+    """got: batched device result; want: oracle fields of image b. Rows matched by (query, class)."""
+    gq = (got["query_index"][b] * K + got["pred_classes"][b]).cpu()
+    wq = want["query_index"] * K + want["pred_classes"]
+    assert torch.equal(gq.sort()[0], wq.sort()[0])                     # same kept set
+    go, wo = torch.argsort(gq), torch.argsort(wq)
+    gm, wm = got["pred_masks"][b].cpu()[go], want["pred_masks"][wo]
+    diff = gm != wm
+    if diff.any():   # a pixel may flip only where the upsampled logit is zero to fp32 rounding
+        assert up is not None and up[want["query_index"][wo]][diff].abs().max().item() < logit_flip_tol
+    else:
+        assert torch.equal(got["pred_boxes"][b].cpu()[go], want["pred_boxes"][wo])
+    torch.testing.assert_close(got["scores"][b].cpu()[go], want["scores"][wo], rtol=2e-5, atol=1e-7)
+    return go, wo
+
+
+def test_instance_inference_golden(msm, golden):
+    """mask upsample + instance_inference (pretrained_meanshiftformer_model.py:337-343, 461-497) against the
+    reference's own method; incl. empty masks (zero box, zero score)."""
+    from unseenobjectswithmeanshift_b200.meanshiftformer import instance_inference as ii
+    g, _ = golden("instance_inference")
+    T, H, W = int(g["topk"]), int(g["height"]), int(g["width"])
+    with torch.no_grad():
+        r = ii.instance_inference_batched(g["pred_logits"].cuda(), g["pred_masks"].cuda(), (H, W), T)
+    assert r["pred_masks"].shape == (2, T, H, W) and r["pred_masks"].dtype == torch.float32
+    assert r["pred_classes"].dtype == torch.int64
+    for b in range(2):
+        mine = torch.argsort(r["scores"][b].cpu(), descending=True, stable=True)
+        ref = torch.argsort(g[f"scores_{b}"], descending=True, stable=True)
+        torch.testing.assert_close(r["scores"][b].cpu()[mine], g[f"scores_{b}"][ref], rtol=2e-5, atol=1e-7)
+        assert torch.equal(r["pred_classes"][b].cpu()[mine], g[f"classes_{b}"][ref])
+        assert torch.equal(r["pred_boxes"][b].cpu()[mine], g[f"boxes_{b}"][ref])
+        assert torch.equal(r["pred_masks"][b].cpu()[mine].to(torch.uint8), g[f"masks_{b}"][ref])
+        # rows come out by descending class score
+        cls_score = torch.softmax(g["pred_logits"][b], -1)[:, :-1]
+        picked = cls_score[r["query_index"][b].cpu(), r["pred_classes"][b].cpu()]
+        assert bool((picked[:-1] >= picked[1:]).all())
+    one = ii.instance_inference(g["pred_logits"][1].cuda(), g["pred_masks"][1].cuda(), (H, W), T)
+    assert torch.equal(one["pred_masks"], r["pred_masks"][1]) and torch.equal(one["scores"], r["scores"][1])
+
+
+@pytest.mark.parametrize("B,Q,K,h,w,H,W,T", [(8, 100, 1, 120, 160, 480, 640, 20),   # config #2 tail
+                                             (2, 100, 2, 56, 56, 224, 224, 100),    # crop stage, keep everything
+                                             (3, 17, 3, 25, 31, 97, 123, 5),        # ragged, W % 4 != 0
+                                             (1, 9, 1, 48, 64, 48, 64, 9)])         # identity resample
+def test_instance_inference_vs_oracle(msm, B, Q, K, h, w, H, W, T):
+    from unseenobjectswithmeanshift_b200.meanshiftformer import instance_inference as ii
+    g = torch.Generator().manual_seed(B * 1000 + Q)
+    logits = 2 * torch.randn(B, Q, K + 1, generator=g)
+    masks = F.interpolate(3 * torch.randn(B, Q, max(2, h // 8), max(2, w // 8), generator=g), size=(h, w),
+                          mode="bicubic") + 0.3 * torch.randn(B, Q, h, w, generator=g)
+    masks[0, 0] = -1.0                                               # an empty mask
+    with torch.no_grad():
+        r = ii.instance_inference_batched(logits.cuda(), masks.cuda(), (H, W), T)
+        again = ii.instance_inference_batched(logits.cuda(), masks.cuda(), (H, W), T)
+    for k in r:
+        assert torch.equal(r[k], again[k])                            # deterministic reductions
+    up = F.interpolate(masks, size=(H, W), mode="bilinear", align_corners=False)
+    want = oii.inference_tail(logits, masks, (H, W), T)
+    for b in range(B):
+        _match_rows(r, b, want[b], K, up=up[b])
+    # properties that hold at any size
+    pm = r["pred_masks"]
+    assert bool(((pm == 0) | (pm == 1)).all())
+    area = pm.flatten(2).sum(2)
+    bx = r["pred_boxes"]
+    assert bool((((bx[..., 2] - bx[..., 0]) * (bx[..., 3] - bx[..., 1])) >= area).all())   # box covers the mask
+    assert bool((r["scores"] >= 0).all()) and bool((r["scores"] <= 1).all())
+    assert bool((r["scores"][area == 0] == 0).all())
 
 
 # ----------------------------------------------------------------------------- dense layers (tcgen05 linear kernel)

@@ -164,3 +164,19 @@ def test_mean_shift_clusterer_d64(golden):
     labels, idx = oms.mean_shift_smart_init(X, 20, 100, 10, first)
     assert torch.equal(labels, g["smart_init_labels"])
     assert int(np.bincount(labels.numpy()).argmax()) == 0
+
+
+def test_instance_inference_tail(golden):
+    """mask upsample + instance_inference: oracle == the reference's own method (rows matched by score order;
+    the three empty masks of image 1 tie at score 0 and are interchangeable)."""
+    from oracle import instance_inference as oii
+    g, _ = golden("instance_inference")
+    T, H, W = int(g["topk"]), int(g["height"]), int(g["width"])
+    res = oii.inference_tail(g["pred_logits"], g["pred_masks"], (H, W), T)
+    for b, r in enumerate(res):
+        mine = torch.argsort(r["scores"], descending=True, stable=True)
+        ref = torch.argsort(g[f"scores_{b}"], descending=True, stable=True)
+        torch.testing.assert_close(r["scores"][mine], g[f"scores_{b}"][ref], rtol=1e-6, atol=1e-7)
+        assert torch.equal(r["pred_classes"][mine], g[f"classes_{b}"][ref])
+        assert torch.equal(r["pred_boxes"][mine], g[f"boxes_{b}"][ref])
+        assert torch.equal(r["pred_masks"][mine].to(torch.uint8), g[f"masks_{b}"][ref])

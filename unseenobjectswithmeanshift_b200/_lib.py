@@ -45,6 +45,9 @@ SIGNATURES = {
     "msm_seed_connected_components": (_I, [_P, _P, _P, _I, _I, _I, _F, _P]),
     "msm_assign_clusters_workspace_bytes": (_Z, [_I, _I]),
     "msm_assign_clusters": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),
+    "msm_instance_topk": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "msm_instance_masks_workspace_bytes": (_Z, [_I, _I, _I]),
+    "msm_instance_masks": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _Z, _P]),
 }
 
 

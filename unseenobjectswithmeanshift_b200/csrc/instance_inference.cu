@@ -1,0 +1,227 @@
+// Eval-mode tail of the segmentation model: the bilinear upsample of the predicted masks
+// (pretrained_meanshiftformer_model.py:337-343 = meanshiftformer_model.py:289-295) fused with instance_inference
+// (:461-497 / :414-450). The reference upsamples all Q = 100 masks of every image to full resolution (983 MB at
+// B = 8, 480x640), gathers the top-k, and then makes five more full-resolution passes (> 0, float, BitMasks boxes,
+// sigmoid, product + sums). Here the top-k is taken first on the [Q, K] class scores and ONE kernel produces, for
+// the kept queries only, the binary masks, the boxes and the mask scores: HBM traffic = the B*T*H*W*4 bytes of
+// pred_masks that the caller asked for; the low-resolution logits (77 KB per mask) stay in L1/L2.
+#include "common.cuh"
+
+namespace msm {
+namespace {
+
+constexpr int kTopkThreads = 256;
+constexpr int kMaskThreads = 256;
+constexpr int kRowsPerCta = 8;
+
+// softmax over the K+1 classes, drop the last ("no object") class, keep the T best of the Q*K scores.
+// Output order: descending score, ties -> lower flattened index (torch.topk(sorted=False) promises no order).
+__global__ void __launch_bounds__(kTopkThreads)
+    instance_topk_kernel(const float* __restrict__ logits, int64_t* __restrict__ topk_query,
+                         int64_t* __restrict__ topk_class, float* __restrict__ topk_score, int Q, int K1, int T) {
+  extern __shared__ float sc[];  // [Q * K]
+  const int b = blockIdx.x, K = K1 - 1, N = Q * K;
+  const float* lb = logits + (size_t)b * Q * K1;
+  for (int q = threadIdx.x; q < Q; q += kTopkThreads) {
+    const float* row = lb + (size_t)q * K1;
+    float mx = row[0];
+    for (int c = 1; c < K1; ++c) mx = fmaxf(mx, row[c]);
+    float sum = 0.f;
+    for (int c = 0; c < K1; ++c) sum += expf(row[c] - mx);
+    for (int c = 0; c < K; ++c) sc[q * K + c] = expf(row[c] - mx) / sum;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < N; e += kTopkThreads) {
+    const float mine = sc[e];
+    int rank = 0;
+    for (int f = 0; f < N; ++f) {
+      const float o = sc[f];
+      rank += (o > mine || (o == mine && f < e)) ? 1 : 0;
+    }
+    if (rank < T) {
+      topk_query[(size_t)b * T + rank] = e / K;
+      topk_class[(size_t)b * T + rank] = e % K;
+      topk_score[(size_t)b * T + rank] = mine;
+    }
+  }
+}
+
+struct Partial {
+  float num;                   // sum of sigmoid(mask) over the foreground pixels
+  int den;                     // number of foreground pixels
+  int x0, y0, x1, y1;          // inclusive extent of the foreground, x0 > x1 = empty
+};
+
+// grid (ceil(H / kRowsPerCta), T, B): bilinear resample (align_corners=False, PyTorch's source-index rule) of the
+// kept query's low-resolution logits, threshold at 0, per-CTA partial reductions (summed in a fixed order by
+// instance_finalize_kernel: results are run-to-run deterministic).
+__global__ void __launch_bounds__(kMaskThreads)
+    instance_masks_kernel(const float* __restrict__ mask_logits, const int64_t* __restrict__ topk_query,
+                          float* __restrict__ pred_masks, Partial* __restrict__ partials, int Q, int h, int w, int T,
+                          int H, int W) {
+  const int tile = blockIdx.x, t = blockIdx.y, b = blockIdx.z;
+  const int q = (int)topk_query[(size_t)b * T + t];
+  const float* mp = mask_logits + ((size_t)b * Q + q) * h * w;
+  float* op = pred_masks + ((size_t)b * T + t) * H * W;
+  const bool identity = (h == H) && (w == W);
+  const float sh = (float)h / (float)H, sw = (float)w / (float)W;
+  const int ya = tile * kRowsPerCta, yb = min(H, ya + kRowsPerCta);
+  float num = 0.f;
+  int den = 0, x0 = W, y0 = H, x1 = -1, y1 = -1;
+  const int Wq = (W + 3) >> 2;  // groups of 4 consecutive pixels of a row
+  const bool vec = (W & 3) == 0;
+  for (int g = threadIdx.x; g < (yb - ya) * Wq; g += kMaskThreads) {
+    const int y = ya + g / Wq, xg = (g % Wq) * 4;
+    float sy = sh * ((float)y + 0.5f) - 0.5f;
+    sy = sy < 0.f ? 0.f : sy;
+    const int yy = (int)sy;
+    const int yp = (yy < h - 1) ? 1 : 0;
+    const float ly = sy - (float)yy, hy = 1.f - ly;
+    float m[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int x = xg + k;
+      m[k] = 0.f;
+      if (x < W) {
+        float val;
+        if (identity) {
+          val = __ldg(mp + (size_t)y * w + x);
+        } else {
+          float sx = sw * ((float)x + 0.5f) - 0.5f;
+          sx = sx < 0.f ? 0.f : sx;
+          const int xx = (int)sx;
+          const int xp = (xx < w - 1) ? 1 : 0;
+          const float lx = sx - (float)xx, hx = 1.f - lx;
+          const float* p = mp + (size_t)yy * w + xx;
+          const float v00 = __ldg(p), v01 = __ldg(p + xp), v10 = __ldg(p + yp * w), v11 = __ldg(p + yp * w + xp);
+          val = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+        }
+        if (val > 0.f) {
+          m[k] = 1.f;
+          num += 1.f / (1.f + expf(-val));
+          den += 1;
+          x0 = min(x0, x);
+          x1 = max(x1, x);
+          y0 = min(y0, y);
+          y1 = max(y1, y);
+        }
+      }
+    }
+    float* o = op + (size_t)y * W + xg;
+    if (vec) {
+      *reinterpret_cast<float4*>(o) = make_float4(m[0], m[1], m[2], m[3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (xg + k < W) o[k] = m[k];
+    }
+  }
+  // block reduction
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    num += __shfl_xor_sync(0xffffffffu, num, o);
+    den += __shfl_xor_sync(0xffffffffu, den, o);
+    x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o));
+    y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+    x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+    y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+  }
+  __shared__ Partial wp[kMaskThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) wp[warp] = Partial{num, den, x0, y0, x1, y1};
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Partial r = wp[0];
+    for (int i = 1; i < kMaskThreads / 32; ++i) {
+      r.num += wp[i].num;
+      r.den += wp[i].den;
+      r.x0 = min(r.x0, wp[i].x0);
+      r.y0 = min(r.y0, wp[i].y0);
+      r.x1 = max(r.x1, wp[i].x1);
+      r.y1 = max(r.y1, wp[i].y1);
+    }
+    partials[((size_t)b * T + t) * gridDim.x + tile] = r;
+  }
+}
+
+// one warp per kept query: boxes as BitMasks.get_bounding_boxes (x0, y0, x1 + 1, y1 + 1; zeros for an empty mask),
+// score = class score * sum(sigmoid * mask) / (sum(mask) + 1e-6)  (:493-494)
+__global__ void instance_finalize_kernel(const Partial* __restrict__ partials, const float* __restrict__ cls_score,
+                                         float* __restrict__ boxes, float* __restrict__ scores, int tiles, int total) {
+  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (item >= total) return;
+  const int lane = threadIdx.x & 31;
+  const Partial* p = partials + (size_t)item * tiles;
+  float num = 0.f;
+  int den = 0, x0 = 1 << 30, y0 = 1 << 30, x1 = -1, y1 = -1;
+  for (int i = lane; i < tiles; i += 32) {
+    num += p[i].num;
+    den += p[i].den;
+    x0 = min(x0, p[i].x0);
+    y0 = min(y0, p[i].y0);
+    x1 = max(x1, p[i].x1);
+    y1 = max(y1, p[i].y1);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    num += __shfl_xor_sync(0xffffffffu, num, o);
+    den += __shfl_xor_sync(0xffffffffu, den, o);
+    x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o));
+    y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+    x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+    y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+  }
+  if (lane == 0) {
+    const bool any = den > 0;
+    float* bx = boxes + (size_t)item * 4;
+    bx[0] = any ? (float)x0 : 0.f;
+    bx[1] = any ? (float)y0 : 0.f;
+    bx[2] = any ? (float)(x1 + 1) : 0.f;
+    bx[3] = any ? (float)(y1 + 1) : 0.f;
+    scores[item] = cls_score[item] * (num / ((float)den + 1e-6f));
+  }
+}
+
+}  // namespace
+}  // namespace msm
+
+using namespace msm;
+
+extern "C" int msm_instance_topk(const float* logits, int64_t* topk_query, int64_t* topk_class, float* topk_score,
+                                 int B, int Q, int K1, int T, void* stream) {
+  MSM_REQUIRE(logits && topk_query && topk_class && topk_score, "logits and the three outputs must be non-null");
+  MSM_REQUIRE(B > 0 && Q > 0 && K1 >= 2, "need B, Q > 0 and at least one class besides 'no object'");
+  MSM_REQUIRE(T > 0 && T <= Q * (K1 - 1), "topk must be in [1, Q * num_classes]");
+  const size_t smem = sizeof(float) * (size_t)Q * (K1 - 1);
+  if (smem > 48 * 1024) {
+    set_error("instance_topk: %d x %d scores do not fit shared memory", Q, K1 - 1);
+    return MSM_E_UNSUPPORTED;
+  }
+  instance_topk_kernel<<<B, kTopkThreads, smem, static_cast<cudaStream_t>(stream)>>>(logits, topk_query, topk_class,
+                                                                                    topk_score, Q, K1, T);
+  return check_launch("instance_topk_kernel");
+}
+
+extern "C" size_t msm_instance_masks_workspace_bytes(int B, int T, int H) {
+  if (B <= 0 || T <= 0 || H <= 0) return 0;
+  return sizeof(Partial) * (size_t)B * T * ((H + kRowsPerCta - 1) / kRowsPerCta);
+}
+
+extern "C" int msm_instance_masks(const float* mask_logits, const int64_t* topk_query, const float* topk_score,
+                                  float* pred_masks, float* boxes, float* scores, int B, int Q, int h, int w, int T,
+                                  int H, int W, void* workspace, size_t workspace_bytes, void* stream) {
+  MSM_REQUIRE(mask_logits && topk_query && topk_score && pred_masks && boxes && scores, "pointers must be non-null");
+  MSM_REQUIRE(B > 0 && Q > 0 && h > 0 && w > 0 && T > 0 && H > 0 && W > 0, "sizes must be positive");
+  MSM_REQUIRE(B <= 65535 && T <= 65535, "at most 65535 images / kept queries per call");
+  MSM_REQUIRE(workspace && workspace_bytes >= msm_instance_masks_workspace_bytes(B, T, H), "workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int tiles = (H + kRowsPerCta - 1) / kRowsPerCta;
+  Partial* partials = static_cast<Partial*>(workspace);
+  instance_masks_kernel<<<dim3(tiles, T, B), kMaskThreads, 0, st>>>(mask_logits, topk_query, pred_masks, partials, Q, h,
+                                                                    w, T, H, W);
+  int rc = check_launch("instance_masks_kernel");
+  if (rc) return rc;
+  const int total = B * T;
+  instance_finalize_kernel<<<(total + 7) / 8, 256, 0, st>>>(partials, topk_score, boxes, scores, tiles, total);
+  return check_launch("instance_finalize_kernel");
+}

@@ -621,6 +621,48 @@ def assign_clusters(X, Z, seed_labels, num_labels):
     return labels[0] if squeeze else labels
 
 
+def instance_topk(pred_logits, topk):
+    """softmax over classes, drop 'no object', keep the ``topk`` best (query, class) pairs per image:
+    pred_logits [B,Q,K+1] -> (query int64 [B,T], class int64 [B,T], score [B,T]), descending score."""
+    lg = _require(pred_logits, "pred_logits").contiguous()
+    if lg.dim() != 3:
+        raise ValueError(f"pred_logits must be [B,Q,K+1], got {tuple(lg.shape)}")
+    B, Q, K1 = lg.shape
+    T = int(topk)
+    if not 1 <= T <= Q * (K1 - 1):
+        raise ValueError(f"topk={T} outside [1, {Q * (K1 - 1)}]")
+    query = torch.empty(B, T, device=lg.device, dtype=torch.int64)
+    cls = torch.empty(B, T, device=lg.device, dtype=torch.int64)
+    score = torch.empty(B, T, device=lg.device, dtype=torch.float32)
+    rc = _lib.lib().msm_instance_topk(lg.data_ptr(), query.data_ptr(), cls.data_ptr(), score.data_ptr(), B, Q, K1, T,
+                                      _stream())
+    check(rc, "msm_instance_topk")
+    return query, cls, score
+
+
+def instance_masks(pred_masks, topk_query, topk_score, size):
+    """kept queries only: bilinear upsample to ``size`` + threshold + box + mask score in one pass:
+    pred_masks [B,Q,h,w] logits -> (masks 0/1 float [B,T,H,W], boxes [B,T,4], scores [B,T])."""
+    pm = _require(pred_masks, "pred_masks").contiguous()
+    B, Q, h, w = pm.shape
+    H, W = int(size[0]), int(size[1])
+    tq = topk_query.to(device=pm.device, dtype=torch.int64).contiguous()
+    ts = _require(topk_score, "topk_score").contiguous()
+    T = tq.shape[1]
+    if tq.shape != (B, T) or ts.shape != (B, T):
+        raise ValueError(f"topk_query {tuple(tq.shape)} / topk_score {tuple(ts.shape)} must both be [{B}, T]")
+    masks = torch.empty(B, T, H, W, device=pm.device, dtype=torch.float32)
+    boxes = torch.empty(B, T, 4, device=pm.device, dtype=torch.float32)
+    scores = torch.empty(B, T, device=pm.device, dtype=torch.float32)
+    L = _lib.lib()
+    ws_bytes = L.msm_instance_masks_workspace_bytes(B, T, H)
+    ws = torch.empty(ws_bytes, device=pm.device, dtype=torch.uint8)
+    rc = L.msm_instance_masks(pm.data_ptr(), tq.data_ptr(), ts.data_ptr(), masks.data_ptr(), boxes.data_ptr(),
+                              scores.data_ptr(), B, Q, h, w, T, H, W, ws.data_ptr(), ws_bytes, _stream())
+    check(rc, "msm_instance_masks")
+    return masks, boxes, scores
+
+
 # ----------------------------------------------------------------------------------------------
 # launch accounting / per-op device timing (used by bench.py; off by default)
 # ----------------------------------------------------------------------------------------------
@@ -786,5 +828,10 @@ seed_connected_components = _instrument("seed_connected_components", 1)(seed_con
 assign_clusters = _instrument("assign_clusters", 2, lambda X, Z, seed_labels, num_labels: (
     f"B{X.shape[0] if X.dim() == 3 else 1} n{X.shape[-2]} m{Z.shape[-2]} d{X.shape[-1]}",
     (4.0 * X.shape[-1] + 8.0) * (X.numel() // X.shape[-1]), 2.0 * X.numel() * Z.shape[-2]))(assign_clusters)
+instance_topk = _instrument("instance_topk", 1)(instance_topk)
+instance_masks = _instrument("instance_masks", 2, lambda pred_masks, topk_query, topk_score, size: (
+    f"B{pred_masks.shape[0]} T{topk_query.shape[1]} {pred_masks.shape[2]}x{pred_masks.shape[3]}->{int(size[0])}x{int(size[1])}",
+    4.0 * pred_masks.shape[0] * topk_query.shape[1] * (int(size[0]) * int(size[1]) + pred_masks.shape[2] * pred_masks.shape[3]),
+    0.0))(instance_masks)
 mean_shift_hill_climb = _instrument("mean_shift_hill_climb", lambda X, Z, kappa, max_iters=10: 2 * int(max_iters),
                                     _work_ms)(mean_shift_hill_climb)
