@@ -12,7 +12,7 @@ namespace {
 
 constexpr int kTopkThreads = 256;
 constexpr int kMaskThreads = 256;
-constexpr int kRowsPerCta = 8;
+constexpr int kRowsPerCta = 16;
 
 // softmax over the K+1 classes, drop the last ("no object") class, keep the T best of the Q*K scores.
 // Output order: descending score, ties -> lower flattened index (torch.topk(sorted=False) promises no order).
@@ -55,6 +55,9 @@ struct Partial {
 // grid (ceil(H / kRowsPerCta), T, B): bilinear resample (align_corners=False, PyTorch's source-index rule) of the
 // kept query's low-resolution logits, threshold at 0, per-CTA partial reductions (summed in a fixed order by
 // instance_finalize_kernel: results are run-to-run deterministic).
+// A thread owns 4 consecutive columns for all rows of the tile: the column weights are computed once, and the two
+// horizontally interpolated source rows are reused for every output row that falls between them (4 at the usual
+// 4x upsample), so a pixel costs two FMAs, the threshold and - for foreground only - the sigmoid.
 __global__ void __launch_bounds__(kMaskThreads)
     instance_masks_kernel(const float* __restrict__ mask_logits, const int64_t* __restrict__ topk_query,
                           float* __restrict__ pred_masks, Partial* __restrict__ partials, int Q, int h, int w, int T,
@@ -63,57 +66,72 @@ __global__ void __launch_bounds__(kMaskThreads)
   const int q = (int)topk_query[(size_t)b * T + t];
   const float* mp = mask_logits + ((size_t)b * Q + q) * h * w;
   float* op = pred_masks + ((size_t)b * T + t) * H * W;
-  const bool identity = (h == H) && (w == W);
   const float sh = (float)h / (float)H, sw = (float)w / (float)W;
   const int ya = tile * kRowsPerCta, yb = min(H, ya + kRowsPerCta);
   float num = 0.f;
   int den = 0, x0 = W, y0 = H, x1 = -1, y1 = -1;
   const int Wq = (W + 3) >> 2;  // groups of 4 consecutive pixels of a row
   const bool vec = (W & 3) == 0;
-  for (int g = threadIdx.x; g < (yb - ya) * Wq; g += kMaskThreads) {
-    const int y = ya + g / Wq, xg = (g % Wq) * 4;
-    float sy = sh * ((float)y + 0.5f) - 0.5f;
-    sy = sy < 0.f ? 0.f : sy;
-    const int yy = (int)sy;
-    const int yp = (yy < h - 1) ? 1 : 0;
-    const float ly = sy - (float)yy, hy = 1.f - ly;
-    float m[4];
+  for (int g = threadIdx.x; g < Wq; g += blockDim.x) {
+    const int xg = g * 4;
+    int xo[4], xp[4];
+    float lx[4], hx[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int x = xg + k;
-      m[k] = 0.f;
-      if (x < W) {
-        float val;
-        if (identity) {
-          val = __ldg(mp + (size_t)y * w + x);
-        } else {
-          float sx = sw * ((float)x + 0.5f) - 0.5f;
-          sx = sx < 0.f ? 0.f : sx;
-          const int xx = (int)sx;
-          const int xp = (xx < w - 1) ? 1 : 0;
-          const float lx = sx - (float)xx, hx = 1.f - lx;
-          const float* p = mp + (size_t)yy * w + xx;
-          const float v00 = __ldg(p), v01 = __ldg(p + xp), v10 = __ldg(p + yp * w), v11 = __ldg(p + yp * w + xp);
-          val = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+      float sx = sw * ((float)(xg + k) + 0.5f) - 0.5f;
+      sx = sx < 0.f ? 0.f : sx;
+      int xx = (int)sx;
+      xx = min(xx, w - 1);  // only columns >= W (never stored) can exceed the source
+      xo[k] = xx;
+      xp[k] = (xx < w - 1) ? 1 : 0;
+      lx[k] = sx - (float)xx;
+      hx[k] = 1.f - lx[k];
+    }
+    int cached = -1;
+    float h0[4], h1[4];
+    for (int y = ya; y < yb; ++y) {
+      float sy = sh * ((float)y + 0.5f) - 0.5f;
+      sy = sy < 0.f ? 0.f : sy;
+      const int yy = (int)sy;
+      const int yp = (yy < h - 1) ? 1 : 0;
+      const float ly = sy - (float)yy, hy = 1.f - ly;
+      if (yy != cached) {
+        const float* r0 = mp + (size_t)yy * w;
+        const float* r1 = r0 + yp * w;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          h0[k] = hx[k] * __ldg(r0 + xo[k]) + lx[k] * __ldg(r0 + xo[k] + xp[k]);
+          h1[k] = hx[k] * __ldg(r1 + xo[k]) + lx[k] * __ldg(r1 + xo[k] + xp[k]);
         }
-        if (val > 0.f) {
-          m[k] = 1.f;
+        cached = yy;
+      }
+      float m[4];
+      uint32_t fg = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float val = hy * h0[k] + ly * h1[k];
+        const bool on = val > 0.f && xg + k < W;
+        m[k] = on ? 1.f : 0.f;
+        if (on) {
+          fg |= 1u << k;
           num += 1.f / (1.f + expf(-val));
-          den += 1;
-          x0 = min(x0, x);
-          x1 = max(x1, x);
-          y0 = min(y0, y);
-          y1 = max(y1, y);
         }
       }
-    }
-    float* o = op + (size_t)y * W + xg;
-    if (vec) {
-      *reinterpret_cast<float4*>(o) = make_float4(m[0], m[1], m[2], m[3]);
-    } else {
+      if (fg) {
+        den += __popc(fg);
+        x0 = min(x0, xg + __ffs(fg) - 1);
+        x1 = max(x1, xg + 31 - __clz(fg));
+        y0 = min(y0, y);
+        y1 = max(y1, y);
+      }
+      float* o = op + (size_t)y * W + xg;
+      if (vec) {
+        *reinterpret_cast<float4*>(o) = make_float4(m[0], m[1], m[2], m[3]);
+      } else {
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (xg + k < W) o[k] = m[k];
+        for (int k = 0; k < 4; ++k)
+          if (xg + k < W) o[k] = m[k];
+      }
     }
   }
   // block reduction
@@ -132,7 +150,7 @@ __global__ void __launch_bounds__(kMaskThreads)
   __syncthreads();
   if (threadIdx.x == 0) {
     Partial r = wp[0];
-    for (int i = 1; i < kMaskThreads / 32; ++i) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) {
       r.num += wp[i].num;
       r.den += wp[i].den;
       r.x0 = min(r.x0, wp[i].x0);
@@ -217,8 +235,9 @@ extern "C" int msm_instance_masks(const float* mask_logits, const int64_t* topk_
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int tiles = (H + kRowsPerCta - 1) / kRowsPerCta;
   Partial* partials = static_cast<Partial*>(workspace);
-  instance_masks_kernel<<<dim3(tiles, T, B), kMaskThreads, 0, st>>>(mask_logits, topk_query, pred_masks, partials, Q, h,
-                                                                    w, T, H, W);
+  const int threads = min(kMaskThreads, ((W + 3) / 4 + 31) / 32 * 32);  // one thread per 4 columns, whole warps
+  instance_masks_kernel<<<dim3(tiles, T, B), threads, 0, st>>>(mask_logits, topk_query, pred_masks, partials, Q, h, w, T,
+                                                               H, W);
   int rc = check_launch("instance_masks_kernel");
   if (rc) return rc;
   const int total = B * T;
