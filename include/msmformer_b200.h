@@ -269,6 +269,37 @@ int msm_instance_masks(const float* mask_logits, const int64_t* topk_query, cons
                        int B, int Q, int h, int w, int T, int H, int W,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Two-stage ("zoom-in") glue, lib/fcn/test_dataset.py:62-198. Label maps are fp32 images holding small
+ * non-negative integer ids, as the reference passes them; ids outside [0, L) are ignored by the statistics.
+ * msm_label_stats: per (image, id) int32 [N][L][6] = {pixels, pixels with depth_z > 0, W - xmin, H - ymin,
+ *   xmax + 1, ymax + 1} (all 0 when the id is absent): the torch.unique / mask_to_tight_box / depth-fraction
+ *   reductions of crop_rois :69,82-83 and filter_labels_depth :186-199 in one pass. depth_z = the z plane of
+ *   image 0 (may be NULL), depth_stride = elements between consecutive images.
+ * msm_relabel_lut: out[n][p] = lut[n][in[n][p] - lo] for ids in [lo, lo + L), else unchanged (:120-121, :197).
+ * msm_crop_resize: every ROI at once (:97-113): rgb / depth crops [num][3][S][S] by bilinear align_corners=True,
+ *   mask crops [num][S][S] = nearest resize of (labels == ids[c]); rois int32 [num][4] = x_min, y_min, x_max, y_max.
+ * msm_crop_label_stats: per (crop, local id) int32 [num][L][4] = {pixels, pixels where init_crop != 0,
+ *   pixels with depth z > 0, 0} and double [num][L] depth sums (:118-135).
+ * msm_paste_crops: refined [H][W]: crops resized back (nearest) into their ROIs in `order`, later ones overwrite
+ *   earlier ones where their relabelled value new_label[c][id] is non-zero (:151-180).
+ * ---------------------------------------------------------------------------------------------- */
+int msm_label_stats(const float* labels, const float* depth_z, int64_t depth_stride, int32_t* stats,
+                    int N, int H, int W, int L, void* stream);
+
+int msm_relabel_lut(const float* in, const float* lut, float* out, int N, int64_t per_image, int L, int lo,
+                    void* stream);
+
+int msm_crop_resize(const float* rgb, const float* depth, const float* labels, const int32_t* rois, const float* ids,
+                    float* rgb_crops, float* depth_crops, float* mask_crops, int num, int H, int W, int S,
+                    void* stream);
+
+int msm_crop_label_stats(const float* labels_crop, const float* init_crop, const float* depth_crop, int32_t* stats,
+                         double* depth_sum, int num, int S, int L, void* stream);
+
+int msm_paste_crops(const float* labels_crop, const float* new_label, const int32_t* order, const int32_t* rois,
+                    float* refined, int num, int H, int W, int S, int L, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,8 @@ import torch.nn.functional as F
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 import ref_shim  # noqa: E402
+sys.path.insert(0, os.path.dirname(HERE))
+from scenes import two_stage_crop_labels, two_stage_scene  # noqa: E402
 
 torch.set_num_threads(4)
 torch.backends.mkldnn.enabled = True
@@ -359,6 +361,50 @@ def gen_instance_inference():
          width=np.int64(W), **out)
 
 
+def gen_two_stage():
+    """Runs the reference's own crop_rois / match_label_crop / filter_labels_depth (lib/fcn/test_dataset.py:62-198)
+    and mask_to_tight_box (lib/utils/mask.py:180-195): the functions are cut out of their files by ast (the modules
+    import cv2, matplotlib, transforms3d ...) and executed with cfg stubbed to the two fields they read."""
+    import ast
+    import types
+    lib = os.path.join(ref_shim.REF_ROOT, "lib")
+
+    def cut(path, names):
+        tree = ast.parse(open(path).read())
+        return ast.Module(body=[n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names],
+                          type_ignores=[])
+
+    util_ns = {"torch": torch, "np": np}
+    exec(compile(cut(os.path.join(lib, "utils", "mask.py"),
+                     {"mask_to_tight_box", "mask_to_tight_box_pytorch", "mask_to_tight_box_numpy"}), "mask.py", "exec"),
+         util_ns)
+    cfg = types.SimpleNamespace(TRAIN=types.SimpleNamespace(SYN_CROP_SIZE=64), device="cpu")
+    ns = {"torch": torch, "F": F, "np": np, "cfg": cfg, "util_": types.SimpleNamespace(**util_ns)}
+    exec(compile(cut(os.path.join(lib, "fcn", "test_dataset.py"),
+                     {"crop_rois", "match_label_crop", "filter_labels_depth"}), "test_dataset.py", "exec"), ns)
+    import warnings
+    warnings.simplefilter("ignore")
+    out = {}
+    for tag, with_depth in (("d", True), ("n", False)):
+        rgb, labels, depth = two_stage_scene(31 if with_depth else 32, with_depth=with_depth)
+        out[f"{tag}_rgb"], out[f"{tag}_labels"] = rgb, labels
+        if with_depth:
+            out["d_depth"] = depth
+            filtered = ns["filter_labels_depth"](labels, depth, 0.5)
+            out["d_filtered_05"] = filtered
+            out["d_filtered_08"] = ns["filter_labels_depth"](labels, depth, 0.8)
+            labels = filtered
+        rgb_crops, mask_crops, rois, depth_crops = ns["crop_rois"](rgb, labels.clone(), depth)
+        labels_crop = two_stage_crop_labels(mask_crops, 7)
+        out[f"{tag}_rgb_crops"], out[f"{tag}_mask_crops"], out[f"{tag}_rois"] = rgb_crops, mask_crops, rois
+        if with_depth:
+            out["d_depth_crops"] = depth_crops
+        out[f"{tag}_labels_crop_in"] = labels_crop.clone()
+        refined, marked = ns["match_label_crop"](labels, labels_crop, mask_crops, rois, depth_crops)
+        out[f"{tag}_refined"], out[f"{tag}_labels_crop_out"] = refined, marked
+    save("two_stage", crop_size=np.int64(64), **out)
+
+
 if __name__ == "__main__":
     gen_hypersphere_attention()
     gen_meanshift_attention()
@@ -373,3 +419,4 @@ if __name__ == "__main__":
     gen_mean_shift()
     gen_mean_shift_d64()
     gen_instance_inference()
+    gen_two_stage()

@@ -15,6 +15,7 @@ from oracle import decoder as odec
 from oracle import instance_inference as oii
 from oracle import mean_shift as oms
 from oracle import pixel_decoder as opd
+from oracle import two_stage as ots
 from oracle import vmf_attention as ovmf
 
 pytestmark = pytest.mark.gpu
@@ -594,6 +595,72 @@ def test_instance_inference_vs_oracle(msm, B, Q, K, h, w, H, W, T):
     assert bool((((bx[..., 2] - bx[..., 0]) * (bx[..., 3] - bx[..., 1])) >= area).all())   # box covers the mask
     assert bool((r["scores"] >= 0).all()) and bool((r["scores"] <= 1).all())
     assert bool((r["scores"][area == 0] == 0).all())
+
+
+# ----------------------------------------------------------------------------- two-stage glue
+def _check_two_stage(td, rgb, labels, depth, S, crop_seed, want=None):
+    """the device functions against the oracle (or stored reference outputs) on one scene; returns the outputs."""
+    from scenes import two_stage_crop_labels
+    dev = lambda t: None if t is None else t.cuda()
+    with torch.no_grad():
+        if depth is not None:
+            for thr in (0.5, 0.8):
+                got = td.filter_labels_depth(dev(labels), dev(depth), thr)
+                assert torch.equal(got.cpu(), ots.filter_labels_depth(labels, depth, thr))
+            labels = ots.filter_labels_depth(labels, depth, 0.5)
+        rgb_crops, mask_crops, rois, depth_crops = td.crop_rois(dev(rgb), dev(labels), dev(depth), crop_size=S)
+        o_rgb, o_mask, o_rois, o_depth = ots.crop_rois(rgb, labels, depth, crop_size=S)
+        assert torch.equal(rois.cpu(), o_rois) and rois.dtype == torch.float32
+        assert torch.equal(mask_crops.cpu(), o_mask)                              # nearest: bit-exact
+        # bilinear weights are formed in a different order on the CPU: 1e-6 of the value range
+        assert (rgb_crops.cpu() - o_rgb).abs().max().item() < 2e-6
+        if depth is not None:
+            assert (depth_crops.cpu() - o_depth).abs().max().item() < 2e-6
+        else:
+            assert depth_crops is None
+        labels_crop = two_stage_crop_labels(o_mask, crop_seed)
+        refined, marked = td.match_label_crop(dev(labels), dev(labels_crop), mask_crops, rois, depth_crops)
+        o_refined, o_marked = ots.match_label_crop(labels, labels_crop, o_mask, o_rois, o_depth)
+        assert torch.equal(marked.cpu(), o_marked)
+        assert torch.equal(refined.cpu(), o_refined) and refined.shape == labels.shape
+    return rgb_crops, mask_crops, rois, depth_crops, refined, marked
+
+
+def test_two_stage_golden(msm, golden):
+    """crop_rois / match_label_crop / filter_labels_depth against the reference's own outputs."""
+    from unseenobjectswithmeanshift_b200.fcn import test_dataset as td
+    g, _ = golden("two_stage")
+    S = int(g["crop_size"])
+    for tag in "dn":
+        depth = g["d_depth"] if tag == "d" else None
+        rgb_crops, mask_crops, rois, depth_crops, refined, marked = _check_two_stage(
+            td, g[tag + "_rgb"], g[tag + "_labels"], depth, S, 7)
+        assert torch.equal(rois.cpu(), g[tag + "_rois"])
+        assert torch.equal(mask_crops.cpu(), g[tag + "_mask_crops"])
+        assert (rgb_crops.cpu() - g[tag + "_rgb_crops"]).abs().max().item() < 2e-6
+        assert torch.equal(refined.cpu(), g[tag + "_refined"])
+        assert torch.equal(marked.cpu(), g[tag + "_labels_crop_out"])
+    with torch.no_grad():
+        assert torch.equal(td.filter_labels_depth(g["d_labels"].cuda(), g["d_depth"].cuda(), 0.5).cpu(), g["d_filtered_05"])
+
+
+@pytest.mark.parametrize("H,W,objects,S,with_depth", [(480, 640, 9, 224, True), (480, 640, 6, 224, False),
+                                                      (61, 77, 3, 32, True), (40, 40, 1, 16, False)])
+def test_two_stage_vs_oracle(msm, H, W, objects, S, with_depth):
+    """full-size frames (480x640, 224x224 crops) and ragged small ones, with and without depth."""
+    from scenes import two_stage_scene
+    from unseenobjectswithmeanshift_b200.fcn import test_dataset as td
+    rgb, labels, depth = two_stage_scene(H + objects, H=H, W=W, objects=objects, with_depth=with_depth)
+    _check_two_stage(td, rgb, labels, depth, S, 3)
+
+
+def test_two_stage_no_objects(msm):
+    from unseenobjectswithmeanshift_b200.fcn import test_dataset as td
+    labels = torch.zeros(1, 30, 40).cuda()
+    rgb_crops, mask_crops, rois, depth_crops = td.crop_rois(torch.rand(1, 3, 30, 40).cuda(), labels, None, crop_size=16)
+    assert rgb_crops.shape == (0, 3, 16, 16) and mask_crops.shape == (0, 16, 16) and rois.shape == (0, 4)
+    refined, marked = td.match_label_crop(labels, torch.zeros(0, 16, 16).cuda(), mask_crops, rois, None)
+    assert refined.shape == (1, 30, 40) and float(refined.abs().sum()) == 0 and marked.shape == (0, 16, 16)
 
 
 # ----------------------------------------------------------------------------- dense layers (tcgen05 linear kernel)

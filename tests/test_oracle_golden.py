@@ -180,3 +180,23 @@ def test_instance_inference_tail(golden):
         assert torch.equal(r["pred_classes"][mine], g[f"classes_{b}"][ref])
         assert torch.equal(r["pred_boxes"][mine], g[f"boxes_{b}"][ref])
         assert torch.equal(r["pred_masks"][mine].to(torch.uint8), g[f"masks_{b}"][ref])
+
+
+def test_two_stage_glue(golden):
+    """crop_rois / match_label_crop / filter_labels_depth (lib/fcn/test_dataset.py:62-198): oracle == reference,
+    with and without depth."""
+    from oracle import two_stage as ots
+    g, _ = golden("two_stage")
+    S = int(g["crop_size"])
+    filtered = ots.filter_labels_depth(g["d_labels"], g["d_depth"], 0.5)
+    assert torch.equal(filtered, g["d_filtered_05"])
+    assert torch.equal(ots.filter_labels_depth(g["d_labels"], g["d_depth"], 0.8), g["d_filtered_08"])
+    for tag in "dn":
+        depth = g["d_depth"] if tag == "d" else None
+        labels = filtered if tag == "d" else g["n_labels"]
+        rgb_crops, mask_crops, rois, depth_crops = ots.crop_rois(g[tag + "_rgb"], labels, depth, crop_size=S)
+        assert torch.equal(rois, g[tag + "_rois"]) and torch.equal(mask_crops, g[tag + "_mask_crops"])
+        assert torch.equal(rgb_crops, g[tag + "_rgb_crops"])
+        assert depth_crops is None or torch.equal(depth_crops, g["d_depth_crops"])
+        refined, marked = ots.match_label_crop(labels, g[tag + "_labels_crop_in"], mask_crops, rois, depth_crops)
+        assert torch.equal(refined, g[tag + "_refined"]) and torch.equal(marked, g[tag + "_labels_crop_out"])

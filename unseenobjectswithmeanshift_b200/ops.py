@@ -663,6 +663,97 @@ def instance_masks(pred_masks, topk_query, topk_score, size):
     return masks, boxes, scores
 
 
+def label_stats(labels, depth=None, num_ids=None):
+    """labels [N,H,W] fp32 ids, depth [N,3,H,W] or None -> int32 [N,L,6] on the device:
+    (pixels, pixels with depth z > 0, W - xmin, H - ymin, xmax + 1, ymax + 1), zeros for an absent id."""
+    lb = _require(labels, "labels").contiguous()
+    if lb.dim() != 3:
+        raise ValueError(f"labels must be [N,H,W], got {tuple(lb.shape)}")
+    N, H, W = lb.shape
+    L = int(num_ids) if num_ids is not None else int(lb.max().item()) + 1
+    if not 1 <= L <= 1024:
+        raise ValueError(f"label ids must lie in [0, 1024), got max id {L - 1}")
+    dz, stride = 0, 0
+    if depth is not None:
+        dp = _require(depth, "depth").contiguous()
+        if dp.shape != (N, 3, H, W):
+            raise ValueError(f"depth must be [{N},3,{H},{W}], got {tuple(dp.shape)}")
+        dz, stride = dp.data_ptr() + 2 * H * W * 4, 3 * H * W
+    stats = torch.empty(N, L, 6, device=lb.device, dtype=torch.int32)
+    rc = _lib.lib().msm_label_stats(lb.data_ptr(), dz, stride, stats.data_ptr(), N, H, W, L, _stream())
+    check(rc, "msm_label_stats")
+    return stats
+
+
+def relabel_lut(labels, lut, lo=0):
+    """out = lut[n][labels - lo] for ids in [lo, lo + L), unchanged elsewhere. labels [N,...] fp32, lut [N,L] fp32."""
+    lb = _require(labels, "labels").contiguous()
+    lt = _require(lut, "lut").contiguous()
+    N = lb.shape[0]
+    if lt.dim() != 2 or lt.shape[0] != N:
+        raise ValueError(f"lut must be [{N}, L], got {tuple(lt.shape)}")
+    out = torch.empty_like(lb)
+    rc = _lib.lib().msm_relabel_lut(lb.data_ptr(), lt.data_ptr(), out.data_ptr(), N, lb.numel() // N, lt.shape[1],
+                                    int(lo), _stream())
+    check(rc, "msm_relabel_lut")
+    return out
+
+
+def crop_resize(rgb, depth, labels, rois, ids, crop_size):
+    """every ROI of one image at once: rgb [3,H,W], depth [3,H,W] or None, labels [H,W], rois int32 [num,4]
+    (x_min, y_min, x_max, y_max), ids fp32 [num] -> (rgb_crops [num,3,S,S], depth_crops or None, mask_crops [num,S,S])."""
+    im = _require(rgb, "rgb").contiguous()
+    lb = _require(labels, "labels").contiguous()
+    _, H, W = im.shape
+    num, S = rois.shape[0], int(crop_size)
+    r = rois.to(device=im.device, dtype=torch.int32).contiguous()
+    i = ids.to(device=im.device, dtype=torch.float32).contiguous()
+    rgb_crops = torch.empty(num, 3, S, S, device=im.device, dtype=torch.float32)
+    mask_crops = torch.empty(num, S, S, device=im.device, dtype=torch.float32)
+    dp = _require(depth, "depth").contiguous() if depth is not None else None
+    depth_crops = torch.empty(num, 3, S, S, device=im.device, dtype=torch.float32) if dp is not None else None
+    if num:
+        rc = _lib.lib().msm_crop_resize(im.data_ptr(), dp.data_ptr() if dp is not None else 0, lb.data_ptr(),
+                                        r.data_ptr(), i.data_ptr(), rgb_crops.data_ptr(),
+                                        depth_crops.data_ptr() if dp is not None else 0, mask_crops.data_ptr(), num, H, W,
+                                        S, _stream())
+        check(rc, "msm_crop_resize")
+    return rgb_crops, depth_crops, mask_crops
+
+
+def crop_label_stats(labels_crop, init_crop, depth_crop=None, num_ids=None):
+    """labels_crop / init_crop [num,S,S], depth_crop [num,3,S,S] or None -> (int32 [num,L,4] = pixels, pixels where
+    init_crop != 0, pixels with depth z > 0, 0;  float64 [num,L] depth sums)."""
+    lb = _require(labels_crop, "labels_crop").contiguous()
+    ic = _require(init_crop, "init_crop").contiguous()
+    num, S = lb.shape[0], lb.shape[-1]
+    L = int(num_ids) if num_ids is not None else int(lb.max().item()) + 1
+    if not 1 <= L <= 1024:
+        raise ValueError(f"label ids must lie in [0, 1024), got max id {L - 1}")
+    dp = _require(depth_crop, "depth_crop").contiguous() if depth_crop is not None else None
+    stats = torch.empty(num, L, 4, device=lb.device, dtype=torch.int32)
+    dsum = torch.empty(num, L, device=lb.device, dtype=torch.float64)
+    rc = _lib.lib().msm_crop_label_stats(lb.data_ptr(), ic.data_ptr(), dp.data_ptr() if dp is not None else 0,
+                                         stats.data_ptr(), dsum.data_ptr(), num, S, L, _stream())
+    check(rc, "msm_crop_label_stats")
+    return stats, dsum
+
+
+def paste_crops(labels_crop, new_label, order, rois, height, width):
+    """refined [H,W]: crops [num,S,S] resized back (nearest) into their ROIs in ``order``; later ones overwrite
+    earlier ones wherever their relabelled value new_label[c][id] is non-zero."""
+    lb = _require(labels_crop, "labels_crop").contiguous()
+    num, S = lb.shape[0], lb.shape[-1]
+    nl = _require(new_label, "new_label").contiguous()
+    od = order.to(device=lb.device, dtype=torch.int32).contiguous()
+    r = rois.to(device=lb.device, dtype=torch.int32).contiguous()
+    refined = torch.empty(int(height), int(width), device=lb.device, dtype=torch.float32)
+    rc = _lib.lib().msm_paste_crops(lb.data_ptr(), nl.data_ptr(), od.data_ptr(), r.data_ptr(), refined.data_ptr(), num,
+                                    int(height), int(width), S, nl.shape[1], _stream())
+    check(rc, "msm_paste_crops")
+    return refined
+
+
 # ----------------------------------------------------------------------------------------------
 # launch accounting / per-op device timing (used by bench.py; off by default)
 # ----------------------------------------------------------------------------------------------
@@ -828,6 +919,11 @@ seed_connected_components = _instrument("seed_connected_components", 1)(seed_con
 assign_clusters = _instrument("assign_clusters", 2, lambda X, Z, seed_labels, num_labels: (
     f"B{X.shape[0] if X.dim() == 3 else 1} n{X.shape[-2]} m{Z.shape[-2]} d{X.shape[-1]}",
     (4.0 * X.shape[-1] + 8.0) * (X.numel() // X.shape[-1]), 2.0 * X.numel() * Z.shape[-2]))(assign_clusters)
+label_stats = _instrument("label_stats", 1)(label_stats)
+relabel_lut = _instrument("relabel_lut", 1)(relabel_lut)
+crop_resize = _instrument("crop_resize", 1)(crop_resize)
+crop_label_stats = _instrument("crop_label_stats", 1)(crop_label_stats)
+paste_crops = _instrument("paste_crops", 1)(paste_crops)
 instance_topk = _instrument("instance_topk", 1)(instance_topk)
 instance_masks = _instrument("instance_masks", 2, lambda pred_masks, topk_query, topk_score, size: (
     f"B{pred_masks.shape[0]} T{topk_query.shape[1]} {pred_masks.shape[2]}x{pred_masks.shape[3]}->{int(size[0])}x{int(size[1])}",
