@@ -255,7 +255,7 @@ int msm_assign_clusters(const float* X, const float* Z, const int64_t* seed_labe
  *   logits [B][Q][K1]; topk_query / topk_class int64 [B][T], topk_score [B][T]; order: descending score
  *   (the reference's topk(sorted=False) promises none).
  * msm_instance_masks: for kept query t of image b, the low-resolution logits mask_logits [B][Q][h][w] resampled to
- *   H x W:  pred_masks [B][T][H][W] = (m > 0) as 0/1 floats; boxes [B][T][4] = (x0, y0, x1+1, y1+1) of the
+ *   H x W:  pred_masks [B][T][H][W] = (m > 0) as 0/1 floats (NULL = not wanted); boxes [B][T][4] = (x0, y0, x1+1, y1+1) of the
  *   foreground, zeros when empty (detectron2 BitMasks.get_bounding_boxes); scores [B][T] =
  *   topk_score * sum(sigmoid(m) * mask) / (sum(mask) + 1e-6).
  * ---------------------------------------------------------------------------------------------- */
@@ -268,6 +268,16 @@ int msm_instance_masks(const float* mask_logits, const int64_t* topk_query, cons
                        float* pred_masks, float* boxes, float* scores,
                        int B, int Q, int h, int w, int T, int H, int W,
                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* get_confident_instances + combine_masks (lib/fcn/test_utils.py:35-52, 93-112) without materialising the masks:
+ * instance_label [B][T] int32 = 2 + (confident instances before t) or -1 when t is dropped (topk_mode: class == 1 and
+ * score > low_threshold when num_class >= 2, everything otherwise; else score > score_threshold); label_map [B][H][W]
+ * = the label of the LAST kept instance whose upsampled logit is > 0 at the pixel, else 0. scores / classes are the
+ * outputs of msm_instance_masks (pred_masks may be NULL there) / msm_instance_topk. T <= 64. */
+int msm_instance_label_map(const float* mask_logits, const int64_t* topk_query, const float* scores,
+                           const int64_t* classes, int32_t* instance_label, float* label_map,
+                           int B, int Q, int h, int w, int T, int H, int W,
+                           int topk_mode, int num_class, float score_threshold, float low_threshold, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Two-stage ("zoom-in") glue, lib/fcn/test_dataset.py:62-198. Label maps are fp32 images holding small

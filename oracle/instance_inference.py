@@ -50,3 +50,23 @@ def canonical(fields, num_classes):
     """rows in a canonical order (ascending flattened (query, class) index) - topk(sorted=False) has none."""
     order = torch.argsort(fields["query_index"] * num_classes + fields["pred_classes"])
     return {k: v[order] for k, v in fields.items()}
+
+
+def get_confident_instances(fields, topk=False, score=0.7, num_class=2, low_threshold=0.4):
+    """lib/fcn/test_utils.py:35-52 on a dict of per-instance tensors."""
+    if topk:
+        if num_class < 2:
+            return fields
+        keep = (fields["pred_classes"] == 1) & (fields["scores"] > low_threshold)
+    else:
+        keep = fields["scores"] > score
+    return {k: v[keep] for k, v in fields.items()}
+
+
+def combine_masks(fields):
+    """lib/fcn/test_utils.py:93-112: instance i paints label i + 2 over everything painted before."""
+    masks = fields["pred_masks"]
+    out = torch.zeros(masks.shape[-2:], dtype=torch.float64)
+    for i in range(masks.shape[0]):
+        out[masks[i] != 0] = i + 2
+    return out

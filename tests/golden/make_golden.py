@@ -336,7 +336,7 @@ def gen_instance_inference():
         def get_bounding_boxes(self):
             return Boxes(oii.get_bounding_boxes(self.tensor))
 
-    ns = {"torch": torch, "F": F, "Instances": Instances, "Boxes": Boxes, "BitMasks": BitMasks}
+    ns = {"torch": torch, "F": F, "np": np, "Instances": Instances, "Boxes": Boxes, "BitMasks": BitMasks}
     exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
     torch.manual_seed(21)
     B, Q, K, h, w, H, W, T = 2, 24, 2, 30, 40, 120, 160, 7
@@ -350,6 +350,24 @@ def gen_instance_inference():
     masks[1, :3] = -3.0 - torch.rand(3, h, w)      # empty masks: zero box, zero score
     logits[1, :3, 0] += 6                           # ... that are certainly kept
     up = F.interpolate(masks, size=(H, W), mode="bilinear", align_corners=False)   # :337-343
+    # get_confident_instances + combine_masks (lib/fcn/test_utils.py:35-52, 93-112), also cut out by ast; the
+    # Instances stub supports what they use: attribute access, boolean-mask indexing, .get(), .to()
+    class Instances(Instances):
+        def __getitem__(self, keep):
+            r = Instances(self.image_size)
+            for k, v in vars(self).items():
+                if k != "image_size":
+                    setattr(r, k, (Boxes(v.tensor[keep]) if isinstance(v, Boxes) else v[keep]))
+            return r
+
+        def get(self, k):
+            return getattr(self, k)
+
+    ns["Instances"] = Instances
+    tu = ast.parse(open(os.path.join(ref_shim.REF_ROOT, "lib", "fcn", "test_utils.py")).read())
+    exec(compile(ast.Module(body=[n for n in tu.body if isinstance(n, ast.FunctionDef)
+                                  and n.name in ("get_confident_instances", "combine_masks")], type_ignores=[]),
+                 "test_utils.py", "exec"), ns)
     out = {}
     for b in range(B):
         self_ = types.SimpleNamespace(sem_seg_head=types.SimpleNamespace(num_classes=K), num_queries=Q,
@@ -357,6 +375,10 @@ def gen_instance_inference():
         r = ns["instance_inference"](self_, logits[b], up[b])
         out.update({f"masks_{b}": r.pred_masks.to(torch.uint8), f"boxes_{b}": r.pred_boxes.tensor,
                     f"scores_{b}": r.scores, f"classes_{b}": r.pred_classes})
+        for tag, kw in (("score", dict(topk=False, score=0.5)), ("topk", dict(topk=True, low_threshold=0.3))):
+            conf = ns["get_confident_instances"]({"instances": r}, num_class=K, **kw)
+            out[f"labelmap_{tag}_{b}"] = ns["combine_masks"](conf)
+            out[f"kept_{tag}_{b}"] = conf.scores
     save("instance_inference", pred_logits=logits, pred_masks=masks, topk=np.int64(T), height=np.int64(H),
          width=np.int64(W), **out)
 

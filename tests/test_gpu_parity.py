@@ -597,6 +597,39 @@ def test_instance_inference_vs_oracle(msm, B, Q, K, h, w, H, W, T):
     assert bool((r["scores"][area == 0] == 0).all())
 
 
+@pytest.mark.parametrize("kw", [dict(topk=False, score=0.5), dict(topk=True, low_threshold=0.3),
+                                dict(topk=False, score=0.99)])
+def test_label_map_from_outputs(msm, golden, kw):
+    """decoder outputs -> label map (instance_inference + get_confident_instances + combine_masks, lib/fcn/
+    test_utils.py:35-52, 93-112) without materialising the masks, against the oracle run in OUR instance order
+    (the reference's topk(sorted=False) order is unspecified; overlaps resolve by that order)."""
+    from unseenobjectswithmeanshift_b200.fcn import test_utils as tu
+    from unseenobjectswithmeanshift_b200.meanshiftformer import instance_inference as ii
+    g, _ = golden("instance_inference")
+    T, H, W = int(g["topk"]), int(g["height"]), int(g["width"])
+    K = g["pred_logits"].shape[-1] - 1
+    with torch.no_grad():
+        label_map, f = tu.label_map_from_outputs(g["pred_logits"].cuda(), g["pred_masks"].cuda(), (H, W), T,
+                                                 num_class=K, **kw)
+        full = ii.instance_inference_batched(g["pred_logits"].cuda(), g["pred_masks"].cuda(), (H, W), T)
+    assert label_map.shape == (2, H, W) and label_map.dtype == torch.float32
+    assert torch.equal(f["scores"], full["scores"]) and torch.equal(f["pred_boxes"], full["pred_boxes"])
+    want = oii.inference_tail(g["pred_logits"], g["pred_masks"], (H, W), T)
+    for b in range(2):
+        mine = (f["query_index"][b] * K + f["pred_classes"][b]).cpu()
+        theirs = (want[b]["query_index"] * K + want[b]["pred_classes"]).tolist()
+        perm = torch.tensor([theirs.index(int(k)) for k in mine])
+        conf = oii.get_confident_instances({k: v[perm] for k, v in want[b].items()}, num_class=K, **kw)
+        assert torch.equal(label_map[b].cpu().double(), oii.combine_masks(conf))
+        kept = f["instance_label"][b].cpu() >= 0
+        assert int(kept.sum()) == conf["scores"].shape[0]
+        assert torch.equal(f["instance_label"][b].cpu()[kept], torch.arange(2, 2 + int(kept.sum()), dtype=torch.int32))
+        # the unfused mirror functions agree with the fused path
+        one = {k: v[b] for k, v in full.items()}
+        lm = tu.combine_masks(tu.get_confident_instances({"instances": one}, num_class=K, **kw))
+        assert torch.equal(lm, label_map[b])
+
+
 # ----------------------------------------------------------------------------- two-stage glue (SURVEY §8 f2)
 def _check_two_stage(td, rgb, labels, depth, S, crop_seed, want=None):
     """the device functions against the oracle (or stored reference outputs) on one scene; returns the outputs."""

@@ -180,6 +180,13 @@ def test_instance_inference_tail(golden):
         assert torch.equal(r["pred_classes"][mine], g[f"classes_{b}"][ref])
         assert torch.equal(r["pred_boxes"][mine], g[f"boxes_{b}"][ref])
         assert torch.equal(r["pred_masks"][mine].to(torch.uint8), g[f"masks_{b}"][ref])
+        # get_confident_instances + combine_masks (lib/fcn/test_utils.py:35-52, 93-112): same CPU topk order as the
+        # reference run, so the label maps must be identical
+        K = g["pred_logits"].shape[-1] - 1
+        for tag, kw in (("score", dict(topk=False, score=0.5)), ("topk", dict(topk=True, low_threshold=0.3))):
+            conf = oii.get_confident_instances(r, num_class=K, **kw)
+            torch.testing.assert_close(conf["scores"], g[f"kept_{tag}_{b}"], rtol=1e-6, atol=1e-7)
+            assert torch.equal(oii.combine_masks(conf), g[f"labelmap_{tag}_{b}"])
 
 
 def test_two_stage_glue(golden):

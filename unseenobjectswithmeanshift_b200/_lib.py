@@ -48,6 +48,7 @@ SIGNATURES = {
     "msm_instance_topk": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "msm_instance_masks_workspace_bytes": (_Z, [_I, _I, _I]),
     "msm_instance_masks": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _Z, _P]),
+    "msm_instance_label_map": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
     "msm_label_stats": (_I, [_P, _P, _L, _P, _I, _I, _I, _I, _P]),
     "msm_relabel_lut": (_I, [_P, _P, _P, _I, _L, _I, _I, _P]),
     "msm_crop_resize": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),

@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(kMaskThreads)
         y0 = min(y0, y);
         y1 = max(y1, y);
       }
+      if (!pred_masks) continue;  // scores / boxes only (the label-map path never materialises the masks)
       float* o = op + (size_t)y * W + xg;
       if (vec) {
         *reinterpret_cast<float4*>(o) = make_float4(m[0], m[1], m[2], m[3]);
@@ -200,6 +201,72 @@ __global__ void instance_finalize_kernel(const Partial* __restrict__ partials, c
   }
 }
 
+// get_confident_instances (lib/fcn/test_utils.py:35-52) + the label numbering of combine_masks (:93-112):
+// label[b][t] = 2 + (number of confident instances before t), or -1 when instance t is not kept. One warp per image.
+__global__ void confident_labels_kernel(const float* __restrict__ scores, const int64_t* __restrict__ classes,
+                                        int32_t* __restrict__ label, int T, int topk_mode, int num_class,
+                                        float score_threshold, float low_threshold) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  int base = 0;
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    const int t = t0 + lane;
+    bool keep = false;
+    if (t < T) {
+      const float s = scores[(size_t)b * T + t];
+      if (topk_mode) keep = num_class >= 2 ? (classes[(size_t)b * T + t] == 1 && s > low_threshold) : true;
+      else keep = s > score_threshold;
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+    if (t < T) label[(size_t)b * T + t] = keep ? 2 + base + __popc(m & ((1u << lane) - 1)) : -1;
+    base += __popc(m);
+  }
+}
+
+// combine_masks without the masks: every pixel takes the label of the LAST kept instance (in instance order) whose
+// upsampled logit is positive - what the reference's sequential bin_mask[label_pos] = object_label leaves - else 0.
+__global__ void __launch_bounds__(256)
+    instance_label_map_kernel(const float* __restrict__ mask_logits, const int64_t* __restrict__ topk_query,
+                              const int32_t* __restrict__ label, float* __restrict__ out, int Q, int h, int w, int T,
+                              int H, int W) {
+  const int b = blockIdx.y;
+  const float sh = (float)h / (float)H, sw = (float)w / (float)W;
+  __shared__ int s_q[64], s_l[64];
+  __shared__ int s_n;
+  if (threadIdx.x == 0) {  // kept instances, last first
+    int n = 0;
+    for (int t = T - 1; t >= 0 && n < 64; --t)
+      if (label[(size_t)b * T + t] >= 0) {
+        s_q[n] = (int)topk_query[(size_t)b * T + t];
+        s_l[n] = label[(size_t)b * T + t];
+        ++n;
+      }
+    s_n = n;
+  }
+  __syncthreads();
+  const int n = s_n;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < H * W; p += gridDim.x * blockDim.x) {
+    const int y = p / W, x = p - y * W;
+    float sy = sh * ((float)y + 0.5f) - 0.5f, sx = sw * ((float)x + 0.5f) - 0.5f;
+    sy = sy < 0.f ? 0.f : sy;
+    sx = sx < 0.f ? 0.f : sx;
+    const int yy = (int)sy, xx = (int)sx;
+    const int yp = (yy < h - 1) ? 1 : 0, xp = (xx < w - 1) ? 1 : 0;
+    const float ly = sy - (float)yy, lx = sx - (float)xx, hy = 1.f - ly, hx = 1.f - lx;
+    const size_t o00 = (size_t)yy * w + xx;
+    float v = 0.f;
+    for (int k = 0; k < n; ++k) {
+      const float* mp = mask_logits + ((size_t)b * Q + s_q[k]) * h * w + o00;
+      const float h0 = hx * __ldg(mp) + lx * __ldg(mp + xp);
+      const float h1 = hx * __ldg(mp + yp * w) + lx * __ldg(mp + yp * w + xp);
+      if (hy * h0 + ly * h1 > 0.f) {
+        v = (float)s_l[k];
+        break;
+      }
+    }
+    out[(size_t)b * H * W + p] = v;
+  }
+}
+
 }  // namespace
 }  // namespace msm
 
@@ -228,7 +295,7 @@ extern "C" size_t msm_instance_masks_workspace_bytes(int B, int T, int H) {
 extern "C" int msm_instance_masks(const float* mask_logits, const int64_t* topk_query, const float* topk_score,
                                   float* pred_masks, float* boxes, float* scores, int B, int Q, int h, int w, int T,
                                   int H, int W, void* workspace, size_t workspace_bytes, void* stream) {
-  MSM_REQUIRE(mask_logits && topk_query && topk_score && pred_masks && boxes && scores, "pointers must be non-null");
+  MSM_REQUIRE(mask_logits && topk_query && topk_score && boxes && scores, "pointers must be non-null (pred_masks may be)");
   MSM_REQUIRE(B > 0 && Q > 0 && h > 0 && w > 0 && T > 0 && H > 0 && W > 0, "sizes must be positive");
   MSM_REQUIRE(B <= 65535 && T <= 65535, "at most 65535 images / kept queries per call");
   MSM_REQUIRE(workspace && workspace_bytes >= msm_instance_masks_workspace_bytes(B, T, H), "workspace too small");
@@ -243,4 +310,22 @@ extern "C" int msm_instance_masks(const float* mask_logits, const int64_t* topk_
   const int total = B * T;
   instance_finalize_kernel<<<(total + 7) / 8, 256, 0, st>>>(partials, topk_score, boxes, scores, tiles, total);
   return check_launch("instance_finalize_kernel");
+}
+
+extern "C" int msm_instance_label_map(const float* mask_logits, const int64_t* topk_query, const float* scores,
+                                      const int64_t* classes, int32_t* instance_label, float* label_map, int B, int Q,
+                                      int h, int w, int T, int H, int W, int topk_mode, int num_class,
+                                      float score_threshold, float low_threshold, void* stream) {
+  MSM_REQUIRE(mask_logits && topk_query && scores && classes && instance_label && label_map, "pointers must be non-null");
+  MSM_REQUIRE(B > 0 && B <= 65535 && Q > 0 && h > 0 && w > 0 && H > 0 && W > 0, "sizes must be positive");
+  MSM_REQUIRE(T > 0 && T <= 64, "at most 64 kept instances per image");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  confident_labels_kernel<<<B, 32, 0, st>>>(scores, classes, instance_label, T, topk_mode, num_class, score_threshold,
+                                            low_threshold);
+  int rc = check_launch("confident_labels_kernel");
+  if (rc) return rc;
+  const int gx = max(1, min((H * W + 255) / 256, (8 * num_sms() + B - 1) / B));
+  instance_label_map_kernel<<<dim3(gx, B), 256, 0, st>>>(mask_logits, topk_query, instance_label, label_map, Q, h, w, T,
+                                                         H, W);
+  return check_launch("instance_label_map_kernel");
 }

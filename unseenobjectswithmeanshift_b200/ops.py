@@ -640,9 +640,9 @@ def instance_topk(pred_logits, topk):
     return query, cls, score
 
 
-def instance_masks(pred_masks, topk_query, topk_score, size):
+def instance_masks(pred_masks, topk_query, topk_score, size, want_masks=True):
     """kept queries only: bilinear upsample to ``size`` + threshold + box + mask score in one pass:
-    pred_masks [B,Q,h,w] logits -> (masks 0/1 float [B,T,H,W], boxes [B,T,4], scores [B,T])."""
+    pred_masks [B,Q,h,w] logits -> (masks 0/1 float [B,T,H,W] or None, boxes [B,T,4], scores [B,T])."""
     pm = _require(pred_masks, "pred_masks").contiguous()
     B, Q, h, w = pm.shape
     H, W = int(size[0]), int(size[1])
@@ -651,16 +651,39 @@ def instance_masks(pred_masks, topk_query, topk_score, size):
     T = tq.shape[1]
     if tq.shape != (B, T) or ts.shape != (B, T):
         raise ValueError(f"topk_query {tuple(tq.shape)} / topk_score {tuple(ts.shape)} must both be [{B}, T]")
-    masks = torch.empty(B, T, H, W, device=pm.device, dtype=torch.float32)
+    masks = torch.empty(B, T, H, W, device=pm.device, dtype=torch.float32) if want_masks else None
     boxes = torch.empty(B, T, 4, device=pm.device, dtype=torch.float32)
     scores = torch.empty(B, T, device=pm.device, dtype=torch.float32)
     L = _lib.lib()
     ws_bytes = L.msm_instance_masks_workspace_bytes(B, T, H)
     ws = torch.empty(ws_bytes, device=pm.device, dtype=torch.uint8)
-    rc = L.msm_instance_masks(pm.data_ptr(), tq.data_ptr(), ts.data_ptr(), masks.data_ptr(), boxes.data_ptr(),
+    rc = L.msm_instance_masks(pm.data_ptr(), tq.data_ptr(), ts.data_ptr(), masks.data_ptr() if want_masks else 0,
+                              boxes.data_ptr(),
                               scores.data_ptr(), B, Q, h, w, T, H, W, ws.data_ptr(), ws_bytes, _stream())
     check(rc, "msm_instance_masks")
     return masks, boxes, scores
+
+
+def instance_label_map(pred_masks, topk_query, scores, classes, size, topk_mode=False, num_class=2, score=0.7,
+                       low_threshold=0.4):
+    """confident instances -> label map without the full-resolution masks: pred_masks [B,Q,h,w] logits, topk_query /
+    scores / classes [B,T] -> (label_map fp32 [B,H,W], instance_label int32 [B,T]: 2.. for kept instances, -1 else)."""
+    pm = _require(pred_masks, "pred_masks").contiguous()
+    B, Q, h, w = pm.shape
+    H, W = int(size[0]), int(size[1])
+    tq = topk_query.to(device=pm.device, dtype=torch.int64).contiguous()
+    sc = _require(scores, "scores").contiguous()
+    cl = classes.to(device=pm.device, dtype=torch.int64).contiguous()
+    T = tq.shape[1]
+    if T > 64:
+        raise ValueError(f"at most 64 instances per image, got {T}")
+    inst = torch.empty(B, T, device=pm.device, dtype=torch.int32)
+    out = torch.empty(B, H, W, device=pm.device, dtype=torch.float32)
+    rc = _lib.lib().msm_instance_label_map(pm.data_ptr(), tq.data_ptr(), sc.data_ptr(), cl.data_ptr(), inst.data_ptr(),
+                                           out.data_ptr(), B, Q, h, w, T, H, W, 1 if topk_mode else 0, int(num_class),
+                                           float(score), float(low_threshold), _stream())
+    check(rc, "msm_instance_label_map")
+    return out, inst
 
 
 def label_stats(labels, depth=None, num_ids=None):
@@ -919,15 +942,17 @@ seed_connected_components = _instrument("seed_connected_components", 1)(seed_con
 assign_clusters = _instrument("assign_clusters", 2, lambda X, Z, seed_labels, num_labels: (
     f"B{X.shape[0] if X.dim() == 3 else 1} n{X.shape[-2]} m{Z.shape[-2]} d{X.shape[-1]}",
     (4.0 * X.shape[-1] + 8.0) * (X.numel() // X.shape[-1]), 2.0 * X.numel() * Z.shape[-2]))(assign_clusters)
+instance_label_map = _instrument("instance_label_map", 2)(instance_label_map)
 label_stats = _instrument("label_stats", 1)(label_stats)
 relabel_lut = _instrument("relabel_lut", 1)(relabel_lut)
 crop_resize = _instrument("crop_resize", 1)(crop_resize)
 crop_label_stats = _instrument("crop_label_stats", 1)(crop_label_stats)
 paste_crops = _instrument("paste_crops", 1)(paste_crops)
 instance_topk = _instrument("instance_topk", 1)(instance_topk)
-instance_masks = _instrument("instance_masks", 2, lambda pred_masks, topk_query, topk_score, size: (
+instance_masks = _instrument("instance_masks", 2, lambda pred_masks, topk_query, topk_score, size, want_masks=True: (
     f"B{pred_masks.shape[0]} T{topk_query.shape[1]} {pred_masks.shape[2]}x{pred_masks.shape[3]}->{int(size[0])}x{int(size[1])}",
-    4.0 * pred_masks.shape[0] * topk_query.shape[1] * (int(size[0]) * int(size[1]) + pred_masks.shape[2] * pred_masks.shape[3]),
+    4.0 * pred_masks.shape[0] * topk_query.shape[1] * ((int(size[0]) * int(size[1]) if want_masks else 0)
+                                                        + pred_masks.shape[2] * pred_masks.shape[3]),
     0.0))(instance_masks)
 mean_shift_hill_climb = _instrument("mean_shift_hill_climb", lambda X, Z, kappa, max_iters=10: 2 * int(max_iters),
                                     _work_ms)(mean_shift_hill_climb)
