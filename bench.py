@@ -358,25 +358,36 @@ def run_tail(args, rank, local_rank, world, dev, sharding, ops):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     sampler = ClockSampler(local_rank)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    from unseenobjectswithmeanshift_b200.graph import GraphedForward
+
+    def step(inp):
+        return ii.instance_inference_batched(inp["logits"], inp["masks"], (H, W), T)
+
     with torch.no_grad():
         for _ in range(args.warmup):
-            ii.instance_inference_batched(logits, masks, (H, W), T)
+            step({"logits": logits, "masks": masks})
+        ops.reset_stats()
+        step({"logits": logits, "masks": masks})
+        launches_per_step = ops.launches()
+        # three small launches: replayed as one CUDA graph on static buffers (resident in HBM)
+        graphed = None if args.no_graph else GraphedForward(step, {"logits": logits, "masks": masks}, warmup=2)
+        run = (lambda: step({"logits": logits, "masks": masks})) if graphed is None else (lambda: graphed())
         torch.cuda.synchronize()
         sharding.barrier()
         if rank == 0:
             sampler.start()
-        ops.reset_stats()
         total = 0.0
         for _ in range(args.steps):   # outputs (197 MB) would otherwise sit in L2: flush between steps, untimed
             flush.zero_()
             e0.record()
-            r = ii.instance_inference_batched(logits, masks, (H, W), T)
+            r = run()
             e1.record()
             torch.cuda.synchronize()
             total += e0.elapsed_time(e1)
         sharding.barrier()
         ms_dev = sharding.max_over_ranks(total, dev)
-        launches = ops.launches()
+        launches = launches_per_step * args.steps
+        r = {k: v.clone() for k, v in r.items()}
         n_e2e = max(1, min(args.steps, 5))
         sl, sm = torch.empty_like(logits), torch.empty_like(masks)
         for timed in (False, True):
@@ -418,6 +429,7 @@ def run_tail(args, rank, local_rank, world, dev, sharding, ops):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"tail Q=100 120x160->480x640 top-20 batch {B}/GPU", "global_batch": B * world,
+                       "launch": "eager" if args.no_graph else "one CUDA graph per step",
                        "parallelism": f"replicas x{world} (batch-sharded, no collective)",
                        "l2_policy": "l2_flushed_between_steps (256 MB memset, untimed)"},
             "clocks": clocks,
@@ -506,9 +518,12 @@ def main():
         ops.reset_stats(timing=False)
 
         # ---------------- the step as ONE CUDA graph (static input / output buffers)
-        runner = step if args.no_graph else GraphedForward(step, dev_feats, warmup=2)
+        # the graph replays on its static input buffers (device copies of dev_feats made once, resident in HBM);
+        # passing dev_feats again would put a 295 MB device-to-device copy inside every timed step
+        graphed = None if args.no_graph else GraphedForward(step, dev_feats, warmup=2)
+        runner = (lambda feats=None: step(dev_feats)) if graphed is None else (lambda feats=None: graphed(feats))
         for _ in range(args.warmup):
-            runner(dev_feats)
+            runner()
         torch.cuda.synchronize()
         sharding.barrier()
         if rank == 0:
@@ -517,7 +532,7 @@ def main():
         torch.cuda.synchronize()
         e0.record()
         for _ in range(args.steps):
-            runner(dev_feats)
+            runner()
         e1.record()
         torch.cuda.synchronize()
         sharding.barrier()
@@ -527,12 +542,12 @@ def main():
         # ---------------- end to end: pinned host features in, predictions out, every step.
         # Three streams: H2D of step i+1 and D2H of step i-1 overlap the graph replay of step i (PCIe is full
         # duplex); device-side staging copies decouple the graph's static buffers from the transfers.
-        out0 = runner(dev_feats)
+        out0 = runner()
         out_keys = ("pred_logits", "pred_masks")
         host_out = {k: torch.empty(out0[k].shape, dtype=out0[k].dtype).pin_memory() for k in out_keys}
         h2d = sum(v.numel() * v.element_size() for v in host_feats.values())
         d2h = sum(v.numel() * v.element_size() for v in host_out.values())
-        static_in = runner.static_in if not args.no_graph else {k: torch.empty_like(v) for k, v in dev_feats.items()}
+        static_in = graphed.static_in if graphed is not None else dev_feats
         stage_in = {k: torch.empty_like(v) for k, v in static_in.items()}
         stage_out = {k: torch.empty_like(out0[k]) for k in out_keys}
         s_main, s_h2d, s_d2h = torch.cuda.current_stream(), torch.cuda.Stream(), torch.cuda.Stream()
@@ -552,7 +567,7 @@ def main():
                 for k in static_in:
                     static_in[k].copy_(stage_in[k], non_blocking=True)
                 ev_in_free.record(s_main)
-                out = runner(static_in)
+                out = runner()
                 s_main.wait_event(ev_out_free)              # previous contents of stage_out are on the host
                 for k in out_keys:
                     stage_out[k].copy_(out[k], non_blocking=True)
