@@ -50,8 +50,9 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
                 and ops.linear_ln_supported(src, attn.output_proj.weight, src, self.norm1) \
                 and ops.linear_ln_supported(src, attn.output_proj.weight, src, self.norm2):
             # inference: both post-norm residual blocks end in a GEMM whose epilogue does the add + LayerNorm
-            sampled = attn(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes, level_start_index,
-                           padding_mask, project=False)
+            # query = src + pos enters one GEMM only: (src + pos) W^T = src W^T + (pos W^T), a cached row-bias table
+            sampled = attn(src, reference_points, src, spatial_shapes, level_start_index, padding_mask, project=False,
+                           query_pos=pos)
             src = ops.linear_ln(sampled, attn.output_proj.weight, attn.output_proj.bias, src, self.norm1)
             if ops.ffn_ln_supported(src, self.linear1.weight, self.linear2.weight, self.norm2):
                 return ops.ffn_ln(src, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias,
@@ -137,8 +138,14 @@ class MSDeformAttnTransformerEncoderOnly(nn.Module):
         dev = srcs[0].device
         shapes = tuple((int(s.shape[-2]), int(s.shape[-1])) for s in srcs)
         src = torch.cat([s.flatten(2).transpose(1, 2) for s in srcs], 1)
-        pos = torch.cat([p.flatten(2).transpose(1, 2) + self.level_embed[l].view(1, 1, -1)
-                         for l, p in enumerate(pos_embeds)], 1)
+
+        def build_pos():
+            return torch.cat([p.flatten(2).transpose(1, 2) + self.level_embed[l].view(1, 1, -1)
+                              for l, p in enumerate(pos_embeds)], 1)
+        if torch.is_grad_enabled():
+            pos = build_pos()
+        else:  # sine embeddings depend on the shapes only: one tensor per pyramid until level_embed changes
+            pos = ops.cached_value(self, "pos%s_%d_%s" % (shapes, B, dev), [self.level_embed], build_pos)
         spatial_shapes, level_start_index, valid_ratios, ref = self._geometry(shapes, B, dev)
         memory = self.encoder(src, spatial_shapes, level_start_index, valid_ratios, pos, None, reference_points=ref)
         return memory, shapes, level_start_index

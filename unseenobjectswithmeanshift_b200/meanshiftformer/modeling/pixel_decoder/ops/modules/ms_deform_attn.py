@@ -6,6 +6,7 @@ Unlike the reference (:116-121) there is no ``try/except`` that silently reroute
 the CUDA op to a PyTorch ``grid_sample`` path: errors propagate.
 """
 import math
+import os
 import warnings
 
 import torch
@@ -57,11 +58,25 @@ class MSDeformAttn(nn.Module):
         constant_(self.output_proj.bias.data, 0.)
 
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
-                input_padding_mask=None, project=True):
+                input_padding_mask=None, project=True, query_pos=None):
         """query [N,Lq,C]; reference_points [N,Lq,L,2] (or 4); input_flatten [N,S,C];
         input_spatial_shapes int64 [L,2]; input_level_start_index int64 [L] -> [N,Lq,C]."""
         N, Lq, _ = query.shape
         S = input_flatten.shape[1]
+        pos_table = None
+        if query_pos is not None:
+            # extension: the caller passes query and its positional embedding separately; on the tensor-core path
+            # the embedding becomes a cached [Lq, N_out] row bias of the offsets / logits GEMM (identical for every
+            # image: sine embeddings + level embedding), otherwise it is added here
+            # measured on B200 (R50 config, M = 50400 rows): the per-row bias reads in the GEMM epilogue cost more
+            # than the separate add kernel saves, so the fold is opt-in (MSM_FOLD_POS=1)
+            fold = (os.environ.get("MSM_FOLD_POS", "0") == "1" and not torch.is_grad_enabled()
+                    and input_padding_mask is None and reference_points.shape[-1] == 2
+                    and ops.tc_linear_enabled() and query.is_contiguous())
+            if fold:
+                pos_table = query_pos
+            else:
+                query = query + query_pos
         if not torch.cuda.is_current_stream_capturing():  # the check reads the device (not capturable)
             assert int((input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum()) == S
         M, L, P = self.n_heads, self.n_levels, self.n_points
@@ -76,7 +91,12 @@ class MSDeformAttn(nn.Module):
         if torch.is_grad_enabled() and self.sampling_offsets.weight.requires_grad:
             ow = torch.cat([self.sampling_offsets(query), self.attention_weights(query)], -1)
         else:
-            ow = ops.dense(query, w_ow, b_ow)
+            if pos_table is not None and ops.linear_supported(query, w_ow):
+                tab = ops.cached_value(self, "ow_pos", [pos_table, w_ow],
+                                       lambda: F.linear(pos_table[0], w_ow).contiguous())
+                ow = ops.linear_fused(query, w_ow, b_ow, rowbias=tab)
+            else:
+                ow = ops.dense(query if pos_table is None else query + pos_table, w_ow, b_ow)
             if reference_points.shape[-1] == 2 and input_padding_mask is None:
                 # inference: softmax + sampling locations + gather in one kernel
                 output = ops.ms_deform_attn_fused_forward(value.contiguous(), input_spatial_shapes,

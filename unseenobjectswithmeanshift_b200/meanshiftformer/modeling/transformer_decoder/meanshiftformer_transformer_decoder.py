@@ -346,7 +346,7 @@ class _MeanShiftDecoderBase(nn.Module):
             else:
                 s = xf.flatten(2).transpose(1, 2) + self.level_embed.weight[l]
             src.append(s)
-            key_in.append(s + self.pe_layer.table(h, w, dev))
+            key_in.append(None)   # src + positional table, built only where the add cannot be folded (below)
 
         # ---- keys / values: independent of the queries, so project them up front per level
         layers_of = [[i for i in range(self.num_layers) if i % L == l] for l in range(L)]
@@ -359,7 +359,18 @@ class _MeanShiftDecoderBase(nn.Module):
             bk = ops.cached_cat(self, tag + "bk", [a.in_proj_bias[C:2 * C] for a in attn])
             wv = ops.cached_cat(self, tag + "wv", [a.in_proj_weight[2 * C:] for a in attn])
             bv = ops.cached_cat(self, tag + "bv", [a.in_proj_bias[2 * C:] for a in attn])
-            K = ops.dense(key_in[level], wk, bk)  # [B,S,n*C]
+            table = self.pe_layer.table(sizes[level][0], sizes[level][1], dev)
+            if (os.environ.get("MSM_FOLD_POS", "0") == "1" and not torch.is_grad_enabled() and ops.tc_linear_enabled()
+                    and ops.linear_supported(src[level], wk) and table.numel() * len(layer_ids) * 4 <= (64 << 20)):
+                # (src + pos) Wk^T = src Wk^T + (pos Wk^T): the positional half is a cached [S, n*C] row bias.
+                # Opt-in: at M = 38400 rows the strided row-bias reads slow the HBM-bound epilogue by more than the
+                # add kernel costs (4.90 -> 5.14 ms per step with both folds on, B200)
+                tab = ops.cached_value(self, tag + "pos", [table, wk], lambda: F.linear(table, wk).contiguous())
+                K = ops.linear_fused(src[level], wk, bk, rowbias=tab)  # [B,S,n*C]
+            else:
+                if key_in[level] is None:
+                    key_in[level] = src[level] + table
+                K = ops.dense(key_in[level], wk, bk)  # [B,S,n*C]
             V = ops.dense(src[level], wv, bv)
             for j, i in enumerate(layer_ids):
                 kv[i] = (K[..., j * C:(j + 1) * C], V[..., j * C:(j + 1) * C])
