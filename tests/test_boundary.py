@@ -67,6 +67,29 @@ def test_cpu_tensors_are_rejected(built):
         ops.mask_logits(torch.zeros(1, 2, 4), torch.zeros(1, 4, 2, 2))
     with pytest.raises(RuntimeError, match="CUDA tensor"):
         ops.mean_shift_hill_climb(torch.zeros(8, 4), torch.zeros(2, 4), 10.0)
+    # the "next" rows (clusterer, eval tail, two-stage glue) have no CPU path either
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.select_smart_seeds(torch.zeros(8, 64), 3, [0])
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.seed_connected_components(torch.zeros(4, 64), 0.04)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.instance_topk(torch.zeros(1, 10, 3), 5)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.label_stats(torch.zeros(1, 8, 8), num_ids=4)
+
+
+def test_new_entry_points_reject_bad_arguments(built):
+    """argument checks of the clusterer / eval tail / two-stage entry points run before any CUDA call."""
+    L = built.lib()
+    assert L.msm_select_smart_seeds(None, None, None, None, 1, 8, 64, 4, None, 0, None) == -1
+    assert b"non-null" in L.msm_last_error()
+    assert L.msm_seed_connected_components(None, None, None, 1, 4, 64, 0.04, None) == -1
+    assert L.msm_instance_topk(None, None, None, None, 1, 10, 3, 5, None) == -1
+    assert L.msm_label_stats(None, None, 0, None, 1, 8, 8, 4, None) == -1
+    assert L.msm_smart_seeds_workspace_bytes(32, 307200, 100) >= 32 * 307200 * 4 + 32 * 100 * 8 + 32 * 4
+    assert L.msm_smart_seeds_workspace_bytes(0, 10, 10) == 0
+    assert L.msm_assign_clusters_workspace_bytes(32, 100) >= 32 * 100 * 4
+    assert L.msm_instance_masks_workspace_bytes(8, 20, 480) >= 8 * 20 * 30 * 24
 
 
 def test_missing_library_is_an_import_error(built, monkeypatch):

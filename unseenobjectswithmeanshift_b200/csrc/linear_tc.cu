@@ -658,10 +658,6 @@ static int launch(const float* X, int64_t ldx, const void* prepared, const float
     int xs = (int)(((size_t)kMaxSmem - fixed) / kAStageBytes);
     P.xstages = xs > kXStages ? kXStages : xs;
   }
-  if (const char* e = getenv("MSM_DEBUG_XSTAGES")) {
-    const int v = atoi(e);
-    if (v >= 1 && v < P.xstages) P.xstages = v;
-  }
   P.wstages = P.BN > 128 ? 3 : kStages;
   P.n_chunks = N / P.BN;
   P.x_nchw = x_nchw; P.y_nchw = y_nchw; P.Mb = Mb; P.y = Y;

@@ -26,9 +26,6 @@ def init_from_env(backend=None):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL writes its banner ("NCCL version ...") and debug lines to stdout by default; bench.py's stdout is
-        # ONE JSON line, so send them to stderr unless the caller chose a file
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group(backend or ("nccl" if torch.cuda.is_available() else "gloo"))
     return rank, local_rank, world
 
