@@ -110,6 +110,9 @@ def run_reference(args, rank, world):
     from unseenobjectswithmeanshift_b200 import workloads
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    if args.workload in ("meanshift", "cluster", "tail"):
+        run_reference_aux(args, cores)
+        return
     head = workloads.build_head(args.workload)
     sd = {k: v.detach() for k, v in head.state_dict().items()}
     sample_b = 2
@@ -131,6 +134,53 @@ def run_reference(args, rank, world):
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
+
+
+def run_reference_aux(args, cores):
+    """--impl reference for the stand-alone workloads: the oracle port of the same op on a bounded sample per step
+    (1 image for the mean-shift / clusterer workloads, 2 for the eval tail), all host threads."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(4)
+    if args.workload == "tail":
+        from oracle import instance_inference as oii
+        Q, K, h, w, H, W, T, sample_b = 100, 1, 120, 160, 480, 640, 20, 2
+        logits = 2 * torch.randn(sample_b, Q, K + 1, generator=g)
+        masks = F.interpolate(3 * torch.randn(sample_b, Q, h // 8, w // 8, generator=g), size=(h, w), mode="bicubic")
+        step = lambda: oii.inference_tail(logits, masks, (H, W), T)  # noqa: E731
+        metric = ("images/sec eval tail: mask upsample + instance_inference (100 queries 120x160 -> top-20 instances "
+                  "at 480x640)")
+        workload = "tail Q=100 120x160->480x640 top-20"
+    else:
+        from oracle import mean_shift as oms
+        n, d, m, sample_b = 480 * 640, 64, 100, 1
+        X = F.normalize(torch.randn(n, d, generator=g), dim=1)
+        if args.workload == "meanshift":
+            Z0 = X[torch.randperm(n, generator=g)[:m]].clone()
+            step = lambda: oms.seed_hill_climbing_ball(X, Z0, 10.0, 10)  # noqa: E731
+            metric = ("images/sec standalone vMF mean-shift hill climb (640x480x64-d embeddings, 100 seeds, kappa=10, "
+                      "10 iterations)")
+            workload = "meanshift n=307200 d=64 m=100 kappa=10 iters=10"
+        else:
+            step = lambda: oms.mean_shift_smart_init(X, 20.0, m, 10, 0)  # noqa: E731
+            metric = ("images/sec classical vMF mean-shift clustering (640x480x64-d embeddings: 100 farthest-point "
+                      "seeds, kappa=20, 10 iterations, connected components, nearest-seed labels)")
+            workload = "cluster n=307200 d=64 m=100 kappa=20 iters=10"
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = sample_b * args.steps / dt
+    emit({"impl": "reference", "metric": metric, "value": val, "unit": "images/s", "n_gpus": args.gpus,
+          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+          "config": {"workload": workload, "per_step_batch": sample_b,
+                     "note": "CPU oracle port of the reference PyTorch path, fp32"},
+          "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port",
+                           "sample": f"{args.steps} steps x {sample_b} image(s) of the same workload"},
+          "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+          "gpu_launches": 0})
 
 
 def run_meanshift(args, rank, local_rank, world, dev, sharding, ops):
