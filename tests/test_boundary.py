@@ -123,3 +123,20 @@ def test_registries_and_state_dict_layout():
         "pixel_decoder.mask_features.weight": (256, 64, 1, 1),
     }.items():
         assert tuple(sd[k].shape) == shape, k
+
+
+def test_meta_arch_registry_and_image_batching():
+    """META_ARCH wrappers register under the reference's names; ImageList-style batching pads bottom / right."""
+    from unseenobjectswithmeanshift_b200 import meanshiftformer as mf
+    from unseenobjectswithmeanshift_b200.d2compat import META_ARCH_REGISTRY
+    from unseenobjectswithmeanshift_b200.meanshiftformer.meanshiftformer_model import _batch_images
+    from unseenobjectswithmeanshift_b200.meanshiftformer import pretrained_meanshiftformer_model as pm
+    assert META_ARCH_REGISTRY.get("MeanShiftMaskFormer") is mf.MeanShiftMaskFormer
+    assert pm.PretrainedMeanShiftMaskFormer is META_ARCH_REGISTRY.get("PretrainedMeanShiftMaskFormer")
+    a, b = torch.ones(3, 30, 40), 2 * torch.ones(3, 20, 50)
+    batch, sizes = _batch_images([a, b], 32)
+    assert batch.shape == (2, 3, 32, 64) and sizes == [(30, 40), (20, 50)]
+    assert float(batch[0, :, :30, :40].min()) == 1 and float(batch[0, :, 30:].abs().sum()) == 0
+    assert float(batch[1, :, :20, :50].min()) == 2 and float(batch[1, :, :, 50:].abs().sum()) == 0
+    same, sizes = _batch_images([a, a], 0)
+    assert same.shape == (2, 3, 30, 40) and sizes == [(30, 40)] * 2

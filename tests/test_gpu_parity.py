@@ -630,6 +630,105 @@ def test_label_map_from_outputs(msm, golden, kw):
         assert torch.equal(lm, label_map[b])
 
 
+# ----------------------------------------------------------------------------- META_ARCH wrappers
+class _ToyPyramid(torch.nn.Module):
+    """stand-in backbone: res2..res5 feature maps with the channel / stride layout of ``_shapes()``."""
+
+    def __init__(self):
+        super().__init__()
+        self.convs = torch.nn.ModuleDict({k: torch.nn.Conv2d(3, s.channels, 1) for k, s in _shapes().items()})
+
+    def forward(self, x):
+        return {k: self.convs[k](F.avg_pool2d(x, s.stride)) for k, s in _shapes().items()}
+
+
+class _ToyEmbedding(torch.nn.Module):
+    """stand-in for the UCN embedding network: (image, label, depth) -> [B,64,H,W]."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv = torch.nn.Conv2d(3, 64, 3, padding=1)
+
+    def forward(self, x, label=None, depth=None):
+        return self.conv(x if depth is None else x + depth)
+
+
+def _same_instances(got, want):
+    """the wrapper against the same pipeline run by hand (two separate launches of the head)."""
+    assert torch.equal(got["pred_classes"], want["pred_classes"])
+    torch.testing.assert_close(got["scores"], want["scores"], rtol=1e-5, atol=1e-7)
+    assert float((got["pred_masks"] == want["pred_masks"]).float().mean()) > 0.9999
+
+
+def _meta_kwargs(head, **extra):
+    kw = dict(sem_seg_head=head, criterion=None, num_queries=10, object_mask_threshold=0.8, overlap_threshold=0.8,
+              metadata=None, size_divisibility=32, sem_seg_postprocess_before_inference=True,
+              pixel_mean=[0.4, 0.5, 0.6], pixel_std=[0.2, 0.25, 0.3], semantic_on=False, panoptic_on=False,
+              instance_on=True, test_topk_per_image=6)
+    kw.update(extra)
+    return kw
+
+
+def test_meta_arch_wrappers(msm):
+    """MeanShiftMaskFormer / PretrainedMeanShiftMaskFormer (meanshiftformer_model.py, pretrained_meanshiftformer_
+    model.py): eval forward == backbone -> head -> inference_tail done by hand; reference state_dict layout."""
+    from unseenobjectswithmeanshift_b200 import meanshiftformer as mf
+    from unseenobjectswithmeanshift_b200.d2compat import META_ARCH_REGISTRY
+    from unseenobjectswithmeanshift_b200.meanshiftformer import instance_inference as ii
+    assert META_ARCH_REGISTRY.get("MeanShiftMaskFormer") is mf.MeanShiftMaskFormer
+    assert META_ARCH_REGISTRY.get("PretrainedMeanShiftMaskFormer") is mf.PretrainedMeanShiftMaskFormer
+    torch.manual_seed(5)
+    head = msm.modeling.PretrainedMeanShiftMaskFormerHead(
+        _shapes(), num_classes=2, pixel_decoder=_pixel_decoder(msm), loss_weight=1.0, ignore_value=255,
+        transformer_predictor=msm.modeling.MeanShiftTransformerDecoder(32, True, **_decoder_kwargs(3)),
+        transformer_in_feature="multi_scale_pixel_decoder")
+    model = mf.MeanShiftMaskFormer(backbone=_ToyPyramid(), **_meta_kwargs(head)).cuda().eval()
+    keys = model.state_dict().keys()
+    assert "criterion.empty_weight" in keys and any(k.startswith("backbone.") for k in keys)
+    assert any(k.startswith("sem_seg_head.predictor.") for k in keys) and "pixel_mean" not in keys
+    imgs = [torch.rand(3, 64, 96), torch.rand(3, 64, 96)]
+    with torch.no_grad():
+        res = model([{"image": im, "height": 64, "width": 96} for im in imgs])
+        batch = torch.stack([(im.cuda() - model.pixel_mean) / model.pixel_std for im in imgs])
+        out, _ = model.sem_seg_head(model.backbone(batch), 64, 96)
+        want = ii.instance_inference_batched(out["pred_logits"], out["pred_masks"], (64, 96), 6)
+    assert len(res) == 2 and set(res[0]) == {"instances"}
+    for b in range(2):
+        inst = res[b]["instances"]
+        assert inst["pred_masks"].shape == (6, 64, 96) and inst["pred_boxes"].shape == (6, 4)
+        _same_instances(inst, {k: v[b] for k, v in want.items()})
+    with pytest.raises(NotImplementedError, match="output size"):
+        with torch.no_grad():
+            model([{"image": imgs[0], "height": 128, "width": 192}])
+    model.train()
+    with pytest.raises(NotImplementedError, match="training"):
+        with torch.no_grad():
+            model([{"image": imgs[0]}])
+
+    # pretrained-embedding variant: unit-norm 64-d pixel embeddings are the head's only feature map
+    from unseenobjectswithmeanshift_b200.d2compat import ShapeSpec
+    shapes = {"res5": ShapeSpec(channels=64, stride=1)}
+    head2 = msm.modeling.PretrainedMeanShiftMaskFormerHead(
+        shapes, num_classes=2, pixel_decoder=msm.modeling.SimpleBasePixelDecoder(shapes, conv_dim=64, mask_dim=32, norm="GN"),
+        loss_weight=1.0, ignore_value=255,
+        transformer_predictor=msm.modeling.PretrainedMeanShiftTransformerDecoder(64, True, **_decoder_kwargs(2)),
+        transformer_in_feature="multi_scale_pixel_decoder")
+    model2 = mf.PretrainedMeanShiftMaskFormer(backbone=_ToyEmbedding(), **_meta_kwargs(head2, size_divisibility=0,
+                                                                                     use_depth=True)).cuda().eval()
+    assert any(k.startswith("pretrained_backbone.") for k in model2.state_dict())
+    rgb, depth = torch.rand(2, 3, 32, 48), torch.rand(2, 3, 32, 48)
+    with torch.no_grad():
+        res2 = model2([{"image": rgb[b], "depth": depth[b]} for b in range(2)])
+        res2b = model2([{"image": rgb, "depth": depth}])                      # one pre-batched entry (:272-273)
+        emb = F.normalize(model2.pretrained_backbone(rgb.cuda(), None, depth.cuda()), p=2, dim=1)
+        out2, _ = model2.sem_seg_head({"res5": emb}, 32, 48)
+        want2 = ii.instance_inference_batched(out2["pred_logits"], out2["pred_masks"], (32, 48), 6)
+    assert len(res2) == 2 and len(res2b) == 2
+    for b in range(2):
+        _same_instances(res2[b]["instances"], {k: v[b] for k, v in want2.items()})
+        _same_instances(res2b[b]["instances"], {k: v[b] for k, v in want2.items()})
+
+
 # ----------------------------------------------------------------------------- two-stage glue (SURVEY §8 f2)
 def _check_two_stage(td, rgb, labels, depth, S, crop_seed, want=None):
     """the device functions against the oracle (or stored reference outputs) on one scene; returns the outputs."""
