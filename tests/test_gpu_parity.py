@@ -729,6 +729,54 @@ def test_meta_arch_wrappers(msm):
         _same_instances(res2b[b]["instances"], {k: v[b] for k, v in want2.items()})
 
 
+def _tiny_embedding_model(msm, seed):
+    from unseenobjectswithmeanshift_b200 import meanshiftformer as mf
+    from unseenobjectswithmeanshift_b200.d2compat import ShapeSpec
+    torch.manual_seed(seed)
+    shapes = {"res5": ShapeSpec(channels=64, stride=1)}
+    head = msm.modeling.PretrainedMeanShiftMaskFormerHead(
+        shapes, num_classes=2, pixel_decoder=msm.modeling.SimpleBasePixelDecoder(shapes, conv_dim=64, mask_dim=32, norm="GN"),
+        loss_weight=1.0, ignore_value=255,
+        transformer_predictor=msm.modeling.PretrainedMeanShiftTransformerDecoder(64, True, **_decoder_kwargs(2)),
+        transformer_in_feature="multi_scale_pixel_decoder")
+    return mf.PretrainedMeanShiftMaskFormer(backbone=_ToyEmbedding(), **_meta_kwargs(head, size_divisibility=0,
+                                                                                    use_depth=True)).cuda().eval()
+
+
+def test_two_stage_label_maps_end_to_end(msm):
+    """label_maps of the wrappers and fcn/test_utils.two_stage_label_maps (test_sample_crop's inference part) on two
+    tiny random networks: the plumbing on the device (shapes, dtypes, one batched second-stage call) against the same
+    pipeline composed by hand."""
+    from unseenobjectswithmeanshift_b200.fcn import test_dataset as td
+    from unseenobjectswithmeanshift_b200.fcn import test_utils as tu
+    stage1, stage2 = _tiny_embedding_model(msm, 11), _tiny_embedding_model(msm, 12)
+    g = torch.Generator().manual_seed(3)
+    rgb, depth = torch.rand(1, 3, 32, 48, generator=g).cuda(), (torch.rand(1, 3, 32, 48, generator=g) + 0.1).cuda()
+    kw = dict(topk=True, low_threshold=0.0)
+    with torch.no_grad():
+        lm, fields = stage1.label_maps([{"image": rgb[0], "depth": depth[0]}], **kw)
+        assert lm.shape == (1, 32, 48) and lm.dtype == torch.float32 and fields["instance_label"].shape == (1, 6)
+        out, _ = stage1.sem_seg_head({"res5": F.normalize(stage1.pretrained_backbone(rgb, None, depth), p=2, dim=1)}, 32, 48)
+        want, _ = tu.label_map_from_outputs(out["pred_logits"], out["pred_masks"], (32, 48), 6, num_class=2, **kw)
+        assert float((lm == want).float().mean()) > 0.999
+        out_label, refined = tu.two_stage_label_maps(stage1, stage2, rgb, depth, crop_size=16, confident_score=0.7, **kw)
+        assert out_label.shape == (1, 32, 48) and out_label.dtype == torch.float32
+        assert torch.equal(out_label, td.filter_labels_depth(lm, depth, 0.5)) or float((out_label == lm).float().mean()) > 0.999
+        ids = out_label.unique()
+        assert bool(((ids == 0) | ((ids >= 2) & (ids < 8))).all())
+        if refined is not None:
+            assert refined.shape == (1, 32, 48) and refined.dtype == torch.float32
+            assert float(refined.min()) >= 0 and bool((refined == refined.round()).all())
+            # by hand: the same crops through stage 2 in one batch
+            rgb_crop, mask_crop, rois, depth_crop = td.crop_rois(rgb, out_label.clone(), depth, crop_size=16)
+            labels_crop, _ = stage2.label_maps([{"image": rgb_crop, "depth": depth_crop}], score=0.7, **kw)
+            assert labels_crop.shape == (rgb_crop.shape[0], 16, 16)
+            by_hand, _ = td.match_label_crop(out_label, labels_crop, mask_crop, rois, depth_crop)
+            assert float((by_hand == refined).float().mean()) > 0.999
+        else:
+            assert int((out_label > 0).sum()) == 0
+
+
 # ----------------------------------------------------------------------------- two-stage glue (SURVEY §8 f2)
 def _check_two_stage(td, rgb, labels, depth, S, crop_seed, want=None):
     """the device functions against the oracle (or stored reference outputs) on one scene; returns the outputs."""

@@ -57,3 +57,42 @@ def test_confident_instances_and_combine_masks(golden):
             assert torch.equal(tu.combine_masks(conf).double(), g[f"labelmap_{tag}_{b}"])
     empty = tu.get_confident_instances(inst, score=2.0)
     assert empty["scores"].numel() == 0 and float(tu.combine_masks(empty).abs().sum()) == 0
+
+
+class _FakeStage:
+    """stands in for a META_ARCH wrapper: ``label_maps`` returns a prepared label map."""
+
+    def __init__(self, fn):
+        self.fn, self.calls = fn, []
+
+    def label_maps(self, batched_inputs, **kw):
+        self.calls.append((batched_inputs, kw))
+        return self.fn(batched_inputs), {}
+
+
+def test_two_stage_orchestration(td, golden):
+    """fcn/test_utils.two_stage_label_maps (inference part of test_sample_crop, lib/fcn/test_utils.py:245-420):
+    with the two networks replaced by the label maps the golden run used, the refined label map must equal the
+    reference's; stage 2 is called ONCE with every crop in the batch."""
+    from scenes import two_stage_crop_labels
+    from unseenobjectswithmeanshift_b200.fcn import test_utils as tu
+    g, _ = golden("two_stage")
+    S = int(g["crop_size"])
+    for tag in "dn":
+        depth = g["d_depth"] if tag == "d" else None
+        stage1 = _FakeStage(lambda inputs: g[tag + "_labels"].clone())
+        stage2 = _FakeStage(lambda inputs: two_stage_crop_labels(g[tag + "_mask_crops"], 7))
+        out_label, refined = tu.two_stage_label_maps(stage1, stage2, g[tag + "_rgb"], depth, crop_size=S,
+                                                     confident_score=0.6)
+        assert torch.equal(out_label, g["d_filtered_05"] if tag == "d" else g["n_labels"])
+        assert torch.equal(refined, g[tag + "_refined"])
+        assert len(stage2.calls) == 1 and stage2.calls[0][0][0]["image"].shape == g[tag + "_rgb_crops"].shape
+        assert ("depth" in stage2.calls[0][0][0]) == (depth is not None)
+        assert stage1.calls[0][1]["score"] == 0.6 and stage1.calls[0][0][0]["image"].dim() == 3
+    # no crop network: first-stage result only
+    out_label, refined = tu.two_stage_label_maps(_FakeStage(lambda i: g["n_labels"].clone()), None, g["n_rgb"][0])
+    assert refined is None and torch.equal(out_label, g["n_labels"])
+    # nothing segmented: no second stage call
+    stage2 = _FakeStage(lambda i: None)
+    out_label, refined = tu.two_stage_label_maps(_FakeStage(lambda i: torch.zeros(1, 96, 128)), stage2, g["n_rgb"])
+    assert refined is None and not stage2.calls

@@ -45,3 +45,30 @@ def label_map_from_outputs(pred_logits, pred_masks, image_size, test_topk_per_im
                                                    num_class=num_class, score=score, low_threshold=low_threshold)
     return label_map, {"pred_boxes": boxes, "scores": scores, "pred_classes": cls, "query_index": query,
                        "instance_label": inst_label}
+
+
+def two_stage_label_maps(model, model_crop, image, depth=None, *, topk=False, confident_score=0.7,
+                         low_threshold=0.4, depth_threshold=0.5, crop_size=224):
+    """The inference part of ``test_sample_crop`` (lib/fcn/test_utils.py:245-420) for one frame, on the device:
+    stage 1 label map -> depth filter -> padded ROI crops -> stage 2 on ALL crops in one batched forward (the
+    reference calls its crop predictor once per object, :397-405) -> overlap test, ordering and paste-back.
+    ``model`` / ``model_crop``: META_ARCH wrappers of this package (``label_maps``); image [1,3,H,W] (or [3,H,W]),
+    depth [1,3,H,W] or None. Returns (out_label [1,H,W], out_label_refined [1,H,W] or None)."""
+    from . import test_dataset as td
+    if image.dim() == 3:
+        image = image.unsqueeze(0)
+    if depth is not None and depth.dim() == 3:
+        depth = depth.unsqueeze(0)
+    sample = {"image": image[0]} if depth is None else {"image": image[0], "depth": depth[0]}
+    out_label, _ = model.label_maps([sample], topk=topk, score=confident_score, low_threshold=low_threshold)
+    if depth is not None:
+        out_label = td.filter_labels_depth(out_label, depth, depth_threshold)
+    refined = None
+    if model_crop is not None:
+        rgb_crop, out_label_crop, rois, depth_crop = td.crop_rois(image, out_label.clone(), depth, crop_size=crop_size)
+        if rgb_crop.shape[0] > 0:
+            crops = {"image": rgb_crop} if depth_crop is None else {"image": rgb_crop, "depth": depth_crop}
+            labels_crop, _ = model_crop.label_maps([crops], topk=topk, score=confident_score,
+                                                   low_threshold=low_threshold)
+            refined, _ = td.match_label_crop(out_label, labels_crop, out_label_crop, rois, depth_crop)
+    return out_label, refined

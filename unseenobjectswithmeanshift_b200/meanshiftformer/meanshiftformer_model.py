@@ -76,6 +76,24 @@ class _MetaArchBase(nn.Module):
             raise NotImplementedError("training (criterion / matcher / embedding loss) is row f4 of SURVEY.md 8: "
                                       "call .eval() and run under torch.no_grad()")
 
+    def forward(self, batched_inputs):
+        """eval branch of the reference's forward: [{"instances": ...}] per image."""
+        self._check_mode()
+        return self._eval_tail(*self._head_outputs(batched_inputs))
+
+    def label_maps(self, batched_inputs, topk=False, score=0.7, low_threshold=0.4):
+        """What the UOIS test scripts do with the instances (lib/fcn/test_utils.py:35-52, 93-112, 216-242:
+        get_confident_instances + combine_masks), fused and batched: -> (label map fp32 [B,H,W] on the device,
+        per-instance fields). The full-resolution masks are never written."""
+        from ..fcn import test_utils as tu
+        self._check_mode()
+        outputs, _, padded_size, sizes = self._head_outputs(batched_inputs)
+        if any(tuple(sz) != tuple(padded_size) for sz in sizes):
+            raise NotImplementedError("images of different sizes in one batch: crop the label maps yourself")
+        return tu.label_map_from_outputs(outputs["pred_logits"], outputs["pred_masks"], padded_size,
+                                         self.test_topk_per_image, topk=topk, score=score,
+                                         num_class=self.sem_seg_head.num_classes, low_threshold=low_threshold)
+
     def _eval_tail(self, outputs, batched_inputs, padded_size, image_sizes):
         if self.semantic_on or self.panoptic_on or not self.instance_on:
             raise NotImplementedError("only the instance output (MODEL.MASK_FORMER.TEST.INSTANCE_ON) is implemented")
@@ -112,13 +130,12 @@ class MeanShiftMaskFormer(_MetaArchBase):
     def from_config(cls, cfg):
         return _from_config(cfg, pretrained=False)
 
-    def forward(self, batched_inputs):
-        self._check_mode()
+    def _head_outputs(self, batched_inputs):
         images = [(x["image"].to(self.device) - self.pixel_mean) / self.pixel_std for x in batched_inputs]
         batch, sizes = _batch_images(images, self.size_divisibility)
         features = self.backbone(batch)
         outputs, _ = self.sem_seg_head(features, batch.shape[-2], batch.shape[-1])
-        return self._eval_tail(outputs, batched_inputs, tuple(batch.shape[-2:]), sizes)
+        return outputs, batched_inputs, tuple(batch.shape[-2:]), sizes
 
 
 @META_ARCH_REGISTRY.register()
@@ -158,8 +175,7 @@ class PretrainedMeanShiftMaskFormer(_MetaArchBase):
             return _batch_images(first.to(self.device), 0)
         return _batch_images([x[key].to(self.device) for x in batched_inputs], self.size_divisibility)
 
-    def forward(self, batched_inputs):
-        self._check_mode()
+    def _head_outputs(self, batched_inputs):
         batch, sizes = self._gather(batched_inputs, "image")
         if self.use_other_backbone:
             features = self.pretrained_backbone(batch)
@@ -172,7 +188,7 @@ class PretrainedMeanShiftMaskFormer(_MetaArchBase):
             features = {"res5": F.normalize(emb, p=2, dim=1)}
         outputs, _ = self.sem_seg_head(features, batch.shape[-2], batch.shape[-1])
         inputs = batched_inputs if len(batched_inputs) == len(sizes) else [{} for _ in sizes]
-        return self._eval_tail(outputs, inputs, tuple(batch.shape[-2:]), sizes)
+        return outputs, inputs, tuple(batch.shape[-2:]), sizes
 
 
 def _from_config(cfg, pretrained):
