@@ -140,3 +140,17 @@ def test_meta_arch_registry_and_image_batching():
     assert float(batch[1, :, :20, :50].min()) == 2 and float(batch[1, :, :, 50:].abs().sum()) == 0
     same, sizes = _batch_images([a, a], 0)
     assert same.shape == (2, 3, 30, 40) and sizes == [(30, 40)] * 2
+
+
+def test_header_is_plain_c(tmp_path):
+    """the boundary is a C ABI: include/msmformer_b200.h must compile as C99 with nothing but libc headers."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "t.c"
+    src.write_text('#include "msmformer_b200.h"\nint main(void) { return msm_abi_version() == MSM_ABI_VERSION ? 0 : 1; }\n')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                        "-I", os.path.join(root, "include"), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
