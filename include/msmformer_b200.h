@@ -57,6 +57,9 @@ int msm_device_arch(void);
  * ---------------------------------------------------------------------------------------------- */
 #define MSM_VMF_NORMALIZE_Q 1
 #define MSM_VMF_NORMALIZE_K 2
+/* training: `den` is [2][G][Nq]; the second plane receives |softmax . v| (the norm removed by the final L2
+ * normalisation), which msm_vmf_attention_bwd needs */
+#define MSM_VMF_SAVE_NORM 4
 
 size_t msm_vmf_attention_workspace_bytes(int batch, int heads, int Nq, int Ns, int hd);
 
@@ -78,6 +81,27 @@ int msm_vmf_attention_weights(const float* q, int64_t q_sb, int64_t q_sh, int64_
                               const uint32_t* blocked_bits, int words_per_row, const int32_t* row_open,
                               const float* add_mask, float* attn,
                               int batch, int heads, int Nq, int Ns, int hd, float kappa, int flags, void* stream);
+
+/* Backward of the attention core (training). The reference differentiates
+ * hypersphere_attention (attention_util.py:64-82) with torch.autograd; this entry point recomputes the weights
+ * tile by tile instead of saving [G][Nq][Ns] tensors. `out` is the forward result, `den` the [2][G][Nq] buffer the
+ * forward filled under MSM_VMF_SAVE_NORM, masks / flags / kappa exactly as passed to the forward. grad_q / grad_k /
+ * grad_v are addressed like q / k / v, each with its own strides. Nq <= 128, hd <= 64. Deterministic. */
+size_t msm_vmf_attention_bwd_workspace_bytes(int batch, int heads, int Nq, int Ns, int hd);
+
+int msm_vmf_attention_bwd(const float* q, int64_t q_sb, int64_t q_sh, int64_t q_sl,
+                          const float* k, int64_t k_sb, int64_t k_sh, int64_t k_sl,
+                          const float* v, int64_t v_sb, int64_t v_sh, int64_t v_sl,
+                          const float* out, int64_t o_sb, int64_t o_sh, int64_t o_sl,
+                          const float* grad_out, int64_t go_sb, int64_t go_sh, int64_t go_sl,
+                          const float* den,
+                          float* grad_q, int64_t gq_sb, int64_t gq_sh, int64_t gq_sl,
+                          float* grad_k, int64_t gk_sb, int64_t gk_sh, int64_t gk_sl,
+                          float* grad_v, int64_t gv_sb, int64_t gv_sh, int64_t gv_sl,
+                          const uint32_t* blocked_bits, int words_per_row, const int32_t* row_open,
+                          const float* add_mask,
+                          int batch, int heads, int Nq, int Ns, int hd, float kappa, int flags,
+                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Mask head.

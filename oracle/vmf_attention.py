@@ -68,3 +68,36 @@ def meanshift_attention(query, key, value, in_w, in_b, out_w, out_b, num_heads, 
     o = o.transpose(0, 1).contiguous().view(L, N, E)
     o = F.linear(o, out_w, out_b)  # :425
     return o, attn.view(N, num_heads, L, S).sum(dim=1) / num_heads  # :427-430
+
+
+def hypersphere_attention_backward(q, k, v, attn_mask, kappa, grad_out):
+    """Gradient of hypersphere_attention (attention_util.py:64-82) wrt q, k, v, written out by hand (no autograd):
+    the statement the CUDA backward (csrc/vmf_attention_bwd.cu) follows. Pinned on torch.autograd run through the
+    reference's own function (tests/golden/hypersphere_attention_bwd.npz).
+
+    With qn = unit(q), kn = unit(k), s = kappa qn kn^T + mask, p = softmax(s), o = p v, out = unit(o):
+      g_o  = (grad_out - out <out, grad_out>) / |o|            (F.normalize, norm above its eps)
+      g_v  = p^T g_o
+      g_s  = p * (g_o v^T - <g_o, o>)                           (softmax; <g_o, o> = 0 up to rounding as g_o _|_ out)
+      g_qn = kappa g_s kn,   g_kn = kappa g_s^T qn
+      g_q  = (g_qn - qn <qn, g_qn>) / |q|,   g_k likewise.
+    Returns (g_q, g_k, g_v)."""
+    qnorm = q.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+    knorm = k.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+    qn, kn = q / qnorm, k / knorm
+    s = kappa * torch.bmm(qn, kn.transpose(-2, -1))
+    if attn_mask is not None:
+        s = s + attn_mask
+    p = F.softmax(s, dim=-1)
+    o = torch.bmm(p, v)
+    onorm = o.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+    out = o / onorm
+    g_o = (grad_out - out * (out * grad_out).sum(-1, keepdim=True)) / onorm
+    g_v = torch.bmm(p.transpose(-2, -1), g_o)
+    delta = (g_o * o).sum(-1, keepdim=True)
+    g_s = p * (torch.bmm(g_o, v.transpose(-2, -1)) - delta)
+    g_qn = kappa * torch.bmm(g_s, kn)
+    g_kn = kappa * torch.bmm(g_s.transpose(-2, -1), qn)
+    g_q = (g_qn - qn * (qn * g_qn).sum(-1, keepdim=True)) / qnorm
+    g_k = (g_kn - kn * (kn * g_kn).sum(-1, keepdim=True)) / knorm
+    return g_q, g_k, g_v

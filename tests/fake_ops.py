@@ -78,3 +78,76 @@ def paste_crops(labels_crop, new_label, order, rois, height, width):
         view = refined[y0:y1 + 1, x0:x1 + 1]
         view[back != 0] = back[back != 0]
     return refined
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Stand-ins for the attention / mask-head entry points (contract of msm_vmf_attention_fwd / _bwd, msm_mask_logits,
+# msm_mask_to_attn_bits in include/msmformer_b200.h), used to exercise the AUTOGRAD WIRING of ops.py and of the
+# decoder's training path on CPU. The backward stand-in is written from the saved (den, |o|) planes like the kernel,
+# not with torch.autograd.
+def _unpack_bits(bits, row_open, Ns):
+    B, Q, words = bits.shape
+    sh = torch.arange(32, dtype=torch.int64)
+    blocked = ((bits.long().unsqueeze(-1) >> sh) & 1).bool().reshape(B, Q, words * 32)[..., :Ns]
+    if row_open is not None:
+        blocked = blocked & (row_open != 0).unsqueeze(-1)
+    return blocked
+
+
+def _weights(q, k, blocked_bits, row_open, add_mask, kappa, normalize_q, normalize_k):
+    B, H, Nq, _ = q.shape
+    Ns = k.shape[2]
+    qn = F.normalize(q, dim=-1, eps=1e-12) if normalize_q else q
+    kn = F.normalize(k, dim=-1, eps=1e-12) if normalize_k else k
+    e = kappa * (qn @ kn.transpose(-1, -2)) - kappa
+    if add_mask is not None:
+        e = e + add_mask.view(B, H, Nq, Ns)
+    w = torch.exp(e)
+    if blocked_bits is not None:
+        w = w.masked_fill(_unpack_bits(blocked_bits, row_open, Ns).unsqueeze(1), 0.0)
+    return qn, kn, w
+
+
+def _bhld_buffer(B, H, L, hd, dtype):
+    return torch.empty(B, L, H, hd, dtype=dtype).permute(0, 2, 1, 3)
+
+
+def vmf_attention(q, k, v, *, blocked_bits=None, row_open=None, add_mask=None, kappa=30.0, normalize_q=True,
+                  normalize_k=True, out=None, return_den=False, save_norm=False):
+    B, H, Nq, hd = q.shape
+    _, _, w = _weights(q, k, blocked_bits, row_open, add_mask, kappa, normalize_q, normalize_k)
+    den = w.sum(-1)
+    o = (w @ v) / den.unsqueeze(-1)
+    norm = o.norm(dim=-1)
+    if out is None:
+        out = _bhld_buffer(B, H, Nq, hd, q.dtype)
+    out.copy_(o / norm.clamp_min(1e-12).unsqueeze(-1))
+    if not return_den:
+        return out
+    den = den.reshape(B * H, Nq)
+    return out, (torch.stack([den, norm.reshape(B * H, Nq)]) if save_norm else den)
+
+
+def vmf_attention_bwd(q, k, v, out, grad_out, den, *, blocked_bits=None, row_open=None, add_mask=None, kappa=30.0,
+                      normalize_q=True, normalize_k=True):
+    B, H, Nq, hd = q.shape
+    Ns = k.shape[2]
+    assert tuple(den.shape) == (2, B * H, Nq)
+    qn, kn, w = _weights(q, k, blocked_bits, row_open, add_mask, kappa, normalize_q, normalize_k)
+    p = w / den[0].view(B, H, Nq, 1)
+    onorm = den[1].view(B, H, Nq, 1).clamp_min(1e-12)
+    g_o = (grad_out - out * (out * grad_out).sum(-1, keepdim=True)) / onorm
+    delta = (g_o * out).sum(-1, keepdim=True) * onorm
+    g_v = p.transpose(-1, -2) @ g_o
+    g_s = kappa * p * (g_o @ v.transpose(-1, -2) - delta)
+    g_q, g_k = g_s @ kn, g_s.transpose(-1, -2) @ qn
+    if normalize_q:
+        g_q = (g_q - qn * (qn * g_q).sum(-1, keepdim=True)) / q.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+    if normalize_k:
+        g_k = (g_k - kn * (kn * g_k).sum(-1, keepdim=True)) / k.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+    res = []
+    for g, L in ((g_q, Nq), (g_k, Ns), (g_v, Ns)):
+        buf = _bhld_buffer(B, H, L, hd, q.dtype)
+        buf.copy_(g)
+        res.append(buf)
+    return tuple(res)

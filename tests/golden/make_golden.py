@@ -59,6 +59,25 @@ def gen_hypersphere_attention():
          kappa_default=np.float32(au.KAPPA))
 
 
+def gen_hypersphere_attention_bwd():
+    """Gradients of the reference's own hypersphere_attention (attention_util.py:30-82) by torch.autograd, masked and
+    unmasked, for a seeded grad_output: pins the hand-written backward of the oracle (row f4 of SURVEY.md 8)."""
+    au = ref_shim.ref("modeling.transformer_decoder.attention_util")
+    torch.manual_seed(20)
+    BH, Q, S, E = 4, 10, 70, 8
+    q, k, v = (torch.randn(BH, n, E).requires_grad_() for n in (Q, S, S))
+    blocked = torch.rand(BH, Q, S) < 0.5
+    blocked[:, :, 0] = False
+    fmask = torch.zeros(BH, Q, S).masked_fill_(blocked, float("-inf"))
+    gout = torch.randn(BH, Q, E)
+    arrays = dict(q=q, k=k, v=v, blocked=blocked, grad_out=gout)
+    for tag, mask, kappa in (("masked", fmask, au.KAPPA), ("nomask", None, au.KAPPA), ("kappa10", None, 10.0)):
+        out, _ = au.hypersphere_attention(q, k, v, mask, 0.0, kappa)
+        gq, gk, gv = torch.autograd.grad(out, (q, k, v), gout)
+        arrays.update({f"out_{tag}": out, f"gq_{tag}": gq, f"gk_{tag}": gk, f"gv_{tag}": gv})
+    save("hypersphere_attention_bwd", **arrays)
+
+
 def gen_meanshift_attention():
     au = ref_shim.ref("modeling.transformer_decoder.attention_util")
     torch.manual_seed(1)
@@ -429,6 +448,7 @@ def gen_two_stage():
 
 if __name__ == "__main__":
     gen_hypersphere_attention()
+    gen_hypersphere_attention_bwd()
     gen_meanshift_attention()
     gen_decoder_multiscale()
     gen_decoder_pretrained()

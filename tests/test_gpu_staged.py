@@ -1,0 +1,96 @@
+"""STAGED GPU tests (marker ``gpu_staged``, not ``gpu``): parity tests of the training-side kernels (SURVEY.md
+section 8, row f4) that were written after this round's GPU minutes were spent. The kernels compile for sm_100a and
+their host wiring is covered on CPU (tests/test_training_wiring.py); they have NOT run on a B200 yet. First GPU call
+of the next round: ``python -m pytest tests -m gpu_staged -x -q``; re-mark as ``gpu`` once green."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu_staged
+
+
+@pytest.fixture(scope="module")
+def msm():
+    from unseenobjectswithmeanshift_b200 import ops
+    return ops
+
+
+def _pack_bits(blocked):
+    B, Q, S = blocked.shape
+    words = (S + 31) // 32
+    pad = torch.zeros(B, Q, words * 32, dtype=torch.bool, device=blocked.device)
+    pad[..., :S] = blocked
+    v = (pad.view(B, Q, words, 32).long() << torch.arange(32, device=blocked.device)).sum(-1)
+    return torch.where(v >= 2 ** 31, v - 2 ** 32, v).to(torch.int32).contiguous()
+
+
+def _close(got, want, rel):
+    err = (got.double() - want.double()).abs().max().item()
+    scale = max(want.abs().max().item(), 1e-30)
+    assert err <= rel * scale, f"max abs err {err:.3e} vs peak {scale:.3e}"
+
+
+def test_vmf_attention_bwd_golden(msm, golden):
+    """Against torch.autograd through the REFERENCE's hypersphere_attention (tests/golden/make_golden.py)."""
+    g, _ = golden("hypersphere_attention_bwd")
+    q, k, v = (g[n].cuda().unsqueeze(1) for n in "qkv")   # [G,1,L,E]: batch = G, one head (E = 8: padded head dim)
+    gout = g["grad_out"].cuda().unsqueeze(1)
+    fmask = torch.zeros(g["blocked"].shape).masked_fill_(g["blocked"], float("-inf")).cuda()
+    for tag, mask, kappa in (("masked", fmask, 30.0), ("nomask", None, 30.0), ("kappa10", None, 10.0)):
+        out, den = msm.vmf_attention(q, k, v, add_mask=mask, kappa=kappa, return_den=True, save_norm=True)
+        _close(out.squeeze(1).cpu(), g[f"out_{tag}"], 2e-5)
+        gq, gk, gv = msm.vmf_attention_bwd(q, k, v, out, gout, den, add_mask=mask, kappa=kappa)
+        for t, name in ((gq, "gq"), (gk, "gk"), (gv, "gv")):
+            _close(t.squeeze(1).cpu(), g[f"{name}_{tag}"], 1e-4)   # fp32: 1e-4 of the peak gradient
+
+
+@pytest.mark.parametrize("B,H,Q,S,hd,masked", [(1, 1, 100, 64, 32, False), (2, 8, 100, 300, 32, True),
+                                               (2, 8, 100, 1200, 32, True), (1, 2, 37, 777, 64, True),
+                                               (1, 4, 128, 130, 16, False), (8, 8, 100, 4800, 32, True)])
+def test_vmf_attention_autograd_vs_fp64(msm, B, H, Q, S, hd, masked):
+    """VmfAttentionFunction on the decoder's strided head views (seq-first projections, fused k|v buffer) against
+    fp64 torch.autograd of the same expression; the last case is the training config's largest level."""
+    dev = torch.device("cuda")
+    gen = torch.Generator(device="cuda").manual_seed(S + hd)
+    C = H * hd
+    q = torch.randn(B, Q, C, device=dev, generator=gen, requires_grad=True)
+    kv = torch.randn(B, S, 2 * C, device=dev, generator=gen, requires_grad=True)
+    heads = lambda t: t.unflatten(-1, (H, hd)).permute(0, 2, 1, 3)
+    bits = ro = eff = None
+    if masked:
+        blocked = torch.rand(B, Q, S, device=dev, generator=gen) < 0.5
+        blocked[:, 3] = True
+        ro = (~blocked).any(-1).to(torch.int32).contiguous()
+        bits = _pack_bits(blocked)
+        eff = (blocked & (ro != 0).unsqueeze(-1)).unsqueeze(1)
+    out = msm.vmf_attention_autograd(heads(q), heads(kv[..., :C]), heads(kv[..., C:]), blocked_bits=bits, row_open=ro)
+    gout = torch.randn(B, H, Q, hd, device=dev, generator=gen)
+    gq, gkv = torch.autograd.grad(out, (q, kv), gout)
+
+    q2, kv2 = q.detach().double().requires_grad_(), kv.detach().double().requires_grad_()
+    qn = torch.nn.functional.normalize(heads(q2), dim=-1, eps=1e-12)
+    kn = torch.nn.functional.normalize(heads(kv2[..., :C]), dim=-1, eps=1e-12)
+    s = 30.0 * qn @ kn.transpose(-1, -2)
+    if eff is not None:
+        s = s.masked_fill(eff, float("-inf"))
+    ref = torch.nn.functional.normalize(torch.softmax(s, -1) @ heads(kv2[..., C:]), dim=-1, eps=1e-12)
+    rq, rkv = torch.autograd.grad(ref, (q2, kv2), gout.double())
+    _close(out, ref, 2e-5)
+    _close(gq, rq, 1e-4)
+    _close(gkv[..., :C], rkv[..., :C], 1e-4)
+    _close(gkv[..., C:], rkv[..., C:], 1e-4)
+    # deterministic: a second backward gives the same bits
+    out2 = msm.vmf_attention_autograd(heads(q), heads(kv[..., :C]), heads(kv[..., C:]), blocked_bits=bits, row_open=ro)
+    gq2, gkv2 = torch.autograd.grad(out2, (q, kv), gout)
+    assert torch.equal(gq, gq2) and torch.equal(gkv, gkv2)
+
+
+def test_vmf_attention_bwd_errors_are_loud(msm):
+    dev = torch.device("cuda")
+    q = torch.randn(1, 1, 200, 32, device=dev)   # more than 128 queries: unsupported by the backward
+    k = torch.randn(1, 1, 64, 32, device=dev)
+    out, den = msm.vmf_attention(q, k, k, return_den=True, save_norm=True)
+    with pytest.raises(RuntimeError, match="at most 128 queries"):
+        msm.vmf_attention_bwd(q, k, k, out, torch.ones_like(out), den)
+    with pytest.raises(ValueError, match="save_norm"):
+        msm.vmf_attention_bwd(q[:, :, :100], k, k, out[:, :, :100].contiguous(), torch.ones(1, 1, 100, 32, device=dev),
+                              den[0])

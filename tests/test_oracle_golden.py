@@ -33,6 +33,22 @@ def test_hypersphere_attention(golden):
     assert float(g["attn_masked"][g["blocked"]].abs().max()) == 0.0
 
 
+def test_hypersphere_attention_backward(golden):
+    """The hand-written backward of the oracle against torch.autograd through the reference's function."""
+    g, _ = golden("hypersphere_attention_bwd")
+    for tag, mask, kappa in (("masked", _additive(g["blocked"]), 30.0), ("nomask", None, 30.0), ("kappa10", None, 10.0)):
+        out, _ = ovmf.hypersphere_attention(g["q"], g["k"], g["v"], mask, kappa)
+        torch.testing.assert_close(out, g[f"out_{tag}"], **TOL)
+        gq, gk, gv = ovmf.hypersphere_attention_backward(g["q"], g["k"], g["v"], mask, kappa, g["grad_out"])
+        for got, name in ((gq, "gq"), (gk, "gk"), (gv, "gv")):
+            want = g[f"{name}_{tag}"]
+            torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-6 * max(1.0, float(want.abs().max())))
+    # blocked keys receive no gradient through their value rows
+    gv = g["gv_masked"]
+    all_blocked = g["blocked"].all(dim=1)  # [BH, S]: keys no query of the problem may attend
+    assert float(gv[all_blocked].abs().max() if all_blocked.any() else 0.0) == 0.0
+
+
 def test_meanshift_attention(golden):
     g, sd = golden("meanshift_attention")
     H = int(g["num_heads"])

@@ -23,6 +23,9 @@ SIGNATURES = {
                                    _P, _I, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P, _Z, _P]),
     "msm_vmf_attention_weights": (_I, [_P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _I, _P, _P, _P,
                                        _I, _I, _I, _I, _I, _F, _I, _P]),
+    "msm_vmf_attention_bwd_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
+    "msm_vmf_attention_bwd": (_I, [_P, _L, _L, _L] * 5 + [_P] + [_P, _L, _L, _L] * 3 +
+                              [_P, _I, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P, _Z, _P]),
     "msm_mask_logits": (_I, [_P, _P, _P, _I, _I, _I, _L, _P]),
     "msm_mask_to_attn_bits": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "msm_linear_weight_bytes": (_Z, [_I, _I]),

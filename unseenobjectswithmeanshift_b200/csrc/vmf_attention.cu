@@ -223,7 +223,8 @@ __global__ void __launch_bounds__(kThreads) vmf_partial_kernel(const VmfParams P
 // One warp per (g, query): fixed-order sum over key splits, divide, L2-normalise (eps 1e-12).
 __global__ void vmf_finalize_kernel(const float* __restrict__ part_acc, const float* __restrict__ part_den,
                                     float* __restrict__ out, int64_t o_sb, int64_t o_sh, int64_t o_sl,
-                                    float* __restrict__ den_out, int G, int heads, int Nq, int hd, int HD, int nsplit) {
+                                    float* __restrict__ den_out, float* __restrict__ norm_out, int G, int heads, int Nq,
+                                    int hd, int HD, int nsplit) {
   pdl_trigger();
   pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -254,6 +255,7 @@ __global__ void vmf_finalize_kernel(const float* __restrict__ part_acc, const fl
     if (d < hd) op[d] = o[r] * inv;
   }
   if (den_out != nullptr && lane == 0) den_out[warp] = den;
+  if (norm_out != nullptr && lane == 0) norm_out[warp] = sqrtf(ss);  // |p.v| before the L2 normalisation (backward)
 }
 
 // Completeness path (the decoder discards these): attention weights for one (g, query) per block.
@@ -291,13 +293,15 @@ __global__ void vmf_weights_kernel(const float* __restrict__ q, int64_t q_sb, in
 }
 
 static int launch_finalize(const float* part_acc, const float* part_den, float* out, int64_t o_sb, int64_t o_sh,
-                           int64_t o_sl, float* den, int G, int heads, int Nq, int hd, int HD, int nsplit,
+                           int64_t o_sl, float* den, int flags, int G, int heads, int Nq, int hd, int HD, int nsplit,
                            cudaStream_t st) {
+  // MSM_VMF_SAVE_NORM: `den` has a second [G][Nq] plane that receives the norms of the un-normalised outputs
+  float* norm = (den != nullptr && (flags & MSM_VMF_SAVE_NORM)) ? den + (size_t)G * Nq : nullptr;
   const int warps = G * Nq;
   const int threads = 256;
   const int blocks = (warps * 32 + threads - 1) / threads;
   MSM_CUDA(launch_pdl(vmf_finalize_kernel, dim3(blocks), dim3(threads), 0, st, part_acc, part_den, out, o_sb, o_sh, o_sl,
-                      den, G, heads, Nq, hd, HD, nsplit));
+                      den, norm, G, heads, Nq, hd, HD, nsplit));
   return check_launch("vmf_finalize_kernel");
 }
 
@@ -365,7 +369,7 @@ int vmf_attention_simt(const float* q, int64_t q_sb, int64_t q_sh, int64_t q_sl,
     default: set_error("head dim %d not supported (max 128)", hd); return MSM_E_UNSUPPORTED;
   }
   if (rc) return rc;
-  return launch_finalize(P.part_acc, P.part_den, out, o_sb, o_sh, o_sl, den, G, heads, Nq, hd, HD, P.nsplit, st);
+  return launch_finalize(P.part_acc, P.part_den, out, o_sb, o_sh, o_sl, den, flags, G, heads, Nq, hd, HD, P.nsplit, st);
 }
 
 // tensor-core path (vmf_attention_tc.cu)
@@ -412,7 +416,7 @@ int vmf_attention(const float* q, int64_t q_sb, int64_t q_sh, int64_t q_sl, cons
                                             row_open, batch, heads, Nq, Ns, hd, kappa, flags, part_acc, part_den,
                                             &nsplit, st);
     if (rc) return rc;
-    return launch_finalize(part_acc, part_den, out, o_sb, o_sh, o_sl, den, G, heads, Nq, hd, hd, nsplit, st);
+    return launch_finalize(part_acc, part_den, out, o_sb, o_sh, o_sl, den, flags, G, heads, Nq, hd, hd, nsplit, st);
   }
   return vmf_attention_simt(q, q_sb, q_sh, q_sl, k, k_sb, k_sh, k_sl, v, v_sb, v_sh, v_sl, out, o_sb, o_sh, o_sl, den,
                             bits, wpr, row_open, add_mask, batch, heads, Nq, Ns, hd, kappa, flags, workspace,

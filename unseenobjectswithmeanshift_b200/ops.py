@@ -40,12 +40,13 @@ def _bhld(t, name):
 
 
 def vmf_attention(q, k, v, *, blocked_bits=None, row_open=None, add_mask=None, kappa=KAPPA,
-                  normalize_q=True, normalize_k=True, out=None, return_den=False):
+                  normalize_q=True, normalize_k=True, out=None, return_den=False, save_norm=False):
     """vMF attention core on [B, H, L, hd] *views* (any batch/head/row strides, see msm_vmf_attention_fwd).
 
     blocked_bits int32 [B, Nq, ceil(Ns/32)] (bit set = blocked), row_open int32 [B, Nq];
     or add_mask float [B*H, Nq, Ns]. Returns out [B, H, Nq, hd] view of a [B, Nq, H*hd] buffer
-    (and den [B*H, Nq] if asked)."""
+    (and den [B*H, Nq] if asked; with ``save_norm`` den is [2, B*H, Nq]: denominators, then |softmax . v| - what
+    vmf_attention_bwd needs)."""
     q, q_sb, q_sh, q_sl = _bhld(q, "q")
     k, k_sb, k_sh, k_sl = _bhld(k, "k")
     v, v_sb, v_sh, v_sl = _bhld(v, "v")
@@ -56,7 +57,10 @@ def vmf_attention(q, k, v, *, blocked_bits=None, row_open=None, add_mask=None, k
     if out is None:
         out = torch.empty(B, Nq, H, hd, device=q.device, dtype=torch.float32).permute(0, 2, 1, 3)
     out, o_sb, o_sh, o_sl = _bhld(out, "out")
-    den = torch.empty(B * H, Nq, device=q.device, dtype=torch.float32) if return_den else None
+    if save_norm and not return_den:
+        raise ValueError("save_norm needs return_den=True")
+    den = torch.empty((2, B * H, Nq) if save_norm else (B * H, Nq), device=q.device,
+                      dtype=torch.float32) if return_den else None
     wpr = 0
     if blocked_bits is not None:
         _require(blocked_bits, "blocked_bits", torch.int32)
@@ -72,7 +76,7 @@ def vmf_attention(q, k, v, *, blocked_bits=None, row_open=None, add_mask=None, k
     L = _lib.lib()
     ws_bytes = L.msm_vmf_attention_workspace_bytes(B, H, Nq, Ns, hd)
     ws = torch.empty(ws_bytes, device=q.device, dtype=torch.uint8)
-    flags = (1 if normalize_q else 0) | (2 if normalize_k else 0)
+    flags = (1 if normalize_q else 0) | (2 if normalize_k else 0) | (4 if save_norm else 0)
     rc = L.msm_vmf_attention_fwd(
         q.data_ptr(), q_sb, q_sh, q_sl, k.data_ptr(), k_sb, k_sh, k_sl, v.data_ptr(), v_sb, v_sh, v_sl,
         out.data_ptr(), o_sb, o_sh, o_sl, den.data_ptr() if den is not None else None,
@@ -82,6 +86,97 @@ def vmf_attention(q, k, v, *, blocked_bits=None, row_open=None, add_mask=None, k
         B, H, Nq, Ns, hd, float(kappa), flags, ws.data_ptr(), ws_bytes, _stream())
     check(rc, "msm_vmf_attention_fwd")
     return (out, den) if return_den else out
+
+
+def vmf_attention_bwd(q, k, v, out, grad_out, den, *, blocked_bits=None, row_open=None, add_mask=None, kappa=KAPPA,
+                      normalize_q=True, normalize_k=True):
+    """Gradients of the vMF attention core wrt q, k, v (msm_vmf_attention_bwd): [B, H, L, hd] views as in
+    vmf_attention, ``out`` / ``den`` from the forward called with return_den=True, save_norm=True and the same
+    masks, kappa and flags. Returns (grad_q, grad_k, grad_v) shaped like q, k, v ([B, H, L, hd] views of
+    [B, L, H*hd] buffers)."""
+    q, q_sb, q_sh, q_sl = _bhld(q, "q")
+    k, k_sb, k_sh, k_sl = _bhld(k, "k")
+    v, v_sb, v_sh, v_sl = _bhld(v, "v")
+    out, o_sb, o_sh, o_sl = _bhld(out, "out")
+    if grad_out.dim() == 4 and grad_out.shape[3] > 1 and grad_out.stride(3) != 1:
+        grad_out = grad_out.contiguous()
+    grad_out, go_sb, go_sh, go_sl = _bhld(grad_out, "grad_out")
+    B, H, Nq, hd = q.shape
+    Ns = k.shape[2]
+    if k.shape != (B, H, Ns, hd) or v.shape != (B, H, Ns, hd) or out.shape != q.shape or grad_out.shape != q.shape:
+        raise ValueError(f"shape mismatch: q {tuple(q.shape)} k {tuple(k.shape)} v {tuple(v.shape)} "
+                         f"out {tuple(out.shape)} grad_out {tuple(grad_out.shape)}")
+    _require(den, "den")
+    if tuple(den.shape) != (2, B * H, Nq) or not den.is_contiguous():
+        raise ValueError("den must be the contiguous [2, B*H, Nq] buffer of a forward run with save_norm=True")
+    wpr = 0
+    if blocked_bits is not None:
+        _require(blocked_bits, "blocked_bits", torch.int32)
+        if not blocked_bits.is_contiguous() or blocked_bits.shape[:2] != (B, Nq):
+            raise ValueError("blocked_bits must be contiguous [B, Nq, words]")
+        wpr = blocked_bits.shape[2]
+        if row_open is not None:
+            _require(row_open, "row_open", torch.int32)
+    if add_mask is not None:
+        _require(add_mask, "add_mask")
+        if not add_mask.is_contiguous() or tuple(add_mask.shape) != (B * H, Nq, Ns):
+            raise ValueError("add_mask must be contiguous [B*H, Nq, Ns]")
+
+    def grad_like(L_):
+        return torch.empty(B, L_, H, hd, device=q.device, dtype=torch.float32).permute(0, 2, 1, 3)
+
+    gq, gk, gv = grad_like(Nq), grad_like(Ns), grad_like(Ns)
+    lib = _lib.lib()
+    ws_bytes = lib.msm_vmf_attention_bwd_workspace_bytes(B, H, Nq, Ns, hd)
+    ws = torch.empty(max(ws_bytes, 1), device=q.device, dtype=torch.uint8)
+    flags = (1 if normalize_q else 0) | (2 if normalize_k else 0)
+    rc = lib.msm_vmf_attention_bwd(
+        q.data_ptr(), q_sb, q_sh, q_sl, k.data_ptr(), k_sb, k_sh, k_sl, v.data_ptr(), v_sb, v_sh, v_sl,
+        out.data_ptr(), o_sb, o_sh, o_sl, grad_out.data_ptr(), go_sb, go_sh, go_sl, den.data_ptr(),
+        gq.data_ptr(), gq.stride(0), gq.stride(1), gq.stride(2),
+        gk.data_ptr(), gk.stride(0), gk.stride(1), gk.stride(2),
+        gv.data_ptr(), gv.stride(0), gv.stride(1), gv.stride(2),
+        blocked_bits.data_ptr() if blocked_bits is not None else None, wpr,
+        row_open.data_ptr() if row_open is not None else None,
+        add_mask.data_ptr() if add_mask is not None else None,
+        B, H, Nq, Ns, hd, float(kappa), flags, ws.data_ptr(), ws_bytes, _stream())
+    check(rc, "msm_vmf_attention_bwd")
+    return gq, gk, gv
+
+
+class VmfAttentionFunction(torch.autograd.Function):
+    """Differentiable vMF attention core: forward = msm_vmf_attention_fwd (keeps two floats per query row),
+    backward = msm_vmf_attention_bwd (weights recomputed per key tile). The reference gets the same gradients
+    from torch.autograd through attention_util.py:64-82, saving three [G, Nq, Ns] tensors per call."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, blocked_bits, row_open, add_mask, kappa, normalize_q, normalize_k):
+        q, k, v = q.detach(), k.detach(), v.detach()
+        out, den = vmf_attention(q, k, v, blocked_bits=blocked_bits, row_open=row_open, add_mask=add_mask,
+                                 kappa=kappa, normalize_q=normalize_q, normalize_k=normalize_k, return_den=True,
+                                 save_norm=True)
+        ctx.save_for_backward(q, k, v, out, den)
+        ctx.masks = (blocked_bits, row_open, add_mask)
+        ctx.conf = (float(kappa), bool(normalize_q), bool(normalize_k))
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        q, k, v, out, den = ctx.saved_tensors
+        bits, row_open, add_mask = ctx.masks
+        kappa, nq, nk = ctx.conf
+        gq, gk, gv = vmf_attention_bwd(q, k, v, out, grad_out, den, blocked_bits=bits, row_open=row_open,
+                                       add_mask=add_mask, kappa=kappa, normalize_q=nq, normalize_k=nk)
+        return gq, gk, gv, None, None, None, None, None, None
+
+
+def vmf_attention_autograd(q, k, v, *, blocked_bits=None, row_open=None, add_mask=None, kappa=KAPPA,
+                           normalize_q=True, normalize_k=True):
+    """vmf_attention for training: same [B, H, L, hd] views in, out [B, H, Nq, hd] (view of a [B, Nq, H*hd]
+    buffer), gradients flow to q, k, v. Masks are constants (the reference detaches its attention mask,
+    meanshiftformer_transformer_decoder.py:680)."""
+    return VmfAttentionFunction.apply(q, k, v, blocked_bits, row_open, add_mask, kappa, normalize_q, normalize_k)
 
 
 def vmf_attention_weights(q, k, den, *, blocked_bits=None, row_open=None, add_mask=None, kappa=KAPPA,
