@@ -151,3 +151,31 @@ def vmf_attention_bwd(q, k, v, out, grad_out, den, *, blocked_bits=None, row_ope
         buf.copy_(g)
         res.append(buf)
     return tuple(res)
+
+
+def mask_logits(mask_embed, mask_features, out=None):
+    res = torch.einsum("bqc,bchw->bqhw", mask_embed, mask_features)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+def mask_to_attn_bits(masks, target_size):
+    """msm_mask_to_attn_bits contract: bit set = key blocked (sigmoid < 0.5 after the bilinear resize), row_open = 0
+    for rows that block every key."""
+    B, Q = masks.shape[:2]
+    m = F.interpolate(masks, size=tuple(int(v) for v in target_size), mode="bilinear", align_corners=False)
+    blocked = m.sigmoid().flatten(2) < 0.5
+    S = blocked.shape[-1]
+    words = (S + 31) // 32
+    pad = torch.zeros(B, Q, words * 32, dtype=torch.bool)
+    pad[..., :S] = blocked
+    v = (pad.view(B, Q, words, 32).long() << torch.arange(32)).sum(-1)
+    bits = torch.where(v >= 2 ** 31, v - 2 ** 32, v).to(torch.int32).contiguous()
+    return bits, (~blocked).any(-1).to(torch.int32).contiguous()
+
+
+def dense(x, weight, bias=None, relu=False):
+    y = F.linear(x, weight, bias)
+    return torch.relu(y) if relu else y

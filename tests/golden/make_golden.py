@@ -22,7 +22,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 import ref_shim  # noqa: E402
 sys.path.insert(0, os.path.dirname(HERE))
-from scenes import two_stage_crop_labels, two_stage_scene  # noqa: E402
+from scenes import probe_loss, two_stage_crop_labels, two_stage_scene  # noqa: E402
 
 torch.set_num_threads(4)
 torch.backends.mkldnn.enabled = True
@@ -131,6 +131,26 @@ def gen_decoder_multiscale():
         o = m(x, mf)
     save("decoder_multiscale", x0=x[0], x1=x[1], x2=x[2], mask_features=mf, in_channels=np.int64(16),
          **_dump_decoder_out(o), **sd_arrays(m))
+
+
+def gen_decoder_multiscale_bwd():
+    """Training side: gradients of probe_loss through the REFERENCE decoder (torch.autograd, CPU) wrt every
+    parameter, the level features and the mask features, on the decoder_multiscale fixture's weights and inputs."""
+    dec = ref_shim.ref("modeling.transformer_decoder.meanshiftformer_transformer_decoder")
+    z = np.load(os.path.join(HERE, "decoder_multiscale.npz"))
+    m = dec.MeanShiftTransformerDecoder(int(z["in_channels"]), True, **_decoder_kwargs())
+    m.load_state_dict({k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd::")}, strict=True)
+    m.train()  # dropout is 0 in every config: train() and eval() compute the same function
+    x = [torch.from_numpy(z[f"x{i}"]).requires_grad_() for i in range(3)]
+    mf = torch.from_numpy(z["mask_features"]).requires_grad_()
+    loss = probe_loss(m(x, mf))
+    names = [n for n, _ in m.named_parameters()]
+    grads = torch.autograd.grad(loss, [p for _, p in m.named_parameters()] + x + [mf], allow_unused=True)
+    arrays = {"loss": loss.detach()}
+    for n, g in zip(names + ["x0", "x1", "x2", "mask_features"], grads):
+        if g is not None:
+            arrays["grad::" + n] = g
+    save("decoder_multiscale_bwd", **arrays)
 
 
 def gen_decoder_pretrained():
@@ -451,6 +471,7 @@ if __name__ == "__main__":
     gen_hypersphere_attention_bwd()
     gen_meanshift_attention()
     gen_decoder_multiscale()
+    gen_decoder_multiscale_bwd()
     gen_decoder_pretrained()
     gen_posenc()
     gen_msdeform_core()

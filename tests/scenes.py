@@ -35,3 +35,16 @@ def two_stage_crop_labels(mask_crops, seed):
         out[i][(mask_crops[i] > 0) & (cols >= split)] = 2
         out[i][:S // 8, :S // 8] = 3
     return out
+
+
+def probe_loss(out):
+    """Deterministic scalar of every prediction of a decoder output (final + aux), with closed-form weights so that
+    the generator and the tests build the same loss without sharing random state."""
+    total = 0.0
+    preds = out["aux_outputs"] + [{"pred_logits": out["pred_logits"], "pred_masks": out["pred_masks"]}]
+    for i, p in enumerate(preds):
+        for j, t in enumerate((p["pred_logits"], p["pred_masks"])):
+            w = torch.cos(torch.arange(t.numel(), dtype=torch.float32, device=t.device) * 0.37 + 0.11 * i + 0.5 * j)
+            total = total + (t.reshape(-1) * w.to(t.dtype)).sum() / t.numel() ** 0.5
+    return total
+

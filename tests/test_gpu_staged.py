@@ -94,3 +94,41 @@ def test_vmf_attention_bwd_errors_are_loud(msm):
     with pytest.raises(ValueError, match="save_norm"):
         msm.vmf_attention_bwd(q[:, :, :100], k, k, out[:, :, :100].contiguous(), torch.ones(1, 1, 100, 32, device=dev),
                               den[0])
+
+
+def test_decoder_training_gradients_golden(golden):
+    """MeanShiftTransformerDecoder with grad enabled on the device (VmfAttentionFunction + MaskLogitsFunction around
+    the kernels, cuBLAS / ATen elsewhere) against torch.autograd through the REFERENCE decoder."""
+    from scenes import probe_loss
+    from unseenobjectswithmeanshift_b200.meanshiftformer.modeling.transformer_decoder import (
+        meanshiftformer_transformer_decoder as dec)
+    g, sd = golden("decoder_multiscale")
+    want, _ = golden("decoder_multiscale_bwd")
+    kw = dict(num_classes=2, hidden_dim=32, num_queries=10, nheads=2, dim_feedforward=64, dec_layers=4,
+              pre_norm=False, mask_dim=32, enforce_input_project=False, use_meanshift_cross_attention=True,
+              disable_attention_mask=False, use_meanshift_self_attention=True, decoder_block_norm=True)
+    m = dec.MeanShiftTransformerDecoder(int(g["in_channels"]), True, **kw)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().train()
+    x = [g[f"x{i}"].cuda().requires_grad_() for i in range(3)]
+    mf = g["mask_features"].cuda().requires_grad_()
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        out = m(x, mf)
+        loss = probe_loss(out)
+        params = list(m.named_parameters())
+        grads = torch.autograd.grad(loss, [p for _, p in params] + x + [mf], allow_unused=True)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+    _close(out["pred_masks"].cpu(), g["pred_masks"], 1e-3)
+    assert abs(loss.item() - float(want["loss"])) <= 1e-3 * max(1.0, abs(float(want["loss"])))
+    seen = 0
+    for name, gr in zip([n for n, _ in params] + ["x0", "x1", "x2", "mask_features"], grads):
+        key = "grad::" + name
+        if gr is None:
+            assert key not in want, name
+            continue
+        _close(gr.cpu(), want[key], 2e-3)   # the hard sigmoid < 0.5 masks make this a same-mask comparison
+        seen += 1
+    assert seen == sum(k.startswith("grad::") for k in want)

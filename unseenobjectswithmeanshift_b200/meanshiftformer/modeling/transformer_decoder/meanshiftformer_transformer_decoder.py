@@ -298,10 +298,13 @@ class _MeanShiftDecoderBase(nn.Module):
             dec = self.decoder_norm(out)
         logits = self.class_embed(dec)
         embed = self.mask_embed(dec)
-        masks = ops.mask_logits(embed, mask_features)
+        if torch.is_grad_enabled() and (embed.requires_grad or mask_features.requires_grad):
+            masks = ops.mask_logits_autograd(embed, mask_features)  # training (row f4)
+        else:
+            masks = ops.mask_logits(embed, mask_features)
         bits = row_open = None
-        if need_mask:
-            bits, row_open = ops.mask_to_attn_bits(masks, target_size)
+        if need_mask:  # the attention mask is a constant of the graph (reference :680 detaches it)
+            bits, row_open = ops.mask_to_attn_bits(masks.detach(), target_size)
         return logits, masks, bits, row_open
 
     def forward_prediction_heads(self, output, mask_features, attn_mask_target_size):
@@ -329,6 +332,9 @@ class _MeanShiftDecoderBase(nn.Module):
         hd = C // H
         dev = x[0].device
         mask_features = mask_features.float().contiguous()
+        # training: the attention core and the mask head run through their autograd Functions
+        # (native forward + backward), every other layer through torch (cuBLAS / ATen, autograd-capable)
+        train = torch.is_grad_enabled()
 
         # ---- per-level memory (keys' input = src + pos, values' input = src), batch-first [B,S,C]
         sizes, src, key_in = [], [], []
@@ -355,10 +361,12 @@ class _MeanShiftDecoderBase(nn.Module):
         def project_kv(level, layer_ids):
             attn = [self.transformer_cross_attention_layers[i].meanshift_attn for i in layer_ids]
             tag = "kv%d_%s" % (level, "_".join(map(str, layer_ids)))
-            wk = ops.cached_cat(self, tag + "wk", [a.in_proj_weight[C:2 * C] for a in attn])
-            bk = ops.cached_cat(self, tag + "bk", [a.in_proj_bias[C:2 * C] for a in attn])
-            wv = ops.cached_cat(self, tag + "wv", [a.in_proj_weight[2 * C:] for a in attn])
-            bv = ops.cached_cat(self, tag + "bv", [a.in_proj_bias[2 * C:] for a in attn])
+            # the cache holds detached copies: under autograd the concatenation has to stay part of the graph
+            cat = (lambda name, ts: torch.cat(ts, 0)) if train else (lambda name, ts: ops.cached_cat(self, name, ts))
+            wk = cat(tag + "wk", [a.in_proj_weight[C:2 * C] for a in attn])
+            bk = cat(tag + "bk", [a.in_proj_bias[C:2 * C] for a in attn])
+            wv = cat(tag + "wv", [a.in_proj_weight[2 * C:] for a in attn])
+            bv = cat(tag + "bv", [a.in_proj_bias[2 * C:] for a in attn])
             table = self.pe_layer.table(sizes[level][0], sizes[level][1], dev)
             if (os.environ.get("MSM_FOLD_POS", "0") == "1" and not torch.is_grad_enabled() and ops.tc_linear_enabled()
                     and ops.linear_supported(src[level], wk) and table.numel() * len(layer_ids) * 4 <= (64 << 20)):
@@ -382,6 +390,16 @@ class _MeanShiftDecoderBase(nn.Module):
 
         def heads_view(t):  # [B,len,C] (row stride may exceed C) -> [B,H,len,hd] view
             return t.unflatten(-1, (H, hd)).permute(0, 2, 1, 3)
+
+        def attention(q_, k_, v_, bits_=None, row_open_=None):  # [B,len,C] projections -> [B,Q,C]
+            if train:
+                o4 = ops.vmf_attention_autograd(heads_view(q_), heads_view(k_), heads_view(v_), blocked_bits=bits_,
+                                                row_open=row_open_)
+                return o4.permute(0, 2, 1, 3).reshape(B, self.num_queries, C)
+            o_ = torch.empty(B, self.num_queries, C, device=dev, dtype=torch.float32)
+            ops.vmf_attention(heads_view(q_), heads_view(k_), heads_view(v_), blocked_bits=bits_, row_open=row_open_,
+                              out=heads_view(o_))
+            return o_
 
         query_pos = self.query_embed.weight.unsqueeze(0)  # [1,Q,C]
         out = self.query_feat.weight.unsqueeze(0).expand(B, -1, -1).contiguous()
@@ -456,17 +474,14 @@ class _MeanShiftDecoderBase(nn.Module):
                 continue
             # cross-attention (reference :245-260), post-norm
             q = ops.dense(out + query_pos, a.in_proj_weight[:C], a.in_proj_bias[:C])
-            o = torch.empty(B, self.num_queries, C, device=dev, dtype=torch.float32)
-            ops.vmf_attention(heads_view(q), heads_view(K), heads_view(V), blocked_bits=bits, row_open=row_open,
-                              out=heads_view(o))
+            o = attention(q, K, V, bits, row_open)
             out = ca.norm(out + ops.dense(o, a.out_proj.weight, a.out_proj.bias))
             del K, V
             # self-attention (reference :171-181): q = k = out + query_pos, v = out
             a = sa
             qk = ops.dense(out + query_pos, a.in_proj_weight[:2 * C], a.in_proj_bias[:2 * C])
             v = ops.dense(out, a.in_proj_weight[2 * C:], a.in_proj_bias[2 * C:])
-            o = torch.empty(B, self.num_queries, C, device=dev, dtype=torch.float32)
-            ops.vmf_attention(heads_view(qk[..., :C]), heads_view(qk[..., C:]), heads_view(v), out=heads_view(o))
+            o = attention(qk[..., :C], qk[..., C:], v)
             out = sl.norm(out + ops.dense(o, a.out_proj.weight, a.out_proj.bias))
             # FFN (reference :300-304) and block norm (:637-638)
             out = ffn(out)

@@ -214,6 +214,41 @@ def mask_logits(mask_embed, mask_features, out=None):
     return out
 
 
+class MaskLogitsFunction(torch.autograd.Function):
+    """Differentiable mask head einsum (meanshiftformer_transformer_decoder.py:668): forward = msm_mask_logits;
+    the backward is two plain batched GEMMs, left to cuBLAS (fp32, TF32 off):
+    g_embed = g_masks . feat^T over the pixels, g_feat = embed^T . g_masks."""
+
+    @staticmethod
+    def forward(ctx, mask_embed, mask_features):
+        e, f = mask_embed.detach().contiguous(), mask_features.detach().contiguous()
+        ctx.save_for_backward(e, f)
+        return mask_logits(e, f)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_masks):
+        e, f = ctx.saved_tensors
+        B, Q, C = e.shape
+        g = grad_masks.reshape(B, Q, -1)
+        ge = gf = None
+        tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            if ctx.needs_input_grad[0]:
+                ge = torch.bmm(g, f.reshape(B, C, -1).transpose(1, 2))
+            if ctx.needs_input_grad[1]:
+                gf = torch.bmm(e.transpose(1, 2), g).reshape(f.shape)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+        return ge, gf
+
+
+def mask_logits_autograd(mask_embed, mask_features):
+    """mask_logits for training: gradients flow to the mask embeddings and the mask features."""
+    return MaskLogitsFunction.apply(mask_embed, mask_features)
+
+
 def mask_to_attn_bits(masks, target_size):
     """masks [B,Q,H,W] -> (blocked bits int32 [B,Q,ceil(Ht*Wt/32)], row_open int32 [B,Q])."""
     m = _require(masks, "masks").contiguous()
