@@ -34,6 +34,9 @@ def load_golden(name):
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
     arrays, sd = {}, {}
     for k in z.files:
+        if z[k].dtype.kind in "US":  # lists of names stay lists of str
+            arrays[k] = [str(v) for v in z[k]]
+            continue
         t = torch.from_numpy(z[k])
         if k.startswith("sd::"):
             sd[k[4:]] = t

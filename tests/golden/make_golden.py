@@ -466,6 +466,81 @@ def gen_two_stage():
     save("two_stage", crop_size=np.int64(64), **out)
 
 
+def gen_criterion():
+    """Training losses: the REFERENCE's SetCriterion + HungarianMatcher (criterion.py, matcher.py) on a small
+    three-layer prediction, with every random point set recorded in the fixture (the reference draws them per image
+    in the matcher and per layer in the criterion; the device mirror draws them once per step, so parity is defined
+    on equal points). Also the gradients of the summed losses wrt the final predictions."""
+    crit = ref_shim.ref("modeling.criterion")
+    mat = ref_shim.ref("modeling.matcher")
+    torch.manual_seed(40)
+    B, Q, K, h, w, H, W = 2, 10, 2, 24, 32, 96, 128
+    layers, P, over, imp = 3, 50, 3.0, 0.75
+    counts = [3, 2]
+    N, S, R = sum(counts), int(P * over), P - int(imp * P)
+    preds = [{"pred_logits": torch.randn(B, Q, K + 1), "pred_masks": torch.randn(B, Q, h, w) * 3} for _ in range(layers)]
+    targets = []
+    yy, xx = torch.meshgrid(torch.arange(H).float(), torch.arange(W).float(), indexing="ij")
+    for b, T in enumerate(counts):
+        masks = torch.zeros(T, H, W, dtype=torch.bool)
+        for t in range(T):
+            cy, cx, r = 20 + 25 * t + 5 * b, 25 + 35 * t, 12 + 4 * t
+            masks[t] = (yy - cy) ** 2 + (xx - cx) ** 2 < r * r
+        targets.append({"labels": torch.randint(0, K, (T,)), "masks": masks})
+    # make one prediction per target resemble it, so that the assignment is not decided by noise alone
+    for l in range(layers):
+        for b, T in enumerate(counts):
+            for t in range(T):
+                small = F.interpolate(targets[b]["masks"][t][None, None].float(), size=(h, w), mode="bilinear")[0, 0]
+                preds[l]["pred_masks"][b, (3 * t + l + b) % Q] += 8 * small - 4
+    m_pts, cand, fill = torch.rand(layers, B, P, 2), torch.rand(layers, N, S, 2), torch.rand(layers, N, R, 2)
+    cursor = {"m": 0, "c": 0, "f": 0}
+
+    def replay(*shape, device=None):
+        if shape == (1, P, 2):
+            i = cursor["m"]; cursor["m"] += 1
+            return m_pts[i // B, i % B][None].clone()
+        if shape == (N, S, 2):
+            cursor["c"] += 1
+            return cand[cursor["c"] - 1].clone()
+        if shape == (N, R, 2):
+            cursor["f"] += 1
+            return fill[cursor["f"] - 1].clone()
+        raise AssertionError(f"unexpected draw {shape}")
+
+    mat.torch = ref_shim.TorchProxy(replay)
+    ref_shim.RAND[0] = replay
+    try:
+        matcher = mat.HungarianMatcher(cost_class=1.0, cost_mask=20.0, cost_dice=1.0, num_points=P)
+        weight = {"loss_ce": 1.0, "loss_mask": 20.0, "loss_dice": 1.0}
+        weight.update({k + f"_{i}": v for i in range(layers - 1) for k, v in list(weight.items())[:3]})
+        c = crit.SetCriterion(K, matcher=matcher, weight_dict=weight, eos_coef=0.1, losses=["labels", "masks"],
+                              num_points=P, oversample_ratio=over, importance_sample_ratio=imp)
+        final = {k: v.clone().requires_grad_() for k, v in preds[0].items()}
+        outputs = dict(final, aux_outputs=preds[1:])
+        losses = c(outputs, targets)
+        assert cursor == {"m": layers * B, "c": layers, "f": layers}, cursor
+        g_logits, g_masks = torch.autograd.grad(sum(losses.values()), (final["pred_logits"], final["pred_masks"]))
+        # the assignment of every layer, replayed on the same points
+        cursor.update(m=0)
+        indices = [matcher(p, targets) for p in preds]
+    finally:
+        mat.torch = torch
+        ref_shim.RAND[0] = torch.rand
+    arrays = {"matcher_points": m_pts, "candidate_points": cand, "fill_points": fill,
+              "num_points": np.int64(P), "oversample_ratio": np.float64(over), "importance_sample_ratio": np.float64(imp),
+              "grad_pred_logits": g_logits, "grad_pred_masks": g_masks, "loss_names": np.array(list(losses))}
+    for l, p in enumerate(preds):
+        arrays[f"pred_logits_{l}"], arrays[f"pred_masks_{l}"] = p["pred_logits"], p["pred_masks"]
+        for b in range(B):
+            arrays[f"match_{l}_{b}_pred"], arrays[f"match_{l}_{b}_tgt"] = indices[l][b]
+    for b, t in enumerate(targets):
+        arrays[f"labels_{b}"], arrays[f"masks_{b}"] = t["labels"], t["masks"]
+    for k, v in losses.items():
+        arrays["loss::" + k] = v
+    save("criterion", **arrays)
+
+
 if __name__ == "__main__":
     gen_hypersphere_attention()
     gen_hypersphere_attention_bwd()
@@ -483,3 +558,4 @@ if __name__ == "__main__":
     gen_mean_shift_d64()
     gen_instance_inference()
     gen_two_stage()
+    gen_criterion()

@@ -122,12 +122,60 @@ def install():
         sys.modules[name] = m
         return m
 
+    # training-side imports of criterion.py / matcher.py: detectron2's PointRend helpers are third-party code absent
+    # from /root/reference; their published algorithm (detectron2 0.6, point_rend/point_features.py) is restated here.
+    # Random draws go through ``RAND`` so that the golden generator can record / replay them.
+    def point_sample(input, point_coords, **kwargs):
+        add_dim = point_coords.dim() == 3
+        if add_dim:
+            point_coords = point_coords.unsqueeze(2)
+        out = F.grid_sample(input, 2.0 * point_coords - 1.0, **kwargs)
+        return out.squeeze(3) if add_dim else out
+
+    def get_uncertain_point_coords_with_randomness(coarse_logits, uncertainty_func, num_points, oversample_ratio,
+                                                   importance_sample_ratio):
+        num_boxes = coarse_logits.shape[0]
+        num_sampled = int(num_points * oversample_ratio)
+        point_coords = RAND[0](num_boxes, num_sampled, 2, device=coarse_logits.device)
+        point_logits = point_sample(coarse_logits, point_coords, align_corners=False)
+        point_uncertainties = uncertainty_func(point_logits)
+        num_uncertain_points = int(importance_sample_ratio * num_points)
+        num_random_points = num_points - num_uncertain_points
+        idx = torch.topk(point_uncertainties[:, 0, :], k=num_uncertain_points, dim=1)[1]
+        shift = num_sampled * torch.arange(num_boxes, dtype=torch.long, device=coarse_logits.device)
+        idx += shift[:, None]
+        point_coords = point_coords.view(-1, 2)[idx.view(-1), :].view(num_boxes, num_uncertain_points, 2)
+        if num_random_points > 0:
+            point_coords = torch.cat(
+                [point_coords, RAND[0](num_boxes, num_random_points, 2, device=coarse_logits.device)], dim=1)
+        return point_coords
+
+    _mod("detectron2.utils.comm", get_world_size=lambda: 1)
+    _mod("detectron2.projects")
+    _mod("detectron2.projects.point_rend")
+    _mod("detectron2.projects.point_rend.point_features", point_sample=point_sample,
+         get_uncertain_point_coords_with_randomness=get_uncertain_point_coords_with_randomness)
+
     pkg("refmsm", REF_PKG)
+    pkg("refmsm.utils", os.path.join(REF_PKG, "utils"))
     pkg("refmsm.modeling", os.path.join(REF_PKG, "modeling"))
     pkg("refmsm.modeling.transformer_decoder", os.path.join(REF_PKG, "modeling", "transformer_decoder"))
     pkg("refmsm.modeling.pixel_decoder", os.path.join(REF_PKG, "modeling", "pixel_decoder"))
     pkg("refmsm.modeling.pixel_decoder.ops", os.path.join(REF_PKG, "modeling", "pixel_decoder", "ops"))
     # ops/modules and ops/functions have harmless __init__.py files: let them import normally
+
+
+RAND = [torch.rand]  # the random source of the restated PointRend helpers (replaced by the golden generator)
+
+
+class TorchProxy:
+    """``torch`` with ``rand`` replaced: assigned to a reference module's global ``torch`` to replay recorded draws."""
+
+    def __init__(self, rand):
+        self.rand = rand
+
+    def __getattr__(self, name):
+        return getattr(torch, name)
 
 
 def ref(name):

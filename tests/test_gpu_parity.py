@@ -700,10 +700,10 @@ def test_meta_arch_wrappers(msm):
     with pytest.raises(NotImplementedError, match="output size"):
         with torch.no_grad():
             model([{"image": imgs[0], "height": 128, "width": 192}])
-    model.train()
-    with pytest.raises(NotImplementedError, match="training"):
-        with torch.no_grad():
-            model([{"image": imgs[0]}])
+    model.train()   # the training branch needs a criterion (build_criterion); tests/test_training_wiring.py covers it
+    with pytest.raises(RuntimeError, match="training needs a criterion"):
+        model([{"image": imgs[0]}])
+    model.eval()
 
     # pretrained-embedding variant: unit-norm 64-d pixel embeddings are the head's only feature map
     from unseenobjectswithmeanshift_b200.d2compat import ShapeSpec

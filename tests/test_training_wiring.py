@@ -135,3 +135,151 @@ def test_decoder_training_path_wiring(ops, monkeypatch, golden):
     params = list(m.named_parameters())
     grads = torch.autograd.grad(loss, [p for _, p in params] + x + [mf], allow_unused=True)
     _check_grads(zip([n for n, _ in params] + ["x0", "x1", "x2", "mask_features"], grads), want, 2e-4)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# losses: batched matcher + criterion against the reference's SetCriterion / HungarianMatcher on recorded points
+class _Replay:
+    def __init__(self, g):
+        self.g = g
+
+    def matcher_points(self, layers, batch, num_points, device):
+        assert tuple(self.g["matcher_points"].shape) == (layers, batch, num_points, 2)
+        return self.g["matcher_points"].to(device)
+
+    def oversampled_points(self, layers, num_masks, num_sampled, device):
+        assert tuple(self.g["candidate_points"].shape) == (layers, num_masks, num_sampled, 2)
+        return self.g["candidate_points"].to(device)
+
+    def random_points(self, layers, num_masks, num_random, device):
+        assert tuple(self.g["fill_points"].shape) == (layers, num_masks, num_random, 2)
+        return self.g["fill_points"].to(device)
+
+
+def _criterion_case(g, device="cpu"):
+    from unseenobjectswithmeanshift_b200.meanshiftformer.modeling.criterion import SetCriterion
+    from unseenobjectswithmeanshift_b200.meanshiftformer.modeling.matcher import HungarianMatcher
+    layers = 3
+    P = int(g["num_points"])
+    preds = [{"pred_logits": g[f"pred_logits_{l}"].to(device), "pred_masks": g[f"pred_masks_{l}"].to(device)}
+             for l in range(layers)]
+    targets = [{"labels": g[f"labels_{b}"].to(device), "masks": g[f"masks_{b}"].to(device)} for b in range(2)]
+    matcher = HungarianMatcher(cost_class=1.0, cost_mask=20.0, cost_dice=1.0, num_points=P)
+    crit = SetCriterion(2, matcher=matcher, weight_dict={}, eos_coef=0.1, losses=["labels", "masks"], num_points=P,
+                        oversample_ratio=float(g["oversample_ratio"]),
+                        importance_sample_ratio=float(g["importance_sample_ratio"])).to(device)
+    return preds, targets, matcher, crit
+
+
+def test_matcher_assignments_match_reference(golden):
+    g, _ = golden("criterion")
+    preds, targets, matcher, _ = _criterion_case(g)
+    got = matcher.match_layers(preds, targets, _Replay(g))
+    for l in range(3):
+        for b in range(2):
+            assert torch.equal(got[l][b][0], g[f"match_{l}_{b}_pred"]) and got[l][b][0].dtype == torch.int64
+            assert torch.equal(got[l][b][1], g[f"match_{l}_{b}_tgt"])
+    # the single-layer entry point keeps the reference's signature
+    class OneLayer(_Replay):
+        def matcher_points(self, layers, batch, num_points, device):
+            return self.g["matcher_points"][1:2].to(device)
+    one = matcher(preds[1], targets, OneLayer(g))
+    assert all(torch.equal(one[b][0], g[f"match_1_{b}_pred"]) for b in range(2))
+
+
+def test_criterion_losses_and_gradients_match_reference(golden):
+    g, _ = golden("criterion")
+    preds, targets, _, crit = _criterion_case(g)
+    final = {k: v.clone().requires_grad_() for k, v in preds[0].items()}
+    losses = crit(dict(final, aux_outputs=preds[1:]), targets, _Replay(g))
+    assert list(losses) == g["loss_names"]   # same keys in the same order
+    for k, v in losses.items():
+        torch.testing.assert_close(v, g["loss::" + k], rtol=1e-5, atol=1e-6)
+    gl, gm = torch.autograd.grad(sum(losses.values()), (final["pred_logits"], final["pred_masks"]))
+    torch.testing.assert_close(gl, g["grad_pred_logits"], rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(gm, g["grad_pred_masks"], rtol=1e-4, atol=1e-7)
+    assert torch.equal(crit.empty_weight, torch.tensor([1.0, 1.0, 0.1]))
+
+
+def test_criterion_without_targets_and_default_points():
+    """No ground truth in the batch: finite losses attached to the graph; default PointSource draws on the device."""
+    from unseenobjectswithmeanshift_b200.meanshiftformer.modeling.criterion import SetCriterion
+    from unseenobjectswithmeanshift_b200.meanshiftformer.modeling.matcher import HungarianMatcher
+    torch.manual_seed(0)
+    crit = SetCriterion(2, matcher=HungarianMatcher(1.0, 20.0, 1.0, num_points=16), weight_dict={}, eos_coef=0.1,
+                        losses=["labels", "masks"], num_points=16, oversample_ratio=3.0, importance_sample_ratio=0.75)
+    out = {"pred_logits": torch.randn(2, 5, 3, requires_grad=True), "pred_masks": torch.randn(2, 5, 8, 8, requires_grad=True)}
+    empty = [{"labels": torch.zeros(0, dtype=torch.int64), "masks": torch.zeros(0, 16, 16, dtype=torch.bool)}] * 2
+    losses = crit(dict(out, aux_outputs=[{k: v.detach() for k, v in out.items()}]), empty)
+    assert float(losses["loss_mask"].detach()) == 0.0 and float(losses["loss_dice"].detach()) == 0.0
+    assert losses["loss_ce"].isfinite()
+    sum(losses.values()).backward()
+    some = [{"labels": torch.tensor([1]), "masks": torch.ones(1, 16, 16, dtype=torch.bool)},
+            {"labels": torch.zeros(0, dtype=torch.int64), "masks": torch.zeros(0, 16, 16, dtype=torch.bool)}]
+    losses = crit(dict(out, aux_outputs=[]), some)
+    assert set(losses) == {"loss_ce", "loss_mask", "loss_dice"} and all(v.isfinite() for v in losses.values())
+
+
+def test_meta_arch_training_branch(ops, monkeypatch):
+    """PretrainedMeanShiftMaskFormer.train(): forward returns the reference's weighted loss dict (train branch of
+    pretrained_meanshiftformer_model.py:303-334) and gradients reach the backbone, the pixel decoder and the decoder."""
+    from torch import nn
+    from unseenobjectswithmeanshift_b200 import meanshiftformer as mf
+    from unseenobjectswithmeanshift_b200.d2compat import ShapeSpec
+    from unseenobjectswithmeanshift_b200.meanshiftformer import modeling
+    from unseenobjectswithmeanshift_b200.meanshiftformer.meanshiftformer_model import build_criterion
+    for name in ("mask_logits", "mask_to_attn_bits", "dense"):
+        monkeypatch.setattr(ops, name, getattr(fake_ops, name))
+    torch.manual_seed(3)
+
+    class ToyEmbedding(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = nn.Conv2d(3, 64, 3, padding=1)
+
+        def forward(self, image, label=None, depth=None):
+            return self.conv(image)
+
+    shapes = {"res5": ShapeSpec(channels=64, stride=1)}
+    kw = dict(DEC_KW, dec_layers=2)
+    head = modeling.PretrainedMeanShiftMaskFormerHead(
+        shapes, num_classes=2, pixel_decoder=modeling.SimpleBasePixelDecoder(shapes, conv_dim=64, mask_dim=32, norm="GN"),
+        loss_weight=1.0, ignore_value=255,
+        transformer_predictor=modeling.PretrainedMeanShiftTransformerDecoder(64, True, **kw),
+        transformer_in_feature="multi_scale_pixel_decoder")
+    crit = build_criterion(2, dec_layers=3, train_num_points=32)
+    assert list(crit.weight_dict) == ["loss_ce", "loss_mask", "loss_dice", "loss_ce_0", "loss_mask_0", "loss_dice_0",
+                                      "loss_ce_1", "loss_mask_1", "loss_dice_1"]
+    model = mf.PretrainedMeanShiftMaskFormer(
+        backbone=ToyEmbedding(), sem_seg_head=head, criterion=crit, num_queries=10, object_mask_threshold=0.8,
+        overlap_threshold=0.8, metadata=None, size_divisibility=0, sem_seg_postprocess_before_inference=True,
+        pixel_mean=[0.0, 0.0, 0.0], pixel_std=[1.0, 1.0, 1.0], semantic_on=False, panoptic_on=False, instance_on=True,
+        test_topk_per_image=5).train()
+    masks = torch.zeros(2, 16, 24, dtype=torch.bool)
+    masks[0, 2:9, 3:12] = True
+    masks[1, 8:15, 14:22] = True
+    batch = [{"image": torch.rand(3, 16, 24), "instances": {"gt_masks": masks, "gt_classes": torch.tensor([0, 1])}},
+             {"image": torch.rand(3, 16, 24), "instances": {"gt_masks": masks[:1], "gt_classes": torch.tensor([1])}}]
+    losses = model(batch)
+    assert list(losses) == list(crit.weight_dict)
+    assert all(v.isfinite() and v.requires_grad for v in losses.values())
+    sum(losses.values()).backward()
+    for prefix in ("pretrained_backbone.", "sem_seg_head.pixel_decoder.", "sem_seg_head.predictor."):
+        grads = [p.grad for n, p in model.named_parameters() if n.startswith(prefix) and p.grad is not None]
+        assert grads and all(g.isfinite().all() for g in grads) and any(float(g.abs().max()) > 0 for g in grads), prefix
+    # loss weighting: mask losses carry the reference's factor 20 relative to the raw criterion output
+    torch.manual_seed(9)
+    raw = crit({k: (v.detach() if torch.is_tensor(v) else [{a: b.detach() for a, b in d.items()} for d in v])
+                for k, v in model._head_outputs(batch)[0].items()}, model.prepare_targets(
+                    [x["instances"] for x in batch], (16, 24)))
+    torch.manual_seed(9)
+    again = crit({k: (v.detach() if torch.is_tensor(v) else [{a: b.detach() for a, b in d.items()} for d in v])
+                  for k, v in model._head_outputs(batch)[0].items()}, model.prepare_targets(
+                      [x["instances"] for x in batch], (16, 24)))
+    assert all(torch.equal(raw[k], again[k]) for k in raw)   # same seed, same points, same losses
+    with pytest.raises(RuntimeError, match="training needs a criterion"):
+        mf.PretrainedMeanShiftMaskFormer(
+            backbone=ToyEmbedding(), sem_seg_head=head, criterion=None, num_queries=10, object_mask_threshold=0.8,
+            overlap_threshold=0.8, metadata=None, size_divisibility=0, sem_seg_postprocess_before_inference=True,
+            pixel_mean=[0.0] * 3, pixel_std=[1.0] * 3, semantic_on=False, panoptic_on=False, instance_on=True,
+            test_topk_per_image=5).train()(batch)

@@ -5,8 +5,10 @@ same ``state_dict`` layout, and the same ``forward(batched_inputs) -> [{"instanc
 
 Scope: the backbone is whatever module the caller supplies (ResNet-50 / UCN are cuDNN work outside the
 hot path); the head runs the CUDA path of this package; the eval tail is ``instance_inference.inference_tail`` (top-k
-first, one fused pass). The training branch (criterion, matcher, embedding loss - row f4) and the semantic / panoptic
-outputs (unused by every UOIS config) raise ``NotImplementedError``.
+first, one fused pass). In training mode ``forward`` returns the weighted loss dict of the reference's train branch
+(pretrained_meanshiftformer_model.py:303-334: prepare_targets, SetCriterion, weight_dict scaling - row f4); the UCN
+embedding loss (``use_embedding_loss``, lib/fcn code that trains the backbone) and the semantic / panoptic outputs
+(unused by every UOIS config) raise ``NotImplementedError``.
 """
 from typing import Tuple
 
@@ -16,6 +18,26 @@ from torch.nn import functional as F
 
 from ..d2compat import META_ARCH_REGISTRY, configurable
 from . import instance_inference as _tail
+from .modeling.criterion import SetCriterion
+from .modeling.matcher import HungarianMatcher
+
+
+def build_criterion(num_classes, *, class_weight=1.0, mask_weight=20.0, dice_weight=1.0, no_object_weight=0.1,
+                    deep_supervision=True, dec_layers=10, train_num_points=112 * 112, oversample_ratio=3.0,
+                    importance_sample_ratio=0.75):
+    """The criterion the reference's from_config assembles (pretrained_meanshiftformer_model.py:165-201); defaults are
+    the values of meanshiftformer/config.py:31-35,129-135 (every UOIS YAML keeps them)."""
+    matcher = HungarianMatcher(cost_class=class_weight, cost_mask=mask_weight, cost_dice=dice_weight,
+                               num_points=train_num_points)
+    weight_dict = {"loss_ce": class_weight, "loss_mask": mask_weight, "loss_dice": dice_weight}
+    if deep_supervision:
+        aux = {}
+        for i in range(dec_layers - 1):
+            aux.update({k + f"_{i}": v for k, v in weight_dict.items()})
+        weight_dict.update(aux)
+    return SetCriterion(num_classes, matcher=matcher, weight_dict=weight_dict, eos_coef=no_object_weight,
+                        losses=["labels", "masks"], num_points=train_num_points, oversample_ratio=oversample_ratio,
+                        importance_sample_ratio=importance_sample_ratio)
 
 
 class _CriterionState(nn.Module):
@@ -73,13 +95,42 @@ class _MetaArchBase(nn.Module):
 
     def _check_mode(self):
         if self.training:
-            raise NotImplementedError("training (criterion / matcher / embedding loss) is row f4 of SURVEY.md 8: "
-                                      "call .eval() and run under torch.no_grad()")
+            raise RuntimeError("inference helper called in training mode: call .eval() first")
 
     def forward(self, batched_inputs):
-        """eval branch of the reference's forward: [{"instances": ...}] per image."""
-        self._check_mode()
+        """Reference forward: the weighted loss dict in training mode (:303-334), [{"instances": ...}] per image in
+        eval mode (:335-378)."""
+        if self.training:
+            return self._losses(batched_inputs)
         return self._eval_tail(*self._head_outputs(batched_inputs))
+
+    def prepare_targets(self, targets, padded_size):
+        """Reference :380-395: ground-truth masks zero-padded to the padded batch size. ``targets``: per image an
+        object with ``gt_masks`` [T,h,w] and ``gt_classes`` [T] (detectron2 Instances) or a dict with those keys."""
+        h_pad, w_pad = padded_size
+        out = []
+        for t in targets:
+            get = (lambda k: t[k]) if isinstance(t, dict) else (lambda k: getattr(t, k))
+            gt_masks = get("gt_masks")
+            gt_masks = getattr(gt_masks, "tensor", gt_masks).to(self.device)  # BitMasks or a plain tensor
+            padded = torch.zeros((gt_masks.shape[0], h_pad, w_pad), dtype=gt_masks.dtype, device=self.device)
+            padded[:, :gt_masks.shape[1], :gt_masks.shape[2]] = gt_masks
+            out.append({"labels": get("gt_classes").to(self.device), "masks": padded})
+        return out
+
+    def _losses(self, batched_inputs, point_source=None):
+        if self.use_embedding_loss:
+            raise NotImplementedError("the UCN embedding loss (lib/fcn/... EmbeddingLoss) trains the embedding "
+                                      "backbone, which is outside this package (SURVEY.md 8, out of scope)")
+        if not isinstance(self.criterion, SetCriterion):
+            raise RuntimeError("training needs a criterion: pass criterion=build_criterion(num_classes, ...)")
+        if "instances" not in batched_inputs[0]:
+            raise ValueError('training inputs need "instances" (gt_masks, gt_classes) per image')
+        outputs, _, padded_size, _ = self._head_outputs(batched_inputs)
+        targets = self.prepare_targets([x["instances"] for x in batched_inputs], padded_size)
+        losses = self.criterion(outputs, targets, point_source)
+        weights = self.criterion.weight_dict
+        return {k: v * weights[k] for k, v in losses.items() if k in weights}  # others are dropped (:329-334)
 
     def label_maps(self, batched_inputs, topk=False, score=0.7, low_threshold=0.4):
         """What the UOIS test scripts do with the instances (lib/fcn/test_utils.py:35-52, 93-112, 216-242:
@@ -192,7 +243,7 @@ class PretrainedMeanShiftMaskFormer(_MetaArchBase):
 
 
 def _from_config(cfg, pretrained):
-    """The reference's from_config (:160-251 / :140-214) minus the criterion: needs detectron2's builders."""
+    """The reference's from_config (:160-251 / :140-214): needs detectron2's builders."""
     try:  # pragma: no cover - detectron2 is not part of the build image
         from detectron2.data import MetadataCatalog
         from detectron2.modeling import build_backbone, build_sem_seg_head
@@ -203,7 +254,12 @@ def _from_config(cfg, pretrained):
     head = build_sem_seg_head(cfg, backbone.output_shape())
     mf = cfg.MODEL.MASK_FORMER
     kw = {
-        "backbone": backbone, "sem_seg_head": head, "criterion": None,
+        "backbone": backbone, "sem_seg_head": head,
+        "criterion": build_criterion(
+            head.num_classes, class_weight=mf.CLASS_WEIGHT, mask_weight=mf.MASK_WEIGHT, dice_weight=mf.DICE_WEIGHT,
+            no_object_weight=mf.NO_OBJECT_WEIGHT, deep_supervision=mf.DEEP_SUPERVISION, dec_layers=mf.DEC_LAYERS,
+            train_num_points=mf.TRAIN_NUM_POINTS, oversample_ratio=mf.OVERSAMPLE_RATIO,
+            importance_sample_ratio=mf.IMPORTANCE_SAMPLE_RATIO),
         "num_queries": mf.NUM_OBJECT_QUERIES, "object_mask_threshold": mf.TEST.OBJECT_MASK_THRESHOLD,
         "overlap_threshold": mf.TEST.OVERLAP_THRESHOLD, "metadata": MetadataCatalog.get(cfg.DATASETS.TRAIN[0]),
         "size_divisibility": mf.SIZE_DIVISIBILITY,
