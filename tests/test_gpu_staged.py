@@ -132,3 +132,49 @@ def test_decoder_training_gradients_golden(golden):
         _close(gr.cpu(), want[key], 2e-3)   # the hard sigmoid < 0.5 masks make this a same-mask comparison
         seen += 1
     assert seen == sum(k.startswith("grad::") for k in want)
+
+
+def test_head_training_steps_r50style(golden):
+    """Whole training step on the device on the small R50-style head of tests/golden/head_r50style.npz: pixel decoder
+    (MSDeformAttn forward / backward kernels), decoder (attention and mask-head Functions), criterion, clipped AdamW.
+    Checks plumbing: finite losses with the reference's keys, gradients on every trainable tensor, parameters move,
+    and the loss of a repeated batch goes down."""
+    from unseenobjectswithmeanshift_b200 import training, workloads
+    from unseenobjectswithmeanshift_b200.d2compat import ShapeSpec
+    from unseenobjectswithmeanshift_b200.meanshiftformer import modeling as M
+    from unseenobjectswithmeanshift_b200.meanshiftformer.meanshiftformer_model import build_criterion
+    g, sd = golden("head_r50style")
+    shapes = {"res2": ShapeSpec(channels=8, stride=4), "res3": ShapeSpec(channels=16, stride=8),
+              "res4": ShapeSpec(channels=32, stride=16), "res5": ShapeSpec(channels=64, stride=32)}
+    kw = dict(num_classes=2, hidden_dim=32, num_queries=10, nheads=2, dim_feedforward=64, dec_layers=4,
+              pre_norm=False, mask_dim=32, enforce_input_project=False, use_meanshift_cross_attention=True,
+              disable_attention_mask=False, use_meanshift_self_attention=True, decoder_block_norm=True)
+    pixel = M.MSDeformAttnPixelDecoder(shapes, transformer_dropout=0.0, transformer_nheads=4,
+                                       transformer_dim_feedforward=64, transformer_enc_layers=2, conv_dim=32,
+                                       mask_dim=32, norm="GN", transformer_in_features=["res3", "res4", "res5"],
+                                       common_stride=4)
+    head = M.PretrainedMeanShiftMaskFormerHead(shapes, num_classes=2, pixel_decoder=pixel, loss_weight=1.0,
+                                               ignore_value=255,
+                                               transformer_predictor=M.MeanShiftTransformerDecoder(32, True, **kw),
+                                               transformer_in_feature="multi_scale_pixel_decoder")
+    head.load_state_dict(sd, strict=True)
+    model = workloads.HeadTrainer(head.train(), build_criterion(2, dec_layers=5, train_num_points=256), 64, 96).cuda()
+    feats = {k[3:]: v.cuda() for k, v in g.items() if k.startswith("in_")}
+    B = next(iter(feats.values())).shape[0]
+    masks = torch.zeros(2, 64, 96, dtype=torch.bool, device="cuda")
+    masks[0, 8:30, 10:40] = True
+    masks[1, 34:60, 50:90] = True
+    targets = [{"labels": torch.tensor([0, 1], device="cuda"), "masks": masks} for _ in range(B)]
+    opt = training.build_optimizer(model, lr=1e-3)
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    torch.manual_seed(0)
+    history = []
+    for _ in range(8):
+        losses = training.train_step(model, opt, {"features": feats, "targets": targets}, clip_value=1.0)
+        history.append(float(sum(losses.values())))
+    assert list(losses) == list(model.criterion.weight_dict)
+    assert all(h == h and abs(h) < 1e6 for h in history), history
+    missing = [n for n, p in model.named_parameters() if p.requires_grad and p.grad is None]
+    assert not missing, missing
+    assert any(not torch.equal(before[n], p) for n, p in model.named_parameters())
+    assert min(history[4:]) < history[0], history

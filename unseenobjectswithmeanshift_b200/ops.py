@@ -1050,6 +1050,16 @@ def _work_ms(X, Z, kappa, max_iters=10):
 
 vmf_attention = _instrument("vmf_attention", 2, _work_vmf)(vmf_attention)
 vmf_attention_weights = _instrument("vmf_attention_weights", 1)(vmf_attention_weights)
+
+
+def _work_vmf_bwd(q, k, v, out, grad_out, den, **kw):
+    B, H, Nq, hd = q.shape
+    Ns = k.shape[2]
+    by = 4.0 * B * H * hd * 4 * (Ns + Nq) + (B * Nq * Ns / 8.0 if kw.get("blocked_bits") is not None else 0)
+    return f"B{B} H{H} Q{Nq} S{Ns} hd{hd}", by, 10.0 * B * H * Nq * Ns * hd  # two score products, three accumulations
+
+
+vmf_attention_bwd = _instrument("vmf_attention_bwd", 2, _work_vmf_bwd)(vmf_attention_bwd)
 mask_logits = _instrument("mask_logits", 1, _work_mask)(mask_logits)
 mask_to_attn_bits = _instrument("mask_to_attn_bits", 1, _work_bits)(mask_to_attn_bits)  # one kernel, no memset
 linear = _instrument("linear", 1, _work_linear)(linear)

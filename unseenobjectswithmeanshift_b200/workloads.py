@@ -5,6 +5,8 @@
 ``ucn``   config #1/#3 stage 1: SimpleBasePixelDecoder on a unit-norm 64-d embedding map at full
           resolution + PretrainedMeanShiftTransformerDecoder, 6 layers (configs/mixture_UCN.yaml).
 ``crop``  config #3 stage 2: same at 224x224, 8 layers (configs/crop_mixture_UCN.yaml).
+``train`` config #5: the r50 head in training mode with the reference's criterion (deep supervision, 12544 points),
+          synthetic rectangular ground-truth instances; one step = forward + losses + backward + clipped AdamW update.
 Weights are random-init by the modules' own (reference-identical) initialisers under a fixed seed.
 """
 import torch
@@ -101,3 +103,45 @@ def head_flops_per_image(kind):
     f += (n + 1) * (2.0 * Q * C * hw + 2.0 * Q * C * C * 3)  # mask head
     f += sum(2.0 * s * 64 * C for s in set(S))  # input_proj
     return f
+
+
+class HeadTrainer(torch.nn.Module):
+    """Head + criterion with the META_ARCH training contract on backbone FEATURES (the backbone is outside the hot
+    path): forward({'features': dict, 'targets': [{'labels','masks'}]}) -> weighted loss dict
+    (pretrained_meanshiftformer_model.py:303-334)."""
+
+    def __init__(self, head, criterion, height, width):
+        super().__init__()
+        self.sem_seg_head = head
+        self.criterion = criterion
+        self.size = (height, width)
+
+    def forward(self, batch):
+        outputs, _ = self.sem_seg_head(batch["features"], *self.size)
+        losses = self.criterion(outputs, batch["targets"])
+        w = self.criterion.weight_dict
+        return {k: v * w[k] for k, v in losses.items() if k in w}
+
+
+def build_trainer(kind="r50", seed=0):
+    from .meanshiftformer.meanshiftformer_model import build_criterion
+    cfg = HEAD_CFG[kind]
+    head = build_head(kind, seed).train()
+    crit = build_criterion(2, dec_layers=cfg["dec_layers"] + 1)  # DEC_LAYERS counts the learnable-query prediction
+    return HeadTrainer(head, crit, cfg["height"], cfg["width"])
+
+
+def synthetic_targets(kind, batch, instances=5, seed=0):
+    """Per image ``instances`` random axis-aligned rectangles (bool masks at image size) with classes in {0, 1}."""
+    cfg = HEAD_CFG[kind]
+    H, W = cfg["height"], cfg["width"]
+    g = torch.Generator().manual_seed(2000 + seed)
+    out = []
+    for _ in range(batch):
+        masks = torch.zeros(instances, H, W, dtype=torch.bool)
+        for t in range(instances):
+            h, w = int(torch.randint(H // 8, H // 3, (1,), generator=g)), int(torch.randint(W // 8, W // 3, (1,), generator=g))
+            y, x = int(torch.randint(0, H - h, (1,), generator=g)), int(torch.randint(0, W - w, (1,), generator=g))
+            masks[t, y:y + h, x:x + w] = True
+        out.append({"labels": torch.randint(0, 2, (instances,), generator=g), "masks": masks})
+    return out
