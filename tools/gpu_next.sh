@@ -1,0 +1,19 @@
+#!/usr/bin/env bash
+# First GPU call of the next round (run on the B200 box: `gpurun --timeout 1500 -- 'bash tools/gpu_next.sh'`):
+# everything that was written after this round's GPU minutes ran out, in order of risk. Every step runs under
+# `timeout`; logs go to gpurun_out/next_*.log.
+set -x
+mkdir -p gpurun_out
+# 1. the green suite must still be green (the attention finalize kernel gained an optional output)
+timeout 600 python -m pytest tests -q -m gpu -x 2>&1 | tail -5
+# 2. staged parity tests of the training side: attention backward kernel, decoder gradients, whole training steps
+timeout 600 python -m pytest tests -q -m gpu_staged -x 2>&1 | tee gpurun_out/next_staged.log | tail -15
+# 3. the same backward kernel under compute-sanitizer (memcheck), smallest cases only
+timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_staged.py -q -x \
+    -k "golden and vmf" > gpurun_out/next_sanitizer.log 2>&1; tail -5 gpurun_out/next_sanitizer.log
+# 4. experimental packed-operand mean-shift kernel: parity + timing against the shipped one
+timeout 420 python tools/dev_vmf_packed.py quick 2>&1 | tee gpurun_out/next_vmf_packed.log | tail -12
+# 5. training workload (config #5), one GPU
+timeout 600 python bench.py --workload train --steps 5 --warmup 3 > gpurun_out/next_bench_train.json \
+    2> gpurun_out/next_bench_train.err; echo "train bench rc=$?"; cut -c1-600 gpurun_out/next_bench_train.json
+tail -3 gpurun_out/next_bench_train.err
