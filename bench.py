@@ -499,11 +499,13 @@ def run_tail(args, rank, local_rank, world, dev, sharding, ops):
 def run_train(args, rank, local_rank, world, dev, sharding, ops):
     """BASELINE.json config #5: training step of the R50-config head - forward, deep-supervision
     losses (one matcher synchronisation), backward (native vMF attention / MSDeformAttn backward kernels, cuBLAS for
-    the dense layers), DDP gradient all-reduce over NCCL when world > 1, full-model clipping, fused AdamW. fp32
-    (the reference trains under fp16 autocast; mixed precision is an open item). `--batch` images per GPU."""
+    the dense layers), DDP gradient all-reduce over NCCL when world > 1, full-model clipping, fused AdamW. fp32 by
+    default; `--amp bf16|fp16` puts the head under autocast like the reference's trainer (the custom kernels and the
+    pixel decoder stay fp32; fp16 without a GradScaler is for timing only). `--batch` images per GPU."""
     from unseenobjectswithmeanshift_b200 import training, workloads
     B = args.batch
-    model = workloads.build_trainer("r50").to(dev)
+    amp = {"off": None, "bf16": torch.bfloat16, "fp16": torch.float16}[args.amp]
+    model = workloads.build_trainer("r50", amp_dtype=amp).to(dev)
     ddp = training.wrap_ddp(model, local_rank)
     opt = training.build_optimizer(model)
     host_feats = workloads.synthetic_features("r50", B, seed=rank, pin=True)
@@ -552,7 +554,8 @@ def run_train(args, rank, local_rank, world, dev, sharding, ops):
     emit({"metric": "images/sec MSMFormer head training step 640x480 (R50 config: forward + deep-supervision losses + "
                     "backward + clipped AdamW)", "value": B * world * args.steps / (ms_dev / 1e3), "unit": "images/s",
           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
-          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+          "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+          "dtype": "f32" if amp is None else f"{args.amp} autocast (dense layers), f32 kernels", "data": "synthetic",
           "config": {"workload": f"train r50-head 640x480 batch {B}/GPU, 100 queries, 9 decoder layers, 5 instances/image",
                      "global_batch": B * world,
                      "parallelism": f"ddp x{world} (gradient all-reduce over NCCL)" if world > 1 else "single GPU",
@@ -579,6 +582,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--vmf-tflops", action="store_true", help="also time the attention core alone (default with the CPU baseline)")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: leave out the host-buffer leg")
+    ap.add_argument("--amp", default="off", choices=["off", "bf16", "fp16"], help="--workload train: autocast dtype")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -76,9 +76,10 @@ class HungarianMatcher(nn.Module):
         try:
             coords = src.matcher_points(len(layer_outputs), B, self.num_points, dev)  # [layers,B,P,2]
             costs = []
-            for l, out in enumerate(layer_outputs):
-                tgt_points = point_sample(masks, coords[l], align_corners=False)  # [B,Tmax,P]
-                costs.append(self.cost_matrices(out, labels, tgt_points, coords[l]))
+            with torch.autocast(device_type=dev.type, enabled=False):  # fp32 costs, as matcher.py:134-141
+                for l, out in enumerate(layer_outputs):
+                    tgt_points = point_sample(masks, coords[l], align_corners=False)  # [B,Tmax,P]
+                    costs.append(self.cost_matrices(out, labels, tgt_points, coords[l]))
             host = torch.stack(costs).cpu()  # the step's only synchronisation of the matcher
         finally:
             torch.backends.cuda.matmul.allow_tf32 = tf32

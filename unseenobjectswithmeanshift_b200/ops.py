@@ -150,6 +150,7 @@ class VmfAttentionFunction(torch.autograd.Function):
     from torch.autograd through attention_util.py:64-82, saving three [G, Nq, Ns] tensors per call."""
 
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)  # fp32 kernels inside an autocast region
     def forward(ctx, q, k, v, blocked_bits, row_open, add_mask, kappa, normalize_q, normalize_k):
         q, k, v = q.detach(), k.detach(), v.detach()
         out, den = vmf_attention(q, k, v, blocked_bits=blocked_bits, row_open=row_open, add_mask=add_mask,
@@ -162,6 +163,7 @@ class VmfAttentionFunction(torch.autograd.Function):
 
     @staticmethod
     @torch.autograd.function.once_differentiable
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, grad_out):
         q, k, v, out, den = ctx.saved_tensors
         bits, row_open, add_mask = ctx.masks
@@ -220,6 +222,7 @@ class MaskLogitsFunction(torch.autograd.Function):
     g_embed = g_masks . feat^T over the pixels, g_feat = embed^T . g_masks."""
 
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, mask_embed, mask_features):
         e, f = mask_embed.detach().contiguous(), mask_features.detach().contiguous()
         ctx.save_for_backward(e, f)
@@ -227,10 +230,11 @@ class MaskLogitsFunction(torch.autograd.Function):
 
     @staticmethod
     @torch.autograd.function.once_differentiable
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, grad_masks):
         e, f = ctx.saved_tensors
         B, Q, C = e.shape
-        g = grad_masks.reshape(B, Q, -1)
+        g = grad_masks.float().reshape(B, Q, -1)
         ge = gf = None
         tf32 = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = False

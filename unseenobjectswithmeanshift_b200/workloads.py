@@ -110,25 +110,28 @@ class HeadTrainer(torch.nn.Module):
     path): forward({'features': dict, 'targets': [{'labels','masks'}]}) -> weighted loss dict
     (pretrained_meanshiftformer_model.py:303-334)."""
 
-    def __init__(self, head, criterion, height, width):
+    def __init__(self, head, criterion, height, width, amp_dtype=None):
         super().__init__()
         self.sem_seg_head = head
         self.criterion = criterion
         self.size = (height, width)
+        self.amp_dtype = amp_dtype  # torch.bfloat16 / torch.float16: autocast around the head, as the reference trains
 
     def forward(self, batch):
-        outputs, _ = self.sem_seg_head(batch["features"], *self.size)
+        dev = next(iter(batch["features"].values())).device.type
+        with torch.autocast(device_type=dev, dtype=self.amp_dtype or torch.bfloat16, enabled=self.amp_dtype is not None):
+            outputs, _ = self.sem_seg_head(batch["features"], *self.size)
         losses = self.criterion(outputs, batch["targets"])
         w = self.criterion.weight_dict
         return {k: v * w[k] for k, v in losses.items() if k in w}
 
 
-def build_trainer(kind="r50", seed=0):
+def build_trainer(kind="r50", seed=0, amp_dtype=None):
     from .meanshiftformer.meanshiftformer_model import build_criterion
     cfg = HEAD_CFG[kind]
     head = build_head(kind, seed).train()
     crit = build_criterion(2, dec_layers=cfg["dec_layers"] + 1)  # DEC_LAYERS counts the learnable-query prediction
-    return HeadTrainer(head, crit, cfg["height"], cfg["width"])
+    return HeadTrainer(head, crit, cfg["height"], cfg["width"], amp_dtype)
 
 
 def synthetic_targets(kind, batch, instances=5, seed=0):
