@@ -24,8 +24,9 @@ def _require(t, name, dtype=torch.float32):
     if t.dtype != dtype:
         raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
     if t.requires_grad and torch.is_grad_enabled():
-        raise RuntimeError(f"{name} requires grad: this op is forward-only, call it under torch.no_grad() "
-                           "(only MSDeformAttnFunction has a backward)")
+        raise RuntimeError(f"{name} requires grad: this op is forward-only, call it under torch.no_grad() (the "
+                           "differentiable entry points are vmf_attention_autograd, mask_logits_autograd and "
+                           "MSDeformAttnFunction)")
     return t
 
 
