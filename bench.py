@@ -496,6 +496,93 @@ def run_tail(args, rank, local_rank, world, dev, sharding, ops):
     emit(line)
 
 
+def run_twostage(args, rank, local_rank, world, dev, sharding, ops):
+    """BASELINE.json config #3: two-stage RGB-D + zoom-crop refinement, `--batch` frames per GPU (default 16 here).
+    Per frame: stage-1 head (6 layers, 307200 keys) -> label map; depth filter; 5 padded ROI crops at 224x224;
+    stage-2 head (8 layers) on all crops of the frame in one batch; overlap test + paste-back. Random-init weights
+    segment noise, so stage 1 runs in full and is timed, but the map handed to the crop stage is a synthetic one with
+    5 objects per frame (fixes the unit of work: 5 crops per frame). Embedding backbone: synthetic stand-in."""
+    from unseenobjectswithmeanshift_b200 import workloads
+    from unseenobjectswithmeanshift_b200.fcn import test_dataset as td
+    B = args.batch if args.batch != PER_GPU_BATCH else 16
+    K = 5
+    model, model_crop = (m.to(dev) for m in workloads.build_two_stage_models())
+    himg, hdepth, hlabels = workloads.synthetic_frames(B, objects=K, seed=rank)
+    himg, hdepth = himg.pin_memory(), hdepth.pin_memory()
+    img, depth, labels = himg.to(dev), hdepth.to(dev), hlabels.to(dev)
+    host_out = torch.empty(B, 480, 640).pin_memory()
+    kw = dict(topk=False, score=0.7, low_threshold=0.4)
+    sampler = ClockSampler(local_rank)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def frame(im, dp, lab):
+        model.label_maps([{"image": im[0], "depth": dp[0]}], **kw)          # stage 1 (result replaced, see above)
+        out_label = td.filter_labels_depth(lab, dp, 0.5)
+        rgb_crop, mask_crop, rois, depth_crop = td.crop_rois(im, out_label.clone(), dp, crop_size=224)
+        labels_crop, _ = model_crop.label_maps([{"image": rgb_crop, "depth": depth_crop}], **kw)
+        refined, _ = td.match_label_crop(out_label, labels_crop, mask_crop, rois, depth_crop)
+        return refined, rgb_crop.shape[0]
+
+    def step(im, dp):
+        outs, crops = [], 0
+        for f in range(B):
+            r, n = frame(im[f:f + 1], dp[f:f + 1], labels[f:f + 1])
+            outs.append(r)
+            crops += n
+        return outs, crops
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            step(img, depth)
+        ops.reset_stats()
+        _, crops = step(img, depth)
+        launches_per_step = ops.launches()
+        torch.cuda.synchronize()
+        sharding.barrier()
+        if rank == 0:
+            sampler.start()
+        e0.record()
+        for _ in range(args.steps):   # every frame streams a 79 MB embedding map and 315 MB of mask features
+            step(img, depth)
+        e1.record()
+        torch.cuda.synchronize()
+        sharding.barrier()
+        ms_dev = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
+        n_e2e = max(1, min(args.steps, 3))
+        si, sd_ = torch.empty_like(img), torch.empty_like(depth)
+        for timed in (False, True):
+            if timed:
+                e0.record()
+            for _ in range(n_e2e if timed else 1):
+                si.copy_(himg, non_blocking=True)
+                sd_.copy_(hdepth, non_blocking=True)
+                outs, _ = step(si, sd_)
+                host_out.copy_(torch.cat(outs), non_blocking=True)
+            if timed:
+                e1.record()
+            torch.cuda.synchronize()
+            sharding.barrier()
+        ms_e2e = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        return
+    emit({"metric": "frames/sec two-stage RGB-D segmentation 640x480 (stage-1 head + 5 zoom-crops through the crop head "
+                    "+ paste-back)", "value": B * world * args.steps / (ms_dev / 1e3), "unit": "images/s",
+          "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+          "config": {"workload": f"twostage 640x480 batch {B}/GPU, {crops} crops of 224x224 per step, stage 1: 6 layers, "
+                                 f"stage 2: 8 layers", "global_batch": B * world, "launch": "eager, one frame per call",
+                     "parallelism": f"replicas x{world} (batch-sharded, no collective)",
+                     "l2_policy": "inputs_exceed_l2 (315 MB of mask features per frame)",
+                     "backbone": "synthetic 1x1 stand-in: the UCN embedding network is outside the hot path (SURVEY.md 8)"},
+          "clocks": clocks,
+          "e2e": {"value": B * world * n_e2e / (ms_e2e / 1e3), "unit": "images/s",
+                  "h2d_bytes_per_step": (himg.numel() + hdepth.numel()) * 4, "d2h_bytes_per_step": host_out.numel() * 4,
+                  "ms_per_step": ms_e2e / n_e2e},
+          "gpu_launches": launches_per_step * args.steps, "roofline": None, "cpu_baseline": None,
+          "note": "auxiliary workload (config #3 end to end); per-kernel rooflines are on the ucn / crop lines"})
+
+
 def run_train(args, rank, local_rank, world, dev, sharding, ops):
     """BASELINE.json config #5: training step of the R50-config head - forward, deep-supervision
     losses (one matcher synchronisation), backward (native vMF attention / MSDeformAttn backward kernels, cuBLAS for
@@ -576,7 +663,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="r50", choices=["r50", "ucn", "crop", "meanshift", "cluster", "tail", "train"])
+    ap.add_argument("--workload", default="r50", choices=["r50", "ucn", "crop", "meanshift", "cluster", "tail", "train", "twostage"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
@@ -613,6 +700,9 @@ def main():
         return
     if kind == "train":
         run_train(args, rank, local_rank, world, dev, sharding, ops)
+        return
+    if kind == "twostage":
+        run_twostage(args, rank, local_rank, world, dev, sharding, ops)
         return
 
     head = workloads.build_head(kind).to(dev)

@@ -17,3 +17,7 @@ timeout 420 python tools/dev_vmf_packed.py quick 2>&1 | tee gpurun_out/next_vmf_
 timeout 600 python bench.py --workload train --steps 5 --warmup 3 > gpurun_out/next_bench_train.json \
     2> gpurun_out/next_bench_train.err; echo "train bench rc=$?"; cut -c1-600 gpurun_out/next_bench_train.json
 tail -3 gpurun_out/next_bench_train.err
+# 6. two-stage pipeline end to end (config #3), one GPU
+timeout 600 python bench.py --workload twostage --steps 3 --warmup 3 > gpurun_out/next_bench_twostage.json \
+    2> gpurun_out/next_bench_twostage.err; echo "twostage bench rc=$?"; cut -c1-600 gpurun_out/next_bench_twostage.json
+tail -3 gpurun_out/next_bench_twostage.err

@@ -5,6 +5,9 @@
 ``ucn``   config #1/#3 stage 1: SimpleBasePixelDecoder on a unit-norm 64-d embedding map at full
           resolution + PretrainedMeanShiftTransformerDecoder, 6 layers (configs/mixture_UCN.yaml).
 ``crop``  config #3 stage 2: same at 224x224, 8 layers (configs/crop_mixture_UCN.yaml).
+``twostage`` config #3 end to end: stage 1 (``ucn`` head) on every frame, K objects per frame cropped to 224x224,
+          stage 2 (``crop`` head) on all crops of a frame in one batch, overlap test and paste-back
+          (lib/fcn/test_utils.py:245-420 via fcn.test_utils / fcn.test_dataset).
 ``train`` config #5: the r50 head in training mode with the reference's criterion (deep supervision, 12544 points),
           synthetic rectangular ground-truth instances; one step = forward + losses + backward + clipped AdamW update.
 Weights are random-init by the modules' own (reference-identical) initialisers under a fixed seed.
@@ -148,3 +151,49 @@ def synthetic_targets(kind, batch, instances=5, seed=0):
             masks[t, y:y + h, x:x + w] = True
         out.append({"labels": torch.randint(0, 2, (instances,), generator=g), "masks": masks})
     return out
+
+
+class SyntheticEmbedding(torch.nn.Module):
+    """Stand-in for the UCN embedding backbone (lib/networks/SEG.py, outside the hot path): a 1x1 projection of
+    image (+ depth) to 64 channels, so that the two-stage pipeline runs end to end on synthetic frames."""
+
+    def __init__(self, seed=0):
+        super().__init__()
+        g = torch.Generator().manual_seed(3000 + seed)
+        self.weight = torch.nn.Parameter(torch.randn(64, 3, 1, 1, generator=g))
+
+    def forward(self, image, label=None, depth=None):
+        return F.conv2d(image if depth is None else image + depth, self.weight)
+
+
+def build_two_stage_models(seed=0):
+    """-> (stage-1 model, crop model): PretrainedMeanShiftMaskFormer wrappers around the ``ucn`` / ``crop`` heads with
+    the synthetic embedding backbone, eval mode."""
+    from .meanshiftformer import PretrainedMeanShiftMaskFormer
+    models = []
+    for i, kind in enumerate(("ucn", "crop")):
+        models.append(PretrainedMeanShiftMaskFormer(
+            backbone=SyntheticEmbedding(seed + i), sem_seg_head=build_head(kind, seed + i), criterion=None,
+            num_queries=100, object_mask_threshold=0.8, overlap_threshold=0.8, metadata=None, size_divisibility=0,
+            sem_seg_postprocess_before_inference=True, pixel_mean=[0.0, 0.0, 0.0], pixel_std=[1.0, 1.0, 1.0],
+            semantic_on=False, panoptic_on=False, instance_on=True, test_topk_per_image=20, use_depth=True).eval())
+    return models
+
+
+def synthetic_frames(batch, objects=5, seed=0, height=480, width=640):
+    """RGB-D frames + a stage-1 label map with ``objects`` disjoint rectangles per frame (ids 2..objects+1, the ids
+    get_confident_instances produces, lib/fcn/test_utils.py:35-52). Random-init networks segment noise, so the bench
+    substitutes this map for stage 1's output to fix the number of crops (SURVEY.md 8d, config #3: K = 5)."""
+    g = torch.Generator().manual_seed(4000 + seed)
+    image = torch.rand(batch, 3, height, width, generator=g) - 0.5
+    depth = torch.rand(batch, 3, height, width, generator=g) * 1.2 + 0.3
+    labels = torch.zeros(batch, height, width)
+    cell = width // objects
+    for b in range(batch):
+        for k in range(objects):
+            h = int(torch.randint(height // 6, height // 2, (1,), generator=g))
+            w = int(torch.randint(cell // 3, cell - 8, (1,), generator=g))
+            y = int(torch.randint(4, height - h - 4, (1,), generator=g))
+            x = k * cell + int(torch.randint(2, cell - w - 2, (1,), generator=g))
+            labels[b, y:y + h, x:x + w] = k + 2
+    return image, depth, labels
