@@ -1,0 +1,98 @@
+// Host emulation of the small CUDA subset the CUDA-core kernels use (test infrastructure only).
+//
+// Purpose: EXECUTE the text of a __global__ kernel on the CPU when no GPU is at hand - every CUDA thread of a block is
+// an OS thread, __syncthreads() is a barrier over the block, warp shuffles exchange through a per-warp slot array.
+// Blocks run one after the other. Only what csrc/vmf_attention_bwd.cu needs is provided (no tcgen05 / TMA / atomics).
+// The kernel source is #included unchanged by the emulation driver with MSM_EMULATE_ON_HOST defined, which hides the
+// host-side launch code (<<< >>> is not C++).
+#pragma once
+#include <cuda_runtime.h>  // vector types (float4, uint3, dim3), cudaStream_t: host-side headers only
+
+#include <algorithm>
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#undef __global__
+#undef __device__
+#undef __host__
+#undef __shared__
+#undef __forceinline__
+#undef __launch_bounds__
+#undef __align__
+#define __global__
+#define __device__
+#define __host__
+#define __shared__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __align__(n) __attribute__((aligned(n)))
+
+namespace cuda_emu {
+struct BlockState {
+  std::unique_ptr<std::barrier<>> block_barrier;
+  std::vector<std::unique_ptr<std::barrier<>>> warp_barrier;
+  std::vector<std::vector<uint32_t>> warp_slots;  // [warp][32]
+};
+inline BlockState* g_block = nullptr;
+}  // namespace cuda_emu
+
+inline thread_local uint3 threadIdx, blockIdx;
+inline thread_local dim3 blockDim, gridDim;
+
+inline void __syncthreads() { cuda_emu::g_block->block_barrier->arrive_and_wait(); }
+
+// all 32 lanes of the warp take part (the kernels only use the full mask)
+inline uint32_t emu_shfl_xor_bits(uint32_t v, int lane_mask) {
+  auto* b = cuda_emu::g_block;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  b->warp_slots[warp][lane] = v;
+  b->warp_barrier[warp]->arrive_and_wait();
+  const uint32_t r = b->warp_slots[warp][lane ^ lane_mask];
+  b->warp_barrier[warp]->arrive_and_wait();
+  return r;
+}
+inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
+  uint32_t u;
+  std::memcpy(&u, &v, 4);
+  u = emu_shfl_xor_bits(u, lane_mask);
+  std::memcpy(&v, &u, 4);
+  return v;
+}
+template <typename T>
+inline T __ldg(const T* p) { return *p; }
+using std::max;
+using std::min;
+
+namespace cuda_emu {
+// run `body()` as a grid of blocks of `threads` threads (1-D blocks, 2-D grid), one block at a time
+inline void launch(dim3 grid, int threads, const std::function<void()>& body) {
+  for (unsigned by = 0; by < grid.y; ++by)
+    for (unsigned bx = 0; bx < grid.x; ++bx) {
+      BlockState st;
+      st.block_barrier = std::make_unique<std::barrier<>>(threads);
+      const int warps = (threads + 31) / 32;
+      for (int w = 0; w < warps; ++w) {
+        st.warp_barrier.push_back(std::make_unique<std::barrier<>>(std::min(32, threads - 32 * w)));
+        st.warp_slots.emplace_back(32, 0u);
+      }
+      g_block = &st;
+      std::vector<std::thread> pool;
+      for (int t = 0; t < threads; ++t)
+        pool.emplace_back([=, &body] {
+          threadIdx = uint3{(unsigned)t, 0, 0};
+          blockIdx = uint3{bx, by, 0};
+          blockDim = dim3(threads, 1, 1);
+          gridDim = grid;
+          body();
+        });
+      for (auto& th : pool) th.join();
+      g_block = nullptr;
+    }
+}
+}  // namespace cuda_emu

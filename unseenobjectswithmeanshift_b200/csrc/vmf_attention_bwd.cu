@@ -365,9 +365,16 @@ template <int HD>
 static int launch(const Params& P, int G, cudaStream_t st) {
   const size_t smem =
       ((size_t)(2 * kQT + 2 * kKT) * (HD + 4) + 2 * (size_t)kQT * kPS + 2 * kQT + kKT) * sizeof(float);
+#ifdef MSM_EMULATE_ON_HOST  // tests/emu: the kernel text executed on CPU threads (no GPU in the authoring container)
+  (void)st;
+  if (smem > sizeof(float) * cuda_emu_smem_floats) return MSM_E_UNSUPPORTED;
+  cuda_emu::launch(dim3(P.nsplit, G), kThreads, [&] { vmf_bwd_kernel<HD>(P); });
+  return 0;
+#else
   MSM_CUDA(cudaFuncSetAttribute(vmf_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   vmf_bwd_kernel<HD><<<dim3(P.nsplit, G), kThreads, smem, st>>>(P);
   return check_launch("vmf_bwd_kernel");
+#endif
 }
 
 }  // namespace vbw
@@ -430,8 +437,16 @@ extern "C" int msm_vmf_attention_bwd(const float* q, int64_t q_sb, int64_t q_sh,
   const int rc = HD == 32 ? vbw::launch<32>(P, G, st) : vbw::launch<64>(P, G, st);
   if (rc) return rc;
   const int warps = G * Nq;
+#ifdef MSM_EMULATE_ON_HOST
+  cuda_emu::launch(dim3((warps * 32 + 255) / 256, 1), 256, [&] {
+    vbw::vmf_bwd_finalize_kernel(P.part_gq, q, q_sb, q_sh, q_sl, grad_q, gq_sb, gq_sh, gq_sl, G, heads, Nq, hd, HD,
+                                 P.nsplit, (flags & MSM_VMF_NORMALIZE_Q) ? 1 : 0);
+  });
+  return 0;
+#else
   vbw::vmf_bwd_finalize_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(
       P.part_gq, q, q_sb, q_sh, q_sl, grad_q, gq_sb, gq_sh, gq_sl, G, heads, Nq, hd, HD, P.nsplit,
       (flags & MSM_VMF_NORMALIZE_Q) ? 1 : 0);
   return check_launch("vmf_bwd_finalize_kernel");
+#endif
 }
