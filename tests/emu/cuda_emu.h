@@ -10,6 +10,11 @@
 
 #include <algorithm>
 #include <barrier>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <mutex>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -34,10 +39,19 @@
 #define __align__(n) __attribute__((aligned(n)))
 
 namespace cuda_emu {
+[[noreturn]] inline void die(const char* what) {
+  std::fprintf(stderr, "cuda_emu: %s\n", what);
+  std::fflush(stderr);
+  std::_Exit(3);
+}
+inline std::chrono::steady_clock::time_point g_deadline = std::chrono::steady_clock::time_point::max();
+inline bool g_deadline_passed() { return std::chrono::steady_clock::now() > g_deadline; }
 struct BlockState {
   std::unique_ptr<std::barrier<>> block_barrier;
   std::vector<std::unique_ptr<std::barrier<>>> warp_barrier;
   std::vector<std::vector<uint32_t>> warp_slots;  // [warp][32]
+  std::mutex named_mu;
+  std::map<std::pair<int, int>, std::unique_ptr<std::barrier<>>> named;  // bar.sync id, nthreads
 };
 inline BlockState* g_block = nullptr;
 }  // namespace cuda_emu
@@ -46,6 +60,19 @@ inline thread_local uint3 threadIdx, blockIdx;
 inline thread_local dim3 blockDim, gridDim;
 
 inline void __syncthreads() { cuda_emu::g_block->block_barrier->arrive_and_wait(); }
+inline void __syncwarp() { cuda_emu::g_block->warp_barrier[threadIdx.x >> 5]->arrive_and_wait(); }
+// bar.sync id, nthreads: the first `nthreads` arrivals on barrier `id` release each other
+inline void emu_named_bar_sync(int id, int nthreads) {
+  std::barrier<>* bar;
+  {
+    auto* b = cuda_emu::g_block;
+    std::lock_guard<std::mutex> l(b->named_mu);
+    auto& slot = b->named[{id, nthreads}];
+    if (!slot) slot = std::make_unique<std::barrier<>>(nthreads);
+    bar = slot.get();
+  }
+  bar->arrive_and_wait();
+}
 
 // all 32 lanes of the warp take part (the kernels only use the full mask)
 inline uint32_t emu_shfl_xor_bits(uint32_t v, int lane_mask) {
@@ -66,15 +93,27 @@ inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
 }
 template <typename T>
 inline T __ldg(const T* p) { return *p; }
+inline float __uint_as_float(uint32_t u) {
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+inline uint32_t __float_as_uint(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  return u;
+}
 using std::max;
 using std::min;
 
 namespace cuda_emu {
 // run `body()` as a grid of blocks of `threads` threads (1-D blocks, 2-D grid), one block at a time
+inline std::function<void()> g_block_begin;  // optional: called before every block (the tc layer resets its state)
 inline void launch(dim3 grid, int threads, const std::function<void()>& body) {
   for (unsigned by = 0; by < grid.y; ++by)
     for (unsigned bx = 0; bx < grid.x; ++bx) {
       BlockState st;
+      if (g_block_begin) g_block_begin();
       st.block_barrier = std::make_unique<std::barrier<>>(threads);
       const int warps = (threads + 31) / 32;
       for (int w = 0; w < warps; ++w) {

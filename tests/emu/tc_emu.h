@@ -1,0 +1,259 @@
+// Host emulation of the msm::tc layer (csrc/tc.cuh): mbarrier, tcgen05 (alloc / mma / commit / ld / st with TMEM),
+// shared-memory matrix descriptors (no swizzle), 1-D bulk copies and the hi/lo operand splits - test infrastructure.
+//
+// Included INSTEAD of the body of tc.cuh when MSM_EMULATE_ON_HOST is defined (tc.cuh forwards here), so that the text
+// of a tensor-core kernel runs on CPU threads (cuda_emu.h). Semantics are the ones tc.cuh documents and the shipped
+// kernels rely on; they are CALIBRATED by running vmf_attn_tc_kernel - green on the B200 - through this emulation
+// (tests/test_kernel_emulation.py) before any not-yet-run kernel is judged with it. MMAs execute synchronously at issue
+// (the tensor pipe is in-order and every consumer waits on a commit barrier, so program-order execution is one legal
+// schedule); races that only asynchrony exposes are NOT detected - that stays the job of the GPU run.
+#pragma once
+#include <atomic>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <thread>
+
+#include "cuda_emu.h"
+
+namespace msm {
+namespace tc {
+
+// ------------------------------------------------------------------------------------------ per-block state
+struct MbarState {
+  uint32_t init = 0;
+  int64_t pending = 0, tx = 0;
+  uint32_t phase = 0;  // parity of the phase in progress
+};
+struct EmuState {
+  std::mutex mu;
+  std::map<uintptr_t, MbarState> bars;
+  std::vector<uint32_t> tmem = std::vector<uint32_t>(128 * 512, 0u);  // [lane][column]
+  uintptr_t smem_base = 0;                                             // generic address of shared-memory offset 0
+};
+inline EmuState* g_tc = nullptr;  // set by the driver for the running block
+
+// shared-memory addresses are byte offsets from the start of the block's dynamic shared memory, as on the device
+inline uint32_t smem_u32(const void* p) { return (uint32_t)(reinterpret_cast<uintptr_t>(p) - g_tc->smem_base); }
+inline uint8_t* smem_ptr(uint32_t saddr) { return reinterpret_cast<uint8_t*>(g_tc->smem_base + saddr); }
+
+// ------------------------------------------------------------------------------------------ mbarrier
+inline void mbar_complete_if_done(MbarState& b) {
+  if (b.pending == 0 && b.tx == 0) {
+    b.phase ^= 1u;
+    b.pending = b.init;
+  }
+}
+inline void mbar_init(uint64_t* bar, uint32_t count) {
+  std::lock_guard<std::mutex> l(g_tc->mu);
+  MbarState& b = g_tc->bars[reinterpret_cast<uintptr_t>(bar)];
+  b = MbarState();
+  b.init = count;
+  b.pending = count;
+}
+inline void fence_mbar_init() {}
+inline void fence_proxy_async() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline void mbar_arrive(uint64_t* bar) {
+  std::lock_guard<std::mutex> l(g_tc->mu);
+  MbarState& b = g_tc->bars.at(reinterpret_cast<uintptr_t>(bar));
+  b.pending -= 1;
+  mbar_complete_if_done(b);
+}
+inline void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  std::lock_guard<std::mutex> l(g_tc->mu);
+  MbarState& b = g_tc->bars.at(reinterpret_cast<uintptr_t>(bar));
+  b.tx += bytes;
+  b.pending -= 1;
+  mbar_complete_if_done(b);
+}
+inline void mbar_complete_tx(uint64_t* bar, uint32_t bytes) {
+  std::lock_guard<std::mutex> l(g_tc->mu);
+  MbarState& b = g_tc->bars.at(reinterpret_cast<uintptr_t>(bar));
+  b.tx -= bytes;
+  mbar_complete_if_done(b);
+}
+inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) {  // true once the phase of this parity has completed
+  std::lock_guard<std::mutex> l(g_tc->mu);
+  return g_tc->bars.at(reinterpret_cast<uintptr_t>(bar)).phase != (parity & 1u);
+}
+inline void mbar_wait(uint64_t* bar, uint32_t parity) {
+  int spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins < 64) std::this_thread::yield();
+    else std::this_thread::sleep_for(std::chrono::microseconds(50));
+    if (cuda_emu::g_deadline_passed()) cuda_emu::die("mbar_wait: no progress (deadlock in the barrier protocol?)");
+  }
+}
+struct Ring {
+  uint32_t stage = 0, phase = 0;
+  inline void advance(uint32_t nstages) {
+    if (++stage == nstages) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
+};
+
+// 1-D bulk copy global -> shared, completing `bytes` of transaction on the barrier
+inline void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  std::memcpy(dst, src, bytes);
+  std::atomic_thread_fence(std::memory_order_seq_cst);
+  mbar_complete_tx(bar, bytes);
+}
+
+// ------------------------------------------------------------------------------------------ tcgen05 / TMEM
+inline uint32_t& tmem_at(uint32_t taddr, uint32_t lane_off, uint32_t col_off) {
+  const uint32_t lane = ((taddr >> 16) & 0xffffu) + lane_off, col = (taddr & 0xffffu) + col_off;
+  if (lane >= 128 || col >= 512) cuda_emu::die("TMEM access out of range");
+  return g_tc->tmem[lane * 512 + col];
+}
+inline void tmem_alloc(uint32_t* dst_smem, uint32_t) { *dst_smem = 0u; }
+inline void tmem_dealloc(uint32_t, uint32_t) {}
+inline void tc_fence_before() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline void tc_fence_after() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+
+inline float bf16_to_f32(uint16_t h) {
+  const uint32_t u = (uint32_t)h << 16;
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+inline float f16_to_f32(uint16_t h) {
+  const uint32_t sign = (h >> 15) & 1u, exp = (h >> 10) & 0x1fu, man = h & 0x3ffu;
+  float v;
+  if (exp == 0) v = std::ldexp((float)man, -24);
+  else if (exp == 31) v = man ? NAN : INFINITY;
+  else v = std::ldexp((float)(man | 0x400u), (int)exp - 25);
+  return sign ? -v : v;
+}
+struct IDesc {
+  int M, N;
+  bool a_bf16, b_bf16, a_mn, b_mn;
+};
+inline IDesc decode_idesc(uint32_t d) {
+  IDesc r;
+  r.a_bf16 = ((d >> 7) & 7u) == 1u;
+  r.b_bf16 = ((d >> 10) & 7u) == 1u;
+  r.a_mn = (d >> 15) & 1u;
+  r.b_mn = (d >> 16) & 1u;
+  r.N = (int)((d >> 17) & 0x3fu) << 3;
+  r.M = (int)((d >> 24) & 0x1fu) << 4;
+  return r;
+}
+// element (mn, k) of a no-swizzle canonical operand described by `desc` (layouts in tc.cuh)
+inline uint16_t smem_operand(uint64_t desc, bool mn_major, int mn, int k) {
+  const uint32_t addr = (uint32_t)(desc & 0x3fffu) << 4, lbo = (uint32_t)((desc >> 16) & 0x3fffu) << 4,
+                 sbo = (uint32_t)((desc >> 32) & 0x3fffu) << 4;
+  if (((desc >> 61) & 7u) != 0) cuda_emu::die("emulation: only the no-swizzle layout is implemented");
+  const uint32_t off = mn_major ? (uint32_t)((mn % 8) * 2 + (k % 8) * 16 + (mn / 8) * sbo + (k / 8) * lbo)
+                                : (uint32_t)((k % 8) * 2 + (mn % 8) * 16 + (mn / 8) * sbo + (k / 8) * lbo);
+  uint16_t v;
+  std::memcpy(&v, smem_ptr(addr) + off, 2);  // 14-bit address field << 4 = offset within the 256 KB window
+  return v;
+}
+inline void mma_common(uint32_t tmem_d, const float (*a)[16], uint64_t desc_b, const IDesc& id, uint32_t accumulate) {
+  for (int m = 0; m < id.M; ++m)
+    for (int n = 0; n < id.N; ++n) {
+      float acc = 0.f;
+      for (int k = 0; k < 16; ++k) {
+        const uint16_t bv = smem_operand(desc_b, id.b_mn, n, k);
+        acc += a[m][k] * (id.b_bf16 ? bf16_to_f32(bv) : f16_to_f32(bv));
+      }
+      uint32_t& d = tmem_at(tmem_d, m, n);
+      float prev;
+      std::memcpy(&prev, &d, 4);
+      const float r = accumulate ? prev + acc : acc;
+      std::memcpy(&d, &r, 4);
+    }
+}
+// D[tmem] (+)= A[tmem] * B[smem]: A row m = TMEM lane m, 8 columns of two 16-bit K elements each (K-major)
+inline void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  const IDesc id = decode_idesc(idesc);
+  if (id.a_mn) cuda_emu::die("emulation: TMEM A operand must be K-major");
+  static thread_local float a[128][16];
+  for (int m = 0; m < id.M; ++m)
+    for (int c = 0; c < 8; ++c) {
+      const uint32_t w = tmem_at(tmem_a, m, c);
+      a[m][2 * c] = id.a_bf16 ? bf16_to_f32(w & 0xffffu) : f16_to_f32(w & 0xffffu);
+      a[m][2 * c + 1] = id.a_bf16 ? bf16_to_f32(w >> 16) : f16_to_f32(w >> 16);
+    }
+  std::lock_guard<std::mutex> l(g_tc->mu);  // one tensor pipe
+  mma_common(tmem_d, a, desc_b, id, accumulate);
+}
+inline void mma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  const IDesc id = decode_idesc(idesc);
+  static thread_local float a[128][16];
+  for (int m = 0; m < id.M; ++m)
+    for (int k = 0; k < 16; ++k) {
+      const uint16_t v = smem_operand(desc_a, id.a_mn, m, k);
+      a[m][k] = id.a_bf16 ? bf16_to_f32(v) : f16_to_f32(v);
+    }
+  std::lock_guard<std::mutex> l(g_tc->mu);
+  mma_common(tmem_d, a, desc_b, id, accumulate);
+}
+inline void mma_commit(uint64_t* bar) { mbar_arrive(bar); }  // every MMA issued so far has already executed
+
+inline void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  const uint32_t lane = threadIdx.x & 31;
+  if ((((taddr >> 16) & 0xffffu) / 32) != ((threadIdx.x >> 5) & 3u)) cuda_emu::die("tcgen05.ld outside the warp's lane quadrant");
+  for (int i = 0; i < 16; ++i) r[i] = tmem_at(taddr, lane, i);
+}
+inline void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  const uint32_t lane = threadIdx.x & 31;
+  if ((((taddr >> 16) & 0xffffu) / 32) != ((threadIdx.x >> 5) & 3u)) cuda_emu::die("tcgen05.ld outside the warp's lane quadrant");
+  for (int i = 0; i < 32; ++i) r[i] = tmem_at(taddr, lane, i);
+}
+inline void tmem_ld_wait() {}
+inline void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  const uint32_t lane = threadIdx.x & 31;
+  if ((((taddr >> 16) & 0xffffu) / 32) != ((threadIdx.x >> 5) & 3u)) cuda_emu::die("tcgen05.st outside the warp's lane quadrant");
+  for (int i = 0; i < 16; ++i) tmem_at(taddr, lane, i) = r[i];
+}
+inline void tmem_st_wait() {}
+
+// ------------------------------------------------------------------------------------------ descriptors (as tc.cuh)
+inline uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+constexpr uint32_t idesc_bf16(int M, int N, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+constexpr uint32_t idesc_f16(int M, int N, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------ operand splits
+inline uint16_t f32_to_bf16_rn(float x) {
+  uint32_t u;
+  std::memcpy(&u, &x, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40u);  // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+inline uint32_t pack_bf16(float x, float y) { return (uint32_t)f32_to_bf16_rn(x) | ((uint32_t)f32_to_bf16_rn(y) << 16); }
+inline void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16(x, y);
+  const float xh = bf16_to_f32(hi & 0xffffu), yh = bf16_to_f32(hi >> 16);
+  lo = pack_bf16(x - xh, y - yh);
+}
+inline uint16_t f32_to_f16_rn(float x) {
+  const _Float16 h = (_Float16)x;  // round-to-nearest-even (x86-64 gcc: soft-float or F16C)
+  uint16_t u;
+  std::memcpy(&u, &h, 2);
+  return u;
+}
+inline void split2h(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const uint16_t hx = f32_to_f16_rn(x), hy = f32_to_f16_rn(y);
+  hi = (uint32_t)hx | ((uint32_t)hy << 16);
+  lo = (uint32_t)f32_to_f16_rn(x - f16_to_f32(hx)) | ((uint32_t)f32_to_f16_rn(y - f16_to_f32(hy)) << 16);
+}
+constexpr bool kGemmF16 = true;
+inline void split2g(float x, float y, uint32_t& hi, uint32_t& lo) { split2h(x, y, hi, lo); }
+constexpr uint32_t idesc_g(int M, int N, bool a, bool b) { return idesc_f16(M, N, a, b); }
+
+}  // namespace tc
+}  // namespace msm

@@ -1,11 +1,18 @@
-"""The TEXT of the CUDA-core training kernel (csrc/vmf_attention_bwd.cu), executed on CPU threads.
+"""The TEXT of CUDA kernels executed on CPU threads (tests/emu).
 
-The authoring container has no GPU and the round's GPU minutes were spent before this kernel was written, so its
-source is compiled as plain C++ against tests/emu/cuda_emu.h (every CUDA thread an OS thread, __syncthreads a barrier,
-warp shuffles through a per-warp slot array) and driven through the SAME C entry point, msm_vmf_attention_bwd. This
-checks indexing, tiling, masks, strides and the split reduction of the real source against the reference's gradients
-(golden) and fp64 autograd; it says nothing about what nvcc / the hardware do with it - that is the staged GPU test
-(tests/test_gpu_staged.py)."""
+The authoring container has no GPU and the round's GPU minutes were spent before some kernels were written, so their
+sources are compiled as plain C++ against tests/emu/cuda_emu.h (every CUDA thread an OS thread, __syncthreads a
+barrier, warp shuffles through a per-warp slot array) and tests/emu/tc_emu.h (mbarrier, TMEM, tcgen05.mma with
+no-swizzle shared-memory descriptors, bulk copies) and driven through their real host entry points:
+
+* csrc/vmf_attention_bwd.cu (training, CUDA cores): against the reference's gradients (golden) and fp64 autograd;
+* csrc/vmf_attention_tc.cu (SHIPPED tcgen05 kernel, parity-green on the B200): the CALIBRATION of the tensor-core
+  emulation - it has to reproduce what the hardware is known to produce for this kernel;
+* csrc/experimental/vmf_packed.cu (tcgen05 + bulk copies, not yet run on a GPU): judged with the calibrated emulation.
+
+This checks indexing, tiling, masks, strides, descriptors and barrier protocols of the real source. MMAs execute
+synchronously at issue, so hazards that only hardware asynchrony exposes are not detected, and nothing is said about
+what nvcc / the hardware do with the code - that is the job of the staged GPU runs (tools/gpu_next.sh)."""
 import ctypes
 import os
 import shutil
@@ -21,19 +28,25 @@ EMU_LIB = os.path.join(ROOT, "build", "emu", "libemu_vmf_bwd.so")
 CUDA_INC = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
 
 
-@pytest.fixture(scope="module")
-def emu():
+CSRC = os.path.join(ROOT, "unseenobjectswithmeanshift_b200", "csrc")
+
+
+def _build(lib, driver, sources):
     if shutil.which("g++") is None or not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
         pytest.skip("needs g++ and the CUDA headers")
-    srcs = [os.path.join(EMU_DIR, "emu_vmf_bwd.cpp"), os.path.join(EMU_DIR, "cuda_emu.h"),
-            os.path.join(ROOT, "unseenobjectswithmeanshift_b200", "csrc", "vmf_attention_bwd.cu"),
-            os.path.join(ROOT, "unseenobjectswithmeanshift_b200", "csrc", "common.cuh")]
-    if not os.path.exists(EMU_LIB) or any(os.path.getmtime(s) > os.path.getmtime(EMU_LIB) for s in srcs):
-        os.makedirs(os.path.dirname(EMU_LIB), exist_ok=True)
+    deps = [os.path.join(EMU_DIR, f) for f in (driver, "cuda_emu.h", "tc_emu.h")] + \
+           [os.path.join(CSRC, f) for f in sources + ["common.cuh", "tc.cuh"]]
+    if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
+        os.makedirs(os.path.dirname(lib), exist_ok=True)
         subprocess.check_call(["g++", "-std=c++20", "-O1", "-w", "-shared", "-fPIC", "-pthread", "-DMSM_EMULATE_ON_HOST",
-                               "-I" + CUDA_INC, "-x", "c++", srcs[0], "-o", EMU_LIB])
+                               "-I" + CUDA_INC, "-I" + EMU_DIR, "-x", "c++", deps[0], "-o", lib])
+    return ctypes.CDLL(lib)
+
+
+@pytest.fixture(scope="module")
+def emu():
     from unseenobjectswithmeanshift_b200._lib import SIGNATURES
-    h = ctypes.CDLL(EMU_LIB)
+    h = _build(EMU_LIB, "emu_vmf_bwd.cpp", ["vmf_attention_bwd.cu"])
     for name in ("msm_vmf_attention_bwd", "msm_vmf_attention_bwd_workspace_bytes"):
         fn = getattr(h, name)
         fn.restype, fn.argtypes = SIGNATURES[name]
@@ -159,3 +172,102 @@ def test_emulated_entry_point_rejects_bad_arguments(emu):
     args = (*st(q), *st(k), *st(k), *st(out), *st(out), den.data_ptr(), *st(g), *st(gk), *st(gk), None, 0, None, None,
             1, 1, 100, 64, 32, 30.0, 3, None, 0, None)
     assert h.msm_vmf_attention_bwd(*args) == -3          # MSM_E_WORKSPACE: no workspace
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# tensor-core kernels through tests/emu/tc_emu.h
+@pytest.fixture(scope="module")
+def emu_tc():
+    h = _build(os.path.join(ROOT, "build", "emu", "libemu_vmf_tc.so"), "emu_vmf_tc.cpp",
+               ["vmf_attention_tc.cu", os.path.join("experimental", "vmf_packed.cu")])
+    P, I, L, Fl, Z, D = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t, ctypes.c_double
+    h.emu_last_error.restype = ctypes.c_char_p
+    h.emu_set_timeout.argtypes = [D]
+    h.emu_vmf_tc_workspace_bytes.restype, h.emu_vmf_tc_workspace_bytes.argtypes = Z, [I, I, I, I]
+    h.emu_vmf_attention_tc_partial.restype = I
+    h.emu_vmf_attention_tc_partial.argtypes = [P, L, L, L] * 3 + [P, I, P, I, I, I, I, I, Fl, I, P, P, D]
+    h.msmx_mean_shift_packed_bytes.restype, h.msmx_mean_shift_packed_bytes.argtypes = Z, [I, I, I]
+    h.msmx_mean_shift_packed_workspace_bytes.restype = Z
+    h.msmx_mean_shift_packed_workspace_bytes.argtypes = [I, I, I, I]
+    h.msmx_mean_shift_pack.restype, h.msmx_mean_shift_pack.argtypes = I, [P, P, I, I, I, P]
+    h.msmx_mean_shift_hill_climb_packed.restype = I
+    h.msmx_mean_shift_hill_climb_packed.argtypes = [P, P, P, I, I, I, I, Fl, I, P, Z, P]
+    return h
+
+
+@pytest.mark.parametrize("B,H,Q,S,hd,shared,masked", [
+    (1, 1, 20, 300, 32, False, False),    # fp16 score operands (q and k normalised by the kernel), 3 key tiles
+    (1, 2, 100, 700, 32, False, True),    # bit mask shared by the heads, 6 tiles: the 4-stage ring wraps
+    (1, 1, 100, 333, 64, True, False),    # mean-shift form: k == v, one bf16 copy serves both products
+])
+def test_calibration_shipped_tcgen05_attention_kernel(emu_tc, B, H, Q, S, hd, shared, masked):
+    """vmf_attn_tc_kernel is parity-green on the B200 (tests/test_gpu_parity.py); the emulation must agree with it -
+    i.e. with the fp64 reference at split-precision accuracy - before it is used to judge anything else."""
+    h = emu_tc
+    torch.manual_seed(S + hd)
+    C = H * hd
+    q, k = torch.randn(B, Q, C), torch.randn(B, S, C)
+    v = k if shared else torch.randn(B, S, C)
+    kappa, flags = (10.0, 0) if shared else (30.0, 3)
+    if shared:
+        k = v = F.normalize(k.view(B, S, H, hd), dim=-1).view(B, S, C)
+        q = F.normalize(q.view(B, Q, H, hd), dim=-1).view(B, Q, C)
+    hv = lambda t: t.unflatten(-1, (H, hd)).permute(0, 2, 1, 3)
+    q4, k4, v4 = hv(q), hv(k), hv(v)
+    bits = ro = eff = None
+    if masked:
+        blocked = torch.rand(B, Q, S) < 0.5
+        blocked[:, 3] = True
+        ro = (~blocked).any(-1).to(torch.int32).contiguous()
+        bits = _pack_bits(blocked)
+        eff = (blocked & (ro != 0).unsqueeze(-1)).unsqueeze(1)
+    G = B * H
+    wsb = h.emu_vmf_tc_workspace_bytes(G, Q, S, hd)
+    ws = torch.zeros(wsb // 4)
+    ns_max = wsb // 4 // (Q * (hd + 1)) // G
+    part_acc, part_den = ws[:G * ns_max * Q * hd], ws[G * ns_max * Q * hd:]
+    st = lambda t: (t.data_ptr(), t.stride(0), t.stride(1), t.stride(2))
+    ns = h.emu_vmf_attention_tc_partial(*st(q4), *st(k4), *st(v4), bits.data_ptr() if masked else None,
+                                        bits.shape[2] if masked else 0, ro.data_ptr() if masked else None,
+                                        B, H, Q, S, hd, kappa, flags, part_acc.data_ptr(), part_den.data_ptr(), 120.0)
+    assert ns > 0, (ns, h.emu_last_error())
+    acc = part_acc[:G * ns * Q * hd].view(G, ns, Q, hd).sum(1)
+    den = part_den[:G * ns * Q].view(G, ns, Q).sum(1)
+    out = F.normalize(acc / den.unsqueeze(-1), dim=-1).view(B, H, Q, hd)
+    qn = F.normalize(q4.double(), dim=-1) if flags & 1 else q4.double()
+    kn = F.normalize(k4.double(), dim=-1) if flags & 2 else k4.double()
+    s = kappa * qn @ kn.transpose(-1, -2)
+    if eff is not None:
+        s = s.masked_fill(eff, float("-inf"))
+    ref = F.normalize(torch.softmax(s, -1) @ v4.double(), dim=-1)
+    assert (out.double() - ref).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("B,n,m,d,kappa,iters", [
+    (1, 128, 100, 64, 10.0, 1),     # exactly one tile
+    (1, 100, 7, 64, 10.0, 2),       # fewer keys than a tile, few seeds
+    (2, 1000, 100, 64, 10.0, 3),    # 8 tiles per CTA: the 6-stage bulk-copy ring wraps; two images
+    (1, 777, 37, 32, 20.0, 3),      # d = 32, key tail, the reference's default kappa
+    (1, 2000, 128, 32, 10.0, 2),    # all 128 TMEM lanes in use
+])
+def test_experimental_packed_mean_shift_kernel(emu_tc, B, n, m, d, kappa, iters):
+    """csrc/experimental/vmf_packed.cu (operands packed once, streamed by bulk copies, 16 softmax warps) through the
+    calibrated emulation, against an fp64 restatement of seed_hill_climbing_ball (mean_shift.py:79-109)."""
+    h = emu_tc
+    torch.manual_seed(n + d)
+    X = F.normalize(torch.randn(B, n, d), dim=-1).contiguous()
+    idx = torch.stack([torch.randperm(n)[:m] for _ in range(B)])
+    Z = torch.gather(X, 1, idx.unsqueeze(-1).expand(B, m, d)).contiguous()
+    packed = torch.zeros(h.msmx_mean_shift_packed_bytes(B, n, d), dtype=torch.uint8)
+    h.emu_set_timeout(120.0)
+    assert h.msmx_mean_shift_pack(X.data_ptr(), packed.data_ptr(), B, n, d, None) == 0
+    wsb = h.msmx_mean_shift_packed_workspace_bytes(B, n, m, d)
+    ws = torch.zeros(wsb, dtype=torch.uint8)
+    out = torch.full_like(Z, float("nan"))
+    rc = h.msmx_mean_shift_hill_climb_packed(packed.data_ptr(), Z.data_ptr(), out.data_ptr(), B, n, m, d, kappa, iters,
+                                             ws.data_ptr(), wsb, None)
+    assert rc == 0, (rc, h.emu_last_error())
+    Xd, Zd = X.double(), Z.double()
+    for _ in range(iters):
+        Zd = F.normalize(torch.exp(kappa * (Zd @ Xd.transpose(-1, -2) - 1.0)) @ Xd, dim=-1, eps=1e-12)
+    assert (out.double() - Zd).abs().max().item() < 2e-5

@@ -56,8 +56,13 @@ constexpr float kLog2e = 1.4426950408889634f;
 // predecessor's tail; pdl_wait() returns once the predecessor has completed and its writes are visible, so all
 // global-memory traffic must come after it. pdl_trigger() lets the NEXT kernel begin its own prologue early.
 // Without the launch attribute both are no-ops.
+#ifdef MSM_EMULATE_ON_HOST  // tests/emu: kernels run one after the other on CPU threads
+__device__ __forceinline__ void pdl_wait() {}
+__device__ __forceinline__ void pdl_trigger() {}
+#else
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 bool pdl_enabled();  // false when MSM_DISABLE_PDL is set
 

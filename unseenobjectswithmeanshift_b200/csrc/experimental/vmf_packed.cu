@@ -43,6 +43,13 @@ struct Params {
   float* part_den;         // [G][nsplit][Nq]
 };
 
+#ifdef MSM_EMULATE_ON_HOST  // tests/emu: the PTX one-liners of this file as plain C++
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { emu_named_bar_sync(id, nthreads); }
+__device__ __forceinline__ float ex2(float x) { return exp2f(x); }
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  tc::bulk_load_1d(dst, src, bytes, bar);
+}
+#else
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -57,6 +64,7 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
                "l"(src), "r"(bytes), "r"(tc::smem_u32(bar))
                : "memory");
 }
+#endif
 
 // grid (ntiles, G), 128 threads: thread = (8-key group of 4 per pass, key in group, 8-channel group), the indexing of
 // the loader warps of vmf_attn_tc_kernel; rows beyond n are zero.
@@ -365,19 +373,31 @@ int climb(const uint8_t* packed, const float* Z0, float* Z_out, int B, int n, in
   P.nstages = stages > kMaxStages ? kMaxStages : stages;
   P.part_acc = part_acc; P.part_den = part_den;
   const size_t smem = (size_t)P.nstages * kStageBytes + fixed;
+#ifdef MSM_EMULATE_ON_HOST
+  if (smem > sizeof(vpk::smem)) return MSM_E_UNSUPPORTED;
+  tc::g_tc->smem_base = reinterpret_cast<uintptr_t>(vpk::smem);
+#else
   MSM_CUDA(cudaFuncSetAttribute(vmf_attn_packed_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+#endif
   const float* zin = Z0;
   for (int it = 0; it < iters; ++it) {
     P.q = zin;
     // >= 116 KB of dynamic shared memory keeps one CTA per SM (each CTA allocates all of TMEM)
     const size_t req = smem < (size_t)(120 << 10) ? (size_t)(120 << 10) : smem;
+    const int warps = B * m;
+#ifdef MSM_EMULATE_ON_HOST
+    (void)req; (void)st;
+    cuda_emu::launch(dim3(B * P.nsplit, 1), kThreads, [&] { vmf_attn_packed_kernel<HD>(P); });
+    cuda_emu::launch(dim3((warps * 32 + 255) / 256, 1), 256,
+                     [&] { vmf_packed_finalize_kernel(part_acc, part_den, Z_out, B, m, HD, P.nsplit); });
+#else
     vmf_attn_packed_kernel<HD><<<B * P.nsplit, kThreads, req, st>>>(P);
     int rc = check_launch("vmf_attn_packed_kernel");
     if (rc) return rc;
-    const int warps = B * m;
     vmf_packed_finalize_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(part_acc, part_den, Z_out, B, m, HD, P.nsplit);
     rc = check_launch("vmf_packed_finalize_kernel");
     if (rc) return rc;
+#endif
     zin = Z_out;
   }
   return 0;
@@ -404,9 +424,17 @@ extern "C" int msmx_mean_shift_pack(const float* X, void* packed, int B, int n, 
   MSM_REQUIRE(d == 32 || d == 64, "embedding dim must be 32 or 64");
   const int ntiles = (n + vpk::kTile - 1) / vpk::kTile;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+#ifdef MSM_EMULATE_ON_HOST
+  (void)st;
+  uint8_t* pk = static_cast<uint8_t*>(packed);
+  if (d == 64) cuda_emu::launch(dim3(ntiles, B), 128, [&] { vpk::vmf_pack_kernel<64>(X, pk, n); });
+  else cuda_emu::launch(dim3(ntiles, B), 128, [&] { vpk::vmf_pack_kernel<32>(X, pk, n); });
+  return 0;
+#else
   if (d == 64) vpk::vmf_pack_kernel<64><<<dim3(ntiles, B), 128, 0, st>>>(X, static_cast<uint8_t*>(packed), n);
   else vpk::vmf_pack_kernel<32><<<dim3(ntiles, B), 128, 0, st>>>(X, static_cast<uint8_t*>(packed), n);
   return check_launch("vmf_pack_kernel");
+#endif
 }
 
 extern "C" int msmx_mean_shift_hill_climb_packed(const void* packed, const float* Z0, float* Z_out, int B, int n, int m,

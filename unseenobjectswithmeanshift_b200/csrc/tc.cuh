@@ -8,6 +8,11 @@
 // as accurate as an fp32 FMA chain of the same length - which the decoder needs: its hard
 // sigmoid<0.5 attention masks amplify TF32/bf16-level noise into flipped mask bits.
 #pragma once
+#ifdef MSM_EMULATE_ON_HOST
+// tests/emu: the same interface implemented in plain C++ so that kernel text can run on CPU threads (no GPU in the
+// authoring container); the emulation driver puts tests/emu on the include path
+#include "tc_emu.h"
+#else
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -252,3 +257,4 @@ int encode_tensor_map_f32(CUtensorMap* map, const void* base, int rank, const ui
 
 }  // namespace tc
 }  // namespace msm
+#endif  // MSM_EMULATE_ON_HOST

@@ -64,6 +64,11 @@ struct Params {
   float* part_den;  // [G][nsplit][Nq]
 };
 
+#ifdef MSM_EMULATE_ON_HOST  // tests/emu: the three PTX one-liners of this file as plain C++
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { emu_named_bar_sync(id, nthreads); }
+__device__ __forceinline__ float ex2(float x) { return exp2f(x); }
+__device__ __forceinline__ uint32_t ld_nc_volatile(const uint32_t* p) { return *p; }
+#else
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -80,6 +85,7 @@ __device__ __forceinline__ uint32_t ld_nc_volatile(const uint32_t* p) {
   asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
+#endif
 
 // 8 consecutive channels of one row: two 16-byte loads (zeros when the row is out of range)
 __device__ __forceinline__ void load8(const float* p, bool in, float4& a, float4& b) {
@@ -458,16 +464,26 @@ static int launch_tc_m(const vtc::Params& P, int G, cudaStream_t st) {
   using namespace vtc;
   const size_t stage = (size_t)(SHARED ? 2 : 4) * kTile * HD * 2;
   const size_t smem = (size_t)P.nstages * stage + 256 + 128 * sizeof(float);
+#ifndef MSM_EMULATE_ON_HOST
   static bool configured = false;
   if (!configured) {
     MSM_CUDA(cudaFuncSetAttribute(vmf_attn_tc_kernel<HD, SHARED, QK16, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kMaxSmem));
     configured = true;
   }
+#endif
+#ifdef MSM_EMULATE_ON_HOST
+  (void)st;
+  if (smem > sizeof(vtc::smem)) return MSM_E_UNSUPPORTED;
+  tc::g_tc->smem_base = reinterpret_cast<uintptr_t>(vtc::smem);
+  cuda_emu::launch(dim3(G * P.nsplit, 1), kThreads, [&] { vmf_attn_tc_kernel<HD, SHARED, QK16, MASKED>(P); });
+  return 0;
+#else
   // >= 116 KB of dynamic shared memory keeps it at one CTA per SM (each CTA allocates all of TMEM)
   const size_t req = smem < (size_t)(120 << 10) ? (size_t)(120 << 10) : smem;
   MSM_CUDA(launch_pdl(vmf_attn_tc_kernel<HD, SHARED, QK16, MASKED>, dim3(G * P.nsplit), dim3(kThreads), req, st, P));
   return check_launch("vmf_attn_tc_kernel");
+#endif
 }
 
 template <int HD, bool SHARED, bool QK16>
