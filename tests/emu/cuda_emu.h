@@ -37,6 +37,8 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
+#undef __grid_constant__
+#define __grid_constant__
 
 namespace cuda_emu {
 [[noreturn]] inline void die(const char* what) {
@@ -103,6 +105,7 @@ inline uint32_t __float_as_uint(float f) {
   std::memcpy(&u, &f, 4);
   return u;
 }
+inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 using std::max;
 using std::min;
 

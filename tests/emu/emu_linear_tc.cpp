@@ -1,0 +1,41 @@
+// Emulation driver for csrc/linear_tc.cu (SHIPPED tcgen05 dense / convolution kernel: tiled TMA with 128B swizzle,
+// A operand converted into TMEM, fused epilogues, TMA stores) compiled as plain C++ - calibration of the tensor-map
+// part of tc_emu.h and a CPU development loop for this kernel. Built and loaded by tests/test_kernel_emulation.py.
+#include "cuda_emu.h"
+#include "tc_emu.h"
+
+#include <cstdarg>
+
+#include "../../unseenobjectswithmeanshift_b200/csrc/common.cuh"
+
+namespace msm {
+static char g_emu_err[512];
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_emu_err, sizeof(g_emu_err), fmt, ap);
+  va_end(ap);
+}
+static int g_sms = 2;
+int num_sms() { return g_sms; }  // few "SMs": persistent CTAs then walk several tiles each
+bool tc_enabled() { return true; }
+bool pdl_enabled() { return false; }
+namespace ltc {
+__attribute__((aligned(1024))) uint8_t smem_raw[232448 + 1024];
+}
+}  // namespace msm
+
+#include "../../unseenobjectswithmeanshift_b200/csrc/linear_tc.cu"
+
+static msm::tc::EmuState g_state;
+
+extern "C" void emu_set_timeout(double timeout_s) {
+  msm::tc::g_tc = &g_state;
+  cuda_emu::g_deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds((long)(timeout_s * 1e3));
+  cuda_emu::g_block_begin = [] {
+    g_state.bars.clear();
+    std::fill(g_state.tmem.begin(), g_state.tmem.end(), 0x7fc00000u);
+  };
+}
+extern "C" void emu_set_sms(int n) { msm::g_sms = n; }
+extern "C" const char* emu_last_error() { return msm::g_emu_err; }

@@ -15,6 +15,8 @@
 #include <mutex>
 #include <thread>
 
+#include <cuda.h>  // CUtensorMap (an opaque 128-byte struct; the emulation keeps its own description inside it)
+
 #include "cuda_emu.h"
 
 namespace msm {
@@ -54,28 +56,37 @@ inline void mbar_init(uint64_t* bar, uint32_t count) {
 }
 inline void fence_mbar_init() {}
 inline void fence_proxy_async() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline MbarState& mbar_state(uint64_t* bar) {
+  auto it = g_tc->bars.find(reinterpret_cast<uintptr_t>(bar));
+  if (it == g_tc->bars.end()) cuda_emu::die("mbarrier used before mbarrier.init");
+  return it->second;
+}
 inline void mbar_arrive(uint64_t* bar) {
   std::lock_guard<std::mutex> l(g_tc->mu);
-  MbarState& b = g_tc->bars.at(reinterpret_cast<uintptr_t>(bar));
+  MbarState& b = mbar_state(bar);
+  if (b.pending <= 0) cuda_emu::die("mbarrier: more arrivals than the init count in one phase");
   b.pending -= 1;
   mbar_complete_if_done(b);
 }
 inline void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   std::lock_guard<std::mutex> l(g_tc->mu);
-  MbarState& b = g_tc->bars.at(reinterpret_cast<uintptr_t>(bar));
+  MbarState& b = mbar_state(bar);
+  if (b.pending <= 0) cuda_emu::die("mbarrier: more arrivals than the init count in one phase");
   b.tx += bytes;
+  if (b.tx > (1 << 20) - 1) cuda_emu::die("mbarrier: transaction count beyond 2^20 - 1 bytes");
   b.pending -= 1;
   mbar_complete_if_done(b);
 }
 inline void mbar_complete_tx(uint64_t* bar, uint32_t bytes) {
   std::lock_guard<std::mutex> l(g_tc->mu);
-  MbarState& b = g_tc->bars.at(reinterpret_cast<uintptr_t>(bar));
+  MbarState& b = mbar_state(bar);
   b.tx -= bytes;
+  if (b.tx < -((1 << 20) - 1)) cuda_emu::die("mbarrier: transaction count below -(2^20 - 1) bytes");
   mbar_complete_if_done(b);
 }
 inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) {  // true once the phase of this parity has completed
   std::lock_guard<std::mutex> l(g_tc->mu);
-  return g_tc->bars.at(reinterpret_cast<uintptr_t>(bar)).phase != (parity & 1u);
+  return mbar_state(bar).phase != (parity & 1u);
 }
 inline void mbar_wait(uint64_t* bar, uint32_t parity) {
   int spins = 0;
@@ -101,6 +112,113 @@ inline void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* b
   std::atomic_thread_fence(std::memory_order_seq_cst);
   mbar_complete_tx(bar, bytes);
 }
+
+// ------------------------------------------------------------------------------------------ tiled TMA (tensor maps)
+enum class TmapType { F32, BF16 };
+enum class TmapSwizzle { None, B128 };
+struct EmuTmap {          // lives in the CUtensorMap's storage
+  const uint8_t* base;
+  uint64_t strides[4];    // bytes, dimensions 1 .. rank-1
+  uint32_t dims[5];
+  uint16_t box[5];
+  uint8_t rank, elem, swizzle, magic;
+};
+static_assert(sizeof(EmuTmap) <= sizeof(CUtensorMap), "tensor map description does not fit");
+inline int encode_tensor_map(CUtensorMap* map, TmapType type, TmapSwizzle swizzle, const void* base, int rank,
+                             const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+  EmuTmap t{};
+  t.base = static_cast<const uint8_t*>(base);
+  t.rank = (uint8_t)rank;
+  t.elem = type == TmapType::F32 ? 4 : 2;
+  t.swizzle = swizzle == TmapSwizzle::B128 ? 1 : 0;
+  t.magic = 0x5a;
+  for (int i = 0; i < rank; ++i) {
+    t.dims[i] = (uint32_t)dims[i];
+    t.box[i] = (uint16_t)box[i];
+    if (i > 0) t.strides[i - 1] = strides_bytes[i - 1];
+    if (box[i] == 0 || box[i] > 256) cuda_emu::die("tensor map: box extents must be in [1, 256]");
+    if (i > 0 && strides_bytes[i - 1] % 16 != 0) cuda_emu::die("tensor map: strides must be multiples of 16 bytes");
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) cuda_emu::die("tensor map: base must be 16-byte aligned");
+  if (t.swizzle && (uint32_t)box[0] * t.elem > 128) cuda_emu::die("tensor map: 128B swizzle needs an inner box <= 128 bytes");
+  if (((uint32_t)box[0] * t.elem) % 16 != 0) cuda_emu::die("tensor map: inner box must be a multiple of 16 bytes");
+  std::memset(map, 0, sizeof(*map));
+  std::memcpy(map, &t, sizeof(t));
+  return 0;
+}
+inline int encode_tensor_map_f32(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                                 const uint64_t* strides_bytes, const uint32_t* box) {
+  return encode_tensor_map(map, TmapType::F32, TmapSwizzle::None, base, rank, dims, strides_bytes, box);
+}
+inline void tma_prefetch_desc(const CUtensorMap*) {}
+// box element (i[rank-1], ..., i[0]) <-> shared memory: dense box order, 16-byte chunks XOR-swizzled by the row index
+inline void tma_copy(uint8_t* smem_tile, const CUtensorMap* map, const int* c, bool load) {
+  EmuTmap t;
+  std::memcpy(&t, map, sizeof(t));
+  if (t.magic != 0x5a) cuda_emu::die("TMA with a tensor map that was never encoded");
+  if (t.swizzle && (reinterpret_cast<uintptr_t>(smem_tile) - g_tc->smem_base) % 1024 != 0)
+    cuda_emu::die("128B-swizzled TMA tile must be 1024-byte aligned in shared memory");
+  if ((reinterpret_cast<uintptr_t>(smem_tile) & 127) != 0) cuda_emu::die("TMA tile must be 128-byte aligned");
+  int idx[5] = {0, 0, 0, 0, 0};
+  uint32_t total = 1;
+  for (int d = 0; d < t.rank; ++d) total *= t.box[d];
+  for (uint32_t e = 0; e < total; ++e) {
+    bool in = true;
+    uint64_t goff = 0;
+    for (int d = 0; d < t.rank; ++d) {
+      const int64_t g = (int64_t)c[d] + idx[d];
+      if (g < 0 || g >= (int64_t)t.dims[d]) in = false;
+      goff += d == 0 ? (uint64_t)g * t.elem : (uint64_t)g * t.strides[d - 1];
+    }
+    uint32_t soff = e * t.elem;
+    if (t.swizzle) soff ^= ((soff >> 7) & 7u) << 4;
+    if (load) {
+      if (in) std::memcpy(smem_tile + soff, t.base + goff, t.elem);
+      else std::memset(smem_tile + soff, 0, t.elem);
+    } else if (in) {
+      std::memcpy(const_cast<uint8_t*>(t.base) + goff, smem_tile + soff, t.elem);
+    }
+    for (int d = 0; d < t.rank; ++d) {  // next box element, innermost dimension fastest
+      if (++idx[d] < t.box[d]) break;
+      idx[d] = 0;
+    }
+  }
+  if (load) std::atomic_thread_fence(std::memory_order_seq_cst);
+}
+inline uint32_t tma_box_bytes(const CUtensorMap* map) {
+  EmuTmap t;
+  std::memcpy(&t, map, sizeof(t));
+  uint32_t total = t.elem;
+  for (int d = 0; d < t.rank; ++d) total *= t.box[d];
+  return total;
+}
+inline void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  const int c[5] = {c0, c1, 0, 0, 0};
+  tma_copy(static_cast<uint8_t*>(dst), m, c, true);
+  mbar_complete_tx(bar, tma_box_bytes(m));
+}
+inline void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  const int c[5] = {c0, c1, c2, 0, 0};
+  tma_copy(static_cast<uint8_t*>(dst), m, c, true);
+  mbar_complete_tx(bar, tma_box_bytes(m));
+}
+inline void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  const int c[5] = {c0, c1, c2, c3, 0};
+  tma_copy(static_cast<uint8_t*>(dst), m, c, true);
+  mbar_complete_tx(bar, tma_box_bytes(m));
+}
+inline void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  const int c[5] = {c0, c1, 0, 0, 0};
+  tma_copy(const_cast<uint8_t*>(static_cast<const uint8_t*>(src)), m, c, false);
+}
+inline void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  const int c[5] = {c0, c1, c2, 0, 0};
+  tma_copy(const_cast<uint8_t*>(static_cast<const uint8_t*>(src)), m, c, false);
+}
+inline void tma_store_commit() {}
+template <int N>
+inline void tma_store_wait_read() {}
+inline void tma_store_wait_all() {}
 
 // ------------------------------------------------------------------------------------------ tcgen05 / TMEM
 inline uint32_t& tmem_at(uint32_t taddr, uint32_t lane_off, uint32_t col_off) {

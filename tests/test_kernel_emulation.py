@@ -8,6 +8,9 @@ no-swizzle shared-memory descriptors, bulk copies) and driven through their real
 * csrc/vmf_attention_bwd.cu (training, CUDA cores): against the reference's gradients (golden) and fp64 autograd;
 * csrc/vmf_attention_tc.cu (SHIPPED tcgen05 kernel, parity-green on the B200): the CALIBRATION of the tensor-core
   emulation - it has to reproduce what the hardware is known to produce for this kernel;
+* csrc/linear_tc.cu (SHIPPED dense / convolution kernel: tiled TMA with 128B swizzle, operand conversion into TMEM,
+  fused epilogues, TMA stores): calibration of the tensor-map emulation, and a CPU development loop for the kernel
+  that dominates the headline step;
 * csrc/experimental/vmf_packed.cu (tcgen05 + bulk copies, not yet run on a GPU): judged with the calibrated emulation.
 
 This checks indexing, tiling, masks, strides, descriptors and barrier protocols of the real source. MMAs execute
@@ -271,3 +274,105 @@ def test_experimental_packed_mean_shift_kernel(emu_tc, B, n, m, d, kappa, iters)
     for _ in range(iters):
         Zd = F.normalize(torch.exp(kappa * (Zd @ Xd.transpose(-1, -2) - 1.0)) @ Xd, dim=-1, eps=1e-12)
     assert (out.double() - Zd).abs().max().item() < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# csrc/linear_tc.cu: tiled TMA (2-D / 3-D / 4-D boxes, 128B swizzle, clipped stores) + every epilogue mode
+@pytest.fixture(scope="module")
+def emu_lin():
+    from unseenobjectswithmeanshift_b200._lib import SIGNATURES
+    h = _build(os.path.join(ROOT, "build", "emu", "libemu_linear_tc.so"), "emu_linear_tc.cpp", ["linear_tc.cu"])
+    for n in ("msm_linear_weight_bytes", "msm_linear_prepare_weight", "msm_linear_fwd", "msm_linear_ln_fwd",
+              "msm_linear_fused_fwd", "msm_conv1x1_fwd", "msm_conv3x3_fwd"):
+        f = getattr(h, n)
+        f.restype, f.argtypes = SIGNATURES[n]
+    h.emu_set_timeout.argtypes = [ctypes.c_double]
+    h.emu_set_sms.argtypes = [ctypes.c_int]
+    h.emu_last_error.restype = ctypes.c_char_p
+    return h
+
+
+def _aligned(nbytes, align=1024):
+    buf = torch.zeros(nbytes + align, dtype=torch.uint8)
+    off = (-buf.data_ptr()) % align
+    return buf[off:off + nbytes]
+
+
+def _prepare(h, W):
+    N, K = W.shape
+    p = _aligned(h.msm_linear_weight_bytes(N, K))
+    assert h.msm_linear_prepare_weight(W.data_ptr(), W.stride(0), p.data_ptr(), N, K, None) == 0
+    return p
+
+
+def _start(h, sms):
+    h.emu_set_timeout(300.0)
+    h.emu_set_sms(sms)   # few "SMs": persistent CTAs walk several tiles, rings wrap around
+
+
+@pytest.mark.parametrize("M,N,K,relu,sms", [(300, 64, 64, True, 2), (800, 256, 256, False, 2), (130, 96, 32, False, 1)])
+def test_calibration_shipped_linear_kernel(emu_lin, M, N, K, relu, sms):
+    h = emu_lin
+    torch.manual_seed(M + N + K)
+    X, W, b = torch.randn(M, K), torch.randn(N, K) / K ** 0.5, torch.randn(N)
+    Y = torch.full((M, N), float("nan"))
+    _start(h, sms)
+    p = _prepare(h, W)
+    rc = h.msm_linear_fwd(X.data_ptr(), K, p.data_ptr(), b.data_ptr(), Y.data_ptr(), N, M, N, K, int(relu), None)
+    assert rc == 0, (rc, h.emu_last_error())
+    ref = X.double() @ W.double().t() + b.double()
+    assert (Y.double() - (ref.relu() if relu else ref)).abs().max().item() < 1e-5
+
+
+def test_calibration_shipped_linear_kernel_fused_epilogues(emu_lin):
+    h = emu_lin
+    torch.manual_seed(7)
+    M, N, K, period = 300, 256, 64, 100
+    X, W, b, R = torch.randn(M, K), torch.randn(N, K) / K ** 0.5, torch.randn(N), torch.randn(M, N)
+    rb, g, be, g2, be2 = torch.randn(period, N), torch.randn(N), torch.randn(N), torch.randn(N), torch.randn(N)
+    Y, Y2 = torch.full((M, N), float("nan")), torch.full((M, N), float("nan"))
+    _start(h, 2)
+    p = _prepare(h, W)
+    rc = h.msm_linear_fused_fwd(X.data_ptr(), K, p.data_ptr(), b.data_ptr(), rb.data_ptr(), period, 1, R.data_ptr(), N,
+                                g.data_ptr(), be.data_ptr(), 1e-5, 1, g2.data_ptr(), be2.data_ptr(), 1e-5,
+                                Y2.data_ptr(), N, Y.data_ptr(), N, M, N, K, None)
+    assert rc == 0, (rc, h.emu_last_error())
+    v = (X.double() @ W.double().t() + b.double() + rb.double().repeat(3, 1)[:M]).relu() + R.double()
+    z = F.normalize(F.layer_norm(v, (N,), g.double(), be.double(), 1e-5), dim=-1)
+    assert (Y.double() - z).abs().max().item() < 1e-5
+    assert (Y2.double() - F.layer_norm(z, (N,), g2.double(), be2.double(), 1e-5)).abs().max().item() < 5e-5
+    # narrow form: residual + LayerNorm over N <= 64 outputs
+    N = 64
+    W, b, R, g, be = torch.randn(N, K) / K ** 0.5, torch.randn(N), torch.randn(M, N), torch.randn(N), torch.randn(N)
+    Y = torch.full((M, N), float("nan"))
+    p = _prepare(h, W)
+    rc = h.msm_linear_ln_fwd(X.data_ptr(), K, p.data_ptr(), b.data_ptr(), R.data_ptr(), N, g.data_ptr(), be.data_ptr(),
+                             1e-5, Y.data_ptr(), N, M, N, K, None)
+    assert rc == 0, (rc, h.emu_last_error())
+    ref = F.layer_norm(R.double() + X.double() @ W.double().t() + b.double(), (N,), g.double(), be.double(), 1e-5)
+    assert (Y.double() - ref).abs().max().item() < 1e-5
+
+
+def test_calibration_shipped_linear_kernel_convolutions(emu_lin):
+    h = emu_lin
+    torch.manual_seed(11)
+    _start(h, 2)
+    for B, K, N, H, W, y_nchw in ((2, 64, 64, 10, 20, True), (2, 32, 96, 9, 16, False)):   # 1x1, NCHW input
+        x, w, b = torch.randn(B, K, H, W), torch.randn(N, K) / K ** 0.5, torch.randn(N)
+        Y = torch.full((B, N, H * W) if y_nchw else (B, H * W, N), float("nan"))
+        p = _prepare(h, w)
+        rc = h.msm_conv1x1_fwd(x.data_ptr(), p.data_ptr(), b.data_ptr(), Y.data_ptr(), int(y_nchw), B, H * W, N, K, 0, None)
+        assert rc == 0, (rc, h.emu_last_error())
+        ref = torch.einsum("nk,bkp->bnp", w.double(), x.double().flatten(2)) + b.double()[None, :, None]
+        assert (Y.double() - (ref if y_nchw else ref.transpose(1, 2))).abs().max().item() < 1e-5
+    B, C, N, H, W = 1, 32, 32, 9, 40                                                          # 3x3 halo tiles, tails
+    x, w, b = torch.randn(B, C, H, W), torch.randn(N, C, 3, 3) / (9 * C) ** 0.5, torch.randn(N)
+    Y = torch.full((B, N, H, W), float("nan"))
+    p = _prepare(h, w.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous())
+    Wp = (W + 2 + 3) // 4 * 4
+    xp = F.pad(x, (1, Wp - W - 1, 1, 1))
+    buf = _aligned(xp.numel() * 4, 128).view(torch.float32).view(xp.shape)
+    buf.copy_(xp)
+    rc = h.msm_conv3x3_fwd(buf.data_ptr(), p.data_ptr(), b.data_ptr(), Y.data_ptr(), B, C, H, W, Wp, N, 1, None)
+    assert rc == 0, (rc, h.emu_last_error())
+    assert (Y.double() - F.conv2d(x.double(), w.double(), b.double(), padding=1).relu()).abs().max().item() < 1e-5

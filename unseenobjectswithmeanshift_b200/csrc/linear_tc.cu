@@ -82,9 +82,13 @@ struct Params {
   float ln2_eps;
 };
 
+#ifdef MSM_EMULATE_ON_HOST  // tests/emu
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { emu_named_bar_sync(id, nthreads); }
+#else
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+#endif
 
 __global__ void __launch_bounds__(kThreads, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap,
@@ -602,9 +606,15 @@ extern "C" int msm_linear_prepare_weight(const float* W, int64_t ldw, void* prep
   MSM_REQUIRE((reinterpret_cast<uintptr_t>(prepared) & 127) == 0, "prepared must be 128-byte aligned");
   const int64_t total = (int64_t)N * (K / 8);
   const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+#ifdef MSM_EMULATE_ON_HOST
+  cuda_emu::launch(dim3(blocks < 8 ? blocks : 8, 1), 256,
+                   [&] { msm::ltc::linear_prepare_weight_kernel(W, ldw, static_cast<uint4*>(prepared), N, K); });
+  return 0;
+#else
   msm::ltc::linear_prepare_weight_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       W, ldw, static_cast<uint4*>(prepared), N, K);
   return msm::check_launch("linear_prepare_weight_kernel");
+#endif
 }
 
 namespace msm {
@@ -717,18 +727,26 @@ static int launch(const float* X, int64_t ldx, const void* prepared, const float
   }
   const size_t smem = 1024 + (size_t)P.xstages * P.xstage_bytes + 8 * kYWarpBytes +
                       (P.w_resident ? (size_t)K * P.BN * 4 : (size_t)P.wstages * 128 * P.BN) + 4 * 384 * sizeof(float) + 512;
+  const int tiles = P.m_tiles * P.n_chunks;
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  if (P.w_resident) grid -= grid % P.n_chunks;  // tiles >= n_chunks and n_chunks <= 64 < SMs, so grid >= n_chunks
+#ifdef MSM_EMULATE_ON_HOST
+  (void)st;
+  if (smem > sizeof(ltc::smem_raw)) return MSM_E_UNSUPPORTED;
+  tc::g_tc->smem_base = reinterpret_cast<uintptr_t>(ltc::smem_raw);
+  cuda_emu::launch(dim3(grid, 1), kThreads, [&] { linear_tc_kernel(xmap, wmap, ymap, y2map, P); });
+  return 0;
+#else
   static bool configured = false;
   if (!configured) {
     MSM_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     configured = true;
   }
-  const int tiles = P.m_tiles * P.n_chunks;
-  int grid = tiles < num_sms() ? tiles : num_sms();
-  if (P.w_resident) grid -= grid % P.n_chunks;  // tiles >= n_chunks and n_chunks <= 64 < SMs, so grid >= n_chunks
   // >= 116 KB of dynamic shared memory keeps it at one CTA per SM (each CTA allocates all of TMEM)
   const size_t req = smem < (size_t)(120 << 10) ? (size_t)(120 << 10) : smem;
   MSM_CUDA(launch_pdl(linear_tc_kernel, dim3(grid), dim3(kThreads), req, st, xmap, wmap, ymap, y2map, P));
   return check_launch("linear_tc_kernel");
+#endif
 }
 
 }  // namespace ltc
