@@ -90,6 +90,12 @@ def _forward_planes(q, k, v, blocked, kappa, nq=True, nk=True):
     return out, torch.stack([den.reshape(B * H, Nq), norm.reshape(B * H, Nq)]).float().contiguous()
 
 
+def _aligned(nbytes, align=1024):
+    buf = torch.zeros(nbytes + align, dtype=torch.uint8)
+    off = (-buf.data_ptr()) % align
+    return buf[off:off + nbytes]
+
+
 def _close(got, want, rel):
     err = (got.double() - want.double()).abs().max().item()
     scale = max(want.abs().max().item(), 1e-30)
@@ -195,6 +201,11 @@ def emu_tc():
     h.msmx_mean_shift_pack.restype, h.msmx_mean_shift_pack.argtypes = I, [P, P, I, I, I, P]
     h.msmx_mean_shift_hill_climb_packed.restype = I
     h.msmx_mean_shift_hill_climb_packed.argtypes = [P, P, P, I, I, I, I, Fl, I, P, Z, P]
+    h.msmx_vmf_packed_bytes.restype, h.msmx_vmf_packed_bytes.argtypes = Z, [I, I, I, I, I]
+    h.msmx_vmf_packed_workspace_bytes.restype, h.msmx_vmf_packed_workspace_bytes.argtypes = Z, [I, I, I, I, I]
+    h.msmx_vmf_pack.restype, h.msmx_vmf_pack.argtypes = I, [P, L, L, L, P, L, L, L, P, I, I, I, I, I, P]
+    h.msmx_vmf_attention_packed_fwd.restype = I
+    h.msmx_vmf_attention_packed_fwd.argtypes = [P, L, L, L, P, P, L, L, L, P, I, P, I, I, I, I, I, Fl, I, P, Z, P]
     return h
 
 
@@ -261,7 +272,7 @@ def test_experimental_packed_mean_shift_kernel(emu_tc, B, n, m, d, kappa, iters)
     X = F.normalize(torch.randn(B, n, d), dim=-1).contiguous()
     idx = torch.stack([torch.randperm(n)[:m] for _ in range(B)])
     Z = torch.gather(X, 1, idx.unsqueeze(-1).expand(B, m, d)).contiguous()
-    packed = torch.zeros(h.msmx_mean_shift_packed_bytes(B, n, d), dtype=torch.uint8)
+    packed = _aligned(h.msmx_mean_shift_packed_bytes(B, n, d), 128)
     h.emu_set_timeout(120.0)
     assert h.msmx_mean_shift_pack(X.data_ptr(), packed.data_ptr(), B, n, d, None) == 0
     wsb = h.msmx_mean_shift_packed_workspace_bytes(B, n, m, d)
@@ -274,6 +285,50 @@ def test_experimental_packed_mean_shift_kernel(emu_tc, B, n, m, d, kappa, iters)
     for _ in range(iters):
         Zd = F.normalize(torch.exp(kappa * (Zd @ Xd.transpose(-1, -2) - 1.0)) @ Xd, dim=-1, eps=1e-12)
     assert (out.double() - Zd).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("B,H,Q,S,hd,masked,flags,kappa,tol", [
+    (1, 2, 100, 700, 32, True, 3, 30.0, 2e-5),    # the decoder's cross-attention: heads by strides, bit mask, 6 tiles
+    (1, 1, 37, 333, 64, False, 3, 30.0, 2e-5),    # hd 64, key tail
+    (2, 2, 100, 300, 32, False, 3, 30.0, 2e-5),   # two images x two heads
+    (1, 1, 100, 1000, 64, True, 3, 30.0, 2e-5),   # hd 64 masked: the 3-stage ring wraps
+    (1, 2, 50, 260, 32, True, 1, 5.0, 1e-4),      # k not normalised: bf16 score operands
+])
+def test_experimental_packed_attention_kernel(emu_tc, B, H, Q, S, hd, masked, flags, kappa, tol):
+    """The general form of csrc/experimental/vmf_packed.cu: K (normalised, fp16 halves) and V (bf16 halves) packed per
+    (batch, head, tile) by vmf_pack_kernel, attention with the decoder's bit masks - what the cross-attention would
+    run once the K/V projection writes the images itself."""
+    h = emu_tc
+    torch.manual_seed(S + hd + Q)
+    C = H * hd
+    q, kv = torch.randn(B, Q, C), torch.randn(B, S, 2 * C)
+    hv = lambda t: t.unflatten(-1, (H, hd)).permute(0, 2, 1, 3)
+    q4, k4, v4 = hv(q), hv(kv[..., :C]), hv(kv[..., C:])   # k | v share one projection buffer
+    bits = ro = eff = None
+    if masked:
+        blocked = torch.rand(B, Q, S) < 0.5
+        blocked[:, 3] = True
+        ro = (~blocked).any(-1).to(torch.int32).contiguous()
+        bits = _pack_bits(blocked)
+        eff = (blocked & (ro != 0).unsqueeze(-1)).unsqueeze(1)
+    st = lambda t: (t.data_ptr(), t.stride(0), t.stride(1), t.stride(2))
+    h.emu_set_timeout(200.0)
+    packed = _aligned(h.msmx_vmf_packed_bytes(B, H, S, hd, flags), 128)
+    assert h.msmx_vmf_pack(*st(k4), *st(v4), packed.data_ptr(), B, H, S, hd, flags, None) == 0, h.emu_last_error()
+    wsb = h.msmx_vmf_packed_workspace_bytes(B, H, Q, S, hd)
+    ws = torch.zeros(wsb, dtype=torch.uint8)
+    out = torch.full((B, Q, H, hd), float("nan")).permute(0, 2, 1, 3)
+    rc = h.msmx_vmf_attention_packed_fwd(*st(q4), packed.data_ptr(), *st(out), bits.data_ptr() if masked else None,
+                                         bits.shape[2] if masked else 0, ro.data_ptr() if masked else None,
+                                         B, H, Q, S, hd, kappa, flags, ws.data_ptr(), wsb, None)
+    assert rc == 0, (rc, h.emu_last_error())
+    qn = F.normalize(q4.double(), dim=-1) if flags & 1 else q4.double()
+    kn = F.normalize(k4.double(), dim=-1) if flags & 2 else k4.double()
+    s = kappa * qn @ kn.transpose(-1, -2)
+    if eff is not None:
+        s = s.masked_fill(eff, float("-inf"))
+    ref = F.normalize(torch.softmax(s, -1) @ v4.double(), dim=-1)
+    assert (out.double() - ref).abs().max().item() < tol
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -290,12 +345,6 @@ def emu_lin():
     h.emu_set_sms.argtypes = [ctypes.c_int]
     h.emu_last_error.restype = ctypes.c_char_p
     return h
-
-
-def _aligned(nbytes, align=1024):
-    buf = torch.zeros(nbytes + align, dtype=torch.uint8)
-    off = (-buf.data_ptr()) % align
-    return buf[off:off + nbytes]
 
 
 def _prepare(h, W):

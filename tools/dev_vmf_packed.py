@@ -1,12 +1,15 @@
-"""GPU dev check of the EXPERIMENTAL packed-operand mean-shift kernel (csrc/experimental/vmf_packed.cu).
+"""GPU dev check of the EXPERIMENTAL packed-operand attention / mean-shift kernels (csrc/experimental/vmf_packed.cu).
 
     python tools/dev_vmf_packed.py build      # cross-compile build/experimental/libmsmx_vmf_packed.so (no GPU needed)
     python tools/dev_vmf_packed.py [quick]    # on the B200 box: build if stale, parity + timing vs the shipped kernel
 
 The experimental library is separate from libmsmformer_b200.so (the product build globs csrc/*.cu only) and is bound
 here and nowhere else. The check runs in a child process under a timeout: a hung mbarrier protocol must not take the
-box with it. Parity: seeds after 10 iterations against the shipped msm_mean_shift_hill_climb and, at small n, an
-fp64 restatement of seed_hill_climbing_ball (transformer_decoder/mean_shift.py:79-109).
+box with it. Parity: (1) mean-shift seeds after 10 iterations against the shipped msm_mean_shift_hill_climb and, at
+small n, an fp64 restatement of seed_hill_climbing_ball (transformer_decoder/mean_shift.py:79-109); (2) the decoder's
+cross-attention (heads by strides, bit masks, K normalised + fp16 halves, V bf16 halves) against the shipped
+msm_vmf_attention_fwd, with the pack kernel timed separately (in production the K/V projection writes the images).
+The same source already runs green on CPU threads under the calibrated emulation (tests/test_kernel_emulation.py).
 """
 import ctypes
 import os
@@ -32,8 +35,13 @@ def build():
 
 
 def bind():
-    P, I, F, Z = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+    P, I, F, Z, L = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_int64
     h = ctypes.CDLL(build())
+    h.msmx_vmf_packed_bytes.restype, h.msmx_vmf_packed_bytes.argtypes = Z, [I, I, I, I, I]
+    h.msmx_vmf_packed_workspace_bytes.restype, h.msmx_vmf_packed_workspace_bytes.argtypes = Z, [I, I, I, I, I]
+    h.msmx_vmf_pack.restype, h.msmx_vmf_pack.argtypes = I, [P, L, L, L, P, L, L, L, P, I, I, I, I, I, P]
+    h.msmx_vmf_attention_packed_fwd.restype = I
+    h.msmx_vmf_attention_packed_fwd.argtypes = [P, L, L, L, P, P, L, L, L, P, I, P, I, I, I, I, I, F, I, P, Z, P]
     h.msm_last_error.restype = ctypes.c_char_p
     h.msmx_mean_shift_packed_bytes.restype = Z
     h.msmx_mean_shift_packed_bytes.argtypes = [I, I, I]
@@ -114,6 +122,63 @@ def child(quick):
               f"pack {t_pack * 1e3:8.1f} us  climb packed {t_new * 1e3:9.1f} us ({by / t_new / 1e6:7.1f} GB/s)  "
               f"shipped {t_old * 1e3:9.1f} us ({by / t_old / 1e6:7.1f} GB/s)", flush=True)
         assert e_ship < 2e-4, "packed kernel disagrees with the shipped kernel"
+
+    # ---- decoder cross-attention on packed K / V images vs the shipped kernel
+    def pack_bits(blocked):
+        Bq, Q, S = blocked.shape
+        words = (S + 31) // 32
+        pad = torch.zeros(Bq, Q, words * 32, dtype=torch.bool, device=dev)
+        pad[..., :S] = blocked
+        v = (pad.view(Bq, Q, words, 32).long() << torch.arange(32, device=dev)).sum(-1)
+        return torch.where(v >= 2 ** 31, v - 2 ** 32, v).to(torch.int32).contiguous()
+
+    xcases = [(1, 2, 100, 700, 32, True), (2, 8, 100, 4800, 32, True), (1, 1, 37, 333, 64, False),
+              (1, 8, 100, 50176, 32, True), (1, 8, 100, 307200, 32, True)]
+    if not quick:
+        xcases.append((2, 8, 100, 307200, 32, True))
+    for (B, H, Q, S, hd, masked) in xcases:
+        g = torch.Generator(device="cuda").manual_seed(S + hd)
+        C = H * hd
+        q = torch.randn(B, Q, C, device=dev, generator=g)
+        kv = torch.randn(B, S, 2 * C, device=dev, generator=g)
+        hv = lambda t: t.unflatten(-1, (H, hd)).permute(0, 2, 1, 3)
+        q4, k4, v4 = hv(q), hv(kv[..., :C]), hv(kv[..., C:])
+        bits = ro = None
+        if masked:
+            blocked = torch.rand(B, Q, S, device=dev, generator=g) < 0.5
+            blocked[:, 3] = True
+            ro = (~blocked).any(-1).to(torch.int32).contiguous()
+            bits = pack_bits(blocked)
+        sd = lambda t: (t.data_ptr(), t.stride(0), t.stride(1), t.stride(2))
+        packed = torch.empty(h.msmx_vmf_packed_bytes(B, H, S, hd, 3), dtype=torch.uint8, device=dev)
+        wsb = h.msmx_vmf_packed_workspace_bytes(B, H, Q, S, hd)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        out = torch.empty(B, Q, H, hd, device=dev).permute(0, 2, 1, 3)
+
+        def pack():
+            rc = h.msmx_vmf_pack(*sd(k4), *sd(v4), packed.data_ptr(), B, H, S, hd, 3, st())
+            assert rc == 0, h.msm_last_error()
+
+        def attend():
+            rc = h.msmx_vmf_attention_packed_fwd(*sd(q4), packed.data_ptr(), *sd(out),
+                                                 bits.data_ptr() if masked else None, bits.shape[2] if masked else 0,
+                                                 ro.data_ptr() if masked else None, B, H, Q, S, hd, 30.0, 3,
+                                                 ws.data_ptr(), wsb, st())
+            assert rc == 0, h.msm_last_error()
+
+        pack()
+        attend()
+        want = ops.vmf_attention(q4, k4, v4, blocked_bits=bits, row_open=ro)
+        torch.cuda.synchronize()
+        err = (out - want).abs().max().item()
+        reps = 3 if S > 100000 else 10
+        t_pack, t_new = timed(pack, reps), timed(attend, reps)
+        t_old = timed(lambda: ops.vmf_attention(q4, k4, v4, blocked_bits=bits, row_open=ro), reps)
+        fl = 4.0 * B * H * Q * S * hd
+        print(f"  attn B{B} H{H} Q{Q} S{S} hd{hd} mask{int(masked)}: |packed - shipped| {err:.2e}   pack {t_pack * 1e3:8.1f} us  "
+              f"packed {t_new * 1e3:9.1f} us ({fl / t_new / 1e9:6.1f} TFLOP/s)  shipped {t_old * 1e3:9.1f} us "
+              f"({fl / t_old / 1e9:6.1f} TFLOP/s)", flush=True)
+        assert err < 2e-4, "packed attention disagrees with the shipped kernel"
 
 
 if __name__ == "__main__":
