@@ -425,3 +425,83 @@ def test_calibration_shipped_linear_kernel_convolutions(emu_lin):
     rc = h.msm_conv3x3_fwd(buf.data_ptr(), p.data_ptr(), b.data_ptr(), Y.data_ptr(), B, C, H, W, Wp, N, 1, None)
     assert rc == 0, (rc, h.emu_last_error())
     assert (Y.double() - F.conv2d(x.double(), w.double(), b.double(), padding=1).relu()).abs().max().item() < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the fused chain of DESIGN.md section 8, item 1: K / V projections write operand images, packed attention reads them
+@pytest.fixture(scope="module")
+def emu_chain():
+    from unseenobjectswithmeanshift_b200._lib import SIGNATURES
+    h = _build(os.path.join(ROOT, "build", "emu", "libemu_kv_chain.so"), "emu_kv_chain.cpp",
+               ["linear_tc.cu", os.path.join("experimental", "vmf_packed.cu")])
+    P, I, L, Fl, Z, D = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t, ctypes.c_double
+    for n in ("msm_linear_weight_bytes", "msm_linear_prepare_weight"):
+        f = getattr(h, n)
+        f.restype, f.argtypes = SIGNATURES[n]
+    h.msmx_linear_packed_kv_fwd.restype = I
+    h.msmx_linear_packed_kv_fwd.argtypes = [P, L, P, P, P, I, I, I, I, I, I, I, I, P]
+    h.msmx_vmf_packed_bytes.restype, h.msmx_vmf_packed_bytes.argtypes = Z, [I, I, I, I, I]
+    h.msmx_vmf_packed_workspace_bytes.restype, h.msmx_vmf_packed_workspace_bytes.argtypes = Z, [I, I, I, I, I]
+    h.msmx_vmf_attention_packed_fwd.restype = I
+    h.msmx_vmf_attention_packed_fwd.argtypes = [P, L, L, L, P, P, L, L, L, P, I, P, I, I, I, I, I, Fl, I, P, Z, P]
+    h.emu_set_timeout.argtypes = [D]
+    h.emu_set_sms.argtypes = [I]
+    h.emu_last_error.restype = ctypes.c_char_p
+    return h
+
+
+@pytest.mark.parametrize("B,S,Cin,C,layers,Q,masked,sms", [
+    (1, 300, 64, 64, 2, 50, True, 2),      # two decoder layers of a level projected by one GEMM, two heads, bit masks
+    (2, 200, 32, 256, 1, 100, False, 2),   # eight heads; a 128-row GEMM tile straddles the two images
+    (1, 130, 64, 32, 3, 20, True, 1),      # three layers, key tail of two keys in the second tile
+])
+def test_experimental_projection_to_packed_attention_chain(emu_chain, B, S, Cin, C, layers, Q, masked, sms):
+    """msmx_linear_packed_kv_fwd (linear_tc_kernel<PACK>: normalise + split in the epilogue, operand images instead of
+    fp32 rows) for K = (src + pos) Wk^T and V = src Wv^T, then msmx_vmf_attention_packed_fwd per layer, against the
+    fp64 cross-attention of the reference (attention_util.py:64-82 on the projected rows)."""
+    h = emu_chain
+    torch.manual_seed(S + C + layers)
+    H = C // 32
+    src, pos = torch.randn(B, S, Cin), torch.randn(B, S, Cin)
+    wk, bk = torch.randn(layers * C, Cin) / Cin ** 0.5, torch.randn(layers * C) * 0.1
+    wv, bv = torch.randn(layers * C, Cin) / Cin ** 0.5, torch.randn(layers * C) * 0.1
+    q = torch.randn(layers, B, Q, C)
+    h.emu_set_timeout(600.0)
+    h.emu_set_sms(sms)
+    per_layer = h.msmx_vmf_packed_bytes(B, H, S, 32, 3)
+    packed = _aligned(layers * per_layer, 128)             # zero-initialised: key tails stay zero
+    key_in = (src + pos).contiguous()
+    pk, pv = _prepare(h, wk), _prepare(h, wv)
+    rc = h.msmx_linear_packed_kv_fwd(key_in.data_ptr(), Cin, pk.data_ptr(), bk.data_ptr(), packed.data_ptr(), B, S,
+                                     layers * C, Cin, C, 0, 1, 1, None)
+    assert rc == 0, h.emu_last_error()
+    rc = h.msmx_linear_packed_kv_fwd(src.data_ptr(), Cin, pv.data_ptr(), bv.data_ptr(), packed.data_ptr(), B, S,
+                                     layers * C, Cin, C, 1, 0, 0, None)
+    assert rc == 0, h.emu_last_error()
+    K = (key_in.double() @ wk.double().t() + bk.double()).view(B, S, layers, H, 32)
+    V = (src.double() @ wv.double().t() + bv.double()).view(B, S, layers, H, 32)
+    st = lambda t: (t.data_ptr(), t.stride(0), t.stride(1), t.stride(2))
+    for j in range(layers):
+        bits = ro = eff = None
+        if masked:
+            blocked = torch.rand(B, Q, S) < 0.5
+            blocked[:, 3] = True
+            ro = (~blocked).any(-1).to(torch.int32).contiguous()
+            bits = _pack_bits(blocked)
+            eff = (blocked & (ro != 0).unsqueeze(-1)).unsqueeze(1)
+        q4 = q[j].unflatten(-1, (H, 32)).permute(0, 2, 1, 3)
+        wsb = h.msmx_vmf_packed_workspace_bytes(B, H, Q, S, 32)
+        ws = torch.zeros(wsb, dtype=torch.uint8)
+        out = torch.full((B, Q, H, 32), float("nan")).permute(0, 2, 1, 3)
+        rc = h.msmx_vmf_attention_packed_fwd(*st(q4), packed.data_ptr() + j * per_layer, *st(out),
+                                             bits.data_ptr() if masked else None, bits.shape[2] if masked else 0,
+                                             ro.data_ptr() if masked else None, B, H, Q, S, 32, 30.0, 3,
+                                             ws.data_ptr(), wsb, None)
+        assert rc == 0, (rc, h.emu_last_error())
+        kj, vj = K[:, :, j].permute(0, 2, 1, 3), V[:, :, j].permute(0, 2, 1, 3)
+        s = 30.0 * F.normalize(q4.double(), dim=-1) @ F.normalize(kj, dim=-1).transpose(-1, -2)
+        if eff is not None:
+            s = s.masked_fill(eff, float("-inf"))
+        ref = F.normalize(torch.softmax(s, -1) @ vj, dim=-1)
+        err = (out.double() - ref).abs().max().item()
+        assert err == err and err < 3e-5, (j, err)

@@ -80,6 +80,12 @@ struct Params {
   int wide, l2norm, has_y2;
   const float *ln2_gamma, *ln2_beta;
   float ln2_eps;
+  // EXPERIMENTAL epilogue: instead of Y, write the operand images the packed attention
+  // kernel (csrc/experimental/vmf_packed.cu) streams - per (layer, image, head of 32 channels, 128-key tile) the
+  // [d/8][key/8][key%8][d%8] 16-bit hi / lo halves of this GEMM's output rows: K rows L2-normalised per head
+  // (pack_norm) as fp16 (pack_f16) or bf16 halves at image slots 0 / 1, V rows as bf16 halves at slots 2 / 3.
+  int pack, pack_S, pack_C, pack_B, pack_ntiles, pack_slot, pack_norm, pack_f16;
+  uint8_t* pack_out;
 };
 
 #ifdef MSM_EMULATE_ON_HOST  // tests/emu
@@ -90,6 +96,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 #endif
 
+// PACK: the experimental operand-image epilogue (Params::pack*) is compiled into its own instantiation, so the
+// shipped <false> kernel is byte-for-byte the one that was validated on the B200
+template <bool PACK>
 __global__ void __launch_bounds__(kThreads, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap,
                  const __grid_constant__ CUtensorMap ymap, const __grid_constant__ CUtensorMap y2map, const Params P) {
@@ -330,6 +339,59 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
       tc::mbar_wait(&acc_full[acc], (t / P.nacc) & 1);
       tc::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 128u;
+      if constexpr (PACK) {
+        // thread = token row (b, key); per 32-column chunk = one head: (normalise) -> split -> four 16-byte stores per
+        // half; the 32 lanes of a warp (32 consecutive keys) write 512 contiguous bytes per 8-channel group
+        constexpr uint32_t kOp = 128u * 32u * 2u, kLbo = 2048u;  // one 16-bit operand of a tile at hd = 32
+        const int grow = mt * kRows + row;
+        const bool in = grow < P.M;
+        const int bi = in ? grow / P.pack_S : 0, key = in ? grow % P.pack_S : 0;
+        const uint32_t koff = (uint32_t)((key & 127) >> 3) * 128u + (uint32_t)(key & 7) * 16u;
+        const int heads = P.pack_C / 32;
+        for (int ch = 0; ch < nchunk; ++ch) {
+          uint32_t r[32];
+          tc::tmem_ld32(taddr + ch * 32, r);
+          tc::tmem_ld_wait();
+          if (ch == nchunk - 1) {
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
+          }
+          if (in) {
+            const int n0 = nc * P.BN + ch * 32;
+            const int layer = n0 / P.pack_C, head = (n0 % P.pack_C) / 32;
+            float v[32];
+            float ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              v[j] = __uint_as_float(r[j]) + wBias[ch * 32 + j];
+              ss = fmaf(v[j], v[j], ss);
+            }
+            const float inv = P.pack_norm ? 1.f / fmaxf(sqrtf(ss), 1e-12f) : 1.f;
+            uint8_t* img = P.pack_out +
+                           ((((int64_t)layer * P.pack_B + bi) * heads + head) * P.pack_ntiles + (key >> 7)) * (4 * kOp) +
+                           (uint32_t)P.pack_slot * kOp + koff;
+#pragma unroll
+            for (int dg = 0; dg < 4; ++dg) {
+              uint4 hi, lo;
+              if (P.pack_f16) {
+                tc::split2h(v[8 * dg + 0] * inv, v[8 * dg + 1] * inv, hi.x, lo.x);
+                tc::split2h(v[8 * dg + 2] * inv, v[8 * dg + 3] * inv, hi.y, lo.y);
+                tc::split2h(v[8 * dg + 4] * inv, v[8 * dg + 5] * inv, hi.z, lo.z);
+                tc::split2h(v[8 * dg + 6] * inv, v[8 * dg + 7] * inv, hi.w, lo.w);
+              } else {
+                tc::split2(v[8 * dg + 0] * inv, v[8 * dg + 1] * inv, hi.x, lo.x);
+                tc::split2(v[8 * dg + 2] * inv, v[8 * dg + 3] * inv, hi.y, lo.y);
+                tc::split2(v[8 * dg + 4] * inv, v[8 * dg + 5] * inv, hi.z, lo.z);
+                tc::split2(v[8 * dg + 6] * inv, v[8 * dg + 7] * inv, hi.w, lo.w);
+              }
+              *reinterpret_cast<uint4*>(img + dg * kLbo) = hi;
+              *reinterpret_cast<uint4*>(img + kOp + dg * kLbo) = lo;
+            }
+          }
+        }
+        continue;
+      }
       if (P.y_nchw) {
         // Y[b][n][pixel]: lane = pixel, so each store instruction writes one 128-byte row segment
         const int bi = mt / P.tiles_per_b;
@@ -639,6 +701,9 @@ struct LnArgs {
   int64_t ldy2 = 0;
   // 3x3 convolution geometry
   int conv3 = 0, H = 0, W = 0, C = 0, Wp = 0;
+  // experimental operand-image epilogue (Params::pack*)
+  int pack = 0, pack_S = 0, pack_C = 0, pack_B = 0, pack_slot = 0, pack_norm = 0, pack_f16 = 0;
+  uint8_t* pack_out = nullptr;
 };
 
 static int launch(const float* X, int64_t ldx, const void* prepared, const float* bias, float* Y, int64_t ldy, int M,
@@ -649,6 +714,9 @@ static int launch(const float* X, int64_t ldx, const void* prepared, const float
   P.residual = ln.residual; P.ldr = ln.ldr; P.ln_gamma = ln.gamma; P.ln_beta = ln.beta; P.ln_eps = ln.eps;
   P.wide = ln.wide; P.l2norm = ln.l2norm; P.rowbias = ln.rowbias; P.rowbias_period = ln.rowbias_period;
   P.has_y2 = ln.y2 != nullptr; P.ln2_gamma = ln.gamma2; P.ln2_beta = ln.beta2; P.ln2_eps = ln.eps2;
+  P.pack = ln.pack; P.pack_S = ln.pack_S; P.pack_C = ln.pack_C; P.pack_B = ln.pack_B; P.pack_slot = ln.pack_slot;
+  P.pack_norm = ln.pack_norm; P.pack_f16 = ln.pack_f16; P.pack_out = ln.pack_out;
+  P.pack_ntiles = ln.pack ? (ln.pack_S + 127) / 128 : 0;
   const int m_tiles_est = x_nchw ? Bt * ((Mb + kRows - 1) / kRows) : (M + kRows - 1) / kRows;
   P.BN = ln.wide ? N : pick_bn(N, ln.conv3 ? sms_many() : m_tiles_est);
   P.nacc = P.BN > 128 ? 1 : kAcc;
@@ -702,8 +770,8 @@ static int launch(const float* X, int64_t ldx, const void* prepared, const float
     int rc = tc::encode_tensor_map(&wmap, tc::TmapType::BF16, tc::TmapSwizzle::None, prepared, 4, dims, strides, box);
     if (rc) return rc;
   }
-  if (y_nchw) {
-    ymap = wmap;  // unused by the kernel in this mode
+  if (y_nchw || ln.pack) {
+    ymap = wmap;  // unused by the kernel in these modes
   } else if (x_nchw) {
     const uint64_t dims[3] = {(uint64_t)N, (uint64_t)Mb, (uint64_t)Bt};
     const uint64_t strides[2] = {(uint64_t)ldy * 4, (uint64_t)ldy * 4 * (uint64_t)Mb};
@@ -734,17 +802,25 @@ static int launch(const float* X, int64_t ldx, const void* prepared, const float
   (void)st;
   if (smem > sizeof(ltc::smem_raw)) return MSM_E_UNSUPPORTED;
   tc::g_tc->smem_base = reinterpret_cast<uintptr_t>(ltc::smem_raw);
-  cuda_emu::launch(dim3(grid, 1), kThreads, [&] { linear_tc_kernel(xmap, wmap, ymap, y2map, P); });
+  cuda_emu::launch(dim3(grid, 1), kThreads, [&] {
+    if (P.pack) linear_tc_kernel<true>(xmap, wmap, ymap, y2map, P);
+    else linear_tc_kernel<false>(xmap, wmap, ymap, y2map, P);
+  });
   return 0;
 #else
-  static bool configured = false;
-  if (!configured) {
-    MSM_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    configured = true;
-  }
   // >= 116 KB of dynamic shared memory keeps it at one CTA per SM (each CTA allocates all of TMEM)
   const size_t req = smem < (size_t)(120 << 10) ? (size_t)(120 << 10) : smem;
-  MSM_CUDA(launch_pdl(linear_tc_kernel, dim3(grid), dim3(kThreads), req, st, xmap, wmap, ymap, y2map, P));
+  if (P.pack) {
+    MSM_CUDA(cudaFuncSetAttribute(linear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    MSM_CUDA(launch_pdl(linear_tc_kernel<true>, dim3(grid), dim3(kThreads), req, st, xmap, wmap, ymap, y2map, P));
+    return check_launch("linear_tc_kernel<pack>");
+  }
+  static bool configured = false;
+  if (!configured) {
+    MSM_CUDA(cudaFuncSetAttribute(linear_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    configured = true;
+  }
+  MSM_CUDA(launch_pdl(linear_tc_kernel<false>, dim3(grid), dim3(kThreads), req, st, xmap, wmap, ymap, y2map, P));
   return check_launch("linear_tc_kernel");
 #endif
 }
@@ -761,6 +837,30 @@ extern "C" int msm_linear_fwd(const float* X, int64_t ldx, const void* prepared,
   MSM_REQUIRE(ldx >= K && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0, "X rows must be 16-byte aligned");
   MSM_REQUIRE(ldy >= N && ldy % 4 == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0, "Y rows must be 16-byte aligned");
   return msm::ltc::launch(X, ldx, prepared, bias, Y, ldy, M, N, K, act, 0, 0, 1, M, static_cast<cudaStream_t>(stream));
+}
+
+// EXPERIMENTAL (not declared in include/msmformer_b200.h): K or V projection of the decoder's cross-attention whose
+// epilogue writes the operand images of csrc/experimental/vmf_packed.cu instead of fp32 rows. X [B*S][K] token-major,
+// W [N][K] with N = layers * C (the projections of all decoder layers of a level in one GEMM), heads of 32 channels.
+// packed: [layers][B][C/32][ceil(S/128)][4][8192] bytes, 128-byte aligned, ZERO-initialised once by the caller (key
+// tails stay zero); which = 0: K (slots 0/1; normalize / f16 as the attention flags say), 1: V (slots 2/3, bf16).
+extern "C" int msmx_linear_packed_kv_fwd(const float* X, int64_t ldx, const void* prepared, const float* bias,
+                                         void* packed, int B, int S, int N, int K, int C, int which, int normalize,
+                                         int f16, void* stream) {
+  MSM_REQUIRE(X && prepared && packed, "X, prepared, packed must be non-null");
+  MSM_REQUIRE(B > 0 && S > 0 && N > 0 && K > 0 && C > 0, "sizes must be positive");
+  MSM_REQUIRE(K % 32 == 0 && C % 32 == 0 && N % C == 0, "K and C must be multiples of 32, N a multiple of C");
+  MSM_REQUIRE(which == 0 || which == 1, "which must be 0 (K) or 1 (V)");
+  MSM_REQUIRE(ldx >= K && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0, "X rows must be 16-byte aligned");
+  MSM_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 127) == 0, "packed must be 128-byte aligned");
+  MSM_REQUIRE((int64_t)B * S < (int64_t)1 << 31, "B * S must fit 31 bits");
+  msm::ltc::LnArgs a;
+  a.pack = 1; a.pack_S = S; a.pack_C = C; a.pack_B = B; a.pack_slot = which == 0 ? 0 : 2;
+  a.pack_norm = which == 0 ? (normalize ? 1 : 0) : 0;
+  a.pack_f16 = which == 0 ? (f16 ? 1 : 0) : 0;
+  a.pack_out = static_cast<uint8_t*>(packed);
+  return msm::ltc::launch(X, ldx, prepared, bias, nullptr, N, B * S, N, K, 0, 0, 0, 1, B * S,
+                          static_cast<cudaStream_t>(stream), a);
 }
 
 extern "C" int msm_linear_ln_fwd(const float* X, int64_t ldx, const void* prepared, const float* bias,
