@@ -180,6 +180,73 @@ def child(quick):
               f"({fl / t_old / 1e9:6.1f} TFLOP/s)", flush=True)
         assert err < 2e-4, "packed attention disagrees with the shipped kernel"
 
+    # ---- the fused chain: K / V projections writing the images (linear_tc_kernel<PACK> in the product library) +
+    # packed attention, against dense K, dense V + the shipped attention kernel
+    from unseenobjectswithmeanshift_b200 import _lib
+    L = _lib.lib()
+    P_, I_, L_ = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+    L.msmx_linear_packed_kv_fwd.restype = I_
+    L.msmx_linear_packed_kv_fwd.argtypes = [P_, L_, P_, P_, P_, I_, I_, I_, I_, I_, I_, I_, I_, P_]
+    ccases = [(2, 300, 256, 256, 3, 100), (1, 4800, 256, 256, 3, 100), (1, 50176, 256, 256, 1, 100),
+              (1, 307200, 256, 256, 1, 100)]
+    for (B, S, Cin, C, layers, Q) in ccases:
+        g = torch.Generator(device="cuda").manual_seed(S + layers)
+        H = C // 32
+        src = torch.randn(B, S, Cin, device=dev, generator=g)
+        key_in = src + torch.randn(B, S, Cin, device=dev, generator=g)
+        wk = torch.randn(layers * C, Cin, device=dev, generator=g) / Cin ** 0.5
+        wv = torch.randn(layers * C, Cin, device=dev, generator=g) / Cin ** 0.5
+        bk, bv = (0.1 * torch.randn(layers * C, device=dev, generator=g) for _ in range(2))
+        q = torch.randn(B, Q, C, device=dev, generator=g)
+        blocked = torch.rand(B, Q, S, device=dev, generator=g) < 0.5
+        blocked[:, 3] = True
+        ro = (~blocked).any(-1).to(torch.int32).contiguous()
+        bits = pack_bits(blocked)
+        hv = lambda t: t.unflatten(-1, (H, 32)).permute(0, 2, 1, 3)
+        per_layer = h.msmx_vmf_packed_bytes(B, H, S, 32, 3)
+        packed = torch.zeros(layers * per_layer, dtype=torch.uint8, device=dev)   # key tails stay zero
+        pk, pv = ops.prepare_linear_weight(wk), ops.prepare_linear_weight(wv)
+        wsb = h.msmx_vmf_packed_workspace_bytes(B, H, Q, S, 32)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        out = torch.empty(B, Q, H, 32, device=dev).permute(0, 2, 1, 3)
+        sd = lambda t: (t.data_ptr(), t.stride(0), t.stride(1), t.stride(2))
+
+        def project_packed():
+            for which, x, w, b in ((0, key_in, pk, bk), (1, src, pv, bv)):
+                rc = L.msmx_linear_packed_kv_fwd(x.data_ptr(), Cin, w.data_ptr(), b.data_ptr(), packed.data_ptr(), B, S,
+                                                 layers * C, Cin, C, which, 1, 1, st())
+                assert rc == 0, L.msm_last_error()
+
+        def attend_packed(j=0):
+            rc = h.msmx_vmf_attention_packed_fwd(*sd(hv(q)), packed.data_ptr() + j * per_layer, *sd(out), bits.data_ptr(),
+                                                 bits.shape[2], ro.data_ptr(), B, H, Q, S, 32, 30.0, 3, ws.data_ptr(), wsb,
+                                                 st())
+            assert rc == 0, h.msm_last_error()
+
+        def shipped(j=0, project=True, attend=True):
+            if project:
+                shipped.K, shipped.V = ops.dense(key_in, wk, bk), ops.dense(src, wv, bv)
+            if attend:
+                return ops.vmf_attention(hv(q), hv(shipped.K[..., j * C:(j + 1) * C]), hv(shipped.V[..., j * C:(j + 1) * C]),
+                                         blocked_bits=bits, row_open=ro)
+
+        with torch.no_grad():
+            project_packed()
+            worst = 0.0
+            for j in range(layers):
+                attend_packed(j)
+                want = shipped(j, project=(j == 0))
+                torch.cuda.synchronize()
+                worst = max(worst, (out - want).abs().max().item())
+            reps = 3 if S > 100000 else 10
+            t_pp, t_pa = timed(project_packed, reps), timed(attend_packed, reps)
+            t_sp = timed(lambda: shipped(project=True, attend=False), reps)
+            t_sa = timed(lambda: shipped(project=False, attend=True), reps)
+        print(f"  chain B{B} S{S} C{C} layers{layers}: |fused - shipped| {worst:.2e}   projections packed {t_pp * 1e3:9.1f} us "
+              f"vs dense {t_sp * 1e3:9.1f} us   attention packed {t_pa * 1e3:9.1f} us vs shipped {t_sa * 1e3:9.1f} us",
+              flush=True)
+        assert worst < 2e-4, "fused chain disagrees with the shipped path"
+
 
 if __name__ == "__main__":
     arg = sys.argv[1] if len(sys.argv) > 1 else "full"
