@@ -256,5 +256,5 @@ if __name__ == "__main__":
         child(len(sys.argv) > 2 and sys.argv[2] == "quick")
     else:
         build()
-        rc = subprocess.call([sys.executable, os.path.abspath(__file__), "child", arg], timeout=400)
+        rc = subprocess.call([sys.executable, os.path.abspath(__file__), "child", arg], timeout=600)
         sys.exit(rc)

@@ -12,7 +12,7 @@ timeout 600 python -m pytest tests -q -m gpu_staged -x 2>&1 | tee gpurun_out/nex
 timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_staged.py -q -x \
     -k "golden and vmf" > gpurun_out/next_sanitizer.log 2>&1; tail -5 gpurun_out/next_sanitizer.log
 # 4. experimental packed-operand mean-shift kernel: parity + timing against the shipped one
-timeout 420 python tools/dev_vmf_packed.py quick 2>&1 | tee gpurun_out/next_vmf_packed.log | tail -12
+timeout 660 python tools/dev_vmf_packed.py quick 2>&1 | tee gpurun_out/next_vmf_packed.log | tail -12
 # 5. training workload (config #5), one GPU
 timeout 600 python bench.py --workload train --steps 5 --warmup 3 > gpurun_out/next_bench_train.json \
     2> gpurun_out/next_bench_train.err; echo "train bench rc=$?"; cut -c1-600 gpurun_out/next_bench_train.json
