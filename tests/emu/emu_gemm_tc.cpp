@@ -1,0 +1,52 @@
+// Emulation driver for the remaining SHIPPED tcgen05 kernels - csrc/mask_head_tc.cu (mask einsum) and csrc/ffn_tc.cu
+// (fused feed-forward block) - compiled as plain C++ together with linear_tc.cu (weight preparation). Calibration
+// breadth for tests/emu and a CPU development loop for these kernels. Built by tests/test_kernel_emulation.py.
+#include "cuda_emu.h"
+#include "tc_emu.h"
+
+#include <cstdarg>
+
+#include "../../unseenobjectswithmeanshift_b200/csrc/common.cuh"
+
+namespace msm {
+static char g_emu_err[512];
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_emu_err, sizeof(g_emu_err), fmt, ap);
+  va_end(ap);
+}
+static int g_sms = 2;
+int num_sms() { return g_sms; }
+bool tc_enabled() { return true; }
+bool pdl_enabled() { return false; }
+namespace ltc {
+__attribute__((aligned(1024))) uint8_t smem_raw[232448 + 1024];
+}
+namespace mtc {
+__attribute__((aligned(1024))) uint8_t smem[232448];
+}
+namespace ftc {
+__attribute__((aligned(1024))) uint8_t smem_raw[232448 + 1024];
+}
+}  // namespace msm
+
+#include "../../unseenobjectswithmeanshift_b200/csrc/linear_tc.cu"
+#include "../../unseenobjectswithmeanshift_b200/csrc/mask_head_tc.cu"
+#include "../../unseenobjectswithmeanshift_b200/csrc/ffn_tc.cu"
+
+static msm::tc::EmuState g_state;
+
+extern "C" void emu_set_timeout(double timeout_s) {
+  msm::tc::g_tc = &g_state;
+  cuda_emu::g_deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds((long)(timeout_s * 1e3));
+  cuda_emu::g_block_begin = [] {
+    g_state.bars.clear();
+    std::fill(g_state.tmem.begin(), g_state.tmem.end(), 0x7fc00000u);
+  };
+}
+extern "C" void emu_set_sms(int n) { msm::g_sms = n; }
+extern "C" const char* emu_last_error() { return msm::g_emu_err; }
+extern "C" int emu_mask_logits_tc(const float* embed, const float* feat, float* masks, int B, int Q, int C, int64_t HW) {
+  return msm::mask_logits_tc(embed, feat, masks, B, Q, C, HW, nullptr);
+}

@@ -505,3 +505,60 @@ def test_experimental_projection_to_packed_attention_chain(emu_chain, B, S, Cin,
         ref = F.normalize(torch.softmax(s, -1) @ vj, dim=-1)
         err = (out.double() - ref).abs().max().item()
         assert err == err and err < 3e-5, (j, err)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the remaining shipped tcgen05 kernels: mask einsum and fused feed-forward block
+@pytest.fixture(scope="module")
+def emu_gemm():
+    from unseenobjectswithmeanshift_b200._lib import SIGNATURES
+    h = _build(os.path.join(ROOT, "build", "emu", "libemu_gemm_tc.so"), "emu_gemm_tc.cpp",
+               ["linear_tc.cu", "mask_head_tc.cu", "ffn_tc.cu"])
+    for n in ("msm_linear_weight_bytes", "msm_linear_prepare_weight", "msm_ffn_ln_fwd"):
+        f = getattr(h, n)
+        f.restype, f.argtypes = SIGNATURES[n]
+    P, I, L = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+    h.emu_mask_logits_tc.restype, h.emu_mask_logits_tc.argtypes = I, [P, P, P, I, I, I, L]
+    h.emu_set_timeout.argtypes = [ctypes.c_double]
+    h.emu_set_sms.argtypes = [I]
+    h.emu_last_error.restype = ctypes.c_char_p
+    return h
+
+
+def _f32_aligned(t):
+    b = _aligned(t.numel() * 4, 128).view(torch.float32).view(t.shape)
+    b.copy_(t)
+    return b
+
+
+@pytest.mark.parametrize("B,Q,C,H,W,sms", [(2, 100, 256, 12, 16, 2), (1, 10, 32, 24, 32, 1), (1, 100, 64, 30, 44, 2)])
+def test_calibration_shipped_mask_head_kernel(emu_gemm, B, Q, C, H, W, sms):
+    h = emu_gemm
+    torch.manual_seed(Q + C + H)
+    e, f = _f32_aligned(torch.randn(B, Q, C)), _f32_aligned(torch.randn(B, C, H, W))
+    out = torch.full((B, Q, H, W), float("nan"))
+    _start(h, sms)
+    rc = h.emu_mask_logits_tc(e.data_ptr(), f.data_ptr(), out.data_ptr(), B, Q, C, H * W)
+    assert rc == 0, (rc, h.emu_last_error())
+    ref = torch.einsum("bqc,bchw->bqhw", e.double(), f.double())
+    assert (out.double() - ref).abs().max().item() < 2e-6 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("M,D,Fh,sms", [(300, 64, 256, 2), (520, 32, 128, 1)])
+def test_calibration_shipped_ffn_kernel(emu_gemm, M, D, Fh, sms):
+    h = emu_gemm
+    torch.manual_seed(M + D + Fh)
+    x = torch.randn(M, D)
+    w1, b1 = torch.randn(Fh, D) / D ** 0.5, torch.randn(Fh) * 0.1
+    w2, b2 = torch.randn(D, Fh) / Fh ** 0.5, torch.randn(D) * 0.1
+    g, be = torch.randn(D), torch.randn(D)
+    y = torch.full((M, D), float("nan"))
+    _start(h, sms)
+    p1, p2 = _prepare(h, w1), _prepare(h, w2)
+    rc = h.msm_ffn_ln_fwd(x.data_ptr(), D, p1.data_ptr(), b1.data_ptr(), p2.data_ptr(), b2.data_ptr(), g.data_ptr(),
+                          be.data_ptr(), 1e-5, y.data_ptr(), D, M, D, Fh, None)
+    assert rc == 0, (rc, h.emu_last_error())
+    xd = x.double()
+    ref = F.layer_norm(xd + F.linear(F.relu(F.linear(xd, w1.double(), b1.double())), w2.double(), b2.double()), (D,),
+                       g.double(), be.double(), 1e-5)
+    assert (y.double() - ref).abs().max().item() < 2e-5

@@ -47,9 +47,13 @@ struct Params {
   int64_t ldx;
 };
 
+#ifdef MSM_EMULATE_ON_HOST  // tests/emu
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { emu_named_bar_sync(id, nthreads); }
+#else
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+#endif
 
 template <int D>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -405,16 +409,24 @@ static int launch(const float* X, int64_t ldx, const void* w1p, const float* b1,
     set_error("ffn: d_ffn %d needs %zu bytes of shared memory", F, smem);
     return MSM_E_UNSUPPORTED;
   }
+  const int n_units = (P.m_tiles + 1) / 2;
+  const int grid = n_units < num_sms() ? n_units : num_sms();
+#ifdef MSM_EMULATE_ON_HOST
+  (void)st;
+  if (smem + 1024 > sizeof(ftc::smem_raw)) return MSM_E_UNSUPPORTED;
+  tc::g_tc->smem_base = reinterpret_cast<uintptr_t>(ftc::smem_raw);
+  cuda_emu::launch(dim3(grid, 1), kThreads, [&] { ffn_tc_kernel<D>(xmap, w1map, w2map, ymap, P); });
+  return 0;
+#else
   static bool configured = false;
   if (!configured) {
     MSM_CUDA(cudaFuncSetAttribute(ffn_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     configured = true;
   }
-  const int n_units = (P.m_tiles + 1) / 2;
-  const int grid = n_units < num_sms() ? n_units : num_sms();
   const size_t req = smem < (size_t)(120 << 10) ? (size_t)(120 << 10) : smem;
   MSM_CUDA(launch_pdl(ffn_tc_kernel<D>, dim3(grid), dim3(kThreads), req, st, xmap, w1map, w2map, ymap, P));
   return check_launch("ffn_tc_kernel");
+#endif
 }
 
 }  // namespace ftc

@@ -298,9 +298,17 @@ int mask_logits_tc(const float* embed, const float* feat, float* masks, int B, i
   const uint32_t box[3] = {(uint32_t)kPx, (uint32_t)kKc, 1};
   int rc = tc::encode_tensor_map_f32(&fmap, feat, 3, dims, strides, box);
   if (rc) return rc;
+#ifdef MSM_EMULATE_ON_HOST  // tests/emu: the kernel text on CPU threads
+  (void)st;
+  if (smem > sizeof(mtc::smem)) return MSM_E_UNSUPPORTED;
+  tc::g_tc->smem_base = reinterpret_cast<uintptr_t>(mtc::smem);
+  cuda_emu::launch(dim3(B * cpi, 1), kThreads, [&] { mask_gemm_tc_kernel(fmap, P); });
+  return 0;
+#else
   MSM_CUDA(cudaFuncSetAttribute(mask_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
   MSM_CUDA(launch_pdl(mask_gemm_tc_kernel, dim3(B * cpi), dim3(kThreads), smem, st, fmap, P));
   return check_launch("mask_gemm_tc_kernel");
+#endif
 }
 
 }  // namespace msm
