@@ -113,6 +113,9 @@ def run_reference(args, rank, world):
     if args.workload in ("meanshift", "cluster", "tail"):
         run_reference_aux(args, cores)
         return
+    if args.workload in ("train", "twostage"):
+        run_reference_train_twostage(args, cores)
+        return
     head = workloads.build_head(args.workload)
     sd = {k: v.detach() for k, v in head.state_dict().items()}
     sample_b = 2
@@ -134,6 +137,60 @@ def run_reference(args, rank, world):
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
+
+
+def run_reference_train_twostage(args, cores):
+    """--impl reference for the train / twostage workloads: the oracle port on a bounded sample per step.
+    train: forward + losses + backward of the R50-config head on 1 image (torch.autograd through the oracle, the
+    criterion mirror on CPU; no optimizer update). twostage: stage-1 oracle head on 1 frame + crop oracle head on its
+    5 crops (the glue between them is negligible on the CPU)."""
+    from oracle import head as ohead
+    from unseenobjectswithmeanshift_b200 import workloads
+    if args.workload == "train":
+        from unseenobjectswithmeanshift_b200.meanshiftformer.meanshiftformer_model import build_criterion
+        head = workloads.build_head("r50")
+        sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in head.state_dict().items()}
+        feats = workloads.synthetic_features("r50", 1)
+        targets = workloads.synthetic_targets("r50", 1)
+        crit = build_criterion(2, dec_layers=workloads.HEAD_CFG["r50"]["dec_layers"] + 1)
+
+        def step():
+            out, _ = ohead.head_forward(sd, feats, **workloads.oracle_kwargs("r50"))
+            losses = crit(out, targets)
+            sum(v * crit.weight_dict[k] for k, v in losses.items()).backward()
+            for t in sd.values():
+                t.grad = None
+        sample_b, metric = 1, ("images/sec MSMFormer head training step 640x480 (R50 config: forward + deep-supervision "
+                               "losses + backward + clipped AdamW)")
+        workload = "train r50-head 640x480, 100 queries, 9 decoder layers, 5 instances/image (no optimizer update)"
+    else:
+        heads = {k: workloads.build_head(k) for k in ("ucn", "crop")}
+        sds = {k: {n: v.detach() for n, v in h.state_dict().items()} for k, h in heads.items()}
+        feats = {"ucn": workloads.synthetic_features("ucn", 1), "crop": workloads.synthetic_features("crop", 5)}
+
+        def step():
+            with torch.no_grad():
+                for k in ("ucn", "crop"):
+                    ohead.head_forward(sds[k], feats[k], **workloads.oracle_kwargs(k))
+        sample_b, metric = 1, ("frames/sec two-stage RGB-D segmentation 640x480 (stage-1 head + 5 zoom-crops through "
+                               "the crop head + paste-back)")
+        workload = "twostage 640x480, 5 crops of 224x224 per frame (heads only)"
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = sample_b * args.steps / dt
+    emit({"impl": "reference", "metric": metric, "value": val, "unit": "images/s", "n_gpus": args.gpus,
+          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+          "config": {"workload": workload, "per_step_batch": sample_b,
+                     "note": "CPU oracle port of the reference PyTorch path, fp32"},
+          "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port",
+                           "sample": f"{args.steps} steps x {sample_b} image(s) of the same workload"},
+          "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+          "gpu_launches": 0})
 
 
 def run_reference_aux(args, cores):
