@@ -112,6 +112,8 @@ using std::min;
 namespace cuda_emu {
 // run `body()` as a grid of blocks of `threads` threads (1-D blocks, 2-D grid), one block at a time
 inline std::function<void()> g_block_begin;  // optional: called before every block (the tc layer resets its state)
+inline std::function<void()> g_block_end;    // optional: after all threads of a block have finished
+inline std::function<void()> g_thread_end;   // optional: in every thread, after the kernel body
 inline void launch(dim3 grid, int threads, const std::function<void()>& body) {
   for (unsigned by = 0; by < grid.y; ++by)
     for (unsigned bx = 0; bx < grid.x; ++bx) {
@@ -132,8 +134,10 @@ inline void launch(dim3 grid, int threads, const std::function<void()>& body) {
           blockDim = dim3(threads, 1, 1);
           gridDim = grid;
           body();
+          if (g_thread_end) g_thread_end();
         });
       for (auto& th : pool) th.join();
+      if (g_block_end) g_block_end();
       g_block = nullptr;
     }
 }

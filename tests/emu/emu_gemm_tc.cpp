@@ -37,14 +37,10 @@ __attribute__((aligned(1024))) uint8_t smem_raw[232448 + 1024];
 
 static msm::tc::EmuState g_state;
 
-extern "C" void emu_set_timeout(double timeout_s) {
-  msm::tc::g_tc = &g_state;
-  cuda_emu::g_deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds((long)(timeout_s * 1e3));
-  cuda_emu::g_block_begin = [] {
-    g_state.bars.clear();
-    std::fill(g_state.tmem.begin(), g_state.tmem.end(), 0x7fc00000u);
-  };
-}
+static int g_late = 0;
+extern "C" void emu_set_timeout(double timeout_s) { msm::tc::emu_prepare(&g_state, timeout_s, g_late); }
+extern "C" void emu_set_late(int late) { g_late = late; }
+extern "C" long emu_deferred_ops() { return g_state.deferred; }
 extern "C" void emu_set_sms(int n) { msm::g_sms = n; }
 extern "C" const char* emu_last_error() { return msm::g_emu_err; }
 extern "C" int emu_mask_logits_tc(const float* embed, const float* feat, float* masks, int B, int Q, int C, int64_t HW) {

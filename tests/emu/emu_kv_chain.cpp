@@ -33,13 +33,9 @@ __attribute__((aligned(1024))) uint8_t smem[232448];
 
 static msm::tc::EmuState g_state;
 
-extern "C" void emu_set_timeout(double timeout_s) {
-  msm::tc::g_tc = &g_state;
-  cuda_emu::g_deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds((long)(timeout_s * 1e3));
-  cuda_emu::g_block_begin = [] {
-    g_state.bars.clear();
-    std::fill(g_state.tmem.begin(), g_state.tmem.end(), 0x7fc00000u);
-  };
-}
+static int g_late = 0;
+extern "C" void emu_set_timeout(double timeout_s) { msm::tc::emu_prepare(&g_state, timeout_s, g_late); }
+extern "C" void emu_set_late(int late) { g_late = late; }
+extern "C" long emu_deferred_ops() { return g_state.deferred; }
 extern "C" void emu_set_sms(int n) { msm::g_sms = n; }
 extern "C" const char* emu_last_error() { return msm::g_emu_err; }

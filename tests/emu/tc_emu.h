@@ -11,6 +11,7 @@
 #include <atomic>
 #include <cstdint>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <thread>
@@ -28,8 +29,18 @@ struct MbarState {
   int64_t pending = 0, tx = 0;
   uint32_t phase = 0;  // parity of the phase in progress
 };
+struct Deferred {
+  uintptr_t bar;               // barrier this operation signals when it completes (0: none)
+  std::function<void()> run;   // executes the operation and signals; called with EmuState::mu held
+};
 struct EmuState {
-  std::mutex mu;
+  std::recursive_mutex mu;
+  // "late" mode: asynchronous operations do not execute at issue but as late as the barrier protocol allows - when a
+  // thread is about to block on the barrier they signal (TMA loads: any order; the tensor pipe: in issue order).
+  // A kernel that reads an operand or a result without waiting, or recycles a buffer too early, then computes garbage.
+  bool late = false;
+  long deferred = 0;  // operations that went through the queues (0 in synchronous mode)
+  std::vector<Deferred> tma_q, mma_q;
   std::map<uintptr_t, MbarState> bars;
   std::vector<uint32_t> tmem = std::vector<uint32_t>(128 * 512, 0u);  // [lane][column]
   uintptr_t smem_base = 0;                                             // generic address of shared-memory offset 0
@@ -48,7 +59,7 @@ inline void mbar_complete_if_done(MbarState& b) {
   }
 }
 inline void mbar_init(uint64_t* bar, uint32_t count) {
-  std::lock_guard<std::mutex> l(g_tc->mu);
+  std::lock_guard<std::recursive_mutex> l(g_tc->mu);
   MbarState& b = g_tc->bars[reinterpret_cast<uintptr_t>(bar)];
   b = MbarState();
   b.init = count;
@@ -62,14 +73,14 @@ inline MbarState& mbar_state(uint64_t* bar) {
   return it->second;
 }
 inline void mbar_arrive(uint64_t* bar) {
-  std::lock_guard<std::mutex> l(g_tc->mu);
+  std::lock_guard<std::recursive_mutex> l(g_tc->mu);
   MbarState& b = mbar_state(bar);
   if (b.pending <= 0) cuda_emu::die("mbarrier: more arrivals than the init count in one phase");
   b.pending -= 1;
   mbar_complete_if_done(b);
 }
 inline void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  std::lock_guard<std::mutex> l(g_tc->mu);
+  std::lock_guard<std::recursive_mutex> l(g_tc->mu);
   MbarState& b = mbar_state(bar);
   if (b.pending <= 0) cuda_emu::die("mbarrier: more arrivals than the init count in one phase");
   b.tx += bytes;
@@ -78,15 +89,52 @@ inline void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   mbar_complete_if_done(b);
 }
 inline void mbar_complete_tx(uint64_t* bar, uint32_t bytes) {
-  std::lock_guard<std::mutex> l(g_tc->mu);
+  std::lock_guard<std::recursive_mutex> l(g_tc->mu);
   MbarState& b = mbar_state(bar);
   b.tx -= bytes;
   if (b.tx < -((1 << 20) - 1)) cuda_emu::die("mbarrier: transaction count below -(2^20 - 1) bytes");
   mbar_complete_if_done(b);
 }
+// late mode: run what has to complete before `bar` can flip - its TMA loads, and the tensor-pipe prefix up to the last
+// queued operation that signals it
+inline void flush_for(uintptr_t bar) {
+  for (size_t i = 0; i < g_tc->tma_q.size();) {
+    if (g_tc->tma_q[i].bar == bar) {
+      auto op = std::move(g_tc->tma_q[i]);
+      g_tc->tma_q.erase(g_tc->tma_q.begin() + i);
+      op.run();
+    } else {
+      ++i;
+    }
+  }
+  size_t last = 0;
+  for (size_t i = 0; i < g_tc->mma_q.size(); ++i)
+    if (g_tc->mma_q[i].bar == bar) last = i + 1;
+  if (last) {
+    std::vector<Deferred> head(std::make_move_iterator(g_tc->mma_q.begin()),
+                               std::make_move_iterator(g_tc->mma_q.begin() + last));
+    g_tc->mma_q.erase(g_tc->mma_q.begin(), g_tc->mma_q.begin() + last);
+    for (auto& op : head) op.run();
+  }
+}
+inline void flush_all() {  // end of a block: everything still in flight completes
+  std::lock_guard<std::recursive_mutex> l(g_tc->mu);
+  while (!g_tc->tma_q.empty() || !g_tc->mma_q.empty()) {
+    std::vector<Deferred> a = std::move(g_tc->tma_q), b = std::move(g_tc->mma_q);
+    g_tc->tma_q.clear();
+    g_tc->mma_q.clear();
+    for (auto& op : a) op.run();
+    for (auto& op : b) op.run();
+  }
+}
 inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) {  // true once the phase of this parity has completed
-  std::lock_guard<std::mutex> l(g_tc->mu);
-  return mbar_state(bar).phase != (parity & 1u);
+  std::lock_guard<std::recursive_mutex> l(g_tc->mu);
+  if (mbar_state(bar).phase != (parity & 1u)) return true;
+  if (g_tc->late) {
+    flush_for(reinterpret_cast<uintptr_t>(bar));
+    return mbar_state(bar).phase != (parity & 1u);
+  }
+  return false;
 }
 inline void mbar_wait(uint64_t* bar, uint32_t parity) {
   int spins = 0;
@@ -107,10 +155,21 @@ struct Ring {
 };
 
 // 1-D bulk copy global -> shared, completing `bytes` of transaction on the barrier
+inline void defer_or_run(std::vector<Deferred>& q, uint64_t* bar, std::function<void()> op) {
+  std::lock_guard<std::recursive_mutex> l(g_tc->mu);
+  if (g_tc->late) {
+    ++g_tc->deferred;
+    q.push_back(Deferred{reinterpret_cast<uintptr_t>(bar), std::move(op)});
+  } else {
+    op();
+  }
+}
 inline void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  std::memcpy(dst, src, bytes);
-  std::atomic_thread_fence(std::memory_order_seq_cst);
-  mbar_complete_tx(bar, bytes);
+  defer_or_run(g_tc->tma_q, bar, [=] {
+    std::memcpy(dst, src, bytes);
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    mbar_complete_tx(bar, bytes);
+  });
 }
 
 // ------------------------------------------------------------------------------------------ tiled TMA (tensor maps)
@@ -193,32 +252,64 @@ inline uint32_t tma_box_bytes(const CUtensorMap* map) {
   return total;
 }
 inline void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
-  const int c[5] = {c0, c1, 0, 0, 0};
-  tma_copy(static_cast<uint8_t*>(dst), m, c, true);
-  mbar_complete_tx(bar, tma_box_bytes(m));
+  const CUtensorMap map = *m;
+  defer_or_run(g_tc->tma_q, bar, [=] {
+    const int c[5] = {c0, c1, 0, 0, 0};
+    tma_copy(static_cast<uint8_t*>(dst), &map, c, true);
+    mbar_complete_tx(bar, tma_box_bytes(&map));
+  });
 }
 inline void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
-  const int c[5] = {c0, c1, c2, 0, 0};
-  tma_copy(static_cast<uint8_t*>(dst), m, c, true);
-  mbar_complete_tx(bar, tma_box_bytes(m));
+  const CUtensorMap map = *m;
+  defer_or_run(g_tc->tma_q, bar, [=] {
+    const int c[5] = {c0, c1, c2, 0, 0};
+    tma_copy(static_cast<uint8_t*>(dst), &map, c, true);
+    mbar_complete_tx(bar, tma_box_bytes(&map));
+  });
 }
 inline void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  const int c[5] = {c0, c1, c2, c3, 0};
-  tma_copy(static_cast<uint8_t*>(dst), m, c, true);
-  mbar_complete_tx(bar, tma_box_bytes(m));
+  const CUtensorMap map = *m;
+  defer_or_run(g_tc->tma_q, bar, [=] {
+    const int c[5] = {c0, c1, c2, c3, 0};
+    tma_copy(static_cast<uint8_t*>(dst), &map, c, true);
+    mbar_complete_tx(bar, tma_box_bytes(&map));
+  });
+}
+// stores belong to bulk async-groups of the issuing thread: [committed groups ..., open group]
+inline thread_local std::vector<std::vector<std::function<void()>>> t_store_groups(1);
+inline void store_issue(std::function<void()> op) {
+  if (g_tc->late) t_store_groups.back().push_back(std::move(op));
+  else op();
 }
 inline void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
-  const int c[5] = {c0, c1, 0, 0, 0};
-  tma_copy(const_cast<uint8_t*>(static_cast<const uint8_t*>(src)), m, c, false);
+  const CUtensorMap map = *m;
+  store_issue([=] {
+    const int c[5] = {c0, c1, 0, 0, 0};
+    tma_copy(const_cast<uint8_t*>(static_cast<const uint8_t*>(src)), &map, c, false);
+  });
 }
 inline void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
-  const int c[5] = {c0, c1, c2, 0, 0};
-  tma_copy(const_cast<uint8_t*>(static_cast<const uint8_t*>(src)), m, c, false);
+  const CUtensorMap map = *m;
+  store_issue([=] {
+    const int c[5] = {c0, c1, c2, 0, 0};
+    tma_copy(const_cast<uint8_t*>(static_cast<const uint8_t*>(src)), &map, c, false);
+  });
 }
-inline void tma_store_commit() {}
+inline void tma_store_commit() { t_store_groups.emplace_back(); }
+inline void store_drain(size_t keep) {  // complete the oldest committed groups until at most `keep` are pending
+  while (t_store_groups.size() - 1 > keep) {
+    for (auto& op : t_store_groups.front()) op();
+    t_store_groups.erase(t_store_groups.begin());
+  }
+}
 template <int N>
-inline void tma_store_wait_read() {}
-inline void tma_store_wait_all() {}
+inline void tma_store_wait_read() { store_drain(N); }
+inline void tma_store_wait_all() { store_drain(0); }
+inline void store_thread_exit() {  // a thread that ends with stores in flight never waited for them
+  bool pending = t_store_groups.size() > 1 || !t_store_groups.back().empty();
+  t_store_groups.assign(1, {});
+  if (pending) cuda_emu::die("thread exited with TMA stores it never waited for (cp.async.bulk.wait_group missing)");
+}
 
 // ------------------------------------------------------------------------------------------ tcgen05 / TMEM
 inline uint32_t& tmem_at(uint32_t taddr, uint32_t lane_off, uint32_t col_off) {
@@ -286,7 +377,7 @@ inline void mma_common(uint32_t tmem_d, const float (*a)[16], uint64_t desc_b, c
     }
 }
 // D[tmem] (+)= A[tmem] * B[smem]: A row m = TMEM lane m, 8 columns of two 16-bit K elements each (K-major)
-inline void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+inline void mma_bf16_ts_now(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   const IDesc id = decode_idesc(idesc);
   if (id.a_mn) cuda_emu::die("emulation: TMEM A operand must be K-major");
   static thread_local float a[128][16];
@@ -296,10 +387,11 @@ inline void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint3
       a[m][2 * c] = id.a_bf16 ? bf16_to_f32(w & 0xffffu) : f16_to_f32(w & 0xffffu);
       a[m][2 * c + 1] = id.a_bf16 ? bf16_to_f32(w >> 16) : f16_to_f32(w >> 16);
     }
-  std::lock_guard<std::mutex> l(g_tc->mu);  // one tensor pipe
+  std::lock_guard<std::recursive_mutex> l(g_tc->mu);  // one tensor pipe
   mma_common(tmem_d, a, desc_b, id, accumulate);
 }
-inline void mma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+inline void mma_bf16_ts_now(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate);
+inline void mma_bf16_ss_now(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   const IDesc id = decode_idesc(idesc);
   static thread_local float a[128][16];
   for (int m = 0; m < id.M; ++m)
@@ -307,10 +399,19 @@ inline void mma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint3
       const uint16_t v = smem_operand(desc_a, id.a_mn, m, k);
       a[m][k] = id.a_bf16 ? bf16_to_f32(v) : f16_to_f32(v);
     }
-  std::lock_guard<std::mutex> l(g_tc->mu);
+  std::lock_guard<std::recursive_mutex> l(g_tc->mu);
   mma_common(tmem_d, a, desc_b, id, accumulate);
 }
-inline void mma_commit(uint64_t* bar) { mbar_arrive(bar); }  // every MMA issued so far has already executed
+inline void mma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  defer_or_run(g_tc->mma_q, nullptr, [=] { mma_bf16_ss_now(tmem_d, desc_a, desc_b, idesc, accumulate); });
+}
+inline void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  defer_or_run(g_tc->mma_q, nullptr, [=] { mma_bf16_ts_now(tmem_d, tmem_a, desc_b, idesc, accumulate); });
+}
+// arrives when every MMA issued before it has executed: immediately, or (late mode) at its place in the pipe
+inline void mma_commit(uint64_t* bar) {
+  defer_or_run(g_tc->mma_q, bar, [=] { mbar_arrive(bar); });
+}
 
 inline void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   const uint32_t lane = threadIdx.x & 31;
@@ -372,6 +473,22 @@ inline void split2h(float x, float y, uint32_t& hi, uint32_t& lo) {
 constexpr bool kGemmF16 = true;
 inline void split2g(float x, float y, uint32_t& hi, uint32_t& lo) { split2h(x, y, hi, lo); }
 constexpr uint32_t idesc_g(int M, int N, bool a, bool b) { return idesc_f16(M, N, a, b); }
+
+// what every emulation driver does before a run: fresh barrier / TMEM state per block, a deadline for hung protocols,
+// late mode on request (or EMU_LATE=1 in the environment)
+inline void emu_prepare(EmuState* state, double timeout_s, int late) {
+  g_tc = state;
+  state->late = late != 0 || (std::getenv("EMU_LATE") != nullptr && std::getenv("EMU_LATE")[0] == '1');
+  cuda_emu::g_deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds((long)(timeout_s * 1e3));
+  cuda_emu::g_block_begin = [state] {
+    state->bars.clear();
+    state->tma_q.clear();
+    state->mma_q.clear();
+    std::fill(state->tmem.begin(), state->tmem.end(), 0x7fc00000u);  // TMEM is not zeroed by the hardware either
+  };
+  cuda_emu::g_block_end = [] { flush_all(); };
+  cuda_emu::g_thread_end = [] { store_thread_exit(); };
+}
 
 }  // namespace tc
 }  // namespace msm

@@ -13,9 +13,12 @@ no-swizzle shared-memory descriptors, bulk copies) and driven through their real
   that dominates the headline step;
 * csrc/experimental/vmf_packed.cu (tcgen05 + bulk copies, not yet run on a GPU): judged with the calibrated emulation.
 
-This checks indexing, tiling, masks, strides, descriptors and barrier protocols of the real source. MMAs execute
-synchronously at issue, so hazards that only hardware asynchrony exposes are not detected, and nothing is said about
-what nvcc / the hardware do with the code - that is the job of the staged GPU runs (tools/gpu_next.sh)."""
+This checks indexing, tiling, masks, strides, descriptors and barrier protocols of the real source. By default
+asynchronous operations (TMA, MMA, commits) execute at issue; in LATE mode (emu_set_late) they execute as late as the
+barrier protocol allows - when a thread is about to block on the barrier they signal, the tensor pipe in issue order,
+TMA stores when their bulk group is waited for - so code that consumes an operand or a result without waiting, or
+recycles a buffer too early, computes garbage. Nothing is said about what nvcc / the hardware do with the code - that
+is the job of the staged GPU runs (tools/gpu_next.sh)."""
 import ctypes
 import os
 import shutil
@@ -562,3 +565,61 @@ def test_calibration_shipped_ffn_kernel(emu_gemm, M, D, Fh, sms):
     ref = F.layer_norm(xd + F.linear(F.relu(F.linear(xd, w1.double(), b1.double())), w2.double(), b2.double()), (D,),
                        g.double(), be.double(), 1e-5)
     assert (y.double() - ref).abs().max().item() < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# late-execution mode: the same kernels with every asynchronous operation delayed as far as their barriers allow
+def test_late_execution_mode_linear_and_chain(emu_lin, emu_chain):
+    for h in (emu_lin, emu_chain):
+        h.emu_set_late.argtypes = [ctypes.c_int]
+        h.emu_deferred_ops.restype = ctypes.c_long
+        h.emu_set_late(1)
+    try:
+        before = emu_lin.emu_deferred_ops()
+        test_calibration_shipped_linear_kernel(emu_lin, 300, 64, 64, True, 2)
+        test_calibration_shipped_linear_kernel_fused_epilogues(emu_lin)
+        assert emu_lin.emu_deferred_ops() > before       # the queues were really in use
+        test_experimental_projection_to_packed_attention_chain(emu_chain, 1, 300, 64, 64, 2, 50, True, 2)
+    finally:
+        for h in (emu_lin, emu_chain):
+            h.emu_set_late(0)
+
+
+def test_late_execution_mode_attention_kernels(emu_tc, emu_gemm):
+    for h in (emu_tc, emu_gemm):
+        h.emu_set_late.argtypes = [ctypes.c_int]
+        h.emu_deferred_ops.restype = ctypes.c_long
+        h.emu_set_late(1)
+    try:
+        before = emu_tc.emu_deferred_ops()
+        test_calibration_shipped_tcgen05_attention_kernel(emu_tc, 1, 2, 100, 700, 32, False, True)
+        test_experimental_packed_mean_shift_kernel(emu_tc, 2, 1000, 100, 64, 10.0, 3)
+        test_experimental_packed_attention_kernel(emu_tc, 1, 1, 100, 1000, 64, True, 3, 30.0, 2e-5)
+        assert emu_tc.emu_deferred_ops() > before
+        test_calibration_shipped_mask_head_kernel(emu_gemm, 1, 100, 64, 30, 44, 2)
+        test_calibration_shipped_ffn_kernel(emu_gemm, 300, 64, 256, 2)
+    finally:
+        for h in (emu_tc, emu_gemm):
+            h.emu_set_late(0)
+
+
+def test_late_mode_detects_a_missing_barrier_wait():
+    """Self-test: a consumer that does not wait for its bulk copy is indistinguishable from a correct one when
+    asynchronous operations execute at issue, and reads stale shared memory in late mode."""
+    lib = os.path.join(ROOT, "build", "emu", "libemu_hazard.so")
+    src = os.path.join(EMU_DIR, "emu_hazard.cpp")
+    deps = [src, os.path.join(EMU_DIR, "cuda_emu.h"), os.path.join(EMU_DIR, "tc_emu.h")]
+    if shutil.which("g++") is None or not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("needs g++ and the CUDA headers")
+    if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
+        os.makedirs(os.path.dirname(lib), exist_ok=True)
+        subprocess.check_call(["g++", "-std=c++20", "-O1", "-w", "-shared", "-fPIC", "-pthread", "-DMSM_EMULATE_ON_HOST",
+                               "-I" + CUDA_INC, "-I" + EMU_DIR, "-x", "c++", src, "-o", lib])
+    h = ctypes.CDLL(lib)
+    h.emu_hazard_copy.restype = ctypes.c_float
+    h.emu_hazard_copy.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    data = torch.arange(256, dtype=torch.float32)
+    want = float(data.sum())
+    assert h.emu_hazard_copy(data.data_ptr(), 1, 0) == want     # correct kernel, synchronous
+    assert h.emu_hazard_copy(data.data_ptr(), 1, 1) == want     # correct kernel, late
+    assert h.emu_hazard_copy(data.data_ptr(), 0, 1) == -256.0   # missing wait: late mode exposes the stale tile
