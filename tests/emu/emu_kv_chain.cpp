@@ -1,5 +1,5 @@
 // Emulation driver for the fused chain of DESIGN.md section 8 item 1: the K / V projections (csrc/linear_tc.cu,
-// operand-image epilogue) feeding the packed attention kernel (csrc/experimental/vmf_packed.cu), compiled as plain C++.
+// operand-image epilogue) feeding the packed attention kernel (csrc/vmf_attention_packed.cu), compiled as plain C++.
 // Built and loaded by tests/test_kernel_emulation.py; never part of the product library.
 #include "cuda_emu.h"
 #include "tc_emu.h"
@@ -29,7 +29,7 @@ __attribute__((aligned(1024))) uint8_t smem[232448];
 }  // namespace msm
 
 #include "../../unseenobjectswithmeanshift_b200/csrc/linear_tc.cu"
-#include "../../unseenobjectswithmeanshift_b200/csrc/experimental/vmf_packed.cu"
+#include "../../unseenobjectswithmeanshift_b200/csrc/vmf_attention_packed.cu"
 
 static msm::tc::EmuState g_state;
 

@@ -1,5 +1,5 @@
 // Emulation driver for the tensor-core attention kernels: csrc/vmf_attention_tc.cu (SHIPPED, green on the B200 - the
-// calibration of tc_emu.h) and csrc/experimental/vmf_packed.cu (not yet run on a GPU), compiled as plain C++.
+// calibration of tc_emu.h) and csrc/vmf_attention_packed.cu (not yet run on a GPU), compiled as plain C++.
 // Built and loaded by tests/test_kernel_emulation.py; never part of the product library.
 #include "cuda_emu.h"
 #include "tc_emu.h"
@@ -28,7 +28,7 @@ __attribute__((aligned(1024))) uint8_t smem[232448];
 }  // namespace msm
 
 #include "../../unseenobjectswithmeanshift_b200/csrc/vmf_attention_tc.cu"
-#include "../../unseenobjectswithmeanshift_b200/csrc/experimental/vmf_packed.cu"
+#include "../../unseenobjectswithmeanshift_b200/csrc/vmf_attention_packed.cu"
 
 static msm::tc::EmuState g_state;
 

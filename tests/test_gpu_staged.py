@@ -178,3 +178,27 @@ def test_head_training_steps_r50style(golden):
     assert not missing, missing
     assert any(not torch.equal(before[n], p) for n, p in model.named_parameters())
     assert min(history[4:]) < history[0], history
+
+
+@pytest.mark.parametrize("decoder,levels", [("MeanShiftTransformerDecoder", 3), ("PretrainedMeanShiftTransformerDecoder", 1)])
+def test_decoder_packed_kv_path_matches_default(monkeypatch, decoder, levels):
+    """MSM_PACKED_KV=1 (K / V projections write operand images, packed attention kernel) against the default path of
+    the same decoder: heads of 32 channels (the packed path's requirement), masks on, key counts with tails."""
+    from unseenobjectswithmeanshift_b200.meanshiftformer import modeling as M
+    torch.manual_seed(3)
+    kw = dict(num_classes=2, hidden_dim=64, num_queries=20, nheads=2, dim_feedforward=128, dec_layers=4,
+              pre_norm=False, mask_dim=64, enforce_input_project=False, use_meanshift_cross_attention=True,
+              disable_attention_mask=False, use_meanshift_self_attention=True, decoder_block_norm=True)
+    m = getattr(M, decoder)(32, True, **kw).cuda().eval()
+    sizes = [(5, 7), (10, 14), (20, 28)][:levels] if levels == 3 else [(20, 28)]
+    x = [torch.randn(2, 32, h, w, device="cuda") for h, w in sizes]
+    mf = torch.randn(2, 64, 40, 56, device="cuda")
+    with torch.no_grad():
+        monkeypatch.setenv("MSM_PACKED_KV", "0")
+        want = m(x, mf)
+        monkeypatch.setenv("MSM_PACKED_KV", "1")
+        got = m(x, mf)
+        again = m(x, mf)     # the cached image buffer is reused: key tails must still be zero
+    for a, b in ((got, want), (again, want)):
+        _close(a["pred_masks"], b["pred_masks"], 1e-3)
+        _close(a["pred_logits"], b["pred_logits"], 1e-3)

@@ -11,7 +11,7 @@ no-swizzle shared-memory descriptors, bulk copies) and driven through their real
 * csrc/linear_tc.cu (SHIPPED dense / convolution kernel: tiled TMA with 128B swizzle, operand conversion into TMEM,
   fused epilogues, TMA stores): calibration of the tensor-map emulation, and a CPU development loop for the kernel
   that dominates the headline step;
-* csrc/experimental/vmf_packed.cu (tcgen05 + bulk copies, not yet run on a GPU): judged with the calibrated emulation.
+* csrc/vmf_attention_packed.cu (tcgen05 + bulk copies, not yet run on a GPU): judged with the calibrated emulation.
 
 This checks indexing, tiling, masks, strides, descriptors and barrier protocols of the real source. By default
 asynchronous operations (TMA, MMA, commits) execute at issue; in LATE mode (emu_set_late) they execute as late as the
@@ -191,7 +191,7 @@ def test_emulated_entry_point_rejects_bad_arguments(emu):
 @pytest.fixture(scope="module")
 def emu_tc():
     h = _build(os.path.join(ROOT, "build", "emu", "libemu_vmf_tc.so"), "emu_vmf_tc.cpp",
-               ["vmf_attention_tc.cu", os.path.join("experimental", "vmf_packed.cu")])
+               ["vmf_attention_tc.cu", "vmf_attention_packed.cu"])
     P, I, L, Fl, Z, D = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t, ctypes.c_double
     h.emu_last_error.restype = ctypes.c_char_p
     h.emu_set_timeout.argtypes = [D]
@@ -268,7 +268,7 @@ def test_calibration_shipped_tcgen05_attention_kernel(emu_tc, B, H, Q, S, hd, sh
     (1, 2000, 128, 32, 10.0, 2),    # all 128 TMEM lanes in use
 ])
 def test_experimental_packed_mean_shift_kernel(emu_tc, B, n, m, d, kappa, iters):
-    """csrc/experimental/vmf_packed.cu (operands packed once, streamed by bulk copies, 16 softmax warps) through the
+    """csrc/vmf_attention_packed.cu (operands packed once, streamed by bulk copies, 16 softmax warps) through the
     calibrated emulation, against an fp64 restatement of seed_hill_climbing_ball (mean_shift.py:79-109)."""
     h = emu_tc
     torch.manual_seed(n + d)
@@ -298,7 +298,7 @@ def test_experimental_packed_mean_shift_kernel(emu_tc, B, n, m, d, kappa, iters)
     (1, 2, 50, 260, 32, True, 1, 5.0, 1e-4),      # k not normalised: bf16 score operands
 ])
 def test_experimental_packed_attention_kernel(emu_tc, B, H, Q, S, hd, masked, flags, kappa, tol):
-    """The general form of csrc/experimental/vmf_packed.cu: K (normalised, fp16 halves) and V (bf16 halves) packed per
+    """The general form of csrc/vmf_attention_packed.cu: K (normalised, fp16 halves) and V (bf16 halves) packed per
     (batch, head, tile) by vmf_pack_kernel, attention with the decoder's bit masks - what the cross-attention would
     run once the K/V projection writes the images itself."""
     h = emu_tc
@@ -436,7 +436,7 @@ def test_calibration_shipped_linear_kernel_convolutions(emu_lin):
 def emu_chain():
     from unseenobjectswithmeanshift_b200._lib import SIGNATURES
     h = _build(os.path.join(ROOT, "build", "emu", "libemu_kv_chain.so"), "emu_kv_chain.cpp",
-               ["linear_tc.cu", os.path.join("experimental", "vmf_packed.cu")])
+               ["linear_tc.cu", "vmf_attention_packed.cu"])
     P, I, L, Fl, Z, D = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t, ctypes.c_double
     for n in ("msm_linear_weight_bytes", "msm_linear_prepare_weight"):
         f = getattr(h, n)

@@ -1,15 +1,16 @@
-"""GPU dev check of the EXPERIMENTAL packed-operand attention / mean-shift kernels (csrc/experimental/vmf_packed.cu).
+"""GPU dev check of the EXPERIMENTAL packed-operand attention / mean-shift kernels (csrc/vmf_attention_packed.cu) and of
+the operand-image projection epilogue (linear_tc_kernel<PACK>).
 
-    python tools/dev_vmf_packed.py build      # cross-compile build/experimental/libmsmx_vmf_packed.so (no GPU needed)
-    python tools/dev_vmf_packed.py [quick]    # on the B200 box: build if stale, parity + timing vs the shipped kernel
+    python tools/dev_vmf_packed.py [quick]    # on the B200 box: build if stale, parity + timing vs the shipped kernels
 
-The experimental library is separate from libmsmformer_b200.so (the product build globs csrc/*.cu only) and is bound
-here and nowhere else. The check runs in a child process under a timeout: a hung mbarrier protocol must not take the
+The kernels live in libmsmformer_b200.so behind msmx_ entry points that nothing calls by default (MSM_PACKED_KV=1 routes
+the decoder through them). The check runs in a child process under a timeout: a hung mbarrier protocol must not take the
 box with it. Parity: (1) mean-shift seeds after 10 iterations against the shipped msm_mean_shift_hill_climb and, at
 small n, an fp64 restatement of seed_hill_climbing_ball (transformer_decoder/mean_shift.py:79-109); (2) the decoder's
 cross-attention (heads by strides, bit masks, K normalised + fp16 halves, V bf16 halves) against the shipped
-msm_vmf_attention_fwd, with the pack kernel timed separately (in production the K/V projection writes the images).
-The same source already runs green on CPU threads under the calibrated emulation (tests/test_kernel_emulation.py).
+msm_vmf_attention_fwd, with the stand-alone pack kernel timed separately; (3) the fused chain - K / V projections
+writing the images, packed attention - against dense projections + the shipped attention.
+The same sources already run green on CPU threads under the calibrated emulation (tests/test_kernel_emulation.py).
 """
 import ctypes
 import os
@@ -18,40 +19,17 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-CSRC = os.path.join(ROOT, "unseenobjectswithmeanshift_b200", "csrc")
-XLIB = os.path.join(ROOT, "build", "experimental", "libmsmx_vmf_packed.so")
-NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 
 def build():
-    srcs = [os.path.join(CSRC, "experimental", "vmf_packed.cu"), os.path.join(CSRC, "common.cu")]
-    deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc.cuh")]
-    if os.path.exists(XLIB) and all(os.path.getmtime(d) <= os.path.getmtime(XLIB) for d in deps):
-        return XLIB
-    os.makedirs(os.path.dirname(XLIB), exist_ok=True)
-    subprocess.check_call([NVCC, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-                           "-Xcompiler", "-fPIC", "-shared", "-o", XLIB] + srcs)
-    return XLIB
+    import __graft_entry__
+    __graft_entry__.build()
 
 
 def bind():
-    P, I, F, Z, L = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_int64
-    h = ctypes.CDLL(build())
-    h.msmx_vmf_packed_bytes.restype, h.msmx_vmf_packed_bytes.argtypes = Z, [I, I, I, I, I]
-    h.msmx_vmf_packed_workspace_bytes.restype, h.msmx_vmf_packed_workspace_bytes.argtypes = Z, [I, I, I, I, I]
-    h.msmx_vmf_pack.restype, h.msmx_vmf_pack.argtypes = I, [P, L, L, L, P, L, L, L, P, I, I, I, I, I, P]
-    h.msmx_vmf_attention_packed_fwd.restype = I
-    h.msmx_vmf_attention_packed_fwd.argtypes = [P, L, L, L, P, P, L, L, L, P, I, P, I, I, I, I, I, F, I, P, Z, P]
-    h.msm_last_error.restype = ctypes.c_char_p
-    h.msmx_mean_shift_packed_bytes.restype = Z
-    h.msmx_mean_shift_packed_bytes.argtypes = [I, I, I]
-    h.msmx_mean_shift_packed_workspace_bytes.restype = Z
-    h.msmx_mean_shift_packed_workspace_bytes.argtypes = [I, I, I, I]
-    h.msmx_mean_shift_pack.restype = I
-    h.msmx_mean_shift_pack.argtypes = [P, P, I, I, I, P]
-    h.msmx_mean_shift_hill_climb_packed.restype = I
-    h.msmx_mean_shift_hill_climb_packed.argtypes = [P, P, P, I, I, I, I, F, I, P, Z, P]
-    return h
+    from unseenobjectswithmeanshift_b200 import _lib
+    build()
+    return _lib.xlib()
 
 
 def ref64(X, Z, kappa, iters):
@@ -182,11 +160,7 @@ def child(quick):
 
     # ---- the fused chain: K / V projections writing the images (linear_tc_kernel<PACK> in the product library) +
     # packed attention, against dense K, dense V + the shipped attention kernel
-    from unseenobjectswithmeanshift_b200 import _lib
-    L = _lib.lib()
-    P_, I_, L_ = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
-    L.msmx_linear_packed_kv_fwd.restype = I_
-    L.msmx_linear_packed_kv_fwd.argtypes = [P_, L_, P_, P_, P_, I_, I_, I_, I_, I_, I_, I_, I_, P_]
+    L = h
     ccases = [(2, 300, 256, 256, 3, 100), (1, 4800, 256, 256, 3, 100), (1, 50176, 256, 256, 1, 100),
               (1, 307200, 256, 256, 1, 100)]
     for (B, S, Cin, C, layers, Q) in ccases:

@@ -11,7 +11,8 @@ timeout 600 python -m pytest tests -q -m gpu_staged -x 2>&1 | tee gpurun_out/nex
 # 3. the same backward kernel under compute-sanitizer (memcheck), smallest cases only
 timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_staged.py -q -x \
     -k "golden and vmf" > gpurun_out/next_sanitizer.log 2>&1; tail -5 gpurun_out/next_sanitizer.log
-# 4. experimental packed-operand mean-shift kernel: parity + timing against the shipped one
+# 4. experimental packed-operand attention / mean-shift kernels and the operand-image projection epilogue: parity + timing
+#    against the shipped kernels (the staged test of step 2 already ran the decoder with MSM_PACKED_KV=1)
 timeout 660 python tools/dev_vmf_packed.py quick 2>&1 | tee gpurun_out/next_vmf_packed.log | tail -12
 # 5. training workload (config #5), one GPU
 timeout 600 python bench.py --workload train --steps 5 --warmup 3 > gpurun_out/next_bench_train.json \
@@ -21,3 +22,7 @@ tail -3 gpurun_out/next_bench_train.err
 timeout 600 python bench.py --workload twostage --steps 3 --warmup 3 > gpurun_out/next_bench_twostage.json \
     2> gpurun_out/next_bench_twostage.err; echo "twostage bench rc=$?"; cut -c1-600 gpurun_out/next_bench_twostage.json
 tail -3 gpurun_out/next_bench_twostage.err
+# 7. UCN head step with the packed K / V path against the default (config #1 / #3 stage 1)
+timeout 400 python bench.py --workload ucn --batch 2 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/next_bench_ucn_default.json 2>/dev/null
+MSM_PACKED_KV=1 timeout 400 python bench.py --workload ucn --batch 2 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/next_bench_ucn_packed.json 2>/dev/null
+cut -c1-300 gpurun_out/next_bench_ucn_default.json gpurun_out/next_bench_ucn_packed.json

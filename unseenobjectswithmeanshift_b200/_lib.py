@@ -60,6 +60,36 @@ SIGNATURES = {
 }
 
 
+# EXPERIMENTAL entry points (prefix msmx_): exported by the library but not part of include/msmformer_b200.h; bound on
+# first use by ops.py and only reachable with MSM_PACKED_KV=1
+X_SIGNATURES = {
+    "msmx_vmf_packed_bytes": (_Z, [_I, _I, _I, _I, _I]),
+    "msmx_vmf_packed_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
+    "msmx_vmf_pack": (_I, [_P, _L, _L, _L, _P, _L, _L, _L, _P, _I, _I, _I, _I, _I, _P]),
+    "msmx_vmf_attention_packed_fwd": (_I, [_P, _L, _L, _L, _P, _P, _L, _L, _L, _P, _I, _P, _I, _I, _I, _I, _I, _F, _I,
+                                           _P, _Z, _P]),
+    "msmx_linear_packed_kv_fwd": (_I, [_P, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "msmx_mean_shift_packed_bytes": (_Z, [_I, _I, _I]),
+    "msmx_mean_shift_packed_workspace_bytes": (_Z, [_I, _I, _I, _I]),
+    "msmx_mean_shift_pack": (_I, [_P, _P, _I, _I, _I, _P]),
+    "msmx_mean_shift_hill_climb_packed": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _I, _P, _Z, _P]),
+}
+_xbound = False
+
+
+def xlib():
+    """lib() with the experimental entry points bound as well."""
+    global _xbound
+    handle = lib()
+    if not _xbound:
+        for name, (res, args) in X_SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _xbound = True
+    return handle
+
+
 def lib():
     global _lib
     if _lib is None:

@@ -1,7 +1,8 @@
-// EXPERIMENTAL - not part of libmsmformer_b200.so (the build globs csrc/*.cu only). Compiles for sm_100a, NOT yet run
-// on a GPU; its logic is checked by executing this source on CPU threads against the emulation that is calibrated on
-// the shipped kernels (tests/emu, tests/test_kernel_emulation.py). Build + check on the B200 box with
-// tools/dev_vmf_packed.py.
+// EXPERIMENTAL - compiled into libmsmformer_b200.so, but its entry points carry the prefix msmx_, are NOT part of
+// include/msmformer_b200.h and nothing calls them unless MSM_PACKED_KV=1 is set (ops.py / the decoder mirror). It
+// compiles for sm_100a and has NOT yet run on a GPU; its logic is checked by executing this source on CPU threads under
+// the emulation that is calibrated on the shipped kernels (tests/emu, tests/test_kernel_emulation.py). Parity + timing
+// against the shipped kernels on the B200 box: tools/dev_vmf_packed.py.
 //
 // vMF attention / mean-shift iteration on PRE-PACKED operands. In vmf_attention_tc.cu
 // eight loader warps read the fp32 rows of K and V, L2-normalise K, split both into 16-bit hi/lo halves and store the
@@ -24,8 +25,8 @@
 //
 // Bound per tile and SM at HD = 64, shared: 36 MMAs ~ 1.1 us of tensor pipe vs 32 KB of HBM (66 % of peak at 100 %
 // tensor pipe): tensor-bound; the shipped kernel reaches 44 % of the pipe.
-#include "../common.cuh"
-#include "../tc.cuh"
+#include "common.cuh"
+#include "tc.cuh"
 
 #define MSMX_VMF_SHARED_KV 8  /* flag: k == v, not normalised - one operand image per tile (mean-shift) */
 

@@ -358,9 +358,30 @@ class _MeanShiftDecoderBase(nn.Module):
         layers_of = [[i for i in range(self.num_layers) if i % L == l] for l in range(L)]
         kv = {}
 
+        # EXPERIMENTAL, opt-in (MSM_PACKED_KV=1; not yet run on a GPU): K / V projections write the attention kernel's
+        # operand images instead of fp32 rows
+        packed_kv = ops.packed_kv_enabled() and not train and hd == 32
+
         def project_kv(level, layer_ids):
             attn = [self.transformer_cross_attention_layers[i].meanshift_attn for i in layer_ids]
             tag = "kv%d_%s" % (level, "_".join(map(str, layer_ids)))
+            if packed_kv:
+                S_l = sizes[level][0] * sizes[level][1]
+                cat = lambda name, ts: ops.cached_cat(self, name, ts)  # noqa: E731
+                wk = cat(tag + "wk", [a.in_proj_weight[C:2 * C] for a in attn])
+                bk = cat(tag + "bk", [a.in_proj_bias[C:2 * C] for a in attn])
+                wv = cat(tag + "wv", [a.in_proj_weight[2 * C:] for a in attn])
+                bv = cat(tag + "bv", [a.in_proj_bias[2 * C:] for a in attn])
+                if key_in[level] is None:
+                    key_in[level] = src[level] + self.pe_layer.table(sizes[level][0], sizes[level][1], dev)
+                # one zero-initialised buffer per (level, shape), reused by every forward (static under graph replay)
+                images, per_layer = ops.cached_value(
+                    self, tag + "img_%d_%d" % (B, S_l), [wk], lambda: ops.packed_kv_alloc(len(layer_ids), B, H, S_l, dev))
+                ops.linear_packed_kv(key_in[level].contiguous(), wk, bk, images, B, S_l, C, 0)
+                ops.linear_packed_kv(src[level].contiguous(), wv, bv, images, B, S_l, C, 1)
+                for j, i in enumerate(layer_ids):
+                    kv[i] = (ops.PackedKV(images[j * per_layer:(j + 1) * per_layer], B, H, S_l), None)
+                return
             # the cache holds detached copies: under autograd the concatenation has to stay part of the graph
             cat = (lambda name, ts: torch.cat(ts, 0)) if train else (lambda name, ts: ops.cached_cat(self, name, ts))
             wk = cat(tag + "wk", [a.in_proj_weight[C:2 * C] for a in attn])
@@ -392,6 +413,10 @@ class _MeanShiftDecoderBase(nn.Module):
             return t.unflatten(-1, (H, hd)).permute(0, 2, 1, 3)
 
         def attention(q_, k_, v_, bits_=None, row_open_=None):  # [B,len,C] projections -> [B,Q,C]
+            if isinstance(k_, ops.PackedKV):
+                o_ = torch.empty(B, self.num_queries, C, device=dev, dtype=torch.float32)
+                ops.vmf_attention_packed(heads_view(q_), k_, blocked_bits=bits_, row_open=row_open_, out=heads_view(o_))
+                return o_
             if train:
                 o4 = ops.vmf_attention_autograd(heads_view(q_), heads_view(k_), heads_view(v_), blocked_bits=bits_,
                                                 row_open=row_open_)
@@ -439,9 +464,12 @@ class _MeanShiftDecoderBase(nn.Module):
                 tq = ops.cached_value(self, f"tq{i}", [qpos, a.in_proj_weight],
                                       lambda: F.linear(qpos, a.in_proj_weight[:C]).contiguous())
                 q = ops.linear_fused(out, a.in_proj_weight[:C], a.in_proj_bias[:C], rowbias=tq)
-                o = torch.empty(B, self.num_queries, C, device=dev, dtype=torch.float32)
-                ops.vmf_attention(heads_view(q), heads_view(K), heads_view(V), blocked_bits=bits, row_open=row_open,
-                                  out=heads_view(o))
+                if isinstance(K, ops.PackedKV):
+                    o = attention(q, K, V, bits, row_open)
+                else:
+                    o = torch.empty(B, self.num_queries, C, device=dev, dtype=torch.float32)
+                    ops.vmf_attention(heads_view(q), heads_view(K), heads_view(V), blocked_bits=bits, row_open=row_open,
+                                      out=heads_view(o))
                 if level >= 2:
                     out = ops.linear_fused(o, a.out_proj.weight, a.out_proj.bias, residual=out, norm=ca.norm)
                 else:

@@ -182,6 +182,74 @@ def vmf_attention_autograd(q, k, v, *, blocked_bits=None, row_open=None, add_mas
     return VmfAttentionFunction.apply(q, k, v, blocked_bits, row_open, add_mask, kappa, normalize_q, normalize_k)
 
 
+# ----------------------------------------------------------------------------------------------
+# EXPERIMENTAL packed-operand cross-attention (csrc/vmf_attention_packed.cu, linear_tc_kernel<PACK>): K / V
+# projections write 16-bit operand images instead of fp32 rows, the attention kernel streams them with bulk copies.
+# Opt-in (MSM_PACKED_KV=1); not yet run on a GPU - see DESIGN.md section 8, item 1.
+# ----------------------------------------------------------------------------------------------
+def packed_kv_enabled():
+    return os.environ.get("MSM_PACKED_KV", "0") == "1"
+
+
+class PackedKV:
+    """Operand images of the K and V projections of ONE decoder layer: uint8 [B][H][ceil(S/128)][4][8192] view."""
+
+    def __init__(self, images, batch, heads, num_keys):
+        self.images, self.batch, self.heads, self.num_keys = images, batch, heads, num_keys
+
+
+def packed_kv_alloc(layers, batch, heads, num_keys, device):
+    """Zero-initialised image buffer for `layers` decoder layers (key tails must stay zero) -> (buffer, bytes/layer)."""
+    per_layer = _lib.xlib().msmx_vmf_packed_bytes(batch, heads, num_keys, 32, 3)
+    return torch.zeros(layers * per_layer, dtype=torch.uint8, device=device), per_layer
+
+
+def linear_packed_kv(x, weight, bias, images, batch, num_keys, channels, which):
+    """K (which=0: rows L2-normalised per 32-channel head, fp16 halves) or V (which=1: bf16 halves) projection of
+    x [B, S, Cin] with weight [layers*C, Cin], written as operand images into `images` (packed_kv_alloc)."""
+    x = _require(x, "x")
+    if x.dim() != 3 or not x.is_contiguous() or x.shape[0] != batch or x.shape[1] != num_keys:
+        raise ValueError("x must be a contiguous [B, S, Cin] tensor")
+    w = _require(weight, "weight")
+    N, K = w.shape
+    if K != x.shape[2] or N % channels or channels % 32 or K % 32:
+        raise ValueError(f"weight {tuple(w.shape)} does not fit x {tuple(x.shape)} / {channels} channels per layer")
+    b = None if bias is None else _require(bias, "bias").contiguous()
+    rc = _lib.xlib().msmx_linear_packed_kv_fwd(x.data_ptr(), K, prepare_linear_weight(w).data_ptr(),
+                                               b.data_ptr() if b is not None else None, images.data_ptr(), batch,
+                                               num_keys, N, K, channels, int(which), 1, 1, _stream())
+    check(rc, "msmx_linear_packed_kv_fwd")
+
+
+def vmf_attention_packed(q, kv, *, blocked_bits=None, row_open=None, kappa=KAPPA, out=None):
+    """vmf_attention with K / V given as operand images (PackedKV): q [B, H, Nq, 32] view, q and k normalised."""
+    q, q_sb, q_sh, q_sl = _bhld(q, "q")
+    B, H, Nq, hd = q.shape
+    if hd != 32 or B != kv.batch or H != kv.heads:
+        raise ValueError(f"q {tuple(q.shape)} does not match the packed K / V ({kv.batch} x {kv.heads} heads of 32)")
+    if out is None:
+        out = torch.empty(B, Nq, H, hd, device=q.device, dtype=torch.float32).permute(0, 2, 1, 3)
+    out, o_sb, o_sh, o_sl = _bhld(out, "out")
+    wpr = 0
+    if blocked_bits is not None:
+        _require(blocked_bits, "blocked_bits", torch.int32)
+        if not blocked_bits.is_contiguous() or blocked_bits.shape[:2] != (B, Nq):
+            raise ValueError("blocked_bits must be contiguous [B, Nq, words]")
+        wpr = blocked_bits.shape[2]
+        if row_open is not None:
+            _require(row_open, "row_open", torch.int32)
+    L = _lib.xlib()
+    ws_bytes = L.msmx_vmf_packed_workspace_bytes(B, H, Nq, kv.num_keys, hd)
+    ws = torch.empty(ws_bytes, device=q.device, dtype=torch.uint8)
+    rc = L.msmx_vmf_attention_packed_fwd(
+        q.data_ptr(), q_sb, q_sh, q_sl, kv.images.data_ptr(), out.data_ptr(), o_sb, o_sh, o_sl,
+        blocked_bits.data_ptr() if blocked_bits is not None else None, wpr,
+        row_open.data_ptr() if row_open is not None else None, B, H, Nq, kv.num_keys, hd, float(kappa), 3,
+        ws.data_ptr(), ws_bytes, _stream())
+    check(rc, "msmx_vmf_attention_packed_fwd")
+    return out
+
+
 def vmf_attention_weights(q, k, den, *, blocked_bits=None, row_open=None, add_mask=None, kappa=KAPPA,
                           normalize_q=True, normalize_k=True):
     """Attention weights [B*H, Nq, Ns] (the second value hypersphere_attention returns)."""
@@ -1065,6 +1133,8 @@ def _work_vmf_bwd(q, k, v, out, grad_out, den, **kw):
 
 
 vmf_attention_bwd = _instrument("vmf_attention_bwd", 2, _work_vmf_bwd)(vmf_attention_bwd)
+linear_packed_kv = _instrument("linear", 1)(linear_packed_kv)
+vmf_attention_packed = _instrument("vmf_attention", 2)(vmf_attention_packed)
 mask_logits = _instrument("mask_logits", 1, _work_mask)(mask_logits)
 mask_to_attn_bits = _instrument("mask_to_attn_bits", 1, _work_bits)(mask_to_attn_bits)  # one kernel, no memset
 linear = _instrument("linear", 1, _work_linear)(linear)
