@@ -202,3 +202,16 @@ def test_decoder_packed_kv_path_matches_default(monkeypatch, decoder, levels):
     for a, b in ((got, want), (again, want)):
         _close(a["pred_masks"], b["pred_masks"], 1e-3)
         _close(a["pred_logits"], b["pred_logits"], 1e-3)
+
+
+def test_mean_shift_packed_path_matches_default(msm, monkeypatch):
+    """MSM_PACKED_MS=1 (X packed once per call, bulk-copy streaming kernel) against the shipped hill climb."""
+    torch.manual_seed(0)
+    for B, n, m, d in ((2, 5000, 100, 64), (1, 777, 37, 32), (2, 40000, 128, 64)):
+        X = torch.nn.functional.normalize(torch.randn(B, n, d, device="cuda"), dim=-1)
+        Z = X[:, torch.randperm(n, device="cuda")[:m]].contiguous()
+        monkeypatch.setenv("MSM_PACKED_MS", "0")
+        want = msm.mean_shift_hill_climb(X, Z, 10.0, 10)
+        monkeypatch.setenv("MSM_PACKED_MS", "1")
+        got = msm.mean_shift_hill_climb(X, Z, 10.0, 10)
+        assert (got - want).abs().max().item() < 1e-4

@@ -26,3 +26,7 @@ tail -3 gpurun_out/next_bench_twostage.err
 timeout 400 python bench.py --workload ucn --batch 2 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/next_bench_ucn_default.json 2>/dev/null
 MSM_PACKED_KV=1 timeout 400 python bench.py --workload ucn --batch 2 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/next_bench_ucn_packed.json 2>/dev/null
 cut -c1-300 gpurun_out/next_bench_ucn_default.json gpurun_out/next_bench_ucn_packed.json
+# 8. mean-shift workload (config #4) with the packed path against the default
+timeout 300 python bench.py --workload meanshift --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/next_bench_ms_default.json 2>/dev/null
+MSM_PACKED_MS=1 timeout 300 python bench.py --workload meanshift --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/next_bench_ms_packed.json 2>/dev/null
+cut -c1-300 gpurun_out/next_bench_ms_default.json gpurun_out/next_bench_ms_packed.json

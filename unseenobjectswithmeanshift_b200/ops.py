@@ -749,6 +749,18 @@ def mean_shift_hill_climb(X, Z, kappa, max_iters=10):
     if Zb.shape[0] != B or Zb.shape[2] != d:
         raise ValueError(f"X {tuple(X.shape)} / Z {tuple(Z.shape)} mismatch")
     out = torch.empty_like(Zb)
+    if os.environ.get("MSM_PACKED_MS", "0") == "1" and d in (32, 64) and m <= 128 and int(max_iters) >= 1:
+        # EXPERIMENTAL, opt-in (not yet run on a GPU): X is split into 16-bit operand images ONCE per call instead of in
+        # every iteration (csrc/vmf_attention_packed.cu)
+        X_ = _lib.xlib()
+        packed = torch.empty(X_.msmx_mean_shift_packed_bytes(B, n, d), device=Xb.device, dtype=torch.uint8)
+        check(X_.msmx_mean_shift_pack(Xb.data_ptr(), packed.data_ptr(), B, n, d, _stream()), "msmx_mean_shift_pack")
+        ws_bytes = X_.msmx_mean_shift_packed_workspace_bytes(B, n, m, d)
+        ws = torch.empty(ws_bytes, device=Xb.device, dtype=torch.uint8)
+        rc = X_.msmx_mean_shift_hill_climb_packed(packed.data_ptr(), Zb.data_ptr(), out.data_ptr(), B, n, m, d,
+                                                  float(kappa), int(max_iters), ws.data_ptr(), ws_bytes, _stream())
+        check(rc, "msmx_mean_shift_hill_climb_packed")
+        return out[0] if squeeze else out
     L = _lib.lib()
     ws_bytes = L.msm_mean_shift_workspace_bytes(B, n, m, d)
     ws = torch.empty(ws_bytes, device=Xb.device, dtype=torch.uint8)
