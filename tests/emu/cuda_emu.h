@@ -141,4 +141,15 @@ inline void launch(dim3 grid, int threads, const std::function<void()>& body) {
       g_block = nullptr;
     }
 }
+// launch with a guard zone: the bytes of the block's shared-memory buffer beyond what the launch asked for are filled
+// with a pattern before the run and must be intact afterwards (an out-of-bounds shared-memory store in the kernel)
+inline void launch_guarded(dim3 grid, int threads, void* smem, size_t used, size_t total,
+                           const std::function<void()>& body) {
+  uint8_t* p = static_cast<uint8_t*>(smem);
+  const size_t guard = total > used ? std::min<size_t>(total - used, 16384) : 0;
+  std::memset(p + used, 0xA5, guard);
+  launch(grid, threads, body);
+  for (size_t i = 0; i < guard; ++i)
+    if (p[used + i] != 0xA5) die("shared-memory store beyond the dynamic shared memory the launch asked for");
+}
 }  // namespace cuda_emu

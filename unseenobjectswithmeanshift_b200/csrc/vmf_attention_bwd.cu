@@ -368,7 +368,8 @@ static int launch(const Params& P, int G, cudaStream_t st) {
 #ifdef MSM_EMULATE_ON_HOST  // tests/emu: the kernel text executed on CPU threads (no GPU in the authoring container)
   (void)st;
   if (smem > sizeof(float) * cuda_emu_smem_floats) return MSM_E_UNSUPPORTED;
-  cuda_emu::launch(dim3(P.nsplit, G), kThreads, [&] { vmf_bwd_kernel<HD>(P); });
+  cuda_emu::launch_guarded(dim3(P.nsplit, G), kThreads, vbw::smem, smem, sizeof(float) * cuda_emu_smem_floats,
+                           [&] { vmf_bwd_kernel<HD>(P); });
   return 0;
 #else
   MSM_CUDA(cudaFuncSetAttribute(vmf_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

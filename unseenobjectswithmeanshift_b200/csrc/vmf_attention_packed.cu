@@ -472,7 +472,8 @@ static int launch_attn(const Params& P, int G, cudaStream_t st) {
   (void)st;
   if (smem > sizeof(vpk::smem)) return MSM_E_UNSUPPORTED;
   tc::g_tc->smem_base = reinterpret_cast<uintptr_t>(vpk::smem);
-  cuda_emu::launch(dim3(G * P.nsplit, 1), kThreads, [&] { vmf_attn_packed_kernel<HD, SHARED, QK16, MASKED>(P); });
+  cuda_emu::launch_guarded(dim3(G * P.nsplit, 1), kThreads, vpk::smem, smem, sizeof(vpk::smem),
+                           [&] { vmf_attn_packed_kernel<HD, SHARED, QK16, MASKED>(P); });
   return 0;
 #else
   MSM_CUDA(cudaFuncSetAttribute(vmf_attn_packed_kernel<HD, SHARED, QK16, MASKED>,
