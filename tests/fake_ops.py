@@ -179,3 +179,19 @@ def mask_to_attn_bits(masks, target_size):
 def dense(x, weight, bias=None, relu=False):
     y = F.linear(x, weight, bias)
     return torch.relu(y) if relu else y
+
+
+def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step=128):
+    """msm_ms_deform_attn_fwd contract through the oracle's pure-torch core: [N, Lq, M*D]."""
+    from oracle import pixel_decoder as opd
+    return opd.ms_deform_attn_core(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
+
+
+def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+                            im2col_step=128):
+    """msm_ms_deform_attn_bwd contract: (grad_value, grad_sampling_loc, grad_attn_weight)."""
+    from oracle import pixel_decoder as opd
+    with torch.enable_grad():
+        v, l, a = (t.detach().clone().requires_grad_() for t in (value, sampling_loc, attn_weight))
+        out = opd.ms_deform_attn_core(v, spatial_shapes, level_start_index, l, a)
+        return torch.autograd.grad(out, (v, l, a), grad_output)

@@ -283,3 +283,48 @@ def test_meta_arch_training_branch(ops, monkeypatch):
             overlap_threshold=0.8, metadata=None, size_divisibility=0, sem_seg_postprocess_before_inference=True,
             pixel_mean=[0.0] * 3, pixel_std=[1.0] * 3, semantic_on=False, panoptic_on=False, instance_on=True,
             test_topk_per_image=5).train()(batch)
+
+
+def test_whole_training_step_on_the_r50_style_head(ops, monkeypatch, golden):
+    """HeadTrainer (MSDeformAttn pixel decoder + multi-scale decoder + criterion) through training.train_step on CPU,
+    every kernel entry point replaced by its contract-level stand-in: the host code of the whole step - which ops
+    take the autograd route, what is detached, optimizer groups, clipping - runs end to end, gradients reach every
+    trainable tensor and a repeated batch is fitted."""
+    from unseenobjectswithmeanshift_b200 import training, workloads
+    from unseenobjectswithmeanshift_b200.d2compat import ShapeSpec
+    from unseenobjectswithmeanshift_b200.meanshiftformer import modeling as M
+    from unseenobjectswithmeanshift_b200.meanshiftformer.meanshiftformer_model import build_criterion
+    for name in ("mask_logits", "mask_to_attn_bits", "dense", "ms_deform_attn_forward", "ms_deform_attn_backward"):
+        monkeypatch.setattr(ops, name, getattr(fake_ops, name))
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)  # no driver in the CPU container
+    g, sd = golden("head_r50style")
+    shapes = {"res2": ShapeSpec(channels=8, stride=4), "res3": ShapeSpec(channels=16, stride=8),
+              "res4": ShapeSpec(channels=32, stride=16), "res5": ShapeSpec(channels=64, stride=32)}
+    pixel = M.MSDeformAttnPixelDecoder(shapes, transformer_dropout=0.0, transformer_nheads=4,
+                                       transformer_dim_feedforward=64, transformer_enc_layers=2, conv_dim=32,
+                                       mask_dim=32, norm="GN", transformer_in_features=["res3", "res4", "res5"],
+                                       common_stride=4)
+    head = M.PretrainedMeanShiftMaskFormerHead(shapes, num_classes=2, pixel_decoder=pixel, loss_weight=1.0,
+                                               ignore_value=255,
+                                               transformer_predictor=M.MeanShiftTransformerDecoder(32, True, **DEC_KW),
+                                               transformer_in_feature="multi_scale_pixel_decoder")
+    head.load_state_dict(sd, strict=True)
+    model = workloads.HeadTrainer(head.train(), build_criterion(2, dec_layers=5, train_num_points=64), 64, 96)
+    feats = {k[3:]: v for k, v in g.items() if k.startswith("in_")}
+    B = next(iter(feats.values())).shape[0]
+    masks = torch.zeros(2, 64, 96, dtype=torch.bool)
+    masks[0, 8:30, 10:40] = True
+    masks[1, 34:60, 50:90] = True
+    targets = [{"labels": torch.tensor([0, 1]), "masks": masks} for _ in range(B)]
+    opt = training.build_optimizer(model, lr=1e-3)
+    assert {(gr["lr"], gr["weight_decay"]) for gr in opt.param_groups} == {(1e-3, 0.05), (1e-3, 0.0)}
+    torch.manual_seed(0)
+    history = []
+    for _ in range(6):
+        losses = training.train_step(model, opt, {"features": feats, "targets": targets}, clip_value=1.0)
+        history.append(float(sum(losses.values())))
+    assert list(losses) == list(model.criterion.weight_dict)
+    assert all(h == h and abs(h) < 1e6 for h in history), history
+    missing = [n for n, p in model.named_parameters() if p.requires_grad and p.grad is None]
+    assert not missing, missing
+    assert min(history[3:]) < history[0], history
