@@ -623,3 +623,76 @@ def test_late_mode_detects_a_missing_barrier_wait():
     assert h.emu_hazard_copy(data.data_ptr(), 1, 0) == want     # correct kernel, synchronous
     assert h.emu_hazard_copy(data.data_ptr(), 1, 1) == want     # correct kernel, late
     assert h.emu_hazard_copy(data.data_ptr(), 0, 1) == -256.0   # missing wait: late mode exposes the stale tile
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# decoder-level wiring of the opt-in packed K / V path, with the REAL kernels running under the emulation
+def test_decoder_packed_kv_wiring_with_emulated_kernels(emu_chain, monkeypatch):
+    """_MeanShiftDecoderBase with MSM_PACKED_KV=1 on CPU: the K / V projections and the cross-attention go through the
+    emulated linear_tc_kernel<PACK> / vmf_attn_packed_kernel (same C entry points as ops.py binds), every other op
+    through its contract-level stand-in; the outputs must equal the default path's. Checks the host side of the
+    opt-in path: per-level image buffers, layer slicing, key counts, caching across calls."""
+    import fake_ops
+    from unseenobjectswithmeanshift_b200 import ops
+    from unseenobjectswithmeanshift_b200.meanshiftformer.modeling.transformer_decoder import (
+        meanshiftformer_transformer_decoder as dec)
+    h = emu_chain
+    for name in ("vmf_attention", "mask_logits", "mask_to_attn_bits", "dense"):
+        monkeypatch.setattr(ops, name, getattr(fake_ops, name))
+    monkeypatch.setattr(ops, "tc_linear_enabled", lambda: False)      # the un-fused layer sequence: fewer stand-ins
+
+    calls = {"alloc": 0, "project": 0, "attend": 0}
+
+    def packed_kv_alloc(layers, batch, heads, num_keys, device):
+        calls["alloc"] += 1
+        per_layer = h.msmx_vmf_packed_bytes(batch, heads, num_keys, 32, 3)
+        return _aligned(layers * per_layer, 128), per_layer
+
+    def linear_packed_kv(x, weight, bias, images, batch, num_keys, channels, which):
+        N, K = weight.shape
+        calls["project"] += 1
+        _start(h, 2)
+        w = weight.detach().contiguous()
+        p = _prepare(h, w)
+        b = bias.detach().contiguous()
+        rc = h.msmx_linear_packed_kv_fwd(x.data_ptr(), K, p.data_ptr(), b.data_ptr(), images.data_ptr(), batch, num_keys,
+                                         N, K, channels, int(which), 1, 1, None)
+        assert rc == 0, h.emu_last_error()
+
+    def vmf_attention_packed(q, kv, *, blocked_bits=None, row_open=None, kappa=30.0, out=None):
+        B, H, Nq, hd = q.shape
+        calls["attend"] += 1
+        st = lambda t: (t.data_ptr(), t.stride(0), t.stride(1), t.stride(2))
+        wsb = h.msmx_vmf_packed_workspace_bytes(B, H, Nq, kv.num_keys, hd)
+        ws = torch.zeros(wsb, dtype=torch.uint8)
+        _start(h, 2)
+        rc = h.msmx_vmf_attention_packed_fwd(*st(q), kv.images.data_ptr(), *st(out),
+                                             blocked_bits.data_ptr() if blocked_bits is not None else None,
+                                             blocked_bits.shape[2] if blocked_bits is not None else 0,
+                                             row_open.data_ptr() if row_open is not None else None,
+                                             B, H, Nq, kv.num_keys, hd, float(kappa), 3, ws.data_ptr(), wsb, None)
+        assert rc == 0, h.emu_last_error()
+        return out
+
+    monkeypatch.setattr(ops, "packed_kv_alloc", packed_kv_alloc)
+    monkeypatch.setattr(ops, "linear_packed_kv", linear_packed_kv)
+    monkeypatch.setattr(ops, "vmf_attention_packed", vmf_attention_packed)
+
+    torch.manual_seed(3)
+    kw = dict(num_classes=2, hidden_dim=64, num_queries=12, nheads=2, dim_feedforward=64, dec_layers=4,
+              pre_norm=False, mask_dim=32, enforce_input_project=False, use_meanshift_cross_attention=True,
+              disable_attention_mask=False, use_meanshift_self_attention=True, decoder_block_norm=True)
+    m = dec.MeanShiftTransformerDecoder(32, True, **kw).eval()
+    x = [torch.randn(2, 32, hh, ww) for hh, ww in ((3, 5), (6, 10), (12, 20))]      # 15 / 60 / 240 keys: tails everywhere
+    mf = torch.randn(2, 32, 24, 40)
+    with torch.no_grad():
+        monkeypatch.setenv("MSM_PACKED_KV", "0")
+        want = m(x, mf)
+        monkeypatch.setenv("MSM_PACKED_KV", "1")
+        got = m(x, mf)
+        again = m(x, mf)   # second call reuses the cached image buffers
+    # two forwards: 3 levels x (K, V) projections each, 4 cross-attentions each; the image buffers allocated once
+    assert calls == {"alloc": 3, "project": 12, "attend": 8}, calls
+    for o in (got, again):
+        assert (o["pred_masks"] - want["pred_masks"]).abs().max().item() < 1e-3 * want["pred_masks"].abs().max().item()
+        assert (o["pred_logits"] - want["pred_logits"]).abs().max().item() < 1e-3
