@@ -696,3 +696,51 @@ def test_decoder_packed_kv_wiring_with_emulated_kernels(emu_chain, monkeypatch):
     for o in (got, again):
         assert (o["pred_masks"] - want["pred_masks"]).abs().max().item() < 1e-3 * want["pred_masks"].abs().max().item()
         assert (o["pred_logits"] - want["pred_logits"]).abs().max().item() < 1e-3
+
+
+def test_decoder_training_gradients_through_the_emulated_backward_kernel(emu, monkeypatch, golden):
+    """The decoder's training path (tests/test_training_wiring.py) with the REAL attention backward kernel: every
+    VmfAttentionFunction.backward of the 4-layer decoder (cross- and self-attention, masks, the decoder's strided head
+    views) runs csrc/vmf_attention_bwd.cu under the emulation; the gradients of the probe loss must equal
+    torch.autograd through the REFERENCE decoder (golden)."""
+    import fake_ops
+    from scenes import probe_loss
+    from unseenobjectswithmeanshift_b200 import ops
+    from unseenobjectswithmeanshift_b200.meanshiftformer.modeling.transformer_decoder import (
+        meanshiftformer_transformer_decoder as dec)
+    for name in ("vmf_attention", "mask_logits", "mask_to_attn_bits", "dense"):
+        monkeypatch.setattr(ops, name, getattr(fake_ops, name))
+    count = {"bwd": 0}
+
+    def vmf_attention_bwd(q, k, v, out, grad_out, den, *, blocked_bits=None, row_open=None, add_mask=None, kappa=30.0,
+                          normalize_q=True, normalize_k=True):
+        count["bwd"] += 1
+        if grad_out.stride(3) != 1:
+            grad_out = grad_out.contiguous()
+        return _bwd(emu, q, k, v, out, grad_out, den.contiguous(), bits=blocked_bits, row_open=row_open, add_mask=add_mask,
+                    kappa=kappa, flags=(1 if normalize_q else 0) | (2 if normalize_k else 0))
+
+    monkeypatch.setattr(ops, "vmf_attention_bwd", vmf_attention_bwd)
+    g, sd = golden("decoder_multiscale")
+    want, _ = golden("decoder_multiscale_bwd")
+    kw = dict(num_classes=2, hidden_dim=32, num_queries=10, nheads=2, dim_feedforward=64, dec_layers=4,
+              pre_norm=False, mask_dim=32, enforce_input_project=False, use_meanshift_cross_attention=True,
+              disable_attention_mask=False, use_meanshift_self_attention=True, decoder_block_norm=True)
+    m = dec.MeanShiftTransformerDecoder(int(g["in_channels"]), True, **kw)
+    m.load_state_dict(sd, strict=True)
+    m.train()
+    x = [g[f"x{i}"].clone().requires_grad_() for i in range(3)]
+    mf = g["mask_features"].clone().requires_grad_()
+    loss = probe_loss(m(x, mf))
+    params = list(m.named_parameters())
+    grads = torch.autograd.grad(loss, [p for _, p in params] + x + [mf], allow_unused=True)
+    assert count["bwd"] == 8          # four cross- and four self-attention calls
+    seen = 0
+    for name, gr in zip([n for n, _ in params] + ["x0", "x1", "x2", "mask_features"], grads):
+        key = "grad::" + name
+        if gr is None:
+            assert key not in want, name
+            continue
+        _close(gr, want[key], 5e-4)
+        seen += 1
+    assert seen == sum(k.startswith("grad::") for k in want)
