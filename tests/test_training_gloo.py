@@ -135,3 +135,28 @@ def test_train_step_updates_parameters_and_clips():
     assert any(not torch.equal(before[n], p) for n, p in model.named_parameters())
     gnorm = torch.sqrt(sum((p.grad ** 2).sum() for p in model.parameters()))
     assert float(gnorm) <= 0.01 * 1.001   # full-model clipping (Base-COCO-InstanceSegmentation.yaml:29-32)
+
+
+def test_optimizer_groups_follow_the_reference_rules():
+    """tabletop_train_net_pretrained.py:113-160: modules named *backbone* train at lr x BACKBONE_MULTIPLIER, norm layers
+    and embeddings get their own weight decay; tensors with equal hyper-parameters share a group."""
+    from unseenobjectswithmeanshift_b200 import training
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.backbone = nn.Sequential(nn.Conv2d(3, 4, 1), nn.GroupNorm(2, 4))
+            self.head = nn.Linear(4, 4)
+            self.norm = nn.LayerNorm(4)
+            self.query_feat = nn.Embedding(5, 4)
+            self.frozen = nn.Linear(2, 2).requires_grad_(False)
+
+    net = Net()
+    opt = training.build_optimizer(net, lr=1e-4, weight_decay=0.05, backbone_multiplier=0.1)
+    groups = {(round(g["lr"], 9), g["weight_decay"]): {id(p) for p in g["params"]} for g in opt.param_groups}
+    assert set(groups) == {(1e-5, 0.05), (1e-5, 0.0), (1e-4, 0.05), (1e-4, 0.0)}
+    assert groups[(1e-5, 0.05)] == {id(p) for p in net.backbone[0].parameters()}
+    assert groups[(1e-5, 0.0)] == {id(p) for p in net.backbone[1].parameters()}
+    assert groups[(1e-4, 0.05)] == {id(p) for p in net.head.parameters()}
+    assert groups[(1e-4, 0.0)] == {id(p) for p in list(net.norm.parameters()) + list(net.query_feat.parameters())}
+    assert not any(id(p) in s for p in net.frozen.parameters() for s in groups.values())
