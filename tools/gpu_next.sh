@@ -30,3 +30,7 @@ cut -c1-300 gpurun_out/next_bench_ucn_default.json gpurun_out/next_bench_ucn_pac
 timeout 300 python bench.py --workload meanshift --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/next_bench_ms_default.json 2>/dev/null
 MSM_PACKED_MS=1 timeout 300 python bench.py --workload meanshift --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/next_bench_ms_packed.json 2>/dev/null
 cut -c1-300 gpurun_out/next_bench_ms_default.json gpurun_out/next_bench_ms_packed.json
+# 9. headline R50 step with the L2 persisting window on the mask features against the default
+timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/next_bench_r50_default.json 2>/dev/null
+MSM_L2_PERSIST=1 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/next_bench_r50_l2persist.json 2> gpurun_out/next_bench_r50_l2persist.err
+cut -c1-260 gpurun_out/next_bench_r50_default.json gpurun_out/next_bench_r50_l2persist.json; tail -2 gpurun_out/next_bench_r50_l2persist.err

@@ -106,3 +106,38 @@ extern "C" int msm_device_arch(void) {
   if (cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess) return -1;
   return major * 10 + minor;
 }
+
+// EXPERIMENTAL (prefix msmx_, not in the public header; opt-in through MSM_L2_PERSIST=1): L2 persisting access window
+// on [ptr, ptr + bytes) for the kernels launched on `stream` from now on (captured into graph kernel nodes). The mask
+// features are re-read by every prediction head call of a step. bytes = 0 clears the window.
+extern "C" int msmx_set_l2_persisting_window(const void* ptr, size_t bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaStreamAttrValue attr = {};
+  if (bytes == 0 || ptr == nullptr) {
+    attr.accessPolicyWindow.num_bytes = 0;
+    MSM_CUDA(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
+    return 0;
+  }
+  int dev = 0, max_window = 0, max_persist = 0;
+  MSM_CUDA(cudaGetDevice(&dev));
+  MSM_CUDA(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+  MSM_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
+  if (max_window <= 0 || max_persist <= 0) {
+    msm::set_error("this device has no persisting L2 cache");
+    return MSM_E_UNSUPPORTED;
+  }
+  static bool limit_set = false;
+  if (!limit_set) {  // set-aside of the L2 for persisting lines: as much as the device allows
+    MSM_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist));
+    limit_set = true;
+  }
+  const size_t window = bytes < (size_t)max_window ? bytes : (size_t)max_window;
+  attr.accessPolicyWindow.base_ptr = const_cast<void*>(ptr);
+  attr.accessPolicyWindow.num_bytes = window;
+  const float ratio = (float)((double)max_persist / (double)window);
+  attr.accessPolicyWindow.hitRatio = ratio < 1.f ? ratio : 1.f;  // the fraction of the window that fits the set-aside
+  attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  MSM_CUDA(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
+  return 0;
+}

@@ -430,6 +430,12 @@ class _MeanShiftDecoderBase(nn.Module):
         out = self.query_feat.weight.unsqueeze(0).expand(B, -1, -1).contiguous()
         need_mask = not self.disable_attention_mask
 
+        # EXPERIMENTAL, opt-in (MSM_L2_PERSIST=1; not yet run on a GPU): the mask features are re-read by every
+        # prediction head call below - keep as much of them as the device allows resident in L2
+        l2_window = ops.l2_persist_enabled() and not train
+        if l2_window:
+            ops.l2_persist(mask_features)
+
         predictions_class, predictions_mask = [], []
         logits, masks, bits, row_open = self._heads(out, mask_features, sizes[0], need_mask)
         predictions_class.append(logits)
@@ -520,6 +526,8 @@ class _MeanShiftDecoderBase(nn.Module):
             predictions_mask.append(masks)
 
         assert len(predictions_class) == self.num_layers + 1
+        if l2_window:
+            ops.l2_persist(None)
         return {
             "pred_logits": predictions_class[-1],
             "pred_masks": predictions_mask[-1],

@@ -250,6 +250,21 @@ def vmf_attention_packed(q, kv, *, blocked_bits=None, row_open=None, kappa=KAPPA
     return out
 
 
+def l2_persist_enabled():
+    return os.environ.get("MSM_L2_PERSIST", "0") == "1"
+
+
+def l2_persist(tensor=None):
+    """EXPERIMENTAL, opt-in (MSM_L2_PERSIST=1; not yet run on a GPU): L2 persisting access window on `tensor` for the
+    kernels launched on the current stream from now on; None clears it."""
+    if tensor is None:
+        rc = _lib.xlib().msmx_set_l2_persisting_window(None, 0, _stream())
+    else:
+        rc = _lib.xlib().msmx_set_l2_persisting_window(tensor.data_ptr(), tensor.numel() * tensor.element_size(),
+                                                       _stream())
+    check(rc, "msmx_set_l2_persisting_window")
+
+
 def vmf_attention_weights(q, k, den, *, blocked_bits=None, row_open=None, add_mask=None, kappa=KAPPA,
                           normalize_q=True, normalize_k=True):
     """Attention weights [B*H, Nq, Ns] (the second value hypersphere_attention returns)."""
