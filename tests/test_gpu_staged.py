@@ -215,3 +215,27 @@ def test_mean_shift_packed_path_matches_default(msm, monkeypatch):
         monkeypatch.setenv("MSM_PACKED_MS", "1")
         got = msm.mean_shift_hill_climb(X, Z, 10.0, 10)
         assert (got - want).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("B,H,Q,S,masked", [(8, 8, 100, 100, False), (8, 8, 100, 300, True), (1, 1, 128, 70, True),
+                                           (2, 2, 37, 1000, True)])
+def test_small_attention_kernel_vs_shipped(msm, B, H, Q, S, masked):
+    """vmf_small_kernel (single launch, CUDA cores, short key sequences) against the shipped dispatcher."""
+    dev = torch.device("cuda")
+    gen = torch.Generator(device="cuda").manual_seed(S + Q)
+    C = H * 32
+    q = torch.randn(B, Q, C, device=dev, generator=gen)
+    kv = torch.randn(B, S, 2 * C, device=dev, generator=gen)
+    hv = lambda t: t.unflatten(-1, (H, 32)).permute(0, 2, 1, 3)
+    bits = ro = None
+    if masked:
+        blocked = torch.rand(B, Q, S, device=dev, generator=gen) < 0.5
+        blocked[:, 3] = True
+        ro = (~blocked).any(-1).to(torch.int32).contiguous()
+        bits = _pack_bits(blocked)
+    want, wden = msm.vmf_attention(hv(q), hv(kv[..., :C]), hv(kv[..., C:]), blocked_bits=bits, row_open=ro,
+                                   return_den=True, save_norm=True)
+    got, gden = msm.vmf_attention_small(hv(q), hv(kv[..., :C]), hv(kv[..., C:]), blocked_bits=bits, row_open=ro,
+                                        return_den=True, save_norm=True)
+    assert (got - want).abs().max().item() < 2e-5
+    assert ((gden - wden).abs() / wden.abs().clamp_min(1e-30)).max().item() < 1e-4

@@ -744,3 +744,73 @@ def test_decoder_training_gradients_through_the_emulated_backward_kernel(emu, mo
         _close(gr, want[key], 5e-4)
         seen += 1
     assert seen == sum(k.startswith("grad::") for k in want)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# csrc/vmf_attention_small.cu: single-launch attention for short key sequences (opt-in MSM_SMALL_ATTN=1)
+@pytest.fixture(scope="module")
+def emu_small():
+    h = _build(os.path.join(ROOT, "build", "emu", "libemu_vmf_small.so"), "emu_vmf_small.cpp", ["vmf_attention_small.cu"])
+    P, I, L, Fl = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+    h.emu_vmf_small_supported.restype, h.emu_vmf_small_supported.argtypes = I, [I, I, I]
+    h.emu_vmf_attention_small.restype = I
+    h.emu_vmf_attention_small.argtypes = [P, L, L, L] * 4 + [P, P, I, P, I, I, I, I, Fl, I]
+    return h
+
+
+@pytest.mark.parametrize("B,H,Q,S,masked,flags,selfattn", [
+    (2, 2, 100, 100, False, 3, True),     # the decoder's self-attention: q | k | v slices of one fused projection
+    (1, 8, 100, 300, True, 3, False),     # coarsest cross-attention level of the R50 config, bit masks
+    (1, 1, 128, 70, True, 3, False),      # all 128 rows, key tail inside the second tile
+    (1, 2, 37, 1000, False, 1, False),    # k not normalised, 16 tiles
+])
+def test_emulated_small_attention_kernel(emu, emu_small, B, H, Q, S, masked, flags, selfattn):
+    """vmf_small_kernel against the fp64 reference; with MSM_VMF_SAVE_NORM its (den, |o|) planes then drive the
+    emulated BACKWARD kernel: a forward -> backward chain of real kernel sources against fp64 autograd."""
+    h = emu_small
+    assert h.emu_vmf_small_supported(Q, S, 32) == 1 and h.emu_vmf_small_supported(Q, 5000, 32) == 0
+    torch.manual_seed(S + Q)
+    hd, C = 32, H * 32
+    hv = lambda t: t.unflatten(-1, (H, hd)).permute(0, 2, 1, 3)
+    if selfattn:
+        qkv = torch.randn(B, S, 3 * C)
+        q4, k4, v4 = hv(qkv[..., :C]), hv(qkv[..., C:2 * C]), hv(qkv[..., 2 * C:])
+    else:
+        qb, kvb = torch.randn(B, Q, C), torch.randn(B, S, 2 * C)
+        if not flags & 2:   # without the kernel's normalisation the rows have to be unit vectors already (the fixed
+            kvb = F.normalize(kvb.view(B, S, 2 * H, hd), dim=-1).reshape(B, S, 2 * C)   # shift assumes |cos| <= 1)
+        q4, k4, v4 = hv(qb), hv(kvb[..., :C]), hv(kvb[..., C:])
+    bits = ro = eff = None
+    if masked:
+        blocked = torch.rand(B, Q, S) < 0.5
+        blocked[:, 3] = True
+        ro = (~blocked).any(-1).to(torch.int32).contiguous()
+        bits = _pack_bits(blocked)
+        eff = (blocked & (ro != 0).unsqueeze(-1)).unsqueeze(1)
+    out = torch.full((B, Q, H, hd), float("nan")).permute(0, 2, 1, 3)
+    den = torch.full((2, B * H, Q), float("nan"))
+    st = lambda t: (t.data_ptr(), t.stride(0), t.stride(1), t.stride(2))
+    rc = h.emu_vmf_attention_small(*st(q4), *st(k4), *st(v4), *st(out), den.data_ptr(),
+                                   bits.data_ptr() if masked else None, bits.shape[2] if masked else 0,
+                                   ro.data_ptr() if masked else None, B, H, Q, S, 30.0, flags | 4)
+    assert rc == 0
+    q2, k2, v2 = (t.double().clone().requires_grad_() for t in (q4, k4, v4))
+    qn = F.normalize(q2, dim=-1) if flags & 1 else q2
+    kn = F.normalize(k2, dim=-1) if flags & 2 else k2
+    s = 30.0 * qn @ kn.transpose(-1, -2)
+    if eff is not None:
+        s = s.masked_fill(eff, float("-inf"))
+    w = torch.exp(s - 30.0)
+    o = (w @ v2) / w.sum(-1, keepdim=True)
+    ref = F.normalize(o, dim=-1)
+    assert (out.double() - ref.detach()).abs().max().item() < 2e-6
+    rel = lambda a, b_: ((a.double() - b_).abs() / b_.abs().clamp_min(1e-30)).max().item()
+    assert rel(den[0].view(B, H, Q), w.sum(-1).detach()) < 1e-5      # softmax denominators with the fixed shift
+    assert rel(den[1].view(B, H, Q), o.norm(dim=-1).detach()) < 1e-5  # |softmax . v|
+    # backward kernel on the planes the forward kernel wrote
+    gout = torch.randn(B, H, Q, hd)
+    gq, gk, gv = _bwd(emu, q4, k4, v4, out, gout, den, bits=bits, row_open=ro, kappa=30.0, flags=flags)
+    rq, rk, rv = torch.autograd.grad(ref, (q2, k2, v2), gout.double())
+    _close(gq, rq, 1e-4)
+    _close(gk, rk, 1e-4)
+    _close(gv, rv, 1e-4)

@@ -34,3 +34,6 @@ cut -c1-300 gpurun_out/next_bench_ms_default.json gpurun_out/next_bench_ms_packe
 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/next_bench_r50_default.json 2>/dev/null
 MSM_L2_PERSIST=1 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/next_bench_r50_l2persist.json 2> gpurun_out/next_bench_r50_l2persist.err
 cut -c1-260 gpurun_out/next_bench_r50_default.json gpurun_out/next_bench_r50_l2persist.json; tail -2 gpurun_out/next_bench_r50_l2persist.err
+# 10. headline R50 step with the single-launch kernel for the short attention problems (self-attention, 300-key level)
+MSM_SMALL_ATTN=1 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/next_bench_r50_smallattn.json 2> gpurun_out/next_bench_r50_smallattn.err
+cut -c1-260 gpurun_out/next_bench_r50_smallattn.json; tail -2 gpurun_out/next_bench_r50_smallattn.err

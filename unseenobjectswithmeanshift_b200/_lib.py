@@ -70,6 +70,7 @@ X_SIGNATURES = {
                                            _P, _Z, _P]),
     "msmx_linear_packed_kv_fwd": (_I, [_P, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "msmx_set_l2_persisting_window": (_I, [_P, _Z, _P]),
+    "msmx_vmf_attention_small_fwd": (_I, [_P, _L, _L, _L] * 4 + [_P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _I, _P]),
     "msmx_mean_shift_packed_bytes": (_Z, [_I, _I, _I]),
     "msmx_mean_shift_packed_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "msmx_mean_shift_pack": (_I, [_P, _P, _I, _I, _I, _P]),

@@ -396,12 +396,24 @@ size_t vmf_workspace_bytes(int batch, int heads, int Nq, int Ns, int hd) {
   return need;
 }
 
+// single-launch kernel for short key sequences (vmf_attention_small.cu; opt-in)
+bool vmf_small_enabled();
+bool vmf_small_supported(const float* add_mask, int Nq, int Ns, int hd);
+int vmf_attention_small(const float* q, int64_t q_sb, int64_t q_sh, int64_t q_sl, const float* k, int64_t k_sb,
+                        int64_t k_sh, int64_t k_sl, const float* v, int64_t v_sb, int64_t v_sh, int64_t v_sl, float* out,
+                        int64_t o_sb, int64_t o_sh, int64_t o_sl, float* den, const uint32_t* bits, int wpr,
+                        const int32_t* row_open, int batch, int heads, int Nq, int Ns, float kappa, int flags,
+                        cudaStream_t st);
+
 // tcgen05 kernel when the shape/strides allow it, fp32 CUDA-core kernel otherwise (same library, same algorithm)
 int vmf_attention(const float* q, int64_t q_sb, int64_t q_sh, int64_t q_sl, const float* k, int64_t k_sb, int64_t k_sh,
                   int64_t k_sl, const float* v, int64_t v_sb, int64_t v_sh, int64_t v_sl, float* out, int64_t o_sb,
                   int64_t o_sh, int64_t o_sl, float* den, const uint32_t* bits, int wpr, const int32_t* row_open,
                   const float* add_mask, int batch, int heads, int Nq, int Ns, int hd, float kappa, int flags,
                   void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (vmf_small_enabled() && vmf_small_supported(add_mask, Nq, Ns, hd))
+    return vmf_attention_small(q, q_sb, q_sh, q_sl, k, k_sb, k_sh, k_sl, v, v_sb, v_sh, v_sl, out, o_sb, o_sh, o_sl, den,
+                               bits, wpr, row_open, batch, heads, Nq, Ns, kappa, flags, st);
   if (tc_enabled() && vmf_tc_supported(q, q_sb, q_sh, q_sl, k, k_sb, k_sh, k_sl, v, v_sb, v_sh, v_sl, add_mask, Nq, hd)) {
     const int G = batch * heads;
     const size_t need = vmf_tc_workspace_bytes(G, Nq, Ns, hd);

@@ -250,6 +250,33 @@ def vmf_attention_packed(q, kv, *, blocked_bits=None, row_open=None, kappa=KAPPA
     return out
 
 
+def vmf_attention_small(q, k, v, *, blocked_bits=None, row_open=None, kappa=KAPPA, normalize_q=True, normalize_k=True,
+                        out=None, return_den=False, save_norm=False):
+    """EXPERIMENTAL (not yet run on a GPU): vmf_attention through the single-launch CUDA-core kernel for short key
+    sequences (csrc/vmf_attention_small.cu; hd 32, Nq <= 128, Ns <= 1024). MSM_SMALL_ATTN=1 makes msm_vmf_attention_fwd
+    pick it by itself; this front-end calls it directly."""
+    q, q_sb, q_sh, q_sl = _bhld(q, "q")
+    k, k_sb, k_sh, k_sl = _bhld(k, "k")
+    v, v_sb, v_sh, v_sl = _bhld(v, "v")
+    B, H, Nq, hd = q.shape
+    Ns = k.shape[2]
+    if out is None:
+        out = torch.empty(B, Nq, H, hd, device=q.device, dtype=torch.float32).permute(0, 2, 1, 3)
+    out, o_sb, o_sh, o_sl = _bhld(out, "out")
+    den = torch.empty((2, B * H, Nq) if save_norm else (B * H, Nq), device=q.device,
+                      dtype=torch.float32) if return_den else None
+    wpr = blocked_bits.shape[2] if blocked_bits is not None else 0
+    flags = (1 if normalize_q else 0) | (2 if normalize_k else 0) | (4 if save_norm else 0)
+    rc = _lib.xlib().msmx_vmf_attention_small_fwd(
+        q.data_ptr(), q_sb, q_sh, q_sl, k.data_ptr(), k_sb, k_sh, k_sl, v.data_ptr(), v_sb, v_sh, v_sl,
+        out.data_ptr(), o_sb, o_sh, o_sl, den.data_ptr() if den is not None else None,
+        _require(blocked_bits, "blocked_bits", torch.int32).data_ptr() if blocked_bits is not None else None, wpr,
+        _require(row_open, "row_open", torch.int32).data_ptr() if row_open is not None else None,
+        B, H, Nq, Ns, hd, float(kappa), flags, _stream())
+    check(rc, "msmx_vmf_attention_small_fwd")
+    return (out, den) if return_den else out
+
+
 def l2_persist_enabled():
     return os.environ.get("MSM_L2_PERSIST", "0") == "1"
 
