@@ -887,7 +887,10 @@ def test_linear_prepared_weight_cache_tracks_updates(msm):
             del w2
 
 
-@pytest.mark.parametrize("M,N,K", [(12600, 64, 64), (12600, 64, 1024), (252, 32, 32), (300, 32, 64)])
+# (6300 / 300 rows x 64 outputs: fewer row tiles than half the SMs - the column chunk must not be narrowed under the
+#  row epilogue; a single image through the R50 pixel decoder has exactly this shape)
+@pytest.mark.parametrize("M,N,K", [(12600, 64, 64), (12600, 64, 1024), (252, 32, 32), (300, 32, 64), (6300, 64, 64),
+                                   (300, 64, 1024)])
 def test_linear_residual_layernorm_vs_fp64(msm, M, N, K):
     """norm(src + linear(x)) of the deformable encoder layer (pixel_decoder/msdeformattn.py:64-84) with the add
     and the LayerNorm in the GEMM epilogue."""

@@ -814,3 +814,22 @@ def test_emulated_small_attention_kernel(emu, emu_small, B, H, Q, S, masked, fla
     _close(gq, rq, 1e-4)
     _close(gk, rk, 1e-4)
     _close(gv, rv, 1e-4)
+
+
+def test_regression_layernorm_epilogue_is_never_split_over_column_chunks(emu_lin):
+    """Found by a shape sweep under this emulation: with N = 64 and fewer row tiles than half the SMs, pick_bn narrowed
+    the column chunk to 32 and the fused residual + LayerNorm normalised the two halves of a row separately (on the
+    B200: M <= 9472 rows, e.g. ONE image through the R50 pixel decoder; the GPU test only had M = 12600)."""
+    h = emu_lin
+    torch.manual_seed(5)
+    M, N, K = 100, 64, 64
+    X, W, b, R = torch.randn(M, K), torch.randn(N, K) / K ** 0.5, torch.randn(N), torch.randn(M, N)
+    g, be = torch.randn(N), torch.randn(N)
+    Y = torch.full((M, N), float("nan"))
+    _start(h, 148)   # as many "SMs" as the B200 has: one row tile leaves room for narrower chunks
+    p = _prepare(h, W)
+    rc = h.msm_linear_ln_fwd(X.data_ptr(), K, p.data_ptr(), b.data_ptr(), R.data_ptr(), N, g.data_ptr(), be.data_ptr(),
+                             1e-5, Y.data_ptr(), N, M, N, K, None)
+    assert rc == 0, h.emu_last_error()
+    ref = F.layer_norm(R.double() + X.double() @ W.double().t() + b.double(), (N,), g.double(), be.double(), 1e-5)
+    assert (Y.double() - ref).abs().max().item() < 1e-5

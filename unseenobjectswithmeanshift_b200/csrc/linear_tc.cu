@@ -718,7 +718,11 @@ static int launch(const float* X, int64_t ldx, const void* prepared, const float
   P.pack_norm = ln.pack_norm; P.pack_f16 = ln.pack_f16; P.pack_out = ln.pack_out;
   P.pack_ntiles = ln.pack ? (ln.pack_S + 127) / 128 : 0;
   const int m_tiles_est = x_nchw ? Bt * ((Mb + kRows - 1) / kRows) : (M + kRows - 1) / kRows;
-  P.BN = ln.wide ? N : pick_bn(N, ln.conv3 ? sms_many() : m_tiles_est);
+  // the row epilogues (LayerNorm over the N outputs of a row) need the whole row in one CTA: never split N for them.
+  // (pick_bn narrows the chunk when there are few row tiles - with N = 64 and fewer than num_sms / 2 tiles that cut
+  //  the fused residual + LayerNorm into two independent 32-column halves; found by the emulation's shape sweep)
+  const bool row_epilogue = ln.wide || ln.gamma != nullptr;
+  P.BN = row_epilogue ? N : pick_bn(N, ln.conv3 ? sms_many() : m_tiles_est);
   P.nacc = P.BN > 128 ? 1 : kAcc;
   P.xstages = (P.BN > 128 || ln.conv3) ? 3 : kXStages;
   P.xstage_bytes = ln.conv3 ? kHaloStage : kAStageBytes;
