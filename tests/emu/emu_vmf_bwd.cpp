@@ -8,7 +8,8 @@
 
 namespace msm {
 void set_error(const char*, ...) {}
-int num_sms() { return 148; }
+static int g_sms = 148;
+int num_sms() { return g_sms; }
 namespace vbw {
 constexpr size_t cuda_emu_smem_floats = 64 * 1024;     // 256 KB: more than any configuration asks for
 alignas(16) float smem[cuda_emu_smem_floats];          // the block's dynamic shared memory (blocks run one at a time)
@@ -16,3 +17,5 @@ alignas(16) float smem[cuda_emu_smem_floats];          // the block's dynamic sh
 }  // namespace msm
 
 #include "../../unseenobjectswithmeanshift_b200/csrc/vmf_attention_bwd.cu"
+
+extern "C" void emu_set_sms(int n) { msm::g_sms = n; }

@@ -16,7 +16,8 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_emu_err, sizeof(g_emu_err), fmt, ap);
   va_end(ap);
 }
-int num_sms() { return 1; }  // one "SM": the split planner then gives every CTA several key tiles (ring wrap-around)
+static int g_sms = 1;  // one "SM": the split planner then gives every CTA several key tiles (ring wrap-around)
+int num_sms() { return g_sms; }
 bool tc_enabled() { return true; }
 bool pdl_enabled() { return false; }
 namespace vtc {
@@ -35,6 +36,7 @@ static msm::tc::EmuState g_state;
 static int g_late = 0;
 static void emu_prepare(double timeout_s) { msm::tc::emu_prepare(&g_state, timeout_s, g_late); }
 extern "C" void emu_set_late(int late) { g_late = late; }
+extern "C" void emu_set_sms(int n) { msm::g_sms = n; }
 extern "C" long emu_deferred_ops() { return g_state.deferred; }
 
 extern "C" const char* emu_last_error() { return msm::g_emu_err; }

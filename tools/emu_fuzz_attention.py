@@ -18,6 +18,7 @@ h.msmx_vmf_pack.restype = I; h.msmx_vmf_pack.argtypes = [P, L, L, L, P, L, L, L,
 h.msmx_vmf_attention_packed_fwd.restype = I
 h.msmx_vmf_attention_packed_fwd.argtypes = [P, L, L, L, P, P, L, L, L, P, I, P, I, I, I, I, I, Fl, I, P, Z, P]
 h.emu_set_timeout.argtypes = [D]; h.emu_set_late.argtypes = [I]; h.emu_last_error.restype = ctypes.c_char_p
+h.emu_set_sms.argtypes = [I]
 def aligned(nbytes, align=128):
     buf = torch.zeros(nbytes + align, dtype=torch.uint8); off = (-buf.data_ptr()) % align
     return buf[off:off + nbytes]
@@ -30,6 +31,7 @@ while time.time() < t_end:
     S = rng.choice([rng.randint(1, 130), rng.randint(100, 700), rng.randint(500, 1500)])
     masked, shared = rng.random() < 0.5, rng.random() < 0.25
     late = rng.choice([0, 1]); h.emu_set_late(late)
+    sms = rng.choice([1, 2, 7, 148]); h.emu_set_sms(sms)   # the key-split planner depends on the SM count
     torch.manual_seed(rng.randrange(1 << 30))
     C = H * hd
     q, kv = torch.randn(B, Q, C), torch.randn(B, S, 2 * C)
@@ -51,7 +53,7 @@ while time.time() < t_end:
         eff = (blocked & (ro != 0).unsqueeze(-1)).unsqueeze(1)
     st = lambda t: (t.data_ptr(), t.stride(0), t.stride(1), t.stride(2))
     G = B * H
-    desc = f"{kind} B{B} H{H} Q{Q} S{S} hd{hd} mask{int(masked)} shared{int(shared)} late{late}"
+    desc = f"{kind} B{B} H{H} Q{Q} S{S} hd{hd} mask{int(masked)} shared{int(shared)} late{late} sms{sms}"
     h.emu_set_timeout(300.0)
     try:
         if kind == "tc":
