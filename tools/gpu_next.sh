@@ -6,6 +6,8 @@ set -x
 mkdir -p gpurun_out
 # 1. the green suite must still be green (the attention finalize kernel gained an optional output)
 timeout 600 python -m pytest tests -q -m gpu -x 2>&1 | tail -5
+# 1b. ONE image through the R50 head against the CPU oracle: the shape of the LayerNorm-epilogue bug fixed on CPU
+timeout 400 python tools/parity_e2e.py --images 1 2>&1 | tail -6
 # 2. staged parity tests of the training side: attention backward kernel, decoder gradients, whole training steps
 timeout 600 python -m pytest tests -q -m gpu_staged -x 2>&1 | tee gpurun_out/next_staged.log | tail -15
 # 3. the same backward kernel under compute-sanitizer (memcheck), smallest cases only
