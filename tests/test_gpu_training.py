@@ -5,7 +5,7 @@ of the next round: ``python -m pytest tests -m gpu_staged -x -q``; re-mark as ``
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu_staged
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")

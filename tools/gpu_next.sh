@@ -11,7 +11,7 @@ timeout 400 python tools/parity_e2e.py --images 1 2>&1 | tail -6
 # 2. staged parity tests of the training side: attention backward kernel, decoder gradients, whole training steps
 timeout 600 python -m pytest tests -q -m gpu_staged -x 2>&1 | tee gpurun_out/next_staged.log | tail -15
 # 3. the same backward kernel under compute-sanitizer (memcheck), smallest cases only
-timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_staged.py -q -x \
+timeout 300 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_staged.py -q -x \
     -k "golden and vmf" > gpurun_out/next_sanitizer.log 2>&1; tail -5 gpurun_out/next_sanitizer.log
 # 4. experimental packed-operand attention / mean-shift kernels and the operand-image projection epilogue: parity + timing
 #    against the shipped kernels (the staged test of step 2 already ran the decoder with MSM_PACKED_KV=1)

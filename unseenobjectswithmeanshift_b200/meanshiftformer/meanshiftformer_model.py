@@ -222,8 +222,8 @@ class PretrainedMeanShiftMaskFormer(_MetaArchBase):
 
     def _gather(self, batched_inputs, key):
         first = batched_inputs[0][key]
-        if first.dim() == 4:                                   # one pre-batched tensor (:272-273)
-            return _batch_images(first.to(self.device), 0)
+        if first.dim() == 4:                                   # one pre-batched tensor (:270-275): padded like a list
+            return _batch_images(first.to(self.device), self.size_divisibility)
         return _batch_images([x[key].to(self.device) for x in batched_inputs], self.size_divisibility)
 
     def _head_outputs(self, batched_inputs):
@@ -269,6 +269,11 @@ def _from_config(cfg, pretrained):
         "instance_on": mf.TEST.INSTANCE_ON, "panoptic_on": mf.TEST.PANOPTIC_ON,
         "test_topk_per_image": cfg.TEST.DETECTIONS_PER_IMAGE,
     }
+    emb = getattr(cfg.MODEL, "EMBEDDING", None)
+    if emb is not None:  # reference from_config :227-236: an unsupported USE_LOSS config must fail loudly, not train without it
+        kw.update(use_embedding_loss=emb.USE_LOSS, embedding_loss_weight=emb.WEIGHT_LOSS, alpha=emb.ALPHA,
+                  delta=emb.DELTA, lambda_intra=emb.LAMBDA_INTRA, lambda_inter=emb.LAMBDA_INTER, metric=emb.METRIC,
+                  normalize=emb.NORMALIZE)
     if pretrained:
         kw.update(feature_crop=cfg.MODEL.EMBEDDING.FEATURE_CROP, use_depth=cfg.MODEL.USE_DEPTH,
                   use_other_backbone=cfg.MODEL.USE_OTHER_BACKBONE)

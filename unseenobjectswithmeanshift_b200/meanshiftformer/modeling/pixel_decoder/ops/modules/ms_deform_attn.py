@@ -88,7 +88,11 @@ class MSDeformAttn(nn.Module):
         n_off = M * L * P * 2
         w_ow = ops.cached_cat(self, "w_ow", [self.sampling_offsets.weight, self.attention_weights.weight])
         b_ow = ops.cached_cat(self, "b_ow", [self.sampling_offsets.bias, self.attention_weights.bias])
-        if torch.is_grad_enabled() and self.sampling_offsets.weight.requires_grad:
+        # autograd route whenever ANY tensor that reaches the op needs a gradient - not only when the offset weights
+        # train: a frozen pixel decoder under a trainable backbone / value_proj must still differentiate through it
+        needs_grad = torch.is_grad_enabled() and (
+            query.requires_grad or input_flatten.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if needs_grad:
             ow = torch.cat([self.sampling_offsets(query), self.attention_weights(query)], -1)
         else:
             if pos_table is not None and ops.linear_supported(query, w_ow):

@@ -15,6 +15,8 @@ import torch
 import torch.distributed as dist
 from torch import nn
 
+from . import ops
+
 
 def wrap_ddp(model, local_rank=None, bucket_cap_mb=64):
     """DistributedDataParallel when torch.distributed is initialised with more than one rank, else the model itself.
@@ -67,4 +69,7 @@ def train_step(model, optimizer, batched_inputs, clip_value=0.01):
         params = [p for g in optimizer.param_groups for p in g["params"] if p.grad is not None]
         nn.utils.clip_grad_norm_(params, clip_value)
     optimizer.step()
+    # fused / multi-tensor optimizers update parameters in place WITHOUT bumping tensor._version: every cache of
+    # derived weights (prepared 16-bit copies, concatenated K/V weights, row-bias tables) is keyed by this epoch
+    ops.bump_weights_epoch()
     return {k: v.detach() for k, v in losses.items()}
