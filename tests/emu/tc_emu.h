@@ -144,6 +144,9 @@ inline void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (cuda_emu::g_deadline_passed()) cuda_emu::die("mbar_wait: no progress (deadlock in the barrier protocol?)");
   }
 }
+// one lane of a converged warp (csrc/tc.cuh: elect.sync)
+inline bool elect_one() { return (threadIdx.x & 31) == 0; }
+
 struct Ring {
   uint32_t stage = 0, phase = 0;
   inline void advance(uint32_t nstages) {

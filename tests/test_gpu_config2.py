@@ -1,0 +1,274 @@
+"""GPU parity at the BENCHMARKED configuration (BASELINE.json config #2: C = 256, 8 heads of 32 channels, 100 queries,
+9 decoder layers, key grids 15x20 / 30x40 / 60x80, masks 120x160) - the shapes at which the decoder takes the tcgen05
+attention kernel (the small golden fixtures have 16-channel heads and run the CUDA-core kernel).
+
+What "parity" can mean for this model: every decoder layer thresholds the previous layer's masks
+(``sigmoid < 0.5``), so two correct fp32 implementations that differ by 1e-6 occasionally disagree on a mask bit, after
+which the layers behind it see different inputs (the reference's own CPU-vs-CPU runs do this too). Hence:
+
+* teacher-forced (each layer gets the ORACLE's input state and mask bits): every layer's logits must agree to <= 1e-3 of
+  peak (north_star's tolerance; measured ~1e-5), mask bits and per-pixel labels must be bit-exact outside a stated margin;
+* free-running over 8 seeds: the statistics are asserted and recorded (layers before the first flipped bit agree to
+  1e-4; label agreement per seed; median of the final error);
+* the TIMED configuration (B = 8, one CUDA graph, programmatic dependent launch on) must reproduce the eager forward
+  bit for bit;
+* bounded random shape sweeps of the dense / attention kernels against fp64.
+"""
+import json
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import decoder as odec
+
+pytestmark = pytest.mark.gpu
+
+LEVELS = [(15, 20), (30, 40), (60, 80)]
+MASK_HW = (120, 160)
+HEADS, LAYERS, Q, C = 8, 9, 100, 256
+
+
+def peak_rel(a, b):
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+def _pack_bits(blocked):
+    B, Qn, S = blocked.shape
+    words = (S + 31) // 32
+    pad = torch.zeros(B, Qn, words * 32, dtype=torch.bool, device=blocked.device)
+    pad[..., :S] = blocked
+    v = (pad.view(B, Qn, words, 32).long() << torch.arange(32, device=blocked.device)).sum(-1)
+    return torch.where(v >= 2 ** 31, v - 2 ** 32, v).to(torch.int32).contiguous()
+
+
+def _decoder(seed):
+    from unseenobjectswithmeanshift_b200 import workloads
+    from unseenobjectswithmeanshift_b200.meanshiftformer import modeling as M
+    torch.manual_seed(seed)
+    m = M.MeanShiftTransformerDecoder(64, True, **workloads.decoder_kwargs(LAYERS)).eval()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    return m, sd
+
+
+def _inputs(batch, seed):
+    g = torch.Generator().manual_seed(7000 + seed)
+    x = [torch.randn(batch, 64, h, w, generator=g) for h, w in LEVELS]
+    mf = torch.randn(batch, C, *MASK_HW, generator=g)
+    return x, mf
+
+
+def test_decoder_config2_teacher_forced():
+    """Each layer of the CUDA decoder is fed the oracle's own layer input (query state + mask bits); its prediction
+    (class logits, mask logits) and the NEXT layer's mask bits it derives are compared with the oracle's."""
+    from unseenobjectswithmeanshift_b200 import ops
+    B = 2
+    m, sd = _decoder(0)
+    x, mf = _inputs(B, 0)
+    trace = []
+    with torch.no_grad():
+        ref = odec.decoder_forward(sd, x, mf, num_heads=HEADS, num_layers=LAYERS, trace=trace)
+    ref_masks = [a["pred_masks"] for a in ref["aux_outputs"]] + [ref["pred_masks"]]
+    ref_logits = [a["pred_logits"] for a in ref["aux_outputs"]] + [ref["pred_logits"]]
+    m = m.cuda()
+    bit_mismatch = []
+
+    def teacher(i, out, bits, row_open):
+        S = LEVELS[i % 3][0] * LEVELS[i % 3][1]
+        want = trace[i]["blocked"].view(B, HEADS, Q, S)[:, 0]          # identical for the 8 heads, after the :618 rule
+        got = ops.unpack_attn_bits(bits, row_open, S, 1).view(B, Q, S).cpu()
+        bit_mismatch.append((got != want).float().mean().item())
+        forced_bits = _pack_bits(want.cuda())
+        return (trace[i]["tgt_in"].transpose(0, 1).contiguous().cuda(), forced_bits,
+                torch.ones(B, Q, dtype=torch.int32, device="cuda"))
+
+    with torch.no_grad():
+        out = m([t.cuda() for t in x], mf.cuda(), _teacher=teacher)
+    got_masks = [a["pred_masks"].cpu() for a in out["aux_outputs"]] + [out["pred_masks"].cpu()]
+    got_logits = [a["pred_logits"].cpu() for a in out["aux_outputs"]] + [out["pred_logits"].cpu()]
+    errs = [peak_rel(g, r) for g, r in zip(got_masks, ref_masks)]
+    lerrs = [peak_rel(g, r) for g, r in zip(got_logits, ref_logits)]
+    print("teacher-forced mask-logit error per prediction (of peak):", ["%.1e" % e for e in errs])
+    print("teacher-forced class-logit error per prediction (of peak):", ["%.1e" % e for e in lerrs])
+    print("mask-bit mismatch fraction per layer:", ["%.1e" % e for e in bit_mismatch])
+    assert max(errs) < 1e-3 and max(lerrs) < 1e-3              # north_star: 1e-3 rel fp32 on mask logits
+    assert max(errs) < 1e-4, "split-precision tensor-core path is expected at ~1e-5"
+    # mask bits: a bit may differ only where the oracle's own resampled logit is within 1e-4 of peak of the threshold;
+    # at 19200..4800 keys x 100 queries x 2 images that is a handful of bits at most
+    assert max(bit_mismatch) < 2e-5
+    # per-pixel instance labels (argmax over queries), bit-exact wherever the oracle's top-2 margin exceeds the tolerance
+    for g, r in zip(got_masks, ref_masks):
+        top2 = r.topk(2, dim=1).values
+        decided = (top2[:, 0] - top2[:, 1]) > 1e-4 * r.abs().max()
+        same = g.argmax(1) == r.argmax(1)
+        assert bool(same[decided].all())
+        assert same.float().mean().item() > 0.9995
+
+
+def test_decoder_config2_free_running_statistics():
+    """No teacher: 8 seeds (weights and inputs), one image each. Asserts what holds for every seed and records the
+    statistics the design doc quotes (gpurun_out/parity_config2_seeds.json when the directory exists)."""
+    rows = []
+    for seed in range(8):
+        m, sd = _decoder(seed)
+        x, mf = _inputs(1, seed)
+        with torch.no_grad():
+            ref = odec.decoder_forward(sd, x, mf, num_heads=HEADS, num_layers=LAYERS)
+            out = m.cuda()([t.cuda() for t in x], mf.cuda())
+        ref_masks = [a["pred_masks"] for a in ref["aux_outputs"]] + [ref["pred_masks"]]
+        got_masks = [a["pred_masks"].cpu() for a in out["aux_outputs"]] + [out["pred_masks"].cpu()]
+        errs = [peak_rel(g, r) for g, r in zip(got_masks, ref_masks)]
+        first = next((i for i, e in enumerate(errs) if e > 1e-4), None)   # prediction index of the first visible flip
+        r, g = ref_masks[-1], got_masks[-1]
+        rows.append({"seed": seed, "first_flip_prediction": first, "final_err_of_peak": errs[-1],
+                     "frac_gt_1e-3": ((g - r).abs() > 1e-3 * r.abs().max()).float().mean().item(),
+                     "argmax_agreement": (g.argmax(1) == r.argmax(1)).float().mean().item(),
+                     "per_prediction_err": errs})
+        # before any bit flips the two paths agree at kernel accuracy
+        upto = len(errs) if first is None else first
+        assert all(e < 1e-4 for e in errs[:upto])
+        assert errs[0] < 2e-5 and errs[1] < 1e-4
+    print(json.dumps(rows))
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "parity_config2_seeds.json"), "w") as f:
+            json.dump(rows, f, indent=1)
+    finals = sorted(r["final_err_of_peak"] for r in rows)
+    assert finals[len(finals) // 2] < 1e-3, finals                      # median over seeds inside north_star's 1e-3
+    assert min(r["argmax_agreement"] for r in rows) > 0.97, rows         # a flipped bit moves a few % of labels at most
+    assert sum(r["argmax_agreement"] > 0.9995 for r in rows) >= 4, rows  # most seeds: no visible flip at all
+
+
+def test_graph_replay_equals_eager_config2():
+    """The timed configuration of bench.py: B = 8, the whole R50-config head as ONE CUDA graph with programmatic
+    dependent launch on (the default). Replay must reproduce the eager forward bit for bit, twice in a row (static
+    buffers reused), and a fresh input must give fresh results."""
+    from unseenobjectswithmeanshift_b200 import workloads
+    from unseenobjectswithmeanshift_b200.graph import GraphedForward
+    assert os.environ.get("MSM_DISABLE_PDL", "") in ("", "0")
+    head = workloads.build_head("r50", seed=0).cuda()
+    feats = {k: v.cuda() for k, v in workloads.synthetic_features("r50", 8, seed=0).items()}
+    feats2 = {k: v.cuda() for k, v in workloads.synthetic_features("r50", 8, seed=1).items()}
+
+    def fwd(f):
+        out, _ = head(f, 480, 640)
+        return {"pred_logits": out["pred_logits"], "pred_masks": out["pred_masks"],
+                "aux": [a["pred_masks"] for a in out["aux_outputs"]]}
+
+    with torch.no_grad():
+        eager = {k: (v.clone() if torch.is_tensor(v) else [t.clone() for t in v]) for k, v in fwd(feats).items()}
+        eager2 = fwd(feats2)["pred_masks"].clone()
+    g = GraphedForward(fwd, feats)
+    for _ in range(2):
+        out = g(feats)
+        torch.cuda.synchronize()
+        assert torch.equal(out["pred_masks"], eager["pred_masks"])
+        assert torch.equal(out["pred_logits"], eager["pred_logits"])
+        for a, b in zip(out["aux"], eager["aux"]):
+            assert torch.equal(a, b)
+    out = g(feats2)
+    torch.cuda.synchronize()
+    assert torch.equal(out["pred_masks"], eager2)
+    assert not torch.equal(eager2, eager["pred_masks"])
+
+
+# ----------------------------------------------------------------------------- bounded random shape sweeps
+def _rng(seed):
+    return torch.Generator(device="cuda").manual_seed(seed)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_linear_shape_sweep_vs_fp64(seed):
+    """msm_linear_fwd on random (M, N, K): N, K multiples of 32, ragged M (row tiles with tails, single rows, several
+    waves), optional bias / ReLU - every element within 2e-5 of the output's peak of the fp64 result."""
+    from unseenobjectswithmeanshift_b200 import ops
+    g = _rng(100 + seed)
+    cpu = torch.Generator().manual_seed(100 + seed)
+    M = int(torch.randint(1, 40000 if seed % 4 == 0 else 3000, (1,), generator=cpu))
+    N = 32 * int(torch.randint(1, 33 if seed % 3 else 9, (1,), generator=cpu))
+    K = 32 * int(torch.randint(1, 65 if seed % 5 == 0 else 17, (1,), generator=cpu))
+    relu, has_bias = bool(seed & 1), bool(seed & 2)
+    x = torch.randn(M, K, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    b = torch.randn(N, device="cuda", generator=g) if has_bias else None
+    y = ops.linear(x, w, b, relu=relu)
+    ref = x.double() @ w.double().t() + (b.double() if has_bias else 0.0)
+    ref = ref.relu() if relu else ref
+    err = (y.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 2e-5, (M, N, K, relu, has_bias, err)
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_linear_ln_and_ffn_shape_sweep_vs_fp64(seed):
+    """msm_linear_ln_fwd (N in {32, 64}: the row epilogue must see whole rows whatever the planner does with few row
+    tiles - the bug class of round 1) and msm_ffn_ln_fwd on random row counts / widths."""
+    from unseenobjectswithmeanshift_b200 import ops
+    g = _rng(200 + seed)
+    cpu = torch.Generator().manual_seed(200 + seed)
+    M = int(torch.randint(1, 20000 if seed % 4 == 0 else 1500, (1,), generator=cpu))
+    N = 32 * int(torch.randint(1, 3, (1,), generator=cpu))
+    K = 32 * int(torch.randint(1, 40, (1,), generator=cpu))
+    x = torch.randn(M, K, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    norm = torch.nn.LayerNorm(N).cuda()
+    with torch.no_grad():
+        norm.weight.copy_(torch.randn(N, device="cuda", generator=g))
+        norm.bias.copy_(torch.randn(N, device="cuda", generator=g))
+        y = ops.linear_ln(x, w, b, res, norm)
+        ref = F.layer_norm(res.double() + x.double() @ w.double().t() + b.double(), (N,), norm.weight.double(),
+                           norm.bias.double(), norm.eps)
+    assert (y.double() - ref).abs().max().item() / ref.abs().max().item() < 3e-5, (M, N, K)
+    D = N
+    Fd = 128 * int(torch.randint(1, 15, (1,), generator=cpu))
+    xx = torch.randn(M, D, device="cuda", generator=g)
+    w1 = torch.randn(Fd, D, device="cuda", generator=g) / D ** 0.5
+    b1 = torch.randn(Fd, device="cuda", generator=g)
+    w2 = torch.randn(D, Fd, device="cuda", generator=g) / Fd ** 0.5
+    b2 = torch.randn(D, device="cuda", generator=g)
+    with torch.no_grad():
+        y = ops.ffn_ln(xx, w1, b1, w2, b2, norm)
+        h = (xx.double() @ w1.double().t() + b1.double()).relu()
+        ref = F.layer_norm(xx.double() + h @ w2.double().t() + b2.double(), (D,), norm.weight.double(),
+                           norm.bias.double(), norm.eps)
+    assert (y.double() - ref).abs().max().item() / ref.abs().max().item() < 3e-5, (M, D, Fd)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_attention_shape_sweep_vs_fp64(seed):
+    """vMF attention on random (B, H, Q <= 128, S, hd in {32, 64}), with and without bit masks (some rows fully
+    blocked -> the un-mask rule), through BOTH tcgen05 kernels: fp32 K / V rows (msm_vmf_attention_fwd) and packed
+    operand images (TMA-streamed, the decoder's default), against the fp64 formula of attention_util.py:64-82."""
+    from unseenobjectswithmeanshift_b200 import ops
+    g = _rng(300 + seed)
+    cpu = torch.Generator().manual_seed(300 + seed)
+    B = int(torch.randint(1, 4, (1,), generator=cpu))
+    H = int(torch.randint(1, 9, (1,), generator=cpu))
+    Qn = int(torch.randint(1, 129, (1,), generator=cpu))
+    S = int(torch.randint(1, 20000 if seed % 6 == 0 else 1500, (1,), generator=cpu))
+    hd = 32 if seed % 3 else 64
+    masked = bool(seed & 1)
+    Cc = H * hd
+    q = torch.randn(B, Qn, Cc, device="cuda", generator=g)
+    kv = torch.randn(B, S, 2 * Cc, device="cuda", generator=g)
+    hv = lambda t: t.unflatten(-1, (H, hd)).permute(0, 2, 1, 3)  # noqa: E731
+    bits = ro = None
+    blocked = torch.zeros(B, Qn, S, dtype=torch.bool, device="cuda")
+    if masked:
+        blocked = torch.rand(B, Qn, S, device="cuda", generator=g) < 0.6
+        blocked[:, Qn // 2] = True
+        ro = (~blocked).any(-1).to(torch.int32).contiguous()
+        bits = _pack_bits(blocked)
+        blocked = blocked & (ro != 0).unsqueeze(-1)
+    q4, k4, v4 = hv(q), hv(kv[..., :Cc]), hv(kv[..., Cc:])
+    qn, kn = F.normalize(q4.double(), dim=-1), F.normalize(k4.double(), dim=-1)
+    s = 30.0 * qn @ kn.transpose(-1, -2)
+    s = s.masked_fill(blocked.unsqueeze(1), float("-inf"))
+    ref = F.normalize(torch.softmax(s, -1) @ v4.double(), dim=-1)
+    got = ops.vmf_attention(q4, k4, v4, blocked_bits=bits, row_open=ro)
+    assert (got.double() - ref).abs().max().item() < 1e-4, ("rows", B, H, Qn, S, hd, masked)
+    if hd == 32:
+        got = ops.vmf_attention_packed(q4, ops.pack_kv(k4, v4), blocked_bits=bits, row_open=ro)
+        assert (got.double() - ref).abs().max().item() < 1e-4, ("packed", B, H, Qn, S, hd, masked)

@@ -136,7 +136,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
 
   if (warp == 0) {
     // =================================================================== X and W1 producer
-    if (lane == 0) {
+    if (tc::elect_one()) {  // one lane of the converged warp (elect.sync: no per-instruction elect loops)
       tc::Ring w1;
       int xi = 0;  // X tiles loaded so far (one shared-memory staging tile, consumed by the converters in order)
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
@@ -157,7 +157,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
     }
   } else if (warp == 2) {
     // =================================================================== W2 producer
-    if (lane == 0) {
+    if (tc::elect_one()) {  // one lane of the converged warp (elect.sync: no per-instruction elect loops)
       tc::Ring w2;
       for (int g = 0; g < total; ++g) {
         tc::mbar_wait(&w2_empty[w2.stage], w2.phase ^ 1);
@@ -168,7 +168,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // =================================================================== MMA issuer
-    if (lane == 0) {
+    if (tc::elect_one()) {  // one lane of the converged warp (elect.sync: no per-instruction elect loops)
       const uint32_t idesc1 = tc::idesc_f16(kRows, kHc, false, false);
       const uint32_t idesc2 = tc::idesc_f16(kRows, D, false, false);
       const uint32_t sw1 = tc::smem_u32(sW1), sw2 = tc::smem_u32(sW2);

@@ -161,7 +161,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
 
   if (warp == 0) {
     // =================================================================== TMA producer
-    if (lane == 0) {
+    if (tc::elect_one()) {  // one lane of the converged warp (elect.sync: no per-instruction elect loops)
       tc::Ring xs, rs;
       if (P.w_resident) {  // weights of this CTA's column chunk: once, spread over the four W barriers so that no
                            // barrier expects more than 32 KB (a single 128 KB expectation behaved erratically)
@@ -218,7 +218,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     }
   } else if (warp == 1) {
     // =================================================================== MMA issuer
-    if (lane == 0) {
+    if (tc::elect_one()) {  // one lane of the converged warp (elect.sync: no per-instruction elect loops)
       const uint32_t idesc = tc::idesc_g(kRows, P.BN, false, false);
       const uint32_t sw = tc::smem_u32(sW);
       tc::Ring as, ws;

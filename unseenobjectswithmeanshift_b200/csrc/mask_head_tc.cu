@@ -137,7 +137,7 @@ mask_gemm_tc_kernel(const __grid_constant__ CUtensorMap fmap, const Params P) {
 
   if (warp == 0) {
     // =================================================================== TMA producer
-    if (lane == 0) {
+    if (tc::elect_one()) {  // one lane of the converged warp (elect.sync: no per-instruction elect loops)
       tc::Ring fs;
       for (int pt = slot; pt < P.tiles_per_image; pt += P.ctas_per_image) {
         for (int kc = 0; kc < nkc; ++kc) {
@@ -150,7 +150,7 @@ mask_gemm_tc_kernel(const __grid_constant__ CUtensorMap fmap, const Params P) {
     }
   } else if (warp == 1) {
     // =================================================================== MMA issuer
-    if (lane == 0) {
+    if (tc::elect_one()) {  // one lane of the converged warp (elect.sync: no per-instruction elect loops)
       const uint32_t idesc = tc::idesc_g(kPx, P.N, /*A (TMEM) K-major*/ false, /*B K-major*/ false);
       const uint32_t ehi = tc::smem_u32(sEhi), elo = tc::smem_u32(sElo);
       tc::Ring as;

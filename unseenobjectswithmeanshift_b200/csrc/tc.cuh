@@ -54,6 +54,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// one lane of a CONVERGED warp (all 32 lanes must execute this): unlike `lane == 0`, ptxas knows the predicate of
+// elect.sync holds for exactly one thread and emits the warp-level tcgen05 / TMA instructions inside the branch
+// directly instead of wrapping each in an elect / retry loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ring-buffer cursor: stage index + phase parity
 struct Ring {
   uint32_t stage = 0, phase = 0;

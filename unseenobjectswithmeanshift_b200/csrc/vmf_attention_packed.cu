@@ -40,7 +40,7 @@ constexpr int kThreads = (kProducerWarp + 1) * 32;  // 576
 constexpr int kTile = 128;
 constexpr int kMaxStages = 6;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColS = 0, kColO = 256, kColQ = 320;
+constexpr uint32_t kColS = 0, kColO = 256, kColQ = 384;  // S/P x2 | O: [hi.hi+lo.hi | hi.lo] (2 HD) | Q hi, lo
 constexpr int kMaxSmem = 232448;
 
 struct Params {
@@ -324,15 +324,18 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_packed_kernel(const Para
       const int64_t prow = ((int64_t)g * P.nsplit + split) * P.Nq + qi;
 #pragma unroll
       for (int c32 = 0; c32 < HD / 32; ++c32) {
-        uint32_t r[32];
+        uint32_t r[32], r2[32];  // the accumulator's two halves: P_hi.V_hi + P_lo.V_hi | P_hi.V_lo
         tc::tmem_ld32(lane_addr + kColO + c32 * 32, r);
+        tc::tmem_ld32(lane_addr + kColO + HD + c32 * 32, r2);
         tc::tmem_ld_wait();
         if (qi < P.Nq) {
           float4* dst = reinterpret_cast<float4*>(P.part_acc + prow * HD + c32 * 32);
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                 __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+            dst[i] = make_float4(__uint_as_float(r[4 * i]) + __uint_as_float(r2[4 * i]),
+                                 __uint_as_float(r[4 * i + 1]) + __uint_as_float(r2[4 * i + 1]),
+                                 __uint_as_float(r[4 * i + 2]) + __uint_as_float(r2[4 * i + 2]),
+                                 __uint_as_float(r[4 * i + 3]) + __uint_as_float(r2[4 * i + 3]));
         }
       }
       if (qi < P.Nq) P.part_den[prow] = den;
@@ -349,57 +352,73 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_packed_kernel(const Para
       }
     }
   } else {
-    // ------------------------------------------------------------------- MMA issuer (as vmf_attn_tc_kernel)
-    if (lane == 0) {
-      const uint32_t idesc_s = QK16 ? tc::idesc_f16(128, kTile, false, false) : tc::idesc_bf16(128, kTile, false, false);
-      const uint32_t idesc_o = tc::idesc_bf16(128, HD, false, true);
-      const uint32_t q_hi = tmem_base + kColQ, q_lo = q_hi + HD / 2;
-      const uint32_t d_o = tmem_base + kColO;
-      const uint32_t v_lbo = 128u, v_sbo = kLboK;
-      const uint32_t skv = tc::smem_u32(sKV);
+    // ------------------------------------------------------------------- MMA issuer
+    // ncu (round 2, S = 307200): the softmax warps spent 62 % of their time waiting for scores while the ONE issuing
+    // lane needed ~2700 cycles per tile for ~380 SASS instructions (descriptor arithmetic in vector registers + R2UR,
+    // 30 MMAs) on a scheduler it shares with four softmax warps. So: the whole warp runs the loop convergently (waits,
+    // ring cursors and descriptors stay warp-uniform - uniform datapath), lane 0 only issues; descriptors are advanced
+    // by adding to their address field; and the weights x values product takes TWO instructions per 16 keys instead of
+    // three: P_hi x [V_hi | V_lo] (N = 2 HD: the lo image follows the hi image at the d-group stride) into a double
+    // width accumulator, P_lo x V_hi into its first half - 22 MMAs per tile instead of 30, same tensor cycles.
+    const bool leader = tc::elect_one();
+    const uint32_t idesc_s = QK16 ? tc::idesc_f16(128, kTile, false, false) : tc::idesc_bf16(128, kTile, false, false);
+    const uint32_t idesc_o2 = tc::idesc_bf16(128, 2 * HD, false, true);
+    const uint32_t idesc_o1 = tc::idesc_bf16(128, HD, false, true);
+    const uint32_t q_hi = tmem_base + kColQ, q_lo = q_hi + HD / 2;
+    const uint32_t d_o = tmem_base + kColO;
+    const uint32_t skv = tc::smem_u32(sKV);
+    // K-major K image: LBO = stride between 8-channel groups, SBO = 128 (8 keys); MN-major V image: LBO = 128 (8 keys),
+    // SBO = stride between 8-channel groups. Stage / k-step offsets are added to the address field (bytes >> 4).
+    const uint64_t kdesc0 = tc::smem_desc(skv, kLboK, 128);
+    const uint64_t vdesc0 = tc::smem_desc(skv + (SHARED ? 0u : 2u * kOpBytes), 128u, kLboK);
+    const uint32_t nstages = (uint32_t)P.nstages;
+    tc::Ring rs, rv;  // stage cursors of the score products (run two tiles ahead) and of the value products
 
-      auto issue_scores = [&](int j) {
-        const int stage = j % P.nstages;
-        tc::mbar_wait(&kv_full[stage], (j / P.nstages) & 1);
-        tc::tc_fence_after();
+    auto issue_scores = [&](int j) {
+      tc::mbar_wait(&kv_full[rs.stage], rs.phase);
+      tc::tc_fence_after();
+      if (leader) {
         const uint32_t d_s = tmem_base + kColS + (uint32_t)(j & 1) * 128u;
-        const uint32_t k_hi = skv + (uint32_t)stage * kStageBytes, k_lo = k_hi + kOpBytes;
+        const uint64_t k_hi = kdesc0 + (uint64_t)((rs.stage * kStageBytes) >> 4);
+        const uint64_t k_lo = k_hi + (uint64_t)(kOpBytes >> 4);
 #pragma unroll
         for (int ks = 0; ks < HD / 16; ++ks) {
-          const uint64_t db_hi = tc::smem_desc(k_hi + ks * 2 * kLboK, kLboK, 128);
-          const uint64_t db_lo = tc::smem_desc(k_lo + ks * 2 * kLboK, kLboK, 128);
-          tc::mma_bf16_ts(d_s, q_lo + ks * 8, db_hi, idesc_s, ks != 0);
-          tc::mma_bf16_ts(d_s, q_hi + ks * 8, db_lo, idesc_s, 1);
-          tc::mma_bf16_ts(d_s, q_hi + ks * 8, db_hi, idesc_s, 1);
+          const uint64_t step = (uint64_t)((ks * 2 * kLboK) >> 4);
+          tc::mma_bf16_ts(d_s, q_lo + ks * 8, k_hi + step, idesc_s, ks != 0);
+          tc::mma_bf16_ts(d_s, q_hi + ks * 8, k_lo + step, idesc_s, 1);
+          tc::mma_bf16_ts(d_s, q_hi + ks * 8, k_hi + step, idesc_s, 1);
         }
         tc::mma_commit(&s_full[j & 1]);
-      };
+      }
+      __syncwarp();
+      rs.advance(nstages);
+    };
 
-      tc::mbar_wait(q_ready, 0);
+    tc::mbar_wait(q_ready, 0);
+    tc::tc_fence_after();
+    issue_scores(0);
+    if (nt > 1) issue_scores(1);
+    for (int j = 0; j < nt; ++j) {
+      tc::mbar_wait(&p_full[j & 1], (j >> 1) & 1);
       tc::tc_fence_after();
-      issue_scores(0);
-      if (nt > 1) issue_scores(1);
-      for (int j = 0; j < nt; ++j) {
-        const int stage = j % P.nstages;
-        tc::mbar_wait(&p_full[j & 1], (j >> 1) & 1);
-        tc::tc_fence_after();
+      if (leader) {
         const uint32_t pw = tmem_base + kColS + (uint32_t)(j & 1) * 128u;
-        const uint32_t v_hi = skv + (uint32_t)stage * kStageBytes + (SHARED ? 0u : 2u * kOpBytes);
-        const uint32_t v_lo = v_hi + kOpBytes;
+        const uint64_t v_hi = vdesc0 + (uint64_t)((rv.stage * kStageBytes) >> 4);
 #pragma unroll
         for (int ks = 0; ks < kTile / 16; ++ks) {
-          const uint64_t db_hi = tc::smem_desc(v_hi + ks * 256, v_lbo, v_sbo);
-          const uint64_t db_lo = tc::smem_desc(v_lo + ks * 256, v_lbo, v_sbo);
+          const uint64_t db = v_hi + (uint64_t)((ks * 256) >> 4);
           const uint32_t p_hi = pw + (uint32_t)(ks >> 1) * 32u + (uint32_t)(ks & 1) * 8u, p_lo = p_hi + 16u;
-          tc::mma_bf16_ts(d_o, p_lo, db_hi, idesc_o, (j | ks) != 0);
-          tc::mma_bf16_ts(d_o, p_hi, db_lo, idesc_o, 1);
-          tc::mma_bf16_ts(d_o, p_hi, db_hi, idesc_o, 1);
+          tc::mma_bf16_ts(d_o, p_hi, db, idesc_o2, (j | ks) != 0);  // [hi.hi | hi.lo]
+          tc::mma_bf16_ts(d_o, p_lo, db, idesc_o1, 1);               // + lo.hi
         }
-        tc::mma_commit(&kv_empty[stage]);
-        if (j + 2 < nt) issue_scores(j + 2);
+        tc::mma_commit(&kv_empty[rv.stage]);
       }
-      tc::mma_commit(o_full);
+      __syncwarp();
+      rv.advance(nstages);
+      if (j + 2 < nt) issue_scores(j + 2);
     }
+    if (leader) tc::mma_commit(o_full);
+    __syncwarp();
   }
 
   tc::tc_fence_before();

@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_tc_kernel(const Params P
     }
   } else {
     // =================================================================== MMA issuer
-    if (lane == 0) {
+    if (tc::elect_one()) {  // one lane of the converged warp (elect.sync: no per-instruction elect loops)
       // A (TMEM) K-major, B K-major; B = V is MN-major
       const uint32_t idesc_s = QK16 ? tc::idesc_f16(128, kTile, false, false) : tc::idesc_bf16(128, kTile, false, false);
       const uint32_t idesc_o = tc::idesc_bf16(128, HD, false, true);

@@ -319,7 +319,11 @@ class _MeanShiftDecoderBase(nn.Module):
         return logits, masks, attn_mask
 
     # ------------------------------------------------------------------ forward
-    def forward(self, x, mask_features, mask=None):
+    def forward(self, x, mask_features, mask=None, _teacher=None):
+        """Reference :540-658 / :894-1010. ``_teacher`` is a test hook (tests/test_gpu_config2.py): a callable
+        ``(layer, out, bits, row_open) -> (out, bits, row_open)`` run at the top of every layer, so that a parity test
+        can feed each layer the ORACLE's inputs (teacher forcing) instead of letting a flipped mask bit of an earlier
+        layer decide what later layers see."""
         assert len(x) == self.num_feature_levels
         del mask  # reference :548 / :900
         if not (self.use_meanshift_cross_attention and self.use_meanshift_self_attention) or self.pre_norm:
@@ -457,6 +461,8 @@ class _MeanShiftDecoderBase(nn.Module):
 
         for i in range(self.num_layers):
             lvl = i % L
+            if _teacher is not None:
+                out, bits, row_open = _teacher(i, out, bits, row_open)
             if i not in kv:
                 project_kv(lvl, [i])
             K, V = kv.pop(i)

@@ -839,7 +839,7 @@ def mean_shift_hill_climb(X, Z, kappa, max_iters=10):
     if Zb.shape[0] != B or Zb.shape[2] != d:
         raise ValueError(f"X {tuple(X.shape)} / Z {tuple(Z.shape)} mismatch")
     out = torch.empty_like(Zb)
-    if os.environ.get("MSM_PACKED_MS", "0") == "1" and d in (32, 64) and m <= 128 and int(max_iters) >= 1:
+    if os.environ.get("MSM_PACKED_MS", "1") == "1" and d in (32, 64) and m <= 128 and int(max_iters) >= 1:
         # EXPERIMENTAL, opt-in (not yet run on a GPU): X is split into 16-bit operand images ONCE per call instead of in
         # every iteration (csrc/vmf_attention_packed.cu)
         X_ = _lib.xlib()
