@@ -462,6 +462,14 @@ inline void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
   const float xh = bf16_to_f32(hi & 0xffffu), yh = bf16_to_f32(hi >> 16);
   lo = pack_bf16(x - xh, y - yh);
 }
+// packed fp32 pairs (csrc/tc.cuh: FFMA2 / FADD2) as a plain struct
+struct f32x2 { float x, y; };
+inline f32x2 f2_pack(float x, float y) { return f32x2{x, y}; }
+inline void f2_unpack(f32x2 v, float& x, float& y) { x = v.x; y = v.y; }
+inline f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) { return f32x2{std::fmaf(a.x, b.x, c.x), std::fmaf(a.y, b.y, c.y)}; }
+inline f32x2 f2_add(f32x2 a, f32x2 b) { return f32x2{a.x + b.x, a.y + b.y}; }
+inline f32x2 f2_sub(f32x2 a, f32x2 b) { return f32x2{a.x - b.x, a.y - b.y}; }
+inline void split2_x2(float x, float y, uint32_t& hi, uint32_t& lo) { split2(x, y, hi, lo); }
 inline uint16_t f32_to_f16_rn(float x) {
   const _Float16 h = (_Float16)x;  // round-to-nearest-even (x86-64 gcc: soft-float or F16C)
   uint16_t u;

@@ -228,6 +228,43 @@ __device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t&
   lo = pack_bf16(x - xh, y - yh);
 }
 
+// ------------------------------------------------------------------------------------------ packed fp32 pairs
+// sm_100 has two-wide fp32 instructions on 64-bit register pairs (FFMA2 / FADD2 in SASS): one issue slot per two
+// elements. The softmax warps of the attention kernels are issue-bound, so scale + shift, row sums and the hi/lo
+// residual go through these. IEEE round-to-nearest per element, identical to the scalar instructions.
+typedef uint64_t f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float x, float y) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& x, float& y) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v));
+}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// (x, y) -> packed bf16 hi halves and the bf16 halves of the residuals, the subtraction as ONE two-wide instruction
+__device__ __forceinline__ void split2_x2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16(x, y);
+  const f32x2 res = f2_sub(f2_pack(x, y), f2_pack(__uint_as_float(hi << 16), __uint_as_float(hi & 0xFFFF0000u)));
+  float rx, ry;
+  f2_unpack(res, rx, ry);
+  lo = pack_bf16(rx, ry);
+}
+
 // ------------------------------------------------------------------------------------------ fp16 hi/lo split
 // Same three-pass scheme with IEEE half operands: 11 + 11 significant bits, i.e. ~2^-22 relative instead of
 // ~2^-17, for operands known to stay inside the fp16 range - unit vectors, probabilities, projected values

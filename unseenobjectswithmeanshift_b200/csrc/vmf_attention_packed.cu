@@ -40,7 +40,12 @@ constexpr int kThreads = (kProducerWarp + 1) * 32;  // 576
 constexpr int kTile = 128;
 constexpr int kMaxStages = 6;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColS = 0, kColO = 256, kColQ = 384;  // S/P x2 | O: [hi.hi+lo.hi | hi.lo] (2 HD) | Q hi, lo
+// TMEM map (512 columns): THREE score / weight tiles of 128 columns (tile j lives in buffer j % 3, so the scores of
+// tile j + 3 only wait for the value product of tile j - the softmax warps of a group find their next score tile
+// ready instead of waiting for a P.V -> Q.K round trip through the issuing warp), then the output accumulator (64
+// columns: HD = 32 -> [P_hi.V_hi + P_lo.V_hi | P_hi.V_lo], HD = 64 -> one HD-wide accumulator), then Q hi | lo.
+constexpr int kSBufs = 3;
+constexpr uint32_t kColS = 0, kColO = 384, kColQ = 448;
 constexpr int kMaxSmem = 232448;
 
 struct Params {
@@ -172,6 +177,7 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_packed_kernel(const Para
   constexpr uint32_t kOpBytes = kTile * HD * 2;
   constexpr uint32_t kStageBytes = (SHARED ? 2 : 4) * kOpBytes;
   constexpr uint32_t kLboK = (kTile / 8) * 128;
+  constexpr bool kWideO = (HD == 32);  // double-width output accumulator: two MMAs per 16 keys instead of three
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -179,9 +185,9 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_packed_kernel(const Para
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)P.nstages * kStageBytes);
   uint64_t* kv_full = bars;                    // [kMaxStages] producer (tx bytes) -> MMA
   uint64_t* kv_empty = kv_full + kMaxStages;   // [kMaxStages] MMA -> producer
-  uint64_t* s_full = kv_empty + kMaxStages;    // [2] MMA -> softmax group
-  uint64_t* p_full = s_full + 2;               // [2] softmax group (8 warps) -> MMA
-  uint64_t* o_full = p_full + 2;
+  uint64_t* s_full = kv_empty + kMaxStages;    // [kSBufs] MMA -> softmax group
+  uint64_t* p_full = s_full + kSBufs;          // [kSBufs] softmax group (8 warps) -> MMA
+  uint64_t* o_full = p_full + kSBufs;
   uint64_t* q_ready = o_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_ready + 1);
   float* s_den = reinterpret_cast<float*>(tmem_slot + 2);  // [3][128] partial row sums of the other three warp sets
@@ -198,7 +204,7 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_packed_kernel(const Para
       tc::mbar_init(&kv_full[i], 1);
       tc::mbar_init(&kv_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kSBufs; ++i) {
       tc::mbar_init(&s_full[i], 1);
       tc::mbar_init(&p_full[i], 8);
     }
@@ -259,13 +265,13 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_packed_kernel(const Para
       }
     };
 
-    float den = 0.f;
-    const float c = P.c;
-    const uint32_t sp = lane_addr + kColS + (uint32_t)grp * 128u;
+    tc::f32x2 den2 = tc::f2_pack(0.f, 0.f);  // row sum, even | odd keys (two-wide adds)
+    const tc::f32x2 c2 = tc::f2_pack(P.c, P.c), nc2 = tc::f2_pack(-P.c, -P.c);
     uint32_t wnext[2];
     load_words(grp, wnext);
-    int use = 0;
-    for (int j = grp; j < nt; j += 2, ++use) {
+    for (int j = grp; j < nt; j += 2) {
+      const int buf = j % kSBufs;
+      const uint32_t sp = lane_addr + kColS + (uint32_t)buf * 128u;
       const int key0 = (tile_begin + j) * kTile;
       uint32_t w[2] = {wnext[0], wnext[1]};
       load_words(j + 2, wnext);
@@ -274,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_packed_kernel(const Para
         const int nv = P.Ns - (key0 + 32 * (half * 2 + i));
         if (nv < 32) w[i] |= (nv <= 0) ? 0xffffffffu : ~((1u << nv) - 1u);
       }
-      tc::mbar_wait(&s_full[grp], use & 1);
+      tc::mbar_wait(&s_full[buf], (j / kSBufs) & 1);
       tc::tc_fence_after();
       const bool plain = !MASKED && (P.Ns - key0 >= kTile);
 #pragma unroll
@@ -285,23 +291,27 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_packed_kernel(const Para
         tc::tmem_ld_wait();
         const uint32_t wm = w[cq];
         uint32_t hi[16], lo[16];
+        // per PAIR of scores: one two-wide fma (kappa log2e (s - 1)), two ex2, (two selects), one two-wide add into
+        // the row sums, bf16 hi pack, one two-wide subtraction for the residuals, bf16 lo pack
         if (plain) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float p0 = ex2(fmaf(__uint_as_float(r[2 * i]), c, -c));
-            const float p1 = ex2(fmaf(__uint_as_float(r[2 * i + 1]), c, -c));
-            den += p0 + p1;
-            tc::split2(p0, p1, hi[i], lo[i]);
+            float x0, x1;
+            tc::f2_unpack(tc::f2_fma(tc::f2_pack(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), c2, nc2), x0, x1);
+            const float p0 = ex2(x0), p1 = ex2(x1);
+            den2 = tc::f2_add(den2, tc::f2_pack(p0, p1));
+            tc::split2_x2(p0, p1, hi[i], lo[i]);
           }
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float p0 = ex2(fmaf(__uint_as_float(r[2 * i]), c, -c));
-            float p1 = ex2(fmaf(__uint_as_float(r[2 * i + 1]), c, -c));
+            float x0, x1;
+            tc::f2_unpack(tc::f2_fma(tc::f2_pack(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), c2, nc2), x0, x1);
+            float p0 = ex2(x0), p1 = ex2(x1);
             if ((wm >> (2 * i)) & 1u) p0 = 0.f;
             if ((wm >> (2 * i + 1)) & 1u) p1 = 0.f;
-            den += p0 + p1;
-            tc::split2(p0, p1, hi[i], lo[i]);
+            den2 = tc::f2_add(den2, tc::f2_pack(p0, p1));
+            tc::split2_x2(p0, p1, hi[i], lo[i]);
           }
         }
         tc::tmem_st16(sp + ch * 32, hi);
@@ -310,11 +320,17 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_packed_kernel(const Para
       tc::tmem_st_wait();
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&p_full[grp]);
+      if (lane == 0) tc::mbar_arrive(&p_full[buf]);
     }
 
     // ---- epilogue
     const int set = grp * 2 + half;  // 0 = the warps that write the result
+    float den;
+    {
+      float de, dodd;
+      tc::f2_unpack(den2, de, dodd);
+      den = de + dodd;
+    }
     if (set != 0) s_den[(set - 1) * 128 + qi] = den;
     named_bar_sync(1, kSoftmaxWarps * 32);
     if (set == 0) {
@@ -324,9 +340,14 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_packed_kernel(const Para
       const int64_t prow = ((int64_t)g * P.nsplit + split) * P.Nq + qi;
 #pragma unroll
       for (int c32 = 0; c32 < HD / 32; ++c32) {
-        uint32_t r[32], r2[32];  // the accumulator's two halves: P_hi.V_hi + P_lo.V_hi | P_hi.V_lo
+        uint32_t r[32], r2[32];  // HD = 32: the accumulator's two halves P_hi.V_hi + P_lo.V_hi | P_hi.V_lo
         tc::tmem_ld32(lane_addr + kColO + c32 * 32, r);
-        tc::tmem_ld32(lane_addr + kColO + HD + c32 * 32, r2);
+        if constexpr (kWideO) {
+          tc::tmem_ld32(lane_addr + kColO + HD + c32 * 32, r2);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r2[i] = 0u;
+        }
         tc::tmem_ld_wait();
         if (qi < P.Nq) {
           float4* dst = reinterpret_cast<float4*>(P.part_acc + prow * HD + c32 * 32);
@@ -372,13 +393,13 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_packed_kernel(const Para
     const uint64_t kdesc0 = tc::smem_desc(skv, kLboK, 128);
     const uint64_t vdesc0 = tc::smem_desc(skv + (SHARED ? 0u : 2u * kOpBytes), 128u, kLboK);
     const uint32_t nstages = (uint32_t)P.nstages;
-    tc::Ring rs, rv;  // stage cursors of the score products (run two tiles ahead) and of the value products
+    tc::Ring rs, rv;  // stage cursors of the score products (run kSBufs tiles ahead) and of the value products
 
     auto issue_scores = [&](int j) {
       tc::mbar_wait(&kv_full[rs.stage], rs.phase);
       tc::tc_fence_after();
       if (leader) {
-        const uint32_t d_s = tmem_base + kColS + (uint32_t)(j & 1) * 128u;
+        const uint32_t d_s = tmem_base + kColS + (uint32_t)(j % kSBufs) * 128u;
         const uint64_t k_hi = kdesc0 + (uint64_t)((rs.stage * kStageBytes) >> 4);
         const uint64_t k_lo = k_hi + (uint64_t)(kOpBytes >> 4);
 #pragma unroll
@@ -388,7 +409,7 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_packed_kernel(const Para
           tc::mma_bf16_ts(d_s, q_hi + ks * 8, k_lo + step, idesc_s, 1);
           tc::mma_bf16_ts(d_s, q_hi + ks * 8, k_hi + step, idesc_s, 1);
         }
-        tc::mma_commit(&s_full[j & 1]);
+        tc::mma_commit(&s_full[j % kSBufs]);
       }
       __syncwarp();
       rs.advance(nstages);
@@ -396,26 +417,31 @@ __global__ void __launch_bounds__(kThreads, 1) vmf_attn_packed_kernel(const Para
 
     tc::mbar_wait(q_ready, 0);
     tc::tc_fence_after();
-    issue_scores(0);
-    if (nt > 1) issue_scores(1);
+    for (int j = 0; j < kSBufs && j < nt; ++j) issue_scores(j);
     for (int j = 0; j < nt; ++j) {
-      tc::mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+      tc::mbar_wait(&p_full[j % kSBufs], (j / kSBufs) & 1);
       tc::tc_fence_after();
       if (leader) {
-        const uint32_t pw = tmem_base + kColS + (uint32_t)(j & 1) * 128u;
+        const uint32_t pw = tmem_base + kColS + (uint32_t)(j % kSBufs) * 128u;
         const uint64_t v_hi = vdesc0 + (uint64_t)((rv.stage * kStageBytes) >> 4);
 #pragma unroll
         for (int ks = 0; ks < kTile / 16; ++ks) {
           const uint64_t db = v_hi + (uint64_t)((ks * 256) >> 4);
           const uint32_t p_hi = pw + (uint32_t)(ks >> 1) * 32u + (uint32_t)(ks & 1) * 8u, p_lo = p_hi + 16u;
-          tc::mma_bf16_ts(d_o, p_hi, db, idesc_o2, (j | ks) != 0);  // [hi.hi | hi.lo]
-          tc::mma_bf16_ts(d_o, p_lo, db, idesc_o1, 1);               // + lo.hi
+          if constexpr (kWideO) {
+            tc::mma_bf16_ts(d_o, p_hi, db, idesc_o2, (j | ks) != 0);  // [hi.hi | hi.lo]: the lo image follows the hi image
+            tc::mma_bf16_ts(d_o, p_lo, db, idesc_o1, 1);               // + lo.hi
+          } else {
+            tc::mma_bf16_ts(d_o, p_lo, db, idesc_o1, (j | ks) != 0);
+            tc::mma_bf16_ts(d_o, p_hi, db + (uint64_t)(kOpBytes >> 4), idesc_o1, 1);
+            tc::mma_bf16_ts(d_o, p_hi, db, idesc_o1, 1);
+          }
         }
         tc::mma_commit(&kv_empty[rv.stage]);
       }
       __syncwarp();
       rv.advance(nstages);
-      if (j + 2 < nt) issue_scores(j + 2);
+      if (j + kSBufs < nt) issue_scores(j + kSBufs);
     }
     if (leader) tc::mma_commit(o_full);
     __syncwarp();
