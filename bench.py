@@ -116,24 +116,30 @@ def run_reference(args, rank, world):
     if args.workload in ("train", "twostage"):
         run_reference_train_twostage(args, cores)
         return
-    head = workloads.build_head(args.workload)
-    sd = {k: v.detach() for k, v in head.state_dict().items()}
-    sample_b = 2
-    feats = workloads.synthetic_features(args.workload, sample_b)
-    for _ in range(args.warmup):
-        cpu_oracle_step(sd, feats, args.workload)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_oracle_step(sd, feats, args.workload)
-    dt = time.perf_counter() - t0
+    kind = args.workload
+    full = kind in FULL_MODEL
+    # bounded sample per step: the whole --steps K --warmup W run has to end within a few minutes
+    sample_b = 1 if (kind in ("demo", "ucn") or args.steps > 50) else 2
+    if kind in ("demo", "ucn"):   # 307200-key configurations take ~30 s per image on the CPU
+        args.steps, args.warmup = min(args.steps, 3), min(args.warmup, 1)
+    host_in = (workloads.synthetic_images(kind, sample_b) if full
+               else workloads.synthetic_features(HEAD_KIND[kind], sample_b))
+    cpu_step, which, note = _cpu_model(kind, full)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            cpu_step(host_in)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_step(host_in)
+        dt = time.perf_counter() - t0
     val = sample_b * args.steps / dt
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": METRICS[kind], "value": val, "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}-head 640x480", "per_step_batch": sample_b,
-                       "queries": 100, "note": "CPU oracle port of the reference PyTorch path, fp32"},
-            "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} steps x {sample_b} image(s) of the same head workload"},
+            "config": {"workload": f"{kind} 640x480 (CPU reference arm: {note})", "per_step_batch": sample_b,
+                       "queries": 100},
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": which,
+                             "sample": f"{args.steps} steps x {sample_b} image(s) of the same workload; {note}"},
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -245,7 +251,7 @@ def run_meanshift(args, rank, local_rank, world, dev, sharding, ops):
     kappa=10, 10 iterations, `--batch` images per GPU (default 32). One step = the whole 10-iteration climb of
     the batch (20 kernel launches: partial + finalize per iteration); X stays resident in HBM across iterations."""
     import torch.nn.functional as F
-    B = args.batch if args.batch != PER_GPU_BATCH else 32
+    B = args.batch if args.batch > 0 else 32
     n, d, m, kappa, iters = 480 * 640, 64, 100, 10.0, 10
     g = torch.Generator().manual_seed(4 + rank)
     hostX = torch.empty(B, n, d).pin_memory()
@@ -338,7 +344,7 @@ def run_cluster(args, rank, local_rank, world, dev, sharding, ops):
     (default 16). One step = the batch through all four stages, no host synchronisation inside."""
     import torch.nn.functional as F
     from unseenobjectswithmeanshift_b200.meanshiftformer.modeling.transformer_decoder import mean_shift as ms
-    B = args.batch if args.batch != PER_GPU_BATCH else 16
+    B = args.batch if args.batch > 0 else 16
     n, d, m, kappa, iters, objects = 480 * 640, 64, 100, 20.0, 10, 12
     g = torch.Generator().manual_seed(40 + rank)
     hostX = torch.empty(B, n, d).pin_memory()
@@ -561,7 +567,7 @@ def run_twostage(args, rank, local_rank, world, dev, sharding, ops):
     5 objects per frame (fixes the unit of work: 5 crops per frame). Embedding backbone: synthetic stand-in."""
     from unseenobjectswithmeanshift_b200 import workloads
     from unseenobjectswithmeanshift_b200.fcn import test_dataset as td
-    B = args.batch if args.batch != PER_GPU_BATCH else 16
+    B = args.batch if args.batch > 0 else 16
     K = 5
     model, model_crop = (m.to(dev) for m in workloads.build_two_stage_models())
     himg, hdepth, hlabels = workloads.synthetic_frames(B, objects=K, seed=rank)
@@ -717,11 +723,22 @@ def run_train(args, rank, local_rank, world, dev, sharding, ops):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="r50", choices=["r50", "ucn", "crop", "meanshift", "cluster", "tail", "train", "twostage"])
-    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU per step")
+    ap.add_argument("--workload", default="r50", choices=["r50", "demo", "r50-head", "ucn", "crop", "meanshift", "cluster",
+                                                          "tail", "train", "twostage"],
+                    help="r50 (default) = BASELINE.json configs[1], whole model; demo = configs[0] (one RGB-D frame, whole "
+                         "model); r50-head / ucn / crop = the head alone on backbone features; the rest: configs[2..4] and "
+                         "the SURVEY 8(f) rows")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (0 = the workload's default)")
+    ap.add_argument("--tail", default="label_map", choices=["label_map", "instances"],
+                    help="whole-model workloads: what the step returns (fused get_confident_instances + combine_masks "
+                         "label map, or the Instances fields incl. full-resolution masks)")
+    ap.add_argument("--skip-profile", action="store_true", help="leave out the CUPTI kernel-share pass")
+    ap.add_argument("--backbone-tf32", action="store_true",
+                    help="whole-model workloads: let cuDNN run the BACKBONE in TF32 (PyTorch's default on a GPU, i.e. the "
+                         "reference's stock behaviour there); default fp32 = the reference's CPU arithmetic")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--vmf-tflops", action="store_true", help="also time the attention core alone (default with the CPU baseline)")
@@ -745,7 +762,9 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    kind, B = args.workload, args.batch
+    kind = args.workload
+    if args.batch <= 0 and kind in ("train", "twostage", "tail"):
+        args.batch = 16 if kind == "twostage" else PER_GPU_BATCH
     if kind == "meanshift":
         run_meanshift(args, rank, local_rank, world, dev, sharding, ops)
         return
@@ -762,22 +781,107 @@ def main():
         run_twostage(args, rank, local_rank, world, dev, sharding, ops)
         return
 
-    head = workloads.build_head(kind).to(dev)
-    host_feats = workloads.synthetic_features(kind, B, seed=rank, pin=True)
-    dev_feats = {k: v.to(dev) for k, v in host_feats.items()}
-    H, W = workloads.HEAD_CFG[kind]["height"], workloads.HEAD_CFG[kind]["width"]
+    run_forward(args, rank, local_rank, world, dev, sharding, ops, workloads)
 
-    def step(feats):
-        out, _ = head(feats, H, W)
-        return {"pred_logits": out["pred_logits"], "pred_masks": out["pred_masks"],
-                "aux_pred_masks": [a["pred_masks"] for a in out["aux_outputs"]]}
 
+# ------------------------------------------------------------------------------------------------------------------
+# forward workloads: whole model at the reference's API boundary (r50 = BASELINE.json configs[1], demo = configs[0]) or
+# the head alone on backbone features (r50-head, ucn, crop)
+# ------------------------------------------------------------------------------------------------------------------
+FULL_MODEL = ("r50", "demo")
+HEAD_KIND = {"r50": "r50", "demo": "ucn", "r50-head": "r50", "ucn": "ucn", "crop": "crop"}
+METRICS = {
+    "r50": "images/sec MSMFormer forward 640x480 (R50 config: ResNet-50 backbone + MSDeformAttn pixel decoder + 9-layer "
+           "mean-shift decoder, 100 queries + instance tail)",
+    "demo": "images/sec MSMFormer forward 640x480 RGB-D single frame (UCN config: SEGNET RGB-D embedding + "
+            "SimpleBasePixelDecoder + 6-layer pretrained mean-shift decoder at full resolution + instance tail)",
+    "r50-head": METRIC,
+    "ucn": "images/sec MSMFormer head forward 640x480 (UCN RGB-D config: SimpleBasePixelDecoder + 6-layer "
+           "pretrained mean-shift decoder on the full-resolution 64-d embedding, 100 queries)",
+    "crop": "crops/sec MSMFormer head forward 224x224 (crop config: SimpleBasePixelDecoder + 8-layer "
+            "pretrained mean-shift decoder, 100 queries)"}
+
+
+def _bytes(tensors):
+    return sum(v.numel() * v.element_size() for v in tensors.values())
+
+
+def _kernel_shares(fn, top=12):
+    """Device time per kernel NAME over one eager pass of `fn`, from CUPTI activity records (torch.profiler): exact
+    kernel durations, no launch gaps and no duration filter. -> (total kernel ms, [(name, launches, ms, share)])."""
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+        agg = {}
+        for ev in prof.events():
+            if getattr(ev, "device_type", None) is not None and "cuda" in str(ev.device_type).lower():
+                name = ev.name
+                if name.startswith("Memcpy") or name.startswith("Memset"):
+                    continue
+                c, t = agg.get(name, (0, 0.0))
+                agg[name] = (c + 1, t + ev.device_time_total / 1e3 if hasattr(ev, "device_time_total") else t)
+        total = sum(t for _, t in agg.values())
+        if total <= 0:
+            return None
+        rows = sorted(((n, c, t, t / total) for n, (c, t) in agg.items()), key=lambda r: -r[2])[:top]
+        return total, rows
+    except Exception as e:  # profiling is evidence, not the measurement: never fail the bench on it
+        print(f"[bench] kernel shares unavailable: {e!r}", file=sys.stderr)
+        return None
+
+
+def _short(name):
+    name = name.replace("void ", "").replace("msm::", "")
+    return name[:96]
+
+
+def run_forward(args, rank, local_rank, world, dev, sharding, ops, workloads):
     from unseenobjectswithmeanshift_b200.graph import GraphedForward
+    kind = args.workload
+    full = kind in FULL_MODEL
+    hk = HEAD_KIND[kind]
+    B = args.batch if args.batch > 0 else (1 if kind == "demo" else PER_GPU_BATCH)
+    H, W = workloads.HEAD_CFG[hk]["height"], workloads.HEAD_CFG[hk]["width"]
+
+    if full:
+        from unseenobjectswithmeanshift_b200 import backbones
+        backbones.set_tf32(args.backbone_tf32)
+        model = workloads.build_model(kind).to(dev)
+        head = model.sem_seg_head
+        host_in = workloads.synthetic_images(kind, B, seed=rank, pin=True)
+
+        if args.tail == "instances":
+            def step(inp):   # forward(batched_inputs) of the reference: Instances fields of every image
+                outputs, _, padded, _ = model._head_outputs([inp])
+                from unseenobjectswithmeanshift_b200.meanshiftformer import instance_inference as ii
+                r = ii.instance_inference_batched(outputs["pred_logits"], outputs["pred_masks"], padded,
+                                                  model.test_topk_per_image)
+                return {k: r[k] for k in ("pred_masks", "pred_boxes", "scores", "pred_classes")}
+        else:
+            def step(inp):   # what the UOIS scripts consume: get_confident_instances + combine_masks, fused on the device
+                label_map, f = model.label_maps([inp])
+                return {"label_map": label_map, "scores": f["scores"], "pred_classes": f["pred_classes"],
+                        "pred_boxes": f["pred_boxes"], "instance_label": f["instance_label"]}
+    else:
+        model = None
+        head = workloads.build_head(hk).to(dev)
+        host_in = workloads.synthetic_features(hk, B, seed=rank, pin=True)
+
+        def step(feats):
+            out, _ = head(feats, H, W)
+            return {"pred_logits": out["pred_logits"], "pred_masks": out["pred_masks"],
+                    "aux_pred_masks": [a["pred_masks"] for a in out["aux_outputs"]]}
+    dev_in = {k: v.to(dev) for k, v in host_in.items()}
+    out_keys = [k for k in ("label_map", "scores", "pred_classes", "pred_boxes", "instance_label", "pred_masks",
+                            "pred_logits")]
     sampler = ClockSampler(local_rank)
+    parts_ms, shares = None, None
     with torch.no_grad():
         # ---------------- eager pass: launch count and per-op device time (CUDA events around every library call)
         for _ in range(args.warmup):
-            step(dev_feats)
+            step(dev_in)
         torch.cuda.synchronize()
         ops.reset_stats(timing=True)
         n_eager = 3
@@ -785,18 +889,39 @@ def main():
             # park the GPU for ~40 ms so the host enqueues the whole step ahead of it: the kernels then run
             # back to back and the event pairs measure kernel time, not launch gaps
             torch.cuda._sleep(int(0.04 * 1.9e9))
-            step(dev_feats)
+            step(dev_in)
             torch.cuda.synchronize()
         launches_per_step = ops.launches() // n_eager
         op_ms = {k: (c / n_eager, t / n_eager) for k, (c, t) in ops.op_times_ms().items()}
         op_groups = ops.op_groups()
         ops.reset_stats(timing=False)
+        if rank == 0 and not args.skip_profile:
+            shares = _kernel_shares(lambda: step(dev_in))
+        if full:   # where the step's time goes: backbone (cuDNN, outside the hot path) | head | tail, eager + events
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            acc = [0.0, 0.0, 0.0]
+            for _ in range(5):
+                torch.cuda._sleep(int(0.04 * 1.9e9))
+                ev[0].record()
+                if model.use_other_backbone:
+                    feats = model.pretrained_backbone(dev_in["image"])
+                else:
+                    emb = model.pretrained_backbone(dev_in["image"], None, dev_in.get("depth"))
+                    feats = {"res5": torch.nn.functional.normalize(emb, p=2, dim=1)}
+                ev[1].record()
+                outputs, _ = head(feats, H, W)
+                ev[2].record()
+                from unseenobjectswithmeanshift_b200.fcn import test_utils as tu
+                tu.label_map_from_outputs(outputs["pred_logits"], outputs["pred_masks"], (H, W), 20)
+                ev[3].record()
+                torch.cuda.synchronize()
+                for i in range(3):
+                    acc[i] += ev[i].elapsed_time(ev[i + 1]) / 5
+            parts_ms = {"backbone_cudnn": acc[0], "head": acc[1], "tail": acc[2], "how": "eager, CUDA events"}
 
-        # ---------------- the step as ONE CUDA graph (static input / output buffers)
-        # the graph replays on its static input buffers (device copies of dev_feats made once, resident in HBM);
-        # passing dev_feats again would put a 295 MB device-to-device copy inside every timed step
-        graphed = None if args.no_graph else GraphedForward(step, dev_feats, warmup=2)
-        runner = (lambda feats=None: step(dev_feats)) if graphed is None else (lambda feats=None: graphed(feats))
+        # ---------------- the step as ONE CUDA graph (static input / output buffers resident in HBM)
+        graphed = None if args.no_graph else GraphedForward(step, dev_in, warmup=2)
+        runner = (lambda inp=None: step(dev_in)) if graphed is None else (lambda inp=None: graphed(inp))
         for _ in range(args.warmup):
             runner()
         torch.cuda.synchronize()
@@ -814,15 +939,14 @@ def main():
         ms_dev = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
         launches = launches_per_step * args.steps
 
-        # ---------------- end to end: pinned host features in, predictions out, every step.
+        # ---------------- end to end: pinned host inputs in, results out, every step.
         # Three streams: H2D of step i+1 and D2H of step i-1 overlap the graph replay of step i (PCIe is full
         # duplex); device-side staging copies decouple the graph's static buffers from the transfers.
         out0 = runner()
-        out_keys = ("pred_logits", "pred_masks")
+        out_keys = [k for k in out_keys if k in out0]
         host_out = {k: torch.empty(out0[k].shape, dtype=out0[k].dtype).pin_memory() for k in out_keys}
-        h2d = sum(v.numel() * v.element_size() for v in host_feats.values())
-        d2h = sum(v.numel() * v.element_size() for v in host_out.values())
-        static_in = graphed.static_in if graphed is not None else dev_feats
+        h2d, d2h = _bytes(host_in), _bytes(host_out)
+        static_in = graphed.static_in if graphed is not None else dev_in
         stage_in = {k: torch.empty_like(v) for k, v in static_in.items()}
         stage_out = {k: torch.empty_like(out0[k]) for k in out_keys}
         s_main, s_h2d, s_d2h = torch.cuda.current_stream(), torch.cuda.Stream(), torch.cuda.Stream()
@@ -836,7 +960,7 @@ def main():
                 with torch.cuda.stream(s_h2d):
                     s_h2d.wait_event(ev_in_free)            # previous contents of stage_in consumed
                     for k in stage_in:
-                        stage_in[k].copy_(host_feats[k], non_blocking=True)
+                        stage_in[k].copy_(host_in[k], non_blocking=True)
                     ev_in_ready.record(s_h2d)
                 s_main.wait_event(ev_in_ready)
                 for k in static_in:
@@ -870,55 +994,75 @@ def main():
     total_images = B * world * args.steps
     value = total_images / (ms_dev / 1e3)
     e2e_value = None if args.skip_e2e else total_images / (ms_e2e / 1e3)
-
     if rank != 0:
         return
 
-    # ---------------- roofline of the dominant kernel of this library: the (kernel, shape) group with the
-    # largest device time per step; achieved = algorithmic bytes (or flops) of its launches / their duration
+    # ---------------- roofline. (1) `roofline`: the (kernel, shape) group of THIS library with the largest device
+    # time per step - every group is a candidate (no duration filter); durations are CUDA events around each library
+    # call on the launching stream (GPU parked first, so the pairs bracket kernel time), and the CUPTI kernel list of
+    # the same step (`kernel_shares`) is printed beside it so the choice can be checked against exact kernel times.
+    # (2) `roofline.step`: the whole step against both roofs - algorithmic bytes and 3 x FLOP (tensor passes of the
+    # split-precision products) of all library launches over ms_per_step.
     peaks = load_peaks()
+    ridge = peaks["bf16_tflops"] * 1e3 / peaks["hbm_gbs"]
     roofline = None
+    step_ms = ms_dev / args.steps
     if op_groups:
-        # candidates: launches of >= 40 us on average - below that the event pairs of an eager pass mostly measure
-        # launch gaps, not kernel time (the graph replay that `value` times has no such gaps)
-        big = {k: v for k, v in op_groups.items() if v["ms"] / v["count"] >= 0.040} or op_groups
-        (tag, sig), g = max(big.items(), key=lambda kv: kv[1]["ms"])
+        (tag, sig), g = max(op_groups.items(), key=lambda kv: kv[1]["ms"])
         per = g["count"] / n_eager
         avg_ms = g["ms"] / g["count"]
         gbs = g["bytes"] / g["ms"] / 1e6
         tfs = g["flops"] / g["ms"] / 1e9
-        # HBM-bound unless the arithmetic intensity (x3 tensor passes of the bf16 split) exceeds the ridge
-        ridge = peaks["bf16_tflops"] * 1e3 / peaks["hbm_gbs"]
         tensor_bound = g["bytes"] > 0 and 3.0 * g["flops"] / g["bytes"] > ridge
-        # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full`
-        # captures of these kernels at these shapes (profiles/r01_ncu_kernels.md); None when no capture exists
-        ncu_traffic = {("mask_logits", "B8 Q100 C256 HW19200"): 186.5e6,
-                       ("ms_deform_attn_forward", "fused N8 S6300 M8 D8 Lq6300"): 76.7e6,
-                       ("ffn", "ffn+LN M50400 D64 F1024"): 13.5e6,
-                       ("linear", "M38400 N768 K256"): None}
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of these
+        # kernels at these shapes (profiles/): a constant of an earlier run, NOT measured by this process
+        traffic_from_profile = {("mask_logits", "B8 Q100 C256 HW19200"): 186.5e6,
+                                ("ms_deform_attn_forward", "fused N8 S6300 M8 D8 Lq6300"): 76.7e6,
+                                ("ffn", "ffn+LN M50400 D64 F1024"): 13.5e6}
         roofline = {"kernel": tag, "shape": sig, "launches_per_step": per, "avg_launch_ms": avg_ms,
-                    "share_of_step": (g["ms"] / n_eager) / (ms_dev / args.steps),
+                    "share_of_step": (g["ms"] / n_eager) / step_ms,
                     "algorithmic_bytes_per_launch": g["bytes"] / g["count"],
-                    "algorithmic_flops_per_launch": g["flops"] / g["count"], "traffic": ncu_traffic.get((tag, sig)),
-                    "timing": "CUDA events around each library call, eager pass of the same step (same stream)",
+                    "algorithmic_flops_per_launch": g["flops"] / g["count"], "traffic": None,
+                    "traffic_from_profile": traffic_from_profile.get((tag, sig)),
+                    "timing": "CUDA events around each library call, eager pass of the same step (same stream); "
+                              "largest group by time, no duration filter",
                     "peak_source": peaks["source"]}
         if tensor_bound:
             roofline.update({"bound": "tensor", "achieved": 3.0 * tfs, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                              "frac": 3.0 * tfs / peaks["bf16_tflops"],
-                             "note": "bf16 tensor passes issued (3 per fp32-grade product)"})
+                             "note": "16-bit tensor passes issued (3 per fp32-grade product)"})
         else:
             roofline.update({"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "frac": gbs / peaks["hbm_gbs"]})
-        top = sorted(op_groups.items(), key=lambda kv: -kv[1]["ms"])[:8]
+        top = sorted(op_groups.items(), key=lambda kv: -kv[1]["ms"])[:10]
         roofline["top_groups"] = [{"kernel": t, "shape": sg, "launches_per_step": v["count"] / n_eager,
                                    "ms_per_step": v["ms"] / n_eager,
                                    "GBps": v["bytes"] / v["ms"] / 1e6 if v["ms"] else None,
                                    "TFLOPps": v["flops"] / v["ms"] / 1e9 if v["ms"] else None} for (t, sg), v in top]
+        lib_bytes = sum(v["bytes"] for v in op_groups.values()) / n_eager
+        lib_flops = sum(v["flops"] for v in op_groups.values()) / n_eager
+        lib_ms = sum(v["ms"] for v in op_groups.values()) / n_eager
+        bb_flops = workloads.backbone_flops_per_image(kind) * B if full else 0.0
+        roofline["step"] = {
+            "ms_per_step": step_ms, "library_ms_per_step_eager_events": lib_ms,
+            "library_algorithmic_bytes_per_step": lib_bytes, "library_flops_per_step": lib_flops,
+            "backbone_flops_per_step": bb_flops,
+            "hbm_GBps": lib_bytes / step_ms / 1e6, "hbm_frac": lib_bytes / step_ms / 1e6 / peaks["hbm_gbs"],
+            "tensor_TFLOPps_x3": 3.0 * lib_flops / step_ms / 1e9,
+            "tensor_frac": 3.0 * lib_flops / step_ms / 1e9 / peaks["bf16_tflops"],
+            "note": "library launches only (the cuDNN backbone is fp32 CUDA-core work); a step far below both roofs "
+                    "is latency / launch bound"}
+    if shares is not None:
+        roofline = roofline or {}
+        roofline["kernel_shares"] = {"source": "CUPTI kernel records of one eager step (torch.profiler)",
+                                     "kernel_ms_per_step": shares[0],
+                                     "top": [{"kernel": _short(n), "launches": c, "ms": t, "share": sh}
+                                             for n, c, t, sh in shares[1]]}
     op_summary = {k: {"calls_per_step": c, "ms_per_step": t} for k, (c, t) in op_ms.items()}
 
     # ---------------- vMF attention TFLOP/s (second half of BASELINE.json's metric): the attention core alone at the
-    # full-resolution key grid of the UCN config (1 image, 8 heads, 100 queries, 307200 keys, hd 32, masked),
-    # L2 flushed between launches, CUDA events on the launching stream
+    # full-resolution key grid of the UCN config (1 image, 8 heads, 100 queries, 307200 keys, hd 32, bit mask), K / V
+    # as the operand images the decoder's projections write, L2 flushed between launches, CUDA events
     vmf = None
     if not args.no_cpu_baseline or args.vmf_tflops:
         with torch.no_grad():
@@ -930,71 +1074,136 @@ def main():
             bits = torch.randint(-2 ** 31, 2 ** 31 - 1, (1, Qn, Sk // 32), device=dev, dtype=torch.int32)
             ro = torch.ones(1, Qn, device=dev, dtype=torch.int32)
             hv = lambda t: t.unflatten(-1, (Hh, hd)).permute(0, 2, 1, 3)  # noqa: E731
+            kvp = ops.pack_kv(hv(k), hv(v))
             flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
             for _ in range(3):
-                ops.vmf_attention(hv(q), hv(k), hv(v), blocked_bits=bits, row_open=ro)
+                ops.vmf_attention_packed(hv(q), kvp, blocked_bits=bits, row_open=ro)
             ts = []
             for _ in range(10):
                 flush.zero_()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
-                ops.vmf_attention(hv(q), hv(k), hv(v), blocked_bits=bits, row_open=ro)
+                ops.vmf_attention_packed(hv(q), kvp, blocked_bits=bits, row_open=ro)
                 b.record()
                 torch.cuda.synchronize()
                 ts.append(a.elapsed_time(b))
             t_ms = statistics.median(ts)
             fl = 4.0 * Hh * Qn * Sk * hd
-            vmf = {"shape": f"B1 H{Hh} Q{Qn} S{Sk} hd{hd} masked", "ms": t_ms, "tflops_useful": fl / t_ms / 1e9,
-                   "tflops_tensor_passes": 3 * fl / t_ms / 1e9,
+            vmf = {"shape": f"B1 H{Hh} Q{Qn} S{Sk} hd{hd} masked, packed K/V images (TMA bulk stream)", "ms": t_ms,
+                   "tflops_useful": fl / t_ms / 1e9, "tflops_tensor_passes": 3 * fl / t_ms / 1e9,
                    "frac_of_bf16_peak": 3 * fl / t_ms / 1e9 / peaks["bf16_tflops"],
-                   "GBps": 4.0 * 2 * Sk * Hh * hd / t_ms / 1e6, "frac_of_hbm_peak": 4.0 * 2 * Sk * Hh * hd / t_ms / 1e6 / peaks["hbm_gbs"]}
-            del q, k, v, bits, flush
+                   "GBps": 4.0 * 2 * Sk * Hh * hd / t_ms / 1e6,
+                   "frac_of_hbm_peak": 4.0 * 2 * Sk * Hh * hd / t_ms / 1e6 / peaks["hbm_gbs"]}
+            del q, k, v, bits, flush, kvp
 
-    # ---------------- CPU baseline (oracle port) on a bounded sample, rank 0, N == 1 only
+    # ---------------- CPU baseline on a bounded sample, rank 0, N == 1 only: the REFERENCE's own modules when the
+    # vendored copy is present (baseline/_ref), else the oracle port
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        sd = {k: v.detach().cpu() for k, v in head.state_dict().items()}
-        sb = 2
-        feats = {k: v[:sb].clone() for k, v in host_feats.items()}
-        t0 = time.perf_counter()
-        ref = cpu_oracle_step(sd, feats, kind)
-        dt = time.perf_counter() - t0
-        with torch.no_grad():
-            got = step({k: v[:sb].to(dev) for k, v in feats.items()})
-        pk = ref["pred_masks"].abs().max().item()
-        err = (got["pred_masks"].cpu() - ref["pred_masks"]).abs().max().item() / pk
-        agree = (got["pred_masks"].cpu().argmax(1) == ref["pred_masks"].argmax(1)).float().mean().item()
-        cpu_baseline = {"value": sb / dt, "unit": "images/s", "cores": cores, "kind": "port",
-                        "sample": f"1 run x {sb} images of the same head workload (oracle, fp32, {cores} threads)",
-                        "parity_on_sample": {"pred_masks_max_err_rel_to_peak": err, "argmax_label_agreement": agree}}
+        cpu_baseline = cpu_baseline_leg(kind, model if full else head, host_in, step, dev, full)
 
-    metric = METRIC if kind == "r50" else {
-        "ucn": "images/sec MSMFormer head forward 640x480 (UCN RGB-D config: SimpleBasePixelDecoder + 6-layer "
-               "pretrained mean-shift decoder on the full-resolution 64-d embedding, 100 queries)",
-        "crop": "crops/sec MSMFormer head forward 224x224 (crop config: SimpleBasePixelDecoder + 8-layer "
-                "pretrained mean-shift decoder, 100 queries)"}[kind]
-    line = {"metric": metric, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{kind}-head 640x480 batch {B}/GPU, 100 queries, "
-                                   f"{workloads.HEAD_CFG[kind]['dec_layers']} decoder layers",
-                       "launch": "eager" if args.no_graph else "one CUDA graph per step",
-                       "global_batch": B * world, "parallelism": f"replicas x{world} (batch-sharded, no collective)",
-                       "l2_policy": f"inputs_exceed_l2 ({h2d / 1e6:.0f} MB of backbone features per step; every layer "
-                                    "streams the mask features and writes a fresh logits tensor)",
-                       "backbone": "excluded: the cuDNN backbone (ResNet-50 / UCN) is outside the hot path "
-                                   "(SURVEY.md §8)",
-                       "gflop_per_image": workloads.head_flops_per_image(kind) / 1e9},
-            "clocks": clocks,
+    hk_cfg = workloads.HEAD_CFG[hk]
+    config = {"workload": (f"{kind} 640x480 batch {B}/GPU: " if kind != "crop" else f"crop 224x224 batch {B}/GPU: ")
+                          + ("whole model, images in -> label maps + instance fields out" if full and args.tail != "instances"
+                             else "whole model, images in -> Instances fields out" if full
+                             else "segmentation head on backbone features"),
+              "queries": 100, "decoder_layers": hk_cfg["dec_layers"],
+              "launch": "eager" if args.no_graph else "one CUDA graph per step",
+              "global_batch": B * world, "parallelism": f"replicas x{world} (batch-sharded, no collective)",
+              "l2_policy": "inputs_exceed_l2 (every decoder layer streams the mask features - 157 MB at batch 8 - and "
+                           "writes a fresh logits tensor; backbone activations exceed L2)",
+              "backbone": (f"included: torchvision ResNet-50, cuDNN {'TF32' if args.backbone_tf32 else 'fp32 (TF32 off)'}, channels_last" if kind == "r50"
+                           else f"included: SEGNET RGB-D (two ResNet34-8s streams), cuDNN {'TF32' if args.backbone_tf32 else 'fp32 (TF32 off)'}" if kind == "demo"
+                           else "excluded: head-only workload on synthetic backbone features"),
+              "gflop_per_image": {"head": workloads.head_flops_per_image(hk) / 1e9,
+                                  "backbone": workloads.backbone_flops_per_image(kind) / 1e9 if full else 0.0}}
+    line = {"metric": METRICS[kind], "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps,
-                    "how": "pinned host features -> device every step, pred_logits + pred_masks -> pinned host every "
-                           "step; transfers of neighbouring steps overlap the graph replay on separate streams"},
-            "gpu_launches": launches,
+                    "how": "pinned host inputs -> device every step, results -> pinned host every step; transfers of "
+                           "neighbouring steps overlap the graph replay on separate streams"},
+            "gpu_launches": launches, "parts_ms": parts_ms,
             "roofline": roofline, "vmf_attention": vmf, "op_ms": op_summary, "cpu_baseline": cpu_baseline}
     emit(line)
+
+
+def _cpu_head(kind_head, sd):
+    """-> (callable(features) -> (outputs, mask_features), kind): the reference's own head modules when available."""
+    from unseenobjectswithmeanshift_b200 import workloads
+    try:
+        from oracle import ref_models
+        if ref_models.reference_root() is not None:
+            ref_head = ref_models.build_reference_head(kind_head, sd)
+            return (lambda feats: ref_head(feats, workloads.HEAD_CFG[kind_head]["height"],
+                                           workloads.HEAD_CFG[kind_head]["width"])), "reference"
+    except Exception as e:
+        print(f"[bench] reference modules unavailable ({e!r}); timing the oracle port", file=sys.stderr)
+    from oracle import head as ohead
+    return (lambda feats: ohead.head_forward(sd, feats, **workloads.oracle_kwargs(kind_head))), "port"
+
+
+def _cpu_model(kind, full, seed=0):
+    """CPU arm for workload `kind`: -> (step(inputs) -> outputs dict with pred_masks, kind_of_baseline, note)."""
+    from oracle import head as ohead
+    from unseenobjectswithmeanshift_b200 import workloads
+    hk = HEAD_KIND[kind]
+    cfg = workloads.HEAD_CFG[hk]
+    if full:
+        model = workloads.build_model(kind, seed)   # same seeds -> same weights as the GPU arm
+        from unseenobjectswithmeanshift_b200 import backbones
+        bb_name = workloads.MODEL_CFG[kind]["backbone"]
+        backbone = (backbones.ResNet50Features(seed=seed, fold_bn=False) if bb_name == "ResNet50Features"
+                    else model.pretrained_backbone)   # plain eval-mode BatchNorm on the CPU side
+        sd = {k: v.detach() for k, v in model.sem_seg_head.state_dict().items()}
+        head_fn, which = _cpu_head(hk, sd)
+
+        def step(inp):
+            if workloads.MODEL_CFG[kind]["use_other_backbone"]:
+                feats = backbone(inp["image"])
+            else:
+                feats = {"res5": torch.nn.functional.normalize(backbone(inp["image"], None, inp.get("depth")), p=2, dim=1)}
+            out, _ = head_fn(feats)
+            ohead.eval_tail(out, (cfg["height"], cfg["width"]), 2, 20)   # upsample + instance_inference (restated)
+            return out, feats
+        note = ("reference modules (head) + the same torchvision/torch backbone on CPU + restated eval tail"
+                if which == "reference" else "oracle port of the head + backbone + restated eval tail")
+        return step, which, note
+    head = workloads.build_head(hk, seed)
+    sd = {k: v.detach() for k, v in head.state_dict().items()}
+    head_fn, which = _cpu_head(hk, sd)
+    return (lambda feats: (head_fn(feats)[0], feats)), which, (
+        "reference modules imported from baseline/_ref" if which == "reference" else "oracle port")
+
+
+def cpu_baseline_leg(kind, gpu_module, host_in, gpu_step, dev, full):
+    from unseenobjectswithmeanshift_b200 import workloads
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    hk = HEAD_KIND[kind]
+    sb = min(2, next(iter(host_in.values())).shape[0])
+    sample = {k: v[:sb].clone() for k, v in host_in.items()}
+    cpu_step, which, note = _cpu_model(kind, full)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        ref, feats = cpu_step(sample)
+        dt = time.perf_counter() - t0
+        # parity of the hot path on the sample: the GPU head on the SAME backbone features the CPU arm saw
+        head = gpu_module.sem_seg_head if full else gpu_module
+        got, _ = head({k: v.to(dev) for k, v in feats.items()}, workloads.HEAD_CFG[hk]["height"],
+                      workloads.HEAD_CFG[hk]["width"])
+    pk = ref["pred_masks"].abs().max().item()
+    err = (got["pred_masks"].cpu() - ref["pred_masks"]).abs().max().item() / pk
+    agree = (got["pred_masks"].cpu().argmax(1) == ref["pred_masks"].argmax(1)).float().mean().item()
+    first = (got["aux_outputs"][0]["pred_masks"].cpu() - ref["aux_outputs"][0]["pred_masks"]).abs().max().item() / \
+        ref["aux_outputs"][0]["pred_masks"].abs().max().item()
+    return {"value": sb / dt, "unit": "images/s", "cores": cores, "kind": which,
+            "sample": f"1 run x {sb} image(s) of the same workload ({note}; fp32, {cores} threads)",
+            "parity_on_sample": {"pred_masks_max_err_rel_to_peak": err, "argmax_label_agreement": agree,
+                                 "first_prediction_max_err_rel_to_peak": first,
+                                 "note": "GPU head vs the CPU arm on identical backbone features; later layers "
+                                         "inherit mask-bit flips (DESIGN.md section 2)"}}
 
 
 if __name__ == "__main__":

@@ -1,0 +1,174 @@
+"""Backbones that FEED the hot path (out of scope as kernels - plain cuDNN work, they stay
+PyTorch). They exist so that the benchmarks and the META_ARCH wrappers can run at the reference's real API boundary
+- images in, instances out (``PretrainedMeanShiftMaskFormer.forward(batched_inputs)``,
+pretrained_meanshiftformer_model.py:244-378) - instead of stopping at backbone features.
+
+``ResNet50Features``   config #2 (configs/tabletop_pretrained_ResNet50.yaml: ``build_resnet_backbone``, DEPTH 50,
+                       STRIDE_IN_1X1 False, torchvision-format weights, FrozenBN): that IS torchvision's ResNet-50 in
+                       eval mode, so torchvision's module is used (third-party code on both sides, like detectron2's
+                       builder in the reference). Returns {"res2".."res5"} with strides 4/8/16/32, 256..2048 channels.
+``SegnetEmbedding``    configs #1 / #3 (lib/networks/SEG.py:88-120 ``SEGNET`` with INPUT RGBD, FUSION_TYPE add:
+                       two ResNet34-8s streams, RGB and XYZ, summed; lib/networks/resnet_dilated.py:287-327: dilated
+                       ResNet-34 at output stride 8, 1x1 classifier to 64 channels, bilinear upsampling
+                       (``upsample_bilinear`` = align_corners True) to the input size). Restated with torchvision's
+                       BasicBlock ResNet-34 and ``replace_stride_with_dilation``-style surgery done by hand (BasicBlock
+                       refuses dilation in torchvision). Random init; no checkpoint exists in the container.
+Both run channels_last through cuDNN in fp32 (TF32 stays off, precision.py: a TF32 backbone changes the features by
+1e-3, which the decoder's hard mask thresholds amplify - parity with the fp32 reference would be lost).
+"""
+import contextlib
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+_TF32 = False
+
+
+def set_tf32(flag):
+    """cuDNN math of the backbones: False (default) = fp32, the reference's CPU arithmetic and what the parity claims of
+    this package are stated against; True = PyTorch's own default on Ampere and later (TF32 tensor cores), i.e. what the
+    reference's stock code does on a GPU."""
+    global _TF32
+    _TF32 = bool(flag)
+
+
+@contextlib.contextmanager
+def _conv_math():
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = _TF32
+    try:
+        yield
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+
+def _fold_bn(conv, bn):
+    """eval-mode BatchNorm folded into the preceding convolution (same arithmetic up to fp32 rounding)."""
+    w = conv.weight * (bn.weight / torch.sqrt(bn.running_var + bn.eps)).reshape(-1, 1, 1, 1)
+    b = bn.bias - bn.running_mean * bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    if conv.bias is not None:
+        b = b + conv.bias * bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    out = nn.Conv2d(conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding, conv.dilation,
+                    conv.groups, bias=True)
+    out.weight.data.copy_(w)
+    out.bias.data.copy_(b)
+    return out
+
+
+class ResNet50Features(nn.Module):
+    """torchvision ResNet-50 trunk -> {"res2","res3","res4","res5"} (detectron2 naming). ``fold_bn``: inference-time
+    folding of the frozen BatchNorms into the convolutions (halves the elementwise launches; off = the plain module)."""
+
+    size_divisibility = 32
+
+    def __init__(self, seed=0, fold_bn=True):
+        super().__init__()
+        import torchvision
+        g = torch.random.get_rng_state()
+        torch.manual_seed(5000 + seed)
+        net = torchvision.models.resnet50(weights=None)
+        torch.random.set_rng_state(g)
+        net.eval()
+        if fold_bn:
+            with torch.no_grad():
+                net.conv1, net.bn1 = _fold_bn(net.conv1, net.bn1), nn.Identity()
+                for layer in (net.layer1, net.layer2, net.layer3, net.layer4):
+                    for blk in layer:
+                        blk.conv1, blk.bn1 = _fold_bn(blk.conv1, blk.bn1), nn.Identity()
+                        blk.conv2, blk.bn2 = _fold_bn(blk.conv2, blk.bn2), nn.Identity()
+                        blk.conv3, blk.bn3 = _fold_bn(blk.conv3, blk.bn3), nn.Identity()
+                        if blk.downsample is not None:
+                            blk.downsample = nn.Sequential(_fold_bn(blk.downsample[0], blk.downsample[1]))
+        self.stem = nn.Sequential(net.conv1, net.bn1, net.relu, net.maxpool)
+        self.res2, self.res3, self.res4, self.res5 = net.layer1, net.layer2, net.layer3, net.layer4
+        for p in self.parameters():
+            p.requires_grad_(False)
+        self.eval()
+        self.to(memory_format=torch.channels_last)   # weights converted ONCE (else cuDNN re-lays them out per call)
+
+    def train(self, mode=True):  # FrozenBN semantics: never leaves eval mode
+        return super().train(False)
+
+    def forward(self, x):
+        x = x.contiguous(memory_format=torch.channels_last)
+        with _conv_math():
+            x = self.stem(x)
+            out = {}
+            for name in ("res2", "res3", "res4", "res5"):
+                x = getattr(self, name)(x)
+                out[name] = x.contiguous()  # the head's kernels take NCHW-contiguous fp32
+        return out
+
+
+class _BasicBlock(nn.Module):
+    """ResNet BasicBlock with dilation (lib/networks/resnet.py's block; torchvision's refuses dilation > 1)."""
+
+    def __init__(self, cin, cout, stride=1, dilation=1, downsample=None):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, stride, dilation, dilation, bias=False)
+        self.bn1 = nn.BatchNorm2d(cout)
+        self.conv2 = nn.Conv2d(cout, cout, 3, 1, dilation, dilation, bias=False)
+        self.bn2 = nn.BatchNorm2d(cout)
+        self.downsample = downsample
+
+    def forward(self, x):
+        idt = x if self.downsample is None else self.downsample(x)
+        y = F.relu(self.bn1(self.conv1(x)))
+        y = self.bn2(self.conv2(y))
+        return F.relu(y + idt)
+
+
+class _Resnet34_8s(nn.Module):
+    """lib/networks/resnet_dilated.py:287-327: ResNet-34, output stride 8 (layer3 / layer4 dilated 2 / 4 instead of
+    strided), fully-convolutional 1x1 classifier to ``num_classes`` channels, bilinear upsampling to the input size."""
+
+    def __init__(self, num_classes=64):
+        super().__init__()
+        self.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.maxpool = nn.MaxPool2d(3, 2, 1)
+        cfg = [(64, 3, 1, 1), (128, 4, 2, 1), (256, 6, 1, 2), (512, 3, 1, 4)]  # (planes, blocks, stride, dilation)
+        layers, cin = [], 64
+        for planes, blocks, stride, dil in cfg:
+            ds = None
+            if stride != 1 or cin != planes:
+                ds = nn.Sequential(nn.Conv2d(cin, planes, 1, stride, bias=False), nn.BatchNorm2d(planes))
+            blk = [_BasicBlock(cin, planes, stride, dil, ds)]
+            blk += [_BasicBlock(planes, planes, 1, dil) for _ in range(blocks - 1)]
+            layers.append(nn.Sequential(*blk))
+            cin = planes
+        self.layer1, self.layer2, self.layer3, self.layer4 = layers
+        self.fc = nn.Conv2d(512, num_classes, 1)
+
+    def forward(self, x):
+        size = x.shape[-2:]
+        x = self.maxpool(F.relu(self.bn1(self.conv1(x))))
+        x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
+        x = self.fc(x)
+        return F.interpolate(x, size=size, mode="bilinear", align_corners=True)  # upsample_bilinear (:325)
+
+
+class SegnetEmbedding(nn.Module):
+    """SEGNET.forward(img, label, depth) for INPUT RGBD / FUSION_TYPE add (lib/networks/SEG.py:88-120): two ResNet34-8s
+    streams, features summed; -> [B,64,H,W] (the META_ARCH wrapper L2-normalises it, :298)."""
+
+    def __init__(self, seed=0, use_depth=True):
+        super().__init__()
+        g = torch.random.get_rng_state()
+        torch.manual_seed(6000 + seed)
+        self.fcn = _Resnet34_8s(64)
+        self.fcn_depth = _Resnet34_8s(64) if use_depth else None
+        torch.random.set_rng_state(g)
+        for p in self.parameters():
+            p.requires_grad_(False)
+        self.eval()
+        self.to(memory_format=torch.channels_last)
+
+    def forward(self, img, label=None, depth=None):
+        img = img.contiguous(memory_format=torch.channels_last)
+        with _conv_math():
+            f = self.fcn(img)
+            if self.fcn_depth is not None and depth is not None:
+                f = f + self.fcn_depth(depth.contiguous(memory_format=torch.channels_last))
+        return f.contiguous()

@@ -1235,8 +1235,22 @@ def _work_vmf_bwd(q, k, v, out, grad_out, den, **kw):
 
 
 vmf_attention_bwd = _instrument("vmf_attention_bwd", 2, _work_vmf_bwd)(vmf_attention_bwd)
-linear_packed_kv = _instrument("linear", 1)(linear_packed_kv)
-vmf_attention_packed = _instrument("vmf_attention", 2)(vmf_attention_packed)
+def _work_linear_packed(x, weight, bias, images, batch, num_keys, channels, which):
+    N, K = weight.shape
+    M = batch * num_keys
+    # reads the fp32 rows, writes 16-bit hi + lo operand images (4 bytes per element, like fp32 rows)
+    return f"{'V' if which else 'K'}-images M{M} N{N} K{K}", 4.0 * (M * K + M * N) + 4.0 * N * K, 2.0 * M * N * K
+
+
+def _work_vmf_packed(q, kv, **kw):
+    B, H, Nq, hd = q.shape
+    Ns = kv.num_keys
+    by = 4.0 * B * H * hd * (2 * Ns + 2 * Nq) + (B * Nq * Ns / 8.0 if kw.get("blocked_bits") is not None else 0)
+    return f"packed B{B} H{H} Q{Nq} S{Ns} hd{hd}", by, 4.0 * B * H * Nq * Ns * hd
+
+
+linear_packed_kv = _instrument("linear", 1, _work_linear_packed)(linear_packed_kv)
+vmf_attention_packed = _instrument("vmf_attention", 2, _work_vmf_packed)(vmf_attention_packed)
 mask_logits = _instrument("mask_logits", 1, _work_mask)(mask_logits)
 mask_to_attn_bits = _instrument("mask_to_attn_bits", 1, _work_bits)(mask_to_attn_bits)  # one kernel, no memset
 linear = _instrument("linear", 1, _work_linear)(linear)

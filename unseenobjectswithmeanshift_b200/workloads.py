@@ -73,6 +73,57 @@ def synthetic_features(kind, batch, seed=0, pin=False):
     return feats
 
 
+MODEL_CFG = {
+    # BASELINE.json config #2: R50 backbone (RGB, USE_OTHER_BACKBONE) + r50 head, 640x480
+    "r50": dict(head="r50", backbone="ResNet50Features", use_depth=False, use_other_backbone=True),
+    # config #1 / #3 stage 1: SEGNET RGB-D embedding (two ResNet34-8s streams, fusion add) + ucn head, 640x480
+    "demo": dict(head="ucn", backbone="SegnetEmbedding", use_depth=True, use_other_backbone=False),
+}
+
+
+def build_model(kind, seed=0):
+    """-> PretrainedMeanShiftMaskFormer (CPU, eval): backbone + head + eval tail behind the reference's META_ARCH API
+    (pretrained_meanshiftformer_model.py:244-378), random-init by the modules' own initialisers under ``seed``."""
+    from . import backbones
+    from .meanshiftformer import PretrainedMeanShiftMaskFormer
+    cfg = MODEL_CFG[kind]
+    backbone = getattr(backbones, cfg["backbone"])(seed=seed)
+    return PretrainedMeanShiftMaskFormer(
+        backbone=backbone, sem_seg_head=build_head(cfg["head"], seed), criterion=None, num_queries=100,
+        object_mask_threshold=0.8, overlap_threshold=0.8, metadata=None, size_divisibility=32,
+        sem_seg_postprocess_before_inference=True, pixel_mean=[0.0, 0.0, 0.0], pixel_std=[1.0, 1.0, 1.0],
+        semantic_on=False, panoptic_on=False, instance_on=True, test_topk_per_image=20, use_depth=cfg["use_depth"],
+        use_other_backbone=cfg["use_other_backbone"]).eval()
+
+
+def synthetic_images(kind, batch, seed=0, pin=False):
+    """Model inputs for ``batch`` frames as CPU tensors: {"image": [B,3,H,W]} (already mean / std normalised - the
+    Pretrained* META_ARCH does not normalise) and for the RGB-D model {"depth": [B,3,H,W]} XYZ metres
+    with 5 % invalid (zero) pixels."""
+    cfg = HEAD_CFG[MODEL_CFG[kind]["head"]]
+    g = torch.Generator().manual_seed(8000 + seed)
+    H, W = cfg["height"], cfg["width"]
+    if MODEL_CFG[kind]["use_depth"]:
+        out = {"image": torch.rand(batch, 3, H, W, generator=g) - 0.5}
+        z = torch.rand(batch, 1, H, W, generator=g) * 1.2 + 0.3
+        xy = (torch.rand(batch, 2, H, W, generator=g) - 0.5) * z
+        out["depth"] = torch.cat([xy, z], 1) * (torch.rand(batch, 1, H, W, generator=g) > 0.05)
+    else:
+        out = {"image": torch.randn(batch, 3, H, W, generator=g)}
+    if pin:
+        out = {k: v.pin_memory() for k, v in out.items()}
+    return out
+
+
+def backbone_flops_per_image(kind):
+    """Algorithmic FLOP (2*MAC) of the backbone per 640x480 frame, for reporting: torchvision ResNet-50 4.09 GMAC at
+    224x224; ResNet-34 at output stride 8 (layer3 / layer4 keep the 1/8 grid) 17.33 GMAC."""
+    px = 480 * 640 / (224.0 * 224.0)
+    if kind == "r50":
+        return 2.0 * 4.09e9 * px
+    return 2.0 * 2 * 17.33e9 * px   # two ResNet34-8s streams (conv MACs counted with forward hooks: 17.33 GMAC at 224x224)
+
+
 def oracle_kwargs(kind):
     cfg = HEAD_CFG[kind]
     kw = dict(pixel_decoder=cfg["pixel_decoder"], num_heads=8, dec_layers=cfg["dec_layers"])
