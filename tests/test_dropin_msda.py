@@ -92,12 +92,12 @@ def test_dropin_forward_backward_vs_oracle():
     value, sh, lsi, loc, w = _case()
     v, l_, w_ = value.cuda(), loc.cuda(), w.cuda()
     out = m.ms_deform_attn_forward(v, sh.cuda(), lsi.cuda(), l_, w_, 128)
-    want = opd.ms_deform_attn_core(value.double(), sh, loc.double(), w.double())
+    want = opd.ms_deform_attn_core(value.double(), sh, lsi, loc.double(), w.double())
     assert out.shape == (2, 37, 64)
     assert (out.cpu().double() - want).abs().max().item() < 1e-6
     go = torch.randn(2, 37, 64, generator=torch.Generator().manual_seed(1))
     vd, ld, wd = (t.double().requires_grad_(True) for t in (value, loc, w))
-    opd.ms_deform_attn_core(vd, sh, ld, wd).backward(go.double())
+    opd.ms_deform_attn_core(vd, sh, lsi, ld, wd).backward(go.double())
     gv, gl, ga = m.ms_deform_attn_backward(v, sh.cuda(), lsi.cuda(), l_, w_, go.cuda(), 128)
     for got, ref in ((gv, vd.grad), (gl, ld.grad), (ga, wd.grad)):
         scale = max(ref.abs().max().item(), 1e-12)

@@ -272,3 +272,40 @@ def test_attention_shape_sweep_vs_fp64(seed):
     if hd == 32:
         got = ops.vmf_attention_packed(q4, ops.pack_kv(k4, v4), blocked_bits=bits, row_open=ro)
         assert (got.double() - ref).abs().max().item() < 1e-4, ("packed", B, H, Qn, S, hd, masked)
+
+
+# ----------------------------------------------------------------------------- a6, narrow heads
+@pytest.mark.parametrize("hw", [(15, 20), (60, 80), (224, 224), (7, 5)])
+def test_position_embedding_sine_table_vs_oracle(hw):
+    """SURVEY 8 row a6 directly: the cached separable [S, C] table (and the reference-shaped forward) against the
+    oracle's cumsum formulation of position_encoding.py:29-52, normalize=True, scale 2 pi."""
+    from unseenobjectswithmeanshift_b200.meanshiftformer.modeling.transformer_decoder.position_encoding import \
+        PositionEmbeddingSine
+    h, w = hw
+    pe = PositionEmbeddingSine(128, normalize=True)
+    want = odec.position_embedding_sine(2, h, w, 128)                       # [B, 256, h, w]
+    got = pe(torch.zeros(2, 3, h, w, device="cuda")).cpu()
+    tab = pe.table(h, w, torch.device("cuda")).cpu()                        # [h*w, 256]
+    assert got.shape == want.shape
+    # sin / cos of arguments up to 2 pi: the device's and the host's libm agree to a few ulp
+    assert (got - want).abs().max().item() < 2e-6
+    assert (tab - want[0].flatten(1).t()).abs().max().item() < 2e-6
+
+
+def test_narrow_head_runs_in_the_library_gemm():
+    """The 3-way class head (N = K + 1 = 3): zero-padded to 32 columns, same tensor-core kernel, no cuBLAS."""
+    from unseenobjectswithmeanshift_b200 import ops
+    g = _rng(9)
+    x = torch.randn(8, 100, 256, device="cuda", generator=g)
+    w = torch.randn(3, 256, device="cuda", generator=g) / 16
+    b = torch.randn(3, device="cuda", generator=g)
+    ops.reset_stats()
+    y = ops.dense(x, w, b)
+    assert ops.launches() == 1 and y.shape == (8, 100, 3)
+    ref = x.double() @ w.double().t() + b.double()
+    assert (y.double() - ref).abs().max().item() / ref.abs().max().item() < 2e-5
+    with torch.no_grad():
+        w.mul_(2.0)   # in-place edit: the padded copy must follow
+    y2 = ops.dense(x, w, b)
+    ref2 = x.double() @ w.double().t() + b.double()
+    assert (y2.double() - ref2).abs().max().item() / ref2.abs().max().item() < 2e-5

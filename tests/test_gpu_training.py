@@ -239,3 +239,41 @@ def test_small_attention_kernel_vs_shipped(msm, B, H, Q, S, masked):
                                         return_den=True, save_norm=True)
     assert (got - want).abs().max().item() < 2e-5
     assert ((gden - wden).abs() / wden.abs().clamp_min(1e-30)).max().item() < 1e-4
+
+
+def test_eval_after_train_step_sees_the_new_weights():
+    """AdamW(fused=True) updates parameters in place WITHOUT bumping tensor._version, and every
+    inference-side cache of derived weights (prepared 16-bit copies, concatenated K/V weights, row-bias tables, the 3x3
+    repack) was keyed on (address, _version) only. eval -> train_step -> eval must equal an eval with fresh caches."""
+    from unseenobjectswithmeanshift_b200 import ops, training, workloads
+    from unseenobjectswithmeanshift_b200.meanshiftformer import modeling as M
+    torch.manual_seed(11)
+    kw = dict(num_classes=2, hidden_dim=64, num_queries=20, nheads=2, dim_feedforward=128, dec_layers=3,
+              pre_norm=False, mask_dim=64, enforce_input_project=False, use_meanshift_cross_attention=True,
+              disable_attention_mask=False, use_meanshift_self_attention=True, decoder_block_norm=True)
+    dec = M.MeanShiftTransformerDecoder(32, True, **kw).cuda()
+    x = [torch.randn(2, 32, h, w, device="cuda") for h, w in ((5, 7), (10, 14), (20, 28))]
+    mf = torch.randn(2, 64, 40, 56, device="cuda")
+
+    def evaluate():
+        dec.eval()
+        with torch.no_grad():
+            return dec(x, mf)["pred_masks"].clone()
+
+    before = evaluate()
+    dec.train()
+    opt = torch.optim.AdamW(dec.parameters(), lr=1e-2, fused=True)
+    versions = [p._version for p in dec.parameters()]
+
+    class Wrap(torch.nn.Module):
+        def forward(self, _):
+            return {"loss": dec(x, mf)["pred_masks"].square().mean()}
+
+    training.train_step(Wrap(), opt, None, clip_value=0)
+    after = evaluate()
+    assert not torch.equal(before, after), "the optimizer step changed nothing?"
+    ops.clear_prepared_weights()          # everything derived from weights is rebuilt from scratch
+    fresh = evaluate()
+    assert torch.equal(after, fresh), "eval after train_step used stale derived weights"
+    # the premise of the fix, recorded: does the fused optimizer bump _version on this torch build?
+    print("fused AdamW bumped _version:", [p._version for p in dec.parameters()] != versions)

@@ -30,7 +30,13 @@ def main():
     h = _lib.xlib()
     st = lambda: torch.cuda.current_stream().cuda_stream  # noqa: E731
     g = torch.Generator(device="cuda").manual_seed(0)
-    if what == "ms":
+    if what.startswith("msp"):   # whole hill climb (10 iterations): persistent kernel unless MSM_MS_PERSISTENT=0
+        B, n, m, d = int(what[3:] or 4), 307200, 100, 64
+        X = torch.nn.functional.normalize(torch.randn(B, n, d, device=dev, generator=g), dim=-1)
+        Z = X[:, :m].contiguous()
+        fn = lambda: ops.mean_shift_hill_climb(X, Z, 10.0, 10)  # noqa: E731
+        flops = 4.0 * B * m * n * d * 10
+    elif what == "ms":
         B, n, m, d = 4, 307200, 100, 64
         X = torch.nn.functional.normalize(torch.randn(B, n, d, device=dev, generator=g), dim=-1)
         Z = X[:, :m].contiguous()

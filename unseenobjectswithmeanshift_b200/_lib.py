@@ -75,6 +75,8 @@ X_SIGNATURES = {
     "msmx_mean_shift_packed_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "msmx_mean_shift_pack": (_I, [_P, _P, _I, _I, _I, _P]),
     "msmx_mean_shift_hill_climb_packed": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _I, _P, _Z, _P]),
+    "msmx_mean_shift_persistent_workspace_bytes": (_Z, [_I, _I, _I, _I]),
+    "msmx_mean_shift_hill_climb_persistent": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _I, _P, _Z, _P]),
 }
 _xbound = False
 

@@ -296,7 +296,7 @@ class _MeanShiftDecoderBase(nn.Module):
         ``dec`` = decoder_norm(out) when the caller already has it (fused into the previous GEMM's epilogue)."""
         if dec is None:
             dec = self.decoder_norm(out)
-        logits = self.class_embed(dec)
+        logits = ops.dense(dec, self.class_embed.weight, self.class_embed.bias)   # N = K + 1: padded to 32 columns
         embed = self.mask_embed(dec)
         if torch.is_grad_enabled() and (embed.requires_grad or mask_features.requires_grad):
             masks = ops.mask_logits_autograd(embed, mask_features)  # training (row f4)

@@ -686,6 +686,7 @@ class _Owner:
 
 
 _CONV3_CACHE_OWNER = _Owner()
+_PAD_CACHE_OWNER = _Owner()
 
 
 def conv_layer(conv, x):
@@ -732,10 +733,28 @@ def dense(x, weight, bias=None, relu=False):
         raise RuntimeError("x must be a CUDA tensor: unseenobjectswithmeanshift_b200 has no CPU path")
     needs_grad = torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad
                                               or (bias is not None and bias.requires_grad))
+    if not needs_grad and not linear_supported(x, weight) and _paddable(x, weight):
+        # narrow heads (the 3-way class head, N = K + 1 classes): zero-padded to 32 output columns once per weight and run
+        # through the same tensor-core kernel; the caller gets the [..., :N] view. No cuBLAS launch left in the decoder.
+        N = weight.shape[0]
+        Np = (N + 31) // 32 * 32
+        wp = cached_value(_PAD_CACHE_OWNER, f"w{weight.data_ptr()}_{tuple(weight.shape)}", [weight],
+                          lambda: torch.cat([weight.detach(), weight.new_zeros(Np - N, weight.shape[1])], 0).contiguous())
+        bp = None
+        if bias is not None:
+            bp = cached_value(_PAD_CACHE_OWNER, f"b{bias.data_ptr()}_{N}", [bias],
+                              lambda: torch.cat([bias.detach(), bias.new_zeros(Np - N)], 0).contiguous())
+        return linear(x, wp, bp, relu=relu)[..., :N]
     if needs_grad or not linear_supported(x, weight):
         y = torch.nn.functional.linear(x, weight, bias)
         return torch.relu_(y) if relu else y
     return linear(x, weight.detach(), None if bias is None else bias.detach(), relu=relu)
+
+
+def _paddable(x, weight):
+    return (tc_linear_enabled() and x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32
+            and weight.dim() == 2 and weight.shape[0] % 32 != 0 and weight.shape[0] <= 1024 and weight.shape[1] % 32 == 0
+            and weight.stride(1) == 1 and x.shape[-1] == weight.shape[1])
 
 
 def cached_cat(owner, name, tensors, dim=0):
@@ -845,6 +864,16 @@ def mean_shift_hill_climb(X, Z, kappa, max_iters=10):
         X_ = _lib.xlib()
         packed = torch.empty(X_.msmx_mean_shift_packed_bytes(B, n, d), device=Xb.device, dtype=torch.uint8)
         check(X_.msmx_mean_shift_pack(Xb.data_ptr(), packed.data_ptr(), B, n, d, _stream()), "msmx_mean_shift_pack")
+        if os.environ.get("MSM_MS_PERSISTENT", "1") == "1":
+            # ONE cooperative launch for all iterations of all images (csrc/mean_shift_persistent.cu): point tiles split
+            # evenly over the SMs, per-image barriers between iterations, seeds re-normalised in the kernel
+            ws_bytes = X_.msmx_mean_shift_persistent_workspace_bytes(B, n, m, d)
+            ws = torch.empty(ws_bytes, device=Xb.device, dtype=torch.uint8)
+            rc = X_.msmx_mean_shift_hill_climb_persistent(packed.data_ptr(), Zb.data_ptr(), out.data_ptr(), B, n, m, d,
+                                                          float(kappa), int(max_iters), ws.data_ptr(), ws_bytes,
+                                                          _stream())
+            check(rc, "msmx_mean_shift_hill_climb_persistent")
+            return out[0] if squeeze else out
         ws_bytes = X_.msmx_mean_shift_packed_workspace_bytes(B, n, m, d)
         ws = torch.empty(ws_bytes, device=Xb.device, dtype=torch.uint8)
         rc = X_.msmx_mean_shift_hill_climb_packed(packed.data_ptr(), Zb.data_ptr(), out.data_ptr(), B, n, m, d,
