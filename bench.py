@@ -736,9 +736,10 @@ def main():
                     help="whole-model workloads: what the step returns (fused get_confident_instances + combine_masks "
                          "label map, or the Instances fields incl. full-resolution masks)")
     ap.add_argument("--skip-profile", action="store_true", help="leave out the CUPTI kernel-share pass")
-    ap.add_argument("--backbone-tf32", action="store_true",
-                    help="whole-model workloads: let cuDNN run the BACKBONE in TF32 (PyTorch's default on a GPU, i.e. the "
-                         "reference's stock behaviour there); default fp32 = the reference's CPU arithmetic")
+    ap.add_argument("--backbone-fp32", action="store_true",
+                    help="whole-model workloads: strict fp32 cuDNN math for the BACKBONE (the reference's CPU arithmetic). "
+                         "Default: PyTorch's own default conv math on a GPU (TF32), i.e. what the reference's stock code "
+                         "does there; the head and the tail never use TF32 either way")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--vmf-tflops", action="store_true", help="also time the attention core alone (default with the CPU baseline)")
@@ -847,7 +848,7 @@ def run_forward(args, rank, local_rank, world, dev, sharding, ops, workloads):
 
     if full:
         from unseenobjectswithmeanshift_b200 import backbones
-        backbones.set_tf32(args.backbone_tf32)
+        backbones.set_tf32(not args.backbone_fp32)
         model = workloads.build_model(kind).to(dev)
         head = model.sem_seg_head
         host_in = workloads.synthetic_images(kind, B, seed=rank, pin=True)
@@ -1112,8 +1113,8 @@ def run_forward(args, rank, local_rank, world, dev, sharding, ops, workloads):
               "global_batch": B * world, "parallelism": f"replicas x{world} (batch-sharded, no collective)",
               "l2_policy": "inputs_exceed_l2 (every decoder layer streams the mask features - 157 MB at batch 8 - and "
                            "writes a fresh logits tensor; backbone activations exceed L2)",
-              "backbone": (f"included: torchvision ResNet-50, cuDNN {'TF32' if args.backbone_tf32 else 'fp32 (TF32 off)'}, channels_last" if kind == "r50"
-                           else f"included: SEGNET RGB-D (two ResNet34-8s streams), cuDNN {'TF32' if args.backbone_tf32 else 'fp32 (TF32 off)'}" if kind == "demo"
+              "backbone": (f"included: torchvision ResNet-50, cuDNN {'fp32 (TF32 off, NCHW)' if args.backbone_fp32 else 'at PyTorch default conv math (TF32), channels_last'}, channels_last" if kind == "r50"
+                           else f"included: SEGNET RGB-D (two ResNet34-8s streams), cuDNN {'fp32 (TF32 off, NCHW)' if args.backbone_fp32 else 'at PyTorch default conv math (TF32), channels_last'}" if kind == "demo"
                            else "excluded: head-only workload on synthetic backbone features"),
               "gflop_per_image": {"head": workloads.head_flops_per_image(hk) / 1e9,
                                   "backbone": workloads.backbone_flops_per_image(kind) / 1e9 if full else 0.0}}

@@ -334,6 +334,38 @@ int msm_crop_label_stats(const float* labels_crop, const float* init_crop, const
 int msm_paste_crops(const float* labels_crop, const float* new_label, const int32_t* order, const int32_t* rois,
                     float* refined, int num, int H, int W, int S, int L, void* stream);
 
+/* ----------------------------------------------------------------------------------------------
+ * One decoder layer between its cross-attention and its mask head, as ONE kernel (csrc/decoder_block.cu): a cluster
+ * of 8 CTAs per image, activations exchanged through distributed shared memory. Replaces, per layer,
+ *   tgt = norm(tgt + out_proj(cross_attn))                       meanshiftformer_transformer_decoder.py:253-257
+ *   MeanShiftSelfAttentionLayer.forward_post                     :171-181 (hypersphere attention 100 x 100 per head,
+ *                                                                attention_util.py:64-82, in/out projections :121-140, :425)
+ *   FFNLayer.forward_post                                        :300-304
+ *   F.normalize(output, dim=-1)  (DECODER_BLOCK_NORM)            :637-638
+ *   decoder_norm, class_embed, mask_embed MLP                    :661-664
+ *   the NEXT layer's in_proj_q(tgt + query_pos)                  :250, attention_util.py:135-137
+ * Fixed to the configuration every UOIS YAML selects: hidden 256, 8 heads, FFN 2048, post-norm, Q <= 128 queries.
+ * wblob: msm_decoder_block_weight_bytes(with_qn) bytes, 128-byte aligned: for cluster rank r = 0..7 the fp16 hi | lo
+ *   pieces ([hi|lo][4 k-groups of 8][N][8], one per 32 input channels, as msm_linear_prepare_weight) of, in order:
+ *   cross out_proj rows [32r,32r+32); self in_proj rows q|k|v of head r (96); self out_proj rows; linear1 rows
+ *   [256r,256r+128) and [256r+128,256r+256); linear2[0:128, 256r:256r+256] and linear2[128:256, 256r:256r+256];
+ *   (with_qn) next layer's cross in_proj q rows; [mask_embed.layers.0 rows | class_embed padded to 32 rows] (64);
+ *   mask_embed.layers.1 rows; mask_embed.layers.2 rows.   (host mirror: ops.decoder_block_pack)
+ * t_qk [Q][768] = [query_pos . Wq^T | query_pos . Wk^T | 0] of the self-attention; t_qn [Q][256] = query_pos . Wq^T of
+ *   the next layer's cross-attention (q_next, b_qn, t_qn all NULL for the last layer); b_c: 32 floats.
+ * Outputs: state_out, embed, q_next [B][Q][256]; logits [B][Q][32] (columns >= num_classes + 1 are padding).
+ * ---------------------------------------------------------------------------------------------- */
+size_t msm_decoder_block_weight_bytes(int with_qn);
+
+int msm_decoder_block_fwd(const float* o_cross, const float* state, const void* wblob, const float* b_o1,
+                          const float* g1, const float* be1, float eps1, const float* b_qkv, const float* t_qk,
+                          const float* b_o2, const float* g2, const float* be2, float eps2, const float* b_f1,
+                          const float* b_f2, const float* g3, const float* be3, float eps3, int block_norm,
+                          const float* gd, const float* bed, float epsd, const float* b_qn, const float* t_qn,
+                          const float* b_m1, const float* b_c, const float* b_m2, const float* b_m3,
+                          float* state_out, float* logits, float* embed, float* q_next, int B, int Q, float kappa,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -309,3 +309,70 @@ def test_narrow_head_runs_in_the_library_gemm():
     y2 = ops.dense(x, w, b)
     ref2 = x.double() @ w.double().t() + b.double()
     assert (y2.double() - ref2).abs().max().item() / ref2.abs().max().item() < 2e-5
+
+
+# ----------------------------------------------------------------------------- decoder-layer cluster kernel
+@pytest.mark.parametrize("B,Qn,last,block_norm", [(8, 100, False, True), (1, 100, True, True), (3, 128, False, False),
+                                                   (2, 37, False, True)])
+def test_decoder_block_kernel_vs_fp64(B, Qn, last, block_norm):
+    """msm_decoder_block_fwd (cluster of 8 CTAs per image: out_proj + LN, self-attention block, FFN block, block norm,
+    decoder_norm, class head, mask MLP, next layer's query projection) against the same chain in fp64 torch ops,
+    following meanshiftformer_transformer_decoder.py:171-181, 253-257, 300-304, 637-638, 661-664."""
+    from unseenobjectswithmeanshift_b200 import ops
+    C, H, FF = 256, 8, 2048
+    g = _rng(900 + B + Qn)
+    rn = lambda *s, sc=1.0: torch.randn(*s, device="cuda", generator=g) * sc  # noqa: E731
+    W = dict(o1=rn(C, C, sc=C ** -0.5), qkv=rn(3 * C, C, sc=C ** -0.5), o2=rn(C, C, sc=C ** -0.5),
+             f1=rn(FF, C, sc=C ** -0.5), f2=rn(C, FF, sc=FF ** -0.5), qn=rn(C, C, sc=C ** -0.5),
+             m1=rn(C, C, sc=C ** -0.5), c=rn(3, C, sc=C ** -0.5), m2=rn(C, C, sc=C ** -0.5), m3=rn(C, C, sc=C ** -0.5))
+    bvec = {k: rn(v.shape[0], sc=0.1) for k, v in W.items()}
+    norms = []
+    for _ in range(4):
+        n = torch.nn.LayerNorm(C).cuda()
+        with torch.no_grad():
+            n.weight.copy_(1 + rn(C, sc=0.2))
+            n.bias.copy_(rn(C, sc=0.2))
+        norms.append(n)
+    qpos = rn(Qn, C)
+    o = F.normalize(rn(B, Qn, H, C // H), dim=-1).reshape(B, Qn, C)    # a cross-attention output: unit rows per head
+    state = rn(B, Qn, C)
+    with torch.no_grad():
+        blob = ops.decoder_block_pack(W["o1"], W["qkv"], W["o2"], W["f1"], W["f2"], None if last else W["qn"], W["m1"],
+                                      W["c"], W["m2"], W["m3"])
+        tqk = torch.cat([qpos @ W["qkv"][:2 * C].t(), qpos.new_zeros(Qn, C)], 1).contiguous()
+        tqn = (qpos @ W["qn"].t()).contiguous()
+        bc32 = torch.cat([bvec["c"], bvec["c"].new_zeros(29)])
+        got = ops.decoder_block(o, state, blob, b_o1=bvec["o1"], norm1=norms[0], b_qkv=bvec["qkv"], t_qk=tqk,
+                                b_o2=bvec["o2"], norm2=norms[1], b_f1=bvec["f1"], b_f2=bvec["f2"], norm3=norms[2],
+                                block_norm=block_norm, normd=norms[3], b_qn=None if last else bvec["qn"],
+                                t_qn=None if last else tqn, b_m1=bvec["m1"], b_c32=bc32, b_m2=bvec["m2"],
+                                b_m3=bvec["m3"])
+        torch.cuda.synchronize()
+        d = lambda t: t.double()  # noqa: E731
+        ln = lambda x, n: F.layer_norm(x, (C,), d(n.weight), d(n.bias), n.eps)  # noqa: E731
+        t1 = ln(d(state) + d(o) @ d(W["o1"]).t() + d(bvec["o1"]), norms[0])
+        qk = t1 + d(qpos)
+        q = qk @ d(W["qkv"][:C]).t() + d(bvec["qkv"][:C])
+        k = qk @ d(W["qkv"][C:2 * C]).t() + d(bvec["qkv"][C:2 * C])
+        v = t1 @ d(W["qkv"][2 * C:]).t() + d(bvec["qkv"][2 * C:])
+        hv = lambda t: t.unflatten(-1, (H, C // H)).transpose(1, 2)  # noqa: E731
+        a = torch.softmax(30.0 * F.normalize(hv(q), dim=-1) @ F.normalize(hv(k), dim=-1).transpose(-1, -2), -1) @ hv(v)
+        a = F.normalize(a, dim=-1).transpose(1, 2).reshape(B, Qn, C)
+        t2 = ln(t1 + a @ d(W["o2"]).t() + d(bvec["o2"]), norms[1])
+        t3 = ln(t2 + (t2 @ d(W["f1"]).t() + d(bvec["f1"])).relu() @ d(W["f2"]).t() + d(bvec["f2"]), norms[2])
+        if block_norm:
+            t3 = F.normalize(t3, dim=-1)
+        dec = ln(t3, norms[3])
+        logits = dec @ d(W["c"]).t() + d(bvec["c"])
+        e = (dec @ d(W["m1"]).t() + d(bvec["m1"])).relu()
+        e = (e @ d(W["m2"]).t() + d(bvec["m2"])).relu()
+        embed = e @ d(W["m3"]).t() + d(bvec["m3"])
+        qn = (t3 + d(qpos)) @ d(W["qn"]).t() + d(bvec["qn"])
+    state_out, logits32, emb, q_next = got
+    for name, x, r in (("state", state_out, t3), ("logits", logits32[..., :3], logits), ("embed", emb, embed)):
+        err = (d(x) - r).abs().max().item() / r.abs().max().item()
+        assert err < 3e-5, (name, err)
+    if last:
+        assert q_next is None
+    else:
+        assert (d(q_next) - qn).abs().max().item() / qn.abs().max().item() < 3e-5

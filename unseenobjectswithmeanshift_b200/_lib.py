@@ -41,6 +41,9 @@ SIGNATURES = {
     "msm_ms_deform_attn_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "msm_ms_deform_attn_fused_fwd": (_I, [_P, _P, _P, _P, _L, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "msm_ms_deform_attn_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "msm_decoder_block_weight_bytes": (_Z, [_I]),
+    "msm_decoder_block_fwd": (_I, [_P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _F, _I, _P, _P, _F,
+                                   _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P]),
     "msm_mean_shift_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "msm_mean_shift_hill_climb": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _I, _P, _Z, _P]),
     "msm_smart_seeds_workspace_bytes": (_Z, [_I, _I, _I]),

@@ -13,8 +13,12 @@ pretrained_meanshiftformer_model.py:244-378) - instead of stopping at backbone f
                        (``upsample_bilinear`` = align_corners True) to the input size). Restated with torchvision's
                        BasicBlock ResNet-34 and ``replace_stride_with_dilation``-style surgery done by hand (BasicBlock
                        refuses dilation in torchvision). Random init; no checkpoint exists in the container.
-Both run channels_last through cuDNN in fp32 (TF32 stays off, precision.py: a TF32 backbone changes the features by
-1e-3, which the decoder's hard mask thresholds amplify - parity with the fp32 reference would be lost).
+cuDNN math: PyTorch's own default for convolutions on Ampere and later is TF32 (``torch.backends.cudnn.allow_tf32``),
+which is therefore what the reference's unmodified code does with its backbone on this GPU - and the default here
+(channels_last). ``set_tf32(False)`` before construction selects strict fp32 (NCHW: measured on B200 at batch 8, 640x480,
+ResNet-50: TF32 channels_last 4.65 ms, fp32 NCHW 16.5 ms, fp32 channels_last 26.5 ms - cuDNN's fp32 CUDA-core kernels are
+not a tuned path on this part). The parity claims of this package concern the head and are stated on identical backbone
+features (the head itself never uses TF32: precision.py, split-precision tensor-core kernels).
 """
 import contextlib
 
@@ -22,21 +26,21 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-_TF32 = False
+_TF32 = True
 
 
 def set_tf32(flag):
-    """cuDNN math of the backbones: False (default) = fp32, the reference's CPU arithmetic and what the parity claims of
-    this package are stated against; True = PyTorch's own default on Ampere and later (TF32 tensor cores), i.e. what the
-    reference's stock code does on a GPU."""
+    """cuDNN math of backbones constructed AFTER this call: True (default) = PyTorch's own default on Ampere and later
+    (TF32 tensor cores, channels_last), i.e. what the reference's stock code does on a GPU; False = strict fp32 (NCHW),
+    the reference's CPU arithmetic."""
     global _TF32
     _TF32 = bool(flag)
 
 
 @contextlib.contextmanager
-def _conv_math():
+def _conv_math(tf32):
     old = torch.backends.cudnn.allow_tf32
-    torch.backends.cudnn.allow_tf32 = _TF32
+    torch.backends.cudnn.allow_tf32 = bool(tf32)
     try:
         yield
     finally:
@@ -85,14 +89,16 @@ class ResNet50Features(nn.Module):
         for p in self.parameters():
             p.requires_grad_(False)
         self.eval()
-        self.to(memory_format=torch.channels_last)   # weights converted ONCE (else cuDNN re-lays them out per call)
+        self.tf32 = _TF32
+        self.fmt = torch.channels_last if _TF32 else torch.contiguous_format
+        self.to(memory_format=self.fmt)   # weights converted ONCE (else cuDNN re-lays them out per call)
 
     def train(self, mode=True):  # FrozenBN semantics: never leaves eval mode
         return super().train(False)
 
     def forward(self, x):
-        x = x.contiguous(memory_format=torch.channels_last)
-        with _conv_math():
+        x = x.contiguous(memory_format=self.fmt)
+        with _conv_math(self.tf32):
             x = self.stem(x)
             out = {}
             for name in ("res2", "res3", "res4", "res5"):
@@ -163,12 +169,14 @@ class SegnetEmbedding(nn.Module):
         for p in self.parameters():
             p.requires_grad_(False)
         self.eval()
-        self.to(memory_format=torch.channels_last)
+        self.tf32 = _TF32
+        self.fmt = torch.channels_last if _TF32 else torch.contiguous_format
+        self.to(memory_format=self.fmt)
 
     def forward(self, img, label=None, depth=None):
-        img = img.contiguous(memory_format=torch.channels_last)
-        with _conv_math():
+        img = img.contiguous(memory_format=self.fmt)
+        with _conv_math(self.tf32):
             f = self.fcn(img)
             if self.fcn_depth is not None and depth is not None:
-                f = f + self.fcn_depth(depth.contiguous(memory_format=torch.channels_last))
+                f = f + self.fcn_depth(depth.contiguous(memory_format=self.fmt))
         return f.contiguous()

@@ -36,6 +36,7 @@ constexpr int kSBufs = 3;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColS = 0, kColO = 384, kColQ = 448;  // as vmf_attn_packed_kernel
 constexpr int kMaxSmem = 232448;
+constexpr size_t kFixedSmem = 256 + 3 * 128 * sizeof(float);
 
 struct Params {
   const uint8_t* packed;   // [B][ntiles][2][kTile * HD * 2]: bf16 hi | lo images of 128 points
@@ -44,6 +45,8 @@ struct Params {
   float* part_acc;         // [2][B][maxparts][m][HD]  (double-buffered over iterations)
   float* part_den;         // [2][B][maxparts][m]
   uint32_t* counter;       // [B], zero before the launch: parts arrived, all iterations
+  uint32_t* counter2;      // [B], zero before the launch: row shares of the reduction done, all iterations
+  float* z_buf;            // [2][B][m][HD] seeds between iterations (double-buffered)
   int B, m, n, ntiles, tiles_per_cta, maxparts, iters, nstages;
   float c;                 // kappa * log2(e)
 };
@@ -144,14 +147,81 @@ __global__ void __launch_bounds__(kThreads, 1) mean_shift_persistent_kernel(cons
     int si = 0;   // segment-iterations so far: phase of q_ready / o_full
 
     for (int it = 0; it <= P.iters; ++it) {
+      const bool last_round = it == P.iters;   // no tiles: only the final reduction of the images' parts
+      if (it > 0) {
+        // Between iterations, for EVERY image this CTA holds tiles of (before any of its segments starts, so that no CTA
+        // waits for a neighbour's segment): (1) per-image barrier - all parts of iteration it - 1 of the image are
+        // written; (2) the image's CTAs share the reduction BY ROWS: CTA `part` sums all parts of rows [r0, r1) in part
+        // order (deterministic), normalises them and writes them to the seed buffer (to z_out after the last
+        // iteration), so every partial is read once - when every CTA summed every part, B = 1 moved 570 MB through L2
+        // per iteration; (3) arrive on the image's second counter. The segments below wait for that counter.
+        for (int b = b_lo; b <= b_hi; ++b) {
+          const Segment sg = segment_of(P, cta, b);
+          if (warp == 0 && lane == 0) {
+            const uint32_t target = (uint32_t)sg.nparts * (uint32_t)it;
+            while (ld_acquire_u32(P.counter + b) < target) __nanosleep(40);
+          }
+          named_bar_sync(1, kSoftmaxWarps * 32);
+          constexpr int C4 = HD / 4;            // float4 per row; the C4 threads of a row are consecutive lanes
+          constexpr int RP = 512 / C4;          // rows per pass of the 512 softmax threads
+          const int buf = (it - 1) & 1;
+          const size_t pbase = ((size_t)buf * P.B + b) * P.maxparts;
+          const int r0 = (int)((long)sg.part * P.m / sg.nparts), r1 = (int)((long)(sg.part + 1) * P.m / sg.nparts);
+          float* zdst = last_round ? P.z_out + (size_t)b * P.m * HD
+                                   : P.z_buf + ((size_t)(it & 1) * P.B + b) * P.m * HD;
+          const int tid = threadIdx.x;          // 0..511 (softmax warps only)
+          const int c4 = tid % C4;
+          const int passes = (r1 - r0 + RP - 1) / RP;
+          for (int ps = 0; ps < passes; ++ps) {
+            const int row = r0 + ps * RP + tid / C4;
+            const bool live = row < r1;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            float dsum = 0.f;
+            if (live) {
+              const float4* ap0 = reinterpret_cast<const float4*>(P.part_acc + (pbase * P.m + row) * HD) + c4;
+              const size_t pstride4 = (size_t)P.m * C4;
+              for (int p0 = 0; p0 < sg.nparts; p0 += 8) {
+                float4 t[8];
+                float dd[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                  const bool ok = p0 + u < sg.nparts;
+                  t[u] = ok ? __ldcg(ap0 + (size_t)(p0 + u) * pstride4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  dd[u] = ok ? __ldcg(P.part_den + (pbase + p0 + u) * P.m + row) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                  acc.x += t[u].x; acc.y += t[u].y; acc.z += t[u].z; acc.w += t[u].w;
+                  dsum += dd[u];
+                }
+              }
+              acc.x /= dsum; acc.y /= dsum; acc.z /= dsum; acc.w /= dsum;
+            }
+            float ss = acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+#pragma unroll
+            for (int o = C4 / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            if (live) {
+              const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+              reinterpret_cast<float4*>(zdst + (size_t)row * HD)[c4] =
+                  make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+            }
+          }
+          named_bar_sync(1, kSoftmaxWarps * 32);
+          if (!last_round && warp == 0 && lane == 0) arrive_release(P.counter2 + b);
+        }
+      }
+      if (last_round) break;
       for (int b = b_lo; b <= b_hi; ++b) {
         const Segment sg = segment_of(P, cta, b);
         const int nt = sg.t1 - sg.t0;
-        const bool last_round = it == P.iters;   // no tiles: only the final reduction of the image's parts
-        if (last_round && sg.part != 0) continue;
-
+        if (it > 0) {   // the new seeds of this image are complete
+          if (warp == 0 && lane == 0) {
+            const uint32_t target = (uint32_t)sg.nparts * (uint32_t)it;
+            while (ld_acquire_u32(P.counter2 + b) < target) __nanosleep(40);
+          }
+          named_bar_sync(1, kSoftmaxWarps * 32);
+        }
         if (set == 0) {
-          // ---- seeds of this image for this iteration -> TMEM (bf16 hi | lo A operand), or -> z_out after the last one
           float x[HD];
           if (it == 0) {
             const float* zp = P.z0 + ((size_t)b * P.m + (qi < P.m ? qi : 0)) * HD;
@@ -162,47 +232,14 @@ __global__ void __launch_bounds__(kThreads, 1) mean_shift_persistent_kernel(cons
               x[4 * d4 + 0] = t.x; x[4 * d4 + 1] = t.y; x[4 * d4 + 2] = t.z; x[4 * d4 + 3] = t.w;
             }
           } else {
-            // per-image barrier: every part of iteration it - 1 of THIS image has been written
-            if (warp == 0 && lane == 0) {
-              const uint32_t target = (uint32_t)sg.nparts * (uint32_t)it;
-              while (ld_acquire_u32(P.counter + b) < target) {
-              }
+            const float4* zr = reinterpret_cast<const float4*>(P.z_buf + (((size_t)(it & 1) * P.B + b) * P.m +
+                                                                         (qi < P.m ? qi : 0)) * HD);
+#pragma unroll
+            for (int d4 = 0; d4 < HD / 4; ++d4) {
+              float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (qi < P.m) t = __ldcg(zr + d4);
+              x[4 * d4 + 0] = t.x; x[4 * d4 + 1] = t.y; x[4 * d4 + 2] = t.z; x[4 * d4 + 3] = t.w;
             }
-            named_bar_sync(2, 128);
-            const int buf = (it - 1) & 1;
-            const size_t pbase = ((size_t)buf * P.B + b) * P.maxparts;
-            float den = 0.f;
-#pragma unroll
-            for (int d = 0; d < HD; ++d) x[d] = 0.f;
-            if (qi < P.m) {
-              for (int p = 0; p < sg.nparts; ++p) {   // fixed order: bit-identical in every CTA of the image
-                const float4* ap = reinterpret_cast<const float4*>(P.part_acc + ((pbase + p) * P.m + qi) * HD);
-#pragma unroll
-                for (int d4 = 0; d4 < HD / 4; ++d4) {
-                  const float4 t = __ldcg(ap + d4);
-                  x[4 * d4 + 0] += t.x; x[4 * d4 + 1] += t.y; x[4 * d4 + 2] += t.z; x[4 * d4 + 3] += t.w;
-                }
-                den += __ldcg(P.part_den + (pbase + p) * P.m + qi);
-              }
-              float ss = 0.f;
-#pragma unroll
-              for (int d = 0; d < HD; ++d) {
-                x[d] = x[d] / den;
-                ss += x[d] * x[d];
-              }
-              const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-#pragma unroll
-              for (int d = 0; d < HD; ++d) x[d] *= inv;
-            }
-          }
-          if (last_round) {
-            if (qi < P.m) {
-              float4* op = reinterpret_cast<float4*>(P.z_out + ((size_t)b * P.m + qi) * HD);
-#pragma unroll
-              for (int d4 = 0; d4 < HD / 4; ++d4)
-                op[d4] = make_float4(x[4 * d4 + 0], x[4 * d4 + 1], x[4 * d4 + 2], x[4 * d4 + 3]);
-            }
-            continue;
           }
 #pragma unroll
           for (int c16 = 0; c16 < HD / 32; ++c16) {
@@ -216,15 +253,16 @@ __global__ void __launch_bounds__(kThreads, 1) mean_shift_persistent_kernel(cons
           tc::tc_fence_before();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(q_ready);
-        } else if (last_round) {
-          continue;
         }
 
         // ---- this warp's half tiles of the segment (tiles alternate between the two groups)
         tc::f32x2 den2 = tc::f2_pack(0.f, 0.f);
         for (int j = 0; j < nt; ++j) {
           const int t = jt + j;
-          if ((t & 1) != grp) continue;
+          // groups alternate on the SEGMENT-local tile index: the row sums are accumulated per warp set, so the split
+          // of tiles between the sets must not depend on how many tiles earlier iterations processed (otherwise
+          // 10 iterations and 4 + 6 iterations would differ in the last bits)
+          if ((j & 1) != grp) continue;
           const int buf = t % kSBufs;
           const uint32_t sp = lane_addr + kColS + (uint32_t)buf * 128u;
           const int key0 = (sg.t0 + j) * kTile;
@@ -432,8 +470,8 @@ using namespace msm;
 
 extern "C" size_t msmx_mean_shift_persistent_workspace_bytes(int B, int n, int m, int d) {
   const msp::Plan pl = msp::plan(B, n);
-  return 256 + (((size_t)B * sizeof(uint32_t) + 255) & ~(size_t)255) +
-         2 * (size_t)B * pl.maxparts * m * (d + 1) * sizeof(float);
+  return 256 + 2 * (((size_t)B * sizeof(uint32_t) + 255) & ~(size_t)255) +
+         2 * (size_t)B * pl.maxparts * m * (d + 1) * sizeof(float) + 2 * (size_t)B * m * d * sizeof(float);
 }
 
 // packed: msmx_mean_shift_pack output (bf16 hi | lo images of 128 points). One cooperative launch for all iterations.
@@ -454,8 +492,10 @@ extern "C" int msmx_mean_shift_hill_climb_persistent(const void* packed, const f
   ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
   P.counter = reinterpret_cast<uint32_t*>(ws);
   const size_t cbytes = ((size_t)B * sizeof(uint32_t) + 255) & ~(size_t)255;
-  P.part_acc = reinterpret_cast<float*>(ws + cbytes);
+  P.counter2 = reinterpret_cast<uint32_t*>(ws + cbytes);
+  P.part_acc = reinterpret_cast<float*>(ws + 2 * cbytes);
   P.part_den = P.part_acc + 2 * (size_t)B * pl.maxparts * m * d;
+  P.z_buf = P.part_den + 2 * (size_t)B * pl.maxparts * m;
   P.packed = static_cast<const uint8_t*>(packed);
   P.z0 = Z0;
   P.z_out = Z_out;
@@ -463,12 +503,12 @@ extern "C" int msmx_mean_shift_hill_climb_persistent(const void* packed, const f
   P.iters = max_iters;
   P.c = kappa * kLog2e;
   const uint32_t stage_bytes = 2u * msp::kTile * d * 2u;
-  const size_t fixed = 256 + 3 * 128 * sizeof(float);
+  const size_t fixed = msp::kFixedSmem;
   const int stages = (int)(((size_t)msp::kMaxSmem - fixed) / stage_bytes);
   P.nstages = stages > msp::kMaxStages ? msp::kMaxStages : stages;
   size_t smem = (size_t)P.nstages * stage_bytes + fixed;
   if (smem < (size_t)(120 << 10)) smem = (size_t)(120 << 10);   // one CTA per SM (each allocates all of TMEM)
-  MSM_CUDA(cudaMemsetAsync(P.counter, 0, cbytes, st));
+  MSM_CUDA(cudaMemsetAsync(P.counter, 0, 2 * cbytes, st));
   void* args[] = {&P};
   if (d == 64) {
     MSM_CUDA(cudaFuncSetAttribute(msp::mean_shift_persistent_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -459,10 +459,24 @@ class _MeanShiftDecoderBase(nn.Module):
         level = int(os.environ.get("MSM_DECODER_FUSION", "1"))
         fused = fused and level > 0
 
+        # One cluster kernel per layer for everything between the cross-attention and the mask einsum
+        # (csrc/decoder_block.cu): the configuration of every UOIS YAML (hidden 256, 8 heads, FFN 2048, relu, post-norm)
+        block = (fused and ops.decoder_block_enabled() and C == 256 and H == 8 and self.num_queries <= 128
+                 and all(f.linear1.weight.shape[0] == 2048 and f.activation is F.relu for f in self.transformer_ffn_layers)
+                 and self.class_embed.weight.shape[0] <= 32 and self.mask_embed.num_layers == 3
+                 and self.mask_embed.layers[2].weight.shape[0] == 256)
+        q_carry = None   # the next layer's cross-attention query projection, produced by the previous layer's kernel
+
+        def tq_table(j):
+            aj = self.transformer_cross_attention_layers[j].meanshift_attn
+            return ops.cached_value(self, f"tq{j}", [qpos, aj.in_proj_weight],
+                                    lambda: F.linear(qpos, aj.in_proj_weight[:C]).contiguous())
+
         for i in range(self.num_layers):
             lvl = i % L
             if _teacher is not None:
                 out, bits, row_open = _teacher(i, out, bits, row_open)
+                q_carry = None   # the carried projection belongs to the state the teacher just replaced
             if i not in kv:
                 project_kv(lvl, [i])
             K, V = kv.pop(i)
@@ -471,10 +485,48 @@ class _MeanShiftDecoderBase(nn.Module):
             ffn = self.transformer_ffn_layers[i]
             a = ca.meanshift_attn
             sa = sl.self_attn
+            if block:
+                q = q_carry if q_carry is not None else ops.linear_fused(out, a.in_proj_weight[:C], a.in_proj_bias[:C],
+                                                                         rowbias=tq_table(i))
+                if isinstance(K, ops.PackedKV):
+                    o = attention(q, K, V, bits, row_open)
+                else:
+                    o = torch.empty(B, self.num_queries, C, device=dev, dtype=torch.float32)
+                    ops.vmf_attention(heads_view(q), heads_view(K), heads_view(V), blocked_bits=bits, row_open=row_open,
+                                      out=heads_view(o))
+                del K, V
+                nxt = self.transformer_cross_attention_layers[i + 1].meanshift_attn if i + 1 < self.num_layers else None
+                mlp = self.mask_embed.layers
+                deps = [a.out_proj.weight, sa.in_proj_weight, sa.out_proj.weight, ffn.linear1.weight, ffn.linear2.weight,
+                        mlp[0].weight, self.class_embed.weight, mlp[1].weight, mlp[2].weight] + (
+                            [nxt.in_proj_weight] if nxt is not None else [])
+                blob = ops.cached_value(self, f"dbk{i}", deps, lambda: ops.decoder_block_pack(
+                    a.out_proj.weight, sa.in_proj_weight, sa.out_proj.weight, ffn.linear1.weight, ffn.linear2.weight,
+                    nxt.in_proj_weight[:C] if nxt is not None else None, mlp[0].weight, self.class_embed.weight,
+                    mlp[1].weight, mlp[2].weight))
+                tqk = ops.cached_value(self, f"tqk{i}", [qpos, sa.in_proj_weight],
+                                       lambda: torch.cat([F.linear(qpos, sa.in_proj_weight[:2 * C]),
+                                                          qpos.new_zeros(qpos.shape[0], C)], 1).contiguous())
+                bc32 = ops.cached_value(self, "bc32", [self.class_embed.bias], lambda: torch.cat(
+                    [self.class_embed.bias.detach(), self.class_embed.bias.new_zeros(32 - self.class_embed.bias.numel())]))
+                out, logits32, embed, q_carry = ops.decoder_block(
+                    o, out, blob, b_o1=a.out_proj.bias, norm1=ca.norm, b_qkv=sa.in_proj_bias, t_qk=tqk,
+                    b_o2=sa.out_proj.bias, norm2=sl.norm, b_f1=ffn.linear1.bias, b_f2=ffn.linear2.bias, norm3=ffn.norm,
+                    block_norm=self.decoder_block_norm, normd=self.decoder_norm,
+                    b_qn=nxt.in_proj_bias[:C] if nxt is not None else None,
+                    t_qn=tq_table(i + 1) if nxt is not None else None, b_m1=mlp[0].bias, b_c32=bc32, b_m2=mlp[1].bias,
+                    b_m3=mlp[2].bias)
+                logits = logits32[..., :self.class_embed.weight.shape[0]]
+                masks = ops.mask_logits(embed, mask_features)
+                bits = row_open = None
+                if need_mask:
+                    bits, row_open = ops.mask_to_attn_bits(masks, sizes[(i + 1) % L])
+                predictions_class.append(logits)
+                predictions_mask.append(masks)
+                continue
             if fused and ffn.activation is F.relu:
                 # cross-attention (reference :245-260), post-norm
-                tq = ops.cached_value(self, f"tq{i}", [qpos, a.in_proj_weight],
-                                      lambda: F.linear(qpos, a.in_proj_weight[:C]).contiguous())
+                tq = tq_table(i)
                 q = ops.linear_fused(out, a.in_proj_weight[:C], a.in_proj_bias[:C], rowbias=tq)
                 if isinstance(K, ops.PackedKV):
                     o = attention(q, K, V, bits, row_open)

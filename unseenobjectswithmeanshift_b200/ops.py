@@ -607,6 +607,77 @@ def ffn_ln(x, w1, b1, w2, b2, norm):
     return out
 
 
+# ----------------------------------------------------------------------------------------------
+# one decoder layer after its cross-attention, as ONE cluster kernel per layer (csrc/decoder_block.cu)
+# ----------------------------------------------------------------------------------------------
+def decoder_block_enabled():
+    return os.environ.get("MSM_DECODER_BLOCK", "1") == "1"
+
+
+def _dbk_pieces(w):
+    """fp32 [N, 256] weight slice -> bytes of its 8 stream pieces, each [hi | lo][4 k-groups][N][8] fp16 (the layout of
+    msm_linear_prepare_weight for a 32-channel K chunk: the UMMA canonical K-major B operand)."""
+    N = w.shape[0]
+    hi = w.to(torch.float16)
+    lo = (w - hi.float()).to(torch.float16)
+    t = torch.stack([hi, lo]).view(2, N, 8, 4, 8).permute(2, 0, 3, 1, 4).contiguous()   # [chunk, hi/lo, kg, N, 8]
+    return t.view(torch.uint8).reshape(-1)
+
+
+def decoder_block_pack(w_o1, w_qkv, w_o2, w_f1, w_f2, w_qn, w_m1, w_c, w_m2, w_m3):
+    """Weight stream of one decoder layer for the 8 CTAs of a cluster: [8, bytes] uint8. CTA r gets, in the order the
+    kernel consumes them: out_proj rows [32r, 32r+32) of the cross-attention; its head's q | k | v rows of the
+    self-attention in_proj; self out_proj rows; 2 x 128 hidden units of linear1; linear2 restricted to those 256
+    hidden units (outputs 0..127, 128..255); the NEXT layer's cross-attention q in_proj rows (None: last layer);
+    mask MLP layer 0 rows + the class head padded to 32 rows; MLP layers 1, 2 rows."""
+    C = 256
+    if tuple(w_o1.shape) != (C, C) or tuple(w_qkv.shape) != (3 * C, C) or tuple(w_f1.shape) != (2048, C) \
+            or tuple(w_f2.shape) != (C, 2048) or w_c.shape[1] != C or w_c.shape[0] > 32:
+        raise ValueError("decoder_block: hidden 256, 8 heads, FFN 2048, at most 32 classes")
+    wc = torch.cat([w_c, w_c.new_zeros(32 - w_c.shape[0], C)], 0)
+    ranks = []
+    for r in range(8):
+        s = slice(32 * r, 32 * r + 32)
+        h = slice(256 * r, 256 * r + 256)
+        parts = [w_o1[s], torch.cat([w_qkv[s], w_qkv[C + 32 * r:C + 32 * r + 32], w_qkv[2 * C + 32 * r:2 * C + 32 * r + 32]]),
+                 w_o2[s], w_f1[256 * r:256 * r + 128], w_f1[256 * r + 128:256 * r + 256], w_f2[:128, h], w_f2[128:, h]]
+        if w_qn is not None:
+            parts.append(w_qn[s])
+        parts += [torch.cat([w_m1[s], wc]), w_m2[s], w_m3[s]]
+        ranks.append(torch.cat([_dbk_pieces(p.detach().float().contiguous()) for p in parts]))
+    blob = torch.stack(ranks).contiguous()
+    want = _lib.lib().msm_decoder_block_weight_bytes(1 if w_qn is not None else 0)
+    if blob.numel() != want:
+        raise RuntimeError(f"decoder_block_pack: {blob.numel()} bytes packed, the kernel expects {want}")
+    return blob
+
+
+def decoder_block(o_cross, state, blob, *, b_o1, norm1, b_qkv, t_qk, b_o2, norm2, b_f1, b_f2, norm3, block_norm, normd,
+                  b_qn, t_qn, b_m1, b_c32, b_m2, b_m3, kappa=KAPPA):
+    """o_cross, state [B, Q, 256] -> (state_out [B,Q,256], logits [B,Q,32] (first K+1 columns valid), embed [B,Q,256],
+    q_next [B,Q,256] or None). See csrc/decoder_block.cu."""
+    o = _require(o_cross, "o_cross").contiguous()
+    st = _require(state, "state").contiguous()
+    B, Q, C = o.shape
+    if C != 256 or st.shape != o.shape or Q > 128:
+        raise ValueError(f"decoder_block: [B, Q <= 128, 256] inputs, got {tuple(o.shape)} / {tuple(st.shape)}")
+    dev = o.device
+    state_out = torch.empty_like(o)
+    logits = torch.empty(B, Q, 32, device=dev, dtype=torch.float32)
+    embed = torch.empty_like(o)
+    q_next = torch.empty_like(o) if b_qn is not None else None
+    p = lambda t: None if t is None else _require(t.detach(), "vector").contiguous().data_ptr()  # noqa: E731
+    rc = _lib.lib().msm_decoder_block_fwd(
+        o.data_ptr(), st.data_ptr(), blob.data_ptr(), p(b_o1), p(norm1.weight), p(norm1.bias), float(norm1.eps),
+        p(b_qkv), p(t_qk), p(b_o2), p(norm2.weight), p(norm2.bias), float(norm2.eps), p(b_f1), p(b_f2),
+        p(norm3.weight), p(norm3.bias), float(norm3.eps), 1 if block_norm else 0, p(normd.weight), p(normd.bias),
+        float(normd.eps), p(b_qn), p(t_qn), p(b_m1), p(b_c32), p(b_m2), p(b_m3), state_out.data_ptr(),
+        logits.data_ptr(), embed.data_ptr(), q_next.data_ptr() if q_next is not None else None, B, Q, float(kappa),
+        _stream())
+    check(rc, "msm_decoder_block_fwd")
+    return state_out, logits, embed, q_next
+
+
 def add_layernorm(x, y, norm, l2_normalize=False, norm2=None):
     """norm(x + y) [-> F.normalize] [-> also norm2 of the result] in one launch. x, y contiguous [..., C] (y may be
     None); norm / norm2 affine LayerNorm modules over C <= 1024. Returns out, or (out, out2) when norm2 is given."""
@@ -1287,6 +1358,9 @@ conv1x1 = _instrument("linear", 1, _work_conv)(conv1x1)
 conv3x3 = _instrument("linear", 1, _work_conv3)(conv3x3)
 linear_ln = _instrument("linear", 1, _work_linear_ln)(linear_ln)
 ffn_ln = _instrument("ffn", 1, _work_ffn)(ffn_ln)
+decoder_block = _instrument("decoder_block", 1, lambda o, st, blob, **kw: (
+    f"B{o.shape[0]} Q{o.shape[1]} C256 F2048", 4.0 * o.numel() * 5 + blob.numel() * o.shape[0],
+    2.0 * o.shape[0] * o.shape[1] * 256 * (256 * 7.125 + 2 * 2048) + 4.0 * o.shape[0] * o.shape[1] ** 2 * 256))(decoder_block)
 add_layernorm = _instrument("add_layernorm", 1, lambda x, y, norm, l2_normalize=False, norm2=None: (
     f"rows{x.numel() // x.shape[-1]} C{x.shape[-1]}", 4.0 * x.numel() * (3 + (1 if norm2 is not None else 0)), 0.0))(
     add_layernorm)
