@@ -59,10 +59,13 @@ def _inputs(batch, seed):
     return x, mf
 
 
-def test_decoder_config2_teacher_forced():
+@pytest.mark.parametrize("block_kernel", ["0", "1"])
+def test_decoder_config2_teacher_forced(monkeypatch, block_kernel):
     """Each layer of the CUDA decoder is fed the oracle's own layer input (query state + mask bits); its prediction
-    (class logits, mask logits) and the NEXT layer's mask bits it derives are compared with the oracle's."""
+    (class logits, mask logits) and the NEXT layer's mask bits it derives are compared with the oracle's. Both forms of
+    the layer: the per-op kernels (default) and the one-launch cluster kernel (MSM_DECODER_BLOCK=1)."""
     from unseenobjectswithmeanshift_b200 import ops
+    monkeypatch.setenv("MSM_DECODER_BLOCK", block_kernel)
     B = 2
     m, sd = _decoder(0)
     x, mf = _inputs(B, 0)

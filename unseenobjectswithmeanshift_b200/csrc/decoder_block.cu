@@ -61,6 +61,8 @@ enum Pass { P_O1 = 0, P_QKV, P_O2, P_F1A, P_F1B, P_F2A, P_F2B, P_QN, P_M1, P_M2,
 __host__ __device__ constexpr int pass_n(int p) {
   return p == P_QKV ? 96 : (p == P_F1A || p == P_F1B || p == P_F2A || p == P_F2B) ? 128 : p == P_M1 ? 64 : 32;
 }
+// 32-channel chunks per bulk copy / ring slot: as many as fit 16 KB (N = 32: 4, N = 64: 2, N >= 96: 1)
+__host__ __device__ constexpr int chunks_per_piece(int p) { return pass_n(p) == 32 ? 4 : pass_n(p) == 64 ? 2 : 1; }
 __host__ __device__ constexpr uint32_t pass_bytes(int p) { return (uint32_t)kPieces * 128u * (uint32_t)pass_n(p); }
 __host__ __device__ constexpr uint32_t blob_bytes(bool with_qn) {
   uint32_t t = 0;
@@ -88,6 +90,7 @@ struct Params {
   int B, Q, block_norm, with_qn;
   float eps1, eps2, eps3, epsd;
   float c;                 // kappa * log2(e) of the self-attention
+  long long* dbg;          // optional [CTAs][32] stage timestamps of row warp 0 (tools/prof_block.py), or null
 };
 
 // ------------------------------------------------------------------------------------------ cluster / DSMEM primitives
@@ -101,14 +104,30 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local_smem_addr, uint32_t rank
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+// Asynchronous remote stores: the data lands in the destination CTA's shared memory and completes `bytes` of
+// transaction on an mbarrier THERE. The sender neither fences nor arrives (a gather of 64 plain st.shared::cluster per
+// thread + fence.proxy.async + a release fence + 8 arrives measured 5 us per exchange, 7 exchanges per layer); the
+// receiver arms its barrier with the byte count of the whole exchange (expect_tx) once per phase.
+__device__ __forceinline__ void st_async_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr),
+               "r"(a), "r"(b), "r"(c), "r"(d), "r"(bar)
+               : "memory");
 }
-__device__ __forceinline__ void st_cluster_v2f(uint32_t addr, float a, float b) {
-  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+__device__ __forceinline__ void st_async_v2f(uint32_t addr, float a, float b, uint32_t bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(addr), "f"(a),
+               "f"(b), "r"(bar)
+               : "memory");
 }
-__device__ __forceinline__ void arrive_remote(uint32_t bar_addr_cluster) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_addr_cluster) : "memory");
+// arrive on the same barrier of all 8 CTAs: ONE release fence at cluster scope, then relaxed remote arrives (eight
+// release-arrives cost eight membars; ncu showed 12 % of the stall samples on them)
+__device__ __forceinline__ void arrive_all(uint32_t bar_local_addr) {
+  asm volatile("fence.acq_rel.cluster;" ::: "memory");
+#pragma unroll
+  for (uint32_t r = 0; r < (uint32_t)kCluster; ++r) {
+    uint32_t addr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(addr) : "r"(bar_local_addr), "r"(r));
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
+  }
 }
 __device__ __forceinline__ void wait_cluster(uint64_t* bar, uint32_t parity) {   // acquire at cluster scope
   const uint32_t addr = tc::smem_u32(bar);
@@ -150,10 +169,10 @@ struct Smem {
   uint64_t* w_full;    // [kSlots] producer -> MMA
   uint64_t* w_empty;   // [kSlots] MMA -> producer
   uint64_t* a_local;   // row warps of THIS CTA wrote the A operand (count 4)
-  uint64_t* a_gather;  // row warps of ALL CTAs wrote their slices of the A operand (count 32)
+  uint64_t* a_gather;  // [2] all 128 KB of an A-operand gather landed (transaction bytes; armed by the MMA warp)
   uint64_t* a_free;    // every CTA is done with its A buffer (count 8)
-  uint64_t* red_full;  // reduce-scatter slabs of all CTAs landed (count 32)
-  uint64_t* st_full;   // [2] statistics of all CTAs landed (count 32)
+  uint64_t* red_full;  // all 128 KB of reduce-scatter slabs landed (transaction bytes)
+  uint64_t* st_full;   // [2] the 8 KB of row statistics of all CTAs landed (transaction bytes; re-armed by thread 0)
   uint64_t* acc_full;  // MMA -> row warps
   uint32_t* tmem_slot;
 };
@@ -168,17 +187,14 @@ struct RowPhase {
 __device__ __forceinline__ void row_stats_exchange(const Smem& S, RowPhase& ph, int rank, int m, int lane, float a, float b) {
   const uint32_t buf = ph.st_buf;
   const uint32_t local = tc::smem_u32(S.stats) + ((buf * kCluster + (uint32_t)rank) * kRows + (uint32_t)m) * 8u;
+  const uint32_t bar = tc::smem_u32(&S.st_full[buf]);
 #pragma unroll
-  for (int r = 0; r < kCluster; ++r) st_cluster_v2f(mapa(local, r), a, b);
-  __syncwarp();
-  if (lane == 0) {
-    const uint32_t bar = tc::smem_u32(&S.st_full[buf]);
-#pragma unroll
-    for (int r = 0; r < kCluster; ++r) arrive_remote(mapa(bar, r));
-  }
+  for (int r = 0; r < kCluster; ++r) st_async_v2f(mapa(local, r), a, b, mapa(bar, r));
   wait_cluster(&S.st_full[buf], ph.st[buf]);
   ph.st[buf] ^= 1;
   ph.st_buf ^= 1;
+  // the buffer's next use is two exchanges away; one thread re-arms it (the phase just completed for everybody here)
+  if (threadIdx.x == 0) tc::mbar_arrive_expect_tx(&S.st_full[buf], kStatsBytes / 2);
 }
 __device__ __forceinline__ void layernorm_slice(const Smem& S, RowPhase& ph, int rank, int m, int lane, float (&v)[kHd],
                                                 const float* gamma, const float* beta, float eps) {
@@ -222,36 +238,27 @@ __device__ __forceinline__ void l2normalize_slice(const Smem& S, RowPhase& ph, i
 }
 
 // this thread's 32 values (columns [32 rank, 32 rank + 32) of row m) -> fp16 hi / lo -> the A operand of ALL CTAs
-__device__ __forceinline__ void gather_slice(const Smem& S, int rank, int m, int lane, const float (&v)[kHd]) {
+__device__ __forceinline__ void gather_slice(const Smem& S, int which, int rank, int m, int lane, const float (&v)[kHd]) {
   const uint32_t a_local = tc::smem_u32(S.a);
+  const uint32_t bar_local = tc::smem_u32(&S.a_gather[which]);
   uint32_t hi[16], lo[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) tc::split2g(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
 #pragma unroll
   for (int r = 0; r < kCluster; ++r) {
-    const uint32_t base = mapa(a_local, r);
+    const uint32_t base = mapa(a_local, r), bar = mapa(bar_local, r);
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       const uint32_t off = ((uint32_t)(rank * 4 + g) * kRows + (uint32_t)m) * 16u;
-      st_cluster_v4(base + off, hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
-      st_cluster_v4(base + kAHalf + off, lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
+      st_async_v4(base + off, hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3], bar);
+      st_async_v4(base + kAHalf + off, lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3], bar);
     }
   }
-  fence_proxy_async_all();   // generic-proxy stores -> visible to the tensor cores' (async proxy) operand reads
-  __syncwarp();
-  if (lane == 0) {
-    const uint32_t bar = tc::smem_u32(S.a_gather);
-#pragma unroll
-    for (int r = 0; r < kCluster; ++r) arrive_remote(mapa(bar, r));
-  }
+  (void)lane;
 }
 // "my A buffer may be overwritten" -> every CTA; then wait until all 8 CTAs said so. `signal`: one thread per CTA.
 __device__ __forceinline__ void a_free_sync(const Smem& S, RowPhase& ph, bool signal) {
-  if (signal) {
-    const uint32_t bar = tc::smem_u32(S.a_free);
-#pragma unroll
-    for (int r = 0; r < kCluster; ++r) arrive_remote(mapa(bar, r));
-  }
+  if (signal) arrive_all(tc::smem_u32(S.a_free));
   wait_cluster(S.a_free, ph.afree);
   ph.afree ^= 1;
 }
@@ -276,7 +283,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
   S.w_empty = S.w_full + kSlots;
   S.a_local = S.w_empty + kSlots;
   S.a_gather = S.a_local + 1;
-  S.a_free = S.a_gather + 1;
+  S.a_free = S.a_gather + 2;
   S.red_full = S.a_free + 1;
   S.st_full = S.red_full + 1;
   S.acc_full = S.st_full + 2;
@@ -292,13 +299,21 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
       tc::mbar_init(&S.w_empty[i], 1);
     }
     tc::mbar_init(S.a_local, kRowWarps);
-    tc::mbar_init(S.a_gather, kCluster * kRowWarps);
+    tc::mbar_init(&S.a_gather[0], 1);
+    tc::mbar_init(&S.a_gather[1], 1);
     tc::mbar_init(S.a_free, kCluster);
-    tc::mbar_init(S.red_full, kCluster * kRowWarps);
-    tc::mbar_init(&S.st_full[0], kCluster * kRowWarps);
-    tc::mbar_init(&S.st_full[1], kCluster * kRowWarps);
+    tc::mbar_init(S.red_full, 1);
+    tc::mbar_init(&S.st_full[0], 1);
+    tc::mbar_init(&S.st_full[1], 1);
     tc::mbar_init(S.acc_full, 1);
     tc::fence_mbar_init();
+    // arm the first phase of every transaction barrier (remote bytes may land before or after: the phase cannot
+    // complete before this arrival)
+    tc::mbar_arrive_expect_tx(&S.a_gather[0], kABytes);
+    tc::mbar_arrive_expect_tx(&S.a_gather[1], kABytes);
+    tc::mbar_arrive_expect_tx(S.red_full, kABytes);
+    tc::mbar_arrive_expect_tx(&S.st_full[0], kStatsBytes / 2);
+    tc::mbar_arrive_expect_tx(&S.st_full[1], kStatsBytes / 2);
   }
   if (warp == kMmaWarp) tc::tmem_alloc(S.tmem_slot, kTmemCols);
   tc::tc_fence_before();
@@ -314,8 +329,9 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
       tc::Ring ring;
       for (int p = 0; p < kNumPasses; ++p) {
         if (p == P_QN && !P.with_qn) continue;
-        const uint32_t bytes = 128u * (uint32_t)pass_n(p);
-        for (int kc = 0; kc < kPieces; ++kc) {
+        const int cpp = chunks_per_piece(p);
+        const uint32_t bytes = 128u * (uint32_t)pass_n(p) * (uint32_t)cpp;
+        for (int pc = 0; pc < kPieces / cpp; ++pc) {
           tc::mbar_wait(&S.w_empty[ring.stage], ring.phase ^ 1);
           tc::mbar_arrive_expect_tx(&S.w_full[ring.stage], bytes);
           bulk_load(S.w + ring.stage * kSlotBytes, src, bytes, &S.w_full[ring.stage]);
@@ -330,7 +346,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
     const uint32_t sa = tc::smem_u32(S.a), sw = tc::smem_u32(S.w);
     const uint64_t adesc_hi = tc::smem_desc(sa, 2048u, 128u), adesc_lo = tc::smem_desc(sa + kAHalf, 2048u, 128u);
     tc::Ring ring;
-    uint32_t ph_local = 0, ph_gather = 0;
+    uint32_t ph_local = 0, n_gather = 0;
     for (int p = 0; p < kNumPasses; ++p) {
       if (p == P_QN && !P.with_qn) continue;
       // which signal completes this pass's A operand
@@ -338,8 +354,11 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
         tc::mbar_wait(S.a_local, ph_local);
         ph_local ^= 1;
       } else if (p != P_F1B && p != P_F2B) {
-        wait_cluster(S.a_gather, ph_gather);
-        ph_gather ^= 1;
+        const uint32_t w = n_gather & 1;
+        wait_cluster(&S.a_gather[w], (n_gather >> 1) & 1);
+        // this barrier's next use is two gathers away: re-arm it now (bytes of that gather may already be landing)
+        if (leader) tc::mbar_arrive_expect_tx(&S.a_gather[w], kABytes);
+        ++n_gather;
       }
       fence_proxy_async_all();
       tc::tc_fence_after();
@@ -347,19 +366,23 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
       const uint32_t idesc = tc::idesc_g(kRows, N, false, false);
       const uint32_t lboB = 16u * (uint32_t)N;
       const uint32_t d = tmem_base + ((p == P_F1B || p == P_F2B) ? 128u : 0u);
-      for (int kc = 0; kc < kPieces; ++kc) {
+      const int cpp = chunks_per_piece(p);
+      for (int pc = 0; pc < kPieces / cpp; ++pc) {
         tc::mbar_wait(&S.w_full[ring.stage], ring.phase);
         tc::tc_fence_after();
         if (leader) {
-          const uint32_t w_hi = sw + ring.stage * kSlotBytes, w_lo = w_hi + 4u * lboB;
+          for (int cc = 0; cc < cpp; ++cc) {
+            const int kc = pc * cpp + cc;
+            const uint32_t w_hi = sw + ring.stage * kSlotBytes + (uint32_t)cc * 8u * lboB, w_lo = w_hi + 4u * lboB;
 #pragma unroll
-          for (int ks = 0; ks < kKc / 16; ++ks) {
-            const uint64_t a_step = (uint64_t)(((uint32_t)(kc * 4 + ks * 2) * 2048u) >> 4);
-            const uint64_t db_hi = tc::smem_desc(w_hi + ks * 2 * lboB, lboB, 128);
-            const uint64_t db_lo = tc::smem_desc(w_lo + ks * 2 * lboB, lboB, 128);
-            tc::mma_bf16_ss(d, adesc_lo + a_step, db_hi, idesc, (kc | ks) != 0);
-            tc::mma_bf16_ss(d, adesc_hi + a_step, db_lo, idesc, 1);
-            tc::mma_bf16_ss(d, adesc_hi + a_step, db_hi, idesc, 1);
+            for (int ks = 0; ks < kKc / 16; ++ks) {
+              const uint64_t a_step = (uint64_t)(((uint32_t)(kc * 4 + ks * 2) * 2048u) >> 4);
+              const uint64_t db_hi = tc::smem_desc(w_hi + ks * 2 * lboB, lboB, 128);
+              const uint64_t db_lo = tc::smem_desc(w_lo + ks * 2 * lboB, lboB, 128);
+              tc::mma_bf16_ss(d, adesc_lo + a_step, db_hi, idesc, (kc | ks) != 0);
+              tc::mma_bf16_ss(d, adesc_hi + a_step, db_lo, idesc, 1);
+              tc::mma_bf16_ss(d, adesc_hi + a_step, db_hi, idesc, 1);
+            }
           }
           tc::mma_commit(&S.w_empty[ring.stage]);
         }
@@ -377,6 +400,12 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
     const size_t grow = ((size_t)b * P.Q + (valid ? m : 0)) * kC;   // this row in the [B][Q][C] global tensors
     RowPhase ph;
     const int c0 = rank * kHd;                                       // first column of this CTA's slice
+    int dbg_i = 0;
+    int ng = 0;   // gathers so far: they alternate between the two transaction barriers
+    auto stamp = [&]() {
+      if (P.dbg != nullptr && threadIdx.x == 0 && dbg_i < 32) P.dbg[blockIdx.x * 32 + dbg_i++] = clock64();
+    };
+    stamp();
     auto acc_wait = [&]() {
       tc::mbar_wait(S.acc_full, ph.acc);
       ph.acc ^= 1;
@@ -420,24 +449,30 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(S.a_local);
     }
+    stamp();   // 1: A operand of O1 written
     float res[kHd];    // residual slice carried between blocks
     float v[kHd];
     load_slice(P.state + grow, res);
 
     // ---- O1: tgt = LN1(state + out_proj(attn))
     acc_wait();
+    stamp();   // 2: O1 product done
     tmem_ld32f(tl, v);
 #pragma unroll
     for (int j = 0; j < kHd; ++j) v[j] += __ldg(P.b_o1 + c0 + j) + res[j];
     layernorm_slice(S, ph, rank, m, lane, v, P.g1, P.be1, P.eps1);
+    stamp();   // 3: LN1 done
 #pragma unroll
     for (int j = 0; j < kHd; ++j) res[j] = v[j];
     tc::tc_fence_before();
-    a_free_sync(S, ph, threadIdx.x == 0);      // acc_wait above: this CTA's O1 product no longer reads its A buffer
-    gather_slice(S, rank, m, lane, v);
+    // no separate "A buffer free" round: the statistics exchange of the LayerNorm above completed only after every row
+    // warp of every CTA had passed its acc_wait, i.e. after every CTA's O1 product finished reading its A buffer
+    gather_slice(S, (ng++) & 1, rank, m, lane, v);
 
+    stamp();   // 4: gather of LN1 issued
     // ---- QKV (N = 96: q | k | v of head `rank`) and the self-attention of that head
     acc_wait();
+    stamp();   // 5: QKV product done
     float o2[kHd];
     {
       float q[kHd], k[kHd], vv[kHd];
@@ -469,21 +504,38 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
       float den = 0.f;
 #pragma unroll
       for (int j = 0; j < kHd; ++j) o2[j] = 0.f;
-      for (int key = 0; key < P.Q; ++key) {     // all lanes read the same key row: shared-memory broadcast
-        float s = 0.f;
+      // four keys per step with independent score chains (one warp per scheduler: only instruction-level parallelism
+      // hides the shared-memory and MUFU latencies); all lanes read the same key rows: broadcast loads
+      for (int key0 = 0; key0 < P.Q; key0 += 4) {
+        float sc[4], pw[4];
 #pragma unroll
-        for (int j4 = 0; j4 < kHd / 4; ++j4) {
-          const float4 kk = sk4[key * (kHd / 4) + j4];
-          s = fmaf(q[4 * j4], kk.x, s); s = fmaf(q[4 * j4 + 1], kk.y, s);
-          s = fmaf(q[4 * j4 + 2], kk.z, s); s = fmaf(q[4 * j4 + 3], kk.w, s);
+        for (int u = 0; u < 4; ++u) {
+          const int key = min(key0 + u, P.Q - 1);
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int j4 = 0; j4 < kHd / 4; j4 += 2) {
+            const float4 ka = sk4[key * (kHd / 4) + j4], kb = sk4[key * (kHd / 4) + j4 + 1];
+            s0 = fmaf(q[4 * j4], ka.x, s0); s0 = fmaf(q[4 * j4 + 1], ka.y, s0);
+            s0 = fmaf(q[4 * j4 + 2], ka.z, s0); s0 = fmaf(q[4 * j4 + 3], ka.w, s0);
+            s1 = fmaf(q[4 * j4 + 4], kb.x, s1); s1 = fmaf(q[4 * j4 + 5], kb.y, s1);
+            s1 = fmaf(q[4 * j4 + 6], kb.z, s1); s1 = fmaf(q[4 * j4 + 7], kb.w, s1);
+          }
+          sc[u] = s0 + s1;
         }
-        const float p = ex2(fmaf(s, P.c, -P.c));
-        den += p;
 #pragma unroll
-        for (int j4 = 0; j4 < kHd / 4; ++j4) {
-          const float4 t = sv4[key * (kHd / 4) + j4];
-          o2[4 * j4] = fmaf(p, t.x, o2[4 * j4]); o2[4 * j4 + 1] = fmaf(p, t.y, o2[4 * j4 + 1]);
-          o2[4 * j4 + 2] = fmaf(p, t.z, o2[4 * j4 + 2]); o2[4 * j4 + 3] = fmaf(p, t.w, o2[4 * j4 + 3]);
+        for (int u = 0; u < 4; ++u) {
+          pw[u] = (key0 + u < P.Q) ? ex2(fmaf(sc[u], P.c, -P.c)) : 0.f;
+          den += pw[u];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int key = min(key0 + u, P.Q - 1);
+#pragma unroll
+          for (int j4 = 0; j4 < kHd / 4; ++j4) {
+            const float4 t = sv4[key * (kHd / 4) + j4];
+            o2[4 * j4] = fmaf(pw[u], t.x, o2[4 * j4]); o2[4 * j4 + 1] = fmaf(pw[u], t.y, o2[4 * j4 + 1]);
+            o2[4 * j4 + 2] = fmaf(pw[u], t.z, o2[4 * j4 + 2]); o2[4 * j4 + 3] = fmaf(pw[u], t.w, o2[4 * j4 + 3]);
+          }
         }
       }
       float so = 0.f;
@@ -497,24 +549,30 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
       for (int j = 0; j < kHd; ++j) o2[j] *= io;
       named_bar_sync(1, kRowWarps * 32);         // every row is done with the scratch
     }
+    stamp();   // 6: self-attention done
     tc::tc_fence_before();
     a_free_sync(S, ph, threadIdx.x == 0);
-    gather_slice(S, rank, m, lane, o2);
+    stamp();   // 7: a_free round
+    gather_slice(S, (ng++) & 1, rank, m, lane, o2);
+    stamp();   // 8: gather issued
 
     // ---- O2: tgt = LN2(tgt + out_proj(self-attention))
     acc_wait();
+    stamp();   // 9: O2 product done
     tmem_ld32f(tl, v);
 #pragma unroll
     for (int j = 0; j < kHd; ++j) v[j] += __ldg(P.b_o2 + c0 + j) + res[j];
     layernorm_slice(S, ph, rank, m, lane, v, P.g2, P.be2, P.eps2);
+    stamp();   // 10: LN2 done
 #pragma unroll
     for (int j = 0; j < kHd; ++j) res[j] = v[j];
     tc::tc_fence_before();
-    a_free_sync(S, ph, threadIdx.x == 0);
-    gather_slice(S, rank, m, lane, v);
+    gather_slice(S, (ng++) & 1, rank, m, lane, v);           // (A buffers free: implied by the LayerNorm's statistics exchange)
 
+    stamp();   // 11: gather issued
     // ---- F1 (two passes of 128 hidden units): h = relu(tgt W1^T + b1) for this CTA's 256 hidden units -> LOCAL A operand
     acc_wait();
+    stamp();   // 12: F1 products done
     {
       const float* b1 = P.b_f1 + rank * 256;
 #pragma unroll 1
@@ -539,8 +597,10 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
       if (lane == 0) tc::mbar_arrive(S.a_local);
     }
 
+    stamp();   // 13: hidden activations converted
     // ---- F2 (K-split: partial sums over this CTA's hidden units, all 256 outputs) -> reduce-scatter -> LN3 -> normalise
     acc_wait();
+    stamp();   // 14: F2 products done
     tc::tc_fence_before();
     a_free_sync(S, ph, threadIdx.x == 0);      // every CTA's F2 product is complete: the A buffers become landing zones
     {
@@ -550,19 +610,16 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
         float y[32];
         tmem_ld32f(tl + r * 32, y);
         const uint32_t dst = mapa(a_local, r) + ((uint32_t)rank * kRows + (uint32_t)m) * 128u;
+        const uint32_t bar = mapa(tc::smem_u32(S.red_full), r);
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4)
-          st_cluster_v4(dst + j4 * 16, __float_as_uint(y[4 * j4]), __float_as_uint(y[4 * j4 + 1]),
-                        __float_as_uint(y[4 * j4 + 2]), __float_as_uint(y[4 * j4 + 3]));
+          st_async_v4(dst + j4 * 16, __float_as_uint(y[4 * j4]), __float_as_uint(y[4 * j4 + 1]),
+                      __float_as_uint(y[4 * j4 + 2]), __float_as_uint(y[4 * j4 + 3]), bar);
       }
-      __syncwarp();
-      if (lane == 0) {
-        const uint32_t bar = tc::smem_u32(S.red_full);
-#pragma unroll
-        for (int r = 0; r < kCluster; ++r) arrive_remote(mapa(bar, r));
-      }
+      stamp();   // 15: a_free + scatter issued
       wait_cluster(S.red_full, ph.red);
       ph.red ^= 1;
+      stamp();   // 16: slabs landed
 #pragma unroll
       for (int j = 0; j < kHd; ++j) v[j] = 0.f;
 #pragma unroll 1
@@ -575,7 +632,6 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
         }
       }
     }
-    named_bar_sync(1, kRowWarps * 32);   // ALL rows of this CTA have read the landing zone (a_free is signalled by one thread)
 #pragma unroll
     for (int j = 0; j < kHd; ++j) v[j] += __ldg(P.b_f2 + c0 + j) + res[j];
     layernorm_slice(S, ph, rank, m, lane, v, P.g3, P.be3, P.eps3);
@@ -585,11 +641,13 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
 #pragma unroll
     for (int j = 0; j < kHd; ++j) dec[j] = v[j];
     layernorm_slice(S, ph, rank, m, lane, dec, P.gd, P.bed, P.epsd);
+    stamp();   // 17: LN3, block norm, decoder_norm done
 
     // ---- QN: next layer's cross-attention query projection of the new state (+ projected query_pos table)
+    // (the landing zones are free again: every row warp of every CTA read its slabs before it arrived on the statistics
+    // exchanges of the LayerNorms above)
     if (P.with_qn) {
-      a_free_sync(S, ph, threadIdx.x == 0);    // landing zone read above
-      gather_slice(S, rank, m, lane, v);
+      gather_slice(S, (ng++) & 1, rank, m, lane, v);
       acc_wait();
       float qn[kHd];
       tmem_ld32f(tl, qn);
@@ -599,10 +657,11 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
       store_slice(P.q_next + grow, qn);
       tc::tc_fence_before();
     }
+    stamp();   // 18: QN done
 
     // ---- M1 (+ class head in columns 32..63): e1 = relu(dec Wm1^T + b); logits = dec Wc^T + bc
-    a_free_sync(S, ph, threadIdx.x == 0);
-    gather_slice(S, rank, m, lane, dec);
+    if (P.with_qn) a_free_sync(S, ph, threadIdx.x == 0);   // the QN product read the A buffers
+    gather_slice(S, (ng++) & 1, rank, m, lane, dec);
     acc_wait();
     tmem_ld32f(tl, v);
     if (rank == 0) {
@@ -621,8 +680,9 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
     for (int j = 0; j < kHd; ++j) v[j] = fmaxf(v[j] + __ldg(P.b_m1 + c0 + j), 0.f);
     tc::tc_fence_before();
     a_free_sync(S, ph, threadIdx.x == 0);
-    gather_slice(S, rank, m, lane, v);
+    gather_slice(S, (ng++) & 1, rank, m, lane, v);
 
+    stamp();   // 19: M1 done, gather issued
     // ---- M2
     acc_wait();
     tmem_ld32f(tl, v);
@@ -630,15 +690,18 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
     for (int j = 0; j < kHd; ++j) v[j] = fmaxf(v[j] + __ldg(P.b_m2 + c0 + j), 0.f);
     tc::tc_fence_before();
     a_free_sync(S, ph, threadIdx.x == 0);
-    gather_slice(S, rank, m, lane, v);
+    gather_slice(S, (ng++) & 1, rank, m, lane, v);
 
+    stamp();   // 20: M2 done, gather issued
     // ---- M3: the mask embedding
     acc_wait();
+    stamp();   // 21: M3 product done
     tmem_ld32f(tl, v);
 #pragma unroll
     for (int j = 0; j < kHd; ++j) v[j] += __ldg(P.b_m3 + c0 + j);
     store_slice(P.embed + grow, v);
     tc::tc_fence_before();
+    stamp();   // 22: end
   }
 
   __syncthreads();
@@ -651,6 +714,10 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
 }  // namespace msm
 
 using namespace msm;
+
+static long long* g_dbk_dbg = nullptr;
+// development only (tools/prof_block.py): device buffer [CTAs][32] for stage timestamps of the next launches, or null
+extern "C" void msmx_decoder_block_debug(long long* buf) { g_dbk_dbg = buf; }
 
 extern "C" size_t msm_decoder_block_weight_bytes(int with_qn) { return (size_t)dbk::kCluster * dbk::blob_bytes(with_qn != 0); }
 
@@ -682,6 +749,7 @@ extern "C" int msm_decoder_block_fwd(const float* o_cross, const float* state, c
   P.B = B; P.Q = Q; P.block_norm = block_norm; P.with_qn = q_next != nullptr;
   P.eps1 = eps1; P.eps2 = eps2; P.eps3 = eps3; P.epsd = epsd;
   P.c = kappa * kLog2e;
+  P.dbg = g_dbk_dbg;
   const size_t smem = 128 + dbk::kABytes + dbk::kSlots * dbk::kSlotBytes + dbk::kStatsBytes + 256;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MSM_CUDA(cudaFuncSetAttribute(dbk::decoder_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -471,7 +471,7 @@ using namespace msm;
 extern "C" size_t msmx_mean_shift_persistent_workspace_bytes(int B, int n, int m, int d) {
   const msp::Plan pl = msp::plan(B, n);
   return 256 + 2 * (((size_t)B * sizeof(uint32_t) + 255) & ~(size_t)255) +
-         2 * (size_t)B * pl.maxparts * m * (d + 1) * sizeof(float) + 2 * (size_t)B * m * d * sizeof(float);
+         2 * (size_t)B * pl.maxparts * m * (d + 1) * sizeof(float) + 16 + 2 * (size_t)B * m * d * sizeof(float);
 }
 
 // packed: msmx_mean_shift_pack output (bf16 hi | lo images of 128 points). One cooperative launch for all iterations.
@@ -495,7 +495,7 @@ extern "C" int msmx_mean_shift_hill_climb_persistent(const void* packed, const f
   P.counter2 = reinterpret_cast<uint32_t*>(ws + cbytes);
   P.part_acc = reinterpret_cast<float*>(ws + 2 * cbytes);
   P.part_den = P.part_acc + 2 * (size_t)B * pl.maxparts * m * d;
-  P.z_buf = P.part_den + 2 * (size_t)B * pl.maxparts * m;
+  P.z_buf = P.part_den + ((2 * (size_t)B * pl.maxparts * m + 3) & ~(size_t)3);   // 16-byte aligned rows (float4 stores)
   P.packed = static_cast<const uint8_t*>(packed);
   P.z0 = Z0;
   P.z_out = Z_out;

@@ -611,7 +611,11 @@ def ffn_ln(x, w1, b1, w2, b2, norm):
 # one decoder layer after its cross-attention, as ONE cluster kernel per layer (csrc/decoder_block.cu)
 # ----------------------------------------------------------------------------------------------
 def decoder_block_enabled():
-    return os.environ.get("MSM_DECODER_BLOCK", "1") == "1"
+    """Opt-in (MSM_DECODER_BLOCK=1). Measured on B200 (R50 config, batch 8): the cluster kernel takes 135-148 us per layer
+    and brings the step from 212 to 97 launches, but the 16 launches it replaces cost ~120 us, so the step is 4 % slower
+    (4.61-4.66 vs 4.44 ms) - the all-gathers through distributed shared memory (128 KB into each of 8 CTAs, ~5 us each,
+    7 per layer) and the CUDA-core self-attention (22 us) pace it; DESIGN.md section 4.3c has the stage timing."""
+    return os.environ.get("MSM_DECODER_BLOCK", "0") == "1"
 
 
 def _dbk_pieces(w):
