@@ -1,10 +1,10 @@
-"""cuDNN math / layout variants of the R50 backbone at B=8 640x480 (B200 box): which fp32 path is usable?"""
-import sys, os, time, itertools
+"""cuDNN variants of the R50 backbone at B=8 640x480 (B200 box): math (TF32 / fp32), layout, fused conv+bias+ReLU."""
+import sys, os, itertools
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from unseenobjectswithmeanshift_b200 import backbones
 
-def timed(fn, reps=5):
+def timed(fn, reps=10):
     for _ in range(3): fn()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -14,21 +14,18 @@ def timed(fn, reps=5):
     return a.elapsed_time(b) / reps
 
 x = torch.randn(8, 3, 480, 640, device="cuda")
-for tf32, cl, bench in itertools.product((False, True), (True, False), (False, True)):
-    torch.backends.cudnn.benchmark = bench
+ref = None
+for tf32, fused in itertools.product((True, False), (False, True)):
     backbones.set_tf32(tf32)
-    m = backbones.ResNet50Features().cuda()
-    if not cl:
-        m = m.to(memory_format=torch.contiguous_format)
-        fwd = m.forward
-        def run(m=m):
-            with backbones._conv_math():
-                y = m.stem(x); out = {}
-                for name in ("res2", "res3", "res4", "res5"):
-                    y = getattr(m, name)(y); out[name] = y
-            return out
-    else:
-        run = lambda m=m: m(x)
+    m = backbones.ResNet50Features(fused_relu=fused).cuda()
     with torch.no_grad():
-        t = timed(run)
-    print(f"tf32={tf32} channels_last={cl} cudnn.benchmark={bench}: {t:.2f} ms", flush=True)
+        out = m(x)
+        if ref is None:
+            ref = out
+        err = max(((out[k] - ref[k]).abs().max() / ref[k].abs().max()).item() for k in out)
+        t = timed(lambda: m(x))
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            m(x)
+        tg = timed(g.replay)
+    print(f"tf32={tf32} fused_relu={fused}: eager {t:.2f} ms, graph {tg:.2f} ms, max rel diff vs first {err:.2e}", flush=True)

@@ -66,8 +66,9 @@ class ResNet50Features(nn.Module):
 
     size_divisibility = 32
 
-    def __init__(self, seed=0, fold_bn=True):
+    def __init__(self, seed=0, fold_bn=True, fused_relu=True):
         super().__init__()
+        self.fused_relu = bool(fused_relu and fold_bn)   # cuDNN conv + bias + (residual) + ReLU kernels at inference
         import torchvision
         g = torch.random.get_rng_state()
         torch.manual_seed(5000 + seed)
@@ -96,13 +97,35 @@ class ResNet50Features(nn.Module):
     def train(self, mode=True):  # FrozenBN semantics: never leaves eval mode
         return super().train(False)
 
+    @staticmethod
+    def _conv_relu(conv, x):
+        return torch.cudnn_convolution_relu(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
+
+    def _bottleneck_fused(self, blk, x):
+        """torchvision Bottleneck.forward with cuDNN's fused conv + bias + ReLU and conv + bias + residual add + ReLU
+        (the BatchNorms are folded): three launches per block instead of eight."""
+        y = self._conv_relu(blk.conv1, x)
+        y = self._conv_relu(blk.conv2, y)
+        idt = x if blk.downsample is None else blk.downsample(x)
+        c3 = blk.conv3
+        return torch.cudnn_convolution_add_relu(y, c3.weight, idt, 1.0, c3.bias, c3.stride, c3.padding, c3.dilation,
+                                                c3.groups)
+
     def forward(self, x):
         x = x.contiguous(memory_format=self.fmt)
+        fused = self.fused_relu and x.is_cuda and not torch.is_grad_enabled()
         with _conv_math(self.tf32):
-            x = self.stem(x)
+            if fused:
+                x = self.stem[3](self._conv_relu(self.stem[0], x))
+            else:
+                x = self.stem(x)
             out = {}
             for name in ("res2", "res3", "res4", "res5"):
-                x = getattr(self, name)(x)
+                if fused:
+                    for blk in getattr(self, name):
+                        x = self._bottleneck_fused(blk, x)
+                else:
+                    x = getattr(self, name)(x)
                 out[name] = x.contiguous()  # the head's kernels take NCHW-contiguous fp32
         return out
 
@@ -118,8 +141,22 @@ class _BasicBlock(nn.Module):
         self.bn2 = nn.BatchNorm2d(cout)
         self.downsample = downsample
 
+    def fold(self):
+        """eval-mode BatchNorms folded into the convolutions (inference): enables cuDNN's fused conv + bias + ReLU."""
+        with torch.no_grad():
+            self.conv1, self.bn1 = _fold_bn(self.conv1, self.bn1), nn.Identity()
+            self.conv2, self.bn2 = _fold_bn(self.conv2, self.bn2), nn.Identity()
+            if self.downsample is not None:
+                self.downsample = nn.Sequential(_fold_bn(self.downsample[0], self.downsample[1]))
+        self.folded = True
+
     def forward(self, x):
         idt = x if self.downsample is None else self.downsample(x)
+        if getattr(self, "folded", False) and x.is_cuda and not torch.is_grad_enabled():
+            c1, c2 = self.conv1, self.conv2
+            y = torch.cudnn_convolution_relu(x, c1.weight, c1.bias, c1.stride, c1.padding, c1.dilation, c1.groups)
+            return torch.cudnn_convolution_add_relu(y, c2.weight, idt, 1.0, c2.bias, c2.stride, c2.padding, c2.dilation,
+                                                    c2.groups)
         y = F.relu(self.bn1(self.conv1(x)))
         y = self.bn2(self.conv2(y))
         return F.relu(y + idt)
@@ -166,6 +203,14 @@ class SegnetEmbedding(nn.Module):
         self.fcn = _Resnet34_8s(64)
         self.fcn_depth = _Resnet34_8s(64) if use_depth else None
         torch.random.set_rng_state(g)
+        self.eval()
+        for net in (self.fcn, self.fcn_depth):
+            if net is not None:
+                with torch.no_grad():
+                    net.conv1, net.bn1 = _fold_bn(net.conv1, net.bn1), nn.Identity()
+                for layer in (net.layer1, net.layer2, net.layer3, net.layer4):
+                    for blk in layer:
+                        blk.fold()
         for p in self.parameters():
             p.requires_grad_(False)
         self.eval()
