@@ -763,6 +763,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    args.numa = sharding.pin_to_gpu_numa(local_rank) if world > 1 else "single process: not pinned"
     kind = args.workload
     if args.batch <= 0 and kind in ("train", "twostage", "tail"):
         args.batch = 16 if kind == "twostage" else PER_GPU_BATCH
@@ -1111,6 +1112,7 @@ def run_forward(args, rank, local_rank, world, dev, sharding, ops, workloads):
               "queries": 100, "decoder_layers": hk_cfg["dec_layers"],
               "launch": "eager" if args.no_graph else "one CUDA graph per step",
               "global_batch": B * world, "parallelism": f"replicas x{world} (batch-sharded, no collective)",
+              "numa": args.numa,
               "l2_policy": "inputs_exceed_l2 (every decoder layer streams the mask features - 157 MB at batch 8 - and "
                            "writes a fresh logits tensor; backbone activations exceed L2)",
               "backbone": (f"included: torchvision ResNet-50, cuDNN {'fp32 (TF32 off, NCHW)' if args.backbone_fp32 else 'at PyTorch default conv math (TF32), channels_last'}, channels_last" if kind == "r50"

@@ -50,3 +50,36 @@ def sum_over_ranks(value, device="cpu"):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def pin_to_gpu_numa(local_rank):
+    """Restrict this process to the CPUs of the NUMA node its GPU hangs off (sysfs: the PCI device's ``numa_node``), so
+    that pinned host buffers allocated afterwards are first-touched on that node and the H2D / D2H copies of the ranks
+    of one box do not all cross the same socket (round 1: 8 ranks on NUMA 0, end-to-end scaling efficiency 0.35).
+    Returns a one-line description for the bench record; never raises (returns the reason when it cannot pin)."""
+    try:
+        p = torch.cuda.get_device_properties(local_rank)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return f"gpu {local_rank} ({bus}): no NUMA affinity reported"
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return f"gpu {local_rank} ({bus}): NUMA node {node} has no CPU this process may use"
+        os.sched_setaffinity(0, allowed)
+        return f"gpu {local_rank} ({bus}) -> NUMA node {node}, {len(allowed)} CPUs"
+    except Exception as e:  # informational: sysfs layout, containers, cpusets differ
+        return f"not pinned: {e!r}"
