@@ -48,9 +48,13 @@ def main():
             loc = torch.rand(N, S, M, L, P, 2, device=dev, generator=g)
             aw = torch.softmax(rn(N, S, M, L * P), -1).view(N, S, M, L, P)
             fn = lambda: ops.ms_deform_attn_forward(value, shapes, lsi, loc, aw)  # noqa: E731
-        elif a.what in ("linear_kv", "linear_ffn1", "linear_ffn2", "linear_ucn"):
+        elif a.what in ("linear_kv", "linear_ffn1", "linear_ffn2", "linear_ucn", "linear_ow", "linear_vp", "linear_small",
+                        "linear_small_ffn1", "linear_small_ffn2", "linear_mf"):
             M, N, K = {"linear_kv": (38400, 768, 256), "linear_ffn1": (50400, 1024, 64),
-                       "linear_ffn2": (50400, 64, 1024), "linear_ucn": (307200, 256, 256)}[a.what]
+                       "linear_ffn2": (50400, 64, 1024), "linear_ucn": (307200, 256, 256),
+                       "linear_ow": (50400, 288, 64), "linear_vp": (50400, 64, 64), "linear_small": (800, 256, 256),
+                       "linear_small_ffn1": (800, 2048, 256), "linear_small_ffn2": (800, 256, 2048),
+                       "linear_mf": (153600, 256, 64)}[a.what]
             x, w, b = rn(M, K), rn(N, K) / K ** 0.5, rn(N)
             out = torch.empty(M, N, device=dev)
             fn = lambda: ops.linear(x, w, b, out=out)  # noqa: E731
