@@ -379,3 +379,31 @@ def test_decoder_block_kernel_vs_fp64(B, Qn, last, block_norm):
         assert q_next is None
     else:
         assert (d(q_next) - qn).abs().max().item() / qn.abs().max().item() < 3e-5
+
+
+def test_lean_eval_path_matches_full_masks():
+    """eval_aux_masks=False (what the META_ARCH wrappers set: the eval branch never reads aux_outputs): intermediate
+    layers compute their mask logits on the next layer's key grid only - interpolate(einsum(e, F)) == einsum(e,
+    interpolate(F)). The final prediction must agree with the full path; an intermediate prediction's low-resolution
+    logits must equal the bilinear resample of the full path's logits."""
+    m, _ = _decoder(3)
+    m = m.cuda()
+    x, mf = _inputs(2, 3)
+    xc, mfc = [t.cuda() for t in x], mf.cuda()
+    with torch.no_grad():
+        full = m(xc, mfc)
+        m.eval_aux_masks = False
+        lean = m(xc, mfc)
+        m.eval_aux_masks = True
+    assert lean["pred_masks"].shape == full["pred_masks"].shape
+    # prediction 0 (from the learnable queries) feeds layer 0 at the 15x20 grid
+    lo = lean["aux_outputs"][0]["pred_masks"]
+    assert tuple(lo.shape[-2:]) == LEVELS[0]
+    want = F.interpolate(full["aux_outputs"][0]["pred_masks"], size=LEVELS[0], mode="bilinear", align_corners=False)
+    assert peak_rel(lo, want) < 2e-5
+    # the two paths may disagree on a mask bit whose logit is within 1e-6 of zero; what they must not do is differ visibly
+    assert peak_rel(lean["pred_logits"], full["pred_logits"]) < 1e-2
+    agree = (lean["pred_masks"].argmax(1) == full["pred_masks"].argmax(1)).float().mean().item()
+    assert agree > 0.995, agree
+    first = peak_rel(lean["aux_outputs"][1]["pred_logits"], full["aux_outputs"][1]["pred_logits"])
+    assert first < 1e-4, first   # after one layer (before any flip can matter much) the class logits are identical

@@ -74,6 +74,10 @@ class _MetaArchBase(nn.Module):
                 size_divisibility, sem_seg_postprocess_before_inference, pixel_mean, pixel_std, semantic_on,
                 panoptic_on, instance_on, test_topk_per_image, use_embedding_loss):
         self.sem_seg_head = sem_seg_head
+        # the eval branch never reads aux_outputs (reference :335-378): let the decoder skip their full-resolution masks
+        predictor = getattr(sem_seg_head, "predictor", None)
+        if predictor is not None and hasattr(predictor, "eval_aux_masks"):
+            predictor.eval_aux_masks = False
         self.criterion = criterion if criterion is not None else _CriterionState(sem_seg_head.num_classes)
         self.num_queries = num_queries
         self.overlap_threshold = overlap_threshold

@@ -232,6 +232,12 @@ class _MeanShiftDecoderBase(nn.Module):
         self.num_layers = dec_layers
         self.pre_norm = pre_norm
         self.use_meanshift_seeds = False  # hard-coded in the reference (:424, :778)
+        # Reference behaviour (True): every prediction, also in eval mode, carries its full-resolution mask logits in
+        # ``aux_outputs``. The eval branch of the META_ARCH never reads them (pretrained_meanshiftformer_model.py:
+        # 335-378), so the wrappers of this package set it False: intermediate layers then compute their masks only on
+        # the next layer's key grid (``_lean_masks``) and ``aux_outputs[i]["pred_masks"]`` holds those low-resolution
+        # logits. Training (grad enabled) always produces the full masks.
+        self.eval_aux_masks = True
         self.use_meanshift_cross_attention = use_meanshift_cross_attention
         self.disable_attention_mask = disable_attention_mask
         self.use_meanshift_self_attention = use_meanshift_self_attention
@@ -291,13 +297,17 @@ class _MeanShiftDecoderBase(nn.Module):
         }
 
     # ------------------------------------------------------------------ prediction heads
-    def _heads(self, out, mask_features, target_size, need_mask, dec=None):
+    def _heads(self, out, mask_features, target_size, need_mask, dec=None, lean_features=None):
         """out [B,Q,C] -> (class logits [B,Q,K+1], mask logits [B,Q,h,w], bits, row_open).
-        ``dec`` = decoder_norm(out) when the caller already has it (fused into the previous GEMM's epilogue)."""
+        ``dec`` = decoder_norm(out) when the caller already has it (fused into the previous GEMM's epilogue).
+        ``lean_features``: the mask features already resampled to ``target_size`` (see ``eval_aux_masks``) - the mask
+        logits are then computed at that resolution only."""
         if dec is None:
             dec = self.decoder_norm(out)
         logits = ops.dense(dec, self.class_embed.weight, self.class_embed.bias)   # N = K + 1: padded to 32 columns
         embed = self.mask_embed(dec)
+        if lean_features is not None:
+            return (logits,) + self._lean_masks(embed, lean_features, target_size)
         if torch.is_grad_enabled() and (embed.requires_grad or mask_features.requires_grad):
             masks = ops.mask_logits_autograd(embed, mask_features)  # training (row f4)
         else:
@@ -306,6 +316,16 @@ class _MeanShiftDecoderBase(nn.Module):
         if need_mask:  # the attention mask is a constant of the graph (reference :680 detaches it)
             bits, row_open = ops.mask_to_attn_bits(masks.detach(), target_size)
         return logits, masks, bits, row_open
+
+    @staticmethod
+    def _lean_masks(embed, lean_features, target_size):
+        """Inference without auxiliary full-resolution masks: interpolate(einsum(e, F)) == einsum(e, interpolate(F))
+        (both linear), so an intermediate layer's attention-mask bits need the mask logits only on the NEXT layer's key
+        grid: 300 / 1200 / 4800 pixels instead of 19200, and 157 MB of mask features are not re-read per layer.
+        -> (low-resolution logits [B,Q,ht,wt], bits, row_open)."""
+        masks = ops.mask_logits(embed, lean_features)
+        bits, row_open = ops.mask_to_attn_bits(masks, target_size)
+        return masks, bits, row_open
 
     def forward_prediction_heads(self, output, mask_features, attn_mask_target_size):
         """Reference :660-682 / :1012-1035 (seq-first ``output`` [Q,B,C]); returns the reference's
@@ -440,8 +460,22 @@ class _MeanShiftDecoderBase(nn.Module):
         if l2_window:
             ops.l2_persist(mask_features)
 
+        lean = (not train and not self.eval_aux_masks and need_mask and _teacher is None
+                and any(tuple(sz) != tuple(mask_features.shape[-2:]) for sz in sizes))
+        lean_cache = {}
+
+        def lean_features(size):
+            """mask features resampled (bilinear, align_corners=False, as :675) to a key grid, once per forward"""
+            if not lean or tuple(size) == tuple(mask_features.shape[-2:]):
+                return None
+            key = tuple(size)
+            if key not in lean_cache:
+                lean_cache[key] = F.interpolate(mask_features, size=key, mode="bilinear", align_corners=False).contiguous()
+            return lean_cache[key]
+
         predictions_class, predictions_mask = [], []
-        logits, masks, bits, row_open = self._heads(out, mask_features, sizes[0], need_mask)
+        logits, masks, bits, row_open = self._heads(out, mask_features, sizes[0], need_mask,
+                                                    lean_features=lean_features(sizes[0]))
         predictions_class.append(logits)
         predictions_mask.append(masks)
 
@@ -517,10 +551,14 @@ class _MeanShiftDecoderBase(nn.Module):
                     t_qn=tq_table(i + 1) if nxt is not None else None, b_m1=mlp[0].bias, b_c32=bc32, b_m2=mlp[1].bias,
                     b_m3=mlp[2].bias)
                 logits = logits32[..., :self.class_embed.weight.shape[0]]
-                masks = ops.mask_logits(embed, mask_features)
-                bits = row_open = None
-                if need_mask:
-                    bits, row_open = ops.mask_to_attn_bits(masks, sizes[(i + 1) % L])
+                lf = lean_features(sizes[(i + 1) % L]) if i + 1 < self.num_layers else None
+                if lf is not None:
+                    masks, bits, row_open = self._lean_masks(embed, lf, sizes[(i + 1) % L])
+                else:
+                    masks = ops.mask_logits(embed, mask_features)
+                    bits = row_open = None
+                    if need_mask:
+                        bits, row_open = ops.mask_to_attn_bits(masks, sizes[(i + 1) % L])
                 predictions_class.append(logits)
                 predictions_mask.append(masks)
                 continue
@@ -560,7 +598,9 @@ class _MeanShiftDecoderBase(nn.Module):
                                    ffn.linear2.weight, ffn.linear2.bias)
                     out, dec = ops.add_layernorm(out, t2, ffn.norm, l2_normalize=self.decoder_block_norm,
                                                  norm2=self.decoder_norm)
-                logits, masks, bits, row_open = self._heads(out, mask_features, sizes[(i + 1) % L], need_mask, dec=dec)
+                logits, masks, bits, row_open = self._heads(
+                    out, mask_features, sizes[(i + 1) % L], need_mask, dec=dec,
+                    lean_features=lean_features(sizes[(i + 1) % L]) if i + 1 < self.num_layers else None)
                 predictions_class.append(logits)
                 predictions_mask.append(masks)
                 continue
@@ -579,7 +619,9 @@ class _MeanShiftDecoderBase(nn.Module):
             out = ffn(out)
             if self.decoder_block_norm:
                 out = F.normalize(out, dim=-1)
-            logits, masks, bits, row_open = self._heads(out, mask_features, sizes[(i + 1) % L], need_mask)
+            logits, masks, bits, row_open = self._heads(
+                out, mask_features, sizes[(i + 1) % L], need_mask,
+                lean_features=lean_features(sizes[(i + 1) % L]) if i + 1 < self.num_layers else None)
             predictions_class.append(logits)
             predictions_mask.append(masks)
 
