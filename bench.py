@@ -59,7 +59,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.idx, self.proc, self.lines = gpu_index, None, []
+        self.idx, self.proc, self.lines, self.skip = gpu_index, None, [], 0
 
     def start(self):
         try:
@@ -67,6 +67,12 @@ class ClockSampler:
                                           "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            # nvidia-smi takes 0.1-0.3 s to attach to the driver and stalls kernel launches while it does: wait for
+            # its first sample HERE, before the timed region is opened, and count only the samples after it
+            t0 = time.perf_counter()
+            while not self.lines and time.perf_counter() - t0 < 3.0 and self.proc.poll() is None:
+                time.sleep(0.01)
+            self.skip = len(self.lines)
         except OSError:
             self.proc = None
 
@@ -80,7 +86,7 @@ class ClockSampler:
         time.sleep(0.25)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in (self.lines[self.skip:] or self.lines):
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -268,9 +274,9 @@ def run_meanshift(args, rank, local_rank, world, dev, sharding, ops):
         for _ in range(args.warmup):
             ops.mean_shift_hill_climb(X, Z0, kappa, iters)
         torch.cuda.synchronize()
-        sharding.barrier()
         if rank == 0:
             sampler.start()
+        sharding.barrier()
         ops.reset_stats()
         e0.record()
         for _ in range(args.steps):
@@ -385,9 +391,9 @@ def run_cluster(args, rank, local_rank, world, dev, sharding, ops):
             torch.cuda.synchronize()
             for i in range(4):
                 stage_ms[i] += ev[i].elapsed_time(ev[i + 1]) / 3
-        sharding.barrier()
         if rank == 0:
             sampler.start()
+        sharding.barrier()
         ops.reset_stats()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -486,9 +492,9 @@ def run_tail(args, rank, local_rank, world, dev, sharding, ops):
         graphed = None if args.no_graph else GraphedForward(step, {"logits": logits, "masks": masks}, warmup=2)
         run = (lambda: step({"logits": logits, "masks": masks})) if graphed is None else (lambda: graphed())
         torch.cuda.synchronize()
-        sharding.barrier()
         if rank == 0:
             sampler.start()
+        sharding.barrier()
         total = 0.0
         for _ in range(args.steps):   # outputs (197 MB) would otherwise sit in L2: flush between steps, untimed
             flush.zero_()
@@ -542,7 +548,9 @@ def run_tail(args, rank, local_rank, world, dev, sharding, ops):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"tail Q=100 120x160->480x640 top-20 batch {B}/GPU", "global_batch": B * world,
-                       "launch": "eager" if args.no_graph else "one CUDA graph per step",
+                       "launch": "eager" if args.no_graph else "one CUDA graph per step" + (
+                  f", {n_fl} steps in flight on {n_fl} streams (each graph has its own static buffers)" if n_fl > 1 else ""),
+              "inflight": n_fl,
                        "parallelism": f"replicas x{world} (batch-sharded, no collective)",
                        "l2_policy": "l2_flushed_between_steps (256 MB memset, untimed)"},
             "clocks": clocks,
@@ -601,9 +609,9 @@ def run_twostage(args, rank, local_rank, world, dev, sharding, ops):
         _, crops = step(img, depth)
         launches_per_step = ops.launches()
         torch.cuda.synchronize()
-        sharding.barrier()
         if rank == 0:
             sampler.start()
+        sharding.barrier()
         e0.record()
         for _ in range(args.steps):   # every frame streams a 79 MB embedding map and 315 MB of mask features
             step(img, depth)
@@ -672,9 +680,9 @@ def run_train(args, rank, local_rank, world, dev, sharding, ops):
     training.train_step(ddp, opt, {"features": feats, "targets": targets})
     launches_per_step = ops.launches()
     torch.cuda.synchronize()
-    sharding.barrier()
     if rank == 0:
         sampler.start()
+    sharding.barrier()
     e0.record()
     for _ in range(args.steps):   # 295 MB of features + every layer's masks and gradients per step: far beyond L2
         losses = training.train_step(ddp, opt, {"features": feats, "targets": targets})
@@ -741,6 +749,9 @@ def main():
                          "Default: PyTorch's own default conv math on a GPU (TF32), i.e. what the reference's stock code "
                          "does there; the head and the tail never use TF32 either way")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inflight", type=int, default=2,
+                    help="forward workloads: graph replays in flight at once (each with its own static buffers, on its own "
+                         "stream); 1 = one step after another")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--vmf-tflops", action="store_true", help="also time the attention core alone (default with the CPU baseline)")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: leave out the host-buffer leg")
@@ -897,8 +908,6 @@ def run_forward(args, rank, local_rank, world, dev, sharding, ops, workloads):
         op_ms = {k: (c / n_eager, t / n_eager) for k, (c, t) in ops.op_times_ms().items()}
         op_groups = ops.op_groups()
         ops.reset_stats(timing=False)
-        if rank == 0 and not args.skip_profile:
-            shares = _kernel_shares(lambda: step(dev_in))
         if full:   # where the step's time goes: backbone (cuDNN, outside the hot path) | head | tail, eager + events
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             acc = [0.0, 0.0, 0.0]
@@ -922,19 +931,53 @@ def run_forward(args, rank, local_rank, world, dev, sharding, ops, workloads):
             parts_ms = {"backbone_cudnn": acc[0], "head": acc[1], "tail": acc[2], "how": "eager, CUDA events"}
 
         # ---------------- the step as ONE CUDA graph (static input / output buffers resident in HBM)
-        graphed = None if args.no_graph else GraphedForward(step, dev_in, warmup=2)
+        # `--inflight F` (default 2): F graphs with their own static buffers, replayed round-robin on F streams, so
+        # that step i+1 starts while step i is still in its latency-bound phases (the 800-row decoder launches fill 64
+        # of 148 SMs). Every step is still one whole batch through the whole path; `serial` below is F = 1.
+        n_fl = 1 if args.no_graph else max(1, args.inflight)
+        graphs = [] if args.no_graph else [GraphedForward(step, dev_in, warmup=2) for _ in range(n_fl)]
+        graphed = graphs[0] if graphs else None
+        s_main = torch.cuda.current_stream()
+        lanes = [s_main] if n_fl == 1 else [torch.cuda.Stream() for _ in range(n_fl)]
         runner = (lambda inp=None: step(dev_in)) if graphed is None else (lambda inp=None: graphed(inp))
+
+        def replay_steps(n, nf):
+            """n steps, nf of them in flight; brackets the work on the current stream."""
+            if nf == 1:
+                for _ in range(n):
+                    runner()
+                return
+            fork = torch.cuda.Event()
+            fork.record(s_main)
+            for i in range(n):
+                with torch.cuda.stream(lanes[i % nf]):
+                    if i < nf:
+                        lanes[i].wait_event(fork)
+                    graphs[i % nf]()
+            for ln in lanes[:nf]:
+                s_main.wait_stream(ln)
+
         for _ in range(args.warmup):
             runner()
+        replay_steps(2 * n_fl, n_fl)
         torch.cuda.synchronize()
-        sharding.barrier()
         if rank == 0:
             sampler.start()
+        sharding.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ms_serial = None
+        if n_fl > 1:   # the same steps one after another (step latency), reported beside the pipelined figure
+            n_ser = max(3, args.steps // 4)
+            torch.cuda.synchronize()
+            e0.record()
+            replay_steps(n_ser, 1)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_serial = sharding.max_over_ranks(e0.elapsed_time(e1), dev) / n_ser
         torch.cuda.synchronize()
+        sharding.barrier()
         e0.record()
-        for _ in range(args.steps):
-            runner()
+        replay_steps(args.steps, n_fl)
         e1.record()
         torch.cuda.synchronize()
         sharding.barrier()
@@ -948,36 +991,47 @@ def run_forward(args, rank, local_rank, world, dev, sharding, ops, workloads):
         out_keys = [k for k in out_keys if k in out0]
         host_out = {k: torch.empty(out0[k].shape, dtype=out0[k].dtype).pin_memory() for k in out_keys}
         h2d, d2h = _bytes(host_in), _bytes(host_out)
-        static_in = graphed.static_in if graphed is not None else dev_in
-        stage_in = {k: torch.empty_like(v) for k, v in static_in.items()}
-        stage_out = {k: torch.empty_like(out0[k]) for k in out_keys}
-        s_main, s_h2d, s_d2h = torch.cuda.current_stream(), torch.cuda.Stream(), torch.cuda.Stream()
-        ev_in_ready, ev_in_free = torch.cuda.Event(), torch.cuda.Event()
-        ev_out_ready, ev_out_free = torch.cuda.Event(), torch.cuda.Event()
+        static_ins = [g.static_in for g in graphs] if graphs else [dev_in]
+        stage_in = [{k: torch.empty_like(v) for k, v in static_ins[0].items()} for _ in range(n_fl)]
+        stage_out = [{k: torch.empty_like(out0[k]) for k in out_keys} for _ in range(n_fl)]
+        s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
+        ev_in_ready, ev_in_free = [torch.cuda.Event() for _ in range(n_fl)], [torch.cuda.Event() for _ in range(n_fl)]
+        ev_out_ready, ev_out_free = [torch.cuda.Event() for _ in range(n_fl)], [torch.cuda.Event() for _ in range(n_fl)]
 
         def e2e_steps(n):
-            ev_in_free.record(s_main)
-            ev_out_free.record(s_d2h)
-            for _ in range(n):
+            fork = torch.cuda.Event()
+            fork.record(s_main)
+            for f in range(n_fl):
+                lanes[f].wait_event(fork)
+                ev_in_free[f].record(lanes[f])
+                s_d2h.wait_event(fork)
+                ev_out_free[f].record(s_d2h)
+            s_h2d.wait_event(fork)
+            for i in range(n):
+                f = i % n_fl
+                lane = lanes[f]
                 with torch.cuda.stream(s_h2d):
-                    s_h2d.wait_event(ev_in_free)            # previous contents of stage_in consumed
-                    for k in stage_in:
-                        stage_in[k].copy_(host_in[k], non_blocking=True)
-                    ev_in_ready.record(s_h2d)
-                s_main.wait_event(ev_in_ready)
-                for k in static_in:
-                    static_in[k].copy_(stage_in[k], non_blocking=True)
-                ev_in_free.record(s_main)
-                out = runner()
-                s_main.wait_event(ev_out_free)              # previous contents of stage_out are on the host
-                for k in out_keys:
-                    stage_out[k].copy_(out[k], non_blocking=True)
-                ev_out_ready.record(s_main)
-                with torch.cuda.stream(s_d2h):
-                    s_d2h.wait_event(ev_out_ready)
+                    s_h2d.wait_event(ev_in_free[f])         # previous contents of stage_in[f] consumed
+                    for k in stage_in[f]:
+                        stage_in[f][k].copy_(host_in[k], non_blocking=True)
+                    ev_in_ready[f].record(s_h2d)
+                with torch.cuda.stream(lane):
+                    lane.wait_event(ev_in_ready[f])
+                    for k in static_ins[f]:
+                        static_ins[f][k].copy_(stage_in[f][k], non_blocking=True)
+                    ev_in_free[f].record(lane)
+                    out = graphs[f]() if graphs else step(dev_in)
+                    lane.wait_event(ev_out_free[f])         # previous contents of stage_out[f] are on the host
                     for k in out_keys:
-                        host_out[k].copy_(stage_out[k], non_blocking=True)
-                    ev_out_free.record(s_d2h)
+                        stage_out[f][k].copy_(out[k], non_blocking=True)
+                    ev_out_ready[f].record(lane)
+                with torch.cuda.stream(s_d2h):
+                    s_d2h.wait_event(ev_out_ready[f])
+                    for k in out_keys:
+                        host_out[k].copy_(stage_out[f][k], non_blocking=True)
+                    ev_out_free[f].record(s_d2h)
+            for ln in lanes:
+                s_main.wait_stream(ln)
             s_main.wait_stream(s_h2d)
             s_main.wait_stream(s_d2h)
 
@@ -1054,12 +1108,6 @@ def run_forward(args, rank, local_rank, world, dev, sharding, ops, workloads):
             "tensor_frac": 3.0 * lib_flops / step_ms / 1e9 / peaks["bf16_tflops"],
             "note": "library launches only (the cuDNN backbone is fp32 CUDA-core work); a step far below both roofs "
                     "is latency / launch bound"}
-    if shares is not None:
-        roofline = roofline or {}
-        roofline["kernel_shares"] = {"source": "CUPTI kernel records of one eager step (torch.profiler)",
-                                     "kernel_ms_per_step": shares[0],
-                                     "top": [{"kernel": _short(n), "launches": c, "ms": t, "share": sh}
-                                             for n, c, t, sh in shares[1]]}
     op_summary = {k: {"calls_per_step": c, "ms_per_step": t} for k, (c, t) in op_ms.items()}
 
     # ---------------- vMF attention TFLOP/s (second half of BASELINE.json's metric): the attention core alone at the
@@ -1098,6 +1146,20 @@ def run_forward(args, rank, local_rank, world, dev, sharding, ops, workloads):
                    "frac_of_hbm_peak": 4.0 * 2 * Sk * Hh * hd / t_ms / 1e6 / peaks["hbm_gbs"]}
             del q, k, v, bits, flush, kvp
 
+    # ---------------- exact kernel durations of one eager step (CUPTI). LAST of the GPU measurements: once kineto has
+    # attached CUPTI to the process it stays attached, and graph replays run ~1.4x slower under it (measured: 7.1 ->
+    # 10.3 ms per step), so nothing timed may follow this pass
+    if not args.skip_profile:
+        with torch.no_grad():
+            shares = _kernel_shares(lambda: step(dev_in))
+    if shares is not None:
+        roofline = roofline or {}
+        roofline["kernel_shares"] = {"source": "CUPTI kernel records of one eager step (torch.profiler), taken after "
+                                               "all timed regions",
+                                     "kernel_ms_per_step": shares[0],
+                                     "top": [{"kernel": _short(n), "launches": c, "ms": t, "share": sh}
+                                             for n, c, t, sh in shares[1]]}
+
     # ---------------- CPU baseline on a bounded sample, rank 0, N == 1 only: the REFERENCE's own modules when the
     # vendored copy is present (baseline/_ref), else the oracle port
     cpu_baseline = None
@@ -1110,7 +1172,9 @@ def run_forward(args, rank, local_rank, world, dev, sharding, ops, workloads):
                              else "whole model, images in -> Instances fields out" if full
                              else "segmentation head on backbone features"),
               "queries": 100, "decoder_layers": hk_cfg["dec_layers"],
-              "launch": "eager" if args.no_graph else "one CUDA graph per step",
+              "launch": "eager" if args.no_graph else "one CUDA graph per step" + (
+                  f", {n_fl} steps in flight on {n_fl} streams (each graph has its own static buffers)" if n_fl > 1 else ""),
+              "inflight": n_fl,
               "global_batch": B * world, "parallelism": f"replicas x{world} (batch-sharded, no collective)",
               "numa": args.numa,
               "l2_policy": "inputs_exceed_l2 (every decoder layer streams the mask features - 157 MB at batch 8 - and "
@@ -1127,6 +1191,9 @@ def run_forward(args, rank, local_rank, world, dev, sharding, ops, workloads):
                     "ms_per_step": ms_e2e / args.steps,
                     "how": "pinned host inputs -> device every step, results -> pinned host every step; transfers of "
                            "neighbouring steps overlap the graph replay on separate streams"},
+            "serial": None if ms_serial is None else {"ms_per_step": ms_serial, "value": B * world / (ms_serial / 1e3),
+                                                       "note": "the same graph replayed one step after another "
+                                                               "(step latency)"},
             "gpu_launches": launches, "parts_ms": parts_ms,
             "roofline": roofline, "vmf_attention": vmf, "op_ms": op_summary, "cpu_baseline": cpu_baseline}
     emit(line)
@@ -1192,10 +1259,17 @@ def cpu_baseline_leg(kind, gpu_module, host_in, gpu_step, dev, full):
         t0 = time.perf_counter()
         ref, feats = cpu_step(sample)
         dt = time.perf_counter() - t0
-        # parity of the hot path on the sample: the GPU head on the SAME backbone features the CPU arm saw
+        # parity of the hot path on the sample: the GPU head on the SAME backbone features the CPU arm saw (with the
+        # auxiliary full-resolution masks the timed eval path skips, so that the first prediction can be compared too)
         head = gpu_module.sem_seg_head if full else gpu_module
+        predictor = getattr(head, "predictor", None)
+        keep = getattr(predictor, "eval_aux_masks", True)
+        if predictor is not None:
+            predictor.eval_aux_masks = True
         got, _ = head({k: v.to(dev) for k, v in feats.items()}, workloads.HEAD_CFG[hk]["height"],
                       workloads.HEAD_CFG[hk]["width"])
+        if predictor is not None:
+            predictor.eval_aux_masks = keep
     pk = ref["pred_masks"].abs().max().item()
     err = (got["pred_masks"].cpu() - ref["pred_masks"]).abs().max().item() / pk
     agree = (got["pred_masks"].cpu().argmax(1) == ref["pred_masks"].argmax(1)).float().mean().item()
