@@ -749,7 +749,7 @@ def main():
                          "Default: PyTorch's own default conv math on a GPU (TF32), i.e. what the reference's stock code "
                          "does there; the head and the tail never use TF32 either way")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=2,
+    ap.add_argument("--inflight", type=int, default=3,
                     help="forward workloads: graph replays in flight at once (each with its own static buffers, on its own "
                          "stream); 1 = one step after another")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
@@ -931,7 +931,7 @@ def run_forward(args, rank, local_rank, world, dev, sharding, ops, workloads):
             parts_ms = {"backbone_cudnn": acc[0], "head": acc[1], "tail": acc[2], "how": "eager, CUDA events"}
 
         # ---------------- the step as ONE CUDA graph (static input / output buffers resident in HBM)
-        # `--inflight F` (default 2): F graphs with their own static buffers, replayed round-robin on F streams, so
+        # `--inflight F` (default 3): F graphs with their own static buffers, replayed round-robin on F streams, so
         # that step i+1 starts while step i is still in its latency-bound phases (the 800-row decoder launches fill 64
         # of 148 SMs). Every step is still one whole batch through the whole path; `serial` below is F = 1.
         n_fl = 1 if args.no_graph else max(1, args.inflight)
@@ -1146,9 +1146,8 @@ def run_forward(args, rank, local_rank, world, dev, sharding, ops, workloads):
                    "frac_of_hbm_peak": 4.0 * 2 * Sk * Hh * hd / t_ms / 1e6 / peaks["hbm_gbs"]}
             del q, k, v, bits, flush, kvp
 
-    # ---------------- exact kernel durations of one eager step (CUPTI). LAST of the GPU measurements: once kineto has
-    # attached CUPTI to the process it stays attached, and graph replays run ~1.4x slower under it (measured: 7.1 ->
-    # 10.3 ms per step), so nothing timed may follow this pass
+    # ---------------- exact kernel durations of one eager step (CUPTI). LAST of the GPU measurements: kineto leaves
+    # CUPTI attached to the process, so nothing timed follows this pass
     if not args.skip_profile:
         with torch.no_grad():
             shares = _kernel_shares(lambda: step(dev_in))

@@ -118,6 +118,11 @@ int msm_mask_logits(const float* embed, const float* feat, float* masks,
 int msm_mask_to_attn_bits(const float* masks, uint32_t* bits, int32_t* row_open,
                           int B, int Q, int H, int W, int Ht, int Wt, void* stream);
 
+/* msm_resample_bilinear_fwd replaces  F.interpolate(x, size=(Ht, Wt), mode="bilinear", align_corners=False)
+ *   (the resampling of decoder.py:675, applied to the mask FEATURES by the inference path that skips the auxiliary
+ *   full-resolution masks): x [planes][H][W] -> y [planes][Ht][Wt], PyTorch's source-index rule. */
+int msm_resample_bilinear_fwd(const float* x, float* y, int64_t planes, int H, int W, int Ht, int Wt, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Dense layer  Y[M][N] = act( X[M][K] . W[N][K]^T + bias[N] ),  act: 0 = identity, 1 = ReLU.
  * Replaces the torch.nn.functional.linear calls of the hot path: the packed q/k/v in-projection

@@ -407,3 +407,17 @@ def test_lean_eval_path_matches_full_masks():
     assert agree > 0.995, agree
     first = peak_rel(lean["aux_outputs"][1]["pred_logits"], full["aux_outputs"][1]["pred_logits"])
     assert first < 1e-4, first   # after one layer (before any flip can matter much) the class logits are identical
+
+
+@pytest.mark.parametrize("shape,size", [((2, 256, 120, 160), (15, 20)), ((2, 256, 120, 160), (60, 80)),
+                                        ((1, 3, 7, 5), (13, 9)), ((3, 5, 33, 17), (33, 17)), ((1, 2, 1, 1), (4, 6)),
+                                        ((2, 100, 120, 160), (480, 640))])
+def test_resample_bilinear_vs_interpolate(shape, size):
+    """msm_resample_bilinear_fwd == F.interpolate(bilinear, align_corners=False): down-, up-sampling, identity, 1x1."""
+    from unseenobjectswithmeanshift_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(*shape, generator=g).cuda()
+    got = ops.resample_bilinear(x, size)
+    want = F.interpolate(x, size=size, mode="bilinear", align_corners=False)
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() <= 2e-6 * max(1.0, want.abs().max().item())

@@ -180,11 +180,17 @@ def test_head_training_steps_r50style(golden):
     assert min(history[4:]) < history[0], history
 
 
+@pytest.mark.parametrize("fold", ["kv", "v", "off"])
 @pytest.mark.parametrize("decoder,levels", [("MeanShiftTransformerDecoder", 3), ("PretrainedMeanShiftTransformerDecoder", 1)])
-def test_decoder_packed_kv_path_matches_default(monkeypatch, decoder, levels):
+def test_decoder_packed_kv_path_matches_default(monkeypatch, decoder, levels, fold):
     """MSM_PACKED_KV=1 (K / V projections write operand images, packed attention kernel) against the default path of
-    the same decoder: heads of 32 channels (the packed path's requirement), masks on, key counts with tails."""
+    the same decoder: heads of 32 channels (the packed path's requirement), masks on, key counts with tails.
+    ``fold``: input_proj (32 -> 64 channels here) folded into both projections, with the keys' sine embedding as two
+    separable tables in the epilogue ("kv", the default), into the value projection only, or not at all; the 35-key
+    level takes the token-major input, the 140- and 560-key levels the channel-major map itself."""
     from unseenobjectswithmeanshift_b200.meanshiftformer import modeling as M
+    monkeypatch.setenv("MSM_FOLD_V", "0" if fold == "off" else "1")
+    monkeypatch.setenv("MSM_FOLD_K", "1" if fold == "kv" else "0")
     torch.manual_seed(3)
     kw = dict(num_classes=2, hidden_dim=64, num_queries=20, nheads=2, dim_feedforward=128, dec_layers=4,
               pre_norm=False, mask_dim=64, enforce_input_project=False, use_meanshift_cross_attention=True,

@@ -443,6 +443,8 @@ def emu_chain():
         f.restype, f.argtypes = SIGNATURES[n]
     h.msmx_linear_packed_kv_fwd.restype = I
     h.msmx_linear_packed_kv_fwd.argtypes = [P, L, P, P, P, I, I, I, I, I, I, I, I, P]
+    h.msmx_linear_packed_kv_pos_fwd.restype = I
+    h.msmx_linear_packed_kv_pos_fwd.argtypes = [P, L, P, P, P, I, I, I, I, I, I, I, I, I, P, P, I, P]
     h.msmx_vmf_packed_bytes.restype, h.msmx_vmf_packed_bytes.argtypes = Z, [I, I, I, I, I]
     h.msmx_vmf_packed_workspace_bytes.restype, h.msmx_vmf_packed_workspace_bytes.argtypes = Z, [I, I, I, I, I]
     h.msmx_vmf_attention_packed_fwd.restype = I
@@ -648,15 +650,24 @@ def test_decoder_packed_kv_wiring_with_emulated_kernels(emu_chain, monkeypatch):
         per_layer = h.msmx_vmf_packed_bytes(batch, heads, num_keys, 32, 3)
         return _aligned(layers * per_layer, 128), per_layer
 
-    def linear_packed_kv(x, weight, bias, images, batch, num_keys, channels, which):
+    def linear_packed_kv(x, weight, bias, images, batch, num_keys, channels, which, pos=None):
         N, K = weight.shape
         calls["project"] += 1
+        calls["folded"] = calls.get("folded", 0) + (1 if pos is not None or x.dim() == 4 else 0)
         _start(h, 2)
         w = weight.detach().contiguous()
         p = _prepare(h, w)
         b = bias.detach().contiguous()
-        rc = h.msmx_linear_packed_kv_fwd(x.data_ptr(), K, p.data_ptr(), b.data_ptr(), images.data_ptr(), batch, num_keys,
-                                         N, K, channels, int(which), 1, 1, None)
+        if pos is None and x.dim() == 3:
+            rc = h.msmx_linear_packed_kv_fwd(x.data_ptr(), K, p.data_ptr(), b.data_ptr(), images.data_ptr(), batch,
+                                             num_keys, N, K, channels, int(which), 1, 1, None)
+        else:   # input_proj folded in: the channel-major map (when S % 4 == 0) and the separable positional tables
+            ty, tx = pos if pos is not None else (None, None)
+            rc = h.msmx_linear_packed_kv_pos_fwd(x.data_ptr(), K, p.data_ptr(), b.data_ptr(), images.data_ptr(), batch,
+                                                 num_keys, N, K, channels, int(which), 1, 1, 1 if x.dim() == 4 else 0,
+                                                 ty.data_ptr() if ty is not None else None,
+                                                 tx.data_ptr() if tx is not None else None,
+                                                 tx.shape[0] if tx is not None else 1, None)
         assert rc == 0, h.emu_last_error()
 
     def vmf_attention_packed(q, kv, *, blocked_bits=None, row_open=None, kappa=30.0, out=None):
@@ -692,7 +703,7 @@ def test_decoder_packed_kv_wiring_with_emulated_kernels(emu_chain, monkeypatch):
         got = m(x, mf)
         again = m(x, mf)   # second call reuses the cached image buffers
     # two forwards: 3 levels x (K, V) projections each, 4 cross-attentions each; the image buffers allocated once
-    assert calls == {"alloc": 3, "project": 12, "attend": 8}, calls
+    assert calls == {"alloc": 3, "project": 12, "attend": 8, "folded": 10}, calls   # the 15-key level: token-major V, no table
     for o in (got, again):
         assert (o["pred_masks"] - want["pred_masks"]).abs().max().item() < 1e-3 * want["pred_masks"].abs().max().item()
         assert (o["pred_logits"] - want["pred_logits"]).abs().max().item() < 1e-3

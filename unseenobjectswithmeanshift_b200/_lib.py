@@ -28,6 +28,7 @@ SIGNATURES = {
                               [_P, _I, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P, _Z, _P]),
     "msm_mask_logits": (_I, [_P, _P, _P, _I, _I, _I, _L, _P]),
     "msm_mask_to_attn_bits": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "msm_resample_bilinear_fwd": (_I, [_P, _P, _L, _I, _I, _I, _I, _P]),
     "msm_linear_weight_bytes": (_Z, [_I, _I]),
     "msm_linear_prepare_weight": (_I, [_P, _L, _P, _I, _I, _P]),
     "msm_linear_fwd": (_I, [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _P]),
@@ -72,6 +73,7 @@ X_SIGNATURES = {
     "msmx_vmf_attention_packed_fwd": (_I, [_P, _L, _L, _L, _P, _P, _L, _L, _L, _P, _I, _P, _I, _I, _I, _I, _I, _F, _I,
                                            _P, _Z, _P]),
     "msmx_linear_packed_kv_fwd": (_I, [_P, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "msmx_linear_packed_kv_pos_fwd": (_I, [_P, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
     "msmx_set_l2_persisting_window": (_I, [_P, _Z, _P]),
     "msmx_vmf_attention_small_fwd": (_I, [_P, _L, _L, _L] * 4 + [_P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _I, _P]),
     "msmx_mean_shift_packed_bytes": (_Z, [_I, _I, _I]),

@@ -86,6 +86,10 @@ struct Params {
   // (pack_norm) as fp16 (pack_f16) or bf16 halves at image slots 0 / 1, V rows as bf16 halves at slots 2 / 3.
   int pack, pack_S, pack_C, pack_B, pack_ntiles, pack_slot, pack_norm, pack_f16;
   uint8_t* pack_out;
+  // separable positional term of the key projection, folded through W_k: + pos_ty[key / pos_W][n] + pos_tx[key % pos_W][n]
+  // (tables [H][N] and [W][N] fp32 - PositionEmbeddingSine is the concatenation of a y-only and an x-only half)
+  const float *pos_ty, *pos_tx;
+  int pos_W;
 };
 
 #ifdef MSM_EMULATE_ON_HOST  // tests/emu
@@ -343,12 +347,48 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         // thread = token row (b, key); per 32-column chunk = one head: (normalise) -> split -> four 16-byte stores per
         // half; the 32 lanes of a warp (32 consecutive keys) write 512 contiguous bytes per 8-channel group
         constexpr uint32_t kOp = 128u * 32u * 2u, kLbo = 2048u;  // one 16-bit operand of a tile at hd = 32
+        // token-major X: rows run over all images; channel-major X (x_nchw): row tiles are per image
         const int grow = mt * kRows + row;
-        const bool in = grow < P.M;
-        const int bi = in ? grow / P.pack_S : 0, key = in ? grow % P.pack_S : 0;
+        const int tkey = (mt % P.tiles_per_b) * kRows + row;
+        const bool in = P.x_nchw ? tkey < P.Mb : grow < P.M;
+        const int bi = !in ? 0 : P.x_nchw ? mt / P.tiles_per_b : grow / P.pack_S;
+        const int key = !in ? 0 : P.x_nchw ? tkey : grow % P.pack_S;
         const uint32_t koff = (uint32_t)((key & 127) >> 3) * 128u + (uint32_t)(key & 7) * 16u;
         const int heads = P.pack_C / 32;
+        // positional tables: the y row is (nearly) the same for the 32 keys of a warp - broadcast loads; the x rows are
+        // 32 different 128-byte lines per chunk, so the warp fetches them 4 rows per instruction (lane = 16-byte piece
+        // lane % 8 of row 4 j + lane / 8) one chunk ahead and turns them through its staging tiles (swizzled as in
+        // store_chunk) into one row per thread
+        const bool pos = P.pos_tx != nullptr;
+        const float* ty_row = nullptr;
+        const float* tx_src[8];
+        float4 stage[8];
+        if (pos) {
+          ty_row = P.pos_ty + (int64_t)(key / P.pos_W) * P.N + nc * P.BN;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int r2 = q * 32 + 4 * j + (lane >> 3);
+            const int g2 = mt * kRows + r2, t2 = (mt % P.tiles_per_b) * kRows + r2;
+            const int k2 = P.x_nchw ? (t2 < P.Mb ? t2 : 0) : (g2 < P.M ? g2 % P.pack_S : 0);
+            tx_src[j] = P.pos_tx + (int64_t)(k2 % P.pos_W) * P.N + nc * P.BN + 4 * (lane & 7);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) stage[j] = __ldg(reinterpret_cast<const float4*>(tx_src[j]));
+        }
         for (int ch = 0; ch < nchunk; ++ch) {
+          uint8_t* tbuf = wY + (ch & 1) * kYWarpBytes;
+          if (pos) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t r2 = 4u * j + ((uint32_t)lane >> 3);
+              *reinterpret_cast<float4*>(tbuf + r2 * 128u + ((((uint32_t)lane & 7u) ^ (r2 & 7u)) << 4)) = stage[j];
+            }
+            __syncwarp();
+            if (ch + 1 < nchunk) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) stage[j] = __ldg(reinterpret_cast<const float4*>(tx_src[j] + (ch + 1) * 32));
+            }
+          }
           uint32_t r[32];
           tc::tmem_ld32(taddr + ch * 32, r);
           tc::tmem_ld_wait();
@@ -363,10 +403,20 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             float v[32];
             float ss = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              v[j] = __uint_as_float(r[j]) + wBias[ch * 32 + j];
-              ss = fmaf(v[j], v[j], ss);
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + wBias[ch * 32 + j];
+            if (pos) {
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(ty_row + ch * 32) + c);
+                const float4 b = *reinterpret_cast<const float4*>(tbuf + rowoff + (((uint32_t)c ^ sx) << 4));
+                v[4 * c + 0] += a.x + b.x;
+                v[4 * c + 1] += a.y + b.y;
+                v[4 * c + 2] += a.z + b.z;
+                v[4 * c + 3] += a.w + b.w;
+              }
             }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) ss = fmaf(v[j], v[j], ss);
             const float inv = P.pack_norm ? 1.f / fmaxf(sqrtf(ss), 1e-12f) : 1.f;
             uint8_t* img = P.pack_out +
                            ((((int64_t)layer * P.pack_B + bi) * heads + head) * P.pack_ntiles + (key >> 7)) * (4 * kOp) +
@@ -704,6 +754,8 @@ struct LnArgs {
   // experimental operand-image epilogue (Params::pack*)
   int pack = 0, pack_S = 0, pack_C = 0, pack_B = 0, pack_slot = 0, pack_norm = 0, pack_f16 = 0;
   uint8_t* pack_out = nullptr;
+  const float *pos_ty = nullptr, *pos_tx = nullptr;
+  int pos_W = 1;
 };
 
 static int launch(const float* X, int64_t ldx, const void* prepared, const float* bias, float* Y, int64_t ldy, int M,
@@ -717,6 +769,7 @@ static int launch(const float* X, int64_t ldx, const void* prepared, const float
   P.pack = ln.pack; P.pack_S = ln.pack_S; P.pack_C = ln.pack_C; P.pack_B = ln.pack_B; P.pack_slot = ln.pack_slot;
   P.pack_norm = ln.pack_norm; P.pack_f16 = ln.pack_f16; P.pack_out = ln.pack_out;
   P.pack_ntiles = ln.pack ? (ln.pack_S + 127) / 128 : 0;
+  P.pos_ty = ln.pos_ty; P.pos_tx = ln.pos_tx; P.pos_W = ln.pos_W;
   const int m_tiles_est = x_nchw ? Bt * ((Mb + kRows - 1) / kRows) : (M + kRows - 1) / kRows;
   // the row epilogues (LayerNorm over the N outputs of a row) need the whole row in one CTA: never split N for them.
   // (pick_bn narrows the chunk when there are few row tiles - with N = 64 and fewer than num_sms / 2 tiles that cut
@@ -848,14 +901,44 @@ extern "C" int msm_linear_fwd(const float* X, int64_t ldx, const void* prepared,
 // W [N][K] with N = layers * C (the projections of all decoder layers of a level in one GEMM), heads of 32 channels.
 // packed: [layers][B][C/32][ceil(S/128)][4][8192] bytes, 128-byte aligned, ZERO-initialised once by the caller (key
 // tails stay zero); which = 0: K (slots 0/1; normalize / f16 as the attention flags say), 1: V (slots 2/3, bf16).
+static int linear_packed_kv(const float* X, int64_t ldx, const void* prepared, const float* bias, void* packed, int B,
+                            int S, int N, int K, int C, int which, int normalize, int f16, int x_nchw,
+                            const float* pos_ty, const float* pos_tx, int pos_W, void* stream);
+
 extern "C" int msmx_linear_packed_kv_fwd(const float* X, int64_t ldx, const void* prepared, const float* bias,
                                          void* packed, int B, int S, int N, int K, int C, int which, int normalize,
                                          int f16, void* stream) {
+  return linear_packed_kv(X, ldx, prepared, bias, packed, B, S, N, K, C, which, normalize, f16, 0, nullptr, nullptr, 1,
+                          stream);
+}
+
+// The same for the projections with input_proj folded in: X may be the channel-major map itself
+// (x_nchw: X [B][K][S], S % 4 == 0; ldx ignored), and the separable positional term of the keys comes as two tables -
+// row (b, key) gets + pos_ty[key / pos_W][n] + pos_tx[key % pos_W][n] before the per-head normalisation; pos_ty
+// [S / pos_W][N] and pos_tx [pos_W][N] are the y-only / x-only halves of PositionEmbeddingSine pushed through W_k
+// (position_encoding.py:38-51). Both tables null: no positional term.
+extern "C" int msmx_linear_packed_kv_pos_fwd(const float* X, int64_t ldx, const void* prepared, const float* bias,
+                                             void* packed, int B, int S, int N, int K, int C, int which, int normalize,
+                                             int f16, int x_nchw, const float* pos_ty, const float* pos_tx, int pos_W,
+                                             void* stream) {
+  MSM_REQUIRE((pos_ty == nullptr) == (pos_tx == nullptr), "pos tables come as a pair");
+  MSM_REQUIRE(!pos_ty || (pos_W > 0 && S % pos_W == 0), "S must be a multiple of pos_W");
+  MSM_REQUIRE(((reinterpret_cast<uintptr_t>(pos_ty) | reinterpret_cast<uintptr_t>(pos_tx)) & 15) == 0,
+              "pos tables must be 16-byte aligned");
+  MSM_REQUIRE(!x_nchw || S % 4 == 0, "a channel-major X needs S % 4 == 0");
+  return linear_packed_kv(X, ldx, prepared, bias, packed, B, S, N, K, C, which, normalize, f16, x_nchw ? 1 : 0, pos_ty,
+                          pos_tx, pos_ty ? pos_W : 1, stream);
+}
+
+static int linear_packed_kv(const float* X, int64_t ldx, const void* prepared, const float* bias, void* packed, int B,
+                            int S, int N, int K, int C, int which, int normalize, int f16, int x_nchw,
+                            const float* pos_ty, const float* pos_tx, int pos_W, void* stream) {
   MSM_REQUIRE(X && prepared && packed, "X, prepared, packed must be non-null");
   MSM_REQUIRE(B > 0 && S > 0 && N > 0 && K > 0 && C > 0, "sizes must be positive");
   MSM_REQUIRE(K % 32 == 0 && C % 32 == 0 && N % C == 0, "K and C must be multiples of 32, N a multiple of C");
   MSM_REQUIRE(which == 0 || which == 1, "which must be 0 (K) or 1 (V)");
-  MSM_REQUIRE(ldx >= K && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0, "X rows must be 16-byte aligned");
+  MSM_REQUIRE((x_nchw || (ldx >= K && ldx % 4 == 0)) && (reinterpret_cast<uintptr_t>(X) & 15) == 0,
+              "X rows must be 16-byte aligned");
   MSM_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 127) == 0, "packed must be 128-byte aligned");
   MSM_REQUIRE((int64_t)B * S < (int64_t)1 << 31, "B * S must fit 31 bits");
   msm::ltc::LnArgs a;
@@ -863,6 +946,9 @@ extern "C" int msmx_linear_packed_kv_fwd(const float* X, int64_t ldx, const void
   a.pack_norm = which == 0 ? (normalize ? 1 : 0) : 0;
   a.pack_f16 = which == 0 ? (f16 ? 1 : 0) : 0;
   a.pack_out = static_cast<uint8_t*>(packed);
+  a.pos_ty = pos_ty; a.pos_tx = pos_tx; a.pos_W = pos_W;
+  if (x_nchw)
+    return msm::ltc::launch(X, 0, prepared, bias, nullptr, N, B * S, N, K, 0, 1, 0, B, S, static_cast<cudaStream_t>(stream), a);
   return msm::ltc::launch(X, ldx, prepared, bias, nullptr, N, B * S, N, K, 0, 0, 0, 1, B * S,
                           static_cast<cudaStream_t>(stream), a);
 }

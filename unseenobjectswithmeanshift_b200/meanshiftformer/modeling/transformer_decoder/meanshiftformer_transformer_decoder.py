@@ -361,22 +361,31 @@ class _MeanShiftDecoderBase(nn.Module):
         train = torch.is_grad_enabled()
 
         # ---- per-level memory (keys' input = src + pos, values' input = src), batch-first [B,S,C]
-        sizes, src, key_in = [], [], []
-        for l in range(L):
-            h, w = x[l].shape[-2:]
-            sizes.append((h, w))
-            xf = x[l].float()
-            proj = self.input_proj[l]
-            if isinstance(proj, nn.Conv2d):
-                bias = proj.bias + self.level_embed.weight[l]
-                if not torch.is_grad_enabled() and ops.conv1x1_supported(xf, proj.weight):
-                    s = ops.conv1x1(xf, proj.weight, bias, tokens_out=True)      # NCHW in, [B,S,C] out
-                else:  # e.g. the pixel decoder's token-major maps seen through a transposed view
-                    s = ops.dense(xf.flatten(2).transpose(1, 2), proj.weight.flatten(1), bias)
-            else:
-                s = xf.flatten(2).transpose(1, 2) + self.level_embed.weight[l]
-            src.append(s)
-            key_in.append(None)   # src + positional table, built only where the add cannot be folded (below)
+        sizes = [tuple(x[l].shape[-2:]) for l in range(L)]
+        key_in = [None] * L   # src + positional table, built only where the add cannot be folded (below)
+
+        class _Src:
+            """src[l], computed on first use: the packed K / V path folds input_proj into the projections and then
+            never needs the [B, S, C] map (315 MB per image at 480x640)"""
+            def __init__(self):
+                self.cache = {}
+
+            def __getitem__(self_, l):
+                if l not in self_.cache:
+                    xf = x[l].float()
+                    proj = self.input_proj[l]
+                    if isinstance(proj, nn.Conv2d):
+                        bias = proj.bias + self.level_embed.weight[l]
+                        if not torch.is_grad_enabled() and ops.conv1x1_supported(xf, proj.weight):
+                            s_ = ops.conv1x1(xf, proj.weight, bias, tokens_out=True)      # NCHW in, [B,S,C] out
+                        else:  # e.g. the pixel decoder's token-major maps seen through a transposed view
+                            s_ = ops.dense(xf.flatten(2).transpose(1, 2), proj.weight.flatten(1), bias)
+                    else:
+                        s_ = xf.flatten(2).transpose(1, 2) + self.level_embed.weight[l]
+                    self_.cache[l] = s_
+                return self_.cache[l]
+
+        src = _Src()
 
         # ---- keys / values: independent of the queries, so project them up front per level
         layers_of = [[i for i in range(self.num_layers) if i % L == l] for l in range(L)]
@@ -396,26 +405,48 @@ class _MeanShiftDecoderBase(nn.Module):
                 bk = cat(tag + "bk", [a.in_proj_bias[C:2 * C] for a in attn])
                 wv = cat(tag + "wv", [a.in_proj_weight[2 * C:] for a in attn])
                 bv = cat(tag + "bv", [a.in_proj_bias[2 * C:] for a in attn])
-                if key_in[level] is None:
-                    key_in[level] = src[level] + self.pe_layer.table(sizes[level][0], sizes[level][1], dev)
                 # one zero-initialised buffer per (level, shape), reused by every forward (static under graph replay)
                 images, per_layer = ops.cached_value(
                     self, tag + "img_%d_%d" % (B, S_l), [wk], lambda: ops.packed_kv_alloc(len(layer_ids), B, H, S_l, dev))
-                ops.linear_packed_kv(key_in[level].contiguous(), wk, bk, images, B, S_l, C, 0)
                 proj = self.input_proj[level]
                 if (isinstance(proj, nn.Conv2d) and proj.weight.shape[1] % 32 == 0 and proj.weight.shape[1] < C
                         and os.environ.get("MSM_FOLD_V", "1") == "1"):
-                    # values = (W_in x + b_in + level_embed) W_v^T + b_v = x (W_v W_in)^T + const: the projection reads
-                    # the 64-channel map instead of the 256-channel one - 4x fewer FLOPs and input bytes (SURVEY 7-4;
-                    # the keys' positional term needs the separable-table epilogue and still takes the long way)
+                    #  input_proj folded into both projections: they read the 64-channel map instead of a
+                    # 256-channel one that is then never built - 4x fewer FLOPs and input bytes.
+                    #   values = (W_in x + b_in + level_embed) W_v^T + b_v = x (W_v W_in)^T + const
+                    #   keys   = (W_in x + b_in + level_embed + pos) W_k^T + b_k
+                    #          = x (W_k W_in)^T + const + ty[y] + tx[x]     (the sine embedding is separable:
+                    #            channels [0, C/2) depend on y only, [C/2, C) on x only - position_encoding.py)
                     w_in = proj.weight.flatten(1)
-                    wv_f = ops.cached_value(self, tag + "wvf", [wv, proj.weight],
-                                            lambda: (wv.double() @ w_in.double()).float().contiguous())
-                    bv_f = ops.cached_value(self, tag + "bvf", [wv, bv, proj.bias, self.level_embed.weight], lambda: (
-                        wv.double() @ (proj.bias + self.level_embed.weight[level]).double() + bv.double()).float().contiguous())
-                    x_tok = x[level].float().flatten(2).transpose(1, 2).contiguous()
+                    const = proj.bias + self.level_embed.weight[level]
+                    x_tok = x[level].float().contiguous()     # the channel-major map itself: no transposed copy
+                    if S_l % 4:
+                        x_tok = x_tok.flatten(2).transpose(1, 2).contiguous()
+                    fold_w = lambda w_: (w_.double() @ w_in.double()).float().contiguous()  # noqa: E731
+                    fold_b = lambda w_, b_: (w_.double() @ const.double() + b_.double()).float().contiguous()  # noqa: E731
+                    wv_f = ops.cached_value(self, tag + "wvf", [wv, proj.weight], lambda: fold_w(wv))
+                    bv_f = ops.cached_value(self, tag + "bvf", [wv, bv, proj.bias, self.level_embed.weight],
+                                            lambda: fold_b(wv, bv))
                     ops.linear_packed_kv(x_tok, wv_f, bv_f, images, B, S_l, C, 1)
+                    if os.environ.get("MSM_FOLD_K", "1") == "1":
+                        wk_f = ops.cached_value(self, tag + "wkf", [wk, proj.weight], lambda: fold_w(wk))
+                        bk_f = ops.cached_value(self, tag + "bkf", [wk, bk, proj.bias, self.level_embed.weight],
+                                                lambda: fold_b(wk, bk))
+                        ty, tx = self.pe_layer.tables(sizes[level][0], sizes[level][1], dev)
+                        npf = ty.shape[1]
+                        pos = ops.cached_value(
+                            self, tag + "postab_%dx%d" % sizes[level], [wk],
+                            lambda: ((ty.double() @ wk[:, :npf].double().t()).float().contiguous(),
+                                     (tx.double() @ wk[:, npf:].double().t()).float().contiguous()))
+                        ops.linear_packed_kv(x_tok, wk_f, bk_f, images, B, S_l, C, 0, pos=pos)
+                    else:
+                        if key_in[level] is None:
+                            key_in[level] = src[level] + self.pe_layer.table(sizes[level][0], sizes[level][1], dev)
+                        ops.linear_packed_kv(key_in[level].contiguous(), wk, bk, images, B, S_l, C, 0)
                 else:
+                    if key_in[level] is None:
+                        key_in[level] = src[level] + self.pe_layer.table(sizes[level][0], sizes[level][1], dev)
+                    ops.linear_packed_kv(key_in[level].contiguous(), wk, bk, images, B, S_l, C, 0)
                     ops.linear_packed_kv(src[level].contiguous(), wv, bv, images, B, S_l, C, 1)
                 for j, i in enumerate(layer_ids):
                     kv[i] = (ops.PackedKV(images[j * per_layer:(j + 1) * per_layer], B, H, S_l), None)
@@ -484,7 +515,7 @@ class _MeanShiftDecoderBase(nn.Module):
                 return None
             key = tuple(size)
             if key not in lean_cache:
-                lean_cache[key] = F.interpolate(mask_features, size=key, mode="bilinear", align_corners=False).contiguous()
+                lean_cache[key] = ops.resample_bilinear(mask_features, key)
             return lean_cache[key]
 
         predictions_class, predictions_mask = [], []

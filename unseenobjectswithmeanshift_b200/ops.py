@@ -206,21 +206,47 @@ def packed_kv_alloc(layers, batch, heads, num_keys, device):
     return torch.zeros(layers * per_layer, dtype=torch.uint8, device=device), per_layer
 
 
-def linear_packed_kv(x, weight, bias, images, batch, num_keys, channels, which):
+def linear_packed_kv(x, weight, bias, images, batch, num_keys, channels, which, pos=None):
     """K (which=0: rows L2-normalised per 32-channel head, fp16 halves) or V (which=1: bf16 halves) projection of
-    x [B, S, Cin] with weight [layers*C, Cin], written as operand images into `images` (packed_kv_alloc)."""
+    x with weight [layers*C, Cin], written as operand images into `images` (packed_kv_alloc). x: token-major
+    [B, S, Cin] or the channel-major map [B, Cin, h, w] itself (h * w = S).
+    ``pos`` = (ty [h, layers*C], tx [w, layers*C]): row (b, y*w + x) gets + ty[y] + tx[x] before the normalisation -
+    the separable sine embedding pushed through the key weights."""
     x = _require(x, "x")
-    if x.dim() != 3 or not x.is_contiguous() or x.shape[0] != batch or x.shape[1] != num_keys:
-        raise ValueError("x must be a contiguous [B, S, Cin] tensor")
+    nchw = x.dim() == 4
     w = _require(weight, "weight")
     N, K = w.shape
-    if K != x.shape[2] or N % channels or channels % 32 or K % 32:
+    if nchw:
+        ok = x.is_contiguous() and x.shape[0] == batch and x.shape[2] * x.shape[3] == num_keys and num_keys % 4 == 0
+        cin = x.shape[1]
+    else:
+        ok = x.dim() == 3 and x.is_contiguous() and x.shape[0] == batch and x.shape[1] == num_keys
+        cin = x.shape[-1]
+    if not ok:
+        raise ValueError("x must be a contiguous [B, S, Cin] or [B, Cin, h, w] (h * w = S, S % 4 == 0) tensor")
+    if K != cin or N % channels or channels % 32 or K % 32:
         raise ValueError(f"weight {tuple(w.shape)} does not fit x {tuple(x.shape)} / {channels} channels per layer")
     b = None if bias is None else _require(bias, "bias").contiguous()
-    rc = _lib.xlib().msmx_linear_packed_kv_fwd(x.data_ptr(), K, prepare_linear_weight(w).data_ptr(),
-                                               b.data_ptr() if b is not None else None, images.data_ptr(), batch,
-                                               num_keys, N, K, channels, int(which), 1, 1, _stream())
-    check(rc, "msmx_linear_packed_kv_fwd")
+    ty = tx = None
+    Wd = 1
+    if pos is not None:
+        ty, tx = (_require(t, "pos table") for t in pos)
+        Wd = tx.shape[0]
+        if (not ty.is_contiguous() or not tx.is_contiguous() or ty.shape[1] != N or tx.shape[1] != N
+                or ty.shape[0] * Wd != num_keys):
+            raise ValueError(f"pos tables {tuple(ty.shape)} / {tuple(tx.shape)} do not fit {num_keys} keys x {N} outputs")
+    if pos is None and not nchw:
+        rc = _lib.xlib().msmx_linear_packed_kv_fwd(x.data_ptr(), K, prepare_linear_weight(w).data_ptr(),
+                                                   b.data_ptr() if b is not None else None, images.data_ptr(), batch,
+                                                   num_keys, N, K, channels, int(which), 1, 1, _stream())
+        check(rc, "msmx_linear_packed_kv_fwd")
+        return
+    rc = _lib.xlib().msmx_linear_packed_kv_pos_fwd(x.data_ptr(), K, prepare_linear_weight(w).data_ptr(),
+                                                   b.data_ptr() if b is not None else None, images.data_ptr(), batch,
+                                                   num_keys, N, K, channels, int(which), 1, 1, 1 if nchw else 0,
+                                                   ty.data_ptr() if ty is not None else None,
+                                                   tx.data_ptr() if tx is not None else None, Wd, _stream())
+    check(rc, "msmx_linear_packed_kv_pos_fwd")
 
 
 def pack_kv(k, v, normalize_k=True):
@@ -395,6 +421,18 @@ def mask_to_attn_bits(masks, target_size):
                                           _stream())
     check(rc, "msm_mask_to_attn_bits")
     return bits, row_open
+
+
+def resample_bilinear(x, size):
+    """F.interpolate(x, size=size, mode="bilinear", align_corners=False) for x [..., H, W] (inference only)."""
+    x = _require(x, "x").contiguous()
+    H, W = x.shape[-2:]
+    Ht, Wt = int(size[0]), int(size[1])
+    y = torch.empty(*x.shape[:-2], Ht, Wt, device=x.device, dtype=torch.float32)
+    planes = x.numel() // (H * W)
+    rc = _lib.lib().msm_resample_bilinear_fwd(x.data_ptr(), y.data_ptr(), planes, H, W, Ht, Wt, _stream())
+    check(rc, "msm_resample_bilinear_fwd")
+    return y
 
 
 def unpack_attn_bits(bits, row_open, num_keys, num_heads):
@@ -1339,7 +1377,7 @@ def _work_vmf_bwd(q, k, v, out, grad_out, den, **kw):
 
 
 vmf_attention_bwd = _instrument("vmf_attention_bwd", 2, _work_vmf_bwd)(vmf_attention_bwd)
-def _work_linear_packed(x, weight, bias, images, batch, num_keys, channels, which):
+def _work_linear_packed(x, weight, bias, images, batch, num_keys, channels, which, pos=None):
     N, K = weight.shape
     M = batch * num_keys
     # reads the fp32 rows, writes 16-bit hi + lo operand images (4 bytes per element, like fp32 rows)
@@ -1357,6 +1395,8 @@ linear_packed_kv = _instrument("linear", 1, _work_linear_packed)(linear_packed_k
 vmf_attention_packed = _instrument("vmf_attention", 2, _work_vmf_packed)(vmf_attention_packed)
 mask_logits = _instrument("mask_logits", 1, _work_mask)(mask_logits)
 mask_to_attn_bits = _instrument("mask_to_attn_bits", 1, _work_bits)(mask_to_attn_bits)  # one kernel, no memset
+resample_bilinear = _instrument("resample_bilinear", 1, lambda x, size: (
+    f"{tuple(x.shape)}->{int(size[0])}x{int(size[1])}", 4.0 * (x.numel() // (x.shape[-1] * x.shape[-2])) * int(size[0]) * int(size[1]) * 5, 0.0))(resample_bilinear)
 linear = _instrument("linear", 1, _work_linear)(linear)
 conv1x1 = _instrument("linear", 1, _work_conv)(conv1x1)
 conv3x3 = _instrument("linear", 1, _work_conv3)(conv3x3)
