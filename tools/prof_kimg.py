@@ -39,6 +39,25 @@ def main():
     ms = e0.elapsed_time(e1) / reps
     by = 4.0 * B * S * (K + N)
     print(f"{what}: {ms * 1e3:.1f} us per launch, {by / ms / 1e6:.0f} GB/s algorithmic ({by / 1e6:.0f} MB)")
+    if "stamps" in sys.argv[3:]:
+        import ctypes
+        from unseenobjectswithmeanshift_b200 import _lib
+        h = _lib.xlib()
+        h.msmx_linear_debug.argtypes = [ctypes.c_void_p]
+        h.msmx_linear_debug.restype = None
+        buf = torch.zeros(148, 32, dtype=torch.int64, device=dev)
+        h.msmx_linear_debug(buf.data_ptr())
+        fn()
+        torch.cuda.synchronize()
+        h.msmx_linear_debug(None)
+        b = buf.double().cpu()
+        names = {0: ("producer", ["wait empty_x", "wait empty_w", "-"]), 4: ("mma", ["wait acc_empty", "wait full_w", "wait full_a"]),
+                 8: ("converter w8", ["wait full_x", "wait empty_a", "-"]), 12: ("epilogue w4", ["wait acc_full", "-", "-"]),
+                 16: ("epilogue w12", ["wait acc_full", "-", "-"])}
+        for base, (role, labels) in names.items():
+            tot = b[:, base + 3].mean().item()
+            parts = ", ".join(f"{lab} {100 * b[:, base + i].mean().item() / max(tot, 1):.0f}%" for i, lab in enumerate(labels) if lab != "-")
+            print(f"  {role:14s} total {tot / 1.9e3:8.1f} us (mean over CTAs): {parts}")
 
 
 if __name__ == "__main__":

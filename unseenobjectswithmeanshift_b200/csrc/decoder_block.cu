@@ -273,7 +273,9 @@ __device__ __forceinline__ void tmem_ld32f(uint32_t taddr, float (&v)[32]) {
 
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) decoder_block_kernel(const Params P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  // (offset arithmetic on the __shared__ array, not a round trip through uintptr_t: the latter makes every later access a
+  //  GENERIC LD / ST - 401 of them in linear_tc_kernel's SASS - instead of LDS / STS)
+  uint8_t* smem = smem_raw + ((128u - (tc::smem_u32(smem_raw) & 127u)) & 127u);
   Smem S;
   S.a = smem;
   S.w = S.a + kABytes;

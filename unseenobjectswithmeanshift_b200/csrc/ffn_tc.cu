@@ -64,7 +64,9 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ 
   constexpr uint32_t kW2Bytes = 2 * D * kHc * 2;       // [hi|lo][16][D][8]
   constexpr uint32_t kW1Lbo = kHc * 16, kW2Lbo = D * 16;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // (offset arithmetic on the __shared__ array, not a round trip through uintptr_t: the latter makes every later access a
+  //  GENERIC LD / ST - 401 of them in linear_tc_kernel's SASS - instead of LDS / STS)
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   uint8_t* sX = smem;                                   // one fp32 X tile

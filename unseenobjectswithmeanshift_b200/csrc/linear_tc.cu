@@ -90,6 +90,8 @@ struct Params {
   // (tables [H][N] and [W][N] fp32 - PositionEmbeddingSine is the concatenation of a y-only and an x-only half)
   const float *pos_ty, *pos_tx;
   int pos_W;
+  // development only (tools/prof_kimg.py stamps): per-CTA [32] cycle counters of the roles' waits, or null
+  long long* dbg;
 };
 
 #ifdef MSM_EMULATE_ON_HOST  // tests/emu
@@ -100,6 +102,22 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 #endif
 
+#ifdef MSM_EMULATE_ON_HOST
+#define LTC_TIMED_WAIT(slot, ...) __VA_ARGS__
+#else
+// wait + (operand-image instantiation, debug buffer set) the cycles it took, summed per CTA into dbg[CTA][slot]
+#define LTC_TIMED_WAIT(slot, ...)                                        \
+  do {                                                                   \
+    if (PACK && P.dbg != nullptr) {                                      \
+      const long long t0_ = clock64();                                   \
+      __VA_ARGS__;                                                       \
+      dbg_acc[slot] += clock64() - t0_;                                  \
+    } else {                                                             \
+      __VA_ARGS__;                                                       \
+    }                                                                    \
+  } while (0)
+#endif
+
 // PACK: the experimental operand-image epilogue (Params::pack*) is compiled into its own instantiation, so the
 // shipped <false> kernel is byte-for-byte the one that was validated on the B200
 template <bool PACK>
@@ -108,7 +126,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                  const __grid_constant__ CUtensorMap ymap, const __grid_constant__ CUtensorMap y2map, const Params P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 128B-swizzled TMA tiles need 1024-byte alignment
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // (offset arithmetic on the __shared__ array, not a round trip through uintptr_t: the latter makes every later access a
+  //  GENERIC LD / ST - 401 of them in linear_tc_kernel's SASS - instead of LDS / STS)
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkc = P.K / kKc;
   const uint32_t bStage = 128u * (uint32_t)P.BN;     // [hi|lo][4 k-groups][BN][8] bf16
@@ -119,7 +139,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
   uint8_t* sW = sY + 8 * kYWarpBytes;                // [wstages][bStage]
   // [4 warps][bias | gamma | beta][128]; wide mode: [bias | gamma | beta | gamma2 | beta2][256] shared by the CTA
   float* sBias = reinterpret_cast<float*>(sW + (P.w_resident ? nkc : P.wstages) * bStage);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 4 * 384);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + (PACK ? 8 : 4) * 384);
   uint64_t* full_x = bars;                           // TMA -> converters
   uint64_t* empty_x = full_x + kXStages;             // converters -> TMA
   uint64_t* full_w = empty_x + kXStages;             // TMA -> MMA
@@ -131,6 +151,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAcc);
 
   const int ntiles = P.m_tiles * P.n_chunks;
+  long long dbg_acc[4] = {0, 0, 0, 0};
+#ifdef MSM_EMULATE_ON_HOST
+  (void)dbg_acc;
+#else
+  const long long dbg_t0 = (PACK && P.dbg != nullptr) ? clock64() : 0;
+#endif
 
   if (threadIdx.x == 0) {
     tc::tma_prefetch_desc(&xmap);
@@ -151,7 +177,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     }
     for (int i = 0; i < kAcc; ++i) {
       tc::mbar_init(&acc_full[i], 1);
-      tc::mbar_init(&acc_empty[i], 4);
+      tc::mbar_init(&acc_empty[i], PACK ? 8 : 4);
     }
     tc::fence_mbar_init();
   }
@@ -204,7 +230,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           continue;
         }
         for (int kc = 0; kc < nkc; ++kc) {
-          tc::mbar_wait(&empty_x[xs.stage], xs.phase ^ 1);
+          LTC_TIMED_WAIT(0, tc::mbar_wait(&empty_x[xs.stage], xs.phase ^ 1));
           tc::mbar_arrive_expect_tx(&full_x[xs.stage], kAStageBytes);
           if (P.x_nchw)
             tc::tma_load_3d(sX + xs.stage * kAStageBytes, &xmap, &full_x[xs.stage], (mt % P.tiles_per_b) * kRows,
@@ -213,7 +239,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             tc::tma_load_2d(sX + xs.stage * kAStageBytes, &xmap, &full_x[xs.stage], kc * kKc, mt * kRows);
           xs.advance(P.xstages);
           if (P.w_resident) continue;
-          tc::mbar_wait(&empty_w[rs.stage], rs.phase ^ 1);
+          LTC_TIMED_WAIT(1, tc::mbar_wait(&empty_w[rs.stage], rs.phase ^ 1));
           tc::mbar_arrive_expect_tx(&full_w[rs.stage], bStage);
           tc::tma_load_4d(sW + rs.stage * bStage, &wmap, &full_w[rs.stage], 0, nc * P.BN, kc * (kKc / 8), 0);
           rs.advance(P.wstages);
@@ -231,12 +257,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         for (int part = 0; part < kStages; ++part) tc::mbar_wait(&full_w[part], 0);
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
         const int acc = t % P.nacc;
-        tc::mbar_wait(&acc_empty[acc], ((t / P.nacc) & 1) ^ 1);
+        LTC_TIMED_WAIT(0, tc::mbar_wait(&acc_empty[acc], ((t / P.nacc) & 1) ^ 1));
         tc::tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)acc * 128u;
         for (int kc = 0; kc < nkc; ++kc) {
-          if (!P.w_resident) tc::mbar_wait(&full_w[ws.stage], ws.phase);
-          tc::mbar_wait(&full_a[as.stage], as.phase);
+          if (!P.w_resident) LTC_TIMED_WAIT(1, tc::mbar_wait(&full_w[ws.stage], ws.phase));
+          LTC_TIMED_WAIT(2, tc::mbar_wait(&full_a[as.stage], as.phase));
           tc::tc_fence_after();
           const uint32_t a_hi = tmem_base + kTmemA + as.stage * 32u, a_lo = a_hi + 16u;
           const uint32_t w_hi = sw + (P.w_resident ? (uint32_t)kc : ws.stage) * bStage, w_lo = w_hi + 4u * lboB;
@@ -258,20 +284,22 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         tc::mma_commit(&acc_full[acc]);
       }
     }
-  } else if (warp >= 8) {
+  } else if (PACK ? (warp >= 8 && warp < 12) : (warp >= 8)) {
     // =================================================================== converters
+    // (operand-image epilogue: ONE team converts - the epilogue is the bottleneck there, 378 instructions per 32x32
+    //  chunk at one warp per scheduler = IPC 0.2 in the ncu capture, so warps 12-15 are a second epilogue group)
     const int team = (warp - 8) >> 2, q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t rowoff = (uint32_t)row * 128u, sx = (uint32_t)(row & 7);
     uint32_t step = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       for (int kc = 0; kc < nkc; ++kc, ++step) {
-        if ((int)(step & 1u) != team) continue;
+        if (!PACK && (int)(step & 1u) != team) continue;
         // 3x3: nine consecutive steps (taps) read the same halo stage
         const uint32_t xuse = P.conv3 ? step / 9u : step;
         const uint32_t xstage = xuse % (uint32_t)P.xstages, xphase = (xuse / (uint32_t)P.xstages) & 1u;
         const uint32_t astage = step % kAStagesT, aphase = (step / kAStagesT) & 1u;
-        tc::mbar_wait(&full_x[xstage], xphase);
+        LTC_TIMED_WAIT(0, tc::mbar_wait(&full_x[xstage], xphase));
         uint32_t hi[16], lo[16];
         if (P.conv3) {   // stage = [32 channels][6 rows][36 cols]; pixel (q, lane) of tap (ky, kx) is (q+ky, lane+kx)
           const uint32_t tap = step % 9u;
@@ -295,7 +323,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         }
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&empty_x[xstage]);
-        tc::mbar_wait(&empty_a[astage], aphase ^ 1u);
+        LTC_TIMED_WAIT(1, tc::mbar_wait(&empty_a[astage], aphase ^ 1u));
         tc::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kTmemA + astage * 32u;
         tc::tmem_st16(taddr, hi);
@@ -310,12 +338,14 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     // =================================================================== epilogue
     // Each warp owns the 32 rows of its TMEM lane quadrant end to end: its own bias / LayerNorm parameter
     // copies, its own two 32x32 staging tiles and its own TMA stores - no block-level barrier in the loop.
-    const int q = warp - 4;
+    const int q = warp & 3;                       // TMEM lane quadrant (warps 4-7, and 12-15 in the operand-image mode)
+    const int egrp = PACK && warp >= 12 ? 1 : 0;  // epilogue group: takes the column chunks ch % ngrp == egrp
+    constexpr int ngrp = PACK ? 2 : 1;
     const int row = q * 32 + lane;
     const uint32_t rowoff = (uint32_t)lane * 128u, sx = (uint32_t)(lane & 7);
     const int nchunk = P.BN / 32;
-    float* wBias = sBias + q * 384;  // [bias 128 | gamma 128 | beta 128] of this warp
-    uint8_t* wY = sY + q * (2 * kYWarpBytes);
+    float* wBias = sBias + (q + 4 * egrp) * 384;  // [bias 128 | gamma 128 | beta 128] of this warp
+    uint8_t* wY = PACK ? sY + (q + 4 * egrp) * kYWarpBytes : sY + q * (2 * kYWarpBytes);
     uint32_t ychunk = 0;  // staging-buffer cursor
     int t = 0;
     if (P.wide) {  // parameters of the fused epilogue: one copy for the CTA (single N chunk)
@@ -332,15 +362,26 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
       const int mt = tile / P.n_chunks, nc = tile % P.n_chunks;
       const int acc = t % P.nacc;
       __syncwarp();  // the previous tile's reads of wBias are done
+      // operand-image mode with positional tables: when the warp's 32 keys lie in one image row, ty[y] is a per-warp
+      // constant of the tile and rides in the bias copy
+      bool ty_in_bias = false;
+      const float* ty_bias = nullptr;
+      if (PACK && P.pos_tx != nullptr) {
+        const int g0 = mt * kRows + q * 32, t0 = (mt % P.tiles_per_b) * kRows + q * 32;
+        const bool in31 = P.x_nchw ? t0 + 31 < P.Mb : g0 + 31 < P.M;
+        const int k0 = P.x_nchw ? t0 : g0 % P.pack_S;
+        ty_in_bias = in31 && (P.x_nchw || k0 + 31 < P.pack_S) && (k0 % P.pos_W) + 31 < P.pos_W;
+        if (ty_in_bias) ty_bias = P.pos_ty + (int64_t)(k0 / P.pos_W) * P.N + nc * P.BN;
+      }
       for (int j = lane; j < P.BN && !P.wide; j += 32) {
-        wBias[j] = P.bias != nullptr ? __ldg(P.bias + nc * P.BN + j) : 0.f;
+        wBias[j] = (P.bias != nullptr ? __ldg(P.bias + nc * P.BN + j) : 0.f) + (ty_bias != nullptr ? __ldg(ty_bias + j) : 0.f);
         if (P.ln_gamma != nullptr) {
           wBias[128 + j] = __ldg(P.ln_gamma + j);
           wBias[256 + j] = __ldg(P.ln_beta + j);
         }
       }
       __syncwarp();
-      tc::mbar_wait(&acc_full[acc], (t / P.nacc) & 1);
+      LTC_TIMED_WAIT(0, tc::mbar_wait(&acc_full[acc], (t / P.nacc) & 1));
       tc::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 128u;
       if constexpr (PACK) {
@@ -354,17 +395,21 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         const int bi = !in ? 0 : P.x_nchw ? mt / P.tiles_per_b : grow / P.pack_S;
         const int key = !in ? 0 : P.x_nchw ? tkey : grow % P.pack_S;
         const uint32_t koff = (uint32_t)((key & 127) >> 3) * 128u + (uint32_t)(key & 7) * 16u;
-        const int heads = P.pack_C / 32;
-        // positional tables: the y row is (nearly) the same for the 32 keys of a warp - broadcast loads; the x rows are
-        // 32 different 128-byte lines per chunk, so the warp fetches them 4 rows per instruction (lane = 16-byte piece
-        // lane % 8 of row 4 j + lane / 8) one chunk ahead and turns them through its staging tiles (swizzled as in
-        // store_chunk) into one row per thread
+        const int hpl = P.pack_C / 32;                      // heads per layer
+        int head = ((nc * P.BN) >> 5) + egrp, layer = head / hpl;
+        head -= layer * hpl;
+        const int my_last = nchunk > egrp ? ((nchunk - 1 - egrp) / ngrp) * ngrp + egrp : -1;
+        // positional tables. y: the 32 keys of a warp share the image row when it does not wrap inside them - then
+        // ty[y] was added to this warp's bias copy above; otherwise per-lane loads. x: 32 different 128-byte lines
+        // per chunk, so the warp fetches them 4 rows per instruction (lane = 16-byte piece lane % 8 of row
+        // 4 j + lane / 8), one chunk ahead, and turns them through its staging tile (swizzled as in store_chunk)
+        // into one row per thread
         const bool pos = P.pos_tx != nullptr;
         const float* ty_row = nullptr;
         const float* tx_src[8];
         float4 stage[8];
         if (pos) {
-          ty_row = P.pos_ty + (int64_t)(key / P.pos_W) * P.N + nc * P.BN;
+          if (!ty_in_bias) ty_row = P.pos_ty + (int64_t)(key / P.pos_W) * P.N + nc * P.BN;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int r2 = q * 32 + 4 * j + (lane >> 3);
@@ -372,54 +417,72 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             const int k2 = P.x_nchw ? (t2 < P.Mb ? t2 : 0) : (g2 < P.M ? g2 % P.pack_S : 0);
             tx_src[j] = P.pos_tx + (int64_t)(k2 % P.pos_W) * P.N + nc * P.BN + 4 * (lane & 7);
           }
+          if (my_last >= 0) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) stage[j] = __ldg(reinterpret_cast<const float4*>(tx_src[j]));
+            for (int j = 0; j < 8; ++j) stage[j] = __ldg(reinterpret_cast<const float4*>(tx_src[j] + egrp * 32));
+          }
         }
-        for (int ch = 0; ch < nchunk; ++ch) {
-          uint8_t* tbuf = wY + (ch & 1) * kYWarpBytes;
+        if (my_last < 0) {  // more epilogue groups than chunks: nothing to read, release the accumulator
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
+        }
+        for (int ch = egrp; ch < nchunk; ch += ngrp) {
           if (pos) {
+            __syncwarp();  // the previous chunk's reads of the staging tile are done
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const uint32_t r2 = 4u * j + ((uint32_t)lane >> 3);
-              *reinterpret_cast<float4*>(tbuf + r2 * 128u + ((((uint32_t)lane & 7u) ^ (r2 & 7u)) << 4)) = stage[j];
+              *reinterpret_cast<float4*>(wY + r2 * 128u + ((((uint32_t)lane & 7u) ^ (r2 & 7u)) << 4)) = stage[j];
             }
             __syncwarp();
-            if (ch + 1 < nchunk) {
+            if (ch + ngrp < nchunk) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) stage[j] = __ldg(reinterpret_cast<const float4*>(tx_src[j] + (ch + 1) * 32));
+              for (int j = 0; j < 8; ++j)
+                stage[j] = __ldg(reinterpret_cast<const float4*>(tx_src[j] + (ch + ngrp) * 32));
             }
           }
           uint32_t r[32];
           tc::tmem_ld32(taddr + ch * 32, r);
           tc::tmem_ld_wait();
-          if (ch == nchunk - 1) {
+          if (ch == my_last) {
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
           }
           if (in) {
-            const int n0 = nc * P.BN + ch * 32;
-            const int layer = n0 / P.pack_C, head = (n0 % P.pack_C) / 32;
             float v[32];
-            float ss = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + wBias[ch * 32 + j];
             if (pos) {
 #pragma unroll
               for (int c = 0; c < 8; ++c) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(ty_row + ch * 32) + c);
-                const float4 b = *reinterpret_cast<const float4*>(tbuf + rowoff + (((uint32_t)c ^ sx) << 4));
-                v[4 * c + 0] += a.x + b.x;
-                v[4 * c + 1] += a.y + b.y;
-                v[4 * c + 2] += a.z + b.z;
-                v[4 * c + 3] += a.w + b.w;
+                const float4 b = *reinterpret_cast<const float4*>(wY + rowoff + (((uint32_t)c ^ sx) << 4));
+                v[4 * c + 0] += b.x;
+                v[4 * c + 1] += b.y;
+                v[4 * c + 2] += b.z;
+                v[4 * c + 3] += b.w;
+              }
+              if (ty_row != nullptr) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  const float4 a = __ldg(reinterpret_cast<const float4*>(ty_row + ch * 32) + c);
+                  v[4 * c + 0] += a.x;
+                  v[4 * c + 1] += a.y;
+                  v[4 * c + 2] += a.z;
+                  v[4 * c + 3] += a.w;
+                }
               }
             }
+            float inv = 1.f;
+            if (P.pack_norm) {
+              float ss = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) ss = fmaf(v[j], v[j], ss);
-            const float inv = P.pack_norm ? 1.f / fmaxf(sqrtf(ss), 1e-12f) : 1.f;
+              for (int j = 0; j < 32; ++j) ss = fmaf(v[j], v[j], ss);
+              inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+            }
             uint8_t* img = P.pack_out +
-                           ((((int64_t)layer * P.pack_B + bi) * heads + head) * P.pack_ntiles + (key >> 7)) * (4 * kOp) +
+                           ((((int64_t)layer * P.pack_B + bi) * hpl + head) * P.pack_ntiles + (key >> 7)) * (4 * kOp) +
                            (uint32_t)P.pack_slot * kOp + koff;
 #pragma unroll
             for (int dg = 0; dg < 4; ++dg) {
@@ -438,6 +501,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
               *reinterpret_cast<uint4*>(img + dg * kLbo) = hi;
               *reinterpret_cast<uint4*>(img + kOp + dg * kLbo) = lo;
             }
+          }
+          head += ngrp;
+          while (head >= hpl) {
+            head -= hpl;
+            ++layer;
           }
         }
         continue;
@@ -663,6 +731,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     }
     if (lane == 0) tc::tma_store_wait_all();
   }
+#ifndef MSM_EMULATE_ON_HOST
+  if (PACK && P.dbg != nullptr && (warp <= 1 || lane == 0) && (dbg_acc[0] | dbg_acc[1] | dbg_acc[2]) != 0) {
+    const int base = warp == 0 ? 0 : warp == 1 ? 4 : warp == 8 ? 8 : warp == 4 ? 12 : warp == 12 ? 16 : -1;
+    if (base >= 0) {
+      long long* o = P.dbg + (int64_t)blockIdx.x * 32 + base;
+      o[0] = dbg_acc[0]; o[1] = dbg_acc[1]; o[2] = dbg_acc[2]; o[3] = clock64() - dbg_t0;
+    }
+  }
+#endif
 
   tc::tc_fence_before();
   __syncthreads();
@@ -758,6 +835,8 @@ struct LnArgs {
   int pos_W = 1;
 };
 
+static long long* g_ltc_dbg = nullptr;  // development only: see msmx_linear_debug
+
 static int launch(const float* X, int64_t ldx, const void* prepared, const float* bias, float* Y, int64_t ldy, int M,
                   int N, int K, int act, int x_nchw, int y_nchw, int Bt, int Mb, cudaStream_t st,
                   const LnArgs& ln = LnArgs()) {
@@ -770,6 +849,7 @@ static int launch(const float* X, int64_t ldx, const void* prepared, const float
   P.pack_norm = ln.pack_norm; P.pack_f16 = ln.pack_f16; P.pack_out = ln.pack_out;
   P.pack_ntiles = ln.pack ? (ln.pack_S + 127) / 128 : 0;
   P.pos_ty = ln.pos_ty; P.pos_tx = ln.pos_tx; P.pos_W = ln.pos_W;
+  P.dbg = ln.pack ? g_ltc_dbg : nullptr;
   const int m_tiles_est = x_nchw ? Bt * ((Mb + kRows - 1) / kRows) : (M + kRows - 1) / kRows;
   // the row epilogues (LayerNorm over the N outputs of a row) need the whole row in one CTA: never split N for them.
   // (pick_bn narrows the chunk when there are few row tiles - with N = 64 and fewer than num_sms / 2 tiles that cut
@@ -789,7 +869,7 @@ static int launch(const float* X, int64_t ldx, const void* prepared, const float
   //  launch failure in ~half of the runs, clean under compute-sanitizer - and is kept on the streaming path)
   P.w_resident = (!no_resident && !ln.wide && !ln.conv3 && !x_nchw && (int64_t)K * P.BN * 4 <= 128 * 1024) ? 1 : 0;
   if (P.w_resident) {
-    const size_t fixed = 1024 + 8 * kYWarpBytes + (size_t)K * P.BN * 4 + 4 * 384 * sizeof(float) + 512;
+    const size_t fixed = 1024 + 8 * kYWarpBytes + (size_t)K * P.BN * 4 + (ln.pack ? 8 : 4) * 384 * sizeof(float) + 512;
     int xs = (int)(((size_t)kMaxSmem - fixed) / kAStageBytes);
     P.xstages = xs > kXStages ? kXStages : xs;
   }
@@ -851,7 +931,7 @@ static int launch(const float* X, int64_t ldx, const void* prepared, const float
     if (rc) return rc;
   }
   const size_t smem = 1024 + (size_t)P.xstages * P.xstage_bytes + 8 * kYWarpBytes +
-                      (P.w_resident ? (size_t)K * P.BN * 4 : (size_t)P.wstages * 128 * P.BN) + 4 * 384 * sizeof(float) + 512;
+                      (P.w_resident ? (size_t)K * P.BN * 4 : (size_t)P.wstages * 128 * P.BN) + (ln.pack ? 8 : 4) * 384 * sizeof(float) + 512;
   const int tiles = P.m_tiles * P.n_chunks;
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (P.w_resident) grid -= grid % P.n_chunks;  // tiles >= n_chunks and n_chunks <= 64 < SMs, so grid >= n_chunks
@@ -904,6 +984,10 @@ extern "C" int msm_linear_fwd(const float* X, int64_t ldx, const void* prepared,
 static int linear_packed_kv(const float* X, int64_t ldx, const void* prepared, const float* bias, void* packed, int B,
                             int S, int N, int K, int C, int which, int normalize, int f16, int x_nchw,
                             const float* pos_ty, const float* pos_tx, int pos_W, void* stream);
+
+// development only (tools/prof_kimg.py stamps): device buffer [CTAs][32] of per-role wait cycles, filled by the next
+// operand-image launches; null switches it off
+extern "C" void msmx_linear_debug(long long* buf) { msm::ltc::g_ltc_dbg = buf; }
 
 extern "C" int msmx_linear_packed_kv_fwd(const float* X, int64_t ldx, const void* prepared, const float* bias,
                                          void* packed, int B, int S, int N, int K, int C, int which, int normalize,
