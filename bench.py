@@ -548,9 +548,7 @@ def run_tail(args, rank, local_rank, world, dev, sharding, ops):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"tail Q=100 120x160->480x640 top-20 batch {B}/GPU", "global_batch": B * world,
-                       "launch": "eager" if args.no_graph else "one CUDA graph per step" + (
-                  f", {n_fl} steps in flight on {n_fl} streams (each graph has its own static buffers)" if n_fl > 1 else ""),
-              "inflight": n_fl,
+                       "launch": "eager" if args.no_graph else "one CUDA graph per step",
                        "parallelism": f"replicas x{world} (batch-sharded, no collective)",
                        "l2_policy": "l2_flushed_between_steps (256 MB memset, untimed)"},
             "clocks": clocks,

@@ -191,6 +191,11 @@ int msm_add_layernorm_fwd(const float* x, const float* y, const float* gamma, co
 int msm_conv1x1_fwd(const float* X, const void* prepared, const float* bias, float* Y, int y_nchw, int B, int HW,
                     int N, int K, int act, void* stream);
 
+/* The same for a channels-last map: X [B][HW][K] (the memory of a channels_last NCHW tensor, e.g. what a cuDNN
+ * channels_last backbone hands to pixel_decoder/msdeformattn.py:258-262) -> Y [B][N][HW]. HW % 128 == 0. */
+int msm_conv1x1_nhwc_fwd(const float* X, const void* prepared, const float* bias, float* Y, int B, int HW, int N, int K,
+                         int act, void* stream);
+
 /* 3x3 convolution, padding 1, stride 1, as an implicit GEMM over K' = 9*C on the same kernel (each tap is the
  * input tile's TMA box shifted by (kx, ky)). X is the input ALREADY zero-padded: [B][C][H+2][Wp], one zero row
  * above and below, one zero column on the left and Wp - W - 1 >= 1 on the right, Wp a multiple of 4;

@@ -421,3 +421,109 @@ def test_resample_bilinear_vs_interpolate(shape, size):
     want = F.interpolate(x, size=size, mode="bilinear", align_corners=False)
     assert got.shape == want.shape
     assert (got - want).abs().max().item() <= 2e-6 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize("B,Hh,Ww,layers,masked", [(2, 16, 64, 2, True),    # image rows never wrap inside a warp
+                                                    (1, 24, 40, 3, True),    # they do: per-lane ty loads
+                                                    (2, 30, 20, 1, False),   # S = 600: last key tile has a tail
+                                                    (1, 5, 7, 2, True)])     # S % 4 != 0: token-major x, tables only
+def test_folded_projection_to_packed_attention_vs_fp64(B, Hh, Ww, layers, masked):
+    """The K / V projections of the UCN / crop configs with input_proj folded in (K = 64): x [B, 64, H, W] channel-major,
+    K = x (W_k W_in)^T + b + ty[y] + tx[x] (separable sine tables in the epilogue), V = x (W_v W_in)^T + b, written as
+    operand images, then the packed attention per layer - against the fp64 cross-attention on
+    K = (W_in x + b_in + pos) W_k^T + b_k, V = (W_in x + b_in) W_v^T + b_v (attention_util.py:64-82, :121-140)."""
+    from unseenobjectswithmeanshift_b200 import ops
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(B * 1000 + Hh * Ww + layers)
+    Cin, C, Hd, Q, S = 64, 256, 8, 100, Hh * Ww
+    x = torch.randn(B, Cin, Hh, Ww, generator=g)
+    w_in, b_in = torch.randn(C, Cin, generator=g) / Cin ** 0.5, torch.randn(C, generator=g) * 0.1
+    wk, bk = torch.randn(layers * C, C, generator=g) / C ** 0.5, torch.randn(layers * C, generator=g) * 0.1
+    wv, bv = torch.randn(layers * C, C, generator=g) / C ** 0.5, torch.randn(layers * C, generator=g) * 0.1
+    ty, tx = torch.randn(Hh, C // 2, generator=g), torch.randn(Ww, C // 2, generator=g)   # any separable embedding
+    q = torch.randn(layers, B, Q, C, generator=g)
+    d = lambda t: t.double()  # noqa: E731
+    # fp64 reference, the long way
+    pos = torch.cat((ty[:, None, :].expand(Hh, Ww, -1), tx[None, :, :].expand(Hh, Ww, -1)), dim=2).reshape(S, C)
+    src = d(x).flatten(2).transpose(1, 2) @ d(w_in).t() + d(b_in)
+    Kref = ((src + d(pos)) @ d(wk).t() + d(bk)).view(B, S, layers, Hd, 32)
+    Vref = (src @ d(wv).t() + d(bv)).view(B, S, layers, Hd, 32)
+    # folded weights (what the decoder caches)
+    fold_w = lambda w_: (d(w_) @ d(w_in)).float().contiguous().to(dev)  # noqa: E731
+    fold_b = lambda w_, b_: (d(w_) @ d(b_in) + d(b_)).float().contiguous().to(dev)  # noqa: E731
+    npf = C // 2
+    tabs = ((d(ty) @ d(wk)[:, :npf].t()).float().contiguous().to(dev), (d(tx) @ d(wk)[:, npf:].t()).float().contiguous().to(dev))
+    images, per_layer = ops.packed_kv_alloc(layers, B, Hd, S, dev)
+    xin = x.to(dev).contiguous() if S % 4 == 0 else x.to(dev).flatten(2).transpose(1, 2).contiguous()
+    ops.linear_packed_kv(xin, fold_w(wk), fold_b(wk, bk), images, B, S, C, 0, pos=tabs)
+    ops.linear_packed_kv(xin, fold_w(wv), fold_b(wv, bv), images, B, S, C, 1)
+    for j in range(layers):
+        bits = ro = eff = None
+        if masked:
+            blocked = torch.rand(B, Q, S, generator=g) < 0.5
+            blocked[:, 3] = True
+            ro = (~blocked).any(-1).to(torch.int32).contiguous().to(dev)
+            words = (S + 31) // 32
+            pad = torch.zeros(B, Q, words * 32, dtype=torch.bool)
+            pad[..., :S] = blocked
+            v = (pad.view(B, Q, words, 32).long() << torch.arange(32)).sum(-1)
+            bits = torch.where(v >= 2 ** 31, v - 2 ** 32, v).to(torch.int32).contiguous().to(dev)
+            eff = (blocked & (ro.cpu() != 0).unsqueeze(-1)).unsqueeze(1)
+        q4 = q[j].to(dev).unflatten(-1, (Hd, 32)).permute(0, 2, 1, 3)
+        kv = ops.PackedKV(images[j * per_layer:(j + 1) * per_layer], B, Hd, S)
+        out = ops.vmf_attention_packed(q4, kv, blocked_bits=bits, row_open=ro)
+        kj, vj = Kref[:, :, j].permute(0, 2, 1, 3), Vref[:, :, j].permute(0, 2, 1, 3)
+        s = 30.0 * F.normalize(d(q[j]).unflatten(-1, (Hd, 32)).permute(0, 2, 1, 3), dim=-1) @ F.normalize(kj, dim=-1).transpose(-1, -2)
+        if eff is not None:
+            s = s.masked_fill(eff, float("-inf"))
+        ref = F.normalize(torch.softmax(s, -1) @ vj, dim=-1)
+        err = (out.cpu().double() - ref).abs().max().item()
+        assert err == err and err < 3e-5, (j, err)
+
+
+@pytest.mark.parametrize("B,K,N,Hh,Ww,bias", [(2, 256, 256, 16, 24, True),    # H*W = 384 = 3 x 128: channel-major result
+                                              (1, 512, 256, 15, 20, True),    # 300 pixels: token-major result, NCHW view
+                                              (2, 64, 64, 8, 16, False)])
+def test_conv1x1_channels_last_input_vs_fp64(B, K, N, Hh, Ww, bias):
+    """A channels_last feature map (what the cuDNN channels_last backbone hands over) through the 1x1 convolutions of
+    the pixel decoder without a layout copy: msm_conv1x1_nhwc_fwd / the token-major linear, against fp64 conv2d."""
+    from unseenobjectswithmeanshift_b200 import ops
+    g = torch.Generator().manual_seed(B + K + Hh)
+    x = torch.randn(B, K, Hh, Ww, generator=g)
+    conv = torch.nn.Conv2d(K, N, 1, bias=bias)
+    with torch.no_grad():
+        want = F.conv2d(x.double(), conv.weight.double(), conv.bias.double() if bias else None)
+        xc = x.cuda().contiguous(memory_format=torch.channels_last)
+        assert ops.conv1x1_nhwc_supported(xc, conv.weight.cuda())
+        got = ops.conv1x1_layer(conv.cuda(), xc)
+    assert got.shape == want.shape
+    assert (got.cpu().double() - want).abs().max().item() / want.abs().max().item() < 1e-5   # split-precision products
+
+
+def test_backbone_fused_channels_last_matches_plain_module():
+    """backbones.ResNet50Features: BatchNorms folded + cuDNN fused conv/bias/ReLU + downsample bias folded into conv3 +
+    channels_last outputs == the plain torchvision module with eval-mode BatchNorms (randomised statistics), at fp32
+    conv math."""
+    import copy
+    from unseenobjectswithmeanshift_b200 import backbones
+    backbones.set_tf32(True)     # the timed configuration's layout (channels_last) ...
+    plain = backbones.ResNet50Features(seed=3, fold_bn=False)
+    plain.tf32 = False           # ... at fp32 math, so that the comparison is tight
+    g = torch.Generator().manual_seed(1)
+    for m in plain.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+            m.weight.data.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+            m.bias.data.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+    fused = copy.deepcopy(plain).fold_()
+    plain, fused = plain.cuda(), fused.cuda()
+    x = torch.randn(2, 3, 64, 96, generator=g).cuda()
+    with torch.no_grad():
+        want, got = plain(x), fused(x)
+    assert fused.fused_relu and not plain.fused_relu
+    for k in want:
+        assert got[k].shape == want[k].shape
+        assert got[k].permute(0, 2, 3, 1).is_contiguous()      # handed to the head without an NCHW copy
+        scale = want[k].abs().max().item()
+        assert (got[k] - want[k]).abs().max().item() / scale < 1e-4, k

@@ -38,6 +38,7 @@ SIGNATURES = {
     "msm_ffn_ln_fwd": (_I, [_P, _L, _P, _P, _P, _P, _P, _P, _F, _P, _L, _I, _I, _I, _P]),
     "msm_add_layernorm_fwd": (_I, [_P, _P, _P, _P, _F, _I, _P, _P, _F, _P, _P, _I, _I, _P]),
     "msm_conv1x1_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "msm_conv1x1_nhwc_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "msm_conv3x3_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "msm_ms_deform_attn_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "msm_ms_deform_attn_fused_fwd": (_I, [_P, _P, _P, _P, _L, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),

@@ -877,7 +877,8 @@ static int launch(const float* X, int64_t ldx, const void* prepared, const float
   P.n_chunks = N / P.BN;
   P.x_nchw = x_nchw; P.y_nchw = y_nchw; P.Mb = Mb; P.y = Y;
   P.conv3 = ln.conv3; P.H = ln.H; P.W = ln.W; P.C = ln.C; P.tiles_x = ln.conv3 ? (ln.W + 31) / 32 : 1;
-  P.tiles_per_b = ln.conv3 ? P.tiles_x * ((ln.H + 3) / 4) : x_nchw ? (Mb + kRows - 1) / kRows : 1;
+  // (token-major X with channel-major Y - msm_conv1x1_nhwc_fwd - has Mb % 128 == 0: row tiles are per image there too)
+  P.tiles_per_b = ln.conv3 ? P.tiles_x * ((ln.H + 3) / 4) : (x_nchw || y_nchw) ? (Mb + kRows - 1) / kRows : 1;
   P.m_tiles = x_nchw ? Bt * P.tiles_per_b : (M + kRows - 1) / kRows;
   CUtensorMap xmap, wmap, ymap, y2map;
   if (ln.conv3) {
@@ -1094,6 +1095,20 @@ extern "C" int msm_linear_fused_fwd(const float* X, int64_t ldx, const void* pre
     a.l2norm = l2_normalize ? 1 : 0; a.gamma2 = ln2_gamma; a.beta2 = ln2_beta; a.eps2 = ln2_eps; a.y2 = Y2; a.ldy2 = ldy2;
   }
   return msm::ltc::launch(X, ldx, prepared, bias, Y, ldy, M, N, K, act, 0, 0, 1, M, static_cast<cudaStream_t>(stream), a);
+}
+
+// 1x1 convolution of a channels-last map (X [B][HW][K], i.e. a channels_last NCHW tensor's memory) with the
+// channel-major result nn.Conv2d returns on contiguous tensors: Y [B][N][HW]. HW % 128 == 0 (row tiles are per image).
+extern "C" int msm_conv1x1_nhwc_fwd(const float* X, const void* prepared, const float* bias, float* Y, int B, int HW,
+                                    int N, int K, int act, void* stream) {
+  MSM_REQUIRE(X && prepared && Y, "X, prepared, Y must be non-null");
+  MSM_REQUIRE(B > 0 && HW > 0 && N > 0 && K > 0, "sizes must be positive");
+  MSM_REQUIRE(K % 32 == 0 && N % 32 == 0, "N and K must be multiples of 32");
+  MSM_REQUIRE(HW % 128 == 0, "H*W must be a multiple of 128");
+  MSM_REQUIRE(act == 0 || act == 1, "act must be 0 (none) or 1 (relu)");
+  MSM_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0,
+              "X and Y must be 16-byte aligned");
+  return msm::ltc::launch(X, K, prepared, bias, Y, N, B * HW, N, K, act, 0, 1, B, HW, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int msm_conv1x1_fwd(const float* X, const void* prepared, const float* bias, float* Y, int y_nchw, int B,

@@ -753,6 +753,39 @@ def conv1x1_supported(x, weight):
             and (x.shape[2] * x.shape[3]) % 4 == 0 and x.data_ptr() % 16 == 0)
 
 
+def _is_channels_last(x):
+    """a dense NCHW-shaped tensor whose memory is [B][H][W][C] (torch.channels_last) and not also NCHW-contiguous"""
+    return x.dim() == 4 and not x.is_contiguous() and x.permute(0, 2, 3, 1).is_contiguous()
+
+
+def conv1x1_nhwc_supported(x, weight):
+    if os.environ.get("MSM_DISABLE_TC_LINEAR", "") not in ("", "0"):
+        return False
+    return (x.is_cuda and x.dtype == torch.float32 and _is_channels_last(x) and weight.dim() == 4
+            and weight.shape[2] == 1 and weight.shape[3] == 1 and weight.is_contiguous()
+            and weight.shape[0] % 32 == 0 and weight.shape[1] % 32 == 0 and x.shape[1] == weight.shape[1]
+            and x.data_ptr() % 16 == 0)
+
+
+def conv1x1_nhwc(x, weight, bias=None, relu=False):
+    """kernel_size=1 convolution of a channels_last x [B,K,H,W] (no layout copy): -> [B,N,H,W], NCHW-contiguous when
+    H*W % 128 == 0 (msm_conv1x1_nhwc_fwd), else the channels_last view of the token-major result."""
+    _require(x, "x")
+    B, K, H, W = x.shape
+    N = weight.shape[0]
+    if (H * W) % 128:
+        y = linear(x.permute(0, 2, 3, 1).reshape(B, H * W, K), weight.detach().view(N, K),
+                   None if bias is None else bias.detach(), relu=relu)
+        return y.transpose(1, 2).reshape(B, N, H, W)
+    wp = prepare_linear_weight(weight.detach().view(N, K))
+    b = None if bias is None else _require(bias.detach(), "bias").contiguous()
+    out = torch.empty(B, N, H, W, device=x.device, dtype=torch.float32)
+    rc = _lib.lib().msm_conv1x1_nhwc_fwd(x.data_ptr(), wp.data_ptr(), b.data_ptr() if b is not None else None,
+                                         out.data_ptr(), B, H * W, N, K, 1 if relu else 0, _stream())
+    check(rc, "msm_conv1x1_nhwc_fwd")
+    return out
+
+
 def conv1x1(x, weight, bias=None, relu=False, tokens_out=False):
     """kernel_size=1 convolution on the tensor cores. x [B,K,H,W] contiguous, weight [N,K,1,1];
     returns [B,N,H,W] (default) or the token-major [B,H*W,N] the decoders consume."""
@@ -827,10 +860,13 @@ def conv1x1_layer(conv, x):
     """Forward of a kernel_size=1 Conv2d module (detectron2-style wrapper with optional .norm / .activation,
     or a plain nn.Conv2d): tensor-core path for inference on shapes it takes, the module itself otherwise."""
     needs_grad = torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad)
-    if needs_grad or conv.kernel_size != (1, 1) or conv.stride != (1, 1) or conv.groups != 1 \
-            or not conv1x1_supported(x, conv.weight):
+    plain = conv.kernel_size == (1, 1) and conv.stride == (1, 1) and conv.groups == 1 and not needs_grad
+    if plain and conv1x1_nhwc_supported(x, conv.weight):   # a channels_last backbone feature: no layout copy
+        y = conv1x1_nhwc(x, conv.weight, conv.bias)
+    elif plain and conv1x1_supported(x, conv.weight):
+        y = conv1x1(x, conv.weight, conv.bias)
+    else:
         return conv(x)
-    y = conv1x1(x, conv.weight, conv.bias)
     if getattr(conv, "norm", None) is not None:
         y = conv.norm(y)
     if getattr(conv, "activation", None) is not None:
@@ -1399,6 +1435,8 @@ resample_bilinear = _instrument("resample_bilinear", 1, lambda x, size: (
     f"{tuple(x.shape)}->{int(size[0])}x{int(size[1])}", 4.0 * (x.numel() // (x.shape[-1] * x.shape[-2])) * int(size[0]) * int(size[1]) * 5, 0.0))(resample_bilinear)
 linear = _instrument("linear", 1, _work_linear)(linear)
 conv1x1 = _instrument("linear", 1, _work_conv)(conv1x1)
+conv1x1_nhwc = _instrument("linear", lambda x, *a, **k: 0 if (x.shape[2] * x.shape[3]) % 128 else 1,
+                           _work_conv)(conv1x1_nhwc)   # (H*W % 128 != 0 goes through `linear`, which counts itself)
 conv3x3 = _instrument("linear", 1, _work_conv3)(conv3x3)
 linear_ln = _instrument("linear", 1, _work_linear_ln)(linear_ln)
 ffn_ln = _instrument("ffn", 1, _work_ffn)(ffn_ln)
