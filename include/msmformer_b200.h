@@ -123,6 +123,12 @@ int msm_mask_to_attn_bits(const float* masks, uint32_t* bits, int32_t* row_open,
  *   full-resolution masks): x [planes][H][W] -> y [planes][Ht][Wt], PyTorch's source-index rule. */
 int msm_resample_bilinear_fwd(const float* x, float* y, int64_t planes, int H, int W, int Ht, int Wt, void* stream);
 
+/* msm_upsample_add_fwd replaces  cur_fpn + F.interpolate(out[-1], size=cur_fpn.shape[-2:], mode="bilinear",
+ *   align_corners=False)  (the FPN top-down step, pixel_decoder/msdeformattn.py:349-352):
+ *   x [planes][H][W], add and y [planes][Ht][Wt]. */
+int msm_upsample_add_fwd(const float* x, const float* add, float* y, int64_t planes, int H, int W, int Ht, int Wt,
+                         void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Dense layer  Y[M][N] = act( X[M][K] . W[N][K]^T + bias[N] ),  act: 0 = identity, 1 = ReLU.
  * Replaces the torch.nn.functional.linear calls of the hot path: the packed q/k/v in-projection
@@ -181,6 +187,12 @@ int msm_ffn_ln_fwd(const float* X, int64_t ldx, const void* w1_prepared, const f
 int msm_add_layernorm_fwd(const float* x, const float* y, const float* gamma, const float* beta, float eps,
                           int l2_normalize, const float* gamma2, const float* beta2, float eps2, float* out,
                           float* out2, int rows, int C, void* stream);
+
+/* 3x3 / stride 2 / padding 1 max-pool of a channels-last map x [B][H][W][C] -> y [B][(H-1)/2+1][(W-1)/2+1][C]
+ * (C % 4 == 0): nn.MaxPool2d(3, 2, 1) of the ResNet stem (torchvision resnet.py; detectron2 BasicStem) on the
+ * channels_last tensors the cuDNN backbone produces. Outside the head's path; kept here because ATen's kernel for
+ * it costs 3 % of the whole-model step. */
+int msm_maxpool3x3s2_nhwc_fwd(const float* x, float* y, int B, int H, int W, int C, void* stream);
 
 /* 1x1 convolution on NCHW input with the same kernel: X [B][K][HW] (pixels contiguous), weight prepared as above
  * from the conv weight viewed as [N][K]. y_nchw != 0: Y [B][N][HW] (what nn.Conv2d returns); y_nchw == 0:

@@ -527,3 +527,26 @@ def test_backbone_fused_channels_last_matches_plain_module():
         assert got[k].permute(0, 2, 3, 1).is_contiguous()      # handed to the head without an NCHW copy
         scale = want[k].abs().max().item()
         assert (got[k] - want[k]).abs().max().item() / scale < 1e-4, k
+
+
+def test_maxpool_and_upsample_add_vs_torch():
+    """The two layout-aware helpers around the pixel decoder: msm_maxpool3x3s2_nhwc_fwd == nn.MaxPool2d(3, 2, 1) on a
+    channels_last map (bit-exact), msm_upsample_add_fwd == cur + F.interpolate(x, size, bilinear)."""
+    from unseenobjectswithmeanshift_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    for shape in ((2, 64, 30, 44), (1, 8, 7, 9), (2, 4, 1, 5)):
+        x = torch.randn(*shape, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+        got = ops.maxpool3x3s2_channels_last(x)
+        want = F.max_pool2d(x, 3, 2, 1)
+        assert got.shape == want.shape and torch.equal(got, want)
+    for (B, C, h, w), (Ht, Wt) in (((2, 256, 15, 20), (30, 40)), ((1, 3, 7, 5), (14, 10)), ((2, 5, 6, 6), (11, 13))):
+        x = torch.randn(B, C, h, w, generator=g).cuda()
+        cur = torch.randn(B, C, Ht, Wt, generator=g).cuda()
+        got = ops.upsample_add(x, cur)
+        want = cur + F.interpolate(x, size=(Ht, Wt), mode="bilinear", align_corners=False)
+        assert (got - want).abs().max().item() <= 4e-6 * max(1.0, want.abs().max().item())
+    # the token-major (channels_last view) map the encoder hands to the FPN step
+    xt = torch.randn(2, 15 * 20, 64, generator=g).cuda().transpose(1, 2).reshape(2, 64, 15, 20)
+    cur = torch.randn(2, 64, 30, 40, generator=g).cuda()
+    want = cur + F.interpolate(xt, size=(30, 40), mode="bilinear", align_corners=False)
+    assert (ops.upsample_add(xt, cur) - want).abs().max().item() <= 4e-6 * want.abs().max().item()

@@ -90,6 +90,11 @@ def main():
         hit = [e for e in evs if m in e[2].lower()]
         if hit:
             print(f"   {m:10s} first +{(hit[0][0] - t0) / 1e3:7.3f} ms  last end +{(max(h[1] for h in hit) - t0) / 1e3:7.3f} ms  n={len(hit)}")
+    if "dump" in sys.argv[2:]:
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open(f"gpurun_out/timeline_{kind}.txt", "w") as f:
+            for s_, e_, n_ in evs:
+                f.write(f"{(s_ - t0):9.1f} {(e_ - s_):8.1f} {n_[:140]}\n")
     # longest kernels
     for s, e, n in sorted(evs, key=lambda x: x[0] - x[1])[:10]:
         print(f"   {e - s:8.1f} us at +{(s - t0) / 1e3:7.3f} ms {n[:90]}")

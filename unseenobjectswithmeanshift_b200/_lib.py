@@ -29,6 +29,7 @@ SIGNATURES = {
     "msm_mask_logits": (_I, [_P, _P, _P, _I, _I, _I, _L, _P]),
     "msm_mask_to_attn_bits": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "msm_resample_bilinear_fwd": (_I, [_P, _P, _L, _I, _I, _I, _I, _P]),
+    "msm_upsample_add_fwd": (_I, [_P, _P, _P, _L, _I, _I, _I, _I, _P]),
     "msm_linear_weight_bytes": (_Z, [_I, _I]),
     "msm_linear_prepare_weight": (_I, [_P, _L, _P, _I, _I, _P]),
     "msm_linear_fwd": (_I, [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _P]),
@@ -37,6 +38,7 @@ SIGNATURES = {
                                   _I, _I, _I, _P]),
     "msm_ffn_ln_fwd": (_I, [_P, _L, _P, _P, _P, _P, _P, _P, _F, _P, _L, _I, _I, _I, _P]),
     "msm_add_layernorm_fwd": (_I, [_P, _P, _P, _P, _F, _I, _P, _P, _F, _P, _P, _I, _I, _P]),
+    "msm_maxpool3x3s2_nhwc_fwd": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "msm_conv1x1_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "msm_conv1x1_nhwc_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "msm_conv3x3_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),

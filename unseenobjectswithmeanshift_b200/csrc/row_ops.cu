@@ -78,7 +78,52 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
   }
 }
 
+// 3x3 / stride 2 / pad 1 max-pool of a channels-last map (the ResNet stem's pool, fed by a channels_last cuDNN
+// backbone): thread = (output pixel, 4 channels). ATen's max_pool_forward_nhwc takes 187 us for [8,64,240,320] on a
+// B200 (197 MB of traffic: 1.05 TB/s); this one is a plain coalesced float4 stream.
+__global__ void __launch_bounds__(256) maxpool3x3s2_nhwc_kernel(const float4* __restrict__ x, float4* __restrict__ y,
+                                                                int64_t total, int H, int W, int Ho, int Wo, int C4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    int64_t p = i / C4;
+    const int ox = (int)(p % Wo);
+    p /= Wo;
+    const int oy = (int)(p % Ho);
+    const int64_t b = p / Ho;
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int iy = 2 * oy - 1 + dy;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int ix = 2 * ox - 1 + dx;
+        if (ix < 0 || ix >= W) continue;
+        const float4 v = __ldg(x + ((b * H + iy) * W + ix) * C4 + c);
+        m.x = fmaxf(m.x, v.x);
+        m.y = fmaxf(m.y, v.y);
+        m.z = fmaxf(m.z, v.z);
+        m.w = fmaxf(m.w, v.w);
+      }
+    }
+    y[i] = m;
+  }
+}
+
 }  // namespace msm
+
+extern "C" int msm_maxpool3x3s2_nhwc_fwd(const float* x, float* y, int B, int H, int W, int C, void* stream) {
+  MSM_REQUIRE(x && y, "x, y must be non-null");
+  MSM_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "sizes must be positive and C a multiple of 4");
+  MSM_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0, "x, y must be 16-byte aligned");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const int64_t total = (int64_t)B * Ho * Wo * (C / 4);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  msm::maxpool3x3s2_nhwc_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), total, H, W, Ho, Wo, C / 4);
+  return msm::check_launch("maxpool3x3s2_nhwc_kernel");
+}
 
 extern "C" int msm_add_layernorm_fwd(const float* x, const float* y, const float* gamma, const float* beta, float eps,
                                      int l2_normalize, const float* gamma2, const float* beta2, float eps2, float* out,

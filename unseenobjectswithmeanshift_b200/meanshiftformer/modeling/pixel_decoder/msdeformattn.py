@@ -234,7 +234,10 @@ class MSDeformAttnPixelDecoder(nn.Module):
             out = [z.transpose(1, 2).reshape(B, -1, *shapes[i]) for i, z in enumerate(torch.split(y, sizes, dim=1))]
             for idx, f in enumerate(self.in_features[:self.num_fpn_levels][::-1]):
                 cur = ops.conv1x1_layer(self.lateral_convs[idx], features[f].float())
-                up = F.interpolate(out[-1], size=cur.shape[-2:], mode="bilinear", align_corners=False)
-                out.append(ops.conv_layer(self.output_convs[idx], cur + up))
+                if cur.is_cuda and not torch.is_grad_enabled():   # fused top-down step (one pass over the map)
+                    merged = ops.upsample_add(out[-1].float(), cur)
+                else:
+                    merged = cur + F.interpolate(out[-1], size=cur.shape[-2:], mode="bilinear", align_corners=False)
+                out.append(ops.conv_layer(self.output_convs[idx], merged))
             multi_scale = out[:self.maskformer_num_feature_levels]
             return ops.conv1x1_layer(self.mask_features, out[-1]), out[0], multi_scale

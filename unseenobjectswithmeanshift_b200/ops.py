@@ -435,6 +435,34 @@ def resample_bilinear(x, size):
     return y
 
 
+def maxpool3x3s2_channels_last(x):
+    """nn.MaxPool2d(3, 2, 1) of a channels_last x [B,C,H,W] (C % 4 == 0) -> channels_last [B,C,Ho,Wo] (inference only)."""
+    _require(x, "x")
+    B, C, H, W = x.shape
+    if not x.permute(0, 2, 3, 1).is_contiguous() or C % 4:
+        raise ValueError("x must be a channels_last tensor with C % 4 == 0")
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.empty(B, Ho, Wo, C, device=x.device, dtype=torch.float32)
+    rc = _lib.lib().msm_maxpool3x3s2_nhwc_fwd(x.data_ptr(), y.data_ptr(), B, H, W, C, _stream())
+    check(rc, "msm_maxpool3x3s2_nhwc_fwd")
+    return y.permute(0, 3, 1, 2)
+
+
+def upsample_add(x, add):
+    """add + F.interpolate(x, size=add.shape[-2:], mode="bilinear", align_corners=False), one pass (inference only)."""
+    x = _require(x, "x").contiguous()
+    add = _require(add, "add").contiguous()
+    H, W = x.shape[-2:]
+    Ht, Wt = add.shape[-2:]
+    if x.shape[:-2] != add.shape[:-2]:
+        raise ValueError(f"x {tuple(x.shape)} and add {tuple(add.shape)} must agree in the leading dimensions")
+    y = torch.empty_like(add)
+    rc = _lib.lib().msm_upsample_add_fwd(x.data_ptr(), add.data_ptr(), y.data_ptr(), x.numel() // (H * W), H, W, Ht, Wt,
+                                         _stream())
+    check(rc, "msm_upsample_add_fwd")
+    return y
+
+
 def unpack_attn_bits(bits, row_open, num_keys, num_heads):
     """bits/row_open -> the reference's bool attn_mask [B*heads, Q, S] AFTER its un-mask rule
     (decoder.py:618). For tests and for callers that want the reference representation."""
@@ -1431,6 +1459,10 @@ linear_packed_kv = _instrument("linear", 1, _work_linear_packed)(linear_packed_k
 vmf_attention_packed = _instrument("vmf_attention", 2, _work_vmf_packed)(vmf_attention_packed)
 mask_logits = _instrument("mask_logits", 1, _work_mask)(mask_logits)
 mask_to_attn_bits = _instrument("mask_to_attn_bits", 1, _work_bits)(mask_to_attn_bits)  # one kernel, no memset
+maxpool3x3s2_channels_last = _instrument("maxpool", 1, lambda x: (
+    f"{tuple(x.shape)}", 4.0 * x.numel() * 1.25, 0.0))(maxpool3x3s2_channels_last)
+upsample_add = _instrument("upsample_add", 1, lambda x, add: (
+    f"{tuple(x.shape)}->{tuple(add.shape[-2:])}", 4.0 * (x.numel() + 2 * add.numel()), 0.0))(upsample_add)
 resample_bilinear = _instrument("resample_bilinear", 1, lambda x, size: (
     f"{tuple(x.shape)}->{int(size[0])}x{int(size[1])}", 4.0 * (x.numel() // (x.shape[-1] * x.shape[-2])) * int(size[0]) * int(size[1]) * 5, 0.0))(resample_bilinear)
 linear = _instrument("linear", 1, _work_linear)(linear)
