@@ -162,7 +162,8 @@ def test_mask_logits_vs_einsum(msm, B, Q, C, H, W):
 
 @pytest.mark.parametrize("src,dst", [((120, 160), (15, 20)), ((120, 160), (30, 40)), ((120, 160), (60, 80)),
                                      ((48, 64), (48, 64)), ((24, 32), (5, 7)), ((9, 11), (20, 30)),
-                                     ((224, 224), (224, 224)), ((60, 80), (240, 320))])  # > 32768 keys: multi-block form
+                                     ((224, 224), (224, 224)), ((60, 80), (240, 320)),   # > 32768 keys: multi-block form
+                                     ((480, 640), (480, 640))])   # same-size stream kernel (also (224, 224))
 def test_mask_to_attn_bits_vs_oracle(msm, src, dst):
     """Same logits in, reference expression out (interpolate -> sigmoid -> < 0.5): bit-exact
     for integer-ratio and identity resampling; general ratios may differ on exact ties only."""
