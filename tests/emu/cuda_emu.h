@@ -93,6 +93,18 @@ inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
   std::memcpy(&v, &u, 4);
   return v;
 }
+inline uint32_t __ballot_sync(unsigned, bool pred) {   // all 32 lanes take part
+  auto* b = cuda_emu::g_block;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  b->warp_slots[warp][lane] = pred ? 1u : 0u;
+  b->warp_barrier[warp]->arrive_and_wait();
+  uint32_t r = 0;
+  for (int l = 0; l < 32; ++l) r |= b->warp_slots[warp][l] << l;
+  b->warp_barrier[warp]->arrive_and_wait();
+  return r;
+}
+inline bool __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) != 0; }
+inline int atomicOr(int32_t* p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 template <typename T>
 inline T __ldg(const T* p) { return *p; }
 inline float __uint_as_float(uint32_t u) {

@@ -470,6 +470,7 @@ inline f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) { return f32x2{std::fmaf(a.x, b.x
 inline f32x2 f2_add(f32x2 a, f32x2 b) { return f32x2{a.x + b.x, a.y + b.y}; }
 inline f32x2 f2_sub(f32x2 a, f32x2 b) { return f32x2{a.x - b.x, a.y - b.y}; }
 inline void split2_x2(float x, float y, uint32_t& hi, uint32_t& lo) { split2(x, y, hi, lo); }
+inline f32x2 f2_mul(f32x2 a, f32x2 b) { return f32x2{a.x * b.x, a.y * b.y}; }
 inline uint16_t f32_to_f16_rn(float x) {
   const _Float16 h = (_Float16)x;  // round-to-nearest-even (x86-64 gcc: soft-float or F16C)
   uint16_t u;
@@ -482,6 +483,7 @@ inline void split2h(float x, float y, uint32_t& hi, uint32_t& lo) {
   lo = (uint32_t)f32_to_f16_rn(x - f16_to_f32(hx)) | ((uint32_t)f32_to_f16_rn(y - f16_to_f32(hy)) << 16);
 }
 constexpr bool kGemmF16 = true;
+inline void split2h_x2(float x, float y, uint32_t& hi, uint32_t& lo) { split2h(x, y, hi, lo); }
 inline void split2g(float x, float y, uint32_t& hi, uint32_t& lo) { split2h(x, y, hi, lo); }
 constexpr uint32_t idesc_g(int M, int N, bool a, bool b) { return idesc_f16(M, N, a, b); }
 

@@ -451,9 +451,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
           }
           if (in) {
+            // (two-wide fp32 instructions where the operands pair up: bias add, scale, the split's residual - the
+            //  epilogue of this instantiation is the kernel's bottleneck, IPC-limited)
             float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + wBias[ch * 32 + j];
+            for (int j = 0; j < 32; j += 2) {
+              const float2 bb = *reinterpret_cast<const float2*>(wBias + ch * 32 + j);
+              tc::f2_unpack(tc::f2_add(tc::f2_pack(__uint_as_float(r[j]), __uint_as_float(r[j + 1])),
+                                       tc::f2_pack(bb.x, bb.y)), v[j], v[j + 1]);
+            }
             if (pos) {
 #pragma unroll
               for (int c = 0; c < 8; ++c) {
@@ -481,22 +487,27 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
               for (int j = 0; j < 32; ++j) ss = fmaf(v[j], v[j], ss);
               inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
             }
+            const tc::f32x2 inv2 = tc::f2_pack(inv, inv);
             uint8_t* img = P.pack_out +
                            ((((int64_t)layer * P.pack_B + bi) * hpl + head) * P.pack_ntiles + (key >> 7)) * (4 * kOp) +
                            (uint32_t)P.pack_slot * kOp + koff;
 #pragma unroll
             for (int dg = 0; dg < 4; ++dg) {
               uint4 hi, lo;
+              float w[8];
+#pragma unroll
+              for (int j = 0; j < 8; j += 2)
+                tc::f2_unpack(tc::f2_mul(tc::f2_pack(v[8 * dg + j], v[8 * dg + j + 1]), inv2), w[j], w[j + 1]);
               if (P.pack_f16) {
-                tc::split2h(v[8 * dg + 0] * inv, v[8 * dg + 1] * inv, hi.x, lo.x);
-                tc::split2h(v[8 * dg + 2] * inv, v[8 * dg + 3] * inv, hi.y, lo.y);
-                tc::split2h(v[8 * dg + 4] * inv, v[8 * dg + 5] * inv, hi.z, lo.z);
-                tc::split2h(v[8 * dg + 6] * inv, v[8 * dg + 7] * inv, hi.w, lo.w);
+                tc::split2h_x2(w[0], w[1], hi.x, lo.x);
+                tc::split2h_x2(w[2], w[3], hi.y, lo.y);
+                tc::split2h_x2(w[4], w[5], hi.z, lo.z);
+                tc::split2h_x2(w[6], w[7], hi.w, lo.w);
               } else {
-                tc::split2(v[8 * dg + 0] * inv, v[8 * dg + 1] * inv, hi.x, lo.x);
-                tc::split2(v[8 * dg + 2] * inv, v[8 * dg + 3] * inv, hi.y, lo.y);
-                tc::split2(v[8 * dg + 4] * inv, v[8 * dg + 5] * inv, hi.z, lo.z);
-                tc::split2(v[8 * dg + 6] * inv, v[8 * dg + 7] * inv, hi.w, lo.w);
+                tc::split2_x2(w[0], w[1], hi.x, lo.x);
+                tc::split2_x2(w[2], w[3], hi.y, lo.y);
+                tc::split2_x2(w[4], w[5], hi.z, lo.z);
+                tc::split2_x2(w[6], w[7], hi.w, lo.w);
               }
               *reinterpret_cast<uint4*>(img + dg * kLbo) = hi;
               *reinterpret_cast<uint4*>(img + kOp + dg * kLbo) = lo;

@@ -235,13 +235,14 @@ __global__ void mask_bits_multi_kernel(const float* __restrict__ masks, uint32_t
 // St % 128 == 0; row flags by atomicOr into a zero-filled array. (The per-element ballot form ran at 1.7 TB/s.)
 __global__ void __launch_bounds__(256) mask_bits_same_size_kernel(const float4* __restrict__ masks,
                                                                   uint32_t* __restrict__ bits,
-                                                                  int32_t* __restrict__ row_open, int64_t groups,
-                                                                  int groups_per_row) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t gidx = warp0; gidx < groups; gidx += nwarps) {   // one group = 128 keys = 4 words
-    const float4 v = __ldg(masks + gidx * 32 + lane);
+                                                                  int32_t* __restrict__ row_open, int groups_per_row) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.y;
+  const float4* mp = masks + (int64_t)row * groups_per_row * 32;
+  uint32_t* bp = bits + (int64_t)row * groups_per_row * 4;
+  bool any_open = false;
+  for (int g = blockIdx.x * 8 + warp; g < groups_per_row; g += gridDim.x * 8) {   // one group = 128 keys = 4 words
+    const float4 v = __ldg(mp + g * 32 + lane);
     const float e[4] = {v.x, v.y, v.z, v.w};
     uint32_t nib = 0;
 #pragma unroll
@@ -250,14 +251,14 @@ __global__ void __launch_bounds__(256) mask_bits_same_size_kernel(const float4* 
       if (fabsf(e[j]) < 1e-4f) blocked = 1.f / (1.f + expf(-e[j])) < 0.5f;
       nib |= (blocked ? 1u : 0u) << j;
     }
+    any_open |= nib != 0xfu;
     uint32_t word = nib << (4 * (lane & 7));
     word |= __shfl_xor_sync(0xffffffffu, word, 1);
     word |= __shfl_xor_sync(0xffffffffu, word, 2);
     word |= __shfl_xor_sync(0xffffffffu, word, 4);
-    if ((lane & 7) == 0) bits[gidx * 4 + (lane >> 3)] = word;
-    const bool any_open = __any_sync(0xffffffffu, nib != 0xfu);
-    if (any_open && lane == 0) atomicOr(row_open + gidx / groups_per_row, 1);
+    if ((lane & 7) == 0) bp[g * 4 + (lane >> 3)] = word;
   }
+  if (__any_sync(0xffffffffu, any_open) && lane == 0) atomicOr(row_open + row, 1);
 }
 
 // Bilinear resample of `planes` images [H][W] -> [Ht][Wt] (align_corners=False, the rule above): one thread per output
@@ -363,14 +364,13 @@ extern "C" int msm_mask_to_attn_bits(const float* masks, uint32_t* bits, int32_t
   const int words = (Ht * Wt + 31) / 32;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (H == Ht && W == Wt && (Ht * Wt) % 128 == 0 && words > 1024 &&
-      (reinterpret_cast<uintptr_t>(masks) & 15) == 0) {  // same-size stream (UCN / crop full-resolution layers)
+      (reinterpret_cast<uintptr_t>(masks) & 15) == 0 && rows <= 65535) {  // same-size stream (UCN / crop full-resolution layers)
     MSM_CUDA(cudaMemsetAsync(row_open, 0, sizeof(int32_t) * rows, st));
     const int gpr = (Ht * Wt) / 128;
-    const int64_t groups = (int64_t)rows * gpr;
-    int64_t blocks = (groups + 7) / 8;
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    msm::mask_bits_same_size_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(masks), bits,
-                                                                     row_open, groups, gpr);
+    int bx = (gpr + 7) / 8;
+    if (bx > 64) bx = 64;
+    msm::mask_bits_same_size_kernel<<<dim3(bx, rows), 256, 0, st>>>(reinterpret_cast<const float4*>(masks), bits, row_open,
+                                                                    gpr);
     return msm::check_launch("mask_bits_same_size_kernel");
   }
   if (words > 1024 && rows <= 65535) {  // one block per row would leave most of the GPU idle

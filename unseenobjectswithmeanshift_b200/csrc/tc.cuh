@@ -276,6 +276,21 @@ __device__ __forceinline__ void split2h(float x, float y, uint32_t& hi, uint32_t
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+// the same with the residual as ONE two-wide subtraction (see "packed fp32 pairs" above)
+__device__ __forceinline__ void split2h_x2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x, y);
+  const float2 f = __half22float2(h);
+  float rx, ry;
+  f2_unpack(f2_sub(f2_pack(x, y), f2_pack(f.x, f.y)), rx, ry);
+  const __half2 l = __floats2half2_rn(rx, ry);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
 // Instruction descriptor for kind::f16 with fp16 A/B (format code 0) and fp32 D.
 __host__ __device__ constexpr uint32_t idesc_f16(int M, int N, bool a_mn_major, bool b_mn_major) {
   return (1u << 4) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
