@@ -1070,9 +1070,14 @@ def run_forward(args, rank, local_rank, world, dev, sharding, ops, workloads):
         tensor_bound = g["bytes"] > 0 and 3.0 * g["flops"] / g["bytes"] > ridge
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of these
         # kernels at these shapes (profiles/): a constant of an earlier run, NOT measured by this process
-        traffic_from_profile = {("mask_logits", "B8 Q100 C256 HW19200"): 186.5e6,
-                                ("ms_deform_attn_forward", "fused N8 S6300 M8 D8 Lq6300"): 76.7e6,
-                                ("ffn", "ffn+LN M50400 D64 F1024"): 13.5e6}
+        # (profiles/r02_ncu_kernels.md, profiles/r02_ncu_operand_images.md)
+        traffic_from_profile = {("linear", "M800 N256 K256"): 1.16e6,
+                                ("mask_logits", "B8 Q100 C256 HW19200"): 185.1e6,
+                                ("ms_deform_attn_forward", "fused N8 S6300 M8 D8 Lq6300"): 75.9e6,
+                                ("ffn", "ffn+LN M50400 D64 F1024"): 13.5e6,
+                                ("linear", "M50400 N288 K64"): 16.9e6,
+                                ("linear", "K-images M307200 N1536 K64"): 1919.2e6,
+                                ("linear", "V-images M307200 N1536 K64"): 1908.7e6}
         roofline = {"kernel": tag, "shape": sig, "launches_per_step": per, "avg_launch_ms": avg_ms,
                     "share_of_step": (g["ms"] / n_eager) / step_ms,
                     "algorithmic_bytes_per_launch": g["bytes"] / g["count"],
