@@ -283,3 +283,33 @@ def test_eval_after_train_step_sees_the_new_weights():
     assert torch.equal(after, fresh), "eval after train_step used stale derived weights"
     # the premise of the fix, recorded: does the fused optimizer bump _version on this torch build?
     print("fused AdamW bumped _version:", [p._version for p in dec.parameters()] != versions)
+
+
+@pytest.mark.parametrize("M,N,K,relu,bias", [(800, 256, 256, False, True), (1000, 64, 1024, True, True),
+                                             (333, 96, 64, False, False), (128, 2048, 256, True, True)])
+def test_dense_function_gradients_vs_fp64(M, N, K, relu, bias):
+    """ops.dense under autograd (fp32 training): forward and the input gradient in linear_tc_kernel, weight / bias
+    gradients in cuBLAS - against fp64 autograd of act(x W^T + b)."""
+    from unseenobjectswithmeanshift_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g) * 0.1 if bias else None
+    go = torch.randn(M, N, generator=g)
+    xd, wd = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    bd = b.double().requires_grad_(True) if bias else None
+    yd = torch.nn.functional.linear(xd, wd, bd)
+    yd = torch.relu(yd) if relu else yd
+    yd.backward(go.double())
+    xc, wc = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+    bc = b.cuda().requires_grad_(True) if bias else None
+    assert ops.dense_autograd_supported(xc, wc)
+    y = ops.dense(xc, wc, bc, relu=relu)
+    assert y.grad_fn is not None and "DenseFunction" in type(y.grad_fn).__name__
+    y.backward(go.cuda())
+    rel = lambda a, r: (a.detach().cpu().double() - r).abs().max().item() / max(r.abs().max().item(), 1e-12)  # noqa: E731
+    assert rel(y, yd.detach()) < 1e-5
+    assert rel(xc.grad, xd.grad) < 1e-5
+    assert rel(wc.grad, wd.grad) < 1e-5
+    if bias:
+        assert rel(bc.grad, bd.grad) < 1e-5

@@ -37,10 +37,11 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
         return tensor if pos is None else tensor + pos
 
     def forward_ffn(self, src):
-        if self.activation is F.relu and not self.training:
-            h = ops.dense(src, self.linear1.weight, self.linear1.bias, relu=True)
-            return self.norm2(src + ops.dense(h, self.linear2.weight, self.linear2.bias))
-        return self.norm2(src + self.dropout3(self.linear2(self.dropout2(self.activation(self.linear1(src))))))
+        relu = self.activation is F.relu   # ops.dense: tensor-core GEMM, also under autograd (fp32 training)
+        h = ops.dense(src, self.linear1.weight, self.linear1.bias, relu=relu)
+        if not relu:
+            h = self.activation(h)
+        return self.norm2(src + self.dropout3(ops.dense(self.dropout2(h), self.linear2.weight, self.linear2.bias)))
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
         attn = self.self_attn

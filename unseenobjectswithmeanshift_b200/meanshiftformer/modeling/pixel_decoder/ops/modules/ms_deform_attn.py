@@ -93,7 +93,8 @@ class MSDeformAttn(nn.Module):
         needs_grad = torch.is_grad_enabled() and (
             query.requires_grad or input_flatten.requires_grad or any(p.requires_grad for p in self.parameters()))
         if needs_grad:
-            ow = torch.cat([self.sampling_offsets(query), self.attention_weights(query)], -1)
+            ow = torch.cat([ops.dense(query, self.sampling_offsets.weight, self.sampling_offsets.bias),
+                            ops.dense(query, self.attention_weights.weight, self.attention_weights.bias)], -1)
         else:
             if pos_table is not None and ops.linear_supported(query, w_ow):
                 tab = ops.cached_value(self, "ow_pos", [pos_table, w_ow],

@@ -52,13 +52,13 @@ def ms_in_projection_packed(q: Tensor, k: Tensor, v: Tensor, w: Tensor, b: Optio
     E = q.size(-1)
     if k is v:
         if q is k:
-            return F.linear(q, w, b).chunk(3, dim=-1)
+            return ops.dense(q, w, b).chunk(3, dim=-1)
         w_q, w_kv = w.split([E, E * 2])
         b_q, b_kv = (None, None) if b is None else b.split([E, E * 2])
-        return (F.linear(q, w_q, b_q),) + F.linear(k, w_kv, b_kv).chunk(2, dim=-1)
+        return (ops.dense(q, w_q, b_q),) + ops.dense(k, w_kv, b_kv).chunk(2, dim=-1)
     w_q, w_k, w_v = w.chunk(3)
     b_q, b_k, b_v = (None, None, None) if b is None else b.chunk(3)
-    return F.linear(q, w_q, b_q), F.linear(k, w_k, b_k), F.linear(v, w_v, b_v)
+    return ops.dense(q, w_q, b_q), ops.dense(k, w_k, b_k), ops.dense(v, w_v, b_v)
 
 
 def hypersphere_attention_forward(query: Tensor, key: Tensor, value: Tensor, embed_dim_to_check: int, num_heads: int,
@@ -105,7 +105,7 @@ def hypersphere_attention_forward(query: Tensor, key: Tensor, value: Tensor, emb
     q4, k4, v4 = heads_view(q, L), heads_view(k, S), heads_view(v, S)
     o = torch.empty(L, N, E, device=q.device, dtype=torch.float32)
     res = ops.vmf_attention(q4, k4, v4, add_mask=add_mask, kappa=KAPPA, out=heads_view(o, L), return_den=need_weights)
-    attn_output = F.linear(o, out_proj_weight, out_proj_bias)
+    attn_output = ops.dense(o, out_proj_weight, out_proj_bias)
     if not need_weights:
         return attn_output, None
     _, den = res

@@ -170,15 +170,16 @@ class FFNLayer(nn.Module):
         _xavier(self)
 
     def forward(self, tgt):
+        def ffn(t):   # ops.dense: tensor-core GEMM in inference AND under autograd (fp32 training, DenseFunction)
+            relu = self.activation is F.relu
+            h = ops.dense(t, self.linear1.weight, self.linear1.bias, relu=relu)
+            if not relu:
+                h = self.activation(h)
+            return ops.dense(self.dropout(h), self.linear2.weight, self.linear2.bias)
+
         if self.normalize_before:
-            t2 = self.norm(tgt)
-            return tgt + self.dropout(self.linear2(self.dropout(self.activation(self.linear1(t2)))))
-        if self.activation is F.relu and not self.training:
-            t2 = ops.dense(ops.dense(tgt, self.linear1.weight, self.linear1.bias, relu=True),
-                           self.linear2.weight, self.linear2.bias)
-        else:
-            t2 = self.linear2(self.dropout(self.activation(self.linear1(tgt))))
-        return self.norm(tgt + self.dropout(t2))
+            return tgt + self.dropout(ffn(self.norm(tgt)))
+        return self.norm(tgt + self.dropout(ffn(tgt)))
 
 
 class MLP(nn.Module):

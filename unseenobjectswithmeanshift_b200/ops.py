@@ -525,6 +525,17 @@ def prepare_linear_weight(weight):
     return buf
 
 
+def _prepare_linear_weight_once(weight):
+    """prepare_linear_weight without the cache: training (the weight changes every step, and so does its transpose)."""
+    w = _require(weight, "weight")
+    N, K = w.shape
+    L = _lib.lib()
+    buf = torch.empty(L.msm_linear_weight_bytes(N, K), device=w.device, dtype=torch.uint8)
+    check(L.msm_linear_prepare_weight(w.data_ptr(), w.stride(0), buf.data_ptr(), N, K, _stream()),
+          "msm_linear_prepare_weight")
+    return buf
+
+
 def tc_linear_enabled():
     """False when MSM_DISABLE_TC_LINEAR is set (dense layers then run in cuBLAS fp32 - a cross-check switch)."""
     return os.environ.get("MSM_DISABLE_TC_LINEAR", "") in ("", "0")
@@ -539,7 +550,7 @@ def linear_supported(x, weight):
             and weight.stride(0) % 4 == 0 and weight.data_ptr() % 16 == 0 and x.shape[-1] == weight.shape[1])
 
 
-def linear(x, weight, bias=None, relu=False, out=None):
+def linear(x, weight, bias=None, relu=False, out=None, _prepared=None):
     """act(x @ weight.T + bias) on the tensor cores (bf16x3 split precision, fp32 accumulate).
     x [..., K] whose leading axes collapse to uniformly strided rows; weight [N, K]; returns [..., N]."""
     _require(x, "x")
@@ -556,7 +567,7 @@ def linear(x, weight, bias=None, relu=False, out=None):
     y2 = out.view(-1, N) if out.is_contiguous() else out
     if y2.dim() != 2 or y2.shape != (M, N) or y2.stride(1) != 1:
         raise ValueError("out must be a [M, N] matrix with contiguous rows")
-    wp = prepare_linear_weight(weight)
+    wp = _prepared if _prepared is not None else prepare_linear_weight(weight)
     b = None
     if bias is not None:
         b = _require(bias, "bias").contiguous()
@@ -902,6 +913,50 @@ def conv1x1_layer(conv, x):
     return y
 
 
+class DenseFunction(torch.autograd.Function):
+    """Differentiable dense layer for fp32 training: forward and the input gradient run in
+    linear_tc_kernel (split-precision tensor-core GEMM, the same arithmetic as inference; dX = dY . W is the same
+    kernel on the transposed weight), the weight gradient dW = dY^T . X - a reduction over all rows - and the bias
+    gradient stay in cuBLAS / ATen (fp32, TF32 off)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        xd, wd = x.detach(), weight.detach()
+        y = linear(xd, wd, None if bias is None else bias.detach(), relu=relu, _prepared=_prepare_linear_weight_once(wd))
+        ctx.save_for_backward(xd, wd, y if relu else None)
+        ctx.relu, ctx.has_bias = relu, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        N, K = w.shape
+        g2 = gy.reshape(-1, N)
+        if ctx.relu:
+            g2 = g2 * (y.reshape(-1, N) > 0)
+        g2 = g2.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            wt = w.t().contiguous()                      # [K, N]: dX = dY . W = linear(dY, W^T)
+            gx = linear(g2, wt, _prepared=_prepare_linear_weight_once(wt)).reshape(x.shape)
+        if ctx.needs_input_grad[1]:
+            tf32 = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = False
+            try:
+                gw = g2.t() @ x.reshape(-1, K)
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g2.sum(0)
+        return gx, gw, gb, None
+
+
+def dense_autograd_supported(x, weight):
+    """fp32 training outside autocast on shapes the tensor-core kernel takes in BOTH directions (N, K multiples of 32)."""
+    return (os.environ.get("MSM_TRAIN_TC_LINEAR", "1") == "1" and linear_supported(x, weight)
+            and not torch.is_autocast_enabled() and weight.is_contiguous() and x.numel() > 0)
+
+
 def dense(x, weight, bias=None, relu=False):
     """The layer call the modules use: tensor-core ``linear`` for inference on shapes it takes,
     torch's F.linear (cuBLAS fp32, autograd-capable) when gradients are needed or N/K are not
@@ -922,6 +977,8 @@ def dense(x, weight, bias=None, relu=False):
             bp = cached_value(_PAD_CACHE_OWNER, f"b{bias.data_ptr()}_{N}", [bias],
                               lambda: torch.cat([bias.detach(), bias.new_zeros(Np - N)], 0).contiguous())
         return linear(x, wp, bp, relu=relu)[..., :N]
+    if needs_grad and dense_autograd_supported(x, weight):
+        return DenseFunction.apply(x, weight, bias, relu)
     if needs_grad or not linear_supported(x, weight):
         y = torch.nn.functional.linear(x, weight, bias)
         return torch.relu_(y) if relu else y
