@@ -118,10 +118,12 @@ int msm_mask_logits(const float* embed, const float* feat, float* masks,
 int msm_mask_to_attn_bits(const float* masks, uint32_t* bits, int32_t* row_open,
                           int B, int Q, int H, int W, int Ht, int Wt, void* stream);
 
-/* msm_resample_bilinear_fwd replaces  F.interpolate(x, size=(Ht, Wt), mode="bilinear", align_corners=False)
- *   (the resampling of decoder.py:675, applied to the mask FEATURES by the inference path that skips the auxiliary
- *   full-resolution masks): x [planes][H][W] -> y [planes][Ht][Wt], PyTorch's source-index rule. */
-int msm_resample_bilinear_fwd(const float* x, float* y, int64_t planes, int H, int W, int Ht, int Wt, void* stream);
+/* msm_resample_bilinear_fwd replaces  F.interpolate(x, size=(Ht, Wt), mode="bilinear", align_corners=...)
+ *   (align_corners = 0: the resampling of decoder.py:675, applied to the mask FEATURES by the inference path that
+ *   skips the auxiliary full-resolution masks; align_corners = 1: upsample_bilinear of the embedding network,
+ *   lib/networks/resnet_dilated.py:325): x [planes][H][W] -> y [planes][Ht][Wt], PyTorch's source-index rules. */
+int msm_resample_bilinear_fwd(const float* x, float* y, int64_t planes, int H, int W, int Ht, int Wt, int align_corners,
+                              void* stream);
 
 /* msm_upsample_add_fwd replaces  cur_fpn + F.interpolate(out[-1], size=cur_fpn.shape[-2:], mode="bilinear",
  *   align_corners=False)  (the FPN top-down step, pixel_decoder/msdeformattn.py:349-352):

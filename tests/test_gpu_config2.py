@@ -413,14 +413,33 @@ def test_lean_eval_path_matches_full_masks():
                                         ((1, 3, 7, 5), (13, 9)), ((3, 5, 33, 17), (33, 17)), ((1, 2, 1, 1), (4, 6)),
                                         ((2, 100, 120, 160), (480, 640))])
 def test_resample_bilinear_vs_interpolate(shape, size):
-    """msm_resample_bilinear_fwd == F.interpolate(bilinear, align_corners=False): down-, up-sampling, identity, 1x1."""
+    """msm_resample_bilinear_fwd == F.interpolate(bilinear), both align_corners rules: down-, up-sampling, identity, 1x1."""
     from unseenobjectswithmeanshift_b200 import ops
     g = torch.Generator().manual_seed(11)
     x = torch.randn(*shape, generator=g).cuda()
-    got = ops.resample_bilinear(x, size)
-    want = F.interpolate(x, size=size, mode="bilinear", align_corners=False)
-    assert got.shape == want.shape
-    assert (got - want).abs().max().item() <= 2e-6 * max(1.0, want.abs().max().item())
+    for ac in (False, True):
+        got = ops.resample_bilinear(x, size, align_corners=ac)
+        want = F.interpolate(x, size=size, mode="bilinear", align_corners=ac)
+        assert got.shape == want.shape
+        assert (got - want).abs().max().item() <= 4e-6 * max(1.0, want.abs().max().item()), ac
+
+
+def test_segnet_embedding_single_upsample_matches_two():
+    """backbones.SegnetEmbedding on the GPU sums the RGB and depth streams at 1/8 resolution and up-samples once
+    (bilinear, align_corners=True, is linear) - against the module's plain path (two up-samplings, then the sum)."""
+    from unseenobjectswithmeanshift_b200 import backbones
+    backbones.set_tf32(False)
+    try:
+        m = backbones.SegnetEmbedding(seed=1).cuda()
+        g = torch.Generator().manual_seed(3)
+        img, dep = torch.randn(1, 3, 96, 128, generator=g).cuda(), torch.randn(1, 3, 96, 128, generator=g).cuda()
+        with torch.no_grad(), backbones._conv_math(False):   # (the module sets its conv math itself; the streams do not)
+            got = m(img, None, dep)
+            want = m.fcn(img) + m.fcn_depth(dep)
+        assert got.is_contiguous() and got.shape == want.shape
+        assert (got - want).abs().max().item() / want.abs().max().item() < 1e-5
+    finally:
+        backbones.set_tf32(True)
 
 
 @pytest.mark.parametrize("B,Hh,Ww,layers,masked", [(2, 16, 64, 2, True),    # image rows never wrap inside a warp

@@ -28,7 +28,7 @@ SIGNATURES = {
                               [_P, _I, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P, _Z, _P]),
     "msm_mask_logits": (_I, [_P, _P, _P, _I, _I, _I, _L, _P]),
     "msm_mask_to_attn_bits": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
-    "msm_resample_bilinear_fwd": (_I, [_P, _P, _L, _I, _I, _I, _I, _P]),
+    "msm_resample_bilinear_fwd": (_I, [_P, _P, _L, _I, _I, _I, _I, _I, _P]),
     "msm_upsample_add_fwd": (_I, [_P, _P, _P, _L, _I, _I, _I, _I, _P]),
     "msm_linear_weight_bytes": (_Z, [_I, _I]),
     "msm_linear_prepare_weight": (_I, [_P, _L, _P, _I, _I, _P]),

@@ -266,15 +266,19 @@ __global__ void __launch_bounds__(256) mask_bits_same_size_kernel(const float4* 
 // (interpolate(einsum(e, F)) == einsum(e, interpolate(F))); ATen's kernel for this NCHW down-sampling takes 1.0-1.25 ms
 // per call at [8,256,120,160] on a B200 (it parallelises over output pixels only) - this one is bandwidth-trivial.
 __global__ void __launch_bounds__(256) resample_bilinear_kernel(const float* __restrict__ x, float* __restrict__ y,
-                                                                int64_t total, int H, int W, int Ht, int Wt) {
-  const float sh = (float)H / (float)Ht, sw = (float)W / (float)Wt;
+                                                                int64_t total, int H, int W, int Ht, int Wt,
+                                                                int align_corners) {
+  // PyTorch's source-index rules: align_corners=False: scale = in / out, src = scale * (dst + 0.5) - 0.5 clamped at 0;
+  // align_corners=True: scale = (in - 1) / (out - 1), src = scale * dst
+  const float sh = align_corners ? (Ht > 1 ? (float)(H - 1) / (float)(Ht - 1) : 0.f) : (float)H / (float)Ht;
+  const float sw = align_corners ? (Wt > 1 ? (float)(W - 1) / (float)(Wt - 1) : 0.f) : (float)W / (float)Wt;
   const int St = Ht * Wt;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t plane = i / St;
     const int s = (int)(i - plane * St);
     const int oy = s / Wt, ox = s - oy * Wt;
-    float sy = sh * ((float)oy + 0.5f) - 0.5f;
-    float sx = sw * ((float)ox + 0.5f) - 0.5f;
+    float sy = align_corners ? sh * (float)oy : sh * ((float)oy + 0.5f) - 0.5f;
+    float sx = align_corners ? sw * (float)ox : sw * ((float)ox + 0.5f) - 0.5f;
     sy = sy < 0.f ? 0.f : sy;
     sx = sx < 0.f ? 0.f : sx;
     const int y0 = (int)sy, x0 = (int)sx;
@@ -328,14 +332,15 @@ extern "C" int msm_upsample_add_fwd(const float* x, const float* add, float* y, 
 }
 
 extern "C" int msm_resample_bilinear_fwd(const float* x, float* y, int64_t planes, int H, int W, int Ht, int Wt,
-                                         void* stream) {
+                                         int align_corners, void* stream) {
   MSM_REQUIRE(x && y, "x, y must be non-null");
   MSM_REQUIRE(planes > 0 && H > 0 && W > 0 && Ht > 0 && Wt > 0, "sizes must be positive");
   MSM_REQUIRE((int64_t)H * W < ((int64_t)1 << 31) && (int64_t)Ht * Wt < ((int64_t)1 << 31), "one plane must fit 31 bits");
   const int64_t total = planes * Ht * Wt;
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  msm::resample_bilinear_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, total, H, W, Ht, Wt);
+  msm::resample_bilinear_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, total, H, W, Ht, Wt,
+                                                                                                 align_corners ? 1 : 0);
   return msm::check_launch("resample_bilinear_kernel");
 }
 

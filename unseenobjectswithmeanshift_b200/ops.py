@@ -423,14 +423,15 @@ def mask_to_attn_bits(masks, target_size):
     return bits, row_open
 
 
-def resample_bilinear(x, size):
-    """F.interpolate(x, size=size, mode="bilinear", align_corners=False) for x [..., H, W] (inference only)."""
+def resample_bilinear(x, size, align_corners=False):
+    """F.interpolate(x, size=size, mode="bilinear", align_corners=align_corners) for x [..., H, W] (inference only)."""
     x = _require(x, "x").contiguous()
     H, W = x.shape[-2:]
     Ht, Wt = int(size[0]), int(size[1])
     y = torch.empty(*x.shape[:-2], Ht, Wt, device=x.device, dtype=torch.float32)
     planes = x.numel() // (H * W)
-    rc = _lib.lib().msm_resample_bilinear_fwd(x.data_ptr(), y.data_ptr(), planes, H, W, Ht, Wt, _stream())
+    rc = _lib.lib().msm_resample_bilinear_fwd(x.data_ptr(), y.data_ptr(), planes, H, W, Ht, Wt, 1 if align_corners else 0,
+                                              _stream())
     check(rc, "msm_resample_bilinear_fwd")
     return y
 
@@ -1520,7 +1521,7 @@ maxpool3x3s2_channels_last = _instrument("maxpool", 1, lambda x: (
     f"{tuple(x.shape)}", 4.0 * x.numel() * 1.25, 0.0))(maxpool3x3s2_channels_last)
 upsample_add = _instrument("upsample_add", 1, lambda x, add: (
     f"{tuple(x.shape)}->{tuple(add.shape[-2:])}", 4.0 * (x.numel() + 2 * add.numel()), 0.0))(upsample_add)
-resample_bilinear = _instrument("resample_bilinear", 1, lambda x, size: (
+resample_bilinear = _instrument("resample_bilinear", 1, lambda x, size, align_corners=False: (
     f"{tuple(x.shape)}->{int(size[0])}x{int(size[1])}", 4.0 * (x.numel() // (x.shape[-1] * x.shape[-2])) * int(size[0]) * int(size[1]) * 5, 0.0))(resample_bilinear)
 linear = _instrument("linear", 1, _work_linear)(linear)
 conv1x1 = _instrument("linear", 1, _work_conv)(conv1x1)
