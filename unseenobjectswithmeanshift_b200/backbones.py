@@ -256,9 +256,21 @@ class SegnetEmbedding(nn.Module):
                 # by the library's resample kernel (ATen's NHWC kernel: 165 us per stream at 480x640, plus the add and
                 # the NHWC -> NCHW copy of the 79 MB map)
                 from . import ops
-                s = self.fcn(img, upsample=False)
                 if self.fcn_depth is not None and depth is not None:
-                    s = s + self.fcn_depth(depth.contiguous(memory_format=self.fmt), upsample=False)
+                    # the two streams are independent and, at batch 1, too small to fill the GPU one after the other:
+                    # the depth stream runs on a side stream (a parallel branch of the step's CUDA graph)
+                    main = torch.cuda.current_stream()
+                    if getattr(self, "_side", None) is None:
+                        self._side = torch.cuda.Stream()
+                    self._side.wait_stream(main)
+                    with torch.cuda.stream(self._side):
+                        d = self.fcn_depth(depth.contiguous(memory_format=self.fmt), upsample=False)
+                    s = self.fcn(img, upsample=False)
+                    main.wait_stream(self._side)
+                    d.record_stream(main)
+                    s = s + d
+                else:
+                    s = self.fcn(img, upsample=False)
                 return ops.resample_bilinear(s.float().contiguous(), img.shape[-2:], align_corners=True)
             f = self.fcn(img)
             if self.fcn_depth is not None and depth is not None:
