@@ -69,9 +69,6 @@ struct Params {
   float ln_eps;
   // ring depths and accumulator count (BN = 256 uses one 256-column accumulator and shallower rings)
   int xstages, wstages, nacc;
-  // the CTA's weight chunk ([BN][K], all K/32 stage-sized pieces) stays in shared memory for all its row tiles:
-  // the grid is a multiple of n_chunks, so tile % n_chunks is the same for every tile of a CTA
-  int w_resident;
   // row-periodic bias: + rowbias[(row % rowbias_period)][n]  (a projected positional embedding folded into the layer)
   const float* rowbias;
   int rowbias_period;
@@ -138,7 +135,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
   uint8_t* sY = sX + P.xstages * P.xstage_bytes;     // [4 warps][2][32 rows][32] fp32, swizzled
   uint8_t* sW = sY + 8 * kYWarpBytes;                // [wstages][bStage]
   // [4 warps][bias | gamma | beta][128]; wide mode: [bias | gamma | beta | gamma2 | beta2][256] shared by the CTA
-  float* sBias = reinterpret_cast<float*>(sW + (P.w_resident ? nkc : P.wstages) * bStage);
+  float* sBias = reinterpret_cast<float*>(sW + P.wstages * bStage);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + (PACK ? 8 : 4) * 384);
   uint64_t* full_x = bars;                           // TMA -> converters
   uint64_t* empty_x = full_x + kXStages;             // converters -> TMA
@@ -193,20 +190,6 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     // =================================================================== TMA producer
     if (tc::elect_one()) {  // one lane of the converged warp (elect.sync: no per-instruction elect loops)
       tc::Ring xs, rs;
-      if (P.w_resident) {  // weights of this CTA's column chunk: once, spread over the four W barriers so that no
-                           // barrier expects more than 32 KB (a single 128 KB expectation behaved erratically)
-        for (int part = 0; part < kStages; ++part) {
-          const int k0 = nkc * part / kStages, k1 = nkc * (part + 1) / kStages;
-          if (k1 > k0) {
-            tc::mbar_arrive_expect_tx(&full_w[part], (uint32_t)(k1 - k0) * bStage);
-            for (int kc = k0; kc < k1; ++kc)
-              tc::tma_load_4d(sW + kc * bStage, &wmap, &full_w[part], 0, (int)(blockIdx.x % P.n_chunks) * P.BN,
-                              kc * (kKc / 8), 0);
-          } else {
-            tc::mbar_arrive(&full_w[part]);
-          }
-        }
-      }
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int mt = tile / P.n_chunks, nc = tile % P.n_chunks;
         if (P.conv3) {
@@ -238,7 +221,6 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           else
             tc::tma_load_2d(sX + xs.stage * kAStageBytes, &xmap, &full_x[xs.stage], kc * kKc, mt * kRows);
           xs.advance(P.xstages);
-          if (P.w_resident) continue;
           LTC_TIMED_WAIT(1, tc::mbar_wait(&empty_w[rs.stage], rs.phase ^ 1));
           tc::mbar_arrive_expect_tx(&full_w[rs.stage], bStage);
           tc::tma_load_4d(sW + rs.stage * bStage, &wmap, &full_w[rs.stage], 0, nc * P.BN, kc * (kKc / 8), 0);
@@ -253,19 +235,17 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
       const uint32_t sw = tc::smem_u32(sW);
       tc::Ring as, ws;
       int t = 0;
-      if (P.w_resident)
-        for (int part = 0; part < kStages; ++part) tc::mbar_wait(&full_w[part], 0);
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
         const int acc = t % P.nacc;
         LTC_TIMED_WAIT(0, tc::mbar_wait(&acc_empty[acc], ((t / P.nacc) & 1) ^ 1));
         tc::tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)acc * 128u;
         for (int kc = 0; kc < nkc; ++kc) {
-          if (!P.w_resident) LTC_TIMED_WAIT(1, tc::mbar_wait(&full_w[ws.stage], ws.phase));
+          LTC_TIMED_WAIT(1, tc::mbar_wait(&full_w[ws.stage], ws.phase));
           LTC_TIMED_WAIT(2, tc::mbar_wait(&full_a[as.stage], as.phase));
           tc::tc_fence_after();
           const uint32_t a_hi = tmem_base + kTmemA + as.stage * 32u, a_lo = a_hi + 16u;
-          const uint32_t w_hi = sw + (P.w_resident ? (uint32_t)kc : ws.stage) * bStage, w_lo = w_hi + 4u * lboB;
+          const uint32_t w_hi = sw + ws.stage * bStage, w_lo = w_hi + 4u * lboB;
 #pragma unroll
           for (int ks = 0; ks < kKc / 16; ++ks) {
             const uint64_t db_hi = tc::smem_desc(w_hi + ks * 2 * lboB, lboB, 128);
@@ -275,10 +255,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             tc::mma_bf16_ts(d, a_hi + ks * 8u, db_hi, idesc, 1);
           }
           tc::mma_commit(&empty_a[as.stage]);
-          if (!P.w_resident) {
-            tc::mma_commit(&empty_w[ws.stage]);
-            ws.advance(P.wstages);
-          }
+          tc::mma_commit(&empty_w[ws.stage]);
+          ws.advance(P.wstages);
           as.advance(kAStagesT);
         }
         tc::mma_commit(&acc_full[acc]);
@@ -870,20 +848,6 @@ static int launch(const float* X, int64_t ldx, const void* prepared, const float
   P.nacc = P.BN > 128 ? 1 : kAcc;
   P.xstages = (P.BN > 128 || ln.conv3) ? 3 : kXStages;
   P.xstage_bytes = ln.conv3 ? kHaloStage : kAStageBytes;
-  // resident weights when the chunk fits beside at least three X stages (K * BN * 4 bytes <= 128 KB)
-  // EXPERIMENTAL, off by default (MSM_LINEAR_RESIDENT=1 enables it): 1.4-1.6x on the K = 256 projections in
-  // isolation (M307200 N256 K256: 250 -> 156 us) and every parity test passes with it, but one in three runs of
-  // the R50 bench step (CUDA-graph replay + programmatic dependent launch) hung, and the NCHW 128 KB configuration
-  // gave wrong results in about half of the runs. Not understood yet - see DESIGN.md section 4.3.
-  static const bool no_resident = getenv("MSM_LINEAR_RESIDENT") == nullptr;
-  // (token-major inputs only: with NCHW input the 128 KB configuration was flaky on B200 - wrong results or a
-  //  launch failure in ~half of the runs, clean under compute-sanitizer - and is kept on the streaming path)
-  P.w_resident = (!no_resident && !ln.wide && !ln.conv3 && !x_nchw && (int64_t)K * P.BN * 4 <= 128 * 1024) ? 1 : 0;
-  if (P.w_resident) {
-    const size_t fixed = 1024 + 8 * kYWarpBytes + (size_t)K * P.BN * 4 + (ln.pack ? 8 : 4) * 384 * sizeof(float) + 512;
-    int xs = (int)(((size_t)kMaxSmem - fixed) / kAStageBytes);
-    P.xstages = xs > kXStages ? kXStages : xs;
-  }
   P.wstages = P.BN > 128 ? 3 : kStages;
   P.n_chunks = N / P.BN;
   P.x_nchw = x_nchw; P.y_nchw = y_nchw; P.Mb = Mb; P.y = Y;
@@ -943,10 +907,9 @@ static int launch(const float* X, int64_t ldx, const void* prepared, const float
     if (rc) return rc;
   }
   const size_t smem = 1024 + (size_t)P.xstages * P.xstage_bytes + 8 * kYWarpBytes +
-                      (P.w_resident ? (size_t)K * P.BN * 4 : (size_t)P.wstages * 128 * P.BN) + (ln.pack ? 8 : 4) * 384 * sizeof(float) + 512;
+                      (size_t)P.wstages * 128 * P.BN + (ln.pack ? 8 : 4) * 384 * sizeof(float) + 512;
   const int tiles = P.m_tiles * P.n_chunks;
   int grid = tiles < num_sms() ? tiles : num_sms();
-  if (P.w_resident) grid -= grid % P.n_chunks;  // tiles >= n_chunks and n_chunks <= 64 < SMs, so grid >= n_chunks
 #ifdef MSM_EMULATE_ON_HOST
   (void)st;
   if (smem > sizeof(ltc::smem_raw)) return MSM_E_UNSUPPORTED;
