@@ -16,7 +16,7 @@ timeout 300 python bench.py --workload demo --steps 50 --warmup 5 --no-cpu-basel
 timeout 300 python bench.py --workload ucn --batch 2 --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/final_bench_ucn_b2.json 2>/dev/null
 timeout 300 python bench.py --workload crop --batch 16 --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/final_bench_crop_b16.json 2>/dev/null
 timeout 300 python bench.py --workload meanshift --steps 20 --warmup 3 > gpurun_out/final_bench_meanshift.json 2>/dev/null
-timeout 300 python bench.py --workload cluster --steps 10 --warmup 3 > gpurun_out/final_bench_cluster.json 2>/dev/null
+timeout 300 python bench.py --workload cluster --steps 20 --warmup 3 > gpurun_out/final_bench_cluster.json 2>/dev/null
 timeout 300 python bench.py --workload tail --steps 20 --warmup 3 > gpurun_out/final_bench_tail.json 2>/dev/null
 timeout 400 python bench.py --workload twostage --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/final_bench_twostage.json 2>/dev/null
 for f in gpurun_out/final_*.json; do echo "$f: $(cut -c1-260 $f)"; done
