@@ -117,10 +117,14 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 // PACK: the experimental operand-image epilogue (Params::pack*) is compiled into its own instantiation, so the
 // shipped <false> kernel is byte-for-byte the one that was validated on the B200
-template <bool PACK>
+// MODE 0: dense layer / convolution; 1: operand-image epilogue; 2: the same with the separable positional tables (its
+// own instantiation: the table prefetch registers would otherwise squeeze the plain operand-image epilogue)
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap,
                  const __grid_constant__ CUtensorMap ymap, const __grid_constant__ CUtensorMap y2map, const Params P) {
+  constexpr bool PACK = MODE != 0;
+  constexpr bool POS = MODE == 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 128B-swizzled TMA tiles need 1024-byte alignment
   // (offset arithmetic on the __shared__ array, not a round trip through uintptr_t: the latter makes every later access a
@@ -344,7 +348,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
       // constant of the tile and rides in the bias copy
       bool ty_in_bias = false;
       const float* ty_bias = nullptr;
-      if (PACK && P.pos_tx != nullptr) {
+      if (POS) {
         const int g0 = mt * kRows + q * 32, t0 = (mt % P.tiles_per_b) * kRows + q * 32;
         const bool in31 = P.x_nchw ? t0 + 31 < P.Mb : g0 + 31 < P.M;
         const int k0 = P.x_nchw ? t0 : g0 % P.pack_S;
@@ -382,7 +386,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         // per chunk, so the warp fetches them 4 rows per instruction (lane = 16-byte piece lane % 8 of row
         // 4 j + lane / 8), one chunk ahead, and turns them through its staging tile (swizzled as in store_chunk)
         // into one row per thread
-        const bool pos = P.pos_tx != nullptr;
+        constexpr bool pos = POS;
         const float* ty_row = nullptr;
         const float* tx_src[8];
         float4 stage[8];
@@ -405,96 +409,117 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
         }
-        for (int ch = egrp; ch < nchunk; ch += ngrp) {
-          if (pos) {
-            __syncwarp();  // the previous chunk's reads of the staging tile are done
+        // everything after the accumulator chunk is in registers: bias (+ tables) -> (normalise) -> split -> stores
+        auto do_chunk = [&](const uint32_t* r, int ch) {
+            if (in) {
+              // (two-wide fp32 instructions where the operands pair up: bias add, scale, the split's residual - the
+              //  epilogue of this instantiation is the kernel's bottleneck, IPC-limited)
+              float v[32];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint32_t r2 = 4u * j + ((uint32_t)lane >> 3);
-              *reinterpret_cast<float4*>(wY + r2 * 128u + ((((uint32_t)lane & 7u) ^ (r2 & 7u)) << 4)) = stage[j];
-            }
-            __syncwarp();
-            if (ch + ngrp < nchunk) {
+              for (int j = 0; j < 32; j += 2) {
+                const float2 bb = *reinterpret_cast<const float2*>(wBias + ch * 32 + j);
+                tc::f2_unpack(tc::f2_add(tc::f2_pack(__uint_as_float(r[j]), __uint_as_float(r[j + 1])),
+                                         tc::f2_pack(bb.x, bb.y)), v[j], v[j + 1]);
+              }
+              if (pos) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                stage[j] = __ldg(reinterpret_cast<const float4*>(tx_src[j] + (ch + ngrp) * 32));
+                for (int c = 0; c < 8; ++c) {
+                  const float4 b = *reinterpret_cast<const float4*>(wY + rowoff + (((uint32_t)c ^ sx) << 4));
+                  v[4 * c + 0] += b.x;
+                  v[4 * c + 1] += b.y;
+                  v[4 * c + 2] += b.z;
+                  v[4 * c + 3] += b.w;
+                }
+                if (ty_row != nullptr) {
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(ty_row + ch * 32) + c);
+                    v[4 * c + 0] += a.x;
+                    v[4 * c + 1] += a.y;
+                    v[4 * c + 2] += a.z;
+                    v[4 * c + 3] += a.w;
+                  }
+                }
+              }
+              float inv = 1.f;
+              if (P.pack_norm) {
+                float ss = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) ss = fmaf(v[j], v[j], ss);
+                inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+              }
+              const tc::f32x2 inv2 = tc::f2_pack(inv, inv);
+              uint8_t* img = P.pack_out +
+                             ((((int64_t)layer * P.pack_B + bi) * hpl + head) * P.pack_ntiles + (key >> 7)) * (4 * kOp) +
+                             (uint32_t)P.pack_slot * kOp + koff;
+#pragma unroll
+              for (int dg = 0; dg < 4; ++dg) {
+                uint4 hi, lo;
+                float w[8];
+#pragma unroll
+                for (int j = 0; j < 8; j += 2)
+                  tc::f2_unpack(tc::f2_mul(tc::f2_pack(v[8 * dg + j], v[8 * dg + j + 1]), inv2), w[j], w[j + 1]);
+                if (P.pack_f16) {
+                  tc::split2h_x2(w[0], w[1], hi.x, lo.x);
+                  tc::split2h_x2(w[2], w[3], hi.y, lo.y);
+                  tc::split2h_x2(w[4], w[5], hi.z, lo.z);
+                  tc::split2h_x2(w[6], w[7], hi.w, lo.w);
+                } else {
+                  tc::split2_x2(w[0], w[1], hi.x, lo.x);
+                  tc::split2_x2(w[2], w[3], hi.y, lo.y);
+                  tc::split2_x2(w[4], w[5], hi.z, lo.z);
+                  tc::split2_x2(w[6], w[7], hi.w, lo.w);
+                }
+                *reinterpret_cast<uint4*>(img + dg * kLbo) = hi;
+                *reinterpret_cast<uint4*>(img + kOp + dg * kLbo) = lo;
+              }
             }
-          }
-          uint32_t r[32];
-          tc::tmem_ld32(taddr + ch * 32, r);
-          tc::tmem_ld_wait();
-          if (ch == my_last) {
+            head += ngrp;
+            while (head >= hpl) {
+              head -= hpl;
+              ++layer;
+            }
+        };
+        if constexpr (!POS) {
+          // at most two chunks per group (BN <= 128): both TMEM loads are issued up front and the accumulator goes
+          // back to the MMA warp before any arithmetic or store is issued
+          const int ch0 = egrp, ch1 = egrp + ngrp;
+          uint32_t r0[32], r1[32];
+          if (ch0 < nchunk) tc::tmem_ld32(taddr + ch0 * 32, r0);
+          if (ch1 < nchunk) tc::tmem_ld32(taddr + ch1 * 32, r1);
+          if (ch0 < nchunk) {
+            tc::tmem_ld_wait();
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
+            do_chunk(r0, ch0);
           }
-          if (in) {
-            // (two-wide fp32 instructions where the operands pair up: bias add, scale, the split's residual - the
-            //  epilogue of this instantiation is the kernel's bottleneck, IPC-limited)
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const float2 bb = *reinterpret_cast<const float2*>(wBias + ch * 32 + j);
-              tc::f2_unpack(tc::f2_add(tc::f2_pack(__uint_as_float(r[j]), __uint_as_float(r[j + 1])),
-                                       tc::f2_pack(bb.x, bb.y)), v[j], v[j + 1]);
-            }
+          if (ch1 < nchunk) do_chunk(r1, ch1);
+        } else {
+          for (int ch = egrp; ch < nchunk; ch += ngrp) {
             if (pos) {
+              __syncwarp();  // the previous chunk's reads of the staging tile are done
 #pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                const float4 b = *reinterpret_cast<const float4*>(wY + rowoff + (((uint32_t)c ^ sx) << 4));
-                v[4 * c + 0] += b.x;
-                v[4 * c + 1] += b.y;
-                v[4 * c + 2] += b.z;
-                v[4 * c + 3] += b.w;
+              for (int j = 0; j < 8; ++j) {
+                const uint32_t r2 = 4u * j + ((uint32_t)lane >> 3);
+                *reinterpret_cast<float4*>(wY + r2 * 128u + ((((uint32_t)lane & 7u) ^ (r2 & 7u)) << 4)) = stage[j];
               }
-              if (ty_row != nullptr) {
+              __syncwarp();
+              if (ch + ngrp < nchunk) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                  const float4 a = __ldg(reinterpret_cast<const float4*>(ty_row + ch * 32) + c);
-                  v[4 * c + 0] += a.x;
-                  v[4 * c + 1] += a.y;
-                  v[4 * c + 2] += a.z;
-                  v[4 * c + 3] += a.w;
-                }
+                for (int j = 0; j < 8; ++j)
+                  stage[j] = __ldg(reinterpret_cast<const float4*>(tx_src[j] + (ch + ngrp) * 32));
               }
             }
-            float inv = 1.f;
-            if (P.pack_norm) {
-              float ss = 0.f;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) ss = fmaf(v[j], v[j], ss);
-              inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+            uint32_t r[32];
+            tc::tmem_ld32(taddr + ch * 32, r);
+            tc::tmem_ld_wait();
+            if (ch == my_last) {
+              tc::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
             }
-            const tc::f32x2 inv2 = tc::f2_pack(inv, inv);
-            uint8_t* img = P.pack_out +
-                           ((((int64_t)layer * P.pack_B + bi) * hpl + head) * P.pack_ntiles + (key >> 7)) * (4 * kOp) +
-                           (uint32_t)P.pack_slot * kOp + koff;
-#pragma unroll
-            for (int dg = 0; dg < 4; ++dg) {
-              uint4 hi, lo;
-              float w[8];
-#pragma unroll
-              for (int j = 0; j < 8; j += 2)
-                tc::f2_unpack(tc::f2_mul(tc::f2_pack(v[8 * dg + j], v[8 * dg + j + 1]), inv2), w[j], w[j + 1]);
-              if (P.pack_f16) {
-                tc::split2h_x2(w[0], w[1], hi.x, lo.x);
-                tc::split2h_x2(w[2], w[3], hi.y, lo.y);
-                tc::split2h_x2(w[4], w[5], hi.z, lo.z);
-                tc::split2h_x2(w[6], w[7], hi.w, lo.w);
-              } else {
-                tc::split2_x2(w[0], w[1], hi.x, lo.x);
-                tc::split2_x2(w[2], w[3], hi.y, lo.y);
-                tc::split2_x2(w[4], w[5], hi.z, lo.z);
-                tc::split2_x2(w[6], w[7], hi.w, lo.w);
-              }
-              *reinterpret_cast<uint4*>(img + dg * kLbo) = hi;
-              *reinterpret_cast<uint4*>(img + kOp + dg * kLbo) = lo;
-            }
-          }
-          head += ngrp;
-          while (head >= hpl) {
-            head -= hpl;
-            ++layer;
+            do_chunk(r, ch);
           }
         }
         continue;
@@ -845,6 +870,7 @@ static int launch(const float* X, int64_t ldx, const void* prepared, const float
   //  the fused residual + LayerNorm into two independent 32-column halves; found by the emulation's shape sweep)
   const bool row_epilogue = ln.wide || ln.gamma != nullptr;
   P.BN = row_epilogue ? N : pick_bn(N, ln.conv3 ? sms_many() : m_tiles_est);
+  if (ln.pack && P.BN > 128) return MSM_E_UNSUPPORTED;   // the operand-image epilogue reads at most two chunks per group
   P.nacc = P.BN > 128 ? 1 : kAcc;
   P.xstages = (P.BN > 128 || ln.conv3) ? 3 : kXStages;
   P.xstage_bytes = ln.conv3 ? kHaloStage : kAStageBytes;
@@ -915,24 +941,30 @@ static int launch(const float* X, int64_t ldx, const void* prepared, const float
   if (smem > sizeof(ltc::smem_raw)) return MSM_E_UNSUPPORTED;
   tc::g_tc->smem_base = reinterpret_cast<uintptr_t>(ltc::smem_raw);
   cuda_emu::launch(dim3(grid, 1), kThreads, [&] {
-    if (P.pack) linear_tc_kernel<true>(xmap, wmap, ymap, y2map, P);
-    else linear_tc_kernel<false>(xmap, wmap, ymap, y2map, P);
+    if (P.pack && P.pos_tx != nullptr) linear_tc_kernel<2>(xmap, wmap, ymap, y2map, P);
+    else if (P.pack) linear_tc_kernel<1>(xmap, wmap, ymap, y2map, P);
+    else linear_tc_kernel<0>(xmap, wmap, ymap, y2map, P);
   });
   return 0;
 #else
   // >= 116 KB of dynamic shared memory keeps it at one CTA per SM (each CTA allocates all of TMEM)
   const size_t req = smem < (size_t)(120 << 10) ? (size_t)(120 << 10) : smem;
   if (P.pack) {
-    MSM_CUDA(cudaFuncSetAttribute(linear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    MSM_CUDA(launch_pdl(linear_tc_kernel<true>, dim3(grid), dim3(kThreads), req, st, xmap, wmap, ymap, y2map, P));
+    if (P.pos_tx != nullptr) {
+      MSM_CUDA(cudaFuncSetAttribute(linear_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+      MSM_CUDA(launch_pdl(linear_tc_kernel<2>, dim3(grid), dim3(kThreads), req, st, xmap, wmap, ymap, y2map, P));
+      return check_launch("linear_tc_kernel<pack+pos>");
+    }
+    MSM_CUDA(cudaFuncSetAttribute(linear_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    MSM_CUDA(launch_pdl(linear_tc_kernel<1>, dim3(grid), dim3(kThreads), req, st, xmap, wmap, ymap, y2map, P));
     return check_launch("linear_tc_kernel<pack>");
   }
   static bool configured = false;
   if (!configured) {
-    MSM_CUDA(cudaFuncSetAttribute(linear_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    MSM_CUDA(cudaFuncSetAttribute(linear_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     configured = true;
   }
-  MSM_CUDA(launch_pdl(linear_tc_kernel<false>, dim3(grid), dim3(kThreads), req, st, xmap, wmap, ymap, y2map, P));
+  MSM_CUDA(launch_pdl(linear_tc_kernel<0>, dim3(grid), dim3(kThreads), req, st, xmap, wmap, ymap, y2map, P));
   return check_launch("linear_tc_kernel");
 #endif
 }
