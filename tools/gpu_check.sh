@@ -10,7 +10,7 @@ timeout 300 python bench.py --impl reference --steps 20 --warmup 2 > gpurun_out/
 timeout 300 python bench.py --backbone-fp32 --steps 50 --warmup 5 --no-cpu-baseline --skip-profile > gpurun_out/final_bench_r50_fp32bb.json 2>/dev/null
 timeout 300 python bench.py --workload r50-head --steps 200 --warmup 10 > gpurun_out/final_bench_r50head.json 2>/dev/null
 timeout 300 python bench.py --inflight 1 --no-cpu-baseline --skip-profile > gpurun_out/final_bench_r50_serial.json 2>/dev/null
-timeout 300 python bench.py --workload train --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/final_bench_train.json 2>/dev/null
+timeout 300 python bench.py --workload train --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/final_bench_train.json 2>/dev/null
 MSM_DECODER_BLOCK=1 timeout 300 python bench.py --workload r50-head --steps 200 --warmup 10 --no-cpu-baseline > gpurun_out/final_bench_r50head_block.json 2>/dev/null
 timeout 300 python bench.py --workload demo --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/final_bench_demo.json 2>/dev/null
 timeout 300 python bench.py --workload ucn --batch 2 --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/final_bench_ucn_b2.json 2>/dev/null
@@ -18,6 +18,6 @@ timeout 300 python bench.py --workload crop --batch 16 --steps 20 --warmup 3 --n
 timeout 300 python bench.py --workload meanshift --steps 20 --warmup 3 > gpurun_out/final_bench_meanshift.json 2>/dev/null
 timeout 300 python bench.py --workload cluster --steps 20 --warmup 3 > gpurun_out/final_bench_cluster.json 2>/dev/null
 timeout 300 python bench.py --workload tail --steps 20 --warmup 3 > gpurun_out/final_bench_tail.json 2>/dev/null
-timeout 400 python bench.py --workload twostage --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/final_bench_twostage.json 2>/dev/null
+timeout 400 python bench.py --workload twostage --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/final_bench_twostage.json 2>/dev/null
 for f in gpurun_out/final_*.json; do echo "$f: $(cut -c1-260 $f)"; done
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/final_launches.csv python bench.py --steps 1 --warmup 3 --no-graph --skip-e2e --no-cpu-baseline --skip-profile > /dev/null 2>&1; echo "launch list rc=$?"
