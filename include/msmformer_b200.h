@@ -146,6 +146,11 @@ size_t msm_linear_weight_bytes(int N, int K);
 
 int msm_linear_prepare_weight(const float* W, int64_t ldw, void* prepared, int N, int K, void* stream);
 
+/* The prepared form of the TRANSPOSE: W fp32 [R][C] -> msm_linear_weight_bytes(C, R) bytes usable as the weight of
+ * Y[M][C] = X[M][R] . (W^T)^T, i.e. the input gradient of a dense layer dX = dY . W (what torch.autograd computes for
+ * F.linear in training) without a transposed copy. R and C multiples of 32. */
+int msm_linear_prepare_weight_t(const float* W, int64_t ldw, void* prepared, int R, int C, void* stream);
+
 int msm_linear_fwd(const float* X, int64_t ldx, const void* prepared, const float* bias, float* Y, int64_t ldy,
                    int M, int N, int K, int act, void* stream);
 

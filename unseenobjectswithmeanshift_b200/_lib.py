@@ -32,6 +32,7 @@ SIGNATURES = {
     "msm_upsample_add_fwd": (_I, [_P, _P, _P, _L, _I, _I, _I, _I, _P]),
     "msm_linear_weight_bytes": (_Z, [_I, _I]),
     "msm_linear_prepare_weight": (_I, [_P, _L, _P, _I, _I, _P]),
+    "msm_linear_prepare_weight_t": (_I, [_P, _L, _P, _I, _I, _P]),
     "msm_linear_fwd": (_I, [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _P]),
     "msm_linear_ln_fwd": (_I, [_P, _L, _P, _P, _P, _L, _P, _P, _F, _P, _L, _I, _I, _I, _P]),
     "msm_linear_fused_fwd": (_I, [_P, _L, _P, _P, _P, _I, _I, _P, _L, _P, _P, _F, _I, _P, _P, _F, _P, _L, _P, _L,

@@ -779,6 +779,28 @@ __global__ void linear_prepare_weight_kernel(const float* __restrict__ W, int64_
   }
 }
 
+// The same for the TRANSPOSE of W: W fp32 [R][C] (row stride ldw) -> the prepared form of W^T [N = C][K = R], i.e.
+// element (n, k) = W[k][n]. Used by the input gradient of a dense layer (dX = dY . W = linear(dY, W^T)) so that training
+// needs no transposed copy of the weight. Threads vary n fastest: the eight strided reads of a thread are coalesced
+// across the warp.
+__global__ void linear_prepare_weight_t_kernel(const float* __restrict__ W, int64_t ldw, uint4* __restrict__ out, int N,
+                                               int K) {
+  const int64_t total = (int64_t)N * (K / 8);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i % N), kg = (int)(i / N);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __ldg(W + (int64_t)(kg * 8 + j) * ldw + n);
+    uint4 hi, lo;
+    tc::split2g(v[0], v[1], hi.x, lo.x);
+    tc::split2g(v[2], v[3], hi.y, lo.y);
+    tc::split2g(v[4], v[5], hi.z, lo.z);
+    tc::split2g(v[6], v[7], hi.w, lo.w);
+    out[i] = hi;
+    out[total + i] = lo;
+  }
+}
+
 // Column-chunk width. Large problems: the widest chunk that divides N (fewest re-reads of X). Problems that cannot
 // fill the GPU anyway (few row tiles): the narrowest chunk that still fits one wave of CTAs - more SMs share the
 // work and the per-CTA MMA / epilogue chain (the latency of these launch-bound layers) gets shorter.
@@ -817,6 +839,26 @@ extern "C" int msm_linear_prepare_weight(const float* W, int64_t ldw, void* prep
   msm::ltc::linear_prepare_weight_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       W, ldw, static_cast<uint4*>(prepared), N, K);
   return msm::check_launch("linear_prepare_weight_kernel");
+#endif
+}
+
+// prepared form of W^T from W [R][C] (see linear_prepare_weight_t_kernel): N = C outputs, K = R reduction length;
+// `prepared` holds msm_linear_weight_bytes(C, R) bytes.
+extern "C" int msm_linear_prepare_weight_t(const float* W, int64_t ldw, void* prepared, int R, int C, void* stream) {
+  MSM_REQUIRE(W && prepared, "W, prepared must be non-null");
+  MSM_REQUIRE(R > 0 && C > 0 && R % 32 == 0 && C % 32 == 0, "R and C must be positive multiples of 32");
+  MSM_REQUIRE(ldw >= C, "ldw must cover a row");
+  MSM_REQUIRE((reinterpret_cast<uintptr_t>(prepared) & 127) == 0, "prepared must be 128-byte aligned");
+  const int64_t total = (int64_t)C * (R / 8);
+  const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+#ifdef MSM_EMULATE_ON_HOST
+  cuda_emu::launch(dim3(blocks < 8 ? blocks : 8, 1), 256,
+                   [&] { msm::ltc::linear_prepare_weight_t_kernel(W, ldw, static_cast<uint4*>(prepared), C, R); });
+  return 0;
+#else
+  msm::ltc::linear_prepare_weight_t_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      W, ldw, static_cast<uint4*>(prepared), C, R);
+  return msm::check_launch("linear_prepare_weight_t_kernel");
 #endif
 }
 

@@ -537,6 +537,17 @@ def _prepare_linear_weight_once(weight):
     return buf
 
 
+def _prepare_linear_weight_t_once(weight):
+    """prepared form of weight.T (weight [N, K] -> a [K, N] layer weight) without materialising the transpose"""
+    w = _require(weight, "weight")
+    N, K = w.shape
+    L = _lib.lib()
+    buf = torch.empty(L.msm_linear_weight_bytes(K, N), device=w.device, dtype=torch.uint8)
+    check(L.msm_linear_prepare_weight_t(w.data_ptr(), w.stride(0), buf.data_ptr(), N, K, _stream()),
+          "msm_linear_prepare_weight_t")
+    return buf
+
+
 def tc_linear_enabled():
     """False when MSM_DISABLE_TC_LINEAR is set (dense layers then run in cuBLAS fp32 - a cross-check switch)."""
     return os.environ.get("MSM_DISABLE_TC_LINEAR", "") in ("", "0")
@@ -938,8 +949,8 @@ class DenseFunction(torch.autograd.Function):
         g2 = g2.contiguous()
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            wt = w.t().contiguous()                      # [K, N]: dX = dY . W = linear(dY, W^T)
-            gx = linear(g2, wt, _prepared=_prepare_linear_weight_once(wt)).reshape(x.shape)
+            # dX = dY . W = linear(dY, W^T): the kernel's weight layout is written straight from W (no transposed copy)
+            gx = linear(g2, w.t(), _prepared=_prepare_linear_weight_t_once(w)).reshape(x.shape)
         if ctx.needs_input_grad[1]:
             tf32 = torch.backends.cuda.matmul.allow_tf32
             torch.backends.cuda.matmul.allow_tf32 = False
