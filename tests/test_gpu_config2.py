@@ -569,3 +569,51 @@ def test_maxpool_and_upsample_add_vs_torch():
     cur = torch.randn(2, 64, 30, 40, generator=g).cuda()
     want = cur + F.interpolate(xt, size=(30, 40), mode="bilinear", align_corners=False)
     assert (ops.upsample_add(xt, cur) - want).abs().max().item() <= 4e-6 * want.abs().max().item()
+
+
+def test_three_graphs_in_flight_equal_serial_replay_whole_model():
+    """The timed configuration of the DEFAULT bench (bench.py --inflight 3): the whole model (cuDNN backbone, head, tail)
+    captured three times with separate static buffers and replayed round-robin on three streams. Every concurrent
+    replay must reproduce, bit for bit, what the same graph gives when it runs alone - i.e. no kernel of the path keeps
+    hidden global scratch that concurrent replays could share, and the derived-weight caches are read-only. (Against the
+    EAGER forward only the head is bit-exact, test_graph_replay_equals_eager_config2: cuDNN may choose other TF32
+    algorithms under capture.)"""
+    from unseenobjectswithmeanshift_b200 import backbones, workloads
+    from unseenobjectswithmeanshift_b200.graph import GraphedForward
+    backbones.set_tf32(True)
+    model = workloads.build_model("r50").cuda()
+    B = 4
+    inputs = [{k: v.cuda() for k, v in workloads.synthetic_images("r50", B, seed=s, pin=False).items()} for s in range(3)]
+
+    def step(inp):
+        outputs, _, padded, _ = model._head_outputs([inp])
+        label_map, f = model.label_maps([inp])
+        return {"pred_masks": outputs["pred_masks"], "pred_logits": outputs["pred_logits"], "label_map": label_map,
+                "scores": f["scores"], "pred_boxes": f["pred_boxes"]}
+
+    with torch.no_grad():
+        graphs = [GraphedForward(step, i, warmup=2) for i in inputs]
+        alone = []
+        for g in graphs:
+            g()
+            torch.cuda.synchronize()
+            alone.append({k: v.clone() for k, v in g.static_out.items()})
+        assert not torch.equal(alone[0]["pred_masks"], alone[1]["pred_masks"])
+        lanes = [torch.cuda.Stream() for _ in graphs]
+        main = torch.cuda.current_stream()
+        for rep in range(4):
+            for g in graphs:                      # poison the outputs: a replay that did not run would be caught
+                for v in g.static_out.values():
+                    v.fill_(-1)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            for g, lane in zip(graphs, lanes):
+                with torch.cuda.stream(lane):
+                    lane.wait_event(fork)
+                    g()
+            for lane in lanes:
+                main.wait_stream(lane)
+            torch.cuda.synchronize()
+            for g, want in zip(graphs, alone):
+                for k in want:
+                    assert torch.equal(g.static_out[k], want[k]), (rep, k)

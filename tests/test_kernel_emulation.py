@@ -702,8 +702,9 @@ def test_decoder_packed_kv_wiring_with_emulated_kernels(emu_chain, monkeypatch):
         monkeypatch.setenv("MSM_PACKED_KV", "1")
         got = m(x, mf)
         again = m(x, mf)   # second call reuses the cached image buffers
-    # two forwards: 3 levels x (K, V) projections each, 4 cross-attentions each; the image buffers allocated once
-    assert calls == {"alloc": 3, "project": 12, "attend": 8, "folded": 10}, calls   # the 15-key level: token-major V, no table
+    # two forwards: 3 levels x (K, V) projections each, 4 cross-attentions each; a fresh image buffer per level and
+    # forward (graphs in flight must not share one)
+    assert calls == {"alloc": 6, "project": 12, "attend": 8, "folded": 10}, calls   # the 15-key level: token-major V, no table
     for o in (got, again):
         assert (o["pred_masks"] - want["pred_masks"]).abs().max().item() < 1e-3 * want["pred_masks"].abs().max().item()
         assert (o["pred_logits"] - want["pred_logits"]).abs().max().item() < 1e-3

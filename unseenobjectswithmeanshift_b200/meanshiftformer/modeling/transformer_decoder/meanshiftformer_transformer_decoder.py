@@ -406,9 +406,8 @@ class _MeanShiftDecoderBase(nn.Module):
                 bk = cat(tag + "bk", [a.in_proj_bias[C:2 * C] for a in attn])
                 wv = cat(tag + "wv", [a.in_proj_weight[2 * C:] for a in attn])
                 bv = cat(tag + "bv", [a.in_proj_bias[2 * C:] for a in attn])
-                # one zero-initialised buffer per (level, shape), reused by every forward (static under graph replay)
-                images, per_layer = ops.cached_value(
-                    self, tag + "img_%d_%d" % (B, S_l), [wk], lambda: ops.packed_kv_alloc(len(layer_ids), B, H, S_l, dev))
+                # a fresh buffer per forward (a graph's own under capture: several graphs may be in flight at once)
+                images, per_layer = ops.packed_kv_alloc(len(layer_ids), B, H, S_l, dev)
                 proj = self.input_proj[level]
                 if (isinstance(proj, nn.Conv2d) and proj.weight.shape[1] % 32 == 0 and proj.weight.shape[1] < C
                         and os.environ.get("MSM_FOLD_V", "1") == "1"):

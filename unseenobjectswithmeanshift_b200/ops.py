@@ -201,9 +201,19 @@ class PackedKV:
 
 
 def packed_kv_alloc(layers, batch, heads, num_keys, device):
-    """Zero-initialised image buffer for `layers` decoder layers (key tails must stay zero) -> (buffer, bytes/layer)."""
+    """Image buffer for `layers` decoder layers -> (buffer, bytes/layer). A FRESH buffer per forward: under CUDA-graph
+    capture it belongs to that graph's pool, so several graphs of the same module can be in flight at once (a buffer
+    cached on the module was shared by all of them - found by test_three_graphs_in_flight_equal_serial_replay). Only the
+    last 128-key tile of every (layer, image, head) is zeroed (the projections never write the key tail; it must read
+    as zero); with num_keys % 128 == 0 nothing is."""
     per_layer = _lib.xlib().msmx_vmf_packed_bytes(batch, heads, num_keys, 32, 3)
-    return torch.zeros(layers * per_layer, dtype=torch.uint8, device=device), per_layer
+    buf = torch.empty(layers * per_layer, dtype=torch.uint8, device=device)
+    tiles = (num_keys + 127) // 128
+    if num_keys % 128 and per_layer == batch * heads * tiles * 32768:
+        buf.view(layers * batch * heads, tiles, 32768)[:, -1].zero_()
+    elif num_keys % 128:
+        buf.zero_()
+    return buf, per_layer
 
 
 def linear_packed_kv(x, weight, bias, images, batch, num_keys, channels, which, pos=None):
