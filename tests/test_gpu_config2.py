@@ -571,7 +571,8 @@ def test_maxpool_and_upsample_add_vs_torch():
     assert (ops.upsample_add(xt, cur) - want).abs().max().item() <= 4e-6 * want.abs().max().item()
 
 
-def test_three_graphs_in_flight_equal_serial_replay_whole_model():
+@pytest.mark.parametrize("kind,B", [("r50", 4), ("demo", 1)])
+def test_three_graphs_in_flight_equal_serial_replay_whole_model(kind, B):
     """The timed configuration of the DEFAULT bench (bench.py --inflight 3): the whole model (cuDNN backbone, head, tail)
     captured three times with separate static buffers and replayed round-robin on three streams. Every concurrent
     replay must reproduce, bit for bit, what the same graph gives when it runs alone - i.e. no kernel of the path keeps
@@ -581,9 +582,8 @@ def test_three_graphs_in_flight_equal_serial_replay_whole_model():
     from unseenobjectswithmeanshift_b200 import backbones, workloads
     from unseenobjectswithmeanshift_b200.graph import GraphedForward
     backbones.set_tf32(True)
-    model = workloads.build_model("r50").cuda()
-    B = 4
-    inputs = [{k: v.cuda() for k, v in workloads.synthetic_images("r50", B, seed=s, pin=False).items()} for s in range(3)]
+    model = workloads.build_model(kind).cuda()
+    inputs = [{k: v.cuda() for k, v in workloads.synthetic_images(kind, B, seed=s, pin=False).items()} for s in range(3)]
 
     def step(inp):
         outputs, _, padded, _ = model._head_outputs([inp])
