@@ -981,6 +981,14 @@ def run_forward(args, rank, local_rank, world, dev, sharding, ops, workloads):
         sharding.barrier()
         ms_dev = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
         launches = launches_per_step * args.steps
+        # the graphs in flight were fed the same batch: their results must be bit-identical (a replay racing with
+        # another one on shared state would show here; tests/test_gpu_config2.py holds the stricter form)
+        inflight_ok = None
+        if n_fl > 1:
+            inflight_ok = all(torch.equal(g.static_out[k], graphs[0].static_out[k])
+                              for g in graphs[1:] for k in graphs[0].static_out if torch.is_tensor(graphs[0].static_out[k]))
+            if not inflight_ok:
+                raise RuntimeError("graphs in flight disagree on identical inputs: concurrent replays share state")
 
         # ---------------- end to end: pinned host inputs in, results out, every step.
         # Three streams: H2D of step i+1 and D2H of step i-1 overlap the graph replay of step i (PCIe is full
@@ -1176,7 +1184,7 @@ def run_forward(args, rank, local_rank, world, dev, sharding, ops, workloads):
               "queries": 100, "decoder_layers": hk_cfg["dec_layers"],
               "launch": "eager" if args.no_graph else "one CUDA graph per step" + (
                   f", {n_fl} steps in flight on {n_fl} streams (each graph has its own static buffers)" if n_fl > 1 else ""),
-              "inflight": n_fl,
+              "inflight": n_fl, "inflight_results_identical": inflight_ok,
               "global_batch": B * world, "parallelism": f"replicas x{world} (batch-sharded, no collective)",
               "numa": args.numa,
               "l2_policy": "inputs_exceed_l2 (every decoder layer streams the mask features - 157 MB at batch 8 - and "
