@@ -15,9 +15,6 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
-    config.addinivalue_line(
-        "markers", "gpu_staged: GPU tests of kernels written after the round's GPU minutes were spent - compiled, "
-        "never yet run on hardware. Run with -m gpu_staged on the box and re-mark as gpu once green.")
 
 
 def pytest_collection_modifyitems(config, items):
@@ -25,7 +22,7 @@ def pytest_collection_modifyitems(config, items):
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:
-        if "gpu" in item.keywords or "gpu_staged" in item.keywords:
+        if "gpu" in item.keywords:
             item.add_marker(skip)
 
 

@@ -1,7 +1,7 @@
-"""STAGED GPU tests (marker ``gpu_staged``, not ``gpu``): parity tests of the training-side kernels (SURVEY.md
-section 8, row f4) that were written after this round's GPU minutes were spent. The kernels compile for sm_100a and
-their host wiring is covered on CPU (tests/test_training_wiring.py); they have NOT run on a B200 yet. First GPU call
-of the next round: ``python -m pytest tests -m gpu_staged -x -q``; re-mark as ``gpu`` once green."""
+"""GPU tests (marker ``gpu``) of the training-side kernels and of the packed-operand paths:
+attention backward, decoder gradients against the reference's autograd, whole training steps, the autograd dense
+layer, the weights-epoch cache rule. Written at the end of round 1 as staged tests; green on the B200 since round 2.
+Their host wiring is covered on CPU by tests/test_training_wiring.py."""
 import pytest
 import torch
 

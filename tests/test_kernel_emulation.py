@@ -11,14 +11,15 @@ no-swizzle shared-memory descriptors, bulk copies) and driven through their real
 * csrc/linear_tc.cu (SHIPPED dense / convolution kernel: tiled TMA with 128B swizzle, operand conversion into TMEM,
   fused epilogues, TMA stores): calibration of the tensor-map emulation, and a CPU development loop for the kernel
   that dominates the headline step;
-* csrc/vmf_attention_packed.cu (tcgen05 + bulk copies, not yet run on a GPU): judged with the calibrated emulation.
+* csrc/vmf_attention_packed.cu (tcgen05 + bulk copies; written under this emulation in round 1, parity-green on the
+  B200 since round 2).
 
 This checks indexing, tiling, masks, strides, descriptors and barrier protocols of the real source. By default
 asynchronous operations (TMA, MMA, commits) execute at issue; in LATE mode (emu_set_late) they execute as late as the
 barrier protocol allows - when a thread is about to block on the barrier they signal, the tensor pipe in issue order,
 TMA stores when their bulk group is waited for - so code that consumes an operand or a result without waiting, or
 recycles a buffer too early, computes garbage. Nothing is said about what nvcc / the hardware do with the code - that
-is the job of the staged GPU runs (tools/gpu_next.sh)."""
+is the job of the -m gpu tests."""
 import ctypes
 import os
 import shutil

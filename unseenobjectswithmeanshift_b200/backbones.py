@@ -21,6 +21,7 @@ not a tuned path on this part). The parity claims of this package concern the he
 features (the head itself never uses TF32: precision.py, split-precision tensor-core kernels).
 """
 import contextlib
+import os
 
 import torch
 import torch.nn.functional as F
@@ -39,12 +40,17 @@ def set_tf32(flag):
 
 @contextlib.contextmanager
 def _conv_math(tf32):
-    old = torch.backends.cudnn.allow_tf32
+    """cuDNN settings of the backbones' convolutions: TF32 on / off, and (MSM_CUDNN_BENCHMARK=1) cuDNN's own autotuner
+    instead of its heuristics - the choices are made in the eager warm-up calls and reused under graph capture."""
+    old, old_b = torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark
     torch.backends.cudnn.allow_tf32 = bool(tf32)
+    if os.environ.get("MSM_CUDNN_BENCHMARK", "0") == "1":
+        torch.backends.cudnn.benchmark = True
     try:
         yield
     finally:
         torch.backends.cudnn.allow_tf32 = old
+        torch.backends.cudnn.benchmark = old_b
 
 
 def _fold_bn(conv, bn):

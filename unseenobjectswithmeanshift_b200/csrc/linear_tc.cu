@@ -77,7 +77,7 @@ struct Params {
   int wide, l2norm, has_y2;
   const float *ln2_gamma, *ln2_beta;
   float ln2_eps;
-  // EXPERIMENTAL epilogue: instead of Y, write the operand images the packed attention
+  // operand-image epilogue: instead of Y, write the operand images the packed attention
   // kernel (csrc/vmf_attention_packed.cu) streams - per (layer, image, head of 32 channels, 128-key tile) the
   // [d/8][key/8][key%8][d%8] 16-bit hi / lo halves of this GEMM's output rows: K rows L2-normalised per head
   // (pack_norm) as fp16 (pack_f16) or bf16 halves at image slots 0 / 1, V rows as bf16 halves at slots 2 / 3.
@@ -1025,7 +1025,7 @@ extern "C" int msm_linear_fwd(const float* X, int64_t ldx, const void* prepared,
   return msm::ltc::launch(X, ldx, prepared, bias, Y, ldy, M, N, K, act, 0, 0, 1, M, static_cast<cudaStream_t>(stream));
 }
 
-// EXPERIMENTAL (not declared in include/msmformer_b200.h): K or V projection of the decoder's cross-attention whose
+// (msmx_: not declared in include/msmformer_b200.h, bound by ops.py) K or V projection of the decoder's cross-attention whose
 // epilogue writes the operand images of csrc/vmf_attention_packed.cu instead of fp32 rows. X [B*S][K] token-major,
 // W [N][K] with N = layers * C (the projections of all decoder layers of a level in one GEMM), heads of 32 channels.
 // packed: [layers][B][C/32][ceil(S/128)][4][8192] bytes, 128-byte aligned, ZERO-initialised once by the caller (key

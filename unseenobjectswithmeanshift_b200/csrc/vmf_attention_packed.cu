@@ -1,8 +1,8 @@
-// EXPERIMENTAL - compiled into libmsmformer_b200.so, but its entry points carry the prefix msmx_, are NOT part of
-// include/msmformer_b200.h and nothing calls them unless MSM_PACKED_KV=1 is set (ops.py / the decoder mirror). It
-// compiles for sm_100a and has NOT yet run on a GPU; its logic is checked by executing this source on CPU threads under
-// the emulation that is calibrated on the shipped kernels (tests/emu, tests/test_kernel_emulation.py). Parity + timing
-// against the shipped kernels on the B200 box: tools/dev_vmf_packed.py.
+// The default attention / mean-shift-iteration kernel since round 2 (MSM_PACKED_KV=0 / MSM_PACKED_MS=0 select the
+// fp32-row kernel of vmf_attention_tc.cu). Its entry points carry the prefix msmx_ and are bound by ops.py only (not
+// part of include/msmformer_b200.h: the operand-image format is an internal contract between this file and
+// linear_tc_kernel's operand-image epilogue). Parity on the B200: tests/test_gpu_training.py, tests/test_gpu_config2.py;
+// ncu: profiles/r02_ncu_attention.md; the same source also runs on CPU threads under tests/emu.
 //
 // vMF attention / mean-shift iteration on PRE-PACKED operands. In vmf_attention_tc.cu
 // eight loader warps read the fp32 rows of K and V, L2-normalise K, split both into 16-bit hi/lo halves and store the

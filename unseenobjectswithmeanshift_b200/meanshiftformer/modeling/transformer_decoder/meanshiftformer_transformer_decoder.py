@@ -392,8 +392,8 @@ class _MeanShiftDecoderBase(nn.Module):
         layers_of = [[i for i in range(self.num_layers) if i % L == l] for l in range(L)]
         kv = {}
 
-        # EXPERIMENTAL, opt-in (MSM_PACKED_KV=1; not yet run on a GPU): K / V projections write the attention kernel's
-        # operand images instead of fp32 rows
+        # default (MSM_PACKED_KV=0 switches it off): K / V projections write the attention kernel's operand images
+        # instead of fp32 rows (DESIGN.md sections 4.2, 4.3)
         packed_kv = ops.packed_kv_enabled() and not train and hd == 32
 
         def project_kv(level, layer_ids):
@@ -499,7 +499,7 @@ class _MeanShiftDecoderBase(nn.Module):
         out = self.query_feat.weight.unsqueeze(0).expand(B, -1, -1).contiguous()
         need_mask = not self.disable_attention_mask
 
-        # EXPERIMENTAL, opt-in (MSM_L2_PERSIST=1; not yet run on a GPU): the mask features are re-read by every
+        # opt-in (MSM_L2_PERSIST=1; measured slower on the B200): the mask features are re-read by every
         # prediction head call below - keep as much of them as the device allows resident in L2
         l2_window = ops.l2_persist_enabled() and not train
         if l2_window:

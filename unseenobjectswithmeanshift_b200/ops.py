@@ -183,9 +183,9 @@ def vmf_attention_autograd(q, k, v, *, blocked_bits=None, row_open=None, add_mas
 
 
 # ----------------------------------------------------------------------------------------------
-# EXPERIMENTAL packed-operand cross-attention (csrc/vmf_attention_packed.cu, linear_tc_kernel<PACK>): K / V
-# projections write 16-bit operand images instead of fp32 rows, the attention kernel streams them with bulk copies.
-# Opt-in (MSM_PACKED_KV=1); not yet run on a GPU - see DESIGN.md section 8, item 1.
+# Packed-operand cross-attention (csrc/vmf_attention_packed.cu, linear_tc_kernel<1|2>; the default since round 2): K / V
+# projections write 16-bit operand images instead of fp32 rows, the attention kernel streams them with bulk copies
+# (DESIGN.md sections 4.2, 4.3). Entry points carry the prefix msmx_ (not in the public header).
 # ----------------------------------------------------------------------------------------------
 def packed_kv_enabled():
     """Default ON since round 2 (B200: parity 2e-6 against the fp32-row kernel; UCN head step 16.1 -> 13.8 ms, R50-level
@@ -307,7 +307,7 @@ def vmf_attention_packed(q, kv, *, blocked_bits=None, row_open=None, kappa=KAPPA
 
 def vmf_attention_small(q, k, v, *, blocked_bits=None, row_open=None, kappa=KAPPA, normalize_q=True, normalize_k=True,
                         out=None, return_den=False, save_norm=False):
-    """EXPERIMENTAL (not yet run on a GPU): vmf_attention through the single-launch CUDA-core kernel for short key
+    """Opt-in (measured slower in the R50 step): vmf_attention through the single-launch CUDA-core kernel for short key
     sequences (csrc/vmf_attention_small.cu; hd 32, Nq <= 128, Ns <= 1024). MSM_SMALL_ATTN=1 makes msm_vmf_attention_fwd
     pick it by itself; this front-end calls it directly."""
     q, q_sb, q_sh, q_sl = _bhld(q, "q")
@@ -337,7 +337,7 @@ def l2_persist_enabled():
 
 
 def l2_persist(tensor=None):
-    """EXPERIMENTAL, opt-in (MSM_L2_PERSIST=1; not yet run on a GPU): L2 persisting access window on `tensor` for the
+    """Opt-in (MSM_L2_PERSIST=1; measured slower): L2 persisting access window on `tensor` for the
     kernels launched on the current stream from now on; None clears it."""
     if tensor is None:
         rc = _lib.xlib().msmx_set_l2_persisting_window(None, 0, _stream())
@@ -1115,8 +1115,8 @@ def mean_shift_hill_climb(X, Z, kappa, max_iters=10):
         raise ValueError(f"X {tuple(X.shape)} / Z {tuple(Z.shape)} mismatch")
     out = torch.empty_like(Zb)
     if os.environ.get("MSM_PACKED_MS", "1") == "1" and d in (32, 64) and m <= 128 and int(max_iters) >= 1:
-        # EXPERIMENTAL, opt-in (not yet run on a GPU): X is split into 16-bit operand images ONCE per call instead of in
-        # every iteration (csrc/vmf_attention_packed.cu)
+        # default: X is split into 16-bit operand images ONCE per call instead of in every iteration, and the whole
+        # climb is one persistent cooperative kernel (csrc/mean_shift_persistent.cu)
         X_ = _lib.xlib()
         packed = torch.empty(X_.msmx_mean_shift_packed_bytes(B, n, d), device=Xb.device, dtype=torch.uint8)
         check(X_.msmx_mean_shift_pack(Xb.data_ptr(), packed.data_ptr(), B, n, d, _stream()), "msmx_mean_shift_pack")
