@@ -313,3 +313,22 @@ def test_dense_function_gradients_vs_fp64(M, N, K, relu, bias):
     assert rel(wc.grad, wd.grad) < 1e-5
     if bias:
         assert rel(bc.grad, bd.grad) < 1e-5
+
+
+@pytest.mark.parametrize("B,Q,C,H,W", [(2, 100, 256, 24, 32), (1, 10, 32, 12, 20), (2, 37, 64, 9, 12), (1, 128, 160, 8, 8)])
+def test_mask_logits_function_gradients_vs_fp64(B, Q, C, H, W):
+    """MaskLogitsFunction: forward = mask kernel; g_feat through the same kernel with queries and channels swapped
+    (zero-padded to 32 queries, 128 channels per launch), g_embed through cuBLAS fp32 - against fp64 autograd of the
+    einsum."""
+    from unseenobjectswithmeanshift_b200 import ops
+    g = torch.Generator().manual_seed(B + Q + C)
+    e, f = torch.randn(B, Q, C, generator=g), torch.randn(B, C, H, W, generator=g)
+    go = torch.randn(B, Q, H, W, generator=g)
+    ed, fd = e.double().requires_grad_(True), f.double().requires_grad_(True)
+    torch.einsum("bqc,bchw->bqhw", ed, fd).backward(go.double())
+    ec, fc = e.cuda().requires_grad_(True), f.cuda().requires_grad_(True)
+    y = ops.mask_logits_autograd(ec, fc)
+    y.backward(go.cuda())
+    rel = lambda a, r: (a.detach().cpu().double() - r).abs().max().item() / max(r.abs().max().item(), 1e-12)  # noqa: E731
+    assert rel(fc.grad, fd.grad) < 1e-5
+    assert rel(ec.grad, ed.grad) < 1e-5

@@ -383,9 +383,11 @@ def mask_logits(mask_embed, mask_features, out=None):
 
 
 class MaskLogitsFunction(torch.autograd.Function):
-    """Differentiable mask head einsum (meanshiftformer_transformer_decoder.py:668): forward = msm_mask_logits;
-    the backward is two plain batched GEMMs, left to cuBLAS (fp32, TF32 off):
-    g_embed = g_masks . feat^T over the pixels, g_feat = embed^T . g_masks."""
+    """Differentiable mask head einsum (meanshiftformer_transformer_decoder.py:668): forward = msm_mask_logits.
+    Backward: g_feat[b,c,p] = sum_q embed[b,q,c] g[b,q,p] is the SAME contraction with the roles of queries and
+    channels swapped, so it runs in the mask kernel too (embed^T as the "embedding", the query-padded gradient as the
+    "features"; 128 channels per launch); g_embed = g . feat^T is a 19200-long reduction over the pixels and stays in
+    cuBLAS (fp32, TF32 off) until the GEMM kernels have a split-K form."""
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
@@ -408,7 +410,17 @@ class MaskLogitsFunction(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 ge = torch.bmm(g, f.reshape(B, C, -1).transpose(1, 2))
             if ctx.needs_input_grad[1]:
-                gf = torch.bmm(e.transpose(1, 2), g).reshape(f.shape)
+                if os.environ.get("MSM_TRAIN_TC_MASK", "1") == "1" and f.dim() == 4 and Q <= 256:
+                    Qp = (Q + 31) // 32 * 32
+                    gp = g.reshape(B, Q, *f.shape[-2:])
+                    et = e.transpose(1, 2)                                   # [B, C, Q]
+                    if Qp != Q:                                              # zero query rows / columns: K of the GEMM
+                        gp = torch.nn.functional.pad(gp, (0, 0, 0, 0, 0, Qp - Q))
+                        et = torch.nn.functional.pad(et, (0, Qp - Q))
+                    parts = [mask_logits(et[:, c0:c0 + 128].contiguous(), gp) for c0 in range(0, C, 128)]
+                    gf = parts[0] if len(parts) == 1 else torch.cat(parts, 1)
+                else:
+                    gf = torch.bmm(e.transpose(1, 2), g).reshape(f.shape)
         finally:
             torch.backends.cuda.matmul.allow_tf32 = tf32
         return ge, gf
