@@ -14,6 +14,7 @@ import torch.distributed as dist
 import torch.nn.functional as F
 from torch import nn
 
+from .matcher import pad_targets
 from .point_features import PointSource, point_sample, uncertain_point_coords
 
 
@@ -51,12 +52,23 @@ class SetCriterion(nn.Module):
     # ---------------------------------------------------------------------------------------------- pieces
     @staticmethod
     def _permutation_idx(indices, which):
-        """(batch index, prediction / target index) of every matched pair (criterion.py:191-201)."""
         batch_idx = torch.cat([torch.full_like(pair[which], b) for b, pair in enumerate(indices)])
         return batch_idx, torch.cat([pair[which] for pair in indices])
 
+    @staticmethod
+    def _device_indices(layer_indices, device):
+        """indices[layer][image] = (pred idx, target idx) on the host -> ONE device tensor [3, L, N]: image, query and
+        target (column of the padded targets) of every matched pair. N = matched pairs per layer - the same for every
+        layer, since every target of an image is matched exactly once. The reference moves one small index tensor per
+        image, layer and use; the step is host-bound, so this is one copy per step."""
+        rows = []
+        for indices in layer_indices:
+            b = torch.cat([torch.full_like(i, k) for k, (i, _) in enumerate(indices)])
+            rows.append(torch.stack([b, torch.cat([i for i, _ in indices]), torch.cat([j for _, j in indices])]))
+        return torch.stack(rows, 1).to(device)    # [3, L, N]
+
     def loss_labels(self, outputs, targets, indices, num_masks):
-        """criterion.py:124-141: weighted cross entropy, unmatched queries -> the no-object class."""
+        """criterion.py:124-141: weighted cross entropy, unmatched queries -> the no-object class (one layer)."""
         src_logits = outputs["pred_logits"].float()
         dev = src_logits.device
         b_idx, s_idx = self._permutation_idx(indices, 0)
@@ -65,19 +77,28 @@ class SetCriterion(nn.Module):
         target_classes[b_idx.to(dev), s_idx.to(dev)] = matched.to(dev)
         return {"loss_ce": F.cross_entropy(src_logits.transpose(1, 2), target_classes, self.empty_weight)}
 
-    def _mask_losses(self, layer_outputs, targets, layer_indices, num_masks, point_source):
+    def _label_losses(self, layer_outputs, labels_pad, idx):
+        """loss_labels for all layers at once -> [L]. F.cross_entropy's weighted mean is sum(w_t * nll) / sum(w_t) over
+        the layer's B * Q queries; computed per layer from one unreduced call."""
+        logits = torch.stack([o["pred_logits"].float() for o in layer_outputs])          # [L,B,Q,K+1]
+        L, B, Q, K1 = logits.shape
+        target = torch.full((L, B, Q), self.num_classes, dtype=torch.int64, device=logits.device)
+        if idx.shape[2]:
+            l_idx = torch.arange(L, device=logits.device)[:, None].expand(L, idx.shape[2])
+            target[l_idx, idx[0], idx[1]] = labels_pad[idx[0], idx[2]]
+        weight = self.empty_weight.to(logits.dtype)
+        nll = F.cross_entropy(logits.reshape(L * B * Q, K1), target.reshape(-1), weight, reduction="none").view(L, B * Q)
+        return nll.sum(1) / weight[target].view(L, B * Q).sum(1)
+
+    def _mask_losses(self, layer_outputs, masks_pad, idx, num_masks, point_source):
         """criterion.py:143-189 for all layers: {'loss_mask': [layers], 'loss_dice': [layers]}."""
         dev = layer_outputs[0]["pred_masks"].device
         nl = len(layer_outputs)
-        src, tgt = [], []
-        for out, indices in zip(layer_outputs, layer_indices):
-            b_idx, s_idx = self._permutation_idx(indices, 0)
-            src.append(out["pred_masks"][b_idx.to(dev), s_idx.to(dev)])
-            tgt.append(torch.cat([t["masks"][J.to(t["masks"].device)] for t, (_, J) in zip(targets, indices)]))
-        N = src[0].shape[0]
+        N = idx.shape[2]
         if N == 0:  # no ground truth in the whole batch: the mask losses vanish but stay attached to the graph
             zero = torch.stack([o["pred_masks"].sum() * 0.0 for o in layer_outputs])
             return {"loss_mask": zero, "loss_dice": zero.clone()}
+        src = [out["pred_masks"][idx[0, l], idx[1, l]] for l, out in enumerate(layer_outputs)]   # L x [N,h,w]
         P = self.num_points
         num_sampled = int(P * self.oversample_ratio)
         num_random = P - int(self.importance_sample_ratio * P)
@@ -87,8 +108,9 @@ class SetCriterion(nn.Module):
         with torch.no_grad():
             coords = uncertain_point_coords(src_all.float(), candidates.flatten(0, 1), fill.flatten(0, 1), P,
                                             self.importance_sample_ratio)
-            labels = torch.stack([point_sample(t[:, None].to(device=dev, dtype=src_all.dtype), c, align_corners=False)
-                                  .squeeze(1) for t, c in zip(tgt, coords.unflatten(0, (nl, N)))])  # [layers, N, P]
+            tgt_all = masks_pad[idx[0].reshape(-1), idx[2].reshape(-1)]                            # [layers * N, H, W]
+            labels = point_sample(tgt_all[:, None].to(src_all.dtype), coords, align_corners=False).squeeze(1)
+            labels = labels.unflatten(0, (nl, N))                                                  # [layers, N, P]
         logits = point_sample(src_all, coords, align_corners=False).squeeze(1).unflatten(0, (nl, N))
         return {"loss_mask": sigmoid_ce_loss(logits, labels, num_masks), "loss_dice": dice_loss(logits, labels, num_masks)}
 
@@ -100,11 +122,14 @@ class SetCriterion(nn.Module):
         src = point_source if point_source is not None else PointSource()
         layer_outputs = [{k: v for k, v in outputs.items() if k != "aux_outputs"}] + list(outputs.get("aux_outputs", []))
         suffix = [""] + [f"_{i}" for i in range(len(layer_outputs) - 1)]
-        layer_indices = self.matcher.match_layers(layer_outputs, targets, src)
+        dev = layer_outputs[0]["pred_logits"].device
+        padded = pad_targets(targets, dev)          # labels [B,Tmax], masks [B,Tmax,H,W]: shared with the matcher
+        layer_indices = self.matcher.match_layers(layer_outputs, targets, src, padded=padded)
+        idx = self._device_indices(layer_indices, dev)
 
         num_masks = float(sum(int(t["labels"].shape[0]) for t in targets))
         if dist.is_available() and dist.is_initialized():  # average over the ranks, criterion.py:225-227
-            n = torch.as_tensor([num_masks], dtype=torch.float, device=layer_outputs[0]["pred_logits"].device)
+            n = torch.as_tensor([num_masks], dtype=torch.float, device=dev)
             dist.all_reduce(n)
             num_masks = torch.clamp(n / dist.get_world_size(), min=1)[0]
         else:
@@ -113,13 +138,15 @@ class SetCriterion(nn.Module):
         unknown = [l for l in self.losses if l not in ("labels", "masks")]
         assert not unknown, f"do you really want to compute {unknown[0]} loss?"
         losses = {}
-        mask_losses = None
+        mask_losses = label_losses = None
         if "masks" in self.losses:
-            mask_losses = self._mask_losses(layer_outputs, targets, layer_indices, num_masks, src)
-        for l, (out, indices, sfx) in enumerate(zip(layer_outputs, layer_indices, suffix)):
+            mask_losses = self._mask_losses(layer_outputs, padded[1], idx, num_masks, src)
+        if "labels" in self.losses:
+            label_losses = self._label_losses(layer_outputs, padded[0], idx)
+        for l, sfx in enumerate(suffix):
             for name in self.losses:  # the reference's key order: per layer, in the order of self.losses
                 if name == "labels":
-                    losses["loss_ce" + sfx] = self.loss_labels(out, targets, indices, num_masks)["loss_ce"]
+                    losses["loss_ce" + sfx] = label_losses[l]
                 else:
                     losses["loss_mask" + sfx] = mask_losses["loss_mask"][l]
                     losses["loss_dice" + sfx] = mask_losses["loss_dice"][l]

@@ -63,24 +63,48 @@ class HungarianMatcher(nn.Module):
         return self.cost_mask * cost_mask + self.cost_class * cost_class + self.cost_dice * cost_dice
 
     @torch.no_grad()
-    def match_layers(self, layer_outputs, targets, point_source=None):
+    def cost_matrices_layers(self, layer_outputs, labels, masks, coords):
+        """All decoder layers of a step at once (the training step is host-bound: ~15 launches per layer become ~25
+        per step). layer_outputs: L dicts; labels [B,Tmax]; masks [B,Tmax,H,W] padded ground truth; coords [L,B,P,2]
+        -> cost [L,B,Q,Tmax], the same arithmetic as ``cost_matrices`` per layer."""
+        L, B, P = coords.shape[:3]
+        T = labels.shape[1]
+        prob = torch.stack([o["pred_logits"].float() for o in layer_outputs]).softmax(-1)      # [L,B,Q,K+1]
+        Q = prob.shape[2]
+        cost_class = -torch.gather(prob, 3, labels[None, :, None, :].expand(L, B, Q, T))
+        # ground truth at every layer's points with ONE sampling call: the points of all layers side by side per image
+        tgt_points = point_sample(masks, coords.permute(1, 0, 2, 3).reshape(B, L * P, 2), align_corners=False)
+        tgt_points = tgt_points.view(B, T, L, P).permute(2, 0, 1, 3).reshape(L * B, T, P)      # [L*B,Tmax,P]
+        out_pts = torch.stack([point_sample(o["pred_masks"].float(), coords[l], align_corners=False)
+                               for l, o in enumerate(layer_outputs)]).flatten(0, 1)           # [L*B,Q,P]
+        tgt_t = tgt_points.transpose(1, 2)
+        pos = F.binary_cross_entropy_with_logits(out_pts, torch.ones_like(out_pts), reduction="none")
+        neg = F.binary_cross_entropy_with_logits(out_pts, torch.zeros_like(out_pts), reduction="none")
+        cost_mask = (torch.bmm(pos, tgt_t) + torch.bmm(neg, 1 - tgt_t)) / P
+        sig = out_pts.sigmoid()
+        numerator = 2 * torch.bmm(sig, tgt_t)
+        denominator = sig.sum(-1)[:, :, None] + tgt_points.sum(-1)[:, None, :]
+        cost_dice = 1 - (numerator + 1) / (denominator + 1)
+        cost = self.cost_mask * cost_mask + self.cost_dice * cost_dice
+        return cost.view(L, B, Q, T) + self.cost_class * cost_class
+
+    @torch.no_grad()
+    def match_layers(self, layer_outputs, targets, point_source=None, padded=None):
         """Matching for every decoder layer of a step with one device->host copy.
         layer_outputs: list of {'pred_logits','pred_masks'}; returns indices[layer][image] = (pred idx, target idx)
-        int64 CPU tensors, as the reference's forward returns per layer."""
+        int64 CPU tensors, as the reference's forward returns per layer. ``padded``: pad_targets(targets) when the
+        caller already has it."""
         dev = layer_outputs[0]["pred_logits"].device
         B = len(targets)
-        labels, masks, counts = pad_targets(targets, dev)
+        labels, masks, counts = padded if padded is not None else pad_targets(targets, dev)
         src = point_source if point_source is not None else PointSource()
         tf32 = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = False  # near-tied costs must not flip with the GEMM mode
         try:
             coords = src.matcher_points(len(layer_outputs), B, self.num_points, dev)  # [layers,B,P,2]
-            costs = []
             with torch.autocast(device_type=dev.type, enabled=False):  # fp32 costs, as matcher.py:134-141
-                for l, out in enumerate(layer_outputs):
-                    tgt_points = point_sample(masks, coords[l], align_corners=False)  # [B,Tmax,P]
-                    costs.append(self.cost_matrices(out, labels, tgt_points, coords[l]))
-            host = torch.stack(costs).cpu()  # the step's only synchronisation of the matcher
+                costs = self.cost_matrices_layers(layer_outputs, labels, masks, coords)
+            host = costs.cpu()  # the step's only synchronisation of the matcher
         finally:
             torch.backends.cuda.matmul.allow_tf32 = tf32
         result = []
